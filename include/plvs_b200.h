@@ -1,0 +1,268 @@
+/* plvs_b200.h -- C ABI of libplvs_b200.so: the B200-native (sm_100a) replacement for the
+ * per-frame data-parallel hot path of PLVS (luigifreda/plvs):
+ *
+ *   ORB extraction      PLVS2::ORBextractor::operator()            src/ORBextractor.cc:1245
+ *   Hamming matching    PLVS2::ORBmatcher::SearchByProjection x2   src/ORBmatcher.cc:71, :1774
+ *                       PLVS2::ORBmatcher::SearchForTriangulation  src/ORBmatcher.cc:999
+ *                       PLVS2::ORBmatcher::DescriptorDistance      src/ORBmatcher.cc:2198
+ *   TSDF integration    chisel::Chisel::IntegrateDepthScan[ColorWithOneCameraModelBGR]
+ *                       Thirdparty/open_chisel/include/open_chisel/Chisel.h:68, :198
+ *                       (reached through chisel_server::ChiselServer::IntegrateLastDepthImage,
+ *                        Thirdparty/chisel_server/src/ChiselServer.cpp:632)
+ *
+ * The reference has no FFI layer: its boundary is the three C++ class surfaces above.  The
+ * header-only shims in shim/ keep those signatures and forward to this ABI.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 (PLVS_OK) or a negative
+ * PLVS_E* code and never aborts; all buffers are caller-owned unless stated; every handle owns a
+ * CUDA stream + workspace and calls on DISTINCT handles are thread-safe (the reference runs
+ * left/right extractors and Tracking/LocalMapping matchers on concurrent threads).  There is no
+ * CPU fallback: without a CUDA device every create() fails with PLVS_ENODEV.
+ */
+#ifndef PLVS_B200_H_
+#define PLVS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLVS_OK 0
+#define PLVS_EINVAL (-1)   /* bad argument */
+#define PLVS_ENODEV (-2)   /* no CUDA device / CUDA runtime failure */
+#define PLVS_ENOMEM (-3)   /* allocation failed */
+#define PLVS_ECAP (-4)     /* caller capacity too small (n_out holds the required size) */
+#define PLVS_ESTATE (-5)   /* missing camera/pose (mirrors ChiselServer gotInfo/gotPose guards) */
+
+#define PLVS_MAX_LEVELS 16
+
+const char* plvs_version(void);
+const char* plvs_last_error(void);          /* thread-local description of the last failure */
+int plvs_device_count(void);
+/* pinned host memory for the e2e path (cudaHostAlloc / cudaFreeHost) */
+int plvs_host_alloc(void** p, size_t bytes);
+int plvs_host_free(void* p);
+
+/* ------------------------------------------------------------------------------------------ */
+/* ORB extraction -- replaces PLVS2::ORBextractor (include/ORBextractor.h:59-170)              */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct plvs_orb plvs_orb;
+
+/* ctor arguments of ORBextractor (include/ORBextractor.h:78) */
+typedef struct {
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+} plvs_orb_params;
+
+/* binary layout of cv::KeyPoint (28 bytes): the shim passes std::vector<cv::KeyPoint>::data() */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} plvs_keypoint;
+
+int plvs_orb_create(const plvs_orb_params* p, int device, plvs_orb** out);
+void plvs_orb_destroy(plvs_orb* h);
+
+/* ORBextractor::operator() (src/ORBextractor.cc:1245-1389).  gray: CV_8UC1, `stride` bytes per row;
+ * on_device!=0 => gray is a device pointer.  (lap0,lap1) = vLappingArea.  kps/desc have room for
+ * `cap` keypoints (desc is cap x 32 bytes).  *n_out = number of keypoints, *mono_index_out = the
+ * value operator() returns.  Returns PLVS_ECAP (with *n_out = needed) if cap is too small. */
+int plvs_orb_extract(plvs_orb* h, const uint8_t* gray, int w, int h_, int stride, int on_device,
+                     int lap0, int lap1, plvs_keypoint* kps, uint8_t* desc, int cap,
+                     int* n_out, int* mono_index_out);
+
+/* Same, for `batch` independent frames of equal size in one pass (frame b starts at
+ * gray + b*frame_stride; outputs at kps + b*cap, desc + b*cap*32, n_out[b], mono_index_out[b]). */
+int plvs_orb_extract_batch(plvs_orb* h, int batch, const uint8_t* gray, int w, int h_, int stride,
+                           size_t frame_stride, int on_device, int lap0, int lap1,
+                           plvs_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_index_out);
+
+/* getters of ORBextractor (include/ORBextractor.h:90-113); arrays hold nlevels entries */
+int plvs_orb_tables(const plvs_orb* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                    int32_t* features_per_level);
+
+/* mvImagePyramid / mvImagePyramidFiltered (include/ORBextractor.h:125-127) of frame `frame` of the
+ * last batch: device pointer + geometry, and a host download for callers that read the pyramid
+ * (Frame::ComputeStereoMatches, src/Frame.cc:1789). */
+int plvs_orb_pyramid_level(const plvs_orb* h, int frame, int level, int blurred,
+                           const uint8_t** dptr, int* w, int* h_, int* pitch);
+int plvs_orb_download_level(plvs_orb* h, int frame, int level, int blurred, uint8_t* host, int host_stride);
+
+/* Device-resident result of frame `frame` of the last batch (valid until the next extract on this
+ * handle; only when no keypoint fell in the lapping area): lets the matcher run without a
+ * device->host->device round trip. */
+typedef struct {
+    int32_t n;
+    const plvs_keypoint* keys;   /* device */
+    const uint8_t* desc;         /* device, n x 32 */
+} plvs_orb_device_view;
+int plvs_orb_device_result(const plvs_orb* h, int frame, plvs_orb_device_view* out);
+
+/* Inspection: FAST candidates of (frame, level) of the last batch in the order they enter
+ * DistributeOctTree (vToDistributeKeys, src/ORBextractor.cc:867-998): x, y in level pixel
+ * coordinates (border included) and the FAST score.  Used by the stage-parity tests. */
+int plvs_orb_candidates(const plvs_orb* h, int frame, int level, int32_t* x, int32_t* y, int32_t* score,
+                        int cap, int* n_out);
+
+/* statistics of the last batch (for bench/roofline accounting) */
+typedef struct {
+    int64_t pyramid_pixels;      /* P of SURVEY.md §8: sum over levels of w*h, one frame */
+    int64_t candidates;          /* FAST candidates after per-cell NMS, summed over the batch */
+    int64_t keypoints;           /* keypoints, summed over the batch */
+    int32_t kernel_launches;     /* kernels launched by the last extract call */
+} plvs_orb_stats;
+int plvs_orb_last_stats(const plvs_orb* h, plvs_orb_stats* out);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Matching -- replaces the three ORBmatcher entry points + DescriptorDistance                 */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct plvs_match plvs_match;
+
+/* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2198-2225): host helper, 32-byte descriptors */
+int plvs_hamming256(const uint8_t* a, const uint8_t* b);
+
+/* Flat view of the Frame / KeyFrame members the matchers read (RGB-D / rectified stereo: Nleft==-1).
+ * Pointers are host pointers unless on_device != 0. */
+typedef struct {
+    int32_t n;                    /* Frame::N */
+    const plvs_keypoint* keys;    /* Frame::mvKeysUn */
+    const uint8_t* desc;          /* Frame::mDescriptors, n x 32 */
+    const float* uright;          /* Frame::mvuRight (NULL => all -1) */
+    float min_x, min_y, max_x, max_y;     /* mnMinX.. (src/Frame.cc:1749-1778) */
+    float grid_inv_w, grid_inv_h;         /* mfGridElementWidthInv / HeightInv (src/Frame.cc:448-449) */
+    float scale_factors[PLVS_MAX_LEVELS]; /* Frame::mvScaleFactors */
+    float level_sigma2[PLVS_MAX_LEVELS];  /* KeyFrame::mvLevelSigma2 (triangulation only) */
+    int32_t nlevels;
+    float bf;                             /* Frame::mbf */
+    int32_t on_device;
+} plvs_frame_view;
+
+#define PLVS_Q_OBS_POSITIVE 1u   /* MapPoint::Observations() > 0 */
+
+/* one in-view local map point, as Frame::isInFrustum leaves it (src/Frame.cc:1006-1014) */
+typedef struct {
+    float proj_x, proj_y, proj_xr;   /* mTrackProjX / Y / XR */
+    float track_depth;               /* mTrackDepth */
+    float view_cos;                  /* mTrackViewCos */
+    int32_t level;                   /* mnTrackScaleLevel */
+    uint32_t flags;                  /* PLVS_Q_* */
+    uint8_t desc[32];                /* MapPoint::GetDescriptor() */
+} plvs_mp_query;
+
+/* one last-frame feature with a non-outlier MapPoint, already projected by the caller with the
+ * reference's own expressions (src/ORBmatcher.cc:1804-1827): uv = project(Tcw*Xw), invz = 1/zc */
+typedef struct {
+    float u, v, invz;
+    int32_t last_octave;
+    float angle;                     /* last-frame keypoint angle (rotation histogram) */
+    uint32_t flags;                  /* PLVS_Q_* */
+    uint8_t desc[32];
+} plvs_last_query;
+
+int plvs_match_create(int device, plvs_match** out);
+void plvs_match_destroy(plvs_match* h);
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPointPtr>&, th, bFarPoints, thFarPoints)
+ * (src/ORBmatcher.cc:71-244), left/RGB-D branch.  Queries are the map points with mbTrackInView,
+ * in mvpLocalMapPoints order.  claimed_in[i]!=0 <=> F.mvpMapPoints[i] && Observations()>0 at call
+ * time (NULL => none).  assign[i] (host, n entries) receives the index of the query written into
+ * F.mvpMapPoints[i] by this call, or -1.  *nmatches = the function's return value. */
+int plvs_match_projection_map(plvs_match* h, const plvs_frame_view* F, const plvs_mp_query* q, int nq,
+                              float th, float nn_ratio, int far_points, float th_far,
+                              const uint8_t* claimed_in, int32_t* assign, int* nmatches);
+
+/* ORBmatcher::SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) (src/ORBmatcher.cc:1774-1993).
+ * forward/backward = bForward/bBackward (:1793-1794) computed by the caller from tlc and mb.
+ * assign[i] = query index finally held by CurrentFrame.mvpMapPoints[i] through this call, or -1. */
+int plvs_match_projection_last(plvs_match* h, const plvs_frame_view* cur, const plvs_last_query* q, int nq,
+                               float th, int forward, int backward, int check_orientation,
+                               const uint8_t* claimed_in, int32_t* assign, int* nmatches);
+
+/* DBoW2::FeatureVector flattened: sorted node ids, CSR offsets, feature indices (ascending per node) */
+typedef struct {
+    int32_t n_nodes;
+    const uint32_t* node_ids;     /* n_nodes, strictly increasing */
+    const int32_t* offsets;       /* n_nodes + 1 */
+    const int32_t* features;      /* offsets[n_nodes] */
+} plvs_featvec;
+
+/* ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:999-1242), monocular-camera branch
+ * (mpCamera2 == NULL).  has_mp*[i]!=0 <=> KeyFrame::GetMapPoint(i) != NULL.  F12 = the matrix
+ * Pinhole::epipolarConstrain builds (src/CameraModels/Pinhole.cpp:125-131), row-major; ep = epipole
+ * in KF2 (:1010-1011).  match12[i] (n1 entries) = matched index in KF2 or -1 (== vMatches12). */
+int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const plvs_frame_view* kf2,
+                             const plvs_featvec* fv1, const plvs_featvec* fv2,
+                             const uint8_t* has_mp1, const uint8_t* has_mp2,
+                             const float F12[9], const float ep[2],
+                             int only_stereo, int coarse, int check_orientation,
+                             int32_t* match12, int* nmatches);
+
+/* ------------------------------------------------------------------------------------------ */
+/* TSDF -- replaces chisel_server::ChiselServer's integrate path (ChiselServer.h:81-322)       */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct plvs_tsdf plvs_tsdf;
+
+/* chisel_server::ChiselServerParams (Thirdparty/chisel_server/src/ChiselServer.cpp:44-69) as
+ * PointCloudMapChisel fills it (src/PointCloudMapChisel.cc:46-61); chunk size is 16^3. */
+typedef struct {
+    float voxel_resolution;
+    float trunc_quad, trunc_linear, trunc_const, trunc_scale;
+    float weight;
+    int32_t use_carving;
+    float carving_dist;
+    int32_t use_color;
+    float near_plane, far_plane;
+    int32_t max_blocks;          /* capacity of the device block pool (48 KiB per block) */
+} plvs_tsdf_params;
+
+void plvs_tsdf_default_params(plvs_tsdf_params* p);   /* the defaults of ChiselServerParams() */
+int plvs_tsdf_create(const plvs_tsdf_params* p, int device, plvs_tsdf** out);
+void plvs_tsdf_destroy(plvs_tsdf* h);
+int plvs_tsdf_reset(plvs_tsdf* h);                                  /* ChiselServer::Reset */
+/* ChiselServer::SetDepthCameraInfo (ChiselServer.h:284) */
+int plvs_tsdf_set_camera(plvs_tsdf* h, double fx, double fy, double cx, double cy, int w, int h_);
+
+#define PLVS_TSDF_SCAN 0         /* Chisel::IntegrateDepthScan (Chisel.h:68): w=1, Carve() */
+#define PLVS_TSDF_SCAN_COLOR 1   /* IntegrateDepthScanColorWithOneCameraModelBGR (Chisel.h:198) */
+
+/* SetDepthPose + SetDepthImage[MemorySharing] (+SetColorImage) + IntegrateLastDepthImage(false).
+ * depth: float32 metres, w*h, row stride = w elements (DepthImage.h:54-74).  bgr: w*h*nch bytes
+ * with `bgr_step` bytes per row (NULL unless mode==PLVS_TSDF_SCAN_COLOR).  Twc: 3x4 row-major
+ * (rotation | translation), camera-to-world (src/PointCloudMapChisel.cc:147-154). */
+int plvs_tsdf_integrate_depth(plvs_tsdf* h, const float* depth, int w, int h_,
+                              const uint8_t* bgr, int bgr_step, int nch,
+                              const float Twc[12], int mode, int on_device);
+
+typedef struct {
+    int32_t n_blocks;            /* live chunks in the map */
+    int32_t n_range;             /* chunks enumerated by GetChunkIDsIntersecting for the last scan */
+    int32_t n_candidates;        /* chunks the voxel kernel actually visited */
+    int32_t n_updated;           /* chunks with >=1 voxel update (needsUpdate==true) */
+    int32_t n_new;               /* chunks created and kept */
+    int32_t n_collected;         /* chunks created then garbage-collected */
+    int32_t kernel_launches;
+    int32_t pool_exhausted;      /* !=0 if max_blocks was hit (results incomplete) */
+} plvs_tsdf_stats;
+int plvs_tsdf_last_stats(const plvs_tsdf* h, plvs_tsdf_stats* out);
+
+/* read-out for tests/merge: chunk ids (x,y,z), per-voxel sdf / weight (4096 each, voxel index
+ * (z*16+y)*16+x as Chunk.h:90-93) and rgba (r,g,b,colour-weight).  Any output may be NULL. */
+int plvs_tsdf_download_blocks(plvs_tsdf* h, int32_t* keys, float* sdf, float* weight, uint8_t* rgba,
+                              int cap, int* n_out);
+
+/* Multi-GPU block merge (not in the reference).  export: pack every live block as
+ * (key, w*sdf, w) into caller device buffers; merge: fold packed blocks into this map with the
+ * commutative weighted sum.  The exchange itself (all-to-all by key owner) is NCCL plumbing done
+ * by the caller (plvs_b200/parallel.py uses torch.distributed). */
+int plvs_tsdf_export_packed(plvs_tsdf* h, int32_t* d_keys, float* d_wsdf, float* d_w, int cap, int* n_out);
+int plvs_tsdf_merge_packed(plvs_tsdf* h, const int32_t* d_keys, const float* d_wsdf, const float* d_w, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLVS_B200_H_ */

@@ -1,0 +1,57 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of oracle/match_oracle.cpp (sequential CPU restatement
+of the three ORBmatcher searches).  Takes the same flat views as plvs_b200.matcher."""
+import ctypes as C
+import numpy as np
+
+from .orb import lib
+from plvs_b200 import _lib as _abi
+from plvs_b200.matcher import MP_QUERY, LAST_QUERY, featvec_struct
+
+
+def _setup():
+    l = lib()
+    l.orc_search_by_projection_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    l.orc_search_by_projection_last.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    l.orc_search_for_triangulation.argtypes = [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    l.orc_hamming256.argtypes = [C.c_void_p, C.c_void_p]
+    return l
+
+
+def hamming256(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return _setup().orc_hamming256(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+
+
+def search_by_projection_map(F, queries, th, nn_ratio, far_points=False, th_far=50.0, claimed=None):
+    l = _setup()
+    q = np.ascontiguousarray(queries, MP_QUERY)
+    v = F.view()
+    assign = np.full(max(F.n, 1), -1, np.int32)
+    cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+    n = l.orc_search_by_projection_map(C.byref(v), q.ctypes.data_as(C.c_void_p), len(q), th, nn_ratio, int(far_points), th_far,
+                                       cl.ctypes.data_as(C.c_void_p) if cl is not None else None, assign.ctypes.data_as(C.c_void_p))
+    return n, assign[:F.n]
+
+
+def search_by_projection_last(Cur, queries, th, forward=False, backward=False, check_ori=True, claimed=None):
+    l = _setup()
+    q = np.ascontiguousarray(queries, LAST_QUERY)
+    v = Cur.view()
+    assign = np.full(max(Cur.n, 1), -1, np.int32)
+    cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+    n = l.orc_search_by_projection_last(C.byref(v), q.ctypes.data_as(C.c_void_p), len(q), th, int(forward), int(backward), int(check_ori),
+                                        cl.ctypes.data_as(C.c_void_p) if cl is not None else None, assign.ctypes.data_as(C.c_void_p))
+    return n, assign[:Cur.n]
+
+
+def search_for_triangulation(K1, K2, fv1, fv2, has1, has2, F12, ep, only_stereo=False, coarse=False, check_ori=True):
+    l = _setup()
+    v1, v2 = K1.view(), K2.view()
+    s1, s2 = featvec_struct(fv1), featvec_struct(fv2)
+    h1 = np.ascontiguousarray(has1, np.uint8); h2 = np.ascontiguousarray(has2, np.uint8)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9); e = np.ascontiguousarray(ep, np.float32)
+    m12 = np.full(max(K1.n, 1), -1, np.int32)
+    n = l.orc_search_for_triangulation(C.byref(v1), C.byref(v2), C.byref(s1), C.byref(s2), h1.ctypes.data_as(C.c_void_p),
+                                       h2.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p),
+                                       int(only_stereo), int(coarse), int(check_ori), m12.ctypes.data_as(C.c_void_p))
+    return n, m12[:K1.n]

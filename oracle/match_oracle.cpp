@@ -1,0 +1,282 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle for the matching rows of SURVEY.md §8a (a11-a16).
+//
+// Restates, on flat arrays, PLVS2::ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2198-2225),
+// Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (src/Frame.cc:716-746,1305-1316,
+// 1231-1303), ORBmatcher::SearchByProjection(Frame&, vector<MapPointPtr>&,...) (src/ORBmatcher.cc:71-157,
+// RGB-D / Nleft==-1 branch), SearchByProjection(Cur, Last,...) (:1774-1993), SearchForTriangulation
+// (:999-1242, single-camera branch), ComputeThreeMaxima (:2123-2164) and the line test of
+// Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:133-147).  Sequential, claim-mutating,
+// exactly in the reference's iteration order.  The structs below mirror include/plvs_b200.h so the
+// tests hand the same buffers to the oracle and to the CUDA path.
+//
+// Parity status: the reference has no test vectors for these functions ("parity unpinned");
+// the Hamming kernel is pinned against numpy's bit counting in tests/test_oracle_match.py.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+const int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 12;
+const int GRID_COLS = 64, GRID_ROWS = 48;
+
+struct KeyPoint { float x, y, size, angle, response; int32_t octave, class_id; };
+
+struct FrameView {
+    int32_t n;
+    const KeyPoint* keys;
+    const uint8_t* desc;
+    const float* uright;
+    float min_x, min_y, max_x, max_y;
+    float grid_inv_w, grid_inv_h;
+    float scale_factors[16];
+    float level_sigma2[16];
+    int32_t nlevels;
+    float bf;
+    int32_t on_device;
+};
+
+struct MpQuery { float proj_x, proj_y, proj_xr, track_depth, view_cos; int32_t level; uint32_t flags; uint8_t desc[32]; };
+struct LastQuery { float u, v, invz; int32_t last_octave; float angle; uint32_t flags; uint8_t desc[32]; };
+struct FeatVec { int32_t n_nodes; const uint32_t* node_ids; const int32_t* offsets; const int32_t* features; };
+
+int hamming(const uint8_t* a, const uint8_t* b)
+{
+    uint64_t pa[4], pb[4];
+    std::memcpy(pa, a, 32); std::memcpy(pb, b, 32);
+    int d = 0;
+    for (int i = 0; i < 4; ++i) d += __builtin_popcountll(pa[i] ^ pb[i]);
+    return d;
+}
+
+struct Grid {
+    std::vector<int> cell[GRID_COLS][GRID_ROWS];
+    const FrameView* f;
+    explicit Grid(const FrameView* fv) : f(fv)
+    {
+        for (int i = 0; i < f->n; ++i) {
+            const KeyPoint& kp = f->keys[i];
+            int px = (int)std::round((kp.x - f->min_x) * f->grid_inv_w);
+            int py = (int)std::round((kp.y - f->min_y) * f->grid_inv_h);
+            if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+            cell[px][py].push_back(i);
+        }
+    }
+    void in_area(float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& out) const
+    {
+        out.clear();
+        const int minCX = std::max(0, (int)std::floor((x - f->min_x - r) * f->grid_inv_w));
+        if (minCX >= GRID_COLS) return;
+        const int maxCX = std::min(GRID_COLS - 1, (int)std::ceil((x - f->min_x + r) * f->grid_inv_w));
+        if (maxCX < 0) return;
+        const int minCY = std::max(0, (int)std::floor((y - f->min_y - r) * f->grid_inv_h));
+        if (minCY >= GRID_ROWS) return;
+        const int maxCY = std::min(GRID_ROWS - 1, (int)std::ceil((y - f->min_y + r) * f->grid_inv_h));
+        if (maxCY < 0) return;
+        const bool check = (minLevel > 0) || (maxLevel >= 0);
+        for (int ix = minCX; ix <= maxCX; ++ix)
+            for (int iy = minCY; iy <= maxCY; ++iy)
+                for (int id : cell[ix][iy]) {
+                    const KeyPoint& kp = f->keys[id];
+                    if (check) {
+                        if (kp.octave < minLevel) continue;
+                        if (kp.octave > maxLevel) continue;      // NB: applied even when maxLevel == -1 (src/Frame.cc:1283-1286)
+                    }
+                    const float dx = kp.x - x, dy = kp.y - y;
+                    if (std::fabs(dx) < r && std::fabs(dy) < r) out.push_back(id);
+                }
+    }
+};
+
+void three_maxima(const std::vector<int>* histo, int L, int& i1, int& i2, int& i3)
+{
+    int m1 = 0, m2 = 0, m3 = 0;
+    for (int i = 0; i < L; ++i) {
+        const int s = (int)histo[i].size();
+        if (s > m1) { m3 = m2; m2 = m1; m1 = s; i3 = i2; i2 = i1; i1 = i; }
+        else if (s > m2) { m3 = m2; m2 = s; i3 = i2; i2 = i; }
+        else if (s > m3) { m3 = s; i3 = i; }
+    }
+    if (m2 < 0.1f * (float)m1) { i2 = -1; i3 = -1; }
+    else if (m3 < 0.1f * (float)m1) { i3 = -1; }
+}
+
+int rot_bin(float a1, float a2)
+{
+    const float factor = HISTO_LENGTH / 360.0f;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)std::round(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_hamming256(const uint8_t* a, const uint8_t* b) { return hamming(a, b); }
+
+// holder[i]: -1 free, -2 pre-claimed by a map point with Observations()>0, >=0 index of the query
+// that wrote it during this call.  assign[i] = holder[i] >= 0 ? holder[i] : -1.
+int orc_search_by_projection_map(const FrameView* F, const MpQuery* q, int nq, float th, float nn_ratio,
+                                 int far_points, float th_far, const uint8_t* claimed_in, int32_t* assign)
+{
+    Grid grid(F);
+    std::vector<int> holder(F->n, -1);
+    if (claimed_in) for (int i = 0; i < F->n; ++i) if (claimed_in[i]) holder[i] = -2;
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    std::vector<int> cand;
+    for (int iq = 0; iq < nq; ++iq) {
+        const MpQuery& m = q[iq];
+        if (far_points && m.track_depth > th_far) continue;
+        const int lvl = m.level;
+        float r = m.view_cos > 0.998 ? 2.5f : 4.0f;
+        if (bFactor) r *= th;
+        grid.in_area(m.proj_x, m.proj_y, r * F->scale_factors[lvl], lvl - 1, lvl, cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : cand) {
+            if (holder[idx] == -2) continue;
+            if (holder[idx] >= 0 && (q[holder[idx]].flags & 1u)) continue;      // Observations()>0
+            if (F->uright && F->uright[idx] > 0) {
+                const float er = std::fabs(m.proj_xr - F->uright[idx]);
+                if (er > r * F->scale_factors[lvl]) continue;
+            }
+            const int dist = hamming(m.desc, F->desc + (size_t)idx * 32);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
+                bestLevel = F->keys[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = F->keys[idx].octave; bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nn_ratio * bestDist2) continue;
+            if (bestLevel != bestLevel2 || bestDist <= nn_ratio * bestDist2) { holder[bestIdx] = iq; ++nmatches; }
+        }
+    }
+    for (int i = 0; i < F->n; ++i) assign[i] = holder[i] >= 0 ? holder[i] : -1;
+    return nmatches;
+}
+
+int orc_search_by_projection_last(const FrameView* C, const LastQuery* q, int nq, float th, int forward, int backward,
+                                  int check_ori, const uint8_t* claimed_in, int32_t* assign)
+{
+    Grid grid(C);
+    std::vector<int> holder(C->n, -1);
+    if (claimed_in) for (int i = 0; i < C->n; ++i) if (claimed_in[i]) holder[i] = -2;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = 0;
+    std::vector<int> cand;
+    for (int iq = 0; iq < nq; ++iq) {
+        const LastQuery& m = q[iq];
+        if (m.invz < 0) continue;
+        if (m.u < C->min_x || m.u > C->max_x) continue;
+        if (m.v < C->min_y || m.v > C->max_y) continue;
+        const int oct = m.last_octave;
+        const float radius = th * C->scale_factors[oct];
+        if (forward) grid.in_area(m.u, m.v, radius, oct, -1, cand);
+        else if (backward) grid.in_area(m.u, m.v, radius, 0, oct, cand);
+        else grid.in_area(m.u, m.v, radius, oct - 1, oct + 1, cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : cand) {
+            if (holder[i2] == -2) continue;
+            if (holder[i2] >= 0 && (q[holder[i2]].flags & 1u)) continue;
+            if (C->uright && C->uright[i2] > 0) {
+                const float ur = m.u - C->bf * m.invz;
+                const float er = std::fabs(ur - C->uright[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = hamming(m.desc, C->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            holder[bestIdx2] = iq;
+            ++nmatches;
+            if (check_ori) rotHist[rot_bin(m.angle, C->keys[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (check_ori) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i)
+            if (i != i1 && i != i2 && i != i3)
+                for (int idx : rotHist[i]) { holder[idx] = -1; --nmatches; }
+    }
+    for (int i = 0; i < C->n; ++i) assign[i] = holder[i] >= 0 ? holder[i] : -1;
+    return nmatches;
+}
+
+int orc_search_for_triangulation(const FrameView* K1, const FrameView* K2, const FeatVec* fv1, const FeatVec* fv2,
+                                 const uint8_t* has_mp1, const uint8_t* has_mp2, const float* F12, const float* ep,
+                                 int only_stereo, int coarse, int check_ori, int32_t* match12)
+{
+    int nmatches = 0;
+    for (int i = 0; i < K1->n; ++i) match12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int a = 0, b = 0;
+    while (a < fv1->n_nodes && b < fv2->n_nodes) {
+        if (fv1->node_ids[a] == fv2->node_ids[b]) {
+            for (int i1 = fv1->offsets[a]; i1 < fv1->offsets[a + 1]; ++i1) {
+                const int idx1 = fv1->features[i1];
+                if (has_mp1[idx1]) continue;
+                const bool stereo1 = K1->uright && K1->uright[idx1] >= 0;
+                if (only_stereo && !stereo1) continue;
+                const KeyPoint& kp1 = K1->keys[idx1];
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int i2 = fv2->offsets[b]; i2 < fv2->offsets[b + 1]; ++i2) {
+                    const int idx2 = fv2->features[i2];
+                    if (has_mp2[idx2]) continue;
+                    const bool stereo2 = K2->uright && K2->uright[idx2] >= 0;
+                    if (only_stereo && !stereo2) continue;
+                    const int dist = hamming(K1->desc + (size_t)idx1 * 32, K2->desc + (size_t)idx2 * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const KeyPoint& kp2 = K2->keys[idx2];
+                    if (!stereo1 && !stereo2) {
+                        const float dx = ep[0] - kp2.x, dy = ep[1] - kp2.y;
+                        if (dx * dx + dy * dy < 100 * K2->scale_factors[kp2.octave]) continue;
+                    }
+                    bool ok = coarse != 0;
+                    if (!ok) {   // Pinhole::epipolarConstrain line test with the caller's F12
+                        const float la = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+                        const float lb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+                        const float lc = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+                        const float num = la * kp2.x + lb * kp2.y + lc;
+                        const float den = la * la + lb * lb;
+                        if (den != 0) {
+                            const float dsqr = num * num / den;
+                            ok = dsqr < 3.84 * K2->level_sigma2[kp2.octave];
+                        }
+                    }
+                    if (ok) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    match12[idx1] = bestIdx2;
+                    ++nmatches;
+                    if (check_ori) rotHist[rot_bin(kp1.angle, K2->keys[bestIdx2].angle)].push_back(idx1);
+                }
+            }
+            ++a; ++b;
+        } else if (fv1->node_ids[a] < fv2->node_ids[b]) {
+            while (a < fv1->n_nodes && fv1->node_ids[a] < fv2->node_ids[b]) ++a;     // lower_bound
+        } else {
+            while (b < fv2->n_nodes && fv2->node_ids[b] < fv1->node_ids[a]) ++b;
+        }
+    }
+    if (check_ori) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int idx : rotHist[i]) { match12[idx] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
+}  // extern "C"

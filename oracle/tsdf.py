@@ -1,0 +1,56 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of oracle/tsdf_oracle.cpp (brute-force CPU restatement of
+Chisel's depth-scan integration).  Same parameter struct as the product (plvs_b200._lib.TsdfParams)."""
+import ctypes as C
+import numpy as np
+
+from .orb import lib
+from plvs_b200 import _lib as _abi
+
+
+class Map:
+    def __init__(self, params, threads=1):
+        self._l = lib()
+        self._l.orc_tsdf_create.restype = C.c_void_p
+        self._l.orc_tsdf_create.argtypes = [C.c_void_p, C.c_int]
+        self._l.orc_tsdf_destroy.argtypes = [C.c_void_p]
+        self._l.orc_tsdf_set_camera.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+        self._l.orc_tsdf_integrate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        self._l.orc_tsdf_stats.argtypes = [C.c_void_p, C.c_void_p]
+        self._l.orc_tsdf_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        self._l.orc_tsdf_reset.argtypes = [C.c_void_p]
+        self.params = params
+        self._h = self._l.orc_tsdf_create(C.byref(params), threads)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.orc_tsdf_destroy(self._h)
+            self._h = None
+
+    def set_camera(self, fx, fy, cx, cy, w, h):
+        self._l.orc_tsdf_set_camera(self._h, fx, fy, cx, cy, w, h)
+
+    def integrate(self, depth, Twc, bgr=None):
+        depth = np.ascontiguousarray(depth, np.float32)
+        T = np.ascontiguousarray(Twc, np.float32).reshape(12)
+        h, w = depth.shape
+        mode = 1 if bgr is not None else 0
+        if bgr is not None:
+            bgr = np.ascontiguousarray(bgr, np.uint8)
+        rc = self._l.orc_tsdf_integrate(self._h, depth.ctypes.data_as(C.c_void_p), w, h,
+                                        bgr.ctypes.data_as(C.c_void_p) if bgr is not None else None,
+                                        bgr.shape[2] if bgr is not None else 0, T.ctypes.data_as(C.c_void_p), mode)
+        assert rc == 0, rc
+
+    def stats(self):
+        s = np.zeros(5, np.int32)
+        self._l.orc_tsdf_stats(self._h, s.ctypes.data_as(C.c_void_p))
+        return dict(n_blocks=int(s[0]), n_range=int(s[1]), n_updated=int(s[2]), n_new=int(s[3]), n_collected=int(s[4]))
+
+    def download(self):
+        n = self._l.orc_tsdf_download(self._h, None, None, None, None, 0)
+        keys = np.zeros((n, 3), np.int32); sdf = np.zeros((n, 4096), np.float32); w = np.zeros((n, 4096), np.float32)
+        rgba = np.zeros((n, 4096, 4), np.uint8)
+        if n:
+            self._l.orc_tsdf_download(self._h, keys.ctypes.data_as(C.c_void_p), sdf.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p),
+                                      rgba.ctypes.data_as(C.c_void_p), n)
+        return keys, sdf, w, rgba

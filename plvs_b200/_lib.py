@@ -1,0 +1,128 @@
+"""ctypes binding of libplvs_b200.so (the C ABI of include/plvs_b200.h).
+
+The library is built in-tree by plvs_b200/csrc/build.py.  There is no CPU fallback: if the
+shared object is missing or no CUDA device is present the product fails loudly.
+"""
+import ctypes as C
+import os
+import pathlib
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libplvs_b200.so"
+
+
+class PlvsError(RuntimeError):
+    pass
+
+
+class Keypoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32), ("class_id", C.c_int32)]
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
+
+
+class OrbStats(C.Structure):
+    _fields_ = [("pyramid_pixels", C.c_int64), ("candidates", C.c_int64), ("keypoints", C.c_int64),
+                ("kernel_launches", C.c_int32)]
+
+
+class OrbDeviceView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys", C.c_void_p), ("desc", C.c_void_p)]
+
+
+MAX_LEVELS = 16
+
+
+class FrameView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys", C.c_void_p), ("desc", C.c_void_p), ("uright", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("grid_inv_w", C.c_float), ("grid_inv_h", C.c_float),
+                ("scale_factors", C.c_float * MAX_LEVELS), ("level_sigma2", C.c_float * MAX_LEVELS),
+                ("nlevels", C.c_int32), ("bf", C.c_float), ("on_device", C.c_int32)]
+
+
+class FeatVec(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("node_ids", C.c_void_p), ("offsets", C.c_void_p), ("features", C.c_void_p)]
+
+
+class TsdfParams(C.Structure):
+    _fields_ = [("voxel_resolution", C.c_float), ("trunc_quad", C.c_float), ("trunc_linear", C.c_float),
+                ("trunc_const", C.c_float), ("trunc_scale", C.c_float), ("weight", C.c_float),
+                ("use_carving", C.c_int32), ("carving_dist", C.c_float), ("use_color", C.c_int32),
+                ("near_plane", C.c_float), ("far_plane", C.c_float), ("max_blocks", C.c_int32)]
+
+
+class TsdfStats(C.Structure):
+    _fields_ = [("n_blocks", C.c_int32), ("n_range", C.c_int32), ("n_candidates", C.c_int32), ("n_updated", C.c_int32),
+                ("n_new", C.c_int32), ("n_collected", C.c_int32), ("kernel_launches", C.c_int32), ("pool_exhausted", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared object (raises PlvsError with the build hint if it is absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise PlvsError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(the product has no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    lib.plvs_version.restype = C.c_char_p
+    lib.plvs_last_error.restype = C.c_char_p
+    lib.plvs_orb_destroy.restype = None
+    lib.plvs_orb_destroy.argtypes = [C.c_void_p]
+    lib.plvs_orb_create.argtypes = [C.POINTER(OrbParams), C.c_int, C.POINTER(C.c_void_p)]
+    lib.plvs_orb_extract_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int,
+                                           C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.plvs_orb_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.plvs_orb_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    lib.plvs_orb_pyramid_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.plvs_orb_download_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.plvs_orb_device_result.argtypes = [C.c_void_p, C.c_int, C.POINTER(OrbDeviceView)]
+    lib.plvs_orb_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.plvs_orb_last_stats.argtypes = [C.c_void_p, C.POINTER(OrbStats)]
+    lib.plvs_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    lib.plvs_host_free.argtypes = [C.c_void_p]
+    lib.plvs_hamming256.argtypes = [C.c_void_p, C.c_void_p]
+    lib.plvs_match_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.plvs_match_projection_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,
+                                              C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    lib.plvs_match_projection_last.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    lib.plvs_match_triangulation.argtypes = [C.c_void_p] * 9 + [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    lib.plvs_tsdf_default_params.restype = None
+    lib.plvs_tsdf_default_params.argtypes = [C.POINTER(TsdfParams)]
+    lib.plvs_tsdf_create.argtypes = [C.POINTER(TsdfParams), C.c_int, C.POINTER(C.c_void_p)]
+    lib.plvs_tsdf_reset.argtypes = [C.c_void_p]
+    lib.plvs_tsdf_set_camera.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.plvs_tsdf_integrate_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    lib.plvs_tsdf_last_stats.argtypes = [C.c_void_p, C.POINTER(TsdfStats)]
+    lib.plvs_tsdf_download_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.plvs_tsdf_export_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.plvs_tsdf_merge_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    for name in ("plvs_match_destroy", "plvs_tsdf_destroy"):
+        if hasattr(lib, name):
+            getattr(lib, name).restype = None
+            getattr(lib, name).argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise PlvsError(f"{what} failed with code {rc}: {load().plvs_last_error().decode()}")
+
+
+def exported_symbols():
+    """Names declared in include/plvs_b200.h (used by the CPU-side ABI test)."""
+    import re
+    hdr = (_HERE.parent / "include" / "plvs_b200.h").read_text()
+    return sorted(set(re.findall(r"\b(plvs_[a-z0-9_]+)\s*\(", hdr)))

@@ -1,0 +1,69 @@
+// Shared host/device helpers for libplvs_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "../../include/plvs_b200.h"
+
+namespace plvs {
+
+void set_error(const char* fmt, ...);
+
+#define PLVS_CUDA(expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ::plvs::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return PLVS_ENODEV;                                                               \
+        }                                                                                     \
+    } while (0)
+
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// Device memory that is released with the owning handle.
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count) {
+        if (count <= n && p) return PLVS_OK;
+        release();
+        if (cudaMalloc((void**)&p, count * sizeof(T)) != cudaSuccess) {
+            p = nullptr; n = 0;
+            set_error("cudaMalloc of %zu bytes failed", count * sizeof(T));
+            return PLVS_ENOMEM;
+        }
+        n = count;
+        return PLVS_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+// Pinned, device-mapped host memory: kernels read/write it directly over PCIe (posted writes),
+// so small control/result records need no separate memcpy launches.
+template <typename T>
+struct PinBuf {
+    T* h = nullptr;   // host view
+    T* d = nullptr;   // device view of the same memory
+    size_t n = 0;
+    int alloc(size_t count) {
+        if (count <= n && h) return PLVS_OK;
+        release();
+        if (cudaHostAlloc((void**)&h, count * sizeof(T), cudaHostAllocMapped) != cudaSuccess) {
+            h = nullptr; n = 0;
+            set_error("cudaHostAlloc of %zu bytes failed", count * sizeof(T));
+            return PLVS_ENOMEM;
+        }
+        if (cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess) { cudaFreeHost(h); h = nullptr; return PLVS_ENODEV; }
+        n = count;
+        return PLVS_OK;
+    }
+    void release() { if (h) cudaFreeHost(h); h = nullptr; d = nullptr; n = 0; }
+    ~PinBuf() { release(); }
+};
+
+}  // namespace plvs

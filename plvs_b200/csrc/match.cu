@@ -1,0 +1,631 @@
+// 256-bit Hamming matching: the three ORBmatcher entry points of the hot path behind the C ABI.
+// reference: src/ORBmatcher.cc:71-157 (SearchByProjection, frame <- local map points),
+//            :1774-1993 (SearchByProjection, current <- last frame), :999-1242 (SearchForTriangulation),
+//            :2198-2225 (DescriptorDistance), src/Frame.cc:716-746,1231-1316 (feature grid).
+//
+// Design (B200): descriptors are 32-byte rows read as 2 x uint4; distances are 8 x __popc; one
+// warp serves one query and keeps the reference's candidate order with ballot compaction.  The
+// reference's searches are *sequential*: a map point claims a keypoint and later points skip it.
+// Instead of serialising, phase A computes every query's ordered candidate list (all the Hamming
+// work, fully parallel) and phase B resolves the claims by fixed-point iteration: each round every
+// query re-selects assuming the claims of LOWER-numbered queries from the previous round.  After
+// round k the first k queries are final (their inputs no longer change), so the fixed point is
+// exactly the sequential result; real frames converge in 2-4 rounds.
+#include <mutex>
+#include <vector>
+#include "common.cuh"
+
+using namespace plvs;
+
+namespace {
+
+constexpr int GRID_COLS = 64, GRID_ROWS = 48, GRID_CELLS = GRID_COLS * GRID_ROWS;
+constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO = 12;
+
+struct GridParams { float min_x, min_y, max_x, max_y, inv_w, inv_h; };
+
+// candidate packing: idx:16 | dist:9 | level:5
+__device__ __forceinline__ uint32_t pack_cand(int idx, int dist, int level) { return (uint32_t)idx | ((uint32_t)dist << 16) | ((uint32_t)level << 25); }
+__device__ __forceinline__ int cand_idx(uint32_t c) { return c & 0xffff; }
+__device__ __forceinline__ int cand_dist(uint32_t c) { return (c >> 16) & 0x1ff; }
+__device__ __forceinline__ int cand_level(uint32_t c) { return c >> 25; }
+
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint8_t* __restrict__ b)
+{
+    const uint4 b0 = *reinterpret_cast<const uint4*>(b), b1 = *reinterpret_cast<const uint4*>(b + 16);
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Frame::AssignFeaturesToGrid (src/Frame.cc:716-746): 64x48 cells, cell = round((p-min)*inv),
+// indices appended in keypoint order.  One CTA: histogram, scan, then ONE warp scatters in index
+// order (match_any ranks equal cells inside a 32-keypoint step) so every cell list is ascending.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_build_grid(const plvs_keypoint* __restrict__ keys, int n, GridParams gp, int* __restrict__ cell_start /*GRID_CELLS+1*/,
+             int* __restrict__ sorted /*n*/, int* __restrict__ kp_cell /*n*/)
+{
+    __shared__ int s_cnt[GRID_CELLS + 1];
+    __shared__ int s_part[32];
+    const int tid = threadIdx.x;
+    for (int i = tid; i <= GRID_CELLS; i += 1024) s_cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const int px = (int)roundf((keys[i].x - gp.min_x) * gp.inv_w);
+        const int py = (int)roundf((keys[i].y - gp.min_y) * gp.inv_h);
+        int c = -1;
+        if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) { c = px * GRID_ROWS + py; atomicAdd(&s_cnt[c], 1); }
+        kp_cell[i] = c;
+    }
+    __syncthreads();
+    // exclusive scan of 3072 counts: 3 per thread
+    int v[3], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { v[k] = s_cnt[tid * 3 + k]; sum += v[k]; }
+    int x = sum;
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_part[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int p = s_part[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, p, o); if (lane >= o) p += y; }
+        s_part[lane] = p;
+    }
+    __syncthreads();
+    int base = (wid ? s_part[wid - 1] : 0) + x - sum;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { s_cnt[tid * 3 + k] = base; base += v[k]; }
+    if (tid == 1023) s_cnt[GRID_CELLS] = base;
+    __syncthreads();
+    for (int i = tid; i <= GRID_CELLS; i += 1024) cell_start[i] = s_cnt[i];
+    __syncthreads();
+    if (wid == 0) {      // stable scatter; s_cnt doubles as the per-cell cursor
+        for (int b = 0; b < n; b += 32) {
+            const int i = b + lane;
+            const int c = i < n ? kp_cell[i] : -1;
+            const uint32_t same = __match_any_sync(0xffffffffu, c);
+            if (c >= 0) {
+                const int rank = __popc(same & ((1u << lane) - 1));
+                sorted[s_cnt[c] + rank] = i;
+            }
+            __syncwarp();
+            if (c >= 0 && (same >> lane) <= 1u) s_cnt[c] += __popc(same);   // highest lane of the group advances the cursor
+            __syncwarp();
+        }
+    }
+}
+
+// Frame::GetFeaturesInArea cell window (src/Frame.cc:1239-1261); returns false if empty
+__device__ __forceinline__ bool cell_window(const GridParams& gp, float x, float y, float r, int& c0, int& c1, int& r0, int& r1)
+{
+    c0 = max(0, (int)floorf((x - gp.min_x - r) * gp.inv_w));
+    if (c0 >= GRID_COLS) return false;
+    c1 = min(GRID_COLS - 1, (int)ceilf((x - gp.min_x + r) * gp.inv_w));
+    if (c1 < 0) return false;
+    r0 = max(0, (int)floorf((y - gp.min_y - r) * gp.inv_h));
+    if (r0 >= GRID_ROWS) return false;
+    r1 = min(GRID_ROWS - 1, (int)ceilf((y - gp.min_y + r) * gp.inv_h));
+    if (r1 < 0) return false;
+    return true;
+}
+
+struct ViewDev {
+    const plvs_keypoint* keys; const uint8_t* desc; const float* uright; int n;
+    GridParams gp; float bf; float scale[PLVS_MAX_LEVELS]; float sigma2[PLVS_MAX_LEVELS];
+};
+
+// ---------------------------------------------------------------------------------------------
+// Phase A (both projection searches): one warp per query walks the window column by column
+// (ix outer, iy inner, insertion order inside a cell == the order GetFeaturesInArea returns),
+// applies the static gates and stores (idx, dist, octave) in that order.
+// mode 0: map points (levels [l-1,l], radius by viewing cosine, xR gate with r*scale)
+// mode 1: last frame (level window by motion direction, radius th*scale, xR gate with bf*invz)
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restrict__ sorted,
+             const void* __restrict__ queries, int nq, float th, int far_points, float th_far, int forward, int backward,
+             uint32_t* __restrict__ cand, int* __restrict__ cand_n, int cap)
+{
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    float px, py, radius, xr_ref, xr_tol;
+    int minL, maxL;
+    const uint8_t* qd;
+    bool active = true;
+    if (MODE == 0) {
+        const plvs_mp_query& m = reinterpret_cast<const plvs_mp_query*>(queries)[q];
+        if (far_points && m.track_depth > th_far) active = false;
+        float r = ((double)m.view_cos > 0.998) ? 2.5f : 4.0f;
+        if (th != 1.0f) r *= th;
+        radius = r * F.scale[m.level];
+        px = m.proj_x; py = m.proj_y; minL = m.level - 1; maxL = m.level;
+        xr_ref = m.proj_xr; xr_tol = radius; qd = m.desc;
+    } else {
+        const plvs_last_query& m = reinterpret_cast<const plvs_last_query*>(queries)[q];
+        if (m.invz < 0) active = false;
+        if (m.u < F.gp.min_x || m.u > F.gp.max_x || m.v < F.gp.min_y || m.v > F.gp.max_y) active = false;
+        radius = th * F.scale[m.last_octave];
+        px = m.u; py = m.v;
+        if (forward) { minL = m.last_octave; maxL = -1; }
+        else if (backward) { minL = 0; maxL = m.last_octave; }
+        else { minL = m.last_octave - 1; maxL = m.last_octave + 1; }
+        xr_ref = m.u - F.bf * m.invz; xr_tol = radius; qd = m.desc;
+    }
+    int c0, c1, r0, r1, count = 0;
+    if (active) active = cell_window(F.gp, px, py, radius, c0, c1, r0, r1);
+    if (active) {
+        const bool check = (minL > 0) || (maxL >= 0);
+        const uint4 a0 = *reinterpret_cast<const uint4*>(qd), a1 = *reinterpret_cast<const uint4*>(qd + 16);
+        uint32_t* out = cand + (size_t)q * cap;
+        for (int ix = c0; ix <= c1; ++ix) {
+            const int pbeg = cell_start[ix * GRID_ROWS + r0], pend = cell_start[ix * GRID_ROWS + r1 + 1];
+            for (int p = pbeg + lane; p < ((pend - pbeg + 31) / 32) * 32 + pbeg; p += 32) {
+                bool ok = p < pend;
+                int idx = 0, oct = 0, dist = 0;
+                if (ok) {
+                    idx = sorted[p];
+                    const plvs_keypoint kp = F.keys[idx];
+                    oct = kp.octave;
+                    if (check && (oct < minL || oct > maxL)) ok = false;     // the maxLevel test applies even for -1 (src/Frame.cc:1283-1286)
+                    if (ok && !(fabsf(kp.x - px) < radius && fabsf(kp.y - py) < radius)) ok = false;
+                    if (ok && F.uright) { const float ur = F.uright[idx]; if (ur > 0 && fabsf(xr_ref - ur) > xr_tol) ok = false; }
+                    if (ok) dist = hamming256(a0, a1, F.desc + (size_t)idx * 32);
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                if (ok) { const int pos = count + __popc(m & ((1u << lane) - 1)); if (pos < cap) out[pos] = pack_cand(idx, dist, oct); }
+                count += __popc(m);
+            }
+        }
+    }
+    if (lane == 0) cand_n[q] = count;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase B: claim resolution by fixed-point rounds (single CTA; thread <-> query, strided).
+// claim[idx] = lowest query index with Observations()>0 currently targeting idx (blocks later ones).
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(1024)
+k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int cap, const void* __restrict__ queries, int nq,
+          const plvs_keypoint* __restrict__ keys, int n, const uint8_t* __restrict__ claimed_in, float nn_ratio, int check_ori,
+          int* __restrict__ claim_a, int* __restrict__ claim_b, int* __restrict__ target /*nq*/,
+          int32_t* __restrict__ assign /*n*/, int* __restrict__ result /*[0]=nmatches,[1]=rounds*/)
+{
+    __shared__ int s_changed, s_count, s_hist[HISTO], s_keep[HISTO];
+    const int tid = threadIdx.x;
+    const int INF = 0x7fffffff;
+    for (int i = tid; i < n; i += 1024) { claim_a[i] = INF; claim_b[i] = INF; }
+    for (int i = tid; i < nq; i += 1024) target[i] = -1;
+    __syncthreads();
+    int* cur = claim_a; int* nxt = claim_b;
+    int rounds = 0;
+    for (;;) {
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        for (int q = tid; q < nq; q += 1024) {
+            const uint32_t* c = cand + (size_t)q * cap;
+            const int m = min(cand_n[q], cap);
+            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+            for (int k = 0; k < m; ++k) {
+                const uint32_t e = c[k];
+                const int idx = cand_idx(e);
+                if (claimed_in && claimed_in[idx]) continue;
+                if (cur[idx] < q) continue;
+                const int dist = cand_dist(e);
+                if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = cand_level(e); bestIdx = idx; }
+                else if (MODE == 0 && dist < bestDist2) { bestLevel2 = cand_level(e); bestDist2 = dist; }
+            }
+            int t = -1;
+            if (bestDist <= TH_HIGH) {
+                if (MODE == 0) {
+                    if (!(bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) &&
+                        (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2)) t = bestIdx;
+                } else t = bestIdx;
+            }
+            if (t != target[q]) { target[q] = t; s_changed = 1; }
+        }
+        __syncthreads();
+        const int changed = s_changed;
+        ++rounds;
+        if (!changed) break;
+        for (int i = tid; i < n; i += 1024) nxt[i] = INF;
+        __syncthreads();
+        for (int q = tid; q < nq; q += 1024) {
+            const int t = target[q];
+            const uint32_t flags = MODE == 0 ? reinterpret_cast<const plvs_mp_query*>(queries)[q].flags
+                                             : reinterpret_cast<const plvs_last_query*>(queries)[q].flags;
+            if (t >= 0 && (flags & PLVS_Q_OBS_POSITIVE)) atomicMin(&nxt[t], q);
+        }
+        __syncthreads();
+        int* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    // final holders: the last (highest) query that wrote each keypoint
+    for (int i = tid; i < n; i += 1024) assign[i] = -1;
+    if (tid == 0) s_count = 0;
+    if (tid < HISTO) { s_hist[tid] = 0; s_keep[tid] = 1; }
+    __syncthreads();
+    int local = 0;
+    for (int q = tid; q < nq; q += 1024) {
+        const int t = target[q];
+        if (t < 0) continue;
+        ++local;
+        atomicMax(&assign[t], q);
+        if (MODE == 1 && check_ori) {
+            const float factor = HISTO / 360.0f;
+            float rot = reinterpret_cast<const plvs_last_query*>(queries)[q].angle - keys[t].angle;
+            if (rot < 0.0f) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == HISTO) bin = 0;
+            atomicAdd(&s_hist[bin], 1);
+        }
+    }
+    atomicAdd(&s_count, local);
+    __syncthreads();
+    if (MODE == 1 && check_ori) {
+        if (tid == 0) {     // ComputeThreeMaxima (src/ORBmatcher.cc:2123-2164)
+            int m1 = 0, m2 = 0, m3 = 0, i1 = -1, i2 = -1, i3 = -1;
+            for (int i = 0; i < HISTO; ++i) {
+                const int s = s_hist[i];
+                if (s > m1) { m3 = m2; m2 = m1; m1 = s; i3 = i2; i2 = i1; i1 = i; }
+                else if (s > m2) { m3 = m2; m2 = s; i3 = i2; i2 = i; }
+                else if (s > m3) { m3 = s; i3 = i; }
+            }
+            if ((float)m2 < 0.1f * (float)m1) { i2 = -1; i3 = -1; }
+            else if ((float)m3 < 0.1f * (float)m1) { i3 = -1; }
+            for (int i = 0; i < HISTO; ++i) s_keep[i] = (i == i1 || i == i2 || i == i3);
+        }
+        __syncthreads();
+        int dropped = 0;
+        for (int q = tid; q < nq; q += 1024) {
+            const int t = target[q];
+            if (t < 0) continue;
+            const float factor = HISTO / 360.0f;
+            float rot = reinterpret_cast<const plvs_last_query*>(queries)[q].angle - keys[t].angle;
+            if (rot < 0.0f) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == HISTO) bin = 0;
+            if (!s_keep[bin]) { assign[t] = -1; ++dropped; }       // the reference nulls the slot whoever holds it now
+        }
+        atomicSub(&s_count, dropped);
+        __syncthreads();
+    }
+    if (tid == 0) { result[0] = s_count; result[1] = rounds; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SearchForTriangulation (src/ORBmatcher.cc:1059-1208): one CTA per shared vocabulary node, one
+// warp per unmatched feature of KF1 in it; lanes sweep the node's KF2 features.  Winner = smallest
+// distance <= TH_LOW among the gated candidates, LAST one on ties (the `dist>bestDist` skip).
+// ---------------------------------------------------------------------------------------------
+struct FvDev { int n_nodes; const uint32_t* ids; const int* off; const int* feat; };
+
+__global__ void __launch_bounds__(256)
+k_triangulate(ViewDev K1, ViewDev K2, FvDev f1, FvDev f2, const uint8_t* __restrict__ has1, const uint8_t* __restrict__ has2,
+              const float* __restrict__ F12, float epx, float epy, int only_stereo, int coarse, int32_t* __restrict__ match12)
+{
+    const int a = blockIdx.x;
+    const uint32_t id = f1.ids[a];
+    int lo = 0, hi = f2.n_nodes - 1, b = -1;
+    while (lo <= hi) { const int mid = (lo + hi) >> 1; const uint32_t v = f2.ids[mid]; if (v == id) { b = mid; break; } if (v < id) lo = mid + 1; else hi = mid - 1; }
+    if (b < 0) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b0 = f2.off[b], b1 = f2.off[b + 1];
+    for (int e = f1.off[a] + wid; e < f1.off[a + 1]; e += 8) {
+        const int idx1 = f1.feat[e];
+        if (has1[idx1]) continue;
+        const bool stereo1 = K1.uright && K1.uright[idx1] >= 0;
+        if (only_stereo && !stereo1) continue;
+        const plvs_keypoint kp1 = K1.keys[idx1];
+        const uint8_t* d1 = K1.desc + (size_t)idx1 * 32;
+        const uint4 a0 = *reinterpret_cast<const uint4*>(d1), a1 = *reinterpret_cast<const uint4*>(d1 + 16);
+        // epipolar line l = x1' F12 (src/CameraModels/Pinhole.cpp:133-136)
+        const float la = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+        const float lb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+        const float lc = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+        const float den = la * la + lb * lb;
+        int best = 0x7fffffff;     // key = dist * 65536 + (65535 - pos): min key == min dist, then max pos
+        int bestIdx = -1;
+        for (int p = b0 + lane; p < b1; p += 32) {
+            const int idx2 = f2.feat[p];
+            if (has2[idx2]) continue;
+            const bool stereo2 = K2.uright && K2.uright[idx2] >= 0;
+            if (only_stereo && !stereo2) continue;
+            const int dist = hamming256(a0, a1, K2.desc + (size_t)idx2 * 32);
+            if (dist > TH_LOW) continue;
+            const plvs_keypoint kp2 = K2.keys[idx2];
+            if (!stereo1 && !stereo2) {
+                const float dx = epx - kp2.x, dy = epy - kp2.y;
+                if (dx * dx + dy * dy < 100 * K2.scale[kp2.octave]) continue;
+            }
+            if (!coarse) {
+                if (den == 0) continue;
+                const float num = la * kp2.x + lb * kp2.y + lc;
+                const float dsqr = num * num / den;
+                if (!((double)dsqr < 3.84 * (double)K2.sigma2[kp2.octave])) continue;
+            }
+            const int key = dist * 65536 + (65535 - (p - b0));
+            if (key < best) { best = key; bestIdx = idx2; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const int ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bestIdx, o);
+            if (ob < best) { best = ob; bestIdx = oi; }
+        }
+        if (lane == 0) match12[idx1] = bestIdx;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_tri_finish(const plvs_keypoint* __restrict__ k1, const plvs_keypoint* __restrict__ k2, int n1, int check_ori,
+             int32_t* __restrict__ match12, int* __restrict__ result)
+{
+    __shared__ int s_hist[HISTO], s_keep[HISTO], s_count;
+    const int tid = threadIdx.x;
+    if (tid < HISTO) { s_hist[tid] = 0; s_keep[tid] = 1; }
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    const float factor = HISTO / 360.0f;
+    int local = 0;
+    for (int i = tid; i < n1; i += 1024) {
+        const int j = match12[i];
+        if (j < 0) continue;
+        ++local;
+        if (check_ori) {
+            float rot = k1[i].angle - k2[j].angle;
+            if (rot < 0.0f) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == HISTO) bin = 0;
+            atomicAdd(&s_hist[bin], 1);
+        }
+    }
+    atomicAdd(&s_count, local);
+    __syncthreads();
+    if (check_ori) {
+        if (tid == 0) {
+            int m1 = 0, m2 = 0, m3 = 0, i1 = -1, i2 = -1, i3 = -1;
+            for (int i = 0; i < HISTO; ++i) {
+                const int s = s_hist[i];
+                if (s > m1) { m3 = m2; m2 = m1; m1 = s; i3 = i2; i2 = i1; i1 = i; }
+                else if (s > m2) { m3 = m2; m2 = s; i3 = i2; i2 = i; }
+                else if (s > m3) { m3 = s; i3 = i; }
+            }
+            if ((float)m2 < 0.1f * (float)m1) { i2 = -1; i3 = -1; }
+            else if ((float)m3 < 0.1f * (float)m1) { i3 = -1; }
+            for (int i = 0; i < HISTO; ++i) s_keep[i] = (i == i1 || i == i2 || i == i3);
+        }
+        __syncthreads();
+        int dropped = 0;
+        for (int i = tid; i < n1; i += 1024) {
+            const int j = match12[i];
+            if (j < 0) continue;
+            float rot = k1[i].angle - k2[j].angle;
+            if (rot < 0.0f) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == HISTO) bin = 0;
+            if (!s_keep[bin]) { match12[i] = -1; ++dropped; }
+        }
+        atomicSub(&s_count, dropped);
+        __syncthreads();
+    }
+    if (tid == 0) result[0] = s_count;
+}
+
+__global__ void k_fill_i32(int32_t* p, int n, int32_t v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
+}  // namespace
+
+struct plvs_match {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // device staging for host-resident views (two frames) and queries
+    DevBuf<plvs_keypoint> d_keys[2];
+    DevBuf<uint8_t> d_desc[2], d_has[2], d_claimed;
+    DevBuf<float> d_uright[2], d_f12;
+    DevBuf<uint8_t> d_query;
+    DevBuf<int> d_cell_start, d_sorted, d_kp_cell, d_cand_n, d_claim_a, d_claim_b, d_target;
+    DevBuf<uint32_t> d_cand;
+    DevBuf<uint32_t> d_fv_ids[2];
+    DevBuf<int> d_fv_off[2], d_fv_feat[2];
+    DevBuf<int32_t> d_assign;
+    PinBuf<int32_t> p_assign;
+    PinBuf<int> p_result, p_cand_n;
+    int cap = 128;
+    int last_rounds = 0, last_launches = 0;
+    std::mutex mu;
+};
+
+namespace {
+
+int stage_view(plvs_match* h, int slot, const plvs_frame_view* v, ViewDev* out)
+{
+    if (!v || v->n < 0 || v->n > 65535 || (v->n && (!v->keys || !v->desc))) { set_error("bad frame view"); return PLVS_EINVAL; }
+    if (v->nlevels < 1 || v->nlevels > PLVS_MAX_LEVELS) { set_error("bad nlevels"); return PLVS_EINVAL; }
+    out->n = v->n;
+    out->gp = GridParams{v->min_x, v->min_y, v->max_x, v->max_y, v->grid_inv_w, v->grid_inv_h};
+    out->bf = v->bf;
+    for (int i = 0; i < PLVS_MAX_LEVELS; ++i) { out->scale[i] = v->scale_factors[i]; out->sigma2[i] = v->level_sigma2[i]; }
+    if (v->on_device) {
+        out->keys = v->keys; out->desc = v->desc; out->uright = v->uright;
+        return PLVS_OK;
+    }
+    int rc;
+    const size_t n = (size_t)std::max(v->n, 1);
+    if ((rc = h->d_keys[slot].alloc(n))) return rc;
+    if ((rc = h->d_desc[slot].alloc(n * 32))) return rc;
+    PLVS_CUDA(cudaMemcpyAsync(h->d_keys[slot].p, v->keys, (size_t)v->n * sizeof(plvs_keypoint), cudaMemcpyHostToDevice, h->stream));
+    PLVS_CUDA(cudaMemcpyAsync(h->d_desc[slot].p, v->desc, (size_t)v->n * 32, cudaMemcpyHostToDevice, h->stream));
+    out->keys = h->d_keys[slot].p; out->desc = h->d_desc[slot].p; out->uright = nullptr;
+    if (v->uright) {
+        if ((rc = h->d_uright[slot].alloc(n))) return rc;
+        PLVS_CUDA(cudaMemcpyAsync(h->d_uright[slot].p, v->uright, (size_t)v->n * 4, cudaMemcpyHostToDevice, h->stream));
+        out->uright = h->d_uright[slot].p;
+    }
+    return PLVS_OK;
+}
+
+template <int MODE>
+int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_t qsize, int nq, float th, float nn_ratio,
+                   int far_points, float th_far, int forward, int backward, int check_ori,
+                   const uint8_t* claimed_in, int32_t* assign, int* nmatches)
+{
+    if (!h || !F || !assign || !nmatches || nq < 0 || (nq && !q)) { set_error("null/invalid argument"); return PLVS_EINVAL; }
+    std::lock_guard<std::mutex> lock(h->mu);
+    PLVS_CUDA(cudaSetDevice(h->device));
+    ViewDev V;
+    int rc = stage_view(h, 0, F, &V);
+    if (rc) return rc;
+    const int n = F->n;
+    *nmatches = 0;
+    for (int i = 0; i < n; ++i) assign[i] = -1;
+    if (n == 0 || nq == 0) return PLVS_OK;
+    cudaStream_t st = h->stream;
+    if ((rc = h->d_query.alloc(qsize * nq))) return rc;
+    PLVS_CUDA(cudaMemcpyAsync(h->d_query.p, q, qsize * nq, cudaMemcpyHostToDevice, st));
+    const uint8_t* d_claimed = nullptr;
+    if (claimed_in) {
+        if ((rc = h->d_claimed.alloc(n))) return rc;
+        PLVS_CUDA(cudaMemcpyAsync(h->d_claimed.p, claimed_in, n, cudaMemcpyHostToDevice, st));
+        d_claimed = h->d_claimed.p;
+    }
+    if ((rc = h->d_cell_start.alloc(GRID_CELLS + 1)) || (rc = h->d_sorted.alloc(n)) || (rc = h->d_kp_cell.alloc(n)) ||
+        (rc = h->d_cand_n.alloc(nq)) || (rc = h->d_claim_a.alloc(n)) || (rc = h->d_claim_b.alloc(n)) || (rc = h->d_target.alloc(nq)) ||
+        (rc = h->d_assign.alloc(n)) || (rc = h->p_assign.alloc(n)) || (rc = h->p_result.alloc(4)) || (rc = h->p_cand_n.alloc(nq)))
+        return rc;
+    int launches = 0;
+    k_build_grid<<<1, 1024, 0, st>>>(V.keys, n, V.gp, h->d_cell_start.p, h->d_sorted.p, h->d_kp_cell.p);
+    ++launches;
+    for (;;) {
+        if ((rc = h->d_cand.alloc((size_t)nq * h->cap))) return rc;
+        k_candidates<MODE><<<div_up(nq, 8), 256, 0, st>>>(V, h->d_cell_start.p, h->d_sorted.p, h->d_query.p, nq, th, far_points, th_far, forward, backward,
+                                                           h->d_cand.p, h->d_cand_n.p, h->cap);
+        ++launches;
+        PLVS_CUDA(cudaMemcpyAsync(h->p_cand_n.h, h->d_cand_n.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+        k_resolve<MODE><<<1, 1024, 0, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
+                                            h->d_claim_a.p, h->d_claim_b.p, h->d_target.p, h->p_assign.d, h->p_result.d);
+        ++launches;
+        PLVS_CUDA(cudaGetLastError());
+        PLVS_CUDA(cudaStreamSynchronize(st));
+        int mx = 0;
+        for (int i = 0; i < nq; ++i) mx = std::max(mx, h->p_cand_n.h[i]);
+        if (mx <= h->cap) break;
+        while (h->cap < mx) h->cap *= 2;       // a window held more candidates than reserved: redo with room (exactness first)
+    }
+    std::memcpy(assign, h->p_assign.h, (size_t)n * 4);
+    *nmatches = h->p_result.h[0];
+    h->last_rounds = h->p_result.h[1];
+    h->last_launches = launches;
+    return PLVS_OK;
+}
+
+int stage_fv(plvs_match* h, int slot, const plvs_featvec* f, int on_device, FvDev* out)
+{
+    if (!f || f->n_nodes < 0) { set_error("bad feature vector"); return PLVS_EINVAL; }
+    out->n_nodes = f->n_nodes;
+    if (on_device) { out->ids = f->node_ids; out->off = f->offsets; out->feat = f->features; return PLVS_OK; }
+    const int total = f->n_nodes ? f->offsets[f->n_nodes] : 0;
+    int rc;
+    if ((rc = h->d_fv_ids[slot].alloc(std::max(f->n_nodes, 1))) || (rc = h->d_fv_off[slot].alloc(f->n_nodes + 1)) ||
+        (rc = h->d_fv_feat[slot].alloc(std::max(total, 1)))) return rc;
+    if (f->n_nodes) {
+        PLVS_CUDA(cudaMemcpyAsync(h->d_fv_ids[slot].p, f->node_ids, (size_t)f->n_nodes * 4, cudaMemcpyHostToDevice, h->stream));
+        PLVS_CUDA(cudaMemcpyAsync(h->d_fv_off[slot].p, f->offsets, (size_t)(f->n_nodes + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+        PLVS_CUDA(cudaMemcpyAsync(h->d_fv_feat[slot].p, f->features, (size_t)total * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    out->ids = h->d_fv_ids[slot].p; out->off = h->d_fv_off[slot].p; out->feat = h->d_fv_feat[slot].p;
+    return PLVS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int plvs_hamming256(const uint8_t* a, const uint8_t* b)
+{
+    uint64_t x[4], y[4];
+    std::memcpy(x, a, 32); std::memcpy(y, b, 32);
+    int d = 0;
+    for (int i = 0; i < 4; ++i) d += __builtin_popcountll(x[i] ^ y[i]);
+    return d;
+}
+
+int plvs_match_create(int device, plvs_match** out)
+{
+    if (!out) return PLVS_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: libplvs_b200 has no CPU fallback"); return PLVS_ENODEV; }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range", device); return PLVS_EINVAL; }
+    PLVS_CUDA(cudaSetDevice(device));
+    plvs_match* h = new plvs_match();
+    h->device = device;
+    { cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+      if (e != cudaSuccess) { delete h; set_error("stream creation failed: %s", cudaGetErrorString(e)); return PLVS_ENODEV; } }
+    *out = h;
+    return PLVS_OK;
+}
+
+void plvs_match_destroy(plvs_match* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    delete h;
+}
+
+int plvs_match_projection_map(plvs_match* h, const plvs_frame_view* F, const plvs_mp_query* q, int nq, float th, float nn_ratio,
+                              int far_points, float th_far, const uint8_t* claimed_in, int32_t* assign, int* nmatches)
+{
+    return run_projection<0>(h, F, q, sizeof(plvs_mp_query), nq, th, nn_ratio, far_points, th_far, 0, 0, 0, claimed_in, assign, nmatches);
+}
+
+int plvs_match_projection_last(plvs_match* h, const plvs_frame_view* cur, const plvs_last_query* q, int nq, float th,
+                               int forward, int backward, int check_orientation, const uint8_t* claimed_in, int32_t* assign, int* nmatches)
+{
+    return run_projection<1>(h, cur, q, sizeof(plvs_last_query), nq, th, 0.f, 0, 0.f, forward, backward, check_orientation, claimed_in, assign, nmatches);
+}
+
+int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const plvs_frame_view* kf2,
+                             const plvs_featvec* fv1, const plvs_featvec* fv2, const uint8_t* has_mp1, const uint8_t* has_mp2,
+                             const float F12[9], const float ep[2], int only_stereo, int coarse, int check_orientation,
+                             int32_t* match12, int* nmatches)
+{
+    if (!h || !kf1 || !kf2 || !fv1 || !fv2 || !has_mp1 || !has_mp2 || !F12 || !ep || !match12 || !nmatches) { set_error("null argument"); return PLVS_EINVAL; }
+    std::lock_guard<std::mutex> lock(h->mu);
+    PLVS_CUDA(cudaSetDevice(h->device));
+    ViewDev V1, V2; FvDev D1, D2;
+    int rc;
+    if ((rc = stage_view(h, 0, kf1, &V1)) || (rc = stage_view(h, 1, kf2, &V2))) return rc;
+    if ((rc = stage_fv(h, 0, fv1, kf1->on_device, &D1)) || (rc = stage_fv(h, 1, fv2, kf2->on_device, &D2))) return rc;
+    const int n1 = kf1->n, n2 = kf2->n;
+    *nmatches = 0;
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    if (n1 == 0 || n2 == 0 || D1.n_nodes == 0 || D2.n_nodes == 0) return PLVS_OK;
+    cudaStream_t st = h->stream;
+    const uint8_t *dh1 = has_mp1, *dh2 = has_mp2;
+    if (!kf1->on_device) {
+        if ((rc = h->d_has[0].alloc(n1))) return rc;
+        PLVS_CUDA(cudaMemcpyAsync(h->d_has[0].p, has_mp1, n1, cudaMemcpyHostToDevice, st)); dh1 = h->d_has[0].p;
+    }
+    if (!kf2->on_device) {
+        if ((rc = h->d_has[1].alloc(n2))) return rc;
+        PLVS_CUDA(cudaMemcpyAsync(h->d_has[1].p, has_mp2, n2, cudaMemcpyHostToDevice, st)); dh2 = h->d_has[1].p;
+    }
+    if ((rc = h->d_f12.alloc(16)) || (rc = h->p_assign.alloc(n1)) || (rc = h->p_result.alloc(4))) return rc;
+    PLVS_CUDA(cudaMemcpyAsync(h->d_f12.p, F12, 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+    k_fill_i32<<<div_up(n1, 256), 256, 0, st>>>(h->p_assign.d, n1, -1);
+    k_triangulate<<<D1.n_nodes, 256, 0, st>>>(V1, V2, D1, D2, dh1, dh2, h->d_f12.p, ep[0], ep[1], only_stereo, coarse, h->p_assign.d);
+    k_tri_finish<<<1, 1024, 0, st>>>(V1.keys, V2.keys, n1, check_orientation, h->p_assign.d, h->p_result.d);
+    PLVS_CUDA(cudaGetLastError());
+    PLVS_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(match12, h->p_assign.h, (size_t)n1 * 4);
+    *nmatches = h->p_result.h[0];
+    h->last_launches = 3;
+    return PLVS_OK;
+}
+
+}  // extern "C"

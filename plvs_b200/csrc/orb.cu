@@ -1,0 +1,446 @@
+// ORB extractor: handle, geometry tables, launch sequence and the extern "C" entry points that
+// replace PLVS2::ORBextractor (reference: include/ORBextractor.h:59-170, src/ORBextractor.cc).
+#include <atomic>
+#include <cstdlib>
+#include <cmath>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include "orb_distribute.hpp"
+#include "orb_kernels.cuh"
+
+using namespace plvs;
+using namespace plvs::orb;
+
+static const int h_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+struct plvs_orb {
+    plvs_orb_params prm{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr;
+    // constructor tables (src/ORBextractor.cc:446-523)
+    float scale[PLVS_MAX_LEVELS], inv_scale[PLVS_MAX_LEVELS], sigma2[PLVS_MAX_LEVELS], inv_sigma2[PLVS_MAX_LEVELS];
+    int quota[PLVS_MAX_LEVELS];
+    int umax[16];
+    // geometry for the current image size
+    int w = 0, h = 0, batch_cap = 0;
+    std::vector<LevelGeom> lv;
+    std::vector<CellDesc> cells;
+    std::vector<TileDesc> blur_tiles;
+    long long frame_stride = 0;      // bytes of one frame's pyramid
+    long long slots_per_frame = 0;
+    int sel_cap = 0;                 // keypoint capacity per frame
+    DevBuf<uint8_t> d_pyr, d_blur, d_dbg_score;
+    bool debug = false;
+    DevBuf<LevelGeom> d_lv;
+    DevBuf<CellDesc> d_cells;
+    DevBuf<TileDesc> d_tiles;
+    DevBuf<BilinearTap> d_taps;
+    DevBuf<uint32_t> d_slots, d_cand;
+    DevBuf<int> d_cell_count, d_cand_count;
+    DevBuf<plvs_keypoint> d_kp;
+    DevBuf<uint8_t> d_desc;
+    PinBuf<uint32_t> p_cand;         // compacted candidates (device writes, host reads)
+    PinBuf<int> p_cand_count;
+    PinBuf<uint32_t> p_sel;          // selected keypoints (host writes, device reads)
+    PinBuf<int> p_sel_off;
+    PinBuf<plvs_keypoint> p_kp;      // results (device writes, host reads)
+    PinBuf<uint8_t> p_desc;
+    std::vector<int> n_kp;           // per frame of the last batch
+    std::vector<char> lapped;
+    int last_batch = 0;
+    plvs_orb_stats stats{};
+    std::mutex mu;
+};
+
+namespace {
+
+int rhe(float v) { return (int)lrintf(v); }
+int rhe(double v) { return (int)lrint(v); }
+
+void build_tables(plvs_orb* o)
+{
+    const plvs_orb_params& p = o->prm;
+    o->scale[0] = 1.0f; o->sigma2[0] = 1.0f;
+    for (int i = 1; i < p.nlevels; ++i) { o->scale[i] = o->scale[i - 1] * p.scale_factor; o->sigma2[i] = o->scale[i] * o->scale[i]; }
+    for (int i = 0; i < p.nlevels; ++i) { o->inv_scale[i] = 1.0f / o->scale[i]; o->inv_sigma2[i] = 1.0f / o->sigma2[i]; }
+    const float factor = 1.0f / p.scale_factor;
+    float want = p.nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)p.nlevels));
+    int sum = 0;
+    for (int l = 0; l < p.nlevels - 1; ++l) { o->quota[l] = rhe(want); sum += o->quota[l]; want *= factor; }
+    o->quota[p.nlevels - 1] = std::max(p.nfeatures - sum, 0);
+    const int vmax = (int)std::floor(kHalfPatch * std::sqrt(2.f) / 2 + 1);
+    const int vmin = (int)std::ceil(kHalfPatch * std::sqrt(2.f) / 2);
+    const double hp2 = kHalfPatch * kHalfPatch;
+    for (int v = 0; v <= vmax; ++v) o->umax[v] = rhe(std::sqrt(hp2 - v * v));
+    for (int v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+        while (o->umax[v0] == o->umax[v0 + 1]) ++v0;
+        o->umax[v] = v0;
+        ++v0;
+    }
+}
+
+// cv::resize INTER_LINEAR coefficient tables for one axis (SURVEY.md §8c' item 1)
+void axis_taps(int S, int D, BilinearTap* t)
+{
+    const double sc = 1. / ((double)D / S);
+    for (int d = 0; d < D; ++d) {
+        float f = (float)((d + 0.5) * sc - 0.5);
+        int s = (int)std::floor(f);
+        f -= s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= S - 1) { s = S - 1; f = 0.f; }
+        t[d].i0 = (unsigned short)s;
+        t[d].i1 = (unsigned short)std::min(s + 1, S - 1);
+        t[d].c0 = (short)std::min(std::max(rhe((1.f - f) * 2048.f), -32768), 32767);
+        t[d].c1 = (short)std::min(std::max(rhe(f * 2048.f), -32768), 32767);
+    }
+}
+
+int setup_geometry(plvs_orb* o, int w, int h, int batch)
+{
+    if (o->w == w && o->h == h && batch <= o->batch_cap) return PLVS_OK;
+    const int nl = o->prm.nlevels;
+    if (w > 4095 || h > 4095) { set_error("image larger than 4095 px is not supported by the 12-bit candidate packing"); return PLVS_EINVAL; }
+    o->lv.assign(nl, LevelGeom{});
+    o->cells.clear(); o->blur_tiles.clear();
+    long long off = 0;
+    int tap_total = 0, slot_total = 0;
+    std::vector<BilinearTap> taps;
+    for (int l = 0; l < nl; ++l) {
+        LevelGeom& g = o->lv[l];
+        g.w = rhe((float)w * o->inv_scale[l]);              // src/ORBextractor.cc:1485-1486
+        g.h = rhe((float)h * o->inv_scale[l]);
+        if (g.w < 8 || g.h < 8) { set_error("pyramid level %d is %dx%d: too small", l, g.w, g.h); return PLVS_EINVAL; }
+        g.pitch = (int)align_up(g.w, 128);
+        g.off = off;
+        off += (long long)g.pitch * g.h;
+        g.scale = o->scale[l];
+        g.patch_size = (int)(31 * o->scale[l]);
+        g.tap_x_off = tap_total; g.tap_y_off = tap_total + g.w;
+        tap_total += g.w + g.h;
+        taps.resize(tap_total);
+        if (l > 0) {
+            axis_taps(o->lv[l - 1].w, g.w, taps.data() + g.tap_x_off);
+            axis_taps(o->lv[l - 1].h, g.h, taps.data() + g.tap_y_off);
+        }
+        // FAST cells (src/ORBextractor.cc:872-947)
+        g.cell_begin = (int)o->cells.size();
+        g.slot_begin = slot_total;
+        const int minB = kRoiMargin, maxBX = g.w - kEdge + 3, maxBY = g.h - kEdge + 3;
+        const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
+        if (width > 0 && height > 0) {
+            const int nCols = (int)(width / 35.f), nRows = (int)(height / 35.f);
+            if (nCols > 0 && nRows > 0) {
+                const int wCell = (int)std::ceil(width / nCols), hCell = (int)std::ceil(height / nRows);
+                for (int i = 0; i < nRows; ++i) {
+                    const float iniY = (float)(minB + i * hCell);
+                    float maxY = iniY + hCell + 6;
+                    if (iniY >= maxBY - 3) continue;
+                    if (maxY > maxBY) maxY = (float)maxBY;
+                    for (int j = 0; j < nCols; ++j) {
+                        const float iniX = (float)(minB + j * wCell);
+                        float maxX = iniX + wCell + 6;
+                        if (iniX >= maxBX - 6) continue;
+                        if (maxX > maxBX) maxX = (float)maxBX;
+                        CellDesc c;
+                        c.level = (short)l;
+                        c.x0 = (short)iniX; c.y0 = (short)iniY; c.x1 = (short)maxX; c.y1 = (short)maxY;
+                        const int iw = std::max(c.x1 - c.x0 - 6, 0), ih = std::max(c.y1 - c.y0 - 6, 0);
+                        c.cap = ((iw + 1) / 2) * ((ih + 1) / 2);
+                        c.slot_off = slot_total;
+                        slot_total += c.cap;
+                        if (c.x1 - c.x0 > kMaxCell || c.y1 - c.y0 > kMaxCell) { set_error("FAST cell larger than %d px", kMaxCell); return PLVS_EINVAL; }
+                        o->cells.push_back(c);
+                    }
+                }
+            }
+        }
+        g.cell_count = (int)o->cells.size() - g.cell_begin;
+        g.slot_count = slot_total - g.slot_begin;
+        if (g.cell_count > 4096) { set_error("more than 4096 FAST cells in level %d", l); return PLVS_EINVAL; }
+        for (int ty = 0; ty < div_up(g.h, kBlurTH); ++ty)
+            for (int tx = 0; tx < div_up(g.w, kBlurTW); ++tx) o->blur_tiles.push_back(TileDesc{(short)l, (short)tx, (short)ty, 0});
+    }
+    o->frame_stride = (long long)align_up((size_t)off, 256);
+    o->slots_per_frame = slot_total;
+    // the distributor may return a few more than the quota per level (it finishes the current split)
+    o->sel_cap = (int)align_up((size_t)(o->prm.nfeatures * 2 + 64 * nl), 32);
+    o->w = w; o->h = h; o->batch_cap = std::max(batch, o->batch_cap);
+    const int B = o->batch_cap;
+    int rc;
+    if ((rc = o->d_pyr.alloc((size_t)o->frame_stride * B))) return rc;
+    if ((rc = o->d_blur.alloc((size_t)o->frame_stride * B))) return rc;
+    if (o->debug) {
+        if ((rc = o->d_dbg_score.alloc((size_t)o->frame_stride * B))) return rc;
+        PLVS_CUDA(cudaMemsetAsync(o->d_dbg_score.p, 0, (size_t)o->frame_stride * B, o->stream));
+    }
+    if ((rc = o->d_lv.alloc(nl))) return rc;
+    if ((rc = o->d_cells.alloc(o->cells.size()))) return rc;
+    if ((rc = o->d_tiles.alloc(o->blur_tiles.size()))) return rc;
+    if ((rc = o->d_taps.alloc(taps.size()))) return rc;
+    if ((rc = o->d_slots.alloc((size_t)slot_total * B))) return rc;
+    if ((rc = o->d_cand.alloc((size_t)slot_total * B))) return rc;
+    if ((rc = o->d_cell_count.alloc(o->cells.size() * B))) return rc;
+    if ((rc = o->d_cand_count.alloc((size_t)nl * B))) return rc;
+    if ((rc = o->d_kp.alloc((size_t)o->sel_cap * B))) return rc;
+    if ((rc = o->d_desc.alloc((size_t)o->sel_cap * B * 32))) return rc;
+    if ((rc = o->p_cand.alloc((size_t)slot_total * B))) return rc;
+    if ((rc = o->p_cand_count.alloc((size_t)nl * B))) return rc;
+    if ((rc = o->p_sel.alloc((size_t)o->sel_cap * B))) return rc;
+    if ((rc = o->p_sel_off.alloc((size_t)(nl + 1) * B))) return rc;
+    if ((rc = o->p_kp.alloc((size_t)o->sel_cap * B))) return rc;
+    if ((rc = o->p_desc.alloc((size_t)o->sel_cap * B * 32))) return rc;
+    PLVS_CUDA(cudaMemcpyAsync(o->d_lv.p, o->lv.data(), nl * sizeof(LevelGeom), cudaMemcpyHostToDevice, o->stream));
+    PLVS_CUDA(cudaMemcpyAsync(o->d_cells.p, o->cells.data(), o->cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice, o->stream));
+    PLVS_CUDA(cudaMemcpyAsync(o->d_tiles.p, o->blur_tiles.data(), o->blur_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, o->stream));
+    PLVS_CUDA(cudaMemcpyAsync(o->d_taps.p, taps.data(), taps.size() * sizeof(BilinearTap), cudaMemcpyHostToDevice, o->stream));
+    PLVS_CUDA(cudaMemcpyToSymbolAsync(c_pattern, h_pattern, sizeof(h_pattern), 0, cudaMemcpyHostToDevice, o->stream));
+    PLVS_CUDA(cudaMemcpyToSymbolAsync(c_umax, o->umax, sizeof(o->umax), 0, cudaMemcpyHostToDevice, o->stream));
+    PLVS_CUDA(cudaStreamSynchronize(o->stream));
+    return PLVS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int plvs_orb_create(const plvs_orb_params* p, int device, plvs_orb** out)
+{
+    if (!p || !out) { set_error("null argument"); return PLVS_EINVAL; }
+    if (p->nlevels < 1 || p->nlevels > PLVS_MAX_LEVELS || p->nfeatures < 1 || !(p->scale_factor > 1.0f)) {
+        set_error("bad ORB parameters"); return PLVS_EINVAL;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: libplvs_b200 has no CPU fallback"); return PLVS_ENODEV; }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range", device); return PLVS_EINVAL; }
+    PLVS_CUDA(cudaSetDevice(device));
+    plvs_orb* o = new plvs_orb();
+    o->prm = *p; o->device = device;
+    { const char* e = getenv("PLVS_ORB_DEBUG"); o->debug = e && e[0] == '1'; }
+    build_tables(o);
+    cudaError_t e1 = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking);
+    cudaError_t e2 = e1 == cudaSuccess ? cudaEventCreateWithFlags(&o->ev, cudaEventDisableTiming) : e1;
+    if (e2 != cudaSuccess) { delete o; set_error("stream/event creation failed: %s", cudaGetErrorString(e2)); return PLVS_ENODEV; }
+    *out = o;
+    return PLVS_OK;
+}
+
+void plvs_orb_destroy(plvs_orb* o)
+{
+    if (!o) return;
+    cudaSetDevice(o->device);
+    if (o->stream) { cudaStreamSynchronize(o->stream); cudaStreamDestroy(o->stream); }
+    if (o->ev) cudaEventDestroy(o->ev);
+    delete o;
+}
+
+int plvs_orb_tables(const plvs_orb* o, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* fpl)
+{
+    if (!o) return PLVS_EINVAL;
+    for (int i = 0; i < o->prm.nlevels; ++i) {
+        if (scale) scale[i] = o->scale[i];
+        if (inv_scale) inv_scale[i] = o->inv_scale[i];
+        if (sigma2) sigma2[i] = o->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = o->inv_sigma2[i];
+        if (fpl) fpl[i] = o->quota[i];
+    }
+    return PLVS_OK;
+}
+
+int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, int h, int stride,
+                           size_t frame_stride_in, int on_device, int lap0, int lap1,
+                           plvs_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_out)
+{
+    if (!o || !n_out || batch < 1) { set_error("null/invalid argument"); return PLVS_EINVAL; }
+    if (!gray || w <= 0 || h <= 0) { for (int b = 0; b < batch; ++b) { n_out[b] = 0; if (mono_out) mono_out[b] = -1; } return PLVS_OK; }  // operator() returns -1 on empty image
+    if (stride < w) { set_error("stride < width"); return PLVS_EINVAL; }
+    std::lock_guard<std::mutex> lock(o->mu);
+    PLVS_CUDA(cudaSetDevice(o->device));
+    int rc = setup_geometry(o, w, h, batch);
+    if (rc) return rc;
+    const int nl = o->prm.nlevels;
+    cudaStream_t st = o->stream;
+    int launches = 0;
+
+    // level 0 <- input (ComputePyramid level 0; the 19-px border frame is never read on this path)
+    const LevelGeom& g0 = o->lv[0];
+    if (on_device) {
+        for (int b = 0; b < batch; ++b)
+            PLVS_CUDA(cudaMemcpy2DAsync(o->d_pyr.p + (size_t)b * o->frame_stride, g0.pitch, gray + b * frame_stride_in, stride, w, h,
+                                        cudaMemcpyDeviceToDevice, st));
+    } else {
+        for (int b = 0; b < batch; ++b)
+            PLVS_CUDA(cudaMemcpy2DAsync(o->d_pyr.p + (size_t)b * o->frame_stride, g0.pitch, gray + b * frame_stride_in, stride, w, h,
+                                        cudaMemcpyHostToDevice, st));
+    }
+    for (int l = 1; l < nl; ++l) {
+        const LevelGeom& g = o->lv[l];
+        dim3 grid(div_up(g.w, 128), div_up(g.h, 8), batch), block(32, 8);
+        k_resize_level<<<grid, block, 0, st>>>(o->d_pyr.p, o->frame_stride, o->lv[l - 1], g, o->d_taps.p);
+        ++launches;
+    }
+    k_fast_cells<<<dim3((unsigned)o->cells.size(), batch), 256, 0, st>>>(o->d_pyr.p, o->frame_stride, o->d_lv.p, o->d_cells.p, o->d_slots.p,
+                                                                          o->slots_per_frame, o->d_cell_count.p, (int)o->cells.size(),
+                                                                          o->prm.ini_th_fast, o->prm.min_th_fast, o->debug ? o->d_dbg_score.p : nullptr);
+    k_compact<<<dim3(nl, batch), 256, 0, st>>>(o->d_slots.p, o->slots_per_frame, o->d_cell_count.p, (int)o->cells.size(), o->d_lv.p, o->d_cells.p, nl,
+                                                o->d_cand.p, o->p_cand.d, o->d_cand_count.p, o->p_cand_count.d);
+    launches += 2;
+    PLVS_CUDA(cudaEventRecord(o->ev, st));
+    // the blur does not depend on the keypoints: it overlaps the host-side distribution
+    k_blur<<<dim3((unsigned)o->blur_tiles.size(), batch), 256, 0, st>>>(o->d_pyr.p, o->d_blur.p, o->frame_stride, o->d_lv.p, o->d_tiles.p);
+    ++launches;
+    PLVS_CUDA(cudaGetLastError());
+    PLVS_CUDA(cudaEventSynchronize(o->ev));
+
+    // ---- DistributeOctTree per (frame, level) on host threads
+    const int ntask = batch * nl;
+    std::vector<std::vector<int>> picked(ntask);
+    {
+        const int nthreads = std::max(1, std::min<int>({ntask, 16, (int)std::thread::hardware_concurrency()}));
+        std::vector<std::thread> pool;
+        std::atomic<int> next{0};
+        auto work = [&]() {
+            Distributor dist;
+            std::vector<int> xs, ys, rs;
+            for (;;) {
+                const int t = next.fetch_add(1);
+                if (t >= ntask) break;
+                const int b = t / nl, l = t % nl;
+                const LevelGeom& g = o->lv[l];
+                const int n = o->p_cand_count.h[b * nl + l];
+                const uint32_t* c = o->p_cand.h + (size_t)b * o->slots_per_frame + g.slot_begin;
+                xs.resize(n); ys.resize(n); rs.resize(n);
+                for (int i = 0; i < n; ++i) { xs[i] = unpack_x(c[i]) - kRoiMargin; ys[i] = unpack_y(c[i]) - kRoiMargin; rs[i] = unpack_s(c[i]); }
+                dist.run(n, xs.data(), ys.data(), rs.data(), kRoiMargin, g.w - kEdge + 3, kRoiMargin, g.h - kEdge + 3, o->quota[l], picked[t]);
+            }
+        };
+        if (nthreads == 1) work();
+        else { for (int i = 0; i < nthreads; ++i) pool.emplace_back(work); for (auto& th : pool) th.join(); }
+    }
+    int64_t ncand = 0, nkp = 0;
+    int max_k = 0;
+    o->n_kp.assign(batch, 0);
+    for (int b = 0; b < batch; ++b) {
+        int* loff = o->p_sel_off.h + (size_t)b * (nl + 1);
+        uint32_t* sel = o->p_sel.h + (size_t)b * o->sel_cap;
+        int k = 0;
+        for (int l = 0; l < nl; ++l) {
+            loff[l] = k;
+            const uint32_t* c = o->p_cand.h + (size_t)b * o->slots_per_frame + o->lv[l].slot_begin;
+            ncand += o->p_cand_count.h[b * nl + l];
+            for (int id : picked[b * nl + l]) { if (k < o->sel_cap) sel[k] = c[id]; ++k; }
+        }
+        if (k > o->sel_cap) { set_error("internal keypoint capacity %d exceeded (%d)", o->sel_cap, k); return PLVS_ENOMEM; }
+        loff[nl] = k;
+        o->n_kp[b] = k;
+        nkp += k;
+        max_k = std::max(max_k, k);
+    }
+    if (max_k > 0) {
+        k_orient_describe<<<dim3(div_up(max_k, 8), batch), 256, 0, st>>>(o->d_pyr.p, o->d_blur.p, o->frame_stride, o->d_lv.p, nl, o->p_sel.d, o->p_sel_off.d,
+                                                                          o->sel_cap, o->d_kp.p, o->d_desc.p, o->p_kp.d, o->p_desc.d);
+        ++launches;
+    }
+    PLVS_CUDA(cudaGetLastError());
+    PLVS_CUDA(cudaStreamSynchronize(st));
+
+    // ---- assemble (src/ORBextractor.cc:1267-1389): mono indices from the front, lapping-area ones from the back
+    o->lapped.assign(batch, 0);
+    int ret = PLVS_OK;
+    for (int b = 0; b < batch; ++b) {
+        const int n = o->n_kp[b];
+        n_out[b] = n;
+        if (n > cap) { ret = PLVS_ECAP; if (mono_out) mono_out[b] = 0; continue; }
+        const plvs_keypoint* sk = o->p_kp.h + (size_t)b * o->sel_cap;
+        const uint8_t* sd = o->p_desc.h + (size_t)b * o->sel_cap * 32;
+        plvs_keypoint* dk = kps ? kps + (size_t)b * cap : nullptr;
+        uint8_t* dd = desc ? desc + (size_t)b * cap * 32 : nullptr;
+        int mono = 0, stereo = n - 1;
+        bool any_lap = false;
+        for (int i = 0; i < n; ++i) {
+            const bool lap = sk[i].x >= (float)lap0 && sk[i].x <= (float)lap1;
+            const int slot = lap ? stereo-- : mono++;
+            any_lap |= lap;
+            if (dk) dk[slot] = sk[i];
+            if (dd) std::memcpy(dd + (size_t)slot * 32, sd + (size_t)i * 32, 32);
+        }
+        o->lapped[b] = any_lap;
+        if (mono_out) mono_out[b] = mono;
+    }
+    if (ret == PLVS_ECAP) set_error("keypoint capacity too small");
+    o->last_batch = batch;
+    o->stats.pyramid_pixels = 0;
+    for (int l = 0; l < nl; ++l) o->stats.pyramid_pixels += (int64_t)o->lv[l].w * o->lv[l].h;
+    o->stats.candidates = ncand; o->stats.keypoints = nkp; o->stats.kernel_launches = launches;
+    return ret;
+}
+
+int plvs_orb_extract(plvs_orb* o, const uint8_t* gray, int w, int h, int stride, int on_device, int lap0, int lap1,
+                     plvs_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_out)
+{
+    return plvs_orb_extract_batch(o, 1, gray, w, h, stride, 0, on_device, lap0, lap1, kps, desc, cap, n_out, mono_out);
+}
+
+int plvs_orb_pyramid_level(const plvs_orb* o, int frame, int level, int blurred, const uint8_t** dptr, int* w, int* h, int* pitch)
+{
+    if (!o || frame < 0 || frame >= o->last_batch || level < 0 || level >= o->prm.nlevels) { set_error("bad frame/level"); return PLVS_EINVAL; }
+    const LevelGeom& g = o->lv[level];
+    if (blurred == 2 && !o->debug) { set_error("score map needs PLVS_ORB_DEBUG=1 at create time"); return PLVS_ESTATE; }
+    if (dptr) *dptr = (blurred == 2 ? o->d_dbg_score.p : blurred ? o->d_blur.p : o->d_pyr.p) + (size_t)frame * o->frame_stride + g.off;
+    if (w) *w = g.w;
+    if (h) *h = g.h;
+    if (pitch) *pitch = g.pitch;
+    return PLVS_OK;
+}
+
+int plvs_orb_download_level(plvs_orb* o, int frame, int level, int blurred, uint8_t* host, int host_stride)
+{
+    const uint8_t* d; int w, h, pitch;
+    int rc = plvs_orb_pyramid_level(o, frame, level, blurred, &d, &w, &h, &pitch);
+    if (rc) return rc;
+    if (!host || host_stride < w) { set_error("bad host buffer"); return PLVS_EINVAL; }
+    std::lock_guard<std::mutex> lock(o->mu);
+    PLVS_CUDA(cudaSetDevice(o->device));
+    PLVS_CUDA(cudaMemcpy2DAsync(host, host_stride, d, pitch, w, h, cudaMemcpyDeviceToHost, o->stream));
+    PLVS_CUDA(cudaStreamSynchronize(o->stream));
+    return PLVS_OK;
+}
+
+int plvs_orb_device_result(const plvs_orb* o, int frame, plvs_orb_device_view* out)
+{
+    if (!o || !out || frame < 0 || frame >= o->last_batch) { set_error("bad frame"); return PLVS_EINVAL; }
+    if (o->lapped[frame]) { set_error("device view unavailable: keypoints were reordered by the lapping area"); return PLVS_ESTATE; }
+    out->n = o->n_kp[frame];
+    out->keys = o->d_kp.p + (size_t)frame * o->sel_cap;
+    out->desc = o->d_desc.p + (size_t)frame * o->sel_cap * 32;
+    return PLVS_OK;
+}
+
+int plvs_orb_candidates(const plvs_orb* o, int frame, int level, int32_t* x, int32_t* y, int32_t* score, int cap, int* n_out)
+{
+    if (!o || !n_out || frame < 0 || frame >= o->last_batch || level < 0 || level >= o->prm.nlevels) { set_error("bad frame/level"); return PLVS_EINVAL; }
+    const int nl = o->prm.nlevels;
+    const int n = o->p_cand_count.h[frame * nl + level];
+    *n_out = n;
+    if (n > cap) { set_error("candidate capacity too small"); return PLVS_ECAP; }
+    const uint32_t* c = o->p_cand.h + (size_t)frame * o->slots_per_frame + o->lv[level].slot_begin;
+    for (int i = 0; i < n; ++i) {
+        if (x) x[i] = unpack_x(c[i]);
+        if (y) y[i] = unpack_y(c[i]);
+        if (score) score[i] = unpack_s(c[i]);
+    }
+    return PLVS_OK;
+}
+
+int plvs_orb_last_stats(const plvs_orb* o, plvs_orb_stats* out)
+{
+    if (!o || !out) return PLVS_EINVAL;
+    *out = o->stats;
+    return PLVS_OK;
+}
+
+}  // extern "C"

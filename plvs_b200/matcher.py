@@ -1,0 +1,142 @@
+"""Host-side mirror of PLVS2::ORBmatcher for the hot-path overloads (reference:
+include/ORBmatcher.h:61-97, src/ORBmatcher.cc).  Frames are flat views (numpy arrays) instead of
+the pointer-rich Frame/KeyFrame/MapPoint graph; the C++ shim (shim/) does the same gather from the
+reference's objects.  Everything runs through the C ABI of libplvs_b200.so."""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from .orb import KP_DTYPE
+
+MP_QUERY = np.dtype([("proj_x", "f4"), ("proj_y", "f4"), ("proj_xr", "f4"), ("track_depth", "f4"), ("view_cos", "f4"),
+                     ("level", "i4"), ("flags", "u4"), ("desc", "u1", 32)])
+LAST_QUERY = np.dtype([("u", "f4"), ("v", "f4"), ("invz", "f4"), ("last_octave", "i4"), ("angle", "f4"),
+                       ("flags", "u4"), ("desc", "u1", 32)])
+assert MP_QUERY.itemsize == 60 and LAST_QUERY.itemsize == 56
+Q_OBS_POSITIVE = 1
+FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48
+
+
+class Frame:
+    """The Frame/KeyFrame members the matchers read (RGB-D, Nleft == -1)."""
+
+    def __init__(self, keys, desc, width, height, scale_factors, level_sigma2=None, uright=None, bf=40.0,
+                 bounds=None, device_ptrs=None):
+        self.keys = np.ascontiguousarray(keys, KP_DTYPE) if keys is not None else None
+        self.desc = np.ascontiguousarray(desc, np.uint8) if desc is not None else None
+        self.uright = None if uright is None else np.ascontiguousarray(uright, np.float32)
+        self.n = len(self.keys) if device_ptrs is None else device_ptrs[0]
+        self.device_ptrs = device_ptrs          # (n, keys_ptr, desc_ptr, uright_ptr|0)
+        self.scale_factors = np.asarray(scale_factors, np.float32)
+        self.level_sigma2 = np.asarray(level_sigma2 if level_sigma2 is not None else self.scale_factors ** 2, np.float32)
+        # Frame::ComputeImageBounds without distortion (src/Frame.cc:1770-1776)
+        self.min_x, self.min_y, self.max_x, self.max_y = bounds or (0.0, 0.0, float(width), float(height))
+        self.grid_inv_w = np.float32(FRAME_GRID_COLS) / np.float32(np.float32(self.max_x) - np.float32(self.min_x))
+        self.grid_inv_h = np.float32(FRAME_GRID_ROWS) / np.float32(np.float32(self.max_y) - np.float32(self.min_y))
+        self.bf = bf
+
+    def view(self):
+        v = _lib.FrameView()
+        v.n = self.n
+        if self.device_ptrs is not None:
+            v.keys, v.desc, v.uright = self.device_ptrs[1], self.device_ptrs[2], self.device_ptrs[3] or None
+            v.on_device = 1
+        else:
+            v.keys = self.keys.ctypes.data
+            v.desc = self.desc.ctypes.data
+            v.uright = self.uright.ctypes.data if self.uright is not None else None
+            v.on_device = 0
+        v.min_x, v.min_y, v.max_x, v.max_y = self.min_x, self.min_y, self.max_x, self.max_y
+        v.grid_inv_w, v.grid_inv_h = float(self.grid_inv_w), float(self.grid_inv_h)
+        nl = len(self.scale_factors)
+        for i in range(nl):
+            v.scale_factors[i] = float(self.scale_factors[i])
+            v.level_sigma2[i] = float(self.level_sigma2[i])
+        v.nlevels = nl
+        v.bf = self.bf
+        return v
+
+
+def featvec(node_of_feature):
+    """Flatten a per-feature node id array into the CSR form of DBoW2::FeatureVector
+    (std::map<NodeId, std::vector<unsigned>>: nodes ascending, features ascending inside a node)."""
+    node = np.asarray(node_of_feature, np.int64)
+    valid = np.nonzero(node >= 0)[0]
+    order = valid[np.argsort(node[valid], kind="stable")]
+    ids, counts = np.unique(node[order], return_counts=True)
+    offsets = np.zeros(len(ids) + 1, np.int32)
+    offsets[1:] = np.cumsum(counts)
+    return ids.astype(np.uint32), offsets, order.astype(np.int32)
+
+
+def featvec_struct(fv):
+    s = _lib.FeatVec()
+    s.n_nodes = len(fv[0])
+    s.node_ids, s.offsets, s.features = fv[0].ctypes.data, fv[1].ctypes.data, fv[2].ctypes.data
+    return s
+
+
+class ORBmatcher:
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 12
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self._lib = _lib.load()
+        self.mfNNratio, self.mbCheckOrientation = nnratio, checkOri
+        self._h = C.c_void_p()
+        _lib.check(self._lib.plvs_match_create(device, C.byref(self._h)), "plvs_match_create")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.plvs_match_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @staticmethod
+    def DescriptorDistance(a, b):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        return _lib.load().plvs_hamming256(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+
+    def SearchByProjectionMap(self, F, queries, th=3.0, bFarPoints=False, thFarPoints=50.0, claimed=None):
+        """SearchByProjection(Frame&, vector<MapPointPtr>&, th, bFarPoints, thFarPoints) -> (nmatches, assign[N])."""
+        q = np.ascontiguousarray(queries, MP_QUERY)
+        assign = np.full(max(F.n, 1), -1, np.int32)
+        nm = C.c_int()
+        v = F.view()
+        cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+        rc = self._lib.plvs_match_projection_map(self._h, C.byref(v), q.ctypes.data_as(C.c_void_p), len(q), C.c_float(th),
+                                                 C.c_float(self.mfNNratio), int(bFarPoints), C.c_float(thFarPoints),
+                                                 cl.ctypes.data_as(C.c_void_p) if cl is not None else None,
+                                                 assign.ctypes.data_as(C.c_void_p), C.byref(nm))
+        _lib.check(rc, "plvs_match_projection_map")
+        return nm.value, assign[:F.n]
+
+    def SearchByProjectionLast(self, Cur, queries, th, bForward=False, bBackward=False, claimed=None):
+        """SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) with the last-frame points pre-projected."""
+        q = np.ascontiguousarray(queries, LAST_QUERY)
+        assign = np.full(max(Cur.n, 1), -1, np.int32)
+        nm = C.c_int()
+        v = Cur.view()
+        cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+        rc = self._lib.plvs_match_projection_last(self._h, C.byref(v), q.ctypes.data_as(C.c_void_p), len(q), C.c_float(th),
+                                                  int(bForward), int(bBackward), int(self.mbCheckOrientation),
+                                                  cl.ctypes.data_as(C.c_void_p) if cl is not None else None,
+                                                  assign.ctypes.data_as(C.c_void_p), C.byref(nm))
+        _lib.check(rc, "plvs_match_projection_last")
+        return nm.value, assign[:Cur.n]
+
+    def SearchForTriangulation(self, KF1, KF2, fv1, fv2, has_mp1, has_mp2, F12, ep, bOnlyStereo=False, bCoarse=False):
+        """-> (nmatches, vMatches12[N1]); vMatchedPairs = [(i, m) for i, m in enumerate(vMatches12) if m >= 0]."""
+        m12 = np.full(max(KF1.n, 1), -1, np.int32)
+        nm = C.c_int()
+        v1, v2 = KF1.view(), KF2.view()
+        s1, s2 = featvec_struct(fv1), featvec_struct(fv2)
+        h1 = np.ascontiguousarray(has_mp1, np.uint8); h2 = np.ascontiguousarray(has_mp2, np.uint8)
+        F = np.ascontiguousarray(F12, np.float32).reshape(9); e = np.ascontiguousarray(ep, np.float32)
+        rc = self._lib.plvs_match_triangulation(self._h, C.byref(v1), C.byref(v2), C.byref(s1), C.byref(s2),
+                                                h1.ctypes.data_as(C.c_void_p), h2.ctypes.data_as(C.c_void_p),
+                                                F.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p),
+                                                int(bOnlyStereo), int(bCoarse), int(self.mbCheckOrientation),
+                                                m12.ctypes.data_as(C.c_void_p), C.byref(nm))
+        _lib.check(rc, "plvs_match_triangulation")
+        return nm.value, m12[:KF1.n]

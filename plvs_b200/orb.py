@@ -1,0 +1,105 @@
+"""Host-side mirror of PLVS2::ORBextractor (reference: include/ORBextractor.h:59-170).
+
+Same constructor arguments, same call semantics (``__call__`` == ``operator()``: returns the
+mono index, fills keypoints + descriptors, honours vLappingArea, returns -1 on an empty image)
+and the same getters, on top of the C ABI of libplvs_b200.so.  Used by tests/bench; the C++ shim in
+shim/ is the drop-in for the reference's C++ callers.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+
+KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"),
+                     ("octave", "i4"), ("class_id", "i4")])
+assert KP_DTYPE.itemsize == C.sizeof(_lib.Keypoint) == 28
+
+
+class ORBextractor:
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0):
+        self._lib = _lib.load()
+        self.nfeatures, self.scaleFactor, self.nlevels = nfeatures, scaleFactor, nlevels
+        self.iniThFAST, self.minThFAST = iniThFAST, minThFAST
+        prm = _lib.OrbParams(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.plvs_orb_create(C.byref(prm), device, C.byref(self._h)), "plvs_orb_create")
+        self._cap = max(2 * nfeatures + 64 * nlevels, 256)
+        t = [np.zeros(nlevels, np.float32) for _ in range(4)] + [np.zeros(nlevels, np.int32)]
+        _lib.check(self._lib.plvs_orb_tables(self._h, *[a.ctypes.data_as(C.c_void_p) for a in t]), "plvs_orb_tables")
+        self.mvScaleFactor, self.mvInvScaleFactor, self.mvLevelSigma2, self.mvInvLevelSigma2, self.mnFeaturesPerLevel = t
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.plvs_orb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # getters (include/ORBextractor.h:90-113)
+    def GetLevels(self): return self.nlevels
+    def GetScaleFactor(self): return self.scaleFactor
+    def GetScaleFactors(self): return self.mvScaleFactor.copy()
+    def GetInverseScaleFactors(self): return self.mvInvScaleFactor.copy()
+    def GetScaleSigmaSquares(self): return self.mvLevelSigma2.copy()
+    def GetInverseScaleSigmaSquares(self): return self.mvInvLevelSigma2.copy()
+
+    def __call__(self, image, mask=None, vLappingArea=(0, 0)):
+        """operator()(image, mask /*ignored*/, keypoints, descriptors, vLappingArea).
+        Returns (monoIndex, keypoints[KP_DTYPE], descriptors[n,32])."""
+        if image is None or image.size == 0:
+            return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        mono, kps, desc = self.extract_batch(image[None], vLappingArea)
+        return mono[0], kps[0], desc[0]
+
+    def extract_batch(self, images, vLappingArea=(0, 0), pinned_out=None):
+        """images: (B,H,W) uint8 host array (or a (ptr, B, H, W, stride, frame_stride) device tuple)."""
+        on_device = isinstance(images, tuple)
+        if on_device:
+            ptr, B, H, W, stride, fstride = images
+        else:
+            assert images.dtype == np.uint8 and images.ndim == 3
+            images = np.ascontiguousarray(images)
+            B, H, W = images.shape
+            ptr, stride, fstride = images.ctypes.data, images.strides[1], images.strides[0]
+        cap = self._cap
+        if pinned_out is not None:
+            kps, desc = pinned_out
+        else:
+            kps = np.empty((B, cap), KP_DTYPE)
+            desc = np.empty((B, cap, 32), np.uint8)
+        n = np.zeros(B, np.int32)
+        mono = np.zeros(B, np.int32)
+        rc = self._lib.plvs_orb_extract_batch(self._h, B, C.c_void_p(ptr), W, H, stride, fstride, int(on_device),
+                                              int(vLappingArea[0]), int(vLappingArea[1]),
+                                              kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), cap,
+                                              n.ctypes.data_as(C.c_void_p), mono.ctypes.data_as(C.c_void_p))
+        _lib.check(rc, "plvs_orb_extract_batch")
+        return mono, [kps[b, :n[b]] for b in range(B)], [desc[b, :n[b]] for b in range(B)]
+
+    def pyramid_level(self, level, blurred=False, frame=0):
+        """Host copy of mvImagePyramid[level] / mvImagePyramidFiltered[level] of the last extract."""
+        w, h, pitch, dptr = C.c_int(), C.c_int(), C.c_int(), C.c_void_p()
+        _lib.check(self._lib.plvs_orb_pyramid_level(self._h, frame, level, int(blurred), C.byref(dptr), C.byref(w), C.byref(h), C.byref(pitch)),
+                   "plvs_orb_pyramid_level")
+        out = np.empty((h.value, w.value), np.uint8)
+        _lib.check(self._lib.plvs_orb_download_level(self._h, frame, level, int(blurred), out.ctypes.data_as(C.c_void_p), out.strides[0]),
+                   "plvs_orb_download_level")
+        return out
+
+    def candidates(self, level, frame=0, cap=1 << 20):
+        """FAST candidates of one level in DistributeOctTree input order: (x, y, score) int32 arrays."""
+        x, y, s = (np.empty(cap, np.int32) for _ in range(3))
+        n = C.c_int()
+        _lib.check(self._lib.plvs_orb_candidates(self._h, frame, level, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
+                                                 s.ctypes.data_as(C.c_void_p), cap, C.byref(n)), "plvs_orb_candidates")
+        return x[:n.value].copy(), y[:n.value].copy(), s[:n.value].copy()
+
+    def device_result(self, frame=0):
+        v = _lib.OrbDeviceView()
+        _lib.check(self._lib.plvs_orb_device_result(self._h, frame, C.byref(v)), "plvs_orb_device_result")
+        return v
+
+    def last_stats(self):
+        s = _lib.OrbStats()
+        _lib.check(self._lib.plvs_orb_last_stats(self._h, C.byref(s)), "plvs_orb_last_stats")
+        return dict(pyramid_pixels=s.pyramid_pixels, candidates=s.candidates, keypoints=s.keypoints, kernel_launches=s.kernel_launches)

@@ -1,0 +1,95 @@
+"""Host-side mirror of chisel_server::ChiselServer's depth-scan integration as PLVS drives it through
+PointCloudMapChisel (reference: Thirdparty/chisel_server/include/chisel_server/ChiselServer.h:81-322,
+src/PointCloudMapChisel.cc:46-225), on top of the C ABI of libplvs_b200.so."""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+
+SCAN, SCAN_COLOR = 0, 1
+
+
+def default_params(**kw):
+    """ChiselServerParams() defaults (ChiselServer.cpp:44-69) overridden the way PointCloudMapChisel does."""
+    lib = _lib.load()
+    p = _lib.TsdfParams()
+    lib.plvs_tsdf_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class ChiselServer:
+    def __init__(self, params=None, device=0, **kw):
+        self._lib = _lib.load()
+        self.params = params or default_params(**kw)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.plvs_tsdf_create(C.byref(self.params), device, C.byref(self._h)), "plvs_tsdf_create")
+        self._pose = None
+        self._depth = None
+        self._color = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.plvs_tsdf_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def Reset(self):
+        _lib.check(self._lib.plvs_tsdf_reset(self._h), "plvs_tsdf_reset")
+
+    def SetDepthCameraInfo(self, fx, fy, cx, cy, width, height):
+        _lib.check(self._lib.plvs_tsdf_set_camera(self._h, C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy), width, height),
+                   "plvs_tsdf_set_camera")
+
+    SetColorCameraInfo = SetDepthCameraInfo      # one camera model (IntegrateDepthScanColorWithOneCameraModelBGR)
+
+    def SetDepthPose(self, Twc):
+        self._pose = np.ascontiguousarray(Twc, np.float32).reshape(12)
+
+    SetColorPose = SetDepthPose
+
+    def SetDepthImageMemorySharing(self, depth):
+        self._depth = np.ascontiguousarray(depth, np.float32)
+
+    def SetColorImageMemorySharing(self, bgr):
+        self._color = np.ascontiguousarray(bgr, np.uint8)
+
+    def IntegrateLastDepthImage(self, updateMesh=False):
+        if self._pose is None or self._depth is None:
+            raise _lib.PlvsError("ChiselServer - PROBLEM in integrating depth scan (no pose / depth)")
+        use_color = bool(self.params.use_color) and self._color is not None
+        h, w = self._depth.shape
+        bgr = self._color if use_color else None
+        rc = self._lib.plvs_tsdf_integrate_depth(self._h, self._depth.ctypes.data_as(C.c_void_p), w, h,
+                                                 bgr.ctypes.data_as(C.c_void_p) if use_color else None,
+                                                 bgr.strides[0] if use_color else 0, bgr.shape[2] if use_color else 0,
+                                                 self._pose.ctypes.data_as(C.c_void_p), SCAN_COLOR if use_color else SCAN, 0)
+        _lib.check(rc, "plvs_tsdf_integrate_depth")
+
+    def integrate(self, depth, Twc, bgr=None):
+        self.SetDepthPose(Twc)
+        self.SetDepthImageMemorySharing(depth)
+        self._color = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
+        self.IntegrateLastDepthImage(False)
+
+    def stats(self):
+        s = _lib.TsdfStats()
+        _lib.check(self._lib.plvs_tsdf_last_stats(self._h, C.byref(s)), "plvs_tsdf_last_stats")
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    def download(self):
+        """-> keys[n,3] (sorted lexicographically), sdf[n,4096], weight[n,4096], rgba[n,4096,4]"""
+        n = C.c_int()
+        _lib.check(self._lib.plvs_tsdf_download_blocks(self._h, None, None, None, None, 0, C.byref(n)), "plvs_tsdf_download_blocks")
+        n = n.value
+        keys = np.zeros((n, 3), np.int32); sdf = np.zeros((n, 4096), np.float32); w = np.zeros((n, 4096), np.float32)
+        rgba = np.zeros((n, 4096, 4), np.uint8)
+        m = C.c_int()
+        if n:
+            _lib.check(self._lib.plvs_tsdf_download_blocks(self._h, keys.ctypes.data_as(C.c_void_p), sdf.ctypes.data_as(C.c_void_p),
+                                                           w.ctypes.data_as(C.c_void_p), rgba.ctypes.data_as(C.c_void_p), n, C.byref(m)),
+                       "plvs_tsdf_download_blocks")
+        order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))
+        return keys[order], sdf[order], w[order], rgba[order]

@@ -1,0 +1,129 @@
+"""-m gpu: the three ORBmatcher searches on the GPU against the sequential CPU oracle (bit-exact pairs)."""
+import numpy as np
+import pytest
+
+from plvs_b200 import synth, scenario
+from plvs_b200.orb import ORBextractor
+from plvs_b200.matcher import ORBmatcher, Frame, featvec, MP_QUERY, LAST_QUERY
+from oracle import match as OM
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def frames(gpu):
+    ex = ORBextractor(2000, 1.2, 8, 20, 7)
+    K = synth.intrinsics(640, 480)
+    out = []
+    for f in (10, 11, 15):
+        mono, kp, desc = ex(synth.gray_frame(f))
+        fr = scenario.make_frame(kp, desc, synth.depth_frame(f), K, ex.GetScaleFactors())
+        fr.level_sigma2 = ex.GetScaleSigmaSquares()
+        out.append((fr, synth.pose(f)))
+    return K, out
+
+
+def test_hamming_helper(gpu):
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (200, 32), dtype=np.uint8); b = rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    for i in range(200):
+        assert ORBmatcher.DescriptorDistance(a[i], b[i]) == int(np.unpackbits(a[i] ^ b[i]).sum())
+
+
+@pytest.mark.parametrize("th", [1.0, 3.0, 5.0, 15.0])
+def test_projection_map(frames, th):
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    q, _ = scenario.map_queries(last, cur, K, Tl, Tc)
+    m = ORBmatcher(0.8, True)
+    n, assign = m.SearchByProjectionMap(cur, q, th)
+    on, oassign = OM.search_by_projection_map(cur, q, th, 0.8)
+    assert on == n and np.array_equal(assign, oassign)
+    if th >= 3:
+        assert n > 200
+
+
+def test_projection_map_claims_and_far(frames):
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    q, _ = scenario.map_queries(last, cur, K, Tl, Tc, seed=3)
+    rng = np.random.default_rng(1)
+    claimed = (rng.random(cur.n) < 0.3).astype(np.uint8)
+    q["flags"] = (rng.random(len(q)) < 0.9).astype(np.uint32)          # some map points without observations
+    # duplicate queries => heavy competition for the same keypoints (sequential claims matter)
+    q = np.concatenate([q, q[::2], q[::3]])
+    m = ORBmatcher(0.8, True)
+    n, assign = m.SearchByProjectionMap(cur, q, 5.0, True, 3.0, claimed)
+    on, oassign = OM.search_by_projection_map(cur, q, 5.0, 0.8, True, 3.0, claimed)
+    assert on == n and np.array_equal(assign, oassign)
+
+
+@pytest.mark.parametrize("th,fwd,bwd", [(15.0, False, False), (7.0, False, False), (15.0, True, False), (15.0, False, True)])
+def test_projection_last(frames, th, fwd, bwd):
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    q, _ = scenario.last_queries(last, cur, K, Tl, Tc)
+    for check in (True, False):
+        m = ORBmatcher(0.9, check)
+        n, assign = m.SearchByProjectionLast(cur, q, th, fwd, bwd)
+        on, oassign = OM.search_by_projection_last(cur, q, th, fwd, bwd, check)
+        assert on == n and np.array_equal(assign, oassign)
+    if not fwd:
+        assert n > 300
+
+
+def test_projection_last_competition(frames):
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    q, _ = scenario.last_queries(last, cur, K, Tl, Tc)
+    q = np.concatenate([q, q[::2]])
+    rng = np.random.default_rng(2)
+    q["flags"] = (rng.random(len(q)) < 0.8).astype(np.uint32)
+    m = ORBmatcher(0.9, True)
+    n, assign = m.SearchByProjectionLast(cur, q, 15.0)
+    on, oassign = OM.search_by_projection_last(cur, q, 15.0)
+    assert on == n and np.array_equal(assign, oassign)
+
+
+@pytest.mark.parametrize("coarse,only_stereo", [(False, False), (True, False), (False, True)])
+def test_triangulation(frames, coarse, only_stereo):
+    K, fr = frames
+    (k1, T1), (k2, T2) = fr[0], fr[2]
+    fv1, fv2 = featvec(scenario.node_ids(k1.desc, 128)), featvec(scenario.node_ids(k2.desc, 128))
+    rng = np.random.default_rng(4)
+    has1 = (rng.random(k1.n) < 0.4).astype(np.uint8); has2 = (rng.random(k2.n) < 0.4).astype(np.uint8)
+    F12, ep = scenario.fundamental(K, T1, T2)
+    for check in (True, False):
+        m = ORBmatcher(0.6, check)
+        n, m12 = m.SearchForTriangulation(k1, k2, fv1, fv2, has1, has2, F12, ep, only_stereo, coarse)
+        on, om12 = OM.search_for_triangulation(k1, k2, fv1, fv2, has1, has2, F12, ep, only_stereo, coarse, check)
+        assert on == n and np.array_equal(m12, om12)
+    if coarse:
+        assert n > 20
+
+
+def test_match_empty_inputs(frames):
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    m = ORBmatcher(0.8, True)
+    n, assign = m.SearchByProjectionMap(cur, np.zeros(0, MP_QUERY), 3.0)
+    assert n == 0 and (assign == -1).all()
+    n, assign = m.SearchByProjectionLast(cur, np.zeros(0, LAST_QUERY), 15.0)
+    assert n == 0 and (assign == -1).all()
+
+
+def test_match_device_resident_view(frames):
+    """extract -> match without a host round trip of keypoints/descriptors."""
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    ex = ORBextractor(2000, 1.2, 8, 20, 7)
+    mono, kp, desc = ex(synth.gray_frame(11))
+    assert np.array_equal(kp, cur.keys)
+    dv = ex.device_result(0)
+    dcur = Frame(None, None, K["w"], K["h"], ex.GetScaleFactors(), bf=K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0))
+    hcur = Frame(cur.keys, cur.desc, K["w"], K["h"], ex.GetScaleFactors(), bf=K["bf"])
+    q, _ = scenario.last_queries(last, cur, K, Tl, Tc)
+    m = ORBmatcher(0.9, True)
+    n, assign = m.SearchByProjectionLast(dcur, q, 15.0)
+    on, oassign = OM.search_by_projection_last(hcur, q, 15.0)
+    assert on == n and np.array_equal(assign, oassign)

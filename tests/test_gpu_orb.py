@@ -1,0 +1,108 @@
+"""-m gpu: the CUDA ORB extractor against the CPU oracle, stage by stage and end to end (bit-exact)."""
+import numpy as np
+import pytest
+
+from plvs_b200 import synth
+from plvs_b200.orb import ORBextractor
+from oracle import orb as O
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("x", "y", "size", "angle", "response", "octave", "class_id")
+
+
+def _compare(img, nfeat, ex=None, lap=(0, 0)):
+    ex = ex or ORBextractor(nfeat, 1.2, 8, 20, 7)
+    mono, kp, desc = ex(img, None, lap)
+    okp, odesc, omono, ncand, internals = O.extract_cv2(img, nfeat, lapping=lap, return_internals=True, angle_impl="c")
+    for l in range(8):
+        assert np.array_equal(ex.pyramid_level(l), internals["pyramid"][l]), f"pyramid level {l}"
+        if internals["blurred"][l] is not None:
+            assert np.array_equal(ex.pyramid_level(l, blurred=True), internals["blurred"][l]), f"blur level {l}"
+    for l in range(8):
+        cx, cy, cs = ex.candidates(l)
+        ox, oy, orr = internals["candidates"][l]
+        if not (len(cx) == len(ox) and np.array_equal(cx - 16, ox.astype(np.int32)) and np.array_equal(cy - 16, oy.astype(np.int32))
+                and np.array_equal(cs, orr.astype(np.int32))):
+            import collections
+            msg = f"level {l}: gpu {len(cx)} vs oracle {len(ox)} candidates"
+            gs = set(zip((cx - 16).tolist(), (cy - 16).tolist(), cs.tolist())); os_ = set(zip(ox.astype(int).tolist(), oy.astype(int).tolist(), orr.astype(int).tolist()))
+            msg += f"; only-gpu {sorted(gs - os_)[:12]} only-oracle {sorted(os_ - gs)[:12]} n_only_gpu {len(gs-os_)} n_only_oracle {len(os_-gs)}"
+            raise AssertionError(msg)
+    assert ex.last_stats()["candidates"] == ncand
+    assert len(kp) == len(okp)
+    for f in FIELDS:
+        assert np.array_equal(kp[f], okp[f]), f"keypoint field {f}"
+    assert np.array_equal(desc, odesc)
+    assert mono == omono
+    return len(kp)
+
+
+def test_orb_score_map(gpu, monkeypatch):
+    """inspection build (PLVS_ORB_DEBUG=1): FAST score map of every level vs the oracle's"""
+    monkeypatch.setenv("PLVS_ORB_DEBUG", "1")
+    img = synth.gray_frame(0)
+    ex = ORBextractor(2000, 1.2, 8, 20, 7)
+    ex(img)
+    tab = O.Tables(2000)
+    pyr = O.pyramid_cv2(img, tab)
+    for l in range(8):
+        got = ex.pyramid_level(l, blurred=2)
+        want = O.fast_score_map(pyr[l], 7)
+        h, w = want.shape
+        bad = np.argwhere(got[19:h - 19, 19:w - 19] != want[19:h - 19, 19:w - 19])
+        assert len(bad) == 0, f"level {l}: {len(bad)} score mismatches, first {bad[:5] + 19}, got {[int(got[y + 19, x + 19]) for y, x in bad[:5]]} want {[int(want[y + 19, x + 19]) for y, x in bad[:5]]}"
+
+
+def test_orb_vga_2000(gpu):
+    assert _compare(synth.gray_frame(0), 2000) > 1500
+
+
+def test_orb_vga_1000_frames(gpu):
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    for f in (1, 7):
+        _compare(synth.gray_frame(f), 1000, ex)
+
+
+def test_orb_lapping_area(gpu):
+    _compare(synth.gray_frame(3), 1000, lap=(200, 400))
+
+
+def test_orb_low_texture_fallback(gpu):
+    # smooth image: almost every cell needs the minThFAST pass, many cells stay empty
+    img = (synth.gray_frame(2).astype(np.float32) * 0.15 + 100).astype(np.uint8)
+    _compare(img, 1000)
+
+
+def test_orb_flat_and_empty(gpu):
+    ex = ORBextractor(500, 1.2, 8, 20, 7)
+    mono, kp, desc = ex(np.full((480, 640), 127, np.uint8))
+    assert mono == 0 and len(kp) == 0
+    assert ex(np.zeros((0, 0), np.uint8))[0] == -1
+
+
+def test_orb_odd_sizes(gpu):
+    rng = np.random.default_rng(5)
+    for (w, h) in ((752, 480), (333, 257)):
+        img = synth.gray_frame(0, 1024, 768)[:h, :w].copy()
+        _compare(img, 1200)
+
+
+def test_orb_batch_matches_single(gpu):
+    ex = ORBextractor(2000, 1.2, 8, 20, 7)
+    imgs = np.stack([synth.gray_frame(f) for f in range(4)])
+    mono, kps, descs = ex.extract_batch(imgs)
+    for b in range(4):
+        m1, k1, d1 = ORBextractor(2000, 1.2, 8, 20, 7)(imgs[b])
+        assert m1 == mono[b] and np.array_equal(k1, kps[b]) and np.array_equal(d1, descs[b])
+
+
+def test_orb_1080p(gpu):
+    img = synth.gray_frame(0, 1920, 1080)
+    ex = ORBextractor(4000, 1.2, 8, 20, 7)
+    mono, kp, desc = ex(img)
+    okp, odesc, omono, ncand = O.extract_port(img, 4000)
+    assert len(kp) == len(okp) and mono == omono
+    for f in FIELDS:
+        assert np.array_equal(kp[f], okp[f]), f
+    assert np.array_equal(desc, odesc)

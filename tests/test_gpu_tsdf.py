@@ -1,0 +1,109 @@
+"""-m gpu: TSDF voxel-block integration on the GPU vs the brute-force CPU oracle.
+Tolerance from north_star: |sdf|,|weight| within 1e-4, identical chunk-key sets (the CUDA path
+follows the oracle's operation order, so in practice the arrays are bit-identical)."""
+import numpy as np
+import pytest
+
+from plvs_b200 import synth, tsdf as T
+from oracle import tsdf as OT
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _pair(w, h, **kw):
+    K = synth.intrinsics(w, h)
+    p = T.default_params(**kw)
+    g = T.ChiselServer(p)
+    g.SetDepthCameraInfo(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
+    o = OT.Map(p, threads=8)
+    o.set_camera(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
+    return g, o
+
+
+def _check(g, o, color=False):
+    gk, gs, gw, gc = g.download()
+    ok, os_, ow, oc = o.download()
+    assert gk.shape == ok.shape and np.array_equal(gk, ok), f"chunk key sets differ: {len(gk)} vs {len(ok)}"
+    assert np.abs(gw - ow).max() <= TOL
+    known = ow > 0
+    assert np.abs(gs[known] - os_[known]).max() <= TOL
+    assert np.array_equal(gs[~known], os_[~known])          # untouched voxels keep the 99999 sentinel
+    if color:
+        assert np.array_equal(gc, oc)
+    so, sg = o.stats(), g.stats()
+    for f in ("n_blocks", "n_range", "n_updated", "n_new"):
+        assert so[f] == sg[f], (f, so, sg)
+    return len(gk)
+
+
+@pytest.mark.parametrize("carve", [1, 0])
+def test_scan_sequence(gpu, carve):
+    g, o = _pair(160, 120, voxel_resolution=0.04, use_carving=carve, near_plane=0.1, far_plane=4.0, max_blocks=4096, use_color=0)
+    for f in (0, 1, 2, 9):
+        d = synth.depth_frame(f, 160, 120)
+        g.integrate(d, synth.pose(f)); o.integrate(d, synth.pose(f))
+        n = _check(g, o)
+    assert n > 50
+
+
+def test_scan_color_sequence(gpu):
+    g, o = _pair(160, 120, voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=4096, use_color=1)
+    for f in (0, 1, 2, 3, 4, 5, 6):
+        d, c = synth.depth_frame(f, 160, 120), synth.bgr_frame(f, 160, 120)
+        g.integrate(d, synth.pose(f), c); o.integrate(d, synth.pose(f), c)
+        _check(g, o, color=True)
+
+
+def test_carving_moves_surface(gpu):
+    """a wall that jumps back by 1 m: voxels in front of the new surface get carved / reset"""
+    for color in (False, True):
+        g, o = _pair(128, 96, voxel_resolution=0.05, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=4096, use_color=int(color))
+        Twc = np.eye(4, dtype=np.float32)[:3]
+        for depth_m in (1.5, 1.5, 2.5, 2.5):
+            d = np.full((96, 128), depth_m, np.float32)
+            c = np.full((96, 128, 3), 90, np.uint8) if color else None
+            g.integrate(d, Twc, c); o.integrate(d, Twc, c)
+            _check(g, o, color)
+
+
+def test_nan_zero_and_rotated_pose(gpu):
+    g, o = _pair(160, 120, voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=8192, use_color=0)
+    rng = np.random.default_rng(0)
+    d = synth.depth_frame(4, 160, 120)
+    d[rng.random(d.shape) < 0.05] = np.nan
+    d[:10] = 0.0
+    a = 0.6
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0.1, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    R, _ = np.linalg.qr(R)
+    Twc = np.concatenate([R, [[0.2], [-0.1], [0.3]]], 1).astype(np.float32)
+    g.integrate(d, Twc); o.integrate(d, Twc)
+    _check(g, o)
+
+
+def test_vga_1cm_single_scan(gpu):
+    """BASELINE config 2 geometry (640x480, 1 cm voxels): one scan, depth clipped to 2 m to bound the oracle's brute force"""
+    g, o = _pair(640, 480, voxel_resolution=0.01, use_carving=1, near_plane=0.1, far_plane=2.2, max_blocks=16384, use_color=1)
+    d = synth.depth_frame(0)
+    d[d > 2.0] = 0.0
+    c = synth.bgr_frame(0)
+    g.integrate(d, synth.pose(0), c); o.integrate(d, synth.pose(0), c)
+    n = _check(g, o, color=True)
+    assert n > 300
+    s = g.stats()
+    assert s["n_candidates"] < 0.5 * s["n_range"]          # the screen-space cull actually prunes
+
+
+def test_reset_and_errors(gpu):
+    g, o = _pair(160, 120, voxel_resolution=0.04, max_blocks=4096, use_color=0)
+    g.integrate(synth.depth_frame(0, 160, 120), synth.pose(0))
+    assert g.stats()["n_blocks"] > 0
+    g.Reset()
+    assert len(g.download()[0]) == 0
+    with pytest.raises(Exception):
+        T.ChiselServer(T.default_params()).integrate(synth.depth_frame(0, 160, 120), synth.pose(0))     # no camera info
+    small = T.ChiselServer(T.default_params(voxel_resolution=0.04, max_blocks=16, use_color=0))
+    K = synth.intrinsics(160, 120)
+    small.SetDepthCameraInfo(K["fx"], K["fy"], K["cx"], K["cy"], 160, 120)
+    with pytest.raises(Exception):
+        small.integrate(synth.depth_frame(0, 160, 120), synth.pose(0))                                  # pool exhausted is reported, not silent
