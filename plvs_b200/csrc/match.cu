@@ -161,7 +161,9 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
     if (active) active = cell_window(F.gp, px, py, radius, c0, c1, r0, r1);
     if (active) {
         const bool check = (minL > 0) || (maxL >= 0);
-        const uint4 a0 = *reinterpret_cast<const uint4*>(qd), a1 = *reinterpret_cast<const uint4*>(qd + 16);
+        // query records are 60/56-byte structs: the embedded descriptor is only 4-byte aligned
+        const uint32_t* qw = reinterpret_cast<const uint32_t*>(qd);
+        const uint4 a0 = make_uint4(qw[0], qw[1], qw[2], qw[3]), a1 = make_uint4(qw[4], qw[5], qw[6], qw[7]);
         uint32_t* out = cand + (size_t)q * cap;
         for (int ix = c0; ix <= c1; ++ix) {
             const int pbeg = cell_start[ix * GRID_ROWS + r0], pend = cell_start[ix * GRID_ROWS + r1 + 1];

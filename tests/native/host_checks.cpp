@@ -1,0 +1,34 @@
+// Host-side checks of product code that needs no GPU: the keypoint distributor (orb_distribute.hpp)
+// and the glibc sincosf port (libm_sincosf.cuh), exposed with C linkage for the CPU test-suite.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../../plvs_b200/csrc/orb_distribute.hpp"
+#include "../../plvs_b200/csrc/libm_sincosf.cuh"
+
+extern "C" {
+
+int chk_distribute(int n, const int* xs, const int* ys, const int* resp, int minX, int maxX, int minY, int maxY, int N, int* sel)
+{
+    plvs::orb::Distributor d;
+    std::vector<int> out;
+    d.run(n, xs, ys, resp, minX, maxX, minY, maxY, N, out);
+    for (size_t i = 0; i < out.size(); ++i) sel[i] = out[i];
+    return (int)out.size();
+}
+
+// sweep floats in [lo_bits, hi_bits] with the given stride; returns the number of (cos,sin) mismatches vs libm
+long chk_sincosf_sweep(uint32_t lo_bits, uint32_t hi_bits, uint32_t stride, float* first_bad)
+{
+    long bad = 0;
+    for (uint64_t b = lo_bits; b <= hi_bits; b += stride) {
+        uint32_t u = (uint32_t)b; float y; std::memcpy(&y, &u, 4);
+        float c, s; plvs::libm_sincosf(y, &c, &s);
+        const float lc = cosf(y), ls = sinf(y);
+        if (std::memcmp(&c, &lc, 4) || std::memcmp(&s, &ls, 4)) { if (!bad && first_bad) *first_bad = y; ++bad; }
+    }
+    return bad;
+}
+
+}

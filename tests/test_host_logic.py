@@ -1,0 +1,100 @@
+"""CPU: product host logic that needs no GPU -- the keypoint distributor against the list-based oracle, the glibc
+sincosf port against libm, and the C-ABI library (loads, exports every declared symbol, fails loudly without a GPU)."""
+import ctypes as C
+import numpy as np
+import pytest
+
+from oracle import orb as O
+from plvs_b200 import _lib, synth
+from tests.native_build import build_host_checks
+
+
+@pytest.fixture(scope="module")
+def host():
+    lib = C.CDLL(build_host_checks())
+    lib.chk_sincosf_sweep.restype = C.c_long
+    lib.chk_sincosf_sweep.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+    return lib
+
+
+def _distribute(host, xs, ys, rs, w, h, n_want):
+    xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32); rs = np.ascontiguousarray(rs, np.int32)
+    sel = np.empty(max(len(xs), 1), np.int32)
+    m = host.chk_distribute(len(xs), xs.ctypes.data_as(C.c_void_p), ys.ctypes.data_as(C.c_void_p), rs.ctypes.data_as(C.c_void_p),
+                            16, w - 16, 16, h - 16, n_want, sel.ctypes.data_as(C.c_void_p))
+    return sel[:m]
+
+
+def test_distributor_matches_list_oracle_on_fast_candidates(host):
+    for frame, (w, h), quotas in ((0, (640, 480), (434, 217, 60)), (3, (257, 193), (175, 87, 20)), (5, (179, 134), (122, 30, 400))):
+        img = synth.gray_frame(frame, w, h)
+        xs, ys, rs = O.fast_cells(img, 20, 7)
+        for n_want in quotas:
+            want = O.distribute_octree(xs, ys, rs, 16, w - 16, 16, h - 16, n_want)
+            got = _distribute(host, xs, ys, rs, w, h, n_want)
+            assert np.array_equal(got, want), (frame, w, h, n_want)
+
+
+def test_distributor_random_sets_ties_and_degenerate(host):
+    rng = np.random.default_rng(42)
+    for trial in range(60):
+        w, h = int(rng.integers(80, 700)), int(rng.integers(80, 500))
+        n = int(rng.integers(0, 3000))
+        xs = rng.integers(0, w - 32, n); ys = rng.integers(0, h - 32, n)
+        rs = rng.integers(7, 12 if trial % 2 else 200, n)        # few distinct responses => many ties
+        if trial % 7 == 0 and n:                                   # duplicates / clusters
+            xs[: n // 2] = xs[0]; ys[: n // 3] = ys[0]
+        n_want = int(rng.integers(1, 600))
+        want = O.distribute_octree(xs, ys, rs, 16, w - 16, 16, h - 16, n_want)
+        got = _distribute(host, xs, ys, rs, w, h, n_want)
+        assert np.array_equal(got, want), trial
+
+
+def test_distributor_tall_image_has_no_root(host):
+    # nIni == 0 when the ROI is more than twice as tall as wide: the reference returns nothing (src/ORBextractor.cc:617-622)
+    assert len(_distribute(host, [1, 2], [1, 2], [9, 9], 60, 200, 10)) == 0
+    assert len(O.distribute_octree([1, 2], [1, 2], [9, 9], 16, 44, 16, 184, 10)) == 0
+
+
+def test_sincosf_port_equals_libm_exhaustively(host):
+    """every float in [0, 6.4] (the steering angle range is [0, 2*pi]): 1.09e9 values, ~10 s"""
+    first = C.c_float()
+    hi = np.array([6.4], np.float32).view(np.uint32)[0]
+    bad = host.chk_sincosf_sweep(0, int(hi), 1, C.byref(first))
+    assert bad == 0, f"{bad} mismatches, first at {first.value!r}"
+
+
+def test_sincosf_port_sampled_up_to_100(host):
+    lo = np.array([6.4], np.float32).view(np.uint32)[0]; hi = np.array([100.0], np.float32).view(np.uint32)[0]
+    assert host.chk_sincosf_sweep(int(lo), int(hi), 97, None) == 0
+
+
+def test_abi_library_loads_and_exports_everything():
+    lib = _lib.load()
+    names = _lib.exported_symbols()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert b"sm_100a" in lib.plvs_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    lib = _lib.load()
+    if lib.plvs_device_count() > 0:
+        pytest.skip("a GPU is present")
+    from plvs_b200.orb import ORBextractor
+    from plvs_b200.matcher import ORBmatcher
+    from plvs_b200 import tsdf
+    for make in (lambda: ORBextractor(1000, 1.2, 8, 20, 7), lambda: ORBmatcher(0.8, True), lambda: tsdf.ChiselServer(tsdf.default_params())):
+        with pytest.raises(_lib.PlvsError, match="no CUDA device"):
+            make()
+
+
+def test_hamming_host_helper():
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (100, 32), dtype=np.uint8); b = rng.integers(0, 256, (100, 32), dtype=np.uint8)
+    lib = _lib.load()
+    for i in range(100):
+        assert lib.plvs_hamming256(a[i].ctypes.data_as(C.c_void_p), b[i].ctypes.data_as(C.c_void_p)) == int(np.unpackbits(a[i] ^ b[i]).sum())
+    z = np.zeros(32, np.uint8); o = np.full(32, 255, np.uint8)
+    assert lib.plvs_hamming256(z.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p)) == 256
