@@ -1,0 +1,302 @@
+#!/usr/bin/env python3
+"""bench.py -- frames/s of the PLVS per-frame hot path (ORB extract + Hamming match + Chisel TSDF) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one batch of `--batch` consecutive 640x480 RGB-D frames of a synthetic stream (BASELINE.json
+configs[1]: ORB nFeatures=2000 + Chisel TSDF 1 cm voxels); every frame is extracted, matched against the
+previous frame (SearchByProjection Cur<-Last), against its local map points (SearchByProjection F<-map),
+triangulation-searched against the previous frame and integrated into the TSDF.  One camera stream per
+rank (weak scaling, no collective on the data path).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import pathlib
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np
+
+METRIC = "frames/sec (extract+match+TSDF) 640x480 RGB-D"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--nfeatures", type=int, default=2000)
+    ap.add_argument("--voxel", type=float, default=0.01)
+    ap.add_argument("--far", type=float, default=5.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=2)
+    return ap.parse_args()
+
+
+def workload_config(a, extra=None):
+    c = {"workload": f"synthetic {a.width}x{a.height} RGB-D stream, ORB nFeatures={a.nfeatures} (8 levels, 1.2, FAST 20/7) + "
+                     f"SearchByProjection(Cur,Last) th=15 + SearchByProjection(F,map) th=3 + SearchForTriangulation + "
+                     f"Chisel TSDF {a.voxel * 100:g} cm voxels (colour depth-scan, carving on, planes 0.1-{a.far:g} m), every frame integrated",
+         "frames_per_step": a.batch, "streams_per_gpu": 1, "parallelism": f"1 camera stream per GPU x{a.gpus}"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restatement of the reference's CPU path) timed on this box's host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(a, frames, threads, generous):
+    """times the oracle on frames [1, frames] of stream 0; returns (frames/s, per-stage seconds per frame)"""
+    import cv2
+    from oracle import orb as O, match as OM, tsdf as OT
+    from plvs_b200 import synth, scenario, tsdf as T
+    from plvs_b200.matcher import featvec
+    cv2.setNumThreads(threads if generous else 1)
+    K = synth.intrinsics(a.width, a.height)
+    tab = O.Tables(a.nfeatures)
+    p = T.default_params(voxel_resolution=a.voxel, use_carving=1, near_plane=0.1, far_plane=a.far, max_blocks=1 << 20, use_color=1)
+    omap = OT.Map(p, threads=threads if generous else 1)
+    omap.set_camera(K["fx"], K["fy"], K["cx"], K["cy"], a.width, a.height)
+    t_ext = t_match = t_tsdf = 0.0
+    prev = None
+    for f in range(frames + 1):
+        img = synth.gray_frame(f, a.width, a.height); depth = synth.depth_frame(f, a.width, a.height); bgr = synth.bgr_frame(f, a.width, a.height)
+        t0 = time.perf_counter()
+        kp, desc, mono, _ = O.extract_cv2(img, a.nfeatures, angle_impl="c")
+        t1 = time.perf_counter()
+        cur = scenario.make_frame(kp, desc, depth, K, tab.scale); cur.level_sigma2 = tab.sigma2
+        if prev is not None:
+            ql, _ = scenario.last_queries(prev, cur, K, synth.pose(f - 1), synth.pose(f))
+            qm, _ = scenario.map_queries(prev, cur, K, synth.pose(f - 1), synth.pose(f), seed=f)
+            fv1, fv2 = featvec(scenario.node_ids(cur.desc)), featvec(scenario.node_ids(prev.desc))
+            F12, ep = scenario.fundamental(K, synth.pose(f), synth.pose(f - 1))
+            t2 = time.perf_counter()
+            n1, a1 = OM.search_by_projection_last(cur, ql, 15.0)
+            OM.search_by_projection_map(cur, qm, 3.0, 0.8, claimed=(a1 >= 0).astype(np.uint8))
+            OM.search_for_triangulation(cur, prev, fv1, fv2, np.zeros(cur.n, np.uint8), np.zeros(prev.n, np.uint8), F12, ep, check_ori=False)
+            t3 = time.perf_counter()
+            omap.integrate(depth, synth.pose(f), bgr)
+            t4 = time.perf_counter()
+            t_ext += t1 - t0; t_match += t3 - t2; t_tsdf += t4 - t3
+        else:
+            omap.integrate(depth, synth.pose(f), bgr)        # map initialisation, untimed
+        prev = cur
+    tot = t_ext + t_match + t_tsdf
+    return frames / tot, dict(extract_s=t_ext / frames, match_s=t_match / frames, tsdf_s=t_tsdf / frames)
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # warmup + steps, each step = one frame of the same workload (bounded sample: the CPU TSDF alone takes seconds per frame)
+    w = max(0, min(a.warmup, 1))
+    if w:
+        cpu_reference_run(a, w, threads, True)
+    t0 = time.perf_counter()
+    fps, stages = cpu_reference_run(a, a.steps, threads, True)
+    wall = time.perf_counter() - t0
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32+f32",
+            "data": "synthetic", "config": workload_config(a, {"frames_per_step": 1, "note": "CPU oracle (cv2 primitives + C++ restatement of the reference), "
+                                                               "all host threads: cv2.setNumThreads(n), TSDF chunks over OpenMP; rank 0 only"}),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": f"{a.steps} frames of the same stream, stage seconds/frame {json.dumps({k: round(v, 4) for k, v in stages.items()})}"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "wall_s": wall}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_b200_arm(a):
+    import torch
+    import torch.distributed as dist
+    from plvs_b200 import _lib
+    from plvs_b200.pipeline import StreamData, HotPath
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    B, K, W = a.batch, a.steps, a.warmup
+    nframes = 1 + (W + K) * B            # frame 0 only seeds the map / the "last frame"
+    data = StreamData(nframes, a.width, a.height, stream=rank, pinned=True)
+    hp = HotPath(data, a.nfeatures, a.voxel, a.far, max_blocks=49152, device=local, batch=B)
+    hp.prepare()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def run(resident, timed_profile=False):
+        hp.tsdf.Reset()
+        hp.tsdf.integrate(data.depth[0], data.poses[0], data.bgr[0])           # seed (untimed)
+        for s in range(W):
+            hp.step(1 + s * B, B, resident)
+        lib.plvs_set_profiling(1 if timed_profile else 0)
+        lib.plvs_tsdf_kernel_times(hp.tsdf._h, None, None, 1)
+        lib.plvs_orb_kernel_times(hp.ex._h, None, None, 1)
+        for m in (hp.m_track, hp.m_map, hp.m_tri):
+            lib.plvs_match_kernel_times(m._h, None, None, 1)
+        sampler = ClockSampler(local); sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        agg = {}
+        for s in range(K):
+            flush.fill_(s & 0xff)                                               # L2 flush between steps
+            o = hp.step(1 + (W + s) * B, B, resident)
+            for k, v in o.items():
+                agg[k] = agg.get(k, 0) + v
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        lib.plvs_set_profiling(0)
+        return float(t_ms.item()), wall, clocks, agg
+
+    import ctypes as C
+    # ---- value arm: inputs resident in HBM ----------------------------------------------------------------
+    hp.upload_inputs()
+    t_ms, wall, clocks, agg = run(resident=True, timed_profile=True)
+    ktimes = {}
+    ms = np.zeros(12, np.float32); cnt = np.zeros(12, np.int32)
+    lib.plvs_tsdf_kernel_times(hp.tsdf._h, ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 0)
+    for i, nme in enumerate(("tsdf.depth_tiles", "tsdf.classify", "tsdf.integrate", "tsdf.commit")):
+        ktimes[nme] = (float(ms[i]), int(cnt[i]))
+    lib.plvs_orb_kernel_times(hp.ex._h, ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 0)
+    for i, nme in enumerate(("orb.pyramid", "orb.fast_cells", "orb.compact", "orb.blur", "orb.orient_describe")):
+        ktimes[nme] = (float(ms[i]), int(cnt[i]))
+    mm = np.zeros(12, np.float32); mc = np.zeros(12, np.int32)
+    for m in (hp.m_track, hp.m_map, hp.m_tri):
+        lib.plvs_match_kernel_times(m._h, ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 0)
+        mm += ms; mc += cnt
+    for i, nme in enumerate(("match.grid", "match.candidates", "match.resolve", "match.triangulate")):
+        ktimes[nme] = (float(mm[i]), int(mc[i]))
+    frames = K * B
+    value = world * frames / (t_ms / 1000.0)
+    launches_per_step = hp.launches_per_frame() * B
+
+    # roofline of the dominant kernel: TSDF voxel update.  Algorithmic bytes per launch:
+    # depth 4*W*H + colour 3*W*H + n_updated_blocks * 4096 voxels * 12 B (sdf f32 + weight f32 + rgba) * 2 (read+write)
+    integ_ms, integ_n = ktimes["tsdf.integrate"]
+    upd_per_launch = agg.get("tsdf_updated", 0) / max(frames, 1)
+    alg_bytes = a.width * a.height * (4 + 3) + upd_per_launch * 4096 * 12 * 2
+    peak, peak_src = peaks()
+    roof = None
+    if integ_n:
+        achieved = alg_bytes / (integ_ms / integ_n / 1000.0) / 1e9
+        roof = {"kernel": "k_integrate (TSDF voxel update)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": integ_ms / integ_n,
+                "updated_blocks_per_launch": upd_per_launch}
+    gpu_time_ms = sum(v[0] for v in ktimes.values())
+
+    # ---- e2e arm: host (pinned) buffers through the public classes, copies inside the timed region ---------
+    t2_ms, wall2, clocks2, agg2 = run(resident=False)
+    e2e_value = world * frames / (t2_ms / 1000.0)
+    h2d = B * data.input_bytes_per_frame()
+    d2h = int(B * (agg2.get("keypoints", 0) / max(frames, 1)) * 60 + B * 3 * a.nfeatures * 4)
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32+f32", "data": "synthetic",
+            "config": workload_config(a, {"l2": "256 MiB device buffer rewritten between steps (inside the timed region); every step reads new frames",
+                                          "timing": "torch.cuda.Event pair around K steps, barrier+synchronize both sides, max over ranks; "
+                                                    "library calls synchronise their own streams before returning",
+                                          "threads": "tracking thread (extract+match) and dense-mapping thread (TSDF) run concurrently, as in the reference"}),
+            "roofline": roof, "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t2_ms / K},
+            "gpu_launches": int(round(launches_per_step * K)), "clocks": clocks,
+            "kernel_ms_per_step": {k: round(v[0] / K, 4) for k, v in ktimes.items()}, "gpu_busy_frac": gpu_time_ms / t_ms,
+            "per_step": {"keypoints": agg.get("keypoints", 0) / K, "matches": agg.get("matches", 0) / K}, "wall_s": [wall, wall2]}
+    if not a.no_cpu_baseline:
+        fps, stages = cpu_reference_run(a, a.cpu_frames, 1, False)
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
+                                "sample": f"{a.cpu_frames} frames of stream 0 (after a 1-frame map seed), faithful mode: 1 thread "
+                                          f"(cv2.setNumThreads(1), single-threaded chunk loop like Chisel.h:91); seconds/frame "
+                                          f"{json.dumps({k: round(v, 4) for k, v in stages.items()})}; host has {os.cpu_count()} cpus"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)

@@ -41,6 +41,23 @@ extern "C" {
 const char* plvs_version(void);
 const char* plvs_last_error(void);          /* thread-local description of the last failure */
 int plvs_device_count(void);
+/* Per-kernel CUDA-event timing on each handle's stream (off by default; used by bench.py for the roofline
+ * figures).  plvs_*_kernel_times() return accumulated milliseconds and launch counts since the last reset. */
+int plvs_set_profiling(int enable);
+#define PLVS_ORB_K_RESIZE 0
+#define PLVS_ORB_K_FAST 1
+#define PLVS_ORB_K_COMPACT 2
+#define PLVS_ORB_K_BLUR 3
+#define PLVS_ORB_K_DESCRIBE 4
+#define PLVS_MATCH_K_GRID 0
+#define PLVS_MATCH_K_CANDIDATES 1
+#define PLVS_MATCH_K_RESOLVE 2
+#define PLVS_MATCH_K_TRIANGULATE 3
+#define PLVS_TSDF_K_TILES 0
+#define PLVS_TSDF_K_CLASSIFY 1
+#define PLVS_TSDF_K_INTEGRATE 2
+#define PLVS_TSDF_K_COMMIT 3
+#define PLVS_K_SLOTS 12
 /* pinned host memory for the e2e path (cudaHostAlloc / cudaFreeHost) */
 int plvs_host_alloc(void** p, size_t bytes);
 int plvs_host_free(void* p);
@@ -117,6 +134,7 @@ typedef struct {
     int32_t kernel_launches;     /* kernels launched by the last extract call */
 } plvs_orb_stats;
 int plvs_orb_last_stats(const plvs_orb* h, plvs_orb_stats* out);
+int plvs_orb_kernel_times(plvs_orb* h, float* ms /*PLVS_K_SLOTS*/, int32_t* launches /*PLVS_K_SLOTS*/, int reset);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Matching -- replaces the three ORBmatcher entry points + DescriptorDistance                 */
@@ -182,6 +200,10 @@ int plvs_match_projection_map(plvs_match* h, const plvs_frame_view* F, const plv
 int plvs_match_projection_last(plvs_match* h, const plvs_frame_view* cur, const plvs_last_query* q, int nq,
                                float th, int forward, int backward, int check_orientation,
                                const uint8_t* claimed_in, int32_t* assign, int* nmatches);
+
+int plvs_match_kernel_times(plvs_match* h, float* ms, int32_t* launches, int reset);
+/* rounds of the claim fixed point and kernels launched by the last projection search */
+int plvs_match_last_stats(const plvs_match* h, int* rounds, int* kernel_launches);
 
 /* DBoW2::FeatureVector flattened: sorted node ids, CSR offsets, feature indices (ascending per node) */
 typedef struct {
@@ -249,6 +271,7 @@ typedef struct {
     int32_t pool_exhausted;      /* !=0 if max_blocks was hit (results incomplete) */
 } plvs_tsdf_stats;
 int plvs_tsdf_last_stats(const plvs_tsdf* h, plvs_tsdf_stats* out);
+int plvs_tsdf_kernel_times(plvs_tsdf* h, float* ms, int32_t* launches, int reset);
 
 /* read-out for tests/merge: chunk ids (x,y,z), per-voxel sdf / weight (4096 each, voxel index
  * (z*16+y)*16+x as Chunk.h:90-93) and rgba (r,g,b,colour-weight).  Any output may be NULL. */

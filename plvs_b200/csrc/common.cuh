@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 #include "../../include/plvs_b200.h"
 
 namespace plvs {
@@ -64,6 +65,34 @@ struct PinBuf {
     }
     void release() { if (h) cudaFreeHost(h); h = nullptr; d = nullptr; n = 0; }
     ~PinBuf() { release(); }
+};
+
+// Optional per-kernel timing with CUDA events on the handle's own stream (bench.py's roofline leg).
+// Off by default: when off, begin()/end() are a load and a branch.
+extern int g_profiling;
+struct KernelTimer {
+    static constexpr int kSlots = 12;
+    std::vector<cudaEvent_t> pool;
+    std::vector<int> pending;      // slot of pair i (events 2i, 2i+1)
+    float ms[kSlots] = {0};
+    int count[kSlots] = {0};
+    void begin(int slot, cudaStream_t st) {
+        if (!g_profiling) return;
+        const size_t i = pending.size();
+        while (pool.size() < 2 * (i + 1)) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        pending.push_back(slot);
+        cudaEventRecord(pool[2 * i], st);
+    }
+    void end(cudaStream_t st) { if (!g_profiling || pending.empty()) return; cudaEventRecord(pool[2 * (pending.size() - 1) + 1], st); }
+    void collect() {           // call after the stream has been synchronised
+        for (size_t i = 0; i < pending.size(); ++i) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, pool[2 * i], pool[2 * i + 1]) == cudaSuccess) { ms[pending[i]] += t; ++count[pending[i]]; }
+        }
+        pending.clear();
+    }
+    void reset() { for (int i = 0; i < kSlots; ++i) { ms[i] = 0.f; count[i] = 0; } pending.clear(); }
+    ~KernelTimer() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
 };
 
 }  // namespace plvs

@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 namespace plvs {
+int g_profiling = 0;
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...)
 {
@@ -17,6 +18,8 @@ extern "C" {
 
 const char* plvs_version(void) { return "plvs_b200 0.1 (sm_100a)"; }
 const char* plvs_last_error(void) { return plvs::g_err; }
+
+int plvs_set_profiling(int enable) { plvs::g_profiling = enable ? 1 : 0; return PLVS_OK; }
 
 int plvs_device_count(void)
 {

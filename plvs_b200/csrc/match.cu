@@ -439,6 +439,7 @@ struct plvs_match {
     PinBuf<int> p_result, p_cand_n;
     int cap = 128;
     int last_rounds = 0, last_launches = 0;
+    KernelTimer timer;
     std::mutex mu;
 };
 
@@ -500,19 +501,26 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         (rc = h->d_assign.alloc(n)) || (rc = h->p_assign.alloc(n)) || (rc = h->p_result.alloc(4)) || (rc = h->p_cand_n.alloc(nq)))
         return rc;
     int launches = 0;
+    h->timer.begin(PLVS_MATCH_K_GRID, st);
     k_build_grid<<<1, 1024, 0, st>>>(V.keys, n, V.gp, h->d_cell_start.p, h->d_sorted.p, h->d_kp_cell.p);
+    h->timer.end(st);
     ++launches;
     for (;;) {
         if ((rc = h->d_cand.alloc((size_t)nq * h->cap))) return rc;
+        h->timer.begin(PLVS_MATCH_K_CANDIDATES, st);
         k_candidates<MODE><<<div_up(nq, 8), 256, 0, st>>>(V, h->d_cell_start.p, h->d_sorted.p, h->d_query.p, nq, th, far_points, th_far, forward, backward,
                                                            h->d_cand.p, h->d_cand_n.p, h->cap);
+        h->timer.end(st);
         ++launches;
         PLVS_CUDA(cudaMemcpyAsync(h->p_cand_n.h, h->d_cand_n.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+        h->timer.begin(PLVS_MATCH_K_RESOLVE, st);
         k_resolve<MODE><<<1, 1024, 0, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
                                             h->d_claim_a.p, h->d_claim_b.p, h->d_target.p, h->p_assign.d, h->p_result.d);
+        h->timer.end(st);
         ++launches;
         PLVS_CUDA(cudaGetLastError());
         PLVS_CUDA(cudaStreamSynchronize(st));
+        h->timer.collect();
         int mx = 0;
         for (int i = 0; i < nq; ++i) mx = std::max(mx, h->p_cand_n.h[i]);
         if (mx <= h->cap) break;
@@ -579,6 +587,23 @@ void plvs_match_destroy(plvs_match* h)
     delete h;
 }
 
+int plvs_match_kernel_times(plvs_match* h, float* ms, int32_t* launches, int reset)
+{
+    if (!h) return PLVS_EINVAL;
+    std::lock_guard<std::mutex> lock(h->mu);
+    for (int i = 0; i < KernelTimer::kSlots; ++i) { if (ms) ms[i] = h->timer.ms[i]; if (launches) launches[i] = h->timer.count[i]; }
+    if (reset) h->timer.reset();
+    return PLVS_OK;
+}
+
+int plvs_match_last_stats(const plvs_match* h, int* rounds, int* kernel_launches)
+{
+    if (!h) return PLVS_EINVAL;
+    if (rounds) *rounds = h->last_rounds;
+    if (kernel_launches) *kernel_launches = h->last_launches;
+    return PLVS_OK;
+}
+
 int plvs_match_projection_map(plvs_match* h, const plvs_frame_view* F, const plvs_mp_query* q, int nq, float th, float nn_ratio,
                               int far_points, float th_far, const uint8_t* claimed_in, int32_t* assign, int* nmatches)
 {
@@ -619,11 +644,14 @@ int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const pl
     }
     if ((rc = h->d_f12.alloc(16)) || (rc = h->p_assign.alloc(n1)) || (rc = h->p_result.alloc(4))) return rc;
     PLVS_CUDA(cudaMemcpyAsync(h->d_f12.p, F12, 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+    h->timer.begin(PLVS_MATCH_K_TRIANGULATE, st);
     k_fill_i32<<<div_up(n1, 256), 256, 0, st>>>(h->p_assign.d, n1, -1);
     k_triangulate<<<D1.n_nodes, 256, 0, st>>>(V1, V2, D1, D2, dh1, dh2, h->d_f12.p, ep[0], ep[1], only_stereo, coarse, h->p_assign.d);
     k_tri_finish<<<1, 1024, 0, st>>>(V1.keys, V2.keys, n1, check_orientation, h->p_assign.d, h->p_result.d);
+    h->timer.end(st);
     PLVS_CUDA(cudaGetLastError());
     PLVS_CUDA(cudaStreamSynchronize(st));
+    h->timer.collect();
     std::memcpy(match12, h->p_assign.h, (size_t)n1 * 4);
     *nmatches = h->p_result.h[0];
     h->last_launches = 3;

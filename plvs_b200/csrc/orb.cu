@@ -53,6 +53,7 @@ struct plvs_orb {
     std::vector<char> lapped;
     int last_batch = 0;
     plvs_orb_stats stats{};
+    KernelTimer timer;
     std::mutex mu;
 };
 
@@ -277,21 +278,29 @@ int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, i
             PLVS_CUDA(cudaMemcpy2DAsync(o->d_pyr.p + (size_t)b * o->frame_stride, g0.pitch, gray + b * frame_stride_in, stride, w, h,
                                         cudaMemcpyHostToDevice, st));
     }
+    o->timer.begin(PLVS_ORB_K_RESIZE, st);
     for (int l = 1; l < nl; ++l) {
         const LevelGeom& g = o->lv[l];
         dim3 grid(div_up(g.w, 128), div_up(g.h, 8), batch), block(32, 8);
         k_resize_level<<<grid, block, 0, st>>>(o->d_pyr.p, o->frame_stride, o->lv[l - 1], g, o->d_taps.p);
         ++launches;
     }
+    o->timer.end(st);
+    o->timer.begin(PLVS_ORB_K_FAST, st);
     k_fast_cells<<<dim3((unsigned)o->cells.size(), batch), 256, 0, st>>>(o->d_pyr.p, o->frame_stride, o->d_lv.p, o->d_cells.p, o->d_slots.p,
                                                                           o->slots_per_frame, o->d_cell_count.p, (int)o->cells.size(),
                                                                           o->prm.ini_th_fast, o->prm.min_th_fast, o->debug ? o->d_dbg_score.p : nullptr);
+    o->timer.end(st);
+    o->timer.begin(PLVS_ORB_K_COMPACT, st);
     k_compact<<<dim3(nl, batch), 256, 0, st>>>(o->d_slots.p, o->slots_per_frame, o->d_cell_count.p, (int)o->cells.size(), o->d_lv.p, o->d_cells.p, nl,
                                                 o->d_cand.p, o->p_cand.d, o->d_cand_count.p, o->p_cand_count.d);
+    o->timer.end(st);
     launches += 2;
     PLVS_CUDA(cudaEventRecord(o->ev, st));
+    o->timer.begin(PLVS_ORB_K_BLUR, st);
     // the blur does not depend on the keypoints: it overlaps the host-side distribution
     k_blur<<<dim3((unsigned)o->blur_tiles.size(), batch), 256, 0, st>>>(o->d_pyr.p, o->d_blur.p, o->frame_stride, o->d_lv.p, o->d_tiles.p);
+    o->timer.end(st);
     ++launches;
     PLVS_CUDA(cudaGetLastError());
     PLVS_CUDA(cudaEventSynchronize(o->ev));
@@ -341,12 +350,15 @@ int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, i
         max_k = std::max(max_k, k);
     }
     if (max_k > 0) {
+        o->timer.begin(PLVS_ORB_K_DESCRIBE, st);
         k_orient_describe<<<dim3(div_up(max_k, 8), batch), 256, 0, st>>>(o->d_pyr.p, o->d_blur.p, o->frame_stride, o->d_lv.p, nl, o->p_sel.d, o->p_sel_off.d,
                                                                           o->sel_cap, o->d_kp.p, o->d_desc.p, o->p_kp.d, o->p_desc.d);
+        o->timer.end(st);
         ++launches;
     }
     PLVS_CUDA(cudaGetLastError());
     PLVS_CUDA(cudaStreamSynchronize(st));
+    o->timer.collect();
 
     // ---- assemble (src/ORBextractor.cc:1267-1389): mono indices from the front, lapping-area ones from the back
     o->lapped.assign(batch, 0);
@@ -433,6 +445,15 @@ int plvs_orb_candidates(const plvs_orb* o, int frame, int level, int32_t* x, int
         if (y) y[i] = unpack_y(c[i]);
         if (score) score[i] = unpack_s(c[i]);
     }
+    return PLVS_OK;
+}
+
+int plvs_orb_kernel_times(plvs_orb* o, float* ms, int32_t* launches, int reset)
+{
+    if (!o) return PLVS_EINVAL;
+    std::lock_guard<std::mutex> lock(o->mu);
+    for (int i = 0; i < KernelTimer::kSlots; ++i) { if (ms) ms[i] = o->timer.ms[i]; if (launches) launches[i] = o->timer.count[i]; }
+    if (reset) o->timer.reset();
     return PLVS_OK;
 }
 

@@ -1,0 +1,194 @@
+"""Stream runner used by bench.py / tests: drives the three reference-facing surfaces (ORBextractor,
+ORBmatcher, ChiselServer) over a synthetic RGB-D stream the way PLVS's threads do -- a *tracking* thread
+(extract + the two SearchByProjection calls + SearchForTriangulation against the previous frame) and a
+*dense-mapping* thread (TSDF integration), which the reference also runs concurrently
+(src/System.cc:317-398: Tracking in the caller's thread, PointCloudMapping::Run in its own).
+
+Caller-side work that is NOT part of the hot path (building map-point / last-frame queries from poses and
+depth) is precomputed once by `prepare()` so the timed region contains only the hot path."""
+import ctypes as C
+import threading
+import numpy as np
+
+from . import _lib, synth, scenario, tsdf as T
+from .matcher import ORBmatcher, Frame, featvec
+from .orb import ORBextractor, KP_DTYPE
+
+
+class PinnedArray:
+    """numpy view of cudaHostAlloc'ed memory (pinned, so H2D copies are true DMA)."""
+
+    def __init__(self, shape, dtype):
+        self.lib = _lib.load()
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = C.c_void_p()
+        _lib.check(self.lib.plvs_host_alloc(C.byref(self.ptr), max(nbytes, 1)), "plvs_host_alloc")
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.plvs_host_free(self.ptr)
+            self.ptr = None
+
+
+class StreamData:
+    """Synthetic inputs of one camera stream: gray u8, depth f32, bgr u8 and poses for `n` frames."""
+
+    def __init__(self, n, w, h, stream=0, pinned=True):
+        self.n, self.w, self.h, self.stream = n, w, h, stream
+        self.K = synth.intrinsics(w, h)
+        mk = (lambda s, d: PinnedArray(s, d)) if pinned else None
+        self._pins = []
+        def alloc(shape, dtype):
+            if pinned:
+                p = PinnedArray(shape, dtype); self._pins.append(p); return p.array
+            return np.empty(shape, dtype)
+        self.gray = alloc((n, h, w), np.uint8)
+        self.depth = alloc((n, h, w), np.float32)
+        self.bgr = alloc((n, h, w, 3), np.uint8)
+        self.poses = np.zeros((n, 3, 4), np.float32)
+        for f in range(n):
+            self.gray[f] = synth.gray_frame(f, w, h, stream)
+            self.depth[f] = synth.depth_frame(f, w, h, stream)
+            self.bgr[f] = np.stack([self.gray[f], np.roll(self.gray[f], 3, 1), 255 - self.gray[f]], -1)
+            self.poses[f] = synth.pose(f)
+
+    def input_bytes_per_frame(self):
+        return self.w * self.h * (1 + 4 + 3)
+
+
+class HotPath:
+    """extract + match + TSDF for one stream on one GPU."""
+
+    def __init__(self, data, nfeatures=2000, voxel=0.01, far=5.0, max_blocks=32768, device=0, batch=8, use_color=True):
+        self.d, self.batch, self.device = data, batch, device
+        self.ex = ORBextractor(nfeatures, 1.2, 8, 20, 7, device=device)
+        self.m_track = ORBmatcher(0.9, True, device=device)      # TrackWithMotionModel (src/Tracking.cc:3593)
+        self.m_map = ORBmatcher(0.8, True, device=device)        # SearchLocalPoints (src/Tracking.cc:4477)
+        self.m_tri = ORBmatcher(0.6, False, device=device)       # CreateNewMapFeatures (src/LocalMapping.cc:537)
+        p = T.default_params(voxel_resolution=voxel, use_carving=1, near_plane=0.1, far_plane=far, max_blocks=max_blocks, use_color=int(use_color))
+        self.tsdf = T.ChiselServer(p, device=device)
+        K = data.K
+        self.tsdf.SetDepthCameraInfo(K["fx"], K["fy"], K["cx"], K["cy"], data.w, data.h)
+        self.use_color = use_color
+        self.prepared = None
+        self.dev = None       # device-resident copies of the inputs (the `value` arm)
+
+    # ---- untimed: caller-side query construction -------------------------------------------------------
+    def prepare(self):
+        d, K = self.d, self.d.K
+        sf, s2 = self.ex.GetScaleFactors(), self.ex.GetScaleSigmaSquares()
+        frames = []
+        for f0 in range(0, d.n, self.batch):
+            mono, kps, descs = self.ex.extract_batch(d.gray[f0:f0 + self.batch])
+            for b in range(len(kps)):
+                fr = scenario.make_frame(kps[b].copy(), descs[b].copy(), d.depth[f0 + b], K, sf)
+                fr.level_sigma2 = s2
+                frames.append(fr)
+        prep = []
+        for f in range(d.n):
+            if f == 0:
+                prep.append(None); continue
+            last, cur = frames[f - 1], frames[f]
+            ql, _ = scenario.last_queries(last, cur, K, d.poses[f - 1], d.poses[f])
+            qm, _ = scenario.map_queries(last, cur, K, d.poses[f - 1], d.poses[f], seed=f)
+            fv_last, fv_cur = featvec(scenario.node_ids(last.desc)), featvec(scenario.node_ids(cur.desc))
+            F12, ep = scenario.fundamental(K, d.poses[f], d.poses[f - 1])
+            prep.append(dict(ql=ql, qm=qm, fv1=fv_cur, fv2=fv_last, F12=F12, ep=ep,
+                             has1=np.zeros(cur.n, np.uint8), has2=np.zeros(last.n, np.uint8)))
+        self.frames, self.prepared = frames, prep
+        self.tsdf.Reset()
+
+    def upload_inputs(self):
+        """device-resident arm: inputs live in HBM before the timed region (torch owns the allocations)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        self.dev = dict(gray=torch.from_numpy(self.d.gray).to(dev), depth=torch.from_numpy(self.d.depth).to(dev),
+                        bgr=torch.from_numpy(self.d.bgr).to(dev))
+        torch.cuda.synchronize(dev)
+
+    # ---- timed: the hot path ---------------------------------------------------------------------------
+    def _track_batch(self, f0, nb, resident, out):
+        d = self.d
+        if resident:
+            g = self.dev["gray"]
+            mono, kps, descs = self.ex.extract_batch((g[f0].data_ptr(), nb, d.h, d.w, d.w, d.w * d.h))
+        else:
+            mono, kps, descs = self.ex.extract_batch(d.gray[f0:f0 + nb])
+        sf, s2 = self.ex.mvScaleFactor, self.ex.mvLevelSigma2
+        nm = 0
+        for b in range(nb):
+            f = f0 + b
+            p = self.prepared[f]
+            if p is None:
+                continue
+            # descriptors/keypoints of the current frame stay on the device for the searches
+            dv = self.ex.device_result(b)
+            cur_ref = self.frames[f]
+            cur = Frame(None, None, d.w, d.h, sf, s2, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0))
+            n1, a1 = self.m_track.SearchByProjectionLast(cur, p["ql"], 15.0)
+            claimed = (a1 >= 0).astype(np.uint8)
+            n2, a2 = self.m_map.SearchByProjectionMap(cur, p["qm"], 3.0, claimed=claimed)
+            last = self.frames[f - 1]
+            n3, m12 = self.m_tri.SearchForTriangulation(Frame(kps[b], descs[b], d.w, d.h, sf, s2, uright=cur_ref.uright, bf=d.K["bf"]), last,
+                                                        p["fv1"], p["fv2"], p["has1"], p["has2"], p["F12"], p["ep"], False, False)
+            nm += n1 + n2 + n3
+        out["matches"] = out.get("matches", 0) + nm
+        out["keypoints"] = out.get("keypoints", 0) + sum(len(k) for k in kps)
+
+    def _map_batch(self, f0, nb, resident, out):
+        d = self.d
+        for b in range(nb):
+            f = f0 + b
+            if resident:
+                self._integrate_device(f)
+            else:
+                self.tsdf.integrate(d.depth[f], d.poses[f], d.bgr[f] if self.use_color else None)
+            st = self.tsdf.stats()
+            out["tsdf_updated"] = out.get("tsdf_updated", 0) + st["n_updated"]
+            out["tsdf_candidates"] = out.get("tsdf_candidates", 0) + st["n_candidates"]
+
+    def _integrate_device(self, f):
+        d = self.d
+        lib, h = self.tsdf._lib, self.tsdf._h
+        pose = np.ascontiguousarray(d.poses[f], np.float32).reshape(12)
+        bgr = self.dev["bgr"][f] if self.use_color else None
+        rc = lib.plvs_tsdf_integrate_depth(h, C.c_void_p(self.dev["depth"][f].data_ptr()), d.w, d.h,
+                                           C.c_void_p(bgr.data_ptr()) if bgr is not None else None, d.w * 3, 3 if bgr is not None else 0,
+                                           pose.ctypes.data_as(C.c_void_p), T.SCAN_COLOR if bgr is not None else T.SCAN, 1)
+        _lib.check(rc, "plvs_tsdf_integrate_depth")
+
+    def step(self, f0, nb, resident=False, concurrent=True):
+        """one step = one batch of `nb` consecutive frames through extract+match (tracking thread) and TSDF
+        (dense-mapping thread)."""
+        out = {}
+        if concurrent:
+            err = []
+            def mapper():
+                try:
+                    self._map_batch(f0, nb, resident, out)
+                except Exception as e:      # surface worker failures in the caller
+                    err.append(e)
+            t = threading.Thread(target=mapper)
+            t.start()
+            self._track_batch(f0, nb, resident, out)
+            t.join()
+            if err:
+                raise err[0]
+        else:
+            self._track_batch(f0, nb, resident, out)
+            self._map_batch(f0, nb, resident, out)
+        return out
+
+    def launches_per_frame(self):
+        """kernel launches of the last batch / frame, as counted by the library"""
+        lib = self.ex._lib
+        n = self.ex.last_stats()["kernel_launches"] / max(self.batch, 1)
+        r, k = C.c_int(), C.c_int()
+        for m in (self.m_track, self.m_map, self.m_tri):
+            lib.plvs_match_last_stats(m._h, C.byref(r), C.byref(k))
+            n += k.value
+        n += self.tsdf.stats()["kernel_launches"]
+        return n

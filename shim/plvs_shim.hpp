@@ -1,0 +1,350 @@
+// plvs_shim.hpp -- header-only C++ shims that keep the reference's class surfaces and forward to the
+// C ABI of libplvs_b200.so (include/plvs_b200.h).  A PLVS checkout swaps its three translation units
+// for these: Tracking / LocalMapping / PointCloudMapping call in unchanged.
+//
+//   PLVS2::ORBextractor              include/ORBextractor.h:59-170     (reference)
+//   PLVS2::ORBmatcher (3 overloads)  include/ORBmatcher.h:61-97
+//   chisel_server::ChiselServer      Thirdparty/chisel_server/include/chisel_server/ChiselServer.h:81-322 (integrate path)
+//
+// With OpenCV/Eigen present the real cv::/Eigen:: types are used.  This build image has neither, so the
+// shim is also compilable against the minimal stand-ins of shim/standin.hpp (define PLVS_SHIM_STANDIN):
+// tests/test_shim_compile.py compiles and links it that way; the member access patterns are the
+// reference's (Frame::mvKeysUn, MapPoint::mTrackProjX, ...), expressed as templates so any type with
+// those members works.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+#include "../include/plvs_b200.h"
+
+#ifdef PLVS_SHIM_STANDIN
+#include "standin.hpp"
+#else
+#include <opencv2/core/core.hpp>
+#include <Eigen/Geometry>
+#endif
+
+namespace plvs_shim {
+inline void check(int rc, const char* what)
+{
+    if (rc != PLVS_OK) throw std::runtime_error(std::string(what) + ": " + plvs_last_error());
+}
+static_assert(sizeof(cv::KeyPoint) == sizeof(plvs_keypoint), "cv::KeyPoint must be the 28-byte POD the ABI mirrors");
+}  // namespace plvs_shim
+
+namespace PLVS2 {
+
+// ------------------------------------------------------------------------------------------------------
+class ORBextractor {
+public:
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+
+    ORBextractor(int nfeatures_, float scaleFactor_, int nlevels_, int iniThFAST_, int minThFAST_, int device = 0)
+        : nfeatures(nfeatures_), scaleFactor(scaleFactor_), nlevels(nlevels_), iniThFAST(iniThFAST_), minThFAST(minThFAST_)
+    {
+        plvs_orb_params p{nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST};
+        plvs_shim::check(plvs_orb_create(&p, device, &h_), "plvs_orb_create");
+        mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels); mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels);
+        mnFeaturesPerLevel.resize(nlevels);
+        plvs_shim::check(plvs_orb_tables(h_, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(),
+                                         mnFeaturesPerLevel.data()), "plvs_orb_tables");
+        mvImagePyramid.resize(nlevels); mvImagePyramidFiltered.resize(nlevels);
+    }
+    ~ORBextractor() { plvs_orb_destroy(h_); }
+    ORBextractor(const ORBextractor&) = delete;
+    ORBextractor& operator=(const ORBextractor&) = delete;
+
+    // Compute the ORB features and descriptors on an image (mask is ignored, as in the reference).
+    int operator()(cv::InputArray _image, cv::InputArray /*_mask*/, std::vector<cv::KeyPoint>& _keypoints, cv::OutputArray _descriptors,
+                   std::vector<int>& vLappingArea)
+    {
+        if (_image.empty()) return -1;
+        cv::Mat image = _image.getMat();
+        const int cap = 2 * nfeatures + 64 * nlevels;
+        _keypoints.resize(cap);
+        cv::Mat desc(cap, 32, CV_8U);
+        int n = 0, mono = 0;
+        const int lap0 = vLappingArea.size() > 0 ? vLappingArea[0] : 0, lap1 = vLappingArea.size() > 1 ? vLappingArea[1] : 0;
+        plvs_shim::check(plvs_orb_extract(h_, image.data, image.cols, image.rows, (int)image.step, 0, lap0, lap1,
+                                          reinterpret_cast<plvs_keypoint*>(_keypoints.data()), desc.data, cap, &n, &mono), "plvs_orb_extract");
+        _keypoints.resize(n);
+        if (n == 0) _descriptors.release();
+        else desc.rowRange(0, n).copyTo(_descriptors);
+        pyramidFresh_ = false;
+        return mono;
+    }
+
+    int inline GetLevels() { return nlevels; }
+    float inline GetScaleFactor() { return scaleFactor; }
+    std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
+    std::vector<float> inline GetInverseScaleFactors() { return mvInvScaleFactor; }
+    std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
+    std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+    int GetBorderX() const { return 19; }
+    int GetBorderY() const { return 19; }
+
+    // mvImagePyramid is a public member that Frame::ComputeStereoMatches reads (src/Frame.cc:1789): the device
+    // pyramid is mirrored to the host on demand instead of on every frame.
+    void SyncImagePyramid(bool filtered = false)
+    {
+        for (int l = 0; l < nlevels; ++l) {
+            const uint8_t* d; int w, h, pitch;
+            plvs_shim::check(plvs_orb_pyramid_level(h_, 0, l, filtered ? 1 : 0, &d, &w, &h, &pitch), "plvs_orb_pyramid_level");
+            cv::Mat& m = filtered ? mvImagePyramidFiltered[l] : mvImagePyramid[l];
+            m.create(h, w, CV_8U);
+            plvs_shim::check(plvs_orb_download_level(h_, 0, l, filtered ? 1 : 0, m.data, (int)m.step), "plvs_orb_download_level");
+        }
+        pyramidFresh_ = true;
+    }
+
+    std::vector<cv::Mat> mvImagePyramid;
+    std::vector<cv::Mat> mvImagePyramidFiltered;
+    plvs_orb* handle() { return h_; }
+
+protected:
+    int nfeatures; float scaleFactor; int nlevels, iniThFAST, minThFAST;
+    std::vector<int> mnFeaturesPerLevel;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+    plvs_orb* h_ = nullptr;
+    bool pyramidFresh_ = false;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// ORBmatcher: the three hot-path overloads.  FrameT / KeyFrameT / MapPointPtr are the reference's own types;
+// only the members the reference's code reads are touched (gather), and only Frame::mvpMapPoints is written
+// (scatter), in the reference's order.
+class ORBmatcher {
+public:
+    ORBmatcher(float nnratio = 0.6f, bool checkOri = true, int device = 0) : mfNNratio(nnratio), mbCheckOrientation(checkOri)
+    {
+        plvs_shim::check(plvs_match_create(device, &h_), "plvs_match_create");
+    }
+    ~ORBmatcher() { plvs_match_destroy(h_); }
+    ORBmatcher(const ORBmatcher&) = delete;
+
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b) { return plvs_hamming256(a.data, b.data); }
+
+    template <class FrameT>
+    static plvs_frame_view view_of(const FrameT& F, const std::vector<cv::KeyPoint>& keysUn, const cv::Mat& descriptors)
+    {
+        plvs_frame_view v{};
+        v.n = F.N;
+        v.keys = reinterpret_cast<const plvs_keypoint*>(keysUn.data());
+        v.desc = descriptors.data;
+        v.uright = F.mvuRight.empty() ? nullptr : F.mvuRight.data();
+        v.min_x = FrameT::mnMinX; v.min_y = FrameT::mnMinY; v.max_x = FrameT::mnMaxX; v.max_y = FrameT::mnMaxY;
+        v.grid_inv_w = FrameT::mfGridElementWidthInv; v.grid_inv_h = FrameT::mfGridElementHeightInv;
+        v.nlevels = (int)F.mvScaleFactors.size();
+        for (int i = 0; i < v.nlevels && i < PLVS_MAX_LEVELS; ++i) { v.scale_factors[i] = F.mvScaleFactors[i]; v.level_sigma2[i] = F.mvLevelSigma2[i]; }
+        v.bf = F.mbf;
+        v.on_device = 0;
+        return v;
+    }
+
+    // int SearchByProjection(Frame &F, const std::vector<MapPointPtr> &vpMapPoints, const float th=3, const bool bFarPoints=false, const float thFarPoints=50.f)
+    template <class FrameT, class MapPointPtr>
+    int SearchByProjection(FrameT& F, const std::vector<MapPointPtr>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
+                           const float thFarPoints = 50.f)
+    {
+        std::vector<plvs_mp_query> q;
+        std::vector<size_t> src;
+        q.reserve(vpMapPoints.size());
+        for (size_t i = 0; i < vpMapPoints.size(); ++i) {
+            const MapPointPtr& pMP = vpMapPoints[i];
+            if (!pMP->mbTrackInView) continue;                 // RGB-D: the right-camera branch does not exist (Nleft == -1)
+            if (pMP->isBad()) continue;
+            plvs_mp_query e{};
+            e.proj_x = pMP->mTrackProjX; e.proj_y = pMP->mTrackProjY; e.proj_xr = pMP->mTrackProjXR;
+            e.track_depth = pMP->mTrackDepth; e.view_cos = pMP->mTrackViewCos; e.level = pMP->mnTrackScaleLevel;
+            e.flags = pMP->Observations() > 0 ? PLVS_Q_OBS_POSITIVE : 0u;
+            const cv::Mat d = pMP->GetDescriptor();
+            std::memcpy(e.desc, d.data, 32);
+            q.push_back(e); src.push_back(i);
+        }
+        std::vector<uint8_t> claimed(F.N, 0);
+        for (int i = 0; i < F.N; ++i) claimed[i] = (F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0) ? 1 : 0;
+        std::vector<int32_t> assign(F.N, -1);
+        int nmatches = 0;
+        const plvs_frame_view v = view_of(F, F.mvKeysUn, F.mDescriptors);
+        plvs_shim::check(plvs_match_projection_map(h_, &v, q.data(), (int)q.size(), th, mfNNratio, bFarPoints ? 1 : 0, thFarPoints, claimed.data(),
+                                                   assign.data(), &nmatches), "plvs_match_projection_map");
+        for (int i = 0; i < F.N; ++i) if (assign[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[src[assign[i]]];
+        return nmatches;
+    }
+
+    // int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
+    template <class FrameT>
+    int SearchByProjection(FrameT& CurrentFrame, const FrameT& LastFrame, const float th, const bool bMono)
+    {
+        const auto Tcw = CurrentFrame.GetPose();
+        const auto twc = Tcw.inverse().translation();
+        const auto Tlw = LastFrame.GetPose();
+        const auto tlc = Tlw * twc;
+        const bool bForward = tlc(2) > CurrentFrame.mb && !bMono;
+        const bool bBackward = -tlc(2) > CurrentFrame.mb && !bMono;
+        std::vector<plvs_last_query> q;
+        std::vector<int> src;
+        for (int i = 0; i < LastFrame.N; ++i) {
+            auto pMP = LastFrame.mvpMapPoints[i];
+            if (!pMP || LastFrame.mvbOutlier[i]) continue;
+            const auto x3Dw = pMP->GetWorldPos();
+            const auto x3Dc = Tcw * x3Dw;                      // the reference's own expressions: projection stays bit-identical
+            plvs_last_query e{};
+            e.invz = (float)(1.0 / x3Dc(2));
+            const auto uv = CurrentFrame.mpCamera->project(x3Dc);
+            e.u = uv(0); e.v = uv(1);
+            e.last_octave = LastFrame.mvKeys[i].octave;
+            e.angle = LastFrame.mvKeysUn[i].angle;
+            e.flags = pMP->Observations() > 0 ? PLVS_Q_OBS_POSITIVE : 0u;
+            const cv::Mat d = pMP->GetDescriptor();
+            std::memcpy(e.desc, d.data, 32);
+            q.push_back(e); src.push_back(i);
+        }
+        std::vector<uint8_t> claimed(CurrentFrame.N, 0);
+        for (int i = 0; i < CurrentFrame.N; ++i)
+            claimed[i] = (CurrentFrame.mvpMapPoints[i] && CurrentFrame.mvpMapPoints[i]->Observations() > 0) ? 1 : 0;
+        std::vector<int32_t> assign(CurrentFrame.N, -1);
+        int nmatches = 0;
+        const plvs_frame_view v = view_of(CurrentFrame, CurrentFrame.mvKeysUn, CurrentFrame.mDescriptors);
+        plvs_shim::check(plvs_match_projection_last(h_, &v, q.data(), (int)q.size(), th, bForward, bBackward, mbCheckOrientation ? 1 : 0,
+                                                    claimed.data(), assign.data(), &nmatches), "plvs_match_projection_last");
+        for (int i = 0; i < CurrentFrame.N; ++i) if (assign[i] >= 0) CurrentFrame.mvpMapPoints[i] = LastFrame.mvpMapPoints[src[assign[i]]];
+        return nmatches;
+    }
+
+    // int SearchForTriangulation(KeyFramePtr& pKF1, KeyFramePtr& pKF2, vector<pair<size_t,size_t>>& vMatchedPairs, bool bOnlyStereo, bool bCoarse=false)
+    template <class KeyFramePtr>
+    int SearchForTriangulation(KeyFramePtr& pKF1, KeyFramePtr& pKF2, std::vector<std::pair<size_t, size_t>>& vMatchedPairs, const bool bOnlyStereo,
+                               const bool bCoarse = false)
+    {
+        struct Flat { std::vector<uint32_t> ids; std::vector<int32_t> off, feat; plvs_featvec fv; };
+        auto flatten = [](const auto& featVec, Flat& f) {       // DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned>>
+            f.off.push_back(0);
+            for (const auto& kv : featVec) {
+                f.ids.push_back(kv.first);
+                for (unsigned i : kv.second) f.feat.push_back((int32_t)i);
+                f.off.push_back((int32_t)f.feat.size());
+            }
+            f.fv = plvs_featvec{(int32_t)f.ids.size(), f.ids.data(), f.off.data(), f.feat.data()};
+        };
+        Flat f1, f2;
+        flatten(pKF1->mFeatVec, f1); flatten(pKF2->mFeatVec, f2);
+        std::vector<uint8_t> has1(pKF1->N), has2(pKF2->N);
+        for (int i = 0; i < pKF1->N; ++i) has1[i] = pKF1->GetMapPoint(i) ? 1 : 0;
+        for (int i = 0; i < pKF2->N; ++i) has2[i] = pKF2->GetMapPoint(i) ? 1 : 0;
+        // F12 and the epipole with the reference's own Eigen expressions (src/CameraModels/Pinhole.cpp:127-131, src/ORBmatcher.cc:1006-1011)
+        float F12[9], ep[2];
+#ifdef PLVS_SHIM_STANDIN
+        standin_fundamental(*pKF1, *pKF2, F12, ep);
+#else
+        {
+            const Sophus::SE3f T1w = pKF1->GetPose(), T2w = pKF2->GetPose(), Tw2 = pKF2->GetPoseInverse();
+            const Eigen::Vector3f Cw = pKF1->GetCameraCenter();
+            const Eigen::Vector3f C2 = T2w * Cw;
+            const Eigen::Vector2f e = pKF2->mpCamera->project(C2);
+            const Sophus::SE3f T12 = T1w * Tw2;
+            const Eigen::Matrix3f R12 = T12.rotationMatrix();
+            const Eigen::Vector3f t12 = T12.translation();
+            const Eigen::Matrix3f t12x = Sophus::SO3f::hat(t12);
+            const Eigen::Matrix3f K1 = pKF1->mpCamera->toK_(), K2 = pKF2->mpCamera->toK_();
+            const Eigen::Matrix3f F = K1.transpose().inverse() * t12x * R12 * K2.inverse();
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) F12[3 * r + c] = F(r, c);
+            ep[0] = e(0); ep[1] = e(1);
+        }
+#endif
+        const plvs_frame_view v1 = view_of(*pKF1, pKF1->mvKeysUn, pKF1->mDescriptors), v2 = view_of(*pKF2, pKF2->mvKeysUn, pKF2->mDescriptors);
+        std::vector<int32_t> m12(pKF1->N, -1);
+        int nmatches = 0;
+        plvs_shim::check(plvs_match_triangulation(h_, &v1, &v2, &f1.fv, &f2.fv, has1.data(), has2.data(), F12, ep, bOnlyStereo ? 1 : 0, bCoarse ? 1 : 0,
+                                                  mbCheckOrientation ? 1 : 0, m12.data(), &nmatches), "plvs_match_triangulation");
+        vMatchedPairs.clear();
+        vMatchedPairs.reserve(nmatches);
+        for (size_t i = 0; i < m12.size(); ++i) if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));
+        return nmatches;
+    }
+
+    static const int TH_LOW = 50, TH_HIGH = 100, HISTO_LENGTH = 12;
+
+protected:
+    float mfNNratio;
+    bool mbCheckOrientation;
+    plvs_match* h_ = nullptr;
+};
+
+}  // namespace PLVS2
+
+// ------------------------------------------------------------------------------------------------------
+namespace chisel_server {
+
+struct ChiselServerParams {        // Thirdparty/chisel_server/include/chisel_server/ChiselServer.h (same field names)
+    int chunkSizeX = 16, chunkSizeY = 16, chunkSizeZ = 16;
+    float voxelResolution = 0.015f;
+    float truncationDistQuad = 0.0019f, truncationDistLinear = -0.00152f, truncationDistConst = 0.001504f, truncationDistScale = 6.0f;
+    int weight = 1;
+    bool useCarving = true, useColor = true, saveFile = true;
+    float carvingDist = 0.05f, nearPlaneDist = 0.05f, farPlaneDist = 5.0f;
+    int fusionMode = 1;
+    int maxBlocks = 65536;         // extension: capacity of the device block pool
+};
+
+class ChiselServer {
+public:
+    enum class FusionMode { DepthImage, PointCloud };
+
+    explicit ChiselServer(ChiselServerParams& params, int device = 0) : useColor(params.useColor)
+    {
+        if (params.chunkSizeX != 16 || params.chunkSizeY != 16 || params.chunkSizeZ != 16) throw std::runtime_error("chunk size must be 16^3");
+        plvs_tsdf_params p{};
+        p.voxel_resolution = params.voxelResolution;
+        p.trunc_quad = params.truncationDistQuad; p.trunc_linear = params.truncationDistLinear; p.trunc_const = params.truncationDistConst;
+        p.trunc_scale = params.truncationDistScale;
+        p.weight = (float)static_cast<uint16_t>(params.weight);
+        p.use_carving = params.useCarving; p.carving_dist = params.carvingDist; p.use_color = params.useColor;
+        p.near_plane = params.nearPlaneDist; p.far_plane = params.farPlaneDist; p.max_blocks = params.maxBlocks;
+        plvs_shim::check(plvs_tsdf_create(&p, device, &h_), "plvs_tsdf_create");
+    }
+    ~ChiselServer() { plvs_tsdf_destroy(h_); }
+    ChiselServer(const ChiselServer&) = delete;
+
+    void Reset() { plvs_shim::check(plvs_tsdf_reset(h_), "plvs_tsdf_reset"); }
+    void SetDepthCameraInfo(const double fx, const double fy, const double cx, const double cy, const int width, const int height)
+    {
+        plvs_shim::check(plvs_tsdf_set_camera(h_, fx, fy, cx, cy, width, height), "plvs_tsdf_set_camera");
+        gotInfo = true;
+    }
+    void SetColorCameraInfo(const double fx, const double fy, const double cx, const double cy, const int w, const int h) { SetDepthCameraInfo(fx, fy, cx, cy, w, h); }
+    void SetDepthPose(const Eigen::Affine3f& tf)
+    {
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) Twc_[4 * r + c] = tf.linear()(r, c); Twc_[4 * r + 3] = tf.translation()(r); }
+        gotPose = true;
+    }
+    void SetColorPose(const Eigen::Affine3f& tf) { SetDepthPose(tf); }
+    // borrowed buffers: must stay valid until IntegrateLastDepthImage returns (as in the reference)
+    void SetDepthImageMemorySharing(float* img, int width, int height, int /*step*/, uint64_t /*timestamp*/) { depth_ = img; dw_ = width; dh_ = height; }
+    void SetColorImageMemorySharing(unsigned char* img, int width, int height, int step, int num_channels, uint64_t /*timestamp*/)
+    {
+        color_ = img; cw_ = width; ch_ = height; cstep_ = step; cn_ = num_channels;
+    }
+    void IntegrateLastDepthImage(bool /*updateMesh*/ = true)
+    {
+        if (!gotInfo || !gotPose || !depth_) { std::fprintf(stderr, "ChiselServer - PROBLEM in integrating depth scan!!! ************\n"); return; }
+        const bool color = useColor && color_;
+        plvs_shim::check(plvs_tsdf_integrate_depth(h_, depth_, dw_, dh_, color ? color_ : nullptr, cstep_, cn_, Twc_,
+                                                   color ? PLVS_TSDF_SCAN_COLOR : PLVS_TSDF_SCAN, 0), "plvs_tsdf_integrate_depth");
+    }
+    plvs_tsdf* handle() { return h_; }
+
+protected:
+    bool useColor, gotInfo = false, gotPose = false;
+    float Twc_[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    float* depth_ = nullptr; int dw_ = 0, dh_ = 0;
+    unsigned char* color_ = nullptr; int cw_ = 0, ch_ = 0, cstep_ = 0, cn_ = 0;
+    plvs_tsdf* h_ = nullptr;
+};
+
+}  // namespace chisel_server

@@ -1,0 +1,63 @@
+// Compile-and-link check of shim/plvs_shim.hpp against stand-in types (no OpenCV/Eigen in this image).
+// The structs below expose exactly the members the reference's Frame / MapPoint / KeyFrame offer to the matchers.
+#define PLVS_SHIM_STANDIN
+#include <map>
+#include <memory>
+#include <vector>
+#include "../../shim/standin.hpp"
+
+struct V3 { float v[3]; float operator()(int i) const { return v[i]; } };
+struct V2 { float v[2]; float operator()(int i) const { return v[i]; } };
+struct Pose {
+    V3 t{};
+    Pose inverse() const { return *this; }
+    V3 translation() const { return t; }
+    V3 operator*(const V3& p) const { return V3{{p.v[0] + t.v[0], p.v[1] + t.v[1], p.v[2] + t.v[2]}}; }
+};
+struct Camera { V2 project(const V3& p) const { return V2{{500.f * p.v[0] / p.v[2] + 320.f, 500.f * p.v[1] / p.v[2] + 240.f}}; } };
+struct MapPoint {
+    bool mbTrackInView = true; float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackDepth = 1, mTrackViewCos = 1; int mnTrackScaleLevel = 0;
+    cv::Mat desc{1, 32, CV_8U}; V3 pos{{0, 0, 2}};
+    bool isBad() const { return false; }
+    int Observations() const { return 1; }
+    cv::Mat GetDescriptor() const { return desc; }
+    V3 GetWorldPos() const { return pos; }
+};
+typedef std::shared_ptr<MapPoint> MapPointPtr;
+struct Frame {
+    int N = 0; std::vector<cv::KeyPoint> mvKeys, mvKeysUn; cv::Mat mDescriptors; std::vector<float> mvuRight, mvScaleFactors, mvLevelSigma2;
+    std::vector<MapPointPtr> mvpMapPoints; std::vector<bool> mvbOutlier; float mbf = 40, mb = 0.08f; Camera* mpCamera = nullptr; Pose pose;
+    static float mnMinX, mnMinY, mnMaxX, mnMaxY, mfGridElementWidthInv, mfGridElementHeightInv;
+    Pose GetPose() const { return pose; }
+};
+float Frame::mnMinX = 0, Frame::mnMinY = 0, Frame::mnMaxX = 640, Frame::mnMaxY = 480, Frame::mfGridElementWidthInv = 0.1f, Frame::mfGridElementHeightInv = 0.1f;
+struct KeyFrame : Frame {
+    std::map<unsigned, std::vector<unsigned>> mFeatVec;
+    MapPointPtr GetMapPoint(int i) const { return mvpMapPoints[i]; }
+};
+static void standin_fundamental(const KeyFrame&, const KeyFrame&, float* F12, float* ep) { for (int i = 0; i < 9; ++i) F12[i] = 0; ep[0] = ep[1] = 0; }
+
+#include "../../shim/plvs_shim.hpp"
+
+extern "C" int shim_instantiate(int run)
+{
+    // instantiating every template is the point; nothing executes without a GPU (run == 0)
+    if (!run) return (int)sizeof(PLVS2::ORBextractor) + (int)sizeof(PLVS2::ORBmatcher) + (int)sizeof(chisel_server::ChiselServer);
+    PLVS2::ORBextractor ex(1000, 1.2f, 8, 20, 7);
+    cv::Mat img(480, 640, CV_8U), desc; std::vector<cv::KeyPoint> kps; std::vector<int> lap{0, 0};
+    int mono = ex(img, cv::Mat(), kps, desc, lap);
+    ex.SyncImagePyramid();
+    PLVS2::ORBmatcher m(0.8f, true);
+    Frame F, L; std::vector<MapPointPtr> mps;
+    int a = m.SearchByProjection(F, mps, 3.f, false, 50.f);
+    int b = m.SearchByProjection(F, L, 15.f, false);
+    auto k1 = std::make_shared<KeyFrame>(), k2 = std::make_shared<KeyFrame>();
+    std::vector<std::pair<size_t, size_t>> pairs;
+    int c = m.SearchForTriangulation(k1, k2, pairs, false, false);
+    chisel_server::ChiselServerParams p; chisel_server::ChiselServer cs(p);
+    cs.SetDepthCameraInfo(500, 500, 320, 240, 640, 480);
+    Eigen::Affine3f T; cs.SetDepthPose(T);
+    std::vector<float> d(640 * 480, 1.f); cs.SetDepthImageMemorySharing(d.data(), 640, 480, 640 * 4, 0);
+    cs.IntegrateLastDepthImage(false);
+    return mono + a + b + c;
+}
