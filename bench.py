@@ -282,7 +282,9 @@ def run_b200_arm(a):
             "roofline": roof, "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t2_ms / K},
             "gpu_launches": int(round(launches_per_step * K)), "clocks": clocks,
             "kernel_ms_per_step": {k: round(v[0] / K, 4) for k, v in ktimes.items()}, "gpu_busy_frac": gpu_time_ms / t_ms,
-            "per_step": {"keypoints": agg.get("keypoints", 0) / K, "matches": agg.get("matches", 0) / K}, "wall_s": [wall, wall2]}
+            "per_step": {"keypoints": agg.get("keypoints", 0) / K, "matches": agg.get("matches", 0) / K,
+                         "tsdf_blocks_visited": agg.get("tsdf_candidates", 0) / K, "tsdf_blocks_updated": agg.get("tsdf_updated", 0) / K,
+                         "match_rounds_last_call": hp.match_rounds()}, "wall_s": [wall, wall2]}
     if not a.no_cpu_baseline:
         fps, stages = cpu_reference_run(a, a.cpu_frames, 1, False)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",

@@ -132,6 +132,10 @@ typedef struct {
     int64_t candidates;          /* FAST candidates after per-cell NMS, summed over the batch */
     int64_t keypoints;           /* keypoints, summed over the batch */
     int32_t kernel_launches;     /* kernels launched by the last extract call */
+    float host_wait_candidates_ms;   /* host blocked until FAST candidates arrived (copy-in + pyramid + FAST + compaction) */
+    float host_distribute_ms;        /* DistributeOctTree on host threads, whole batch */
+    float host_wait_describe_ms;     /* host blocked on blur (overlapped) + orientation/descriptor kernel */
+    float host_assemble_ms;          /* copy-out into the caller's vectors */
 } plvs_orb_stats;
 int plvs_orb_last_stats(const plvs_orb* h, plvs_orb_stats* out);
 int plvs_orb_kernel_times(plvs_orb* h, float* ms /*PLVS_K_SLOTS*/, int32_t* launches /*PLVS_K_SLOTS*/, int reset);
@@ -223,6 +227,24 @@ int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const pl
                              const float F12[9], const float ep[2],
                              int only_stereo, int coarse, int check_orientation,
                              int32_t* match12, int* nmatches);
+
+/* Device view of one frame's pyramid (all levels) of an extractor handle: what Frame::ComputeStereoMatches
+ * reads through mpORBextractorLeft/Right->mvImagePyramid (src/Frame.cc:1886,1914). */
+typedef struct {
+    const uint8_t* data[PLVS_MAX_LEVELS];    /* device pointers */
+    int32_t w[PLVS_MAX_LEVELS], h[PLVS_MAX_LEVELS], pitch[PLVS_MAX_LEVELS];
+    int32_t nlevels;
+} plvs_pyramid_view;
+int plvs_orb_pyramid_view(const plvs_orb* h, int frame, int blurred, plvs_pyramid_view* out);
+
+/* Frame::ComputeStereoMatches (src/Frame.cc:1780-1983), rectified stereo: row-band Hamming search (best < 75),
+ * 11x11 SAD refinement over +-5 px on the unblurred level of the left keypoint, parabola sub-pixel fit, depth =
+ * bf/disparity, median-based outlier cut.  left/right: views whose `keys` are mvKeys / mvKeysRight (distorted
+ * coordinates are what the reference uses here) with scale_factors filled; inv_scale = mvInvScaleFactors.
+ * uright/depth (host, left->n entries) receive mvuRight / mvDepth (-1 where unmatched). */
+int plvs_stereo_match(plvs_match* h, const plvs_frame_view* left, const plvs_frame_view* right,
+                      const plvs_pyramid_view* pyr_left, const plvs_pyramid_view* pyr_right, const float* inv_scale,
+                      float mb, float mbf, float* uright, float* depth, int* n_valid);
 
 /* ------------------------------------------------------------------------------------------ */
 /* TSDF -- replaces chisel_server::ChiselServer's integrate path (ChiselServer.h:81-322)       */

@@ -55,3 +55,26 @@ def search_for_triangulation(K1, K2, fv1, fv2, has1, has2, F12, ep, only_stereo=
                                        h2.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p),
                                        int(only_stereo), int(coarse), int(check_ori), m12.ctypes.data_as(C.c_void_p))
     return n, m12[:K1.n]
+
+
+class _Level(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("w", C.c_int), ("h", C.c_int), ("stride", C.c_int)]
+
+
+def compute_stereo_matches(left, right, pyr_left, pyr_right, scale, inv_scale, mb, mbf):
+    """oracle of Frame::ComputeStereoMatches; pyr_* are lists of contiguous uint8 level images (unblurred)."""
+    l = _setup()
+    nl = len(pyr_left)
+    L = (_Level * nl)(); R = (_Level * nl)()
+    keep = []
+    for i in range(nl):
+        a = np.ascontiguousarray(pyr_left[i], np.uint8); b = np.ascontiguousarray(pyr_right[i], np.uint8); keep += [a, b]
+        L[i] = _Level(a.ctypes.data, a.shape[1], a.shape[0], a.strides[0]); R[i] = _Level(b.ctypes.data, b.shape[1], b.shape[0], b.strides[0])
+    sc = np.ascontiguousarray(scale, np.float32); isc = np.ascontiguousarray(inv_scale, np.float32)
+    ur = np.full(max(left.n, 1), -1, np.float32); dp = np.full(max(left.n, 1), -1, np.float32)
+    l.orc_compute_stereo_matches.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    kept = l.orc_compute_stereo_matches(left.n, left.keys.ctypes.data, left.desc.ctypes.data, right.n, right.keys.ctypes.data, right.desc.ctypes.data,
+                                        C.cast(L, C.c_void_p), C.cast(R, C.c_void_p), sc.ctypes.data, isc.ctypes.data, mb, mbf,
+                                        ur.ctypes.data, dp.ctypes.data)
+    return ur[:left.n], dp[:left.n], kept

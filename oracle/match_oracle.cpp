@@ -280,3 +280,100 @@ int orc_search_for_triangulation(const FrameView* K1, const FrameView* K2, const
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// a17: Frame::ComputeStereoMatches (src/Frame.cc:1780-1983) -- rectified stereo row matching with
+// 11x11 SAD refinement on the UNBLURRED pyramid level of the left keypoint, parabola sub-pixel fit,
+// median-based outlier cut.  The reference's pyramid levels sit inside a 19-px BORDER_REFLECT_101
+// frame (src/ORBextractor.cc:1496-1501); the SAD windows may reach up to 10 columns into it on the
+// left, so out-of-level columns are read through the same reflection.
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+struct OrcLevel { const uint8_t* data; int w, h, stride; };
+
+static inline int refl101(int p, int n) { if (p < 0) p = -p; if (p >= n) p = 2 * n - 2 - p; return p; }
+
+int orc_compute_stereo_matches(int N, const KeyPoint* keysL, const uint8_t* descL, int Nr, const KeyPoint* keysR, const uint8_t* descR,
+                               const OrcLevel* pyrL, const OrcLevel* pyrR, const float* scale, const float* inv_scale,
+                               float mb, float mbf, float* uRight, float* depthOut)
+{
+    for (int i = 0; i < N; ++i) { uRight[i] = -1.0f; depthOut[i] = -1.0f; }
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    const int nRows = pyrL[0].h;
+    std::vector<std::vector<int>> rows(nRows);
+    for (int iR = 0; iR < Nr; ++iR) {
+        const float kpY = keysR[iR].y;
+        const float r = 2.0f * scale[keysR[iR].octave];
+        const int maxr = (int)std::ceil(kpY + r), minr = (int)std::floor(kpY - r);
+        for (int yi = minr; yi <= maxr; ++yi) if (yi >= 0 && yi < nRows) rows[yi].push_back(iR);   // the reference indexes unchecked; keypoints are >=19 px inside
+    }
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;
+    std::vector<std::pair<int, int>> vDistIdx;
+    for (int iL = 0; iL < N; ++iL) {
+        const KeyPoint& kpL = keysL[iL];
+        const int levelL = kpL.octave;
+        const float vL = kpL.y, uL = kpL.x;
+        const std::vector<int>& cands = rows[(int)vL];
+        if (cands.empty()) continue;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH; int bestIdxR = 0;
+        for (int iR : cands) {
+            const KeyPoint& kpR = keysR[iR];
+            if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+            const float uR = kpR.x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = hamming(descL + (size_t)iL * 32, descR + (size_t)iR * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (bestDist < thOrbDist) {
+            const float uR0 = keysR[bestIdxR].x;
+            const float sf = inv_scale[kpL.octave];
+            const float scaleduL = std::round(kpL.x * sf), scaledvL = std::round(kpL.y * sf), scaleduR0 = std::round(uR0 * sf);
+            const int w = 5, L = 5;
+            const OrcLevel& IL = pyrL[kpL.octave]; const OrcLevel& IR = pyrR[kpL.octave];
+            int bestD = 2147483647, bestincR = 0;
+            float vDists[11];
+            const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+            if (iniu < 0 || endu >= IR.w) continue;
+            for (int incR = -L; incR <= L; ++incR) {
+                double acc = 0;
+                for (int dy = -w; dy <= w; ++dy)
+                    for (int dx = -w; dx <= w; ++dx) {
+                        const int yl = refl101((int)scaledvL + dy, IL.h), xl = refl101((int)scaleduL + dx, IL.w);
+                        const int yr = refl101((int)scaledvL + dy, IR.h), xr = refl101((int)scaleduR0 + incR + dx, IR.w);
+                        acc += std::abs((int)IL.data[(size_t)yl * IL.stride + xl] - (int)IR.data[(size_t)yr * IR.stride + xr]);
+                    }
+                const float dist = (float)acc;            // cv::norm returns double, stored into float
+                if (dist < bestD) { bestD = (int)dist; bestincR = incR; }
+                vDists[L + incR] = dist;
+            }
+            if (bestincR == -L || bestincR == L) continue;
+            const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+            const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = scale[kpL.octave] * ((float)scaleduR0 + (float)bestincR + deltaR);
+            float disparity = (uL - bestuR);
+            if (disparity >= minD && disparity < maxD) {
+                if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+                depthOut[iL] = mbf / disparity;
+                uRight[iL] = bestuR;
+                vDistIdx.push_back(std::pair<int, int>(bestD, iL));
+            }
+        }
+    }
+    if (vDistIdx.empty()) return 0;          // (the reference would index an empty vector here)
+    std::sort(vDistIdx.begin(), vDistIdx.end());
+    const float median = (float)vDistIdx[vDistIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    int kept = (int)vDistIdx.size();
+    for (int i = (int)vDistIdx.size() - 1; i >= 0; --i) {
+        if (vDistIdx[i].first < thDist) break;
+        uRight[vDistIdx[i].second] = -1; depthOut[vDistIdx[i].second] = -1; --kept;
+    }
+    return kept;
+}
+
+}  // extern "C"

@@ -27,7 +27,8 @@ class OrbParams(C.Structure):
 
 class OrbStats(C.Structure):
     _fields_ = [("pyramid_pixels", C.c_int64), ("candidates", C.c_int64), ("keypoints", C.c_int64),
-                ("kernel_launches", C.c_int32)]
+                ("kernel_launches", C.c_int32), ("host_wait_candidates_ms", C.c_float), ("host_distribute_ms", C.c_float),
+                ("host_wait_describe_ms", C.c_float), ("host_assemble_ms", C.c_float)]
 
 
 class OrbDeviceView(C.Structure):
@@ -43,6 +44,11 @@ class FrameView(C.Structure):
                 ("grid_inv_w", C.c_float), ("grid_inv_h", C.c_float),
                 ("scale_factors", C.c_float * MAX_LEVELS), ("level_sigma2", C.c_float * MAX_LEVELS),
                 ("nlevels", C.c_int32), ("bf", C.c_float), ("on_device", C.c_int32)]
+
+
+class PyramidView(C.Structure):
+    _fields_ = [("data", C.c_void_p * MAX_LEVELS), ("w", C.c_int32 * MAX_LEVELS), ("h", C.c_int32 * MAX_LEVELS),
+                ("pitch", C.c_int32 * MAX_LEVELS), ("nlevels", C.c_int32)]
 
 
 class FeatVec(C.Structure):
@@ -98,6 +104,9 @@ def load():
     lib.plvs_match_projection_last.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                                C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     lib.plvs_match_triangulation.argtypes = [C.c_void_p] * 9 + [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    lib.plvs_orb_pyramid_view.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(PyramidView)]
+    lib.plvs_stereo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                      C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     lib.plvs_tsdf_default_params.restype = None
     lib.plvs_tsdf_default_params.argtypes = [C.POINTER(TsdfParams)]
     lib.plvs_tsdf_create.argtypes = [C.POINTER(TsdfParams), C.c_int, C.POINTER(C.c_void_p)]

@@ -39,8 +39,8 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
 
 // ---------------------------------------------------------------------------------------------
 // Frame::AssignFeaturesToGrid (src/Frame.cc:716-746): 64x48 cells, cell = round((p-min)*inv),
-// indices appended in keypoint order.  One CTA: histogram, scan, then ONE warp scatters in index
-// order (match_any ranks equal cells inside a 32-keypoint step) so every cell list is ascending.
+// indices appended in keypoint order.  One CTA: histogram, scan, unordered scatter, per-cell insertion sort
+// (cells hold a handful of keypoints), so every cell list is ascending == the reference's push_back order.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 k_build_grid(const plvs_keypoint* __restrict__ keys, int n, GridParams gp, int* __restrict__ cell_start /*GRID_CELLS+1*/,
@@ -83,18 +83,17 @@ k_build_grid(const plvs_keypoint* __restrict__ keys, int n, GridParams gp, int* 
     __syncthreads();
     for (int i = tid; i <= GRID_CELLS; i += 1024) cell_start[i] = s_cnt[i];
     __syncthreads();
-    if (wid == 0) {      // stable scatter; s_cnt doubles as the per-cell cursor
-        for (int b = 0; b < n; b += 32) {
-            const int i = b + lane;
-            const int c = i < n ? kp_cell[i] : -1;
-            const uint32_t same = __match_any_sync(0xffffffffu, c);
-            if (c >= 0) {
-                const int rank = __popc(same & ((1u << lane) - 1));
-                sorted[s_cnt[c] + rank] = i;
-            }
-            __syncwarp();
-            if (c >= 0 && (same >> lane) <= 1u) s_cnt[c] += __popc(same);   // highest lane of the group advances the cursor
-            __syncwarp();
+    // scatter in arbitrary order (s_cnt doubles as the per-cell cursor), then every cell list -- they hold
+    // 0-3 entries in practice -- is put back into ascending index order (== push_back order) by one thread
+    for (int i = tid; i < n; i += 1024) { const int c = kp_cell[i]; if (c >= 0) sorted[atomicAdd(&s_cnt[c], 1)] = i; }
+    __syncthreads();
+    for (int c = tid; c < GRID_CELLS; c += 1024) {
+        const int b0 = cell_start[c], b1 = cell_start[c + 1];
+        for (int i = b0 + 1; i < b1; ++i) {
+            const int v = sorted[i];
+            int j = i - 1;
+            while (j >= b0 && sorted[j] > v) { sorted[j + 1] = sorted[j]; --j; }
+            sorted[j + 1] = v;
         }
     }
 }
@@ -189,64 +188,150 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// Phase B: claim resolution by fixed-point rounds (single CTA; thread <-> query, strided).
+// Phase B: claim resolution by fixed-point rounds on ONE thread-block cluster (8 CTAs x 32 warps, one
+// warp per query per pass; rounds are separated by cluster barriers, claims live in L2).
 // claim[idx] = lowest query index with Observations()>0 currently targeting idx (blocks later ones).
+// The reference's running best / second-best over the candidate sequence equals the two smallest
+// (distance, position) keys of the unblocked candidates, so a warp finds them with shuffles:
+//   best   = lexicographic min (dist, pos)                       -> first strict minimum, as `dist<bestDist`
+//   second = lexicographic min over the rest                     -> what `else if(dist<bestDist2)` / the
+//                                                                   demotion of the old best leave behind
 // ---------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(1024)
+constexpr int kResolveCtas = 8;
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o)
+{
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, o), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), o);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t cluster_cta_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+
+// SMEM == true: every CTA keeps (a) a private copy of the claim table and (b) the candidate lists of the
+// queries its warps own in shared memory, so a round costs one coalesced L2 read of the table plus
+// shared-memory traffic; SMEM == false reads lists and claims from L2 (any size).
+template <int MODE, bool SMEM>
+__global__ void __cluster_dims__(kResolveCtas, 1, 1) __launch_bounds__(1024)
 k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int cap, const void* __restrict__ queries, int nq,
           const plvs_keypoint* __restrict__ keys, int n, const uint8_t* __restrict__ claimed_in, float nn_ratio, int check_ori,
-          int* __restrict__ claim_a, int* __restrict__ claim_b, int* __restrict__ target /*nq*/,
-          int32_t* __restrict__ assign /*n*/, int* __restrict__ result /*[0]=nmatches,[1]=rounds*/)
+          int* claim_a, int* claim_b, int* target /*nq*/, int* state /*[2] changed flags, zeroed by the host*/,
+          int32_t* assign /*n, device*/, int32_t* assign_out /*n, mapped host*/, int* result /*[0]=nmatches,[1]=rounds*/, int slots)
 {
-    __shared__ int s_changed, s_count, s_hist[HISTO], s_keep[HISTO];
-    const int tid = threadIdx.x;
+    extern __shared__ uint32_t s_dyn[];
+    __shared__ int s_count, s_hist[HISTO], s_keep[HISTO];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int crank = (int)cluster_cta_rank();
+    const int gtid = crank * 1024 + tid, gthreads = kResolveCtas * 1024;
+    const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
     const int INF = 0x7fffffff;
-    for (int i = tid; i < n; i += 1024) { claim_a[i] = INF; claim_b[i] = INF; }
-    for (int i = tid; i < nq; i += 1024) target[i] = -1;
-    __syncthreads();
+    const unsigned long long KINF = ~0ull;
+    // shared layout (SMEM): claims[n] | per-warp list lengths [32*slots] | per-warp lists [32*slots*cap]
+    int* s_claim = reinterpret_cast<int*>(s_dyn);
+    int* s_len = s_claim + (SMEM ? n : 0);
+    uint32_t* s_list = reinterpret_cast<uint32_t*>(s_len + (SMEM ? 32 * slots : 0));
+    for (int i = gtid; i < n; i += gthreads) { claim_a[i] = INF; claim_b[i] = INF; }
+    for (int i = gtid; i < nq; i += gthreads) target[i] = -1;
+    if (SMEM) {
+        for (int sl = 0; sl < slots; ++sl) {
+            const int q = gwarp + sl * gwarps;
+            const int m = q < nq ? min(cand_n[q], cap) : 0;
+            if (lane == 0) s_len[wid * slots + sl] = m;
+            const uint32_t* c = cand + (size_t)q * cap;
+            uint32_t* d = s_list + (size_t)(wid * slots + sl) * cap;
+            for (int k = lane; k < m; k += 32) {
+                uint32_t e = c[k];
+                if (claimed_in && claimed_in[cand_idx(e)]) e = 0xffffffffu;      // pre-claimed keypoints never compete
+                d[k] = e;
+            }
+        }
+    }
+    cluster_sync_all();
     int* cur = claim_a; int* nxt = claim_b;
     int rounds = 0;
     for (;;) {
-        if (tid == 0) s_changed = 0;
-        __syncthreads();
-        for (int q = tid; q < nq; q += 1024) {
-            const uint32_t* c = cand + (size_t)q * cap;
-            const int m = min(cand_n[q], cap);
-            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-            for (int k = 0; k < m; ++k) {
-                const uint32_t e = c[k];
-                const int idx = cand_idx(e);
-                if (claimed_in && claimed_in[idx]) continue;
-                if (cur[idx] < q) continue;
-                const int dist = cand_dist(e);
-                if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = cand_level(e); bestIdx = idx; }
-                else if (MODE == 0 && dist < bestDist2) { bestLevel2 = cand_level(e); bestDist2 = dist; }
-            }
-            int t = -1;
-            if (bestDist <= TH_HIGH) {
-                if (MODE == 0) {
-                    if (!(bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) &&
-                        (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2)) t = bestIdx;
-                } else t = bestIdx;
-            }
-            if (t != target[q]) { target[q] = t; s_changed = 1; }
+        const int par = rounds & 1;
+        bool changed_here = false;
+        if (SMEM) {
+            for (int i = tid; i < n; i += 1024) s_claim[i] = rounds ? __ldcg(&cur[i]) : INF;
+            __syncthreads();
         }
-        __syncthreads();
-        const int changed = s_changed;
+        for (int sl = 0; sl < slots; ++sl) {
+            const int q = gwarp + sl * gwarps;
+            if (q >= nq) break;
+            unsigned long long k1 = KINF, k2 = KINF;
+            if (SMEM) {
+                const uint32_t* c = s_list + (size_t)(wid * slots + sl) * cap;
+                const int m = s_len[wid * slots + sl];
+                for (int k = lane; k < m; k += 32) {
+                    const uint32_t e = c[k];
+                    if (e == 0xffffffffu || s_claim[cand_idx(e)] < q) continue;
+                    const unsigned long long key = ((unsigned long long)cand_dist(e) << 48) | ((unsigned long long)k << 32) | e;
+                    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                }
+            } else {
+                const uint32_t* c = cand + (size_t)q * cap;
+                const int m = min(cand_n[q], cap);
+                for (int k = lane; k < m; k += 32) {
+                    const uint32_t e = c[k];
+                    const int idx = cand_idx(e);
+                    if ((claimed_in && claimed_in[idx]) || __ldcg(&cur[idx]) < q) continue;
+                    const unsigned long long key = ((unsigned long long)cand_dist(e) << 48) | ((unsigned long long)k << 32) | e;
+                    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const unsigned long long o1 = shfl_xor_u64(k1, o), o2 = shfl_xor_u64(k2, o);
+                const unsigned long long lo = k1 < o1 ? k1 : o1, hi = k1 < o1 ? o1 : k1;
+                const unsigned long long s2 = k2 < o2 ? k2 : o2;
+                k1 = lo; k2 = hi < s2 ? hi : s2;
+            }
+            if (lane == 0) {
+                int t = -1;
+                if (k1 != KINF) {
+                    const uint32_t e1 = (uint32_t)k1;
+                    const int bestDist = cand_dist(e1);
+                    if (bestDist <= TH_HIGH) {
+                        if (MODE == 0) {
+                            const int bestLevel = cand_level(e1);
+                            const int bestDist2 = k2 != KINF ? cand_dist((uint32_t)k2) : 256;
+                            const int bestLevel2 = k2 != KINF ? cand_level((uint32_t)k2) : -1;
+                            if (!(bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) &&
+                                (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2)) t = cand_idx(e1);
+                        } else t = cand_idx(e1);
+                    }
+                }
+                if (t != target[q]) { target[q] = t; changed_here = true; }
+            }
+        }
+        if (__syncthreads_or(changed_here ? 1 : 0) && tid == 0) atomicOr(&state[par], 1);
+        cluster_sync_all();
+        const int changed = __ldcg(&state[par]);
         ++rounds;
         if (!changed) break;
-        for (int i = tid; i < n; i += 1024) nxt[i] = INF;
-        __syncthreads();
-        for (int q = tid; q < nq; q += 1024) {
-            const int t = target[q];
+        if (gtid == 0) state[par ^ 1] = 0;
+        for (int i = gtid; i < n; i += gthreads) nxt[i] = INF;
+        cluster_sync_all();
+        for (int q = gtid; q < nq; q += gthreads) {
+            const int t = __ldcg(&target[q]);
             const uint32_t flags = MODE == 0 ? reinterpret_cast<const plvs_mp_query*>(queries)[q].flags
                                              : reinterpret_cast<const plvs_last_query*>(queries)[q].flags;
             if (t >= 0 && (flags & PLVS_Q_OBS_POSITIVE)) atomicMin(&nxt[t], q);
         }
-        __syncthreads();
+        cluster_sync_all();
         int* tmp = cur; cur = nxt; nxt = tmp;
     }
+    if (crank != 0) return;        // the wrap-up is one cheap pass: CTA 0 finishes alone (no cluster barrier after this point)
     // final holders: the last (highest) query that wrote each keypoint
     for (int i = tid; i < n; i += 1024) assign[i] = -1;
     if (tid == 0) s_count = 0;
@@ -254,7 +339,7 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
     __syncthreads();
     int local = 0;
     for (int q = tid; q < nq; q += 1024) {
-        const int t = target[q];
+        const int t = __ldcg(&target[q]);
         if (t < 0) continue;
         ++local;
         atomicMax(&assign[t], q);
@@ -285,7 +370,7 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
         __syncthreads();
         int dropped = 0;
         for (int q = tid; q < nq; q += 1024) {
-            const int t = target[q];
+            const int t = __ldcg(&target[q]);
             if (t < 0) continue;
             const float factor = HISTO / 360.0f;
             float rot = reinterpret_cast<const plvs_last_query*>(queries)[q].angle - keys[t].angle;
@@ -295,8 +380,9 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
             if (!s_keep[bin]) { assign[t] = -1; ++dropped; }       // the reference nulls the slot whoever holds it now
         }
         atomicSub(&s_count, dropped);
-        __syncthreads();
     }
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) assign_out[i] = assign[i];
     if (tid == 0) { result[0] = s_count; result[1] = rounds; }
 }
 
@@ -365,7 +451,7 @@ k_triangulate(ViewDev K1, ViewDev K2, FvDev f1, FvDev f2, const uint8_t* __restr
 
 __global__ void __launch_bounds__(1024)
 k_tri_finish(const plvs_keypoint* __restrict__ k1, const plvs_keypoint* __restrict__ k2, int n1, int check_ori,
-             int32_t* __restrict__ match12, int* __restrict__ result)
+             int32_t* __restrict__ match12, int32_t* __restrict__ match_out, int* __restrict__ result)
 {
     __shared__ int s_hist[HISTO], s_keep[HISTO], s_count;
     const int tid = threadIdx.x;
@@ -413,14 +499,157 @@ k_tri_finish(const plvs_keypoint* __restrict__ k1, const plvs_keypoint* __restri
             if (!s_keep[bin]) { match12[i] = -1; ++dropped; }
         }
         atomicSub(&s_count, dropped);
-        __syncthreads();
     }
+    __syncthreads();
+    for (int i = tid; i < n1; i += 1024) match_out[i] = match12[i];
     if (tid == 0) result[0] = s_count;
 }
 
 __global__ void k_fill_i32(int32_t* p, int n, int32_t v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// a17  Frame::ComputeStereoMatches (src/Frame.cc:1780-1983).  One warp per left keypoint:
+//  (1) lanes sweep the right keypoints: row band (vRowIndices membership), octave window, disparity range,
+//      Hamming; winner = smallest distance, first index on ties (`dist<bestDist` over ascending iR);
+//  (2) if < (TH_HIGH+TH_LOW)/2: 11 SAD windows of 11x11 px on the unblurred level of the LEFT keypoint,
+//      lanes over the 121 pixels, integer sums (exact), first minimum wins; parabola fit in fp32 as written;
+//  (3) a single-CTA pass selects the median SAD (radix select on the 15-bit values) and applies the
+//      1.5*1.4*median cut.  Columns left of the level are read through BORDER_REFLECT_101 like the
+//      reference's bordered pyramid buffers.
+// ---------------------------------------------------------------------------------------------
+struct PyrDev { const uint8_t* data[PLVS_MAX_LEVELS]; int w[PLVS_MAX_LEVELS], h[PLVS_MAX_LEVELS], pitch[PLVS_MAX_LEVELS]; };
+struct StereoScales { float scale[PLVS_MAX_LEVELS], inv[PLVS_MAX_LEVELS]; };
+
+__device__ __forceinline__ int refl101(int p, int n) { if (p < 0) p = -p; if (p >= n) p = 2 * n - 2 - p; return p; }
+
+__global__ void __launch_bounds__(256)
+k_stereo_rows(const plvs_keypoint* __restrict__ kl, const uint8_t* __restrict__ dl, int n,
+              const plvs_keypoint* __restrict__ kr, const uint8_t* __restrict__ dr, int nr,
+              PyrDev PL, PyrDev PR, StereoScales S, int n_rows, float mb, float mbf,
+              float* __restrict__ uright, float* __restrict__ depth, int* __restrict__ sad /*n: best SAD or -1*/)
+{
+    const int iL = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (iL >= n) return;
+    const plvs_keypoint kpL = kl[iL];
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    const int row = (int)vL;
+    const float minD = 0.f, maxD = mbf / mb;
+    const float minU = uL - maxD, maxU = uL - minD;
+    float out_u = -1.0f, out_d = -1.0f; int out_sad = -1;
+    if (!(maxU < 0) && row >= 0 && row < n_rows) {
+        const uint4 a0 = *reinterpret_cast<const uint4*>(dl + (size_t)iL * 32), a1 = *reinterpret_cast<const uint4*>(dl + (size_t)iL * 32 + 16);
+        int best = 0x7fffffff;          // dist * 65536 + iR: lexicographic (dist, iR)
+        for (int iR = lane; iR < nr; iR += 32) {
+            const plvs_keypoint r = kr[iR];
+            const float rr = 2.0f * S.scale[r.octave];
+            if (row < (int)floorf(r.y - rr) || row > (int)ceilf(r.y + rr)) continue;      // vRowIndices[row] membership
+            if (r.octave < levelL - 1 || r.octave > levelL + 1) continue;
+            if (!(r.x >= minU && r.x <= maxU)) continue;
+            const int dist = hamming256(a0, a1, dr + (size_t)iR * 32);
+            if (dist < TH_HIGH) best = min(best, dist * 65536 + iR);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (best != 0x7fffffff && (best >> 16) < (TH_HIGH + TH_LOW) / 2) {
+            const int bestIdxR = best & 0xffff;
+            const float uR0 = kr[bestIdxR].x;
+            const float sf = S.inv[levelL];
+            const int su = (int)roundf(kpL.x * sf), sv = (int)roundf(kpL.y * sf), sr = (int)roundf(uR0 * sf);
+            const int w = 5, L = 5;
+            const uint8_t* IL = PL.data[levelL]; const uint8_t* IR = PR.data[levelL];
+            const int wl = PL.w[levelL], hl = PL.h[levelL], pl = PL.pitch[levelL], wr = PR.w[levelL], hr = PR.h[levelL], pr = PR.pitch[levelL];
+            const float iniu = (float)sr + L - w, endu = (float)sr + L + w + 1;
+            if (!(iniu < 0 || endu >= (float)wr)) {
+                int vl[4], py[4], px[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int p = lane + 32 * k;
+                    py[k] = p / 11 - w; px[k] = p % 11 - w;
+                    vl[k] = p < 121 ? IL[(size_t)refl101(sv + py[k], hl) * pl + refl101(su + px[k], wl)] : 0;
+                }
+                float vd[11];
+                int bestD = 0x7fffffff, bestinc = 0;
+#pragma unroll
+                for (int inc = -L; inc <= L; ++inc) {
+                    int acc = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int p = lane + 32 * k;
+                        if (p < 121) acc += abs(vl[k] - (int)IR[(size_t)refl101(sv + py[k], hr) * pr + refl101(sr + inc + px[k], wr)]);
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    const float dist = (float)acc;
+                    if (dist < (float)bestD) { bestD = (int)dist; bestinc = inc; }
+                    vd[L + inc] = dist;
+                }
+                if (!(bestinc == -L || bestinc == L)) {
+                    float d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 11; ++k) { if (k == L + bestinc - 1) d1 = vd[k]; if (k == L + bestinc) d2 = vd[k]; if (k == L + bestinc + 1) d3 = vd[k]; }
+                    const float deltaR = (d1 - d3) / (2.0f * (d1 + d3 - 2.0f * d2));
+                    if (!(deltaR < -1 || deltaR > 1)) {
+                        float bestuR = S.scale[levelL] * ((float)sr + (float)bestinc + deltaR);
+                        float disparity = uL - bestuR;
+                        if (disparity >= minD && disparity < maxD) {
+                            if (disparity <= 0) { disparity = 0.01f; bestuR = uL - 0.01f; }
+                            out_d = mbf / disparity; out_u = bestuR; out_sad = bestD;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { uright[iL] = out_u; depth[iL] = out_d; sad[iL] = out_sad; }
+}
+
+__global__ void __launch_bounds__(1024)
+k_stereo_median(int n, const int* __restrict__ sad, float* __restrict__ uright, float* __restrict__ depth, float* __restrict__ uright_out,
+                float* __restrict__ depth_out, int* __restrict__ result)
+{
+    __shared__ int s_cnt, s_total, s_prefix, s_rank;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_total = 0; }
+    __syncthreads();
+    int local = 0;
+    for (int i = tid; i < n; i += 1024) local += sad[i] >= 0;
+    atomicAdd(&s_total, local);
+    __syncthreads();
+    const int total = s_total;
+    int kept = 0;
+    if (total > 0) {
+        // k-th smallest (k = total/2, 0-based) by radix select from the most significant of 15 bits
+        if (tid == 0) { s_prefix = 0; s_rank = total / 2; }
+        __syncthreads();
+        for (int bit = 14; bit >= 0; --bit) {
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            const int prefix = s_prefix, mask_hi = ~((1 << (bit + 1)) - 1) & 0x7fff;
+            int c = 0;
+            for (int i = tid; i < n; i += 1024) { const int v = sad[i]; if (v >= 0 && (v & mask_hi) == prefix && !(v & (1 << bit))) ++c; }
+            atomicAdd(&s_cnt, c);
+            __syncthreads();
+            if (tid == 0) { if (s_rank >= s_cnt) { s_rank -= s_cnt; s_prefix |= 1 << bit; } }
+            __syncthreads();
+        }
+        const float median = (float)s_prefix;
+        const float thDist = 1.5f * 1.4f * median;
+        for (int i = tid; i < n; i += 1024) {
+            const int v = sad[i];
+            if (v >= 0 && !((float)v < thDist)) { uright[i] = -1.f; depth[i] = -1.f; }
+            else if (v >= 0) ++kept;
+        }
+    }
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    atomicAdd(&s_cnt, kept);
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) { uright_out[i] = uright[i]; depth_out[i] = depth[i]; }
+    if (tid == 0) result[0] = s_cnt;
+}
 
 struct plvs_match {
     int device = 0;
@@ -430,11 +659,13 @@ struct plvs_match {
     DevBuf<uint8_t> d_desc[2], d_has[2], d_claimed;
     DevBuf<float> d_uright[2], d_f12;
     DevBuf<uint8_t> d_query;
-    DevBuf<int> d_cell_start, d_sorted, d_kp_cell, d_cand_n, d_claim_a, d_claim_b, d_target;
+    DevBuf<int> d_cell_start, d_sorted, d_kp_cell, d_cand_n, d_claim_a, d_claim_b, d_target, d_state;
     DevBuf<uint32_t> d_cand;
     DevBuf<uint32_t> d_fv_ids[2];
     DevBuf<int> d_fv_off[2], d_fv_feat[2];
     DevBuf<int32_t> d_assign;
+    DevBuf<float> d_su, d_sd;
+    PinBuf<float> p_su, p_sd;
     PinBuf<int32_t> p_assign;
     PinBuf<int> p_result, p_cand_n;
     int cap = 128;
@@ -497,7 +728,7 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         d_claimed = h->d_claimed.p;
     }
     if ((rc = h->d_cell_start.alloc(GRID_CELLS + 1)) || (rc = h->d_sorted.alloc(n)) || (rc = h->d_kp_cell.alloc(n)) ||
-        (rc = h->d_cand_n.alloc(nq)) || (rc = h->d_claim_a.alloc(n)) || (rc = h->d_claim_b.alloc(n)) || (rc = h->d_target.alloc(nq)) ||
+        (rc = h->d_cand_n.alloc(nq)) || (rc = h->d_state.alloc(2)) || (rc = h->d_claim_a.alloc(n)) || (rc = h->d_claim_b.alloc(n)) || (rc = h->d_target.alloc(nq)) ||
         (rc = h->d_assign.alloc(n)) || (rc = h->p_assign.alloc(n)) || (rc = h->p_result.alloc(4)) || (rc = h->p_cand_n.alloc(nq)))
         return rc;
     int launches = 0;
@@ -514,8 +745,25 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         ++launches;
         PLVS_CUDA(cudaMemcpyAsync(h->p_cand_n.h, h->d_cand_n.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
         h->timer.begin(PLVS_MATCH_K_RESOLVE, st);
-        k_resolve<MODE><<<1, 1024, 0, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
-                                            h->d_claim_a.p, h->d_claim_b.p, h->d_target.p, h->p_assign.d, h->p_result.d);
+        PLVS_CUDA(cudaMemsetAsync(h->d_state.p, 0, 2 * sizeof(int), st));
+        {
+            const int slots = div_up(nq, kResolveCtas * 32);
+            const size_t smem = ((size_t)n + (size_t)32 * slots + (size_t)32 * slots * h->cap) * sizeof(uint32_t);
+            if (smem <= 200 * 1024) {
+                static thread_local bool attr_set[2] = {false, false};
+                if (!attr_set[MODE]) {
+                    PLVS_CUDA(cudaFuncSetAttribute(k_resolve<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    attr_set[MODE] = true;
+                }
+                k_resolve<MODE, true><<<kResolveCtas, 1024, smem, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
+                                                                        h->d_claim_a.p, h->d_claim_b.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d,
+                                                                        h->p_result.d, slots);
+            } else {
+                k_resolve<MODE, false><<<kResolveCtas, 1024, 0, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
+                                                                      h->d_claim_a.p, h->d_claim_b.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d,
+                                                                      h->p_result.d, slots);
+            }
+        }
         h->timer.end(st);
         ++launches;
         PLVS_CUDA(cudaGetLastError());
@@ -642,12 +890,12 @@ int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const pl
         if ((rc = h->d_has[1].alloc(n2))) return rc;
         PLVS_CUDA(cudaMemcpyAsync(h->d_has[1].p, has_mp2, n2, cudaMemcpyHostToDevice, st)); dh2 = h->d_has[1].p;
     }
-    if ((rc = h->d_f12.alloc(16)) || (rc = h->p_assign.alloc(n1)) || (rc = h->p_result.alloc(4))) return rc;
+    if ((rc = h->d_f12.alloc(16)) || (rc = h->p_assign.alloc(n1)) || (rc = h->d_assign.alloc(n1)) || (rc = h->p_result.alloc(4))) return rc;
     PLVS_CUDA(cudaMemcpyAsync(h->d_f12.p, F12, 9 * sizeof(float), cudaMemcpyHostToDevice, st));
     h->timer.begin(PLVS_MATCH_K_TRIANGULATE, st);
-    k_fill_i32<<<div_up(n1, 256), 256, 0, st>>>(h->p_assign.d, n1, -1);
-    k_triangulate<<<D1.n_nodes, 256, 0, st>>>(V1, V2, D1, D2, dh1, dh2, h->d_f12.p, ep[0], ep[1], only_stereo, coarse, h->p_assign.d);
-    k_tri_finish<<<1, 1024, 0, st>>>(V1.keys, V2.keys, n1, check_orientation, h->p_assign.d, h->p_result.d);
+    k_fill_i32<<<div_up(n1, 256), 256, 0, st>>>(h->d_assign.p, n1, -1);
+    k_triangulate<<<D1.n_nodes, 256, 0, st>>>(V1, V2, D1, D2, dh1, dh2, h->d_f12.p, ep[0], ep[1], only_stereo, coarse, h->d_assign.p);
+    k_tri_finish<<<1, 1024, 0, st>>>(V1.keys, V2.keys, n1, check_orientation, h->d_assign.p, h->p_assign.d, h->p_result.d);
     h->timer.end(st);
     PLVS_CUDA(cudaGetLastError());
     PLVS_CUDA(cudaStreamSynchronize(st));
@@ -655,6 +903,42 @@ int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const pl
     std::memcpy(match12, h->p_assign.h, (size_t)n1 * 4);
     *nmatches = h->p_result.h[0];
     h->last_launches = 3;
+    return PLVS_OK;
+}
+
+int plvs_stereo_match(plvs_match* h, const plvs_frame_view* left, const plvs_frame_view* right,
+                      const plvs_pyramid_view* pyr_left, const plvs_pyramid_view* pyr_right, const float* inv_scale,
+                      float mb, float mbf, float* uright, float* depth, int* n_valid)
+{
+    if (!h || !left || !right || !pyr_left || !pyr_right || !inv_scale || !uright || !depth) { set_error("null argument"); return PLVS_EINVAL; }
+    if (!(mb > 0.f)) { set_error("baseline must be positive"); return PLVS_EINVAL; }
+    std::lock_guard<std::mutex> lock(h->mu);
+    PLVS_CUDA(cudaSetDevice(h->device));
+    ViewDev VL, VR;
+    int rc;
+    if ((rc = stage_view(h, 0, left, &VL)) || (rc = stage_view(h, 1, right, &VR))) return rc;
+    const int n = left->n, nr = right->n;
+    for (int i = 0; i < n; ++i) { uright[i] = -1.f; depth[i] = -1.f; }
+    if (n_valid) *n_valid = 0;
+    if (n == 0 || nr == 0) return PLVS_OK;
+    PyrDev PL{}, PR{}; StereoScales S{};
+    const int nl = std::min(pyr_left->nlevels, (int)PLVS_MAX_LEVELS);
+    for (int l = 0; l < nl; ++l) {
+        PL.data[l] = pyr_left->data[l]; PL.w[l] = pyr_left->w[l]; PL.h[l] = pyr_left->h[l]; PL.pitch[l] = pyr_left->pitch[l];
+        PR.data[l] = pyr_right->data[l]; PR.w[l] = pyr_right->w[l]; PR.h[l] = pyr_right->h[l]; PR.pitch[l] = pyr_right->pitch[l];
+        S.scale[l] = left->scale_factors[l]; S.inv[l] = inv_scale[l];
+    }
+    if ((rc = h->d_su.alloc(n)) || (rc = h->d_sd.alloc(n)) || (rc = h->d_assign.alloc(n)) || (rc = h->p_su.alloc(n)) || (rc = h->p_sd.alloc(n)) ||
+        (rc = h->p_result.alloc(4))) return rc;
+    cudaStream_t st = h->stream;
+    k_stereo_rows<<<div_up(n, 8), 256, 0, st>>>(VL.keys, VL.desc, n, VR.keys, VR.desc, nr, PL, PR, S, PL.h[0], mb, mbf, h->d_su.p, h->d_sd.p, h->d_assign.p);
+    k_stereo_median<<<1, 1024, 0, st>>>(n, h->d_assign.p, h->d_su.p, h->d_sd.p, h->p_su.d, h->p_sd.d, h->p_result.d);
+    PLVS_CUDA(cudaGetLastError());
+    PLVS_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(uright, h->p_su.h, (size_t)n * 4);
+    std::memcpy(depth, h->p_sd.h, (size_t)n * 4);
+    if (n_valid) *n_valid = h->p_result.h[0];
+    h->last_launches = 2;
     return PLVS_OK;
 }
 

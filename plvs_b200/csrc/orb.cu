@@ -1,6 +1,7 @@
 // ORB extractor: handle, geometry tables, launch sequence and the extern "C" entry points that
 // replace PLVS2::ORBextractor (reference: include/ORBextractor.h:59-170, src/ORBextractor.cc).
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <cmath>
 #include <mutex>
@@ -39,7 +40,8 @@ struct plvs_orb {
     DevBuf<CellDesc> d_cells;
     DevBuf<TileDesc> d_tiles;
     DevBuf<BilinearTap> d_taps;
-    DevBuf<uint32_t> d_slots, d_cand;
+    DevBuf<uint32_t> d_slots, d_cand, d_sel;
+    DevBuf<int> d_sel_off;
     DevBuf<int> d_cell_count, d_cand_count;
     DevBuf<plvs_keypoint> d_kp;
     DevBuf<uint8_t> d_desc;
@@ -192,6 +194,8 @@ int setup_geometry(plvs_orb* o, int w, int h, int batch)
     if ((rc = o->p_cand.alloc((size_t)slot_total * B))) return rc;
     if ((rc = o->p_cand_count.alloc((size_t)nl * B))) return rc;
     if ((rc = o->p_sel.alloc((size_t)o->sel_cap * B))) return rc;
+    if ((rc = o->d_sel.alloc((size_t)o->sel_cap * B))) return rc;
+    if ((rc = o->d_sel_off.alloc((size_t)(nl + 1) * B))) return rc;
     if ((rc = o->p_sel_off.alloc((size_t)(nl + 1) * B))) return rc;
     if ((rc = o->p_kp.alloc((size_t)o->sel_cap * B))) return rc;
     if ((rc = o->p_desc.alloc((size_t)o->sel_cap * B * 32))) return rc;
@@ -303,7 +307,9 @@ int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, i
     o->timer.end(st);
     ++launches;
     PLVS_CUDA(cudaGetLastError());
+    const auto tp0 = std::chrono::steady_clock::now();
     PLVS_CUDA(cudaEventSynchronize(o->ev));
+    const auto tp1 = std::chrono::steady_clock::now();
 
     // ---- DistributeOctTree per (frame, level) on host threads
     const int ntask = batch * nl;
@@ -330,6 +336,7 @@ int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, i
         if (nthreads == 1) work();
         else { for (int i = 0; i < nthreads; ++i) pool.emplace_back(work); for (auto& th : pool) th.join(); }
     }
+    const auto tp2 = std::chrono::steady_clock::now();
     int64_t ncand = 0, nkp = 0;
     int max_k = 0;
     o->n_kp.assign(batch, 0);
@@ -350,14 +357,18 @@ int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, i
         max_k = std::max(max_k, k);
     }
     if (max_k > 0) {
+        // selected keypoints go down in two DMA copies from pinned memory (kernels do not read host memory)
+        PLVS_CUDA(cudaMemcpyAsync(o->d_sel.p, o->p_sel.h, (size_t)o->sel_cap * batch * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        PLVS_CUDA(cudaMemcpyAsync(o->d_sel_off.p, o->p_sel_off.h, (size_t)(nl + 1) * batch * sizeof(int), cudaMemcpyHostToDevice, st));
         o->timer.begin(PLVS_ORB_K_DESCRIBE, st);
-        k_orient_describe<<<dim3(div_up(max_k, 8), batch), 256, 0, st>>>(o->d_pyr.p, o->d_blur.p, o->frame_stride, o->d_lv.p, nl, o->p_sel.d, o->p_sel_off.d,
+        k_orient_describe<<<dim3(div_up(max_k, 8), batch), 256, 0, st>>>(o->d_pyr.p, o->d_blur.p, o->frame_stride, o->d_lv.p, nl, o->d_sel.p, o->d_sel_off.p,
                                                                           o->sel_cap, o->d_kp.p, o->d_desc.p, o->p_kp.d, o->p_desc.d);
         o->timer.end(st);
         ++launches;
     }
     PLVS_CUDA(cudaGetLastError());
     PLVS_CUDA(cudaStreamSynchronize(st));
+    const auto tp3 = std::chrono::steady_clock::now();
     o->timer.collect();
 
     // ---- assemble (src/ORBextractor.cc:1267-1389): mono indices from the front, lapping-area ones from the back
@@ -388,6 +399,12 @@ int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, i
     o->stats.pyramid_pixels = 0;
     for (int l = 0; l < nl; ++l) o->stats.pyramid_pixels += (int64_t)o->lv[l].w * o->lv[l].h;
     o->stats.candidates = ncand; o->stats.keypoints = nkp; o->stats.kernel_launches = launches;
+    {
+        const auto tp4 = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<float, std::milli>(b - a).count(); };
+        o->stats.host_wait_candidates_ms = ms(tp0, tp1); o->stats.host_distribute_ms = ms(tp1, tp2);
+        o->stats.host_wait_describe_ms = ms(tp2, tp3); o->stats.host_assemble_ms = ms(tp3, tp4);
+    }
     return ret;
 }
 
@@ -406,6 +423,19 @@ int plvs_orb_pyramid_level(const plvs_orb* o, int frame, int level, int blurred,
     if (w) *w = g.w;
     if (h) *h = g.h;
     if (pitch) *pitch = g.pitch;
+    return PLVS_OK;
+}
+
+int plvs_orb_pyramid_view(const plvs_orb* o, int frame, int blurred, plvs_pyramid_view* out)
+{
+    if (!o || !out || frame < 0 || frame >= o->last_batch) { set_error("bad frame"); return PLVS_EINVAL; }
+    std::memset(out, 0, sizeof(*out));
+    out->nlevels = o->prm.nlevels;
+    for (int l = 0; l < o->prm.nlevels; ++l) {
+        const LevelGeom& g = o->lv[l];
+        out->data[l] = (blurred ? o->d_blur.p : o->d_pyr.p) + (size_t)frame * o->frame_stride + g.off;
+        out->w[l] = g.w; out->h[l] = g.h; out->pitch[l] = g.pitch;
+    }
     return PLVS_OK;
 }
 

@@ -140,3 +140,17 @@ class ORBmatcher:
                                                 m12.ctypes.data_as(C.c_void_p), C.byref(nm))
         _lib.check(rc, "plvs_match_triangulation")
         return nm.value, m12[:KF1.n]
+
+
+def ComputeStereoMatches(matcher, left, right, pyr_left, pyr_right, inv_scale, mb, mbf):
+    """Frame::ComputeStereoMatches (src/Frame.cc:1780): left/right are Frame views whose keys are mvKeys / mvKeysRight,
+    pyr_* the extractors' device pyramid views.  Returns (mvuRight, mvDepth, number of stereo points kept)."""
+    lib = _lib.load()
+    ur = np.full(max(left.n, 1), -1, np.float32); dp = np.full(max(left.n, 1), -1, np.float32)
+    vl, vr = left.view(), right.view()
+    inv = np.ascontiguousarray(inv_scale, np.float32)
+    nv = C.c_int()
+    rc = lib.plvs_stereo_match(matcher._h, C.byref(vl), C.byref(vr), C.byref(pyr_left), C.byref(pyr_right), inv.ctypes.data_as(C.c_void_p),
+                               C.c_float(mb), C.c_float(mbf), ur.ctypes.data_as(C.c_void_p), dp.ctypes.data_as(C.c_void_p), C.byref(nv))
+    _lib.check(rc, "plvs_stereo_match")
+    return ur[:left.n], dp[:left.n], nv.value

@@ -94,6 +94,11 @@ class ORBextractor:
                                                  s.ctypes.data_as(C.c_void_p), cap, C.byref(n)), "plvs_orb_candidates")
         return x[:n.value].copy(), y[:n.value].copy(), s[:n.value].copy()
 
+    def pyramid_view(self, frame=0, blurred=False):
+        v = _lib.PyramidView()
+        _lib.check(self._lib.plvs_orb_pyramid_view(self._h, frame, int(blurred), C.byref(v)), "plvs_orb_pyramid_view")
+        return v
+
     def device_result(self, frame=0):
         v = _lib.OrbDeviceView()
         _lib.check(self._lib.plvs_orb_device_result(self._h, frame, C.byref(v)), "plvs_orb_device_result")
@@ -102,4 +107,4 @@ class ORBextractor:
     def last_stats(self):
         s = _lib.OrbStats()
         _lib.check(self._lib.plvs_orb_last_stats(self._h, C.byref(s)), "plvs_orb_last_stats")
-        return dict(pyramid_pixels=s.pyramid_pixels, candidates=s.candidates, keypoints=s.keypoints, kernel_launches=s.kernel_launches)
+        return {f: getattr(s, f) for f, _ in s._fields_}

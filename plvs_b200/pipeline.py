@@ -182,6 +182,15 @@ class HotPath:
             self._map_batch(f0, nb, resident, out)
         return out
 
+    def match_rounds(self):
+        lib = self.ex._lib
+        out = []
+        r, k = C.c_int(), C.c_int()
+        for m in (self.m_track, self.m_map):
+            lib.plvs_match_last_stats(m._h, C.byref(r), C.byref(k))
+            out.append(r.value)
+        return out
+
     def launches_per_frame(self):
         """kernel launches of the last batch / frame, as counted by the library"""
         lib = self.ex._lib
