@@ -49,6 +49,7 @@ int plvs_set_profiling(int enable);
 #define PLVS_ORB_K_COMPACT 2
 #define PLVS_ORB_K_BLUR 3
 #define PLVS_ORB_K_DESCRIBE 4
+#define PLVS_ORB_K_DISTRIBUTE 5
 #define PLVS_MATCH_K_GRID 0
 #define PLVS_MATCH_K_CANDIDATES 1
 #define PLVS_MATCH_K_RESOLVE 2

@@ -217,119 +217,96 @@ __device__ __forceinline__ uint32_t cluster_cta_rank()
     return r;
 }
 
-// SMEM == true: every CTA keeps (a) a private copy of the claim table and (b) the candidate lists of the
-// queries its warps own in shared memory, so a round costs one coalesced L2 read of the table plus
-// shared-memory traffic; SMEM == false reads lists and claims from L2 (any size).
+// One thread per query: it walks its candidate list exactly like the reference's inner loop (running best / second
+// best with strict `<`), skipping candidates claimed by lower-numbered queries.  SMEM == true: the CTA caches the
+// lists of its queries (row stride cap|1: conflict-free column walks) and a private copy of the claim table in
+// shared memory, so a round is one coalesced L2 read of the table + shared-memory traffic; SMEM == false reads both
+// from L2 (any size).  Three claim tables rotate (read r, write r+1, clear r+2) and four change flags, so a round
+// needs a single cluster barrier.
 template <int MODE, bool SMEM>
 __global__ void __cluster_dims__(kResolveCtas, 1, 1) __launch_bounds__(1024)
 k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int cap, const void* __restrict__ queries, int nq,
           const plvs_keypoint* __restrict__ keys, int n, const uint8_t* __restrict__ claimed_in, float nn_ratio, int check_ori,
-          int* claim_a, int* claim_b, int* target /*nq*/, int* state /*[2] changed flags, zeroed by the host*/,
-          int32_t* assign /*n, device*/, int32_t* assign_out /*n, mapped host*/, int* result /*[0]=nmatches,[1]=rounds*/, int slots)
+          int* claims /*3*n*/, int* target /*nq*/, int* state /*[4] change flags, zeroed by the host*/,
+          int32_t* assign /*n, device*/, int32_t* assign_out /*n, mapped host*/, int* result /*[0]=nmatches,[1]=rounds*/, int per_cta)
 {
     extern __shared__ uint32_t s_dyn[];
     __shared__ int s_count, s_hist[HISTO], s_keep[HISTO];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x;
     const int crank = (int)cluster_cta_rank();
     const int gtid = crank * 1024 + tid, gthreads = kResolveCtas * 1024;
-    const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
     const int INF = 0x7fffffff;
-    const unsigned long long KINF = ~0ull;
-    // shared layout (SMEM): claims[n] | per-warp list lengths [32*slots] | per-warp lists [32*slots*cap]
-    int* s_claim = reinterpret_cast<int*>(s_dyn);
-    int* s_len = s_claim + (SMEM ? n : 0);
-    uint32_t* s_list = reinterpret_cast<uint32_t*>(s_len + (SMEM ? 32 * slots : 0));
-    for (int i = gtid; i < n; i += gthreads) { claim_a[i] = INF; claim_b[i] = INF; }
-    for (int i = gtid; i < nq; i += gthreads) target[i] = -1;
+    const int stride = cap | 1;
+    int* s_claim = reinterpret_cast<int*>(s_dyn);                               // n   (SMEM only)
+    uint32_t* s_list = s_dyn + (SMEM ? n : 0);                                  // per_cta * stride (SMEM only)
+    const int q0 = crank * per_cta;
+    const int q = q0 + tid;
+    const bool mine = tid < per_cta && q < nq;
+    for (int i = gtid; i < 3 * n; i += gthreads) claims[i] = INF;
+    int m = 0, my_target = -1;
+    uint32_t my_flags = 0;
+    if (mine) {
+        target[q] = -1;
+        m = min(cand_n[q], cap);
+        my_flags = MODE == 0 ? reinterpret_cast<const plvs_mp_query*>(queries)[q].flags : reinterpret_cast<const plvs_last_query*>(queries)[q].flags;
+    }
     if (SMEM) {
-        for (int sl = 0; sl < slots; ++sl) {
-            const int q = gwarp + sl * gwarps;
-            const int m = q < nq ? min(cand_n[q], cap) : 0;
-            if (lane == 0) s_len[wid * slots + sl] = m;
-            const uint32_t* c = cand + (size_t)q * cap;
-            uint32_t* d = s_list + (size_t)(wid * slots + sl) * cap;
-            for (int k = lane; k < m; k += 32) {
-                uint32_t e = c[k];
-                if (claimed_in && claimed_in[cand_idx(e)]) e = 0xffffffffu;      // pre-claimed keypoints never compete
-                d[k] = e;
+        const int rows = min(per_cta, max(nq - q0, 0));
+        for (int i = tid; i < rows * cap; i += 1024) {
+            const int j = i / cap, k = i - j * cap;
+            if (k < min(cand_n[q0 + j], cap)) {
+                uint32_t e = cand[(size_t)(q0 + j) * cap + k];
+                if (claimed_in && claimed_in[cand_idx(e)]) e = 0xffffffffu;     // pre-claimed keypoints never compete
+                s_list[j * stride + k] = e;
             }
         }
     }
     cluster_sync_all();
-    int* cur = claim_a; int* nxt = claim_b;
     int rounds = 0;
     for (;;) {
-        const int par = rounds & 1;
-        bool changed_here = false;
+        const int* cur = claims + (size_t)(rounds % 3) * n;
+        int* nxt = claims + (size_t)((rounds + 1) % 3) * n;
+        int* clr = claims + (size_t)((rounds + 2) % 3) * n;
         if (SMEM) {
             for (int i = tid; i < n; i += 1024) s_claim[i] = rounds ? __ldcg(&cur[i]) : INF;
             __syncthreads();
         }
-        for (int sl = 0; sl < slots; ++sl) {
-            const int q = gwarp + sl * gwarps;
-            if (q >= nq) break;
-            unsigned long long k1 = KINF, k2 = KINF;
-            if (SMEM) {
-                const uint32_t* c = s_list + (size_t)(wid * slots + sl) * cap;
-                const int m = s_len[wid * slots + sl];
-                for (int k = lane; k < m; k += 32) {
-                    const uint32_t e = c[k];
-                    if (e == 0xffffffffu || s_claim[cand_idx(e)] < q) continue;
-                    const unsigned long long key = ((unsigned long long)cand_dist(e) << 48) | ((unsigned long long)k << 32) | e;
-                    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+        bool changed_here = false;
+        if (mine) {
+            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+            for (int k = 0; k < m; ++k) {
+                uint32_t e; int idx;
+                if (SMEM) {
+                    e = s_list[tid * stride + k];
+                    if (e == 0xffffffffu) continue;
+                    idx = cand_idx(e);
+                    if (s_claim[idx] < q) continue;
+                } else {
+                    e = cand[(size_t)q * cap + k];
+                    idx = cand_idx(e);
+                    if ((claimed_in && claimed_in[idx]) || (rounds && __ldcg(&cur[idx]) < q)) continue;
                 }
-            } else {
-                const uint32_t* c = cand + (size_t)q * cap;
-                const int m = min(cand_n[q], cap);
-                for (int k = lane; k < m; k += 32) {
-                    const uint32_t e = c[k];
-                    const int idx = cand_idx(e);
-                    if ((claimed_in && claimed_in[idx]) || __ldcg(&cur[idx]) < q) continue;
-                    const unsigned long long key = ((unsigned long long)cand_dist(e) << 48) | ((unsigned long long)k << 32) | e;
-                    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
-                }
+                const int dist = cand_dist(e);
+                if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = cand_level(e); bestIdx = idx; }
+                else if (MODE == 0 && dist < bestDist2) { bestLevel2 = cand_level(e); bestDist2 = dist; }
             }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const unsigned long long o1 = shfl_xor_u64(k1, o), o2 = shfl_xor_u64(k2, o);
-                const unsigned long long lo = k1 < o1 ? k1 : o1, hi = k1 < o1 ? o1 : k1;
-                const unsigned long long s2 = k2 < o2 ? k2 : o2;
-                k1 = lo; k2 = hi < s2 ? hi : s2;
+            int t = -1;
+            if (bestDist <= TH_HIGH) {
+                if (MODE == 0) {
+                    if (!(bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) &&
+                        (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2)) t = bestIdx;
+                } else t = bestIdx;
             }
-            if (lane == 0) {
-                int t = -1;
-                if (k1 != KINF) {
-                    const uint32_t e1 = (uint32_t)k1;
-                    const int bestDist = cand_dist(e1);
-                    if (bestDist <= TH_HIGH) {
-                        if (MODE == 0) {
-                            const int bestLevel = cand_level(e1);
-                            const int bestDist2 = k2 != KINF ? cand_dist((uint32_t)k2) : 256;
-                            const int bestLevel2 = k2 != KINF ? cand_level((uint32_t)k2) : -1;
-                            if (!(bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) &&
-                                (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2)) t = cand_idx(e1);
-                        } else t = cand_idx(e1);
-                    }
-                }
-                if (t != target[q]) { target[q] = t; changed_here = true; }
-            }
+            if (t != my_target) { my_target = t; target[q] = t; changed_here = true; }
+            if (t >= 0 && (my_flags & PLVS_Q_OBS_POSITIVE)) atomicMin(&nxt[t], q);
         }
-        if (__syncthreads_or(changed_here ? 1 : 0) && tid == 0) atomicOr(&state[par], 1);
+        for (int i = gtid; i < n; i += gthreads) clr[i] = INF;
+        if (gtid == 0) state[(rounds + 2) & 3] = 0;
+        if (__syncthreads_or(changed_here ? 1 : 0) && tid == 0) atomicOr(&state[rounds & 3], 1);
         cluster_sync_all();
-        const int changed = __ldcg(&state[par]);
+        const int changed = __ldcg(&state[rounds & 3]);
         ++rounds;
         if (!changed) break;
-        if (gtid == 0) state[par ^ 1] = 0;
-        for (int i = gtid; i < n; i += gthreads) nxt[i] = INF;
-        cluster_sync_all();
-        for (int q = gtid; q < nq; q += gthreads) {
-            const int t = __ldcg(&target[q]);
-            const uint32_t flags = MODE == 0 ? reinterpret_cast<const plvs_mp_query*>(queries)[q].flags
-                                             : reinterpret_cast<const plvs_last_query*>(queries)[q].flags;
-            if (t >= 0 && (flags & PLVS_Q_OBS_POSITIVE)) atomicMin(&nxt[t], q);
-        }
-        cluster_sync_all();
-        int* tmp = cur; cur = nxt; nxt = tmp;
     }
     if (crank != 0) return;        // the wrap-up is one cheap pass: CTA 0 finishes alone (no cluster barrier after this point)
     // final holders: the last (highest) query that wrote each keypoint
@@ -728,7 +705,7 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         d_claimed = h->d_claimed.p;
     }
     if ((rc = h->d_cell_start.alloc(GRID_CELLS + 1)) || (rc = h->d_sorted.alloc(n)) || (rc = h->d_kp_cell.alloc(n)) ||
-        (rc = h->d_cand_n.alloc(nq)) || (rc = h->d_state.alloc(2)) || (rc = h->d_claim_a.alloc(n)) || (rc = h->d_claim_b.alloc(n)) || (rc = h->d_target.alloc(nq)) ||
+        (rc = h->d_cand_n.alloc(nq)) || (rc = h->d_state.alloc(4)) || (rc = h->d_claim_a.alloc((size_t)3 * n)) || (rc = h->d_target.alloc(nq)) ||
         (rc = h->d_assign.alloc(n)) || (rc = h->p_assign.alloc(n)) || (rc = h->p_result.alloc(4)) || (rc = h->p_cand_n.alloc(nq)))
         return rc;
     int launches = 0;
@@ -745,24 +722,22 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         ++launches;
         PLVS_CUDA(cudaMemcpyAsync(h->p_cand_n.h, h->d_cand_n.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
         h->timer.begin(PLVS_MATCH_K_RESOLVE, st);
-        PLVS_CUDA(cudaMemsetAsync(h->d_state.p, 0, 2 * sizeof(int), st));
+        PLVS_CUDA(cudaMemsetAsync(h->d_state.p, 0, 4 * sizeof(int), st));
         {
-            const int slots = div_up(nq, kResolveCtas * 32);
-            const size_t smem = ((size_t)n + (size_t)32 * slots + (size_t)32 * slots * h->cap) * sizeof(uint32_t);
-            if (smem <= 200 * 1024) {
+            const int per_cta = div_up(nq, kResolveCtas);
+            const size_t smem = ((size_t)n + (size_t)per_cta * (h->cap | 1)) * sizeof(uint32_t);
+            if (per_cta <= 1024 && smem <= 200 * 1024) {
                 static thread_local bool attr_set[2] = {false, false};
                 if (!attr_set[MODE]) {
                     PLVS_CUDA(cudaFuncSetAttribute(k_resolve<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     attr_set[MODE] = true;
                 }
                 k_resolve<MODE, true><<<kResolveCtas, 1024, smem, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
-                                                                        h->d_claim_a.p, h->d_claim_b.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d,
-                                                                        h->p_result.d, slots);
-            } else {
+                                                                        h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta);
+            } else if (per_cta <= 1024) {
                 k_resolve<MODE, false><<<kResolveCtas, 1024, 0, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
-                                                                      h->d_claim_a.p, h->d_claim_b.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d,
-                                                                      h->p_result.d, slots);
-            }
+                                                                      h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta);
+            } else { set_error("more than %d queries per search are not supported", kResolveCtas * 1024); return PLVS_EINVAL; }
         }
         h->timer.end(st);
         ++launches;

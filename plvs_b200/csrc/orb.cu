@@ -9,6 +9,7 @@
 #include <vector>
 #include "orb_distribute.hpp"
 #include "orb_kernels.cuh"
+#include "orb_distribute.cuh"
 
 using namespace plvs;
 using namespace plvs::orb;
@@ -41,7 +42,14 @@ struct plvs_orb {
     DevBuf<TileDesc> d_tiles;
     DevBuf<BilinearTap> d_taps;
     DevBuf<uint32_t> d_slots, d_cand, d_sel;
-    DevBuf<int> d_sel_off;
+    DevBuf<int> d_sel_off, d_sel_count, d_quota, d_dist_i32;
+    DevBuf<unsigned long long> d_dist_u64;
+    DevBuf<DNode> d_dist_nodes;
+    DevBuf<uint32_t> d_dist_stage;
+    DevBuf<DistLevel> d_dist_levels;
+    PinBuf<int> p_nkp, p_err;
+    bool host_distribute = false;
+    int dist_smem = 0;
     DevBuf<int> d_cell_count, d_cand_count;
     DevBuf<plvs_keypoint> d_kp;
     DevBuf<uint8_t> d_desc;
@@ -196,6 +204,46 @@ int setup_geometry(plvs_orb* o, int w, int h, int batch)
     if ((rc = o->p_sel.alloc((size_t)o->sel_cap * B))) return rc;
     if ((rc = o->d_sel.alloc((size_t)o->sel_cap * B))) return rc;
     if ((rc = o->d_sel_off.alloc((size_t)(nl + 1) * B))) return rc;
+    {
+        // scratch of the device distributor: per (frame, level) carved out of a few big allocations
+        size_t i32_per_frame = 0, u64_per_frame = 0, node_per_frame = 0, stage_per_frame = 0;
+        int max_quota = 0;
+        std::vector<int> ncap(nl);
+        for (int l = 0; l < nl; ++l) {
+            const size_t nmax = (size_t)o->lv[l].slot_count + 8;
+            ncap[l] = 16 * o->quota[l] + 256;
+            max_quota = std::max(max_quota, o->quota[l]);
+            i32_per_frame += 4 * nmax + 6 * (size_t)ncap[l];            // perm[2], node_of[2] | order[2], plist, nkids, nexp, flag
+            u64_per_frame += 2 * (nmax + 1) + 2 * (size_t)ncap[l];     // scan_a, scan_b | expand[2]
+            node_per_frame += ncap[l];
+            stage_per_frame += ncap[l];
+        }
+        if ((rc = o->d_dist_i32.alloc(i32_per_frame * B)) || (rc = o->d_dist_u64.alloc(u64_per_frame * B)) || (rc = o->d_dist_nodes.alloc(node_per_frame * B)) ||
+            (rc = o->d_dist_stage.alloc(stage_per_frame * B)) || (rc = o->d_dist_levels.alloc((size_t)nl * B)) || (rc = o->d_sel_count.alloc((size_t)nl * B)) ||
+            (rc = o->d_quota.alloc(nl)) || (rc = o->p_nkp.alloc(B)) || (rc = o->p_err.alloc(1))) return rc;
+        std::vector<DistLevel> tab((size_t)nl * B);
+        for (int b = 0; b < B; ++b) {
+            int* pi = o->d_dist_i32.p + (size_t)b * i32_per_frame;
+            unsigned long long* pu = o->d_dist_u64.p + (size_t)b * u64_per_frame;
+            DNode* pn = o->d_dist_nodes.p + (size_t)b * node_per_frame;
+            uint32_t* ps = o->d_dist_stage.p + (size_t)b * stage_per_frame;
+            for (int l = 0; l < nl; ++l) {
+                const size_t nmax = (size_t)o->lv[l].slot_count + 8;
+                DistLevel& d = tab[(size_t)b * nl + l];
+                d.perm[0] = pi; pi += nmax; d.perm[1] = pi; pi += nmax; d.node_of[0] = pi; pi += nmax; d.node_of[1] = pi; pi += nmax;
+                d.order[0] = pi; pi += ncap[l]; d.order[1] = pi; pi += ncap[l]; d.plist = pi; pi += ncap[l];
+                d.nkids = pi; pi += ncap[l]; d.nexp = pi; pi += ncap[l]; d.flag = pi; pi += ncap[l];
+                d.scan_a = pu; pu += nmax + 1; d.scan_b = pu; pu += nmax + 1; d.expand[0] = pu; pu += ncap[l]; d.expand[1] = pu; pu += ncap[l];
+                d.nodes = pn; pn += ncap[l]; d.stage = ps; ps += ncap[l];
+                d.ncap = ncap[l];
+            }
+        }
+        PLVS_CUDA(cudaMemcpyAsync(o->d_dist_levels.p, tab.data(), tab.size() * sizeof(DistLevel), cudaMemcpyHostToDevice, o->stream));
+        PLVS_CUDA(cudaMemcpyAsync(o->d_quota.p, o->quota, nl * sizeof(int), cudaMemcpyHostToDevice, o->stream));
+        PLVS_CUDA(cudaStreamSynchronize(o->stream));          // tab is a local
+        o->dist_smem = (max_quota + 8) * (int)sizeof(unsigned long long);
+        if (o->dist_smem > 48 * 1024) PLVS_CUDA(cudaFuncSetAttribute(k_distribute, cudaFuncAttributeMaxDynamicSharedMemorySize, o->dist_smem));
+    }
     if ((rc = o->p_sel_off.alloc((size_t)(nl + 1) * B))) return rc;
     if ((rc = o->p_kp.alloc((size_t)o->sel_cap * B))) return rc;
     if ((rc = o->p_desc.alloc((size_t)o->sel_cap * B * 32))) return rc;
@@ -226,6 +274,7 @@ int plvs_orb_create(const plvs_orb_params* p, int device, plvs_orb** out)
     plvs_orb* o = new plvs_orb();
     o->prm = *p; o->device = device;
     { const char* e = getenv("PLVS_ORB_DEBUG"); o->debug = e && e[0] == '1'; }
+    { const char* e = getenv("PLVS_ORB_HOST_DISTRIBUTE"); o->host_distribute = e && e[0] == '1'; }   // A/B aid: run DistributeOctTree on host threads
     build_tables(o);
     cudaError_t e1 = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking);
     cudaError_t e2 = e1 == cudaSuccess ? cudaEventCreateWithFlags(&o->ev, cudaEventDisableTiming) : e1;
@@ -300,6 +349,37 @@ int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, i
                                                 o->d_cand.p, o->p_cand.d, o->d_cand_count.p, o->p_cand_count.d);
     o->timer.end(st);
     launches += 2;
+    int64_t ncand = 0, nkp = 0;
+    o->n_kp.assign(batch, 0);
+    auto tp0 = std::chrono::steady_clock::now(), tp1 = tp0, tp2 = tp0;
+    if (!o->host_distribute) {
+        // ---- device path: distribute -> pack -> blur -> orient/describe, one synchronisation at the very end
+        DistArgs da{};
+        da.cand = o->d_cand.p; da.cand_count = o->d_cand_count.p; da.slots_per_frame = o->slots_per_frame; da.levels = o->d_lv.p; da.nlevels = nl;
+        da.quota = o->d_quota.p; da.scratch = o->d_dist_levels.p; da.sel = o->d_sel.p; da.sel_count = o->d_sel_count.p; da.sel_cap = o->sel_cap;
+        da.error = o->p_err.d;
+        o->p_err.h[0] = 0;
+        o->timer.begin(PLVS_ORB_K_DISTRIBUTE, st);
+        k_distribute<<<dim3(nl, batch), kDistThreads, o->dist_smem, st>>>(da);
+        k_pack_selected<<<batch, 256, 0, st>>>(da, o->d_sel_off.p, o->p_nkp.d);
+        o->timer.end(st);
+        o->timer.begin(PLVS_ORB_K_BLUR, st);
+        k_blur<<<dim3((unsigned)o->blur_tiles.size(), batch), 256, 0, st>>>(o->d_pyr.p, o->d_blur.p, o->frame_stride, o->d_lv.p, o->d_tiles.p);
+        o->timer.end(st);
+        o->timer.begin(PLVS_ORB_K_DESCRIBE, st);
+        k_orient_describe<<<dim3(div_up(o->sel_cap, 8), batch), 256, 0, st>>>(o->d_pyr.p, o->d_blur.p, o->frame_stride, o->d_lv.p, nl, o->d_sel.p, o->d_sel_off.p,
+                                                                              o->sel_cap, o->d_kp.p, o->d_desc.p, o->p_kp.d, o->p_desc.d);
+        o->timer.end(st);
+        launches += 4;
+        PLVS_CUDA(cudaGetLastError());
+        tp0 = tp1 = tp2 = std::chrono::steady_clock::now();
+        PLVS_CUDA(cudaStreamSynchronize(st));
+        if (o->p_err.h[0]) { set_error("keypoint distributor ran out of %s", o->p_err.h[0] == 1 ? "node pool" : "keypoint slots"); return PLVS_ENOMEM; }
+        for (int b = 0; b < batch; ++b) {
+            o->n_kp[b] = o->p_nkp.h[b]; nkp += o->n_kp[b];
+            for (int l = 0; l < nl; ++l) ncand += o->p_cand_count.h[b * nl + l];
+        }
+    } else {
     PLVS_CUDA(cudaEventRecord(o->ev, st));
     o->timer.begin(PLVS_ORB_K_BLUR, st);
     // the blur does not depend on the keypoints: it overlaps the host-side distribution
@@ -307,11 +387,11 @@ int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, i
     o->timer.end(st);
     ++launches;
     PLVS_CUDA(cudaGetLastError());
-    const auto tp0 = std::chrono::steady_clock::now();
+    tp0 = std::chrono::steady_clock::now();
     PLVS_CUDA(cudaEventSynchronize(o->ev));
-    const auto tp1 = std::chrono::steady_clock::now();
+    tp1 = std::chrono::steady_clock::now();
 
-    // ---- DistributeOctTree per (frame, level) on host threads
+    // ---- DistributeOctTree per (frame, level) on host threads (PLVS_ORB_HOST_DISTRIBUTE=1: A/B aid for the device kernel)
     const int ntask = batch * nl;
     std::vector<std::vector<int>> picked(ntask);
     {
@@ -336,10 +416,8 @@ int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, i
         if (nthreads == 1) work();
         else { for (int i = 0; i < nthreads; ++i) pool.emplace_back(work); for (auto& th : pool) th.join(); }
     }
-    const auto tp2 = std::chrono::steady_clock::now();
-    int64_t ncand = 0, nkp = 0;
+    tp2 = std::chrono::steady_clock::now();
     int max_k = 0;
-    o->n_kp.assign(batch, 0);
     for (int b = 0; b < batch; ++b) {
         int* loff = o->p_sel_off.h + (size_t)b * (nl + 1);
         uint32_t* sel = o->p_sel.h + (size_t)b * o->sel_cap;
@@ -368,6 +446,7 @@ int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, i
     }
     PLVS_CUDA(cudaGetLastError());
     PLVS_CUDA(cudaStreamSynchronize(st));
+    }
     const auto tp3 = std::chrono::steady_clock::now();
     o->timer.collect();
 

@@ -6,6 +6,9 @@
 #include <vector>
 #include "../../plvs_b200/csrc/orb_distribute.hpp"
 #include "../../plvs_b200/csrc/libm_sincosf.cuh"
+#include "../../plvs_b200/csrc/stdsort_emul.cuh"
+#include <algorithm>
+#include <utility>
 
 extern "C" {
 
@@ -16,6 +19,19 @@ int chk_distribute(int n, const int* xs, const int* ys, const int* resp, int min
     d.run(n, xs, ys, resp, minX, maxX, minY, maxY, N, out);
     for (size_t i = 0; i < out.size(); ++i) sel[i] = out[i];
     return (int)out.size();
+}
+
+// std::sort emulation vs the real std::sort with a key-only (non-total) comparator; returns #position mismatches
+int chk_stdsort(int n, const uint32_t* keys, int* order_out)
+{
+    std::vector<std::pair<uint32_t, int>> ref(n);
+    std::vector<plvs::stdsort::elem_t> em(n);
+    for (int i = 0; i < n; ++i) { ref[i] = std::make_pair(keys[i], i); em[i] = ((plvs::stdsort::elem_t)keys[i] << 32) | (uint32_t)i; }
+    std::sort(ref.begin(), ref.end(), [](const std::pair<uint32_t, int>& a, const std::pair<uint32_t, int>& b) { return a.first < b.first; });
+    plvs::stdsort::sort(em.data(), n);
+    int bad = 0;
+    for (int i = 0; i < n; ++i) { if ((int)(uint32_t)em[i] != ref[i].second) ++bad; if (order_out) order_out[i] = (int)(uint32_t)em[i]; }
+    return bad;
 }
 
 // sweep floats in [lo_bits, hi_bits] with the given stride; returns the number of (cos,sin) mismatches vs libm

@@ -106,3 +106,18 @@ def test_orb_1080p(gpu):
     for f in FIELDS:
         assert np.array_equal(kp[f], okp[f]), f
     assert np.array_equal(desc, odesc)
+
+
+@pytest.mark.parametrize("nfeat", [300, 1000, 2000, 5000])
+def test_device_distributor_equals_host_distributor(gpu, monkeypatch, nfeat):
+    """DistributeOctTree on the device (default) vs the host implementation (PLVS_ORB_HOST_DISTRIBUTE=1): same keypoints, same order"""
+    imgs = [synth.gray_frame(5), (synth.gray_frame(6).astype(np.float32) * 0.2 + 80).astype(np.uint8), synth.gray_frame(0, 333, 257)]
+    dev = ORBextractor(nfeat, 1.2, 8, 20, 7)
+    monkeypatch.setenv("PLVS_ORB_HOST_DISTRIBUTE", "1")
+    host = ORBextractor(nfeat, 1.2, 8, 20, 7)
+    monkeypatch.delenv("PLVS_ORB_HOST_DISTRIBUTE")
+    for img in imgs:
+        m1, k1, d1 = dev(img)
+        m2, k2, d2 = host(img)
+        assert m1 == m2 and len(k1) == len(k2)
+        assert np.array_equal(k1, k2) and np.array_equal(d1, d2)

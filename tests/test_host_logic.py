@@ -56,6 +56,28 @@ def test_distributor_tall_image_has_no_root(host):
     assert len(O.distribute_octree([1, 2], [1, 2], [9, 9], 16, 44, 16, 184, 10)) == 0
 
 
+def test_stdsort_emulation_matches_libstdcxx_on_ties(host):
+    """the distributor's tie order is whatever std::sort does with a key-only comparator: the emulation must permute alike"""
+    rng = np.random.default_rng(7)
+    for trial in range(400):
+        n = int(rng.integers(0, 3000)) if trial % 5 else int(rng.integers(0, 40))
+        kind = trial % 4
+        if kind == 0:
+            keys = rng.integers(0, 4, n)                       # almost everything ties
+        elif kind == 1:
+            keys = rng.integers(0, 1 << 20, n)
+        elif kind == 2:
+            keys = np.sort(rng.integers(0, 50, n))[::-1].copy()   # descending runs
+        else:
+            keys = (rng.integers(2, 30, n) << 16) | rng.integers(0, 600, n)   # (size, UL.x) like the real use
+        keys = np.ascontiguousarray(keys, np.uint32)
+        assert host.chk_stdsort(n, keys.ctypes.data_as(C.c_void_p), None) == 0, (trial, n)
+    # adversarial for median-of-3 quicksort: organ-pipe and many-duplicates inputs big enough to hit the heapsort fallback
+    for n in (5000, 20000):
+        pipe = np.concatenate([np.arange(n // 2), np.arange(n // 2)[::-1]]).astype(np.uint32)
+        assert host.chk_stdsort(len(pipe), pipe.ctypes.data_as(C.c_void_p), None) == 0
+
+
 def test_sincosf_port_equals_libm_exhaustively(host):
     """every float in [0, 6.4] (the steering angle range is [0, 2*pi]): 1.09e9 values, ~10 s"""
     first = C.c_float()
