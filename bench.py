@@ -194,12 +194,12 @@ def run_b200_arm(a):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def run(resident, timed_profile=False):
+    def run(resident, timed_profile=0):
         hp.tsdf.Reset()
         hp.tsdf.integrate(data.depth[0], data.poses[0], data.bgr[0])           # seed (untimed)
         for s in range(W):
             hp.step(1 + s * B, B, resident)
-        lib.plvs_set_profiling(1 if timed_profile else 0)
+        lib.plvs_set_profiling(timed_profile)
         lib.plvs_tsdf_kernel_times(hp.tsdf._h, None, None, 1)
         lib.plvs_orb_kernel_times(hp.ex._h, None, None, 1)
         for m in (hp.m_track, hp.m_map, hp.m_tri):
@@ -228,14 +228,20 @@ def run_b200_arm(a):
     import ctypes as C
     # ---- value arm: inputs resident in HBM ----------------------------------------------------------------
     hp.upload_inputs()
-    t_ms, wall, clocks, agg = run(resident=True, timed_profile=True)
+    # timed run: only the roofline kernel (k_integrate) carries events (2 per frame); the per-kernel table comes from a
+    # second, untimed pass with all events on
+    t_ms, wall, clocks, agg = run(resident=True, timed_profile=4 | 8)
+    ms = np.zeros(12, np.float32); cnt = np.zeros(12, np.int32)
+    lib.plvs_tsdf_kernel_times(hp.tsdf._h, ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 0)
+    integ_live = (float(ms[2]), int(cnt[2]))
+    run(resident=True, timed_profile=7)
     ktimes = {}
     ms = np.zeros(12, np.float32); cnt = np.zeros(12, np.int32)
     lib.plvs_tsdf_kernel_times(hp.tsdf._h, ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 0)
     for i, nme in enumerate(("tsdf.depth_tiles", "tsdf.classify", "tsdf.integrate", "tsdf.commit")):
         ktimes[nme] = (float(ms[i]), int(cnt[i]))
     lib.plvs_orb_kernel_times(hp.ex._h, ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 0)
-    for i, nme in enumerate(("orb.pyramid", "orb.fast_cells", "orb.compact", "orb.blur", "orb.orient_describe")):
+    for i, nme in enumerate(("orb.pyramid", "orb.fast_cells", "orb.compact", "orb.blur", "orb.orient_describe", "orb.distribute")):
         ktimes[nme] = (float(ms[i]), int(cnt[i]))
     mm = np.zeros(12, np.float32); mc = np.zeros(12, np.int32)
     for m in (hp.m_track, hp.m_map, hp.m_tri):
@@ -249,8 +255,10 @@ def run_b200_arm(a):
 
     # roofline of the dominant kernel: TSDF voxel update.  Algorithmic bytes per launch:
     # depth 4*W*H + colour 3*W*H + n_updated_blocks * 4096 voxels * 12 B (sdf f32 + weight f32 + rgba) * 2 (read+write)
-    integ_ms, integ_n = ktimes["tsdf.integrate"]
-    upd_per_launch = agg.get("tsdf_updated", 0) / max(frames, 1)
+    integ_ms, integ_n = integ_live
+    tst = hp.tsdf.stats()          # running totals since the Reset at the start of the last pass (seed + warm-up + timed scans)
+    upd_per_launch = tst["total_updated"] / max(tst["total_integrations"], 1)
+    vis_per_launch = tst["total_candidates"] / max(tst["total_integrations"], 1)
     alg_bytes = a.width * a.height * (4 + 3) + upd_per_launch * 4096 * 12 * 2
     peak, peak_src = peaks()
     roof = None
@@ -283,7 +291,7 @@ def run_b200_arm(a):
             "gpu_launches": int(round(launches_per_step * K)), "clocks": clocks,
             "kernel_ms_per_step": {k: round(v[0] / K, 4) for k, v in ktimes.items()}, "gpu_busy_frac": gpu_time_ms / t_ms,
             "per_step": {"keypoints": agg.get("keypoints", 0) / K, "matches": agg.get("matches", 0) / K,
-                         "tsdf_blocks_visited": agg.get("tsdf_candidates", 0) / K, "tsdf_blocks_updated": agg.get("tsdf_updated", 0) / K,
+                         "tsdf_blocks_visited_per_scan": vis_per_launch, "tsdf_blocks_updated_per_scan": upd_per_launch,
                          "match_rounds_last_call": hp.match_rounds()}, "wall_s": [wall, wall2]}
     if not a.no_cpu_baseline:
         fps, stages = cpu_reference_run(a, a.cpu_frames, 1, False)

@@ -43,7 +43,8 @@ const char* plvs_last_error(void);          /* thread-local description of the l
 int plvs_device_count(void);
 /* Per-kernel CUDA-event timing on each handle's stream (off by default; used by bench.py for the roofline
  * figures).  plvs_*_kernel_times() return accumulated milliseconds and launch counts since the last reset. */
-int plvs_set_profiling(int enable);
+/* mask: 1 = ORB kernels, 2 = matcher kernels, 4 = TSDF kernels, 8 = restrict to the roofline kernel (k_integrate); 0 = off */
+int plvs_set_profiling(int mask);
 #define PLVS_ORB_K_RESIZE 0
 #define PLVS_ORB_K_FAST 1
 #define PLVS_ORB_K_COMPACT 2
@@ -118,6 +119,7 @@ typedef struct {
     int32_t n;
     const plvs_keypoint* keys;   /* device */
     const uint8_t* desc;         /* device, n x 32 */
+    uint64_t cache_key;          /* unique per (handle, extract call, frame): pass it on in plvs_frame_view.cache_key */
 } plvs_orb_device_view;
 int plvs_orb_device_result(const plvs_orb* h, int frame, plvs_orb_device_view* out);
 
@@ -163,6 +165,9 @@ typedef struct {
     int32_t nlevels;
     float bf;                             /* Frame::mbf */
     int32_t on_device;
+    uint64_t cache_key;                   /* 0 = none.  Same non-zero key on consecutive searches of one handle = same keypoints:
+                                             the feature grid built for the previous search is reused (the reference builds it once
+                                             per Frame, src/Frame.cc:598) */
 } plvs_frame_view;
 
 #define PLVS_Q_OBS_POSITIVE 1u   /* MapPoint::Observations() > 0 */
@@ -276,6 +281,9 @@ int plvs_tsdf_set_camera(plvs_tsdf* h, double fx, double fy, double cx, double c
 #define PLVS_TSDF_SCAN_COLOR 1   /* IntegrateDepthScanColorWithOneCameraModelBGR (Chisel.h:198) */
 
 /* SetDepthPose + SetDepthImage[MemorySharing] (+SetColorImage) + IntegrateLastDepthImage(false).
+ * With host buffers the call returns as soon as the (borrowed) buffers have been read -- the copy of scan k+1 overlaps
+ * the kernels of scan k; statistics, read-outs and a pool-exhaustion error are delivered by the next call that needs the
+ * finished map (plvs_tsdf_last_stats / download_blocks / export / reset).  Device-resident inputs are finished before return.
  * depth: float32 metres, w*h, row stride = w elements (DepthImage.h:54-74).  bgr: w*h*nch bytes
  * with `bgr_step` bytes per row (NULL unless mode==PLVS_TSDF_SCAN_COLOR).  Twc: 3x4 row-major
  * (rotation | translation), camera-to-world (src/PointCloudMapChisel.cc:147-154). */
@@ -292,6 +300,9 @@ typedef struct {
     int32_t n_collected;         /* chunks created then garbage-collected */
     int32_t kernel_launches;
     int32_t pool_exhausted;      /* !=0 if max_blocks was hit (results incomplete) */
+    int64_t total_updated;       /* since create/reset: sum of n_updated over all scans */
+    int64_t total_candidates;    /* ... of chunks visited */
+    int64_t total_integrations;  /* ... number of scans */
 } plvs_tsdf_stats;
 int plvs_tsdf_last_stats(const plvs_tsdf* h, plvs_tsdf_stats* out);
 int plvs_tsdf_kernel_times(plvs_tsdf* h, float* ms, int32_t* launches, int reset);

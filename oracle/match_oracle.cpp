@@ -36,6 +36,7 @@ struct FrameView {
     int32_t nlevels;
     float bf;
     int32_t on_device;
+    uint64_t cache_key;
 };
 
 struct MpQuery { float proj_x, proj_y, proj_xr, track_depth, view_cos; int32_t level; uint32_t flags; uint8_t desc[32]; };

@@ -32,7 +32,7 @@ class OrbStats(C.Structure):
 
 
 class OrbDeviceView(C.Structure):
-    _fields_ = [("n", C.c_int32), ("keys", C.c_void_p), ("desc", C.c_void_p)]
+    _fields_ = [("n", C.c_int32), ("keys", C.c_void_p), ("desc", C.c_void_p), ("cache_key", C.c_uint64)]
 
 
 MAX_LEVELS = 16
@@ -43,7 +43,7 @@ class FrameView(C.Structure):
                 ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
                 ("grid_inv_w", C.c_float), ("grid_inv_h", C.c_float),
                 ("scale_factors", C.c_float * MAX_LEVELS), ("level_sigma2", C.c_float * MAX_LEVELS),
-                ("nlevels", C.c_int32), ("bf", C.c_float), ("on_device", C.c_int32)]
+                ("nlevels", C.c_int32), ("bf", C.c_float), ("on_device", C.c_int32), ("cache_key", C.c_uint64)]
 
 
 class PyramidView(C.Structure):
@@ -64,7 +64,8 @@ class TsdfParams(C.Structure):
 
 class TsdfStats(C.Structure):
     _fields_ = [("n_blocks", C.c_int32), ("n_range", C.c_int32), ("n_candidates", C.c_int32), ("n_updated", C.c_int32),
-                ("n_new", C.c_int32), ("n_collected", C.c_int32), ("kernel_launches", C.c_int32), ("pool_exhausted", C.c_int32)]
+                ("n_new", C.c_int32), ("n_collected", C.c_int32), ("kernel_launches", C.c_int32), ("pool_exhausted", C.c_int32),
+                ("total_updated", C.c_int64), ("total_candidates", C.c_int64), ("total_integrations", C.c_int64)]
 
 
 _lib = None

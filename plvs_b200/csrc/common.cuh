@@ -76,14 +76,19 @@ struct KernelTimer {
     std::vector<int> pending;      // slot of pair i (events 2i, 2i+1)
     float ms[kSlots] = {0};
     int count[kSlots] = {0};
+    int component = 0;             // bit of g_profiling that enables this timer (1 orb, 2 match, 4 tsdf)
+    int only_slot = -1;            // g_profiling bit 8 set => only this slot is timed (the roofline kernel)
+    bool on(int slot) const { return (g_profiling & component) && (!(g_profiling & 8) || slot == only_slot); }
     void begin(int slot, cudaStream_t st) {
-        if (!g_profiling) return;
+        armed = on(slot);
+        if (!armed) return;
         const size_t i = pending.size();
         while (pool.size() < 2 * (i + 1)) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
         pending.push_back(slot);
         cudaEventRecord(pool[2 * i], st);
     }
-    void end(cudaStream_t st) { if (!g_profiling || pending.empty()) return; cudaEventRecord(pool[2 * (pending.size() - 1) + 1], st); }
+    bool armed = false;
+    void end(cudaStream_t st) { if (!armed || pending.empty()) return; cudaEventRecord(pool[2 * (pending.size() - 1) + 1], st); armed = false; }
     void collect() {           // call after the stream has been synchronised
         for (size_t i = 0; i < pending.size(); ++i) {
             float t = 0.f;

@@ -19,7 +19,7 @@ extern "C" {
 const char* plvs_version(void) { return "plvs_b200 0.1 (sm_100a)"; }
 const char* plvs_last_error(void) { return plvs::g_err; }
 
-int plvs_set_profiling(int enable) { plvs::g_profiling = enable ? 1 : 0; return PLVS_OK; }
+int plvs_set_profiling(int mask) { plvs::g_profiling = mask; return PLVS_OK; }
 
 int plvs_device_count(void)
 {

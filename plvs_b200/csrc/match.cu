@@ -199,12 +199,6 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
 // ---------------------------------------------------------------------------------------------
 constexpr int kResolveCtas = 8;
 
-__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o)
-{
-    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, o), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), o);
-    return ((unsigned long long)hi << 32) | lo;
-}
-
 __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n" "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
@@ -364,28 +358,32 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// SearchForTriangulation (src/ORBmatcher.cc:1059-1208): one CTA per shared vocabulary node, one
-// warp per unmatched feature of KF1 in it; lanes sweep the node's KF2 features.  Winner = smallest
+// SearchForTriangulation (src/ORBmatcher.cc:1059-1208): one warp per feature of KF1 (entries of its feature
+// vector, flattened); lanes sweep the KF2 features of the same vocabulary node.  Winner = smallest
 // distance <= TH_LOW among the gated candidates, LAST one on ties (the `dist>bestDist` skip).
 // ---------------------------------------------------------------------------------------------
 struct FvDev { int n_nodes; const uint32_t* ids; const int* off; const int* feat; };
 
 __global__ void __launch_bounds__(256)
 k_triangulate(ViewDev K1, ViewDev K2, FvDev f1, FvDev f2, const uint8_t* __restrict__ has1, const uint8_t* __restrict__ has2,
-              const float* __restrict__ F12, float epx, float epy, int only_stereo, int coarse, int32_t* __restrict__ match12)
+              const float* __restrict__ F12, float epx, float epy, int only_stereo, int coarse, int total1, int32_t* __restrict__ match12)
 {
-    const int a = blockIdx.x;
-    const uint32_t id = f1.ids[a];
-    int lo = 0, hi = f2.n_nodes - 1, b = -1;
+    // one warp per entry of KF1's feature vector (flattened); its vocabulary node comes from two binary searches
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (e >= total1 || e >= f1.off[f1.n_nodes]) return;
+    int lo = 0, hi = f1.n_nodes;                        // last node with off[a] <= e
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (f1.off[mid] <= e) lo = mid; else hi = mid; }
+    const uint32_t id = f1.ids[lo];
+    int b = -1;
+    lo = 0; hi = f2.n_nodes - 1;
     while (lo <= hi) { const int mid = (lo + hi) >> 1; const uint32_t v = f2.ids[mid]; if (v == id) { b = mid; break; } if (v < id) lo = mid + 1; else hi = mid - 1; }
     if (b < 0) return;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int b0 = f2.off[b], b1 = f2.off[b + 1];
-    for (int e = f1.off[a] + wid; e < f1.off[a + 1]; e += 8) {
+    {
         const int idx1 = f1.feat[e];
-        if (has1[idx1]) continue;
+        if (has1[idx1]) return;
         const bool stereo1 = K1.uright && K1.uright[idx1] >= 0;
-        if (only_stereo && !stereo1) continue;
+        if (only_stereo && !stereo1) return;
         const plvs_keypoint kp1 = K1.keys[idx1];
         const uint8_t* d1 = K1.desc + (size_t)idx1 * 32;
         const uint4 a0 = *reinterpret_cast<const uint4*>(d1), a1 = *reinterpret_cast<const uint4*>(d1 + 16);
@@ -647,6 +645,7 @@ struct plvs_match {
     PinBuf<int> p_result, p_cand_n;
     int cap = 128;
     int last_rounds = 0, last_launches = 0;
+    uint64_t grid_key = 0; int grid_n = -1;
     KernelTimer timer;
     std::mutex mu;
 };
@@ -709,10 +708,13 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         (rc = h->d_assign.alloc(n)) || (rc = h->p_assign.alloc(n)) || (rc = h->p_result.alloc(4)) || (rc = h->p_cand_n.alloc(nq)))
         return rc;
     int launches = 0;
-    h->timer.begin(PLVS_MATCH_K_GRID, st);
-    k_build_grid<<<1, 1024, 0, st>>>(V.keys, n, V.gp, h->d_cell_start.p, h->d_sorted.p, h->d_kp_cell.p);
-    h->timer.end(st);
-    ++launches;
+    if (!(F->cache_key != 0 && F->cache_key == h->grid_key && n == h->grid_n)) {
+        h->timer.begin(PLVS_MATCH_K_GRID, st);
+        k_build_grid<<<1, 1024, 0, st>>>(V.keys, n, V.gp, h->d_cell_start.p, h->d_sorted.p, h->d_kp_cell.p);
+        h->timer.end(st);
+        ++launches;
+        h->grid_key = F->cache_key; h->grid_n = n;
+    }
     for (;;) {
         if ((rc = h->d_cand.alloc((size_t)nq * h->cap))) return rc;
         h->timer.begin(PLVS_MATCH_K_CANDIDATES, st);
@@ -795,7 +797,7 @@ int plvs_match_create(int device, plvs_match** out)
     if (device < 0 || device >= ndev) { set_error("device %d out of range", device); return PLVS_EINVAL; }
     PLVS_CUDA(cudaSetDevice(device));
     plvs_match* h = new plvs_match();
-    h->device = device;
+    h->device = device; h->timer.component = 2;
     { cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
       if (e != cudaSuccess) { delete h; set_error("stream creation failed: %s", cudaGetErrorString(e)); return PLVS_ENODEV; } }
     *out = h;
@@ -869,7 +871,9 @@ int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const pl
     PLVS_CUDA(cudaMemcpyAsync(h->d_f12.p, F12, 9 * sizeof(float), cudaMemcpyHostToDevice, st));
     h->timer.begin(PLVS_MATCH_K_TRIANGULATE, st);
     k_fill_i32<<<div_up(n1, 256), 256, 0, st>>>(h->d_assign.p, n1, -1);
-    k_triangulate<<<D1.n_nodes, 256, 0, st>>>(V1, V2, D1, D2, dh1, dh2, h->d_f12.p, ep[0], ep[1], only_stereo, coarse, h->d_assign.p);
+    const int total1 = n1;         // every feature sits in at most one vocabulary node
+    if (total1 > 0)
+        k_triangulate<<<div_up(total1, 8), 256, 0, st>>>(V1, V2, D1, D2, dh1, dh2, h->d_f12.p, ep[0], ep[1], only_stereo, coarse, total1, h->d_assign.p);
     k_tri_finish<<<1, 1024, 0, st>>>(V1.keys, V2.keys, n1, check_orientation, h->d_assign.p, h->p_assign.d, h->p_result.d);
     h->timer.end(st);
     PLVS_CUDA(cudaGetLastError());

@@ -62,6 +62,7 @@ struct plvs_orb {
     std::vector<int> n_kp;           // per frame of the last batch
     std::vector<char> lapped;
     int last_batch = 0;
+    uint64_t serial = 0, epoch = 0;
     plvs_orb_stats stats{};
     KernelTimer timer;
     std::mutex mu;
@@ -272,7 +273,8 @@ int plvs_orb_create(const plvs_orb_params* p, int device, plvs_orb** out)
     if (device < 0 || device >= ndev) { set_error("device %d out of range", device); return PLVS_EINVAL; }
     PLVS_CUDA(cudaSetDevice(device));
     plvs_orb* o = new plvs_orb();
-    o->prm = *p; o->device = device;
+    o->prm = *p; o->device = device; o->timer.component = 1;
+    { static std::atomic<uint64_t> counter{1}; o->serial = counter.fetch_add(1); }
     { const char* e = getenv("PLVS_ORB_DEBUG"); o->debug = e && e[0] == '1'; }
     { const char* e = getenv("PLVS_ORB_HOST_DISTRIBUTE"); o->host_distribute = e && e[0] == '1'; }   // A/B aid: run DistributeOctTree on host threads
     build_tables(o);
@@ -475,6 +477,7 @@ int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, i
     }
     if (ret == PLVS_ECAP) set_error("keypoint capacity too small");
     o->last_batch = batch;
+    ++o->epoch;
     o->stats.pyramid_pixels = 0;
     for (int l = 0; l < nl; ++l) o->stats.pyramid_pixels += (int64_t)o->lv[l].w * o->lv[l].h;
     o->stats.candidates = ncand; o->stats.keypoints = nkp; o->stats.kernel_launches = launches;
@@ -538,6 +541,7 @@ int plvs_orb_device_result(const plvs_orb* o, int frame, plvs_orb_device_view* o
     out->n = o->n_kp[frame];
     out->keys = o->d_kp.p + (size_t)frame * o->sel_cap;
     out->desc = o->d_desc.p + (size_t)frame * o->sel_cap * 32;
+    out->cache_key = (o->serial << 44) | ((o->epoch & 0xfffffffffull) << 8) | (uint64_t)(frame & 0xff);
     return PLVS_OK;
 }
 

@@ -26,7 +26,7 @@ class Frame:
         self.desc = np.ascontiguousarray(desc, np.uint8) if desc is not None else None
         self.uright = None if uright is None else np.ascontiguousarray(uright, np.float32)
         self.n = len(self.keys) if device_ptrs is None else device_ptrs[0]
-        self.device_ptrs = device_ptrs          # (n, keys_ptr, desc_ptr, uright_ptr|0)
+        self.device_ptrs = device_ptrs          # (n, keys_ptr, desc_ptr, uright_ptr|0[, cache_key])
         self.scale_factors = np.asarray(scale_factors, np.float32)
         self.level_sigma2 = np.asarray(level_sigma2 if level_sigma2 is not None else self.scale_factors ** 2, np.float32)
         # Frame::ComputeImageBounds without distortion (src/Frame.cc:1770-1776)
@@ -41,6 +41,7 @@ class Frame:
         if self.device_ptrs is not None:
             v.keys, v.desc, v.uright = self.device_ptrs[1], self.device_ptrs[2], self.device_ptrs[3] or None
             v.on_device = 1
+            v.cache_key = self.device_ptrs[4] if len(self.device_ptrs) > 4 else 0
         else:
             v.keys = self.keys.ctypes.data
             v.desc = self.desc.ctypes.data
@@ -97,7 +98,7 @@ class ORBmatcher:
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
         return _lib.load().plvs_hamming256(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
 
-    def SearchByProjectionMap(self, F, queries, th=3.0, bFarPoints=False, thFarPoints=50.0, claimed=None):
+    def SearchByProjectionMap(self, F, queries, th=3.0, bFarPoints=False, thFarPoints=50.0, claimed=None, nnratio=None):
         """SearchByProjection(Frame&, vector<MapPointPtr>&, th, bFarPoints, thFarPoints) -> (nmatches, assign[N])."""
         q = np.ascontiguousarray(queries, MP_QUERY)
         assign = np.full(max(F.n, 1), -1, np.int32)
@@ -105,7 +106,7 @@ class ORBmatcher:
         v = F.view()
         cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
         rc = self._lib.plvs_match_projection_map(self._h, C.byref(v), q.ctypes.data_as(C.c_void_p), len(q), C.c_float(th),
-                                                 C.c_float(self.mfNNratio), int(bFarPoints), C.c_float(thFarPoints),
+                                                 C.c_float(self.mfNNratio if nnratio is None else nnratio), int(bFarPoints), C.c_float(thFarPoints),
                                                  cl.ctypes.data_as(C.c_void_p) if cl is not None else None,
                                                  assign.ctypes.data_as(C.c_void_p), C.byref(nm))
         _lib.check(rc, "plvs_match_projection_map")

@@ -127,10 +127,11 @@ class HotPath:
             # descriptors/keypoints of the current frame stay on the device for the searches
             dv = self.ex.device_result(b)
             cur_ref = self.frames[f]
-            cur = Frame(None, None, d.w, d.h, sf, s2, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0))
+            cur = Frame(None, None, d.w, d.h, sf, s2, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key))
             n1, a1 = self.m_track.SearchByProjectionLast(cur, p["ql"], 15.0)
             claimed = (a1 >= 0).astype(np.uint8)
-            n2, a2 = self.m_map.SearchByProjectionMap(cur, p["qm"], 3.0, claimed=claimed)
+            # same tracking-thread workspace => the feature grid of the frame is built once for both searches
+            n2, a2 = self.m_track.SearchByProjectionMap(cur, p["qm"], 3.0, claimed=claimed, nnratio=0.8)
             last = self.frames[f - 1]
             n3, m12 = self.m_tri.SearchForTriangulation(Frame(kps[b], descs[b], d.w, d.h, sf, s2, uright=cur_ref.uright, bf=d.K["bf"]), last,
                                                         p["fv1"], p["fv2"], p["has1"], p["has2"], p["F12"], p["ep"], False, False)
@@ -146,9 +147,7 @@ class HotPath:
                 self._integrate_device(f)
             else:
                 self.tsdf.integrate(d.depth[f], d.poses[f], d.bgr[f] if self.use_color else None)
-            st = self.tsdf.stats()
-            out["tsdf_updated"] = out.get("tsdf_updated", 0) + st["n_updated"]
-            out["tsdf_candidates"] = out.get("tsdf_candidates", 0) + st["n_candidates"]
+        # no per-frame statistics here: asking for them would wait for the scan (the library keeps running totals on the device)
 
     def _integrate_device(self, f):
         d = self.d
@@ -186,9 +185,8 @@ class HotPath:
         lib = self.ex._lib
         out = []
         r, k = C.c_int(), C.c_int()
-        for m in (self.m_track, self.m_map):
-            lib.plvs_match_last_stats(m._h, C.byref(r), C.byref(k))
-            out.append(r.value)
+        lib.plvs_match_last_stats(self.m_track._h, C.byref(r), C.byref(k))
+        out.append(r.value)
         return out
 
     def launches_per_frame(self):
@@ -196,8 +194,8 @@ class HotPath:
         lib = self.ex._lib
         n = self.ex.last_stats()["kernel_launches"] / max(self.batch, 1)
         r, k = C.c_int(), C.c_int()
-        for m in (self.m_track, self.m_map, self.m_tri):
+        for m in (self.m_track, self.m_tri):
             lib.plvs_match_last_stats(m._h, C.byref(r), C.byref(k))
-            n += k.value
+            n += k.value * (2 if m is self.m_track else 1)
         n += self.tsdf.stats()["kernel_launches"]
         return n

@@ -156,3 +156,27 @@ def test_compute_stereo_matches(gpu):
         zt = z[kl["y"][ok].astype(int), kl["x"][ok].astype(int)]
         good = zt > 0
         assert np.median(np.abs(dp[ok][good] - zt[good]) / zt[good]) < 0.03
+
+
+def test_grid_cache_key_reuses_grid_and_stays_exact(frames):
+    """two searches on the same device-resident frame through one handle: the second reuses the cached feature grid"""
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    ex = ORBextractor(2000, 1.2, 8, 20, 7)
+    mono, kp, desc = ex(synth.gray_frame(11))
+    dv = ex.device_result(0)
+    assert dv.cache_key != 0
+    dcur = Frame(None, None, K["w"], K["h"], ex.GetScaleFactors(), bf=K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key))
+    hcur = Frame(cur.keys, cur.desc, K["w"], K["h"], ex.GetScaleFactors(), bf=K["bf"])
+    ql, _ = scenario.last_queries(last, cur, K, Tl, Tc)
+    qm, _ = scenario.map_queries(last, cur, K, Tl, Tc)
+    m = ORBmatcher(0.9, True)
+    n1, a1 = m.SearchByProjectionLast(dcur, ql, 15.0)
+    claimed = (a1 >= 0).astype(np.uint8)
+    n2, a2 = m.SearchByProjectionMap(dcur, qm, 3.0, claimed=claimed, nnratio=0.8)
+    on1, oa1 = OM.search_by_projection_last(hcur, ql, 15.0)
+    on2, oa2 = OM.search_by_projection_map(hcur, qm, 3.0, 0.8, claimed=(oa1 >= 0).astype(np.uint8))
+    assert (n1, n2) == (on1, on2) and np.array_equal(a1, oa1) and np.array_equal(a2, oa2)
+    # a new extraction gets a new key: no stale grid
+    mono, kp, desc = ex(synth.gray_frame(12))
+    assert ex.device_result(0).cache_key != dv.cache_key

@@ -107,4 +107,5 @@ def test_reset_and_errors(gpu):
     K = synth.intrinsics(160, 120)
     small.SetDepthCameraInfo(K["fx"], K["fy"], K["cx"], K["cy"], 160, 120)
     with pytest.raises(Exception):
-        small.integrate(synth.depth_frame(0, 160, 120), synth.pose(0))                                  # pool exhausted is reported, not silent
+        small.integrate(synth.depth_frame(0, 160, 120), synth.pose(0))                                  # pool exhausted is reported, not silent:
+        small.stats()                                                                                   # at the latest by the next call that needs the map
