@@ -291,6 +291,14 @@ int plvs_tsdf_integrate_depth(plvs_tsdf* h, const float* depth, int w, int h_,
                               const uint8_t* bgr, int bgr_step, int nch,
                               const float Twc[12], int mode, int on_device);
 
+/* Chisel::IntegratePointCloudWidthDepth (Thirdparty/open_chisel/src/Chisel.cpp:382-585) as reached through
+ * ChiselServer::SetPointCloud + IntegrateLastPointCloud (PLVS's default Chisel route, src/PointCloudMapChisel.cc:100-131):
+ * xyz = n camera-frame points (x,y,z float triples), rgb = n colour triples in [0,1] (r,g,b; NULL = no colour),
+ * depth = the registered depth image used by the carve pass (NULL or carving off = no carve pass), Twc as above.
+ * Host pointers.  Synchronous. */
+int plvs_tsdf_integrate_cloud(plvs_tsdf* h, const float* xyz, const float* rgb, int n, const float* depth, int w, int h_,
+                              const float Twc[12]);
+
 typedef struct {
     int32_t n_blocks;            /* live chunks in the map */
     int32_t n_range;             /* chunks enumerated by GetChunkIDsIntersecting for the last scan */

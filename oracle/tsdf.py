@@ -41,6 +41,18 @@ class Map:
                                         bgr.shape[2] if bgr is not None else 0, T.ctypes.data_as(C.c_void_p), mode)
         assert rc == 0, rc
 
+    def integrate_cloud(self, xyz, rgb, Twc, depth=None):
+        """Chisel::IntegratePointCloudWidthDepth: xyz [n,3] camera-frame points, rgb [n,3] floats in [0,1] (or None)."""
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        T = np.ascontiguousarray(Twc, np.float32).reshape(12)
+        rgb = None if rgb is None else np.ascontiguousarray(rgb, np.float32)
+        d = None if depth is None else np.ascontiguousarray(depth, np.float32)
+        self._l.orc_tsdf_integrate_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        rc = self._l.orc_tsdf_integrate_cloud(self._h, xyz.ctypes.data_as(C.c_void_p), rgb.ctypes.data_as(C.c_void_p) if rgb is not None else None,
+                                              len(xyz), d.ctypes.data_as(C.c_void_p) if d is not None else None,
+                                              d.shape[1] if d is not None else 0, d.shape[0] if d is not None else 0, T.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+
     def stats(self):
         s = np.zeros(5, np.int32)
         self._l.orc_tsdf_stats(self._h, s.ctypes.data_as(C.c_void_p))

@@ -282,4 +282,161 @@ int orc_tsdf_download(void* h, int32_t* keys, float* sdf, float* weight, uint8_t
     return (int)ord.size();
 }
 
+// ---------------------------------------------------------------------------------------------
+// a26: Chisel::IntegratePointCloudWidthDepth (Thirdparty/open_chisel/src/Chisel.cpp:382-585) -- PLVS's default
+// Chisel route (src/PointCloudMapping.cc:641-642): (i) ProjectionIntegrator::CarveWithDepth over the existing chunks
+// of the camera frustum (ProjectionIntegrator.h:271-335), (ii) per cloud point an Amanatides-Woo voxel walk
+// (src/geometry/Raycast.cpp:65-182) over +-max(trunc, diag) along the ray with
+// u = |Pc| (depth/Pc.z - 1), w = weight/(2 trunc), DistVoxel::Integrate + ColorVoxel::IntegrateSimple,
+// (iii) garbage collection of chunks that were created but never updated.  Points are processed in order, so the
+// running means see the reference's sequence.  Eigen::Affine3f::inverse() is a general 3x3 inverse (cofactors /
+// determinant), restated as such.
+// ---------------------------------------------------------------------------------------------
+static inline float sgn_f(int x) { return x > 0 ? 1.f : x < 0 ? -1.f : 0.f; }
+static inline float mod1(float value, float modulus) { return std::fmod(std::fmod(value, modulus) + modulus, modulus); }
+static float intbound(float s, int ds)
+{
+    // smallest positive t such that s + t*ds is an integer (Raycast.cpp)
+    if (ds < 0) return intbound(-s, -ds);
+    s = mod1(s, 1.f);
+    return (1 - s) / ds;
+}
+
+int orc_tsdf_integrate_cloud(void* h, const float* xyz, const float* rgb, int n, const float* depth, int w, int ht, const float* Twc)
+{
+    Map* m = (Map*)h;
+    const Params& P = m->p;
+    const float res = P.voxel_resolution;
+    const float diagD = (float)(2.0 * (double)std::sqrt(3.0f) * (double)res);
+    const float r00 = Twc[0], r01 = Twc[1], r02 = Twc[2], r10 = Twc[4], r11 = Twc[5], r12 = Twc[6], r20 = Twc[8], r21 = Twc[9], r22 = Twc[10];
+    const V3 t{Twc[3], Twc[7], Twc[11]};
+    int n_carved = 0;
+    if (P.use_carving && depth && m->got_camera) {
+        int32_t lo[3], hi[3];
+        orc_tsdf_chunk_range(h, depth, w, ht, Twc, 1, lo, hi);       // camera near/far planes (SetupFrustum of the stored camera)
+        const float half = res * 0.5f;
+        Frustum fr;
+        frustum_from_params(fr, Twc, P.near_plane, P.far_plane, m->fy, m->fy, m->cy, (float)m->width, (float)m->height);
+        for (auto& kv : m->blocks) {
+            const Key k = kv.first;
+            if (k.x < lo[0] || k.x > hi[0] || k.y < lo[1] || k.y > hi[1] || k.z < lo[2] || k.z > hi[2]) continue;   // ChunkManager::GetChunkIDsIntersecting
+            {
+                const V3 bmn{(float)(k.x * 16) * res, (float)(k.y * 16) * res, (float)(k.z * 16) * res};
+                if (!intersects(fr, bmn, bmn + V3{16.f * res, 16.f * res, 16.f * res})) continue;
+            }
+            Block& B = *kv.second;
+            const V3 origin{(float)(16 * k.x) * res, (float)(16 * k.y) * res, (float)(16 * k.z) * res};
+            bool upd = false;
+            int i = 0;
+            for (int z = 0; z < 16; ++z) for (int y = 0; y < 16; ++y) for (int x = 0; x < 16; ++x, ++i) {
+                if (B.w[i] <= 1e-15) continue;
+                const V3 c = V3{(float)x * res + half, (float)y * res + half, (float)z * res + half} + origin;
+                const V3 dv = c - t;
+                const V3 pc{r00 * dv.x + (r10 * dv.y + r20 * dv.z), r01 * dv.x + (r11 * dv.y + r21 * dv.z), r02 * dv.x + (r12 * dv.y + r22 * dv.z)};
+                const float invZ = 1.0f / pc.z;
+                const float u = m->fx * pc.x * invZ + m->cx, v = m->fy * pc.y * invZ + m->cy;
+                if (pc.z < 0 || !(u >= 0 && v >= 0 && u < m->width && v < m->height)) continue;
+                const float d = depth[(int)u + (int)v * w];
+                if (std::isnan(d)) continue;
+                const float trunc = std::max((P.trunc_quad * d * d + P.trunc_linear * d + P.trunc_const) * P.trunc_scale, diagD);
+                const float s = d - pc.z;
+                if (s > trunc + P.carving_dist && B.sdf[i] < 1e-5) { B.sdf[i] = 99999.f; B.w[i] = 0.f; upd = true; }
+            }
+            n_carved += upd;
+        }
+    }
+    // inverse pose, Eigen style
+    float inv[9], tinv[3];
+    {
+        const float a[9] = {r00, r01, r02, r10, r11, r12, r20, r21, r22};
+        auto cof = [&](int i, int j) { return a[((i + 1) % 3) * 3 + (j + 1) % 3] * a[((i + 2) % 3) * 3 + (j + 2) % 3] - a[((i + 1) % 3) * 3 + (j + 2) % 3] * a[((i + 2) % 3) * 3 + (j + 1) % 3]; };
+        const float c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+        const float det = c0 * a[0] + (c1 * a[3] + c2 * a[6]);
+        const float invdet = 1.0f / det;
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) inv[j * 3 + i] = cof(i, j) * invdet;
+        for (int i = 0; i < 3; ++i) tinv[i] = -(inv[i * 3] * t.x + (inv[i * 3 + 1] * t.y + inv[i * 3 + 2] * t.z));
+    }
+    const float roundToVoxel = 1.0f / res;
+    const float half = 0.5f * res;          // Vec3(0.5,0.5,0.5) * resolution
+    const float rf = 1.0f / (16 * res);
+    std::unordered_map<Key, bool, KeyHash> updated, created;
+    m->n_updated = m->n_new = m->n_collected = 0;
+    std::vector<Key> walk;
+    for (int i = 0; i < n; ++i) {
+        const V3 p{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        const float dpt = p.z;
+        if (dpt < 0.01f) continue;
+        const V3 wp{r00 * p.x + (r01 * p.y + r02 * p.z) + t.x, r10 * p.x + (r11 * p.y + r12 * p.z) + t.y, r20 * p.x + (r21 * p.y + r22 * p.z) + t.z};
+        V3 dir = wp - t;
+        const float nn = std::sqrt(dir.x * dir.x + (dir.y * dir.y + dir.z * dir.z));
+        dir = V3{dir.x / nn, dir.y / nn, dir.z / nn};
+        const float trunc = std::max((P.trunc_quad * dpt * dpt + P.trunc_linear * dpt + P.trunc_const) * P.trunc_scale, diagD);
+        const V3 swp = wp * roundToVoxel;
+        const V3 sdt = (dir * trunc) * roundToVoxel;
+        const V3 start = swp - sdt, end = swp + sdt;
+        // Raycast
+        walk.clear();
+        {
+            int x = (int)std::floor(start.x), y = (int)std::floor(start.y), z = (int)std::floor(start.z);
+            const int endX = (int)std::floor(end.x), endY = (int)std::floor(end.y), endZ = (int)std::floor(end.z);
+            const V3 direction = end - start;
+            const float maxDist = direction.x * direction.x + (direction.y * direction.y + direction.z * direction.z);
+            const float dx = (float)(endX - x), dy = (float)(endY - y), dz = (float)(endZ - z);
+            const int stepX = (int)sgn_f((int)dx), stepY = (int)sgn_f((int)dy), stepZ = (int)sgn_f((int)dz);
+            float tMaxX = intbound(start.x, (int)dx), tMaxY = intbound(start.y, (int)dy), tMaxZ = intbound(start.z, (int)dz);
+            const float tDeltaX = ((float)stepX) / dx, tDeltaY = ((float)stepY) / dy, tDeltaZ = ((float)stepZ) / dz;
+            if (!(stepX == 0 && stepY == 0 && stepZ == 0)) {
+                for (;;) {
+                    walk.push_back(Key{x, y, z});
+                    const V3 d3{(float)x - start.x, (float)y - start.y, (float)z - start.z};
+                    const float dist = d3.x * d3.x + (d3.y * d3.y + d3.z * d3.z);
+                    if (dist > maxDist) break;
+                    if (x == endX && y == endY && z == endZ) break;
+                    if (tMaxX < tMaxY) { if (tMaxX < tMaxZ) { x += stepX; tMaxX += tDeltaX; } else { z += stepZ; tMaxZ += tDeltaZ; } }
+                    else { if (tMaxY < tMaxZ) { y += stepY; tMaxY += tDeltaY; } else { z += stepZ; tMaxZ += tDeltaZ; } }
+                }
+            }
+        }
+        for (const Key& vc : walk) {
+            const V3 center{(float)vc.x * res + half, (float)vc.y * res + half, (float)vc.z * res + half};
+            const Key cid{(int)std::floor(center.x * rf), (int)std::floor(center.y * rf), (int)std::floor(center.z * rf)};
+            auto it = m->blocks.find(cid);
+            if (it == m->blocks.end()) { it = m->blocks.emplace(cid, std::make_unique<Block>()).first; created[cid] = true; updated[cid] = false; }
+            const int lx = vc.x - cid.x * 16, ly = vc.y - cid.y * 16, lz = vc.z - cid.z * 16;
+            const int id = (lz * 16 + ly) * 16 + lx;
+            if (!(id >= 0 && id < 4096)) continue;
+            Block& B = *it->second;
+            const V3 cc{inv[0] * center.x + (inv[1] * center.y + inv[2] * center.z) + tinv[0], inv[3] * center.x + (inv[4] * center.y + inv[5] * center.z) + tinv[1],
+                        inv[6] * center.x + (inv[7] * center.y + inv[8] * center.z) + tinv[2]};
+            const float length = std::sqrt(cc.x * cc.x + (cc.y * cc.y + cc.z * cc.z));
+            const float u = length * (dpt / cc.z - 1);
+            const float weight = P.weight / (2.0f * trunc);
+            if (std::fabs(u) < trunc) {
+                const float ow = B.w[id], os = B.sdf[id];
+                B.sdf[id] = (ow * os + weight * u) / (weight + ow);
+                B.w[id] = ow + weight;
+                if (rgb) {
+                    uint8_t* cv = &B.rgba[(size_t)id * 4];
+                    if (!(cv[3] >= 255 - 1)) {
+                        const uint8_t nr = (uint8_t)(rgb[3 * i] * 255.0f), ng = (uint8_t)(rgb[3 * i + 1] * 255.0f), nb = (uint8_t)(rgb[3 * i + 2] * 255.0f);
+                        const float invw = 1.f / (float)(1 + cv[3]);
+                        cv[0] = (uint8_t)((float)(cv[3] * cv[0] + 1 * nr) * invw);
+                        cv[1] = (uint8_t)((float)(cv[3] * cv[1] + 1 * ng) * invw);
+                        cv[2] = (uint8_t)((float)(cv[3] * cv[2] + 1 * nb) * invw);
+                        cv[3] = (uint8_t)(cv[3] + 1);
+                    }
+                }
+                updated[cid] = true;
+            }
+        }
+    }
+    for (auto& kv : updated) if (kv.second) ++m->n_updated;
+    for (auto& kv : created) {
+        if (!updated[kv.first]) { m->blocks.erase(kv.first); ++m->n_collected; }
+        else ++m->n_new;
+    }
+    m->n_range = n_carved;
+    return 0;
+}
+
 }  // extern "C"

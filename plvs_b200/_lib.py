@@ -114,6 +114,7 @@ def load():
     lib.plvs_tsdf_reset.argtypes = [C.c_void_p]
     lib.plvs_tsdf_set_camera.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
     lib.plvs_tsdf_integrate_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    lib.plvs_tsdf_integrate_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.plvs_tsdf_last_stats.argtypes = [C.c_void_p, C.POINTER(TsdfStats)]
     lib.plvs_tsdf_download_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.plvs_tsdf_export_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]

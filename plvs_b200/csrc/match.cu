@@ -245,13 +245,25 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
         my_flags = MODE == 0 ? reinterpret_cast<const plvs_mp_query*>(queries)[q].flags : reinterpret_cast<const plvs_last_query*>(queries)[q].flags;
     }
     if (SMEM) {
+        // stage the candidate lists: uint4 loads, 4 in flight per thread (rows are cap*4 bytes, cap is a multiple of 4)
         const int rows = min(per_cta, max(nq - q0, 0));
-        for (int i = tid; i < rows * cap; i += 1024) {
-            const int j = i / cap, k = i - j * cap;
-            if (k < min(cand_n[q0 + j], cap)) {
-                uint32_t e = cand[(size_t)(q0 + j) * cap + k];
-                if (claimed_in && claimed_in[cand_idx(e)]) e = 0xffffffffu;     // pre-claimed keypoints never compete
-                s_list[j * stride + k] = e;
+        const int c4 = cap >> 2, total4 = rows * c4;
+        const uint4* src4 = reinterpret_cast<const uint4*>(cand + (size_t)q0 * cap);
+        for (int i0 = tid; i0 < total4; i0 += 4 * 1024) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * 1024; v[u] = i < total4 ? src4[i] : make_uint4(0, 0, 0, 0); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * 1024;
+                if (i >= total4) continue;
+                const int j = i / c4, k = (i - j * c4) * 4;
+                uint32_t e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (claimed_in && cand_idx(e[t]) < n && claimed_in[cand_idx(e[t])]) e[t] = 0xffffffffu;   // pre-claimed keypoints never compete (slots past a list's length hold junk and are never read)
+                    s_list[j * stride + k + t] = e[t];
+                }
             }
         }
     }

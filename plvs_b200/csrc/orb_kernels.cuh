@@ -140,7 +140,7 @@ k_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, long long fr
 //     thresholds: maxima(t) = {strict 3x3 maxima of the cell-masked score map} ∩ {score >= t}.
 //     Candidates leave in the reference's order (raster inside the cell) into the cell's slots.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int fast_corner_score(const uint8_t* p, int stride, int min_th)
+__device__ __forceinline__ int fast_corner_score(const uint8_t* p, int stride, int min_th, int use_tree)
 {
     const int v = p[0];
     int d[16];
@@ -161,6 +161,22 @@ __device__ __forceinline__ int fast_corner_score(const uint8_t* p, int stride, i
     // (An unrolled min/max-tree formulation returned max(d)-1 inside this kernel on the B200 although
     // the same tree passes standalone -- tools/vimnmx_probe.cu -- and on the host; until that is
     // understood the score uses compares and bit logic only.  DESIGN.md "open issues".)
+    if (use_tree) {
+        // max over the 16 arcs of (min d) / (min -d), minus 1: doubling windows 2 -> 4 -> 8 (+1)
+        int lo2[16], hi2[16], lo4[16], hi4[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
+        int best = -1000;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
+            const int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
+            best = max(best, max(lo9, -hi9));
+        }
+        return best - 1;
+    }
     int lo = min_th, hi = 255;
 #pragma unroll 1
     while (hi - lo > 1) {
@@ -180,7 +196,7 @@ __global__ void __launch_bounds__(256)
 k_fast_cells(const uint8_t* __restrict__ pyr, long long frame_stride,
              const LevelGeom* __restrict__ levels, const CellDesc* __restrict__ cells,
              uint32_t* __restrict__ slots, long long slots_per_frame,
-             int* __restrict__ cell_count, int cells_per_frame, int ini_th, int min_th,
+             int* __restrict__ cell_count, int cells_per_frame, int ini_th, int min_th, int use_tree,
              uint8_t* __restrict__ dbg_score /* optional: score map in pyramid layout (inspection) */)
 {
     __shared__ uint8_t s_img[kMaxCell * kMaxCell];
@@ -203,7 +219,7 @@ k_fast_cells(const uint8_t* __restrict__ pyr, long long frame_stride,
     const int n = iw * ih;
     for (int i = tid; i < n; i += 256) {
         const int r = i / iw + 3, cc = i - (r - 3) * iw + 3;
-        s_sc[r * kMaxCell + cc] = (uint8_t)fast_corner_score(&s_img[r * kMaxCell + cc], kMaxCell, min_th);
+        s_sc[r * kMaxCell + cc] = (uint8_t)fast_corner_score(&s_img[r * kMaxCell + cc], kMaxCell, min_th, use_tree);
     }
     __syncthreads();
     if (dbg_score) {

@@ -99,3 +99,21 @@ def fundamental(K, Twc1, Twc2):
     C2 = R2.T @ (t1 - t2)
     ep = np.array([K["fx"] * C2[0] / C2[2] + K["cx"], K["fy"] * C2[1] / C2[2] + K["cy"]])
     return F12.astype(np.float32), ep.astype(np.float32)
+
+
+def cloud_from_depth(depth, bgr, K, step=2, min_depth=0.1, max_depth=5.0):
+    """Caller-side point cloud in the camera frame, the way PointCloudMapping builds it for the Chisel back-end
+    (src/PointCloudMapping.cc:838-846,929-1010: every `step`-th pixel with a valid depth; colours in [0,1], r,g,b)."""
+    h, w = depth.shape
+    v, u = np.mgrid[0:h:step, 0:w:step]
+    z = depth[v, u].astype(np.float32)
+    ok = (z > np.float32(min_depth)) & (z < np.float32(max_depth))
+    u, v, z = u[ok].astype(np.float32), v[ok].astype(np.float32), z[ok]
+    x = (u - np.float32(K["cx"])) * z / np.float32(K["fx"])
+    y = (v - np.float32(K["cy"])) * z / np.float32(K["fy"])
+    xyz = np.stack([x, y, z], 1).astype(np.float32)
+    rgb = None
+    if bgr is not None:
+        c = bgr[v.astype(int), u.astype(int)].astype(np.float32) / np.float32(255.0)
+        rgb = np.ascontiguousarray(c[:, ::-1])
+    return xyz, rgb

@@ -74,6 +74,17 @@ class ChiselServer:
         self._color = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
         self.IntegrateLastDepthImage(False)
 
+    def integrate_cloud(self, xyz, rgb, Twc, depth=None):
+        """SetPointCloud + (SetDepthImageMemorySharing) + IntegrateLastPointCloud(false): Chisel::IntegratePointCloudWidthDepth."""
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        T = np.ascontiguousarray(Twc, np.float32).reshape(12)
+        rgb = None if rgb is None else np.ascontiguousarray(rgb, np.float32)
+        d = None if depth is None else np.ascontiguousarray(depth, np.float32)
+        rc = self._lib.plvs_tsdf_integrate_cloud(self._h, xyz.ctypes.data_as(C.c_void_p), rgb.ctypes.data_as(C.c_void_p) if rgb is not None else None,
+                                                 len(xyz), d.ctypes.data_as(C.c_void_p) if d is not None else None,
+                                                 d.shape[1] if d is not None else 0, d.shape[0] if d is not None else 0, T.ctypes.data_as(C.c_void_p))
+        _lib.check(rc, "plvs_tsdf_integrate_cloud")
+
     def stats(self):
         s = _lib.TsdfStats()
         _lib.check(self._lib.plvs_tsdf_last_stats(self._h, C.byref(s)), "plvs_tsdf_last_stats")

@@ -109,3 +109,59 @@ def test_reset_and_errors(gpu):
     with pytest.raises(Exception):
         small.integrate(synth.depth_frame(0, 160, 120), synth.pose(0))                                  # pool exhausted is reported, not silent:
         small.stats()                                                                                   # at the latest by the next call that needs the map
+
+
+def _check_cloud(g, o, color):
+    gk, gs, gw, gc = g.download()
+    ok, os_, ow, oc = o.download()
+    assert gk.shape == ok.shape and np.array_equal(gk, ok), f"chunk key sets differ: {len(gk)} vs {len(ok)}"
+    assert np.abs(gw - ow).max() <= TOL
+    known = ow > 0
+    assert np.abs(gs[known] - os_[known]).max() <= TOL
+    assert np.array_equal(gs[~known], os_[~known])
+    if color:
+        assert np.array_equal(gc, oc)
+    assert g.stats()["n_blocks"] == o.stats()["n_blocks"]
+    return len(gk)
+
+
+@pytest.mark.parametrize("color,carve", [(True, 1), (False, 1), (True, 0)])
+def test_cloud_sequence(gpu, color, carve):
+    """a26: Chisel::IntegratePointCloudWidthDepth (PLVS's default Chisel route) -- carve pass over the existing chunks,
+    then per-point truncation-band ray casting with chunk creation; several points hit the same voxel, so the
+    per-voxel update ORDER (point index) is part of the contract."""
+    from plvs_b200 import scenario
+    w, h = 320, 240
+    K = synth.intrinsics(w, h)
+    g, o = _pair(w, h, voxel_resolution=0.02, use_carving=carve, carving_dist=0.05, near_plane=0.1, far_plane=5.0, max_blocks=16384, use_color=int(color))
+    for f in (0, 1, 2, 5):
+        d = synth.depth_frame(f, w, h)
+        c = synth.bgr_frame(f, w, h) if color else None
+        xyz, rgb = scenario.cloud_from_depth(d, c, K, step=2)
+        assert len(xyz) > 10000
+        g.integrate_cloud(xyz, rgb, synth.pose(f), d); o.integrate_cloud(xyz, rgb, synth.pose(f), d)
+        n = _check_cloud(g, o, color)
+    assert n > 200
+
+
+def test_cloud_edge_cases(gpu):
+    from plvs_b200 import scenario
+    w, h = 160, 120
+    K = synth.intrinsics(w, h)
+    g, o = _pair(w, h, voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=4096, use_color=1)
+    Twc = synth.pose(3)
+    # empty cloud with a depth image: only the carve pass runs (on an empty map: nothing)
+    e = np.zeros((0, 3), np.float32)
+    g.integrate_cloud(e, e, Twc, synth.depth_frame(3, w, h)); o.integrate_cloud(e, e, Twc, synth.depth_frame(3, w, h))
+    assert g.stats()["n_blocks"] == 0
+    # cloud without a depth image and without colours
+    d = synth.depth_frame(3, w, h)
+    xyz, _ = scenario.cloud_from_depth(d, None, K, step=1)
+    g.integrate_cloud(xyz, None, Twc); o.integrate_cloud(xyz, None, Twc)
+    _check_cloud(g, o, True)
+    # mixed with the projective depth-scan path on the same map
+    g.integrate(d, Twc, synth.bgr_frame(3, w, h)); o.integrate(d, Twc, synth.bgr_frame(3, w, h))
+    _check_cloud(g, o, True)
+    xyz, rgb = scenario.cloud_from_depth(synth.depth_frame(4, w, h), synth.bgr_frame(4, w, h), K, step=3)
+    g.integrate_cloud(xyz, rgb, synth.pose(4), synth.depth_frame(4, w, h)); o.integrate_cloud(xyz, rgb, synth.pose(4), synth.depth_frame(4, w, h))
+    _check_cloud(g, o, True)

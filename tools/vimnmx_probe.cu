@@ -42,6 +42,24 @@ __global__ void probe(const int* in, int n, int* bad, int* first)
     int a = score_tree(d), b = score_ref(d);
     if (a != b) { if (atomicAdd(bad, 1) == 0) { first[0] = i; first[1] = a; first[2] = b; } }
 }
+
+// same tree, but the differences come from BYTES in shared memory (centre minus ring pixel), as in k_fast_cells:
+// the compiler now knows every d[k] fits in 9 bits and is free to pick narrower / packed min-max forms
+__global__ void probe_u8(const unsigned char* in, int n, int* bad, int* first)
+{
+    __shared__ unsigned char s[256 * 17];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int k = 0; k < 17; ++k) s[threadIdx.x * 17 + k] = i < n ? in[(size_t)i * 17 + k] : 0;
+    __syncthreads();
+    if (i >= n) return;
+    const unsigned char* p = &s[threadIdx.x * 17];
+    const int v = p[0];
+    int d[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) d[k] = v - p[1 + k];
+    int a = score_tree(d), b = score_ref(d);
+    if (a != b) { if (atomicAdd(bad, 1) == 0) { first[0] = i; first[1] = a; first[2] = b; } }
+}
 int main()
 {
     const int n = 1 << 20;
@@ -56,5 +74,13 @@ int main()
     int bad = -1, first[3] = {0, 0, 0};
     cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost); cudaMemcpy(first, d_first, 12, cudaMemcpyDeviceToHost);
     printf("vimnmx_probe: %d of %d mismatches (first idx %d tree %d ref %d) err=%s\n", bad, n, first[0], first[1], first[2], cudaGetErrorString(cudaGetLastError()));
+    std::vector<unsigned char> hb((size_t)n * 17);
+    for (auto& v : hb) v = (unsigned char)(rand() & 255);
+    unsigned char* d_b; cudaMalloc(&d_b, hb.size());
+    cudaMemcpy(d_b, hb.data(), hb.size(), cudaMemcpyHostToDevice);
+    cudaMemset(d_bad, 0, 4);
+    probe_u8<<<n / 256, 256>>>(d_b, n, d_bad, d_first);
+    cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost); cudaMemcpy(first, d_first, 12, cudaMemcpyDeviceToHost);
+    printf("vimnmx_probe_u8: %d of %d mismatches (first idx %d tree %d ref %d) err=%s\n", bad, n, first[0], first[1], first[2], cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
