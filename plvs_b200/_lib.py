@@ -8,7 +8,7 @@ import os
 import pathlib
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libplvs_b200.so"
+LIB_PATH = pathlib.Path(os.environ.get("PLVS_B200_LIB", str(pathlib.Path(__file__).resolve().parent / "libplvs_b200.so")))
 
 
 class PlvsError(RuntimeError):

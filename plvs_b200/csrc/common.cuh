@@ -24,6 +24,17 @@ void set_error(const char* fmt, ...);
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
+// Per-frame buffers are sized by data-dependent counts (keypoints, queries, chunk ranges).  Growing one means
+// cudaFree + cudaMalloc (device-wide synchronisation) or cudaHostAlloc (milliseconds), so small buffers grow with
+// slack: 25 % on top of the request, at least 1.5x the old size.  Buffers above 64 MiB are allocated exactly.
+inline size_t grow_capacity(size_t count, size_t old_n, size_t elem)
+{
+    if (count * elem > ((size_t)64 << 20)) return count;
+    size_t c = count + count / 4 + 64;
+    if (c < old_n + old_n / 2) c = old_n + old_n / 2;
+    return c;
+}
+
 // Device memory that is released with the owning handle.
 template <typename T>
 struct DevBuf {
@@ -31,6 +42,7 @@ struct DevBuf {
     size_t n = 0;
     int alloc(size_t count) {
         if (count <= n && p) return PLVS_OK;
+        count = grow_capacity(count, n, sizeof(T));
         release();
         if (cudaMalloc((void**)&p, count * sizeof(T)) != cudaSuccess) {
             p = nullptr; n = 0;
@@ -53,6 +65,7 @@ struct PinBuf {
     size_t n = 0;
     int alloc(size_t count) {
         if (count <= n && h) return PLVS_OK;
+        count = grow_capacity(count, n, sizeof(T));
         release();
         if (cudaHostAlloc((void**)&h, count * sizeof(T), cudaHostAllocMapped) != cudaSuccess) {
             h = nullptr; n = 0;
