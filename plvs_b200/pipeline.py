@@ -8,6 +8,7 @@ Caller-side work that is NOT part of the hot path (building map-point / last-fra
 depth) is precomputed once by `prepare()` so the timed region contains only the hot path."""
 import ctypes as C
 import threading
+import time
 import numpy as np
 
 from . import _lib, synth, scenario, tsdf as T
@@ -65,6 +66,7 @@ class HotPath:
     def __init__(self, data, nfeatures=2000, voxel=0.01, far=5.0, max_blocks=32768, device=0, batch=8, use_color=True):
         self.d, self.batch, self.device = data, batch, device
         self.ex = ORBextractor(nfeatures, 1.2, 8, 20, 7, device=device)
+        self.ex2 = None           # second extractor workspace, created by run_stream (batch k+1 extracts while batch k is matched)
         self.m_track = ORBmatcher(0.9, True, device=device)      # TrackWithMotionModel (src/Tracking.cc:3593)
         self.m_map = ORBmatcher(0.8, True, device=device)        # SearchLocalPoints (src/Tracking.cc:4477)
         self.m_tri = ORBmatcher(0.6, False, device=device)       # CreateNewMapFeatures (src/LocalMapping.cc:537)
@@ -179,6 +181,123 @@ class HotPath:
         else:
             self._track_batch(f0, nb, resident, out)
             self._map_batch(f0, nb, resident, out)
+        return out
+
+    # ---- timed: the same hot path as a 4-stage software pipeline over consecutive steps --------------------
+    def run_stream(self, f0, nsteps, resident=False, per_step=None):
+        """`nsteps` steps of `batch` frames starting at frame f0, with the reference's thread structure made explicit:
+        frame construction / ORB extraction, Tracking's two SearchByProjection calls, LocalMapping's
+        SearchForTriangulation and PointCloudMapping's TSDF integration run in four threads, each on its own library
+        handle (= its own CUDA stream), connected by queues.  Every call is still synchronous for its caller; the
+        overlap is between calls of different stages (batch k+1 extracts while batch k is matched, ...).
+        Returns the summed statistics once everything has drained."""
+        import queue
+        d, nb = self.d, self.batch
+        if self.ex2 is None:
+            self.ex2 = ORBextractor(self.ex.nfeatures, 1.2, 8, 20, 7, device=self.device)
+        exs = (self.ex, self.ex2)
+        free = [threading.Semaphore(1), threading.Semaphore(1)]      # extractor workspace i may be overwritten
+        q_track, q_tri = queue.Queue(), queue.Queue()
+        out, err = {}, []
+        lock = threading.Lock()
+        sf, s2 = self.ex.mvScaleFactor, self.ex.mvLevelSigma2
+
+        def add(k, v):
+            with lock:
+                out[k] = out.get(k, 0) + v
+
+        def guard(fn):
+            def run():
+                try:
+                    fn()
+                except Exception as e:          # surface worker failures in the caller
+                    err.append(e)
+                    q_track.put(None); q_tri.put(None)
+                    for sem in free:
+                        sem.release()
+            return run
+
+        def extract_stage():
+            for s in range(nsteps):
+                if err:
+                    break
+                i = s & 1
+                free[i].acquire()
+                t0 = time.perf_counter()
+                if per_step is not None:
+                    per_step(s)
+                fs = f0 + s * nb
+                if resident:
+                    g = self.dev["gray"]
+                    mono, kps, descs = exs[i].extract_batch((g[fs].data_ptr(), nb, d.h, d.w, d.w, d.w * d.h))
+                else:
+                    mono, kps, descs = exs[i].extract_batch(d.gray[fs:fs + nb])
+                add("keypoints", sum(len(k) for k in kps))
+                add("busy_extract_s", time.perf_counter() - t0)
+                q_track.put((s, i, kps, descs))
+            q_track.put(None)
+
+        def track_stage():
+            while True:
+                it = q_track.get()
+                if it is None:
+                    break
+                s, i, kps, descs = it
+                q_tri.put((s, kps, descs))
+                t0 = time.perf_counter()
+                nm = 0
+                for b in range(nb):
+                    f = f0 + s * nb + b
+                    p = self.prepared[f]
+                    if p is None:
+                        continue
+                    dv = exs[i].device_result(b)
+                    cur = Frame(None, None, d.w, d.h, sf, s2, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key))
+                    n1, a1 = self.m_track.SearchByProjectionLast(cur, p["ql"], 15.0)
+                    claimed = (a1 >= 0).astype(np.uint8)
+                    n2, a2 = self.m_track.SearchByProjectionMap(cur, p["qm"], 3.0, claimed=claimed, nnratio=0.8)
+                    nm += n1 + n2
+                free[i].release()
+                add("matches", nm)
+                add("busy_track_s", time.perf_counter() - t0)
+            q_tri.put(None)
+
+        def tri_stage():
+            while True:
+                it = q_tri.get()
+                if it is None:
+                    break
+                s, kps, descs = it
+                t0 = time.perf_counter()
+                nm = 0
+                for b in range(nb):
+                    f = f0 + s * nb + b
+                    p = self.prepared[f]
+                    if p is None:
+                        continue
+                    cur_ref, last = self.frames[f], self.frames[f - 1]
+                    n3, m12 = self.m_tri.SearchForTriangulation(Frame(kps[b], descs[b], d.w, d.h, sf, s2, uright=cur_ref.uright, bf=d.K["bf"]), last,
+                                                                p["fv1"], p["fv2"], p["has1"], p["has2"], p["F12"], p["ep"], False, False)
+                    nm += n3
+                add("matches", nm)
+                add("busy_tri_s", time.perf_counter() - t0)
+
+        def map_stage():
+            t0 = time.perf_counter()
+            for s in range(nsteps):
+                if err:
+                    break
+                self._map_batch(f0 + s * nb, nb, resident, out)
+            self.tsdf.stats()                      # waits for the last scan
+            add("busy_map_s", time.perf_counter() - t0)
+
+        ts = [threading.Thread(target=guard(fn)) for fn in (extract_stage, track_stage, tri_stage, map_stage)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if err:
+            raise err[0]
         return out
 
     def match_rounds(self):

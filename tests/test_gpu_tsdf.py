@@ -165,3 +165,39 @@ def test_cloud_edge_cases(gpu):
     xyz, rgb = scenario.cloud_from_depth(synth.depth_frame(4, w, h), synth.bgr_frame(4, w, h), K, step=3)
     g.integrate_cloud(xyz, rgb, synth.pose(4), synth.depth_frame(4, w, h)); o.integrate_cloud(xyz, rgb, synth.pose(4), synth.depth_frame(4, w, h))
     _check_cloud(g, o, True)
+
+
+def test_1080p_5mm_scan_pair(gpu):
+    """BASELINE config 3 geometry (1920x1080, 5 mm voxels): two consecutive scans (the second one exercises carving, the
+    carvable-octant mask and the bulk-copy ring over existing chunks); depth clipped to 3.2 m to bound the oracle."""
+    w, h = 1920, 1080
+    g, o = _pair(w, h, voxel_resolution=0.005, use_carving=1, near_plane=0.1, far_plane=3.4, max_blocks=40000, use_color=1)
+    o2 = OT.Map(T.default_params(voxel_resolution=0.005, use_carving=1, near_plane=0.1, far_plane=3.4, max_blocks=40000, use_color=1), threads=32)
+    K = synth.intrinsics(w, h)
+    o2.set_camera(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
+    for f in (0, 1):
+        d = synth.depth_frame(f, w, h)
+        d[d > 3.2] = 0.0
+        c = synth.bgr_frame(f, w, h)
+        g.integrate(d, synth.pose(f), c); o2.integrate(d, synth.pose(f), c)
+        n = _check(g, o2, color=True)
+    assert n > 1000
+
+
+def test_many_scans_carvable_mask_stays_exact(gpu):
+    """20 scans of a moving camera + a surface that retreats: the per-octant carvable mask must never hide a voxel the
+    reference would carve (sdf / weight / colour compared after every scan)."""
+    g, o = _pair(160, 120, voxel_resolution=0.03, use_carving=1, carving_dist=0.02, near_plane=0.1, far_plane=4.5, max_blocks=8192, use_color=1)
+    for f in range(20):
+        d = synth.depth_frame(f, 160, 120)
+        if f >= 10:
+            d = d + np.float32(0.12 * (f - 9))           # everything moves away from the camera: old surface voxels get carved
+        c = synth.bgr_frame(f, 160, 120)
+        g.integrate(d, synth.pose(f), c); o.integrate(d, synth.pose(f), c)
+        _check(g, o, color=True)
+    # the no-colour variant carves with Carve() (weight += 1.5) instead of Reset()
+    g, o = _pair(160, 120, voxel_resolution=0.03, use_carving=1, carving_dist=0.02, near_plane=0.1, far_plane=4.5, max_blocks=8192, use_color=0)
+    for f in range(12):
+        d = synth.depth_frame(f, 160, 120) + np.float32(0.1 * max(0, f - 5))
+        g.integrate(d, synth.pose(f)); o.integrate(d, synth.pose(f))
+        _check(g, o)
