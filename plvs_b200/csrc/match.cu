@@ -188,21 +188,23 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// Phase B: claim resolution by fixed-point rounds on ONE thread-block cluster (8 CTAs x 32 warps, one
-// warp per query per pass; rounds are separated by cluster barriers, claims live in L2).
-// claim[idx] = lowest query index with Observations()>0 currently targeting idx (blocks later ones).
-// The reference's running best / second-best over the candidate sequence equals the two smallest
-// (distance, position) keys of the unblocked candidates, so a warp finds them with shuffles:
-//   best   = lexicographic min (dist, pos)                       -> first strict minimum, as `dist<bestDist`
-//   second = lexicographic min over the rest                     -> what `else if(dist<bestDist2)` / the
-//                                                                   demotion of the old best leave behind
+// Phase B: claim resolution.  The reference walks the queries in order and a keypoint taken by an earlier query
+// (one whose map point has Observations() > 0) is skipped by the later ones (src/ORBmatcher.cc:113-115,1848-1850), so
+// target(q) is a function of target(0..q-1).  One thread-block cluster of 8 co-scheduled CTAs runs that recurrence as a
+// WAVEFRONT over 8 query ranges:
+//   - inside a range (<= 1024 queries, one thread each) the CTA iterates to the fixed point in shared memory:
+//     claim[idx] = lowest own query currently targeting idx; every query re-walks its candidate list (exactly the
+//     reference's running best / second best with strict `<`) skipping candidates claimed by a lower query; repeat
+//     until no target moves.  By induction on q the fixed point is the sequential result; an iteration costs three
+//     __syncthreads and no global traffic;
+//   - range c first converges against no outside claims (overlaps the wait), then waits for range c-1 to be FINAL
+//     (release/acquire flag in global memory), folds the final targets of all lower ranges into its blocked table and
+//     converges again (usually one more iteration: cross-range conflicts are rare), publishes, raises its flag;
+//   - the last range owns the wrap-up (holders, rotation histogram, copy-out): by then everything is final.
+// No cluster barrier, no global atomics, no per-round table clears: the previous design (global Jacobi rounds separated by
+// cluster barriers) spent 6.4 us per round and needed up to 9 rounds (profiles/r01_*).
 // ---------------------------------------------------------------------------------------------
 constexpr int kResolveCtas = 8;
-
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n" "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
 
 __device__ __forceinline__ uint32_t cluster_cta_rank()
 {
@@ -210,40 +212,37 @@ __device__ __forceinline__ uint32_t cluster_cta_rank()
     asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
     return r;
 }
+__device__ __forceinline__ int ld_acquire(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// One thread per query: it walks its candidate list exactly like the reference's inner loop (running best / second
-// best with strict `<`), skipping candidates claimed by lower-numbered queries.  SMEM == true: the CTA caches the
-// lists of its queries (row stride cap|1: conflict-free column walks) and a private copy of the claim table in
-// shared memory, so a round is one coalesced L2 read of the table + shared-memory traffic; SMEM == false reads both
-// from L2 (any size).  Three claim tables rotate (read r, write r+1, clear r+2) and four change flags, so a round
-// needs a single cluster barrier.
+// SMEM == true: the candidate lists of the range are cached in shared memory (row stride cap|1: conflict-free column
+// walks); SMEM == false reads them from L2 (any size).
 template <int MODE, bool SMEM>
 __global__ void __cluster_dims__(kResolveCtas, 1, 1) __launch_bounds__(1024)
 k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int cap, const void* __restrict__ queries, int nq,
           const plvs_keypoint* __restrict__ keys, int n, const uint8_t* __restrict__ claimed_in, float nn_ratio, int check_ori,
-          int* claims /*3*n*/, int* target /*nq*/, int* state /*[4] change flags, zeroed by the host*/,
+          int* target /*nq*/, int* flags /*[kResolveCtas] range-final flags + [8] total inner iterations, zeroed by the host*/,
           int32_t* assign /*n, device*/, int32_t* assign_out /*n, mapped host*/, int* result /*[0]=nmatches,[1]=rounds*/, int per_cta)
 {
     extern __shared__ uint32_t s_dyn[];
     __shared__ int s_count, s_hist[HISTO], s_keep[HISTO];
     const int tid = threadIdx.x;
     const int crank = (int)cluster_cta_rank();
-    const int gtid = crank * 1024 + tid, gthreads = kResolveCtas * 1024;
     const int INF = 0x7fffffff;
     const int stride = cap | 1;
-    int* s_claim = reinterpret_cast<int*>(s_dyn);                               // n   (SMEM only)
-    uint32_t* s_list = s_dyn + (SMEM ? n : 0);                                  // per_cta * stride (SMEM only)
+    int* s_blocked = reinterpret_cast<int*>(s_dyn);                             // n: 1 = taken by a query of a lower range (or pre-claimed)
+    int* s_claim = s_blocked + n;                                               // n: lowest own query targeting the keypoint
+    uint32_t* s_list = s_dyn + 2 * n;                                           // per_cta * stride (SMEM only)
     const int q0 = crank * per_cta;
     const int q = q0 + tid;
     const bool mine = tid < per_cta && q < nq;
-    for (int i = gtid; i < 3 * n; i += gthreads) claims[i] = INF;
     int m = 0, my_target = -1;
     uint32_t my_flags = 0;
     if (mine) {
-        target[q] = -1;
         m = min(cand_n[q], cap);
         my_flags = MODE == 0 ? reinterpret_cast<const plvs_mp_query*>(queries)[q].flags : reinterpret_cast<const plvs_last_query*>(queries)[q].flags;
     }
+    for (int i = tid; i < n; i += 1024) s_blocked[i] = (claimed_in && claimed_in[i]) ? 1 : 0;   // pre-claimed keypoints never compete
     if (SMEM) {
         // stage the candidate lists: uint4 loads, 4 in flight per thread (rows are cap*4 bytes, cap is a multiple of 4)
         const int rows = min(per_cta, max(nq - q0, 0));
@@ -258,63 +257,64 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
                 const int i = i0 + u * 1024;
                 if (i >= total4) continue;
                 const int j = i / c4, k = (i - j * c4) * 4;
-                uint32_t e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if (claimed_in && cand_idx(e[t]) < n && claimed_in[cand_idx(e[t])]) e[t] = 0xffffffffu;   // pre-claimed keypoints never compete (slots past a list's length hold junk and are never read)
-                    s_list[j * stride + k + t] = e[t];
-                }
+                s_list[j * stride + k] = v[u].x; s_list[j * stride + k + 1] = v[u].y; s_list[j * stride + k + 2] = v[u].z; s_list[j * stride + k + 3] = v[u].w;
             }
         }
     }
-    cluster_sync_all();
-    int rounds = 0;
-    for (;;) {
-        const int* cur = claims + (size_t)(rounds % 3) * n;
-        int* nxt = claims + (size_t)((rounds + 1) % 3) * n;
-        int* clr = claims + (size_t)((rounds + 2) % 3) * n;
-        if (SMEM) {
-            for (int i = tid; i < n; i += 1024) s_claim[i] = rounds ? __ldcg(&cur[i]) : INF;
+    __syncthreads();
+
+    int iterations = 0;
+    // local fixed point of the range against the current s_blocked
+    auto converge = [&]() {
+        for (;;) {
+            for (int i = tid; i < n; i += 1024) s_claim[i] = INF;
             __syncthreads();
-        }
-        bool changed_here = false;
-        if (mine) {
-            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-            for (int k = 0; k < m; ++k) {
-                uint32_t e; int idx;
-                if (SMEM) {
-                    e = s_list[tid * stride + k];
-                    if (e == 0xffffffffu) continue;
-                    idx = cand_idx(e);
-                    if (s_claim[idx] < q) continue;
-                } else {
-                    e = cand[(size_t)q * cap + k];
-                    idx = cand_idx(e);
-                    if ((claimed_in && claimed_in[idx]) || (rounds && __ldcg(&cur[idx]) < q)) continue;
+            if (mine && my_target >= 0 && (my_flags & PLVS_Q_OBS_POSITIVE)) atomicMin(&s_claim[my_target], q);
+            __syncthreads();
+            bool changed_here = false;
+            if (mine) {
+                int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+                for (int k = 0; k < m; ++k) {
+                    const uint32_t e = SMEM ? s_list[tid * stride + k] : cand[(size_t)q * cap + k];
+                    const int idx = cand_idx(e);
+                    if (s_blocked[idx] || s_claim[idx] < q) continue;
+                    const int dist = cand_dist(e);
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = cand_level(e); bestIdx = idx; }
+                    else if (MODE == 0 && dist < bestDist2) { bestLevel2 = cand_level(e); bestDist2 = dist; }
                 }
-                const int dist = cand_dist(e);
-                if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = cand_level(e); bestIdx = idx; }
-                else if (MODE == 0 && dist < bestDist2) { bestLevel2 = cand_level(e); bestDist2 = dist; }
+                int t = -1;
+                if (bestDist <= TH_HIGH) {
+                    if (MODE == 0) {
+                        if (!(bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) &&
+                            (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2)) t = bestIdx;
+                    } else t = bestIdx;
+                }
+                if (t != my_target) { my_target = t; changed_here = true; }
             }
-            int t = -1;
-            if (bestDist <= TH_HIGH) {
-                if (MODE == 0) {
-                    if (!(bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) &&
-                        (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2)) t = bestIdx;
-                } else t = bestIdx;
-            }
-            if (t != my_target) { my_target = t; target[q] = t; changed_here = true; }
-            if (t >= 0 && (my_flags & PLVS_Q_OBS_POSITIVE)) atomicMin(&nxt[t], q);
+            ++iterations;
+            if (!__syncthreads_or(changed_here ? 1 : 0)) break;
         }
-        for (int i = gtid; i < n; i += gthreads) clr[i] = INF;
-        if (gtid == 0) state[(rounds + 2) & 3] = 0;
-        if (__syncthreads_or(changed_here ? 1 : 0) && tid == 0) atomicOr(&state[rounds & 3], 1);
-        cluster_sync_all();
-        const int changed = __ldcg(&state[rounds & 3]);
-        ++rounds;
-        if (!changed) break;
+    };
+    converge();                                          // against the pre-claimed keypoints only: overlaps the wait below
+    if (crank > 0) {
+        if (tid == 0) { while (ld_acquire(&flags[crank - 1]) == 0) { } }
+        __syncthreads();
+        // fold the FINAL targets of every lower range into the blocked table
+        bool any = false;
+        for (int qq = tid; qq < q0; qq += 1024) {
+            const int t = __ldcg(&target[qq]);
+            if (t < 0) continue;
+            const uint32_t f = MODE == 0 ? reinterpret_cast<const plvs_mp_query*>(queries)[qq].flags : reinterpret_cast<const plvs_last_query*>(queries)[qq].flags;
+            if (f & PLVS_Q_OBS_POSITIVE) { s_blocked[t] = 1; any = true; }
+        }
+        if (__syncthreads_or(any ? 1 : 0)) converge();
     }
-    if (crank != 0) return;        // the wrap-up is one cheap pass: CTA 0 finishes alone (no cluster barrier after this point)
+    if (mine) target[q] = my_target;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) { atomicAdd(&flags[kResolveCtas], iterations); st_release(&flags[crank], 1); }
+    if (crank != kResolveCtas - 1) return;
+    const int rounds = atomicAdd(&flags[kResolveCtas], 0);      // total inner iterations over the ranges (statistic)
     // final holders: the last (highest) query that wrote each keypoint
     for (int i = tid; i < n; i += 1024) assign[i] = -1;
     if (tid == 0) s_count = 0;
@@ -716,7 +716,7 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         d_claimed = h->d_claimed.p;
     }
     if ((rc = h->d_cell_start.alloc(GRID_CELLS + 1)) || (rc = h->d_sorted.alloc(n)) || (rc = h->d_kp_cell.alloc(n)) ||
-        (rc = h->d_cand_n.alloc(nq)) || (rc = h->d_state.alloc(4)) || (rc = h->d_claim_a.alloc((size_t)3 * n)) || (rc = h->d_target.alloc(nq)) ||
+        (rc = h->d_cand_n.alloc(nq)) || (rc = h->d_state.alloc(16)) || (rc = h->d_claim_a.alloc((size_t)3 * n)) || (rc = h->d_target.alloc(nq)) ||
         (rc = h->d_assign.alloc(n)) || (rc = h->p_assign.alloc(n)) || (rc = h->p_result.alloc(4)) || (rc = h->p_cand_n.alloc(nq)))
         return rc;
     int launches = 0;
@@ -736,10 +736,11 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         ++launches;
         PLVS_CUDA(cudaMemcpyAsync(h->p_cand_n.h, h->d_cand_n.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
         h->timer.begin(PLVS_MATCH_K_RESOLVE, st);
-        PLVS_CUDA(cudaMemsetAsync(h->d_state.p, 0, 4 * sizeof(int), st));
+        PLVS_CUDA(cudaMemsetAsync(h->d_state.p, 0, 16 * sizeof(int), st));
         {
             const int per_cta = div_up(nq, kResolveCtas);
-            const size_t smem = ((size_t)n + (size_t)per_cta * (h->cap | 1)) * sizeof(uint32_t);
+            const size_t smem = ((size_t)2 * n + (size_t)per_cta * (h->cap | 1)) * sizeof(uint32_t);
+            const size_t smem_small = (size_t)2 * n * sizeof(uint32_t);
             if (per_cta <= 1024 && smem <= 200 * 1024) {
                 static thread_local bool attr_set[2] = {false, false};
                 if (!attr_set[MODE]) {
@@ -747,10 +748,10 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
                     attr_set[MODE] = true;
                 }
                 k_resolve<MODE, true><<<kResolveCtas, 1024, smem, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
-                                                                        h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta);
+                                                                        h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta);
             } else if (per_cta <= 1024) {
-                k_resolve<MODE, false><<<kResolveCtas, 1024, 0, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
-                                                                      h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta);
+                k_resolve<MODE, false><<<kResolveCtas, 1024, smem_small, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
+                                                                      h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta);
             } else { set_error("more than %d queries per search are not supported", kResolveCtas * 1024); return PLVS_EINVAL; }
         }
         h->timer.end(st);

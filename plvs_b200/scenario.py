@@ -114,6 +114,6 @@ def cloud_from_depth(depth, bgr, K, step=2, min_depth=0.1, max_depth=5.0):
     xyz = np.stack([x, y, z], 1).astype(np.float32)
     rgb = None
     if bgr is not None:
-        c = bgr[v.astype(int), u.astype(int)].astype(np.float32) / np.float32(255.0)
+        c = bgr[v.astype(int), u.astype(int)].astype(np.float32) * (np.float32(1.0) / np.float32(255.0))     # byteToFloat, Conversions.h:78
         rgb = np.ascontiguousarray(c[:, ::-1])
     return xyz, rgb

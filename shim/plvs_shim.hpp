@@ -30,6 +30,10 @@
 #endif
 
 namespace plvs_shim {
+// colours of a cloud point, when it has them (PointXYZ has none: SetPointsAndColors is a no-op for it, Conversions.h:63-67)
+template <class P> auto point_rgb_impl(const P& pt, float k, float* out, int) -> decltype((void)pt.r, true) { out[0] = pt.r * k; out[1] = pt.g * k; out[2] = pt.b * k; return true; }
+template <class P> bool point_rgb_impl(const P&, float, float*, long) { return false; }
+template <class P> bool point_rgb(const P& pt, float k, float* out) { return point_rgb_impl(pt, k, out, 0); }
 inline void check(int rc, const char* what)
 {
     if (rc != PLVS_OK) throw std::runtime_error(std::string(what) + ": " + plvs_last_error());
@@ -337,10 +341,41 @@ public:
         plvs_shim::check(plvs_tsdf_integrate_depth(h_, depth_, dw_, dh_, color ? color_ : nullptr, cstep_, cn_, Twc_,
                                                    color ? PLVS_TSDF_SCAN_COLOR : PLVS_TSDF_SCAN, 0), "plvs_tsdf_integrate_depth");
     }
+    // ChiselServer::SetPointCloud (ChiselServer.cpp:560-583): camera-frame cloud + its pose; colours become floats with
+    // byteToFloat = 1.0f / 255.0f exactly as PclPointCloudToChisel does (Conversions.h:69-94).  CloudT is any
+    // pcl::PointCloud<PointT>-like type whose points have x, y, z (and r, g, b when useColor).
+    template <class CloudT>
+    void SetPointCloud(const CloudT& cloud_camera, const Eigen::Affine3f& Twc)
+    {
+        const size_t n = cloud_camera.points.size();
+        cloudXyz_.resize(3 * n);
+        cloudRgb_.resize(useColor && useColorCloud_ ? 3 * n : 0);
+        const float byteToFloat = 1.0f / 255.0f;
+        size_t i = 0;
+        for (const auto& pt : cloud_camera.points) {
+            cloudXyz_[3 * i] = pt.x; cloudXyz_[3 * i + 1] = pt.y; cloudXyz_[3 * i + 2] = pt.z;
+            if (!cloudRgb_.empty() && !plvs_shim::point_rgb(pt, byteToFloat, &cloudRgb_[3 * i])) { cloudRgb_.clear(); useColorCloud_ = false; }
+            ++i;
+        }
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) cloudTwc_[4 * r + c] = Twc.linear()(r, c); cloudTwc_[4 * r + 3] = Twc.translation()(r); }
+        gotCloudPose = true;
+    }
+    // ChiselServer::IntegrateLastPointCloud (ChiselServer.cpp:664-705) -> Chisel::IntegratePointCloudWidthDepth: the carve pass
+    // uses the depth image registered with SetDepthImage[MemorySharing] when the depth camera info is known
+    void IntegrateLastPointCloud(bool /*updateMesh*/ = true)
+    {
+        if (!gotCloudPose) { std::fprintf(stderr, "ChiselServer - PROBLEM in integrating point cloud!!! ************\n"); return; }
+        const bool with_depth = gotInfo && depth_;
+        plvs_shim::check(plvs_tsdf_integrate_cloud(h_, cloudXyz_.data(), cloudRgb_.empty() ? nullptr : cloudRgb_.data(), (int)(cloudXyz_.size() / 3),
+                                                   with_depth ? depth_ : nullptr, with_depth ? dw_ : 0, with_depth ? dh_ : 0, cloudTwc_), "plvs_tsdf_integrate_cloud");
+    }
     plvs_tsdf* handle() { return h_; }
 
 protected:
-    bool useColor, gotInfo = false, gotPose = false;
+    bool useColor, gotInfo = false, gotPose = false, gotCloudPose = false;
+    std::vector<float> cloudXyz_, cloudRgb_;
+    bool useColorCloud_ = true;       // false once a colourless point type was seen
+    float cloudTwc_[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     float Twc_[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     float* depth_ = nullptr; int dw_ = 0, dh_ = 0;
     unsigned char* color_ = nullptr; int cw_ = 0, ch_ = 0, cstep_ = 0, cn_ = 0;

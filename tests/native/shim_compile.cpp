@@ -59,5 +59,12 @@ extern "C" int shim_instantiate(int run)
     Eigen::Affine3f T; cs.SetDepthPose(T);
     std::vector<float> d(640 * 480, 1.f); cs.SetDepthImageMemorySharing(d.data(), 640, 480, 640 * 4, 0);
     cs.IntegrateLastDepthImage(false);
+    // a26: SetPointCloud + IntegrateLastPointCloud with a coloured and a colourless PCL-like cloud
+    struct PointXYZRGBA { float x, y, z; unsigned char b, g, r, a; };
+    struct PointXYZ { float x, y, z; };
+    struct CloudC { std::vector<PointXYZRGBA> points; } cc; cc.points.push_back({0.1f, 0.2f, 1.f, 1, 2, 3, 255});
+    struct CloudP { std::vector<PointXYZ> points; } cp; cp.points.push_back({0.1f, 0.2f, 1.f});
+    cs.SetPointCloud(cc, T); cs.IntegrateLastPointCloud(false);
+    cs.SetPointCloud(cp, T); cs.IntegrateLastPointCloud(false);
     return mono + a + b + c;
 }
