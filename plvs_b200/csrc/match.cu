@@ -190,19 +190,15 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
 // ---------------------------------------------------------------------------------------------
 // Phase B: claim resolution.  The reference walks the queries in order and a keypoint taken by an earlier query
 // (one whose map point has Observations() > 0) is skipped by the later ones (src/ORBmatcher.cc:113-115,1848-1850), so
-// target(q) is a function of target(0..q-1).  One thread-block cluster of 8 co-scheduled CTAs runs that recurrence as a
-// WAVEFRONT over 8 query ranges:
-//   - inside a range (<= 1024 queries, one thread each) the CTA iterates to the fixed point in shared memory:
-//     claim[idx] = lowest own query currently targeting idx; every query re-walks its candidate list (exactly the
-//     reference's running best / second best with strict `<`) skipping candidates claimed by a lower query; repeat
-//     until no target moves.  By induction on q the fixed point is the sequential result; an iteration costs three
-//     __syncthreads and no global traffic;
-//   - range c first converges against no outside claims (overlaps the wait), then waits for range c-1 to be FINAL
-//     (release/acquire flag in global memory), folds the final targets of all lower ranges into its blocked table and
-//     converges again (usually one more iteration: cross-range conflicts are rare), publishes, raises its flag;
-//   - the last range owns the wrap-up (holders, rotation histogram, copy-out): by then everything is final.
-// No cluster barrier, no global atomics, no per-round table clears: the previous design (global Jacobi rounds separated by
-// cluster barriers) spent 6.4 us per round and needed up to 9 rounds (profiles/r01_*).
+// target(q) is a function of target(0..q-1).  It is evaluated as a fixed-point (Jacobi) iteration on ONE thread-block
+// cluster of 8 co-scheduled CTAs: claim[idx] = lowest query (with Observations() > 0) currently targeting idx; in every
+// round each query re-walks its candidate list skipping the candidates claimed by a LOWER query; rounds repeat until no
+// target moves.  By induction on q the fixed point is the sequential result; the number of rounds is the longest chain of
+// displaced queries (5-9 on the bench stream).  A round is: claim table r from L2 into shared memory, the list walks
+// (lists cached in shared memory, lpq lanes per query, 4 candidates in flight per lane), lowest-query claims into table
+// r+1 with atomicMin, table r+2 cleared, ONE cluster barrier.  Measured alternatives, both slower on the bench stream:
+// a strict wavefront over the 8 query ranges (8 serial release/acquire hops) and per-range shared-memory fixed points
+// between global rounds (every round pays a confirming sweep).
 // ---------------------------------------------------------------------------------------------
 constexpr int kResolveCtas = 8;
 
@@ -212,8 +208,10 @@ __device__ __forceinline__ uint32_t cluster_cta_rank()
     asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ int ld_acquire(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
 
 // SMEM == true: the candidate lists of the range are cached in shared memory (row stride cap|1: conflict-free column
 // walks); SMEM == false reads them from L2 (any size).
@@ -221,9 +219,13 @@ template <int MODE, bool SMEM>
 __global__ void __cluster_dims__(kResolveCtas, 1, 1) __launch_bounds__(1024)
 k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int cap, const void* __restrict__ queries, int nq,
           const plvs_keypoint* __restrict__ keys, int n, const uint8_t* __restrict__ claimed_in, float nn_ratio, int check_ori,
-          int* target /*nq*/, int* flags /*[kResolveCtas] range-final flags + [8] total inner iterations, zeroed by the host*/,
-          int32_t* assign /*n, device*/, int32_t* assign_out /*n, mapped host*/, int* result /*[0]=nmatches,[1]=rounds*/, int per_cta)
+          int* claims /*3*n, L2*/, int* target /*nq*/, int* flags /*[4] rotating change flags, zeroed by the host*/,
+          int32_t* assign /*n, device*/, int32_t* assign_out /*n, mapped host*/, int* result /*[0]=nmatches,[1]=rounds*/, int per_cta,
+          int lpq /*lanes per query: power of two <= 32, per_cta * lpq <= 1024*/, long long* trace /*dev tool: 32 clock64 stamps per CTA, or null*/)
 {
+    int tr_n = 0;
+    auto stamp = [&]() { if (trace && threadIdx.x == 0 && tr_n < 32) trace[cluster_cta_rank() * 32 + tr_n++] = clock64(); };
+    stamp();
     extern __shared__ uint32_t s_dyn[];
     __shared__ int s_count, s_hist[HISTO], s_keep[HISTO];
     const int tid = threadIdx.x;
@@ -234,8 +236,9 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
     int* s_claim = s_blocked + n;                                               // n: lowest own query targeting the keypoint
     uint32_t* s_list = s_dyn + 2 * n;                                           // per_cta * stride (SMEM only)
     const int q0 = crank * per_cta;
-    const int q = q0 + tid;
-    const bool mine = tid < per_cta && q < nq;
+    const int qi = tid / lpq, lane = tid & (lpq - 1);          // lpq lanes share a query: strided list walk + shuffle merge
+    const int q = q0 + qi;
+    const bool mine = qi < per_cta && q < nq;
     int m = 0, my_target = -1;
     uint32_t my_flags = 0;
     if (mine) {
@@ -262,59 +265,77 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
         }
     }
     __syncthreads();
+    stamp();
 
-    int iterations = 0;
-    // local fixed point of the range against the current s_blocked
-    auto converge = [&]() {
-        for (;;) {
-            for (int i = tid; i < n; i += 1024) s_claim[i] = INF;
-            __syncthreads();
-            if (mine && my_target >= 0 && (my_flags & PLVS_Q_OBS_POSITIVE)) atomicMin(&s_claim[my_target], q);
-            __syncthreads();
-            bool changed_here = false;
-            if (mine) {
-                int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-                for (int k = 0; k < m; ++k) {
-                    const uint32_t e = SMEM ? s_list[tid * stride + k] : cand[(size_t)q * cap + k];
-                    const int idx = cand_idx(e);
-                    if (s_blocked[idx] || s_claim[idx] < q) continue;
-                    const int dist = cand_dist(e);
-                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = cand_level(e); bestIdx = idx; }
-                    else if (MODE == 0 && dist < bestDist2) { bestLevel2 = cand_level(e); bestDist2 = dist; }
-                }
-                int t = -1;
-                if (bestDist <= TH_HIGH) {
-                    if (MODE == 0) {
-                        if (!(bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) &&
-                            (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2)) t = bestIdx;
-                    } else t = bestIdx;
-                }
-                if (t != my_target) { my_target = t; changed_here = true; }
-            }
-            ++iterations;
-            if (!__syncthreads_or(changed_here ? 1 : 0)) break;
-        }
-    };
-    converge();                                          // against the pre-claimed keypoints only: overlaps the wait below
-    if (crank > 0) {
-        if (tid == 0) { while (ld_acquire(&flags[crank - 1]) == 0) { } }
+    // Jacobi rounds over all queries of the cluster: read claim table r (L2 -> shared), every query re-walks its list,
+    // lowest-query claims go into table r+1 (atomicMin in L2), table r+2 is cleared; ONE cluster barrier per round.
+    const int gtid = crank * 1024 + tid, gthreads = kResolveCtas * 1024;
+    for (int i = gtid; i < 3 * n; i += gthreads) claims[i] = INF;
+    cluster_sync_all();
+    stamp();
+    int rounds = 0;
+    for (;;) {
+        const int* cur = claims + (size_t)(rounds % 3) * n;
+        int* nxt = claims + (size_t)((rounds + 1) % 3) * n;
+        int* clr = claims + (size_t)((rounds + 2) % 3) * n;
+        for (int i = tid; i < n; i += 1024) s_claim[i] = rounds ? __ldcg(&cur[i]) : INF;
         __syncthreads();
-        // fold the FINAL targets of every lower range into the blocked table
-        bool any = false;
-        for (int qq = tid; qq < q0; qq += 1024) {
-            const int t = __ldcg(&target[qq]);
-            if (t < 0) continue;
-            const uint32_t f = MODE == 0 ? reinterpret_cast<const plvs_mp_query*>(queries)[qq].flags : reinterpret_cast<const plvs_last_query*>(queries)[qq].flags;
-            if (f & PLVS_Q_OBS_POSITIVE) { s_blocked[t] = 1; any = true; }
+        // The reference's running best / second best (strict `<` in list order, the old best demoted to second) are the two
+        // smallest (distance, position) keys of the unblocked candidates: each lane keeps the two smallest of its strided
+        // share (4 candidates in flight per step), shuffles merge the lanes.
+        uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+        if (mine) {
+            for (int k = lane; k < m; k += 4 * lpq) {
+                uint32_t key[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int kk = k + j * lpq;
+                    const bool valid = kk < m;
+                    const uint32_t e = valid ? (SMEM ? s_list[qi * stride + kk] : cand[(size_t)q * cap + kk]) : 0u;
+                    const int idx = valid ? cand_idx(e) : 0;
+                    const bool blocked = s_blocked[idx] || s_claim[idx] < q;
+                    key[j] = (!valid || blocked) ? 0xffffffffu : (((uint32_t)cand_dist(e) << 16) | (uint32_t)kk);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { if (key[j] < k1) { k2 = k1; k1 = key[j]; } else if (key[j] < k2) k2 = key[j]; }
+            }
         }
-        if (__syncthreads_or(any ? 1 : 0)) converge();
+        for (int o = 1; o < lpq; o <<= 1) {
+            const uint32_t a1 = __shfl_xor_sync(0xffffffffu, k1, o), a2 = __shfl_xor_sync(0xffffffffu, k2, o);
+            const uint32_t lo = min(k1, a1), hi = max(k1, a1);
+            k2 = min(hi, min(k2, a2));
+            k1 = lo;
+        }
+        bool changed_here = false;
+        if (mine && lane == 0) {
+            int t = -1;
+            const int bestDist = k1 == 0xffffffffu ? 256 : (int)(k1 >> 16);
+            if (bestDist <= TH_HIGH) {
+                const uint32_t e1 = SMEM ? s_list[qi * stride + (k1 & 0xffffu)] : cand[(size_t)q * cap + (k1 & 0xffffu)];
+                if (MODE == 0) {
+                    int bestDist2 = 256, bestLevel2 = -1;
+                    if (k2 != 0xffffffffu) {
+                        const uint32_t e2 = SMEM ? s_list[qi * stride + (k2 & 0xffffu)] : cand[(size_t)q * cap + (k2 & 0xffffu)];
+                        bestDist2 = (int)(k2 >> 16); bestLevel2 = cand_level(e2);
+                    }
+                    const int bestLevel = cand_level(e1);
+                    if (!(bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) &&
+                        (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2)) t = cand_idx(e1);
+                } else t = cand_idx(e1);
+            }
+            if (t != my_target || rounds == 0) { my_target = t; target[q] = t; changed_here = true; }
+            if (t >= 0 && (my_flags & PLVS_Q_OBS_POSITIVE)) atomicMin(&nxt[t], q);
+        }
+        for (int i = gtid; i < n; i += gthreads) clr[i] = INF;
+        if (gtid == 0) flags[(rounds + 2) & 3] = 0;
+        if (__syncthreads_or(changed_here ? 1 : 0) && tid == 0) atomicOr(&flags[rounds & 3], 1);
+        cluster_sync_all();
+        stamp();
+        const int changed = __ldcg(&flags[rounds & 3]);
+        ++rounds;
+        if (!changed) break;
     }
-    if (mine) target[q] = my_target;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) { atomicAdd(&flags[kResolveCtas], iterations); st_release(&flags[crank], 1); }
-    if (crank != kResolveCtas - 1) return;
-    const int rounds = atomicAdd(&flags[kResolveCtas], 0);      // total inner iterations over the ranges (statistic)
+    if (crank != 0) return;        // the wrap-up is one cheap pass: CTA 0 finishes alone (no cluster barrier after this point)
     // final holders: the last (highest) query that wrote each keypoint
     for (int i = tid; i < n; i += 1024) assign[i] = -1;
     if (tid == 0) s_count = 0;
@@ -367,6 +388,7 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
     __syncthreads();
     for (int i = tid; i < n; i += 1024) assign_out[i] = assign[i];
     if (tid == 0) { result[0] = s_count; result[1] = rounds; }
+    stamp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -646,6 +668,7 @@ struct plvs_match {
     DevBuf<uint8_t> d_desc[2], d_has[2], d_claimed;
     DevBuf<float> d_uright[2], d_f12;
     DevBuf<uint8_t> d_query;
+    DevBuf<long long> d_trace;        // PLVS_RESOLVE_TRACE=1: phase stamps of k_resolve (development)
     DevBuf<int> d_cell_start, d_sorted, d_kp_cell, d_cand_n, d_claim_a, d_claim_b, d_target, d_state;
     DevBuf<uint32_t> d_cand;
     DevBuf<uint32_t> d_fv_ids[2];
@@ -737,8 +760,12 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         PLVS_CUDA(cudaMemcpyAsync(h->p_cand_n.h, h->d_cand_n.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
         h->timer.begin(PLVS_MATCH_K_RESOLVE, st);
         PLVS_CUDA(cudaMemsetAsync(h->d_state.p, 0, 16 * sizeof(int), st));
+        static const bool trace_on = std::getenv("PLVS_RESOLVE_TRACE") != nullptr;
+        if (trace_on) { if ((rc = h->d_trace.alloc(kResolveCtas * 32))) return rc; PLVS_CUDA(cudaMemsetAsync(h->d_trace.p, 0, kResolveCtas * 32 * 8, st)); }
         {
             const int per_cta = div_up(nq, kResolveCtas);
+            int lpq = 1;
+            while (lpq < 32 && per_cta * lpq * 2 <= 1024) lpq *= 2;
             const size_t smem = ((size_t)2 * n + (size_t)per_cta * (h->cap | 1)) * sizeof(uint32_t);
             const size_t smem_small = (size_t)2 * n * sizeof(uint32_t);
             if (per_cta <= 1024 && smem <= 200 * 1024) {
@@ -748,10 +775,10 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
                     attr_set[MODE] = true;
                 }
                 k_resolve<MODE, true><<<kResolveCtas, 1024, smem, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
-                                                                        h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta);
+                                                                        h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta, lpq, h->d_trace.p);
             } else if (per_cta <= 1024) {
                 k_resolve<MODE, false><<<kResolveCtas, 1024, smem_small, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
-                                                                      h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta);
+                                                                      h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta, lpq, h->d_trace.p);
             } else { set_error("more than %d queries per search are not supported", kResolveCtas * 1024); return PLVS_EINVAL; }
         }
         h->timer.end(st);
@@ -759,6 +786,15 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         PLVS_CUDA(cudaGetLastError());
         PLVS_CUDA(cudaStreamSynchronize(st));
         h->timer.collect();
+        if (trace_on) {
+            long long tr[kResolveCtas * 32];
+            cudaMemcpy(tr, h->d_trace.p, sizeof(tr), cudaMemcpyDeviceToHost);
+            for (int c = 0; c < kResolveCtas; c += kResolveCtas - 1) {
+                std::fprintf(stderr, "resolve<%d> nq=%d cta%d cycles:", MODE, nq, c);
+                for (int i = 1; i < 32 && tr[c * 32 + i]; ++i) std::fprintf(stderr, " %lld", tr[c * 32 + i] - tr[c * 32 + i - 1]);
+                std::fprintf(stderr, "\n");
+            }
+        }
         int mx = 0;
         for (int i = 0; i < nq; ++i) mx = std::max(mx, h->p_cand_n.h[i]);
         if (mx <= h->cap) break;

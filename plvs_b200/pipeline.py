@@ -76,6 +76,7 @@ class HotPath:
         self.tsdf.SetDepthCameraInfo(K["fx"], K["fy"], K["cx"], K["cy"], data.w, data.h)
         self.use_color = use_color
         self.prepared = None
+        self._pins = []
         self.dev = None       # device-resident copies of the inputs (the `value` arm)
 
     # ---- untimed: caller-side query construction -------------------------------------------------------
@@ -100,6 +101,21 @@ class HotPath:
             F12, ep = scenario.fundamental(K, d.poses[f], d.poses[f - 1])
             prep.append(dict(ql=ql, qm=qm, fv1=fv_cur, fv2=fv_last, F12=F12, ep=ep,
                              has1=np.zeros(cur.n, np.uint8), has2=np.zeros(last.n, np.uint8)))
+        # the caller keeps its query records in pinned memory (one slab per kind), so the per-call H2D copy is a plain DMA
+        for key in ("ql", "qm"):
+            items = [p[key] for p in prep if p is not None]
+            if not items:
+                continue
+            slab = PinnedArray((sum(len(a) for a in items),), items[0].dtype)
+            self._pins.append(slab)
+            o = 0
+            for p in prep:
+                if p is None:
+                    continue
+                a = p[key]
+                slab.array[o:o + len(a)] = a
+                p[key] = slab.array[o:o + len(a)]
+                o += len(a)
         self.frames, self.prepared = frames, prep
         self.tsdf.Reset()
 
