@@ -265,8 +265,17 @@ def run_b200_arm(a):
     roof = None
     if integ_n:
         achieved = alg_bytes / (integ_ms / integ_n / 1000.0) / 1e9
+        # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (not measurable live)
+        traffic, traffic_src = None, None
+        tp = ROOT / "profiles" / "r01_k_integrate_traffic.json"
+        if tp.exists():
+            try:
+                tj = json.loads(tp.read_text())
+                traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj.get("source")
+            except Exception:
+                pass
         roof = {"kernel": "k_integrate (TSDF voxel update)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": integ_ms / integ_n,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": integ_ms / integ_n,
                 "updated_blocks_per_launch": upd_per_launch}
     gpu_time_ms = sum(v[0] for v in ktimes.values())
 

@@ -283,7 +283,8 @@ int plvs_tsdf_set_camera(plvs_tsdf* h, double fx, double fy, double cx, double c
 /* SetDepthPose + SetDepthImage[MemorySharing] (+SetColorImage) + IntegrateLastDepthImage(false).
  * With host buffers the call returns as soon as the (borrowed) buffers have been read -- the copy of scan k+1 overlaps
  * the kernels of scan k; statistics, read-outs and a pool-exhaustion error are delivered by the next call that needs the
- * finished map (plvs_tsdf_last_stats / download_blocks / export / reset).  Device-resident inputs are finished before return.
+ * finished map (plvs_tsdf_last_stats / download_blocks / export / reset).  Device-resident inputs (on_device=1) are not copied:
+ * the call only enqueues, and the images must stay valid and unmodified until one of those waiting calls returns.
  * depth: float32 metres, w*h, row stride = w elements (DepthImage.h:54-74).  bgr: w*h*nch bytes
  * with `bgr_step` bytes per row (NULL unless mode==PLVS_TSDF_SCAN_COLOR).  Twc: 3x4 row-major
  * (rotation | translation), camera-to-world (src/PointCloudMapChisel.cc:147-154). */
