@@ -172,6 +172,7 @@ def peaks():
 
 def run_b200_arm(a):
     import torch
+    sys.setswitchinterval(1e-4)          # 4 stage threads: hand the GIL over quickly when a library call returns
     import torch.distributed as dist
     from plvs_b200 import _lib
     from plvs_b200.pipeline import StreamData, HotPath
