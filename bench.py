@@ -57,8 +57,12 @@ def workload_config(a, extra=None):
 # ------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (restatement of the reference's CPU path) timed on this box's host cores
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(a, frames, threads, generous):
-    """times the oracle on frames [1, frames] of stream 0; returns (frames/s, per-stage seconds per frame)"""
+def cpu_reference_run(a, frames, threads, generous, tsdf_ref_frames=0):
+    """times the CPU path on frames [1, frames] of stream 0; returns (frames/s, per-stage seconds per frame).
+    Extract = cv2 primitives + C++ restatement, match = C++ restatement.  TSDF = the restatement (OpenMP over chunks when
+    `generous`), and additionally -- for the first `tsdf_ref_frames` timed frames, when oracle/_ref/libchisel_ref.so
+    exists -- the REFERENCE's own open_chisel code (single-threaded, as Chisel.h:91 is), whose mean seconds/frame then
+    replaces the restatement's in the total ("tsdf_s"; the restatement's time stays in "tsdf_port_s")."""
     import cv2
     from oracle import orb as O, match as OM, tsdf as OT
     from plvs_b200 import synth, scenario, tsdf as T
@@ -69,7 +73,12 @@ def cpu_reference_run(a, frames, threads, generous):
     p = T.default_params(voxel_resolution=a.voxel, use_carving=1, near_plane=0.1, far_plane=a.far, max_blocks=1 << 20, use_color=1)
     omap = OT.Map(p, threads=threads if generous else 1)
     omap.set_camera(K["fx"], K["fy"], K["cx"], K["cy"], a.width, a.height)
-    t_ext = t_match = t_tsdf = 0.0
+    rmap = None
+    if tsdf_ref_frames > 0 and OT.ref_available():
+        rmap = OT.RefMap(p)
+        rmap.set_camera(K["fx"], K["fy"], K["cx"], K["cy"], a.width, a.height)
+    t_ext = t_match = t_tsdf = t_ref = 0.0
+    n_ref = 0
     prev = None
     for f in range(frames + 1):
         img = synth.gray_frame(f, a.width, a.height); depth = synth.depth_frame(f, a.width, a.height); bgr = synth.bgr_frame(f, a.width, a.height)
@@ -90,31 +99,71 @@ def cpu_reference_run(a, frames, threads, generous):
             omap.integrate(depth, synth.pose(f), bgr)
             t4 = time.perf_counter()
             t_ext += t1 - t0; t_match += t3 - t2; t_tsdf += t4 - t3
+            if rmap is not None and n_ref < tsdf_ref_frames:
+                with _quiet_stdout():
+                    rmap.integrate(depth, synth.pose(f), bgr)
+                t_ref += time.perf_counter() - t4; n_ref += 1
         else:
             omap.integrate(depth, synth.pose(f), bgr)        # map initialisation, untimed
+            if rmap is not None:
+                with _quiet_stdout():
+                    rmap.integrate(depth, synth.pose(f), bgr)
         prev = cur
-    tot = t_ext + t_match + t_tsdf
-    return frames / tot, dict(extract_s=t_ext / frames, match_s=t_match / frames, tsdf_s=t_tsdf / frames)
+    stages = dict(extract_s=t_ext / frames, match_s=t_match / frames, tsdf_s=t_tsdf / frames)
+    if n_ref:
+        stages["tsdf_port_s"] = stages["tsdf_s"]
+        stages["tsdf_s"] = t_ref / n_ref
+        stages["tsdf_ref_frames"] = n_ref
+    tot = stages["extract_s"] + stages["match_s"] + stages["tsdf_s"]
+    return 1.0 / tot, stages
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def _quiet_stdout():
+    """the reference's open_chisel prints per scan; bench.py must print exactly one JSON line"""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    null = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(null, 1)
+    try:
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1); os.close(null); os.close(saved)
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import tsdf as OT
     threads = os.cpu_count() or 1
-    # warmup + steps, each step = one frame of the same workload (bounded sample: the CPU TSDF alone takes seconds per frame)
+    have_ref = OT.ref_available()
+    # each step = one frame of the same workload (a bounded sample: the CPU TSDF alone takes seconds per frame).  The
+    # warm-up frames run the multi-threaded restatement only; the timed frames run extract/match through the restatement with
+    # all host threads and the TSDF through the reference's own open_chisel code (oracle/_ref) for the first REF_FRAMES frames.
+    REF_FRAMES = 2
     w = max(0, min(a.warmup, 1))
     if w:
         cpu_reference_run(a, w, threads, True)
     t0 = time.perf_counter()
-    fps, stages = cpu_reference_run(a, a.steps, threads, True)
+    fps, stages = cpu_reference_run(a, a.steps, threads, True, tsdf_ref_frames=REF_FRAMES if have_ref else 0)
     wall = time.perf_counter() - t0
+    port_fps = 1.0 / (stages["extract_s"] + stages["match_s"] + stages.get("tsdf_port_s", stages["tsdf_s"]))
+    kind = "reference" if have_ref else "port"
+    note = ("extract = cv2 primitives + C++ restatement (cv2.setNumThreads(n)), match = C++ restatement, TSDF = the reference's own open_chisel "
+            "sources compiled into oracle/_ref (single-threaded: Chisel.h:91 has its parallel_for commented out); 'port_value' = same run with "
+            "the restated TSDF spread over all host threads with OpenMP; rank 0 only") if have_ref else \
+           "CPU oracle (cv2 primitives + C++ restatement of the reference), all host threads: cv2.setNumThreads(n), TSDF chunks over OpenMP; rank 0 only"
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32+f32",
-            "data": "synthetic", "config": workload_config(a, {"frames_per_step": 1, "note": "CPU oracle (cv2 primitives + C++ restatement of the reference), "
-                                                               "all host threads: cv2.setNumThreads(n), TSDF chunks over OpenMP; rank 0 only"}),
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": f"{a.steps} frames of the same stream, stage seconds/frame {json.dumps({k: round(v, 4) for k, v in stages.items()})}"},
+            "data": "synthetic", "config": workload_config(a, {"frames_per_step": 1, "note": note}),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "port_value": port_fps,
+                             "sample": f"{a.steps} frames of the same stream (TSDF through oracle/_ref on the first {stages.get('tsdf_ref_frames', 0)}), "
+                                       f"stage seconds/frame {json.dumps({k: round(v, 4) for k, v in stages.items()})}"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "wall_s": wall}
     print(json.dumps(line), flush=True)
@@ -309,11 +358,17 @@ def run_b200_arm(a):
                          "match_rounds_last_call": hp.match_rounds()},
             "stage_busy_ms_per_step": {k[5:-2]: round(v / K * 1e3, 3) for k, v in agg.items() if k.startswith("busy_")}, "wall_s": [wall, wall2]}
     if not a.no_cpu_baseline:
-        fps, stages = cpu_reference_run(a, a.cpu_frames, 1, False)
-        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
+        from oracle import tsdf as OT
+        have_ref = OT.ref_available()
+        fps, stages = cpu_reference_run(a, a.cpu_frames, 1, False, tsdf_ref_frames=1 if have_ref else 0)
+        port_fps = 1.0 / (stages["extract_s"] + stages["match_s"] + stages.get("tsdf_port_s", stages["tsdf_s"]))
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference" if have_ref else "port", "port_value": port_fps,
                                 "sample": f"{a.cpu_frames} frames of stream 0 (after a 1-frame map seed), faithful mode: 1 thread "
-                                          f"(cv2.setNumThreads(1), single-threaded chunk loop like Chisel.h:91); seconds/frame "
-                                          f"{json.dumps({k: round(v, 4) for k, v in stages.items()})}; host has {os.cpu_count()} cpus"}
+                                          f"(cv2.setNumThreads(1), single-threaded chunk loop like Chisel.h:91); extract = real OpenCV primitives + "
+                                          f"restated octree/descriptor code, match = restatement, TSDF = "
+                                          + ("the reference's own open_chisel sources (oracle/_ref, 1 frame; 'port_value'/'tsdf_port_s' = the restated TSDF)"
+                                             if have_ref else "restatement") +
+                                          f"; seconds/frame {json.dumps({k: round(v, 4) for k, v in stages.items()})}; host has {os.cpu_count()} cpus"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

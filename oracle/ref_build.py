@@ -1,0 +1,47 @@
+"""TEST INFRASTRUCTURE ONLY -- compile the reference's own open_chisel (TSDF) sources into oracle/_ref/libchisel_ref.so.
+
+The sources are compiled where they lie under /root/reference/Thirdparty/open_chisel (nothing is copied into this
+repository); outputs go only to oracle/_ref/ (git-ignored, but it travels to the GPU box with gpurun).  open_chisel's
+one external dependency is Eigen, which this image does not have: the sources are compiled against the stand-in
+headers in oracle/eigen_standin/ (fixed-size vector/matrix arithmetic restated with Eigen 3.4's evaluation order; see
+the header of oracle/eigen_standin/Eigen/Core).  Flags mirror the reference's Ubuntu-24.04 configuration
+(config.sh:19-21: no -march=native, hence no FMA contraction).  The reference's own build system (cmake) is not run.
+
+On the GPU box /root/reference does not exist: build() then just returns the prebuilt library (or None).
+"""
+import pathlib
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = pathlib.Path(__file__).resolve().parent
+REF = pathlib.Path("/root/reference/Thirdparty/open_chisel")
+OUTDIR = HERE / "_ref"
+OUT = OUTDIR / "libchisel_ref.so"
+CXXFLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w",
+            "-I", str(HERE / "eigen_standin"), "-I", str(REF / "include")]
+
+
+def build(force=False):
+    if not REF.exists():
+        return str(OUT) if OUT.exists() else None
+    srcs = sorted(REF.glob("src/*.cpp")) + sorted(REF.glob("src/*/*.cpp")) + [HERE / "ref_chisel_harness.cpp"]
+    deps = srcs + list((HERE / "eigen_standin" / "Eigen").iterdir())
+    if OUT.exists() and not force and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return str(OUT)
+    objdir = OUTDIR / "obj"
+    objdir.mkdir(parents=True, exist_ok=True)
+
+    def cc(src):
+        obj = objdir / (src.stem + ".o")
+        subprocess.check_call(["g++"] + CXXFLAGS + ["-c", str(src), "-o", str(obj)])
+        return str(obj)
+
+    with ThreadPoolExecutor(8) as ex:
+        objs = list(ex.map(cc, srcs))
+    subprocess.check_call(["g++", "-shared", "-o", str(OUT)] + objs + ["-lm", "-pthread"])
+    return str(OUT)
+
+
+if __name__ == "__main__":
+    print(build(force="-f" in sys.argv))

@@ -1,0 +1,172 @@
+// TEST INFRASTRUCTURE ONLY -- C driver around the REFERENCE's own open_chisel sources.
+//
+// oracle/ref_build.py compiles /root/reference/Thirdparty/open_chisel/src/**/*.cpp where they lie (nothing is copied)
+// together with this file into oracle/_ref/libchisel_ref.so.  Eigen is absent from the image, so the sources are
+// compiled against oracle/eigen_standin/ (see its header for exactly what is restated there).  This file only does
+// what chisel_server::ChiselServer does around the library (ChiselServer.cpp is PCL-bound and cannot be compiled):
+//   ctor                         Thirdparty/chisel_server/src/ChiselServer.cpp:100-110   (Chisel(16^3, res, useColor) +
+//                                SetupProjectionIntegrator :623-631 incl. the static_cast<uint16_t>(weight) of :108)
+//   SetDepthCameraInfo           ChiselServer.cpp:444-450 + Conversions.h:494-506 (near/far planes from the params)
+//   IntegrateLastDepthImage      ChiselServer.cpp:632-662 (colour -> IntegrateDepthScanColorWithOneCameraModelBGR,
+//                                else IntegrateDepthScan)
+//   IntegrateLastPointCloud      ChiselServer.cpp:664-705 (IntegratePointCloudWidthDepth)
+// and exposes the same C entry points as oracle/tsdf_oracle.cpp with the prefix ref_ so one Python class drives both.
+#include <open_chisel/Chisel.h>
+#include <open_chisel/ProjectionIntegrator.h>
+#include <open_chisel/truncation/QuadraticTruncator.h>
+#include <open_chisel/weighting/ConstantWeighter.h>
+#include <open_chisel/camera/DepthImage.h>
+#include <open_chisel/camera/ColorImage.h>
+#include <open_chisel/camera/PinholeCamera.h>
+#include <open_chisel/pointcloud/PointCloud.h>
+
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <tuple>
+
+namespace {
+
+struct Params {
+    float voxel_resolution, trunc_quad, trunc_linear, trunc_const, trunc_scale, weight;
+    int32_t use_carving; float carving_dist; int32_t use_color; float near_plane, far_plane; int32_t max_blocks;
+};
+
+struct Ref {
+    Params p;
+    std::unique_ptr<chisel::Chisel> map;
+    chisel::ProjectionIntegrator integrator;
+    chisel::PinholeCamera depthCam, colorCam;
+    bool got_camera = false;
+    int n_range = 0;
+};
+
+void make_map(Ref* r)
+{
+    const Params& p = r->p;
+    r->map.reset(new chisel::Chisel(Eigen::Vector3i(16, 16, 16), p.voxel_resolution, p.use_color != 0));
+    chisel::Vec4 truncation(p.trunc_quad, p.trunc_linear, p.trunc_const, p.trunc_scale);
+    const uint16_t weight = static_cast<uint16_t>(p.weight);
+    r->integrator.SetCentroids(r->map->GetChunkManager().GetCentroids());
+    r->integrator.SetTruncator(chisel::TruncatorPtr(new chisel::QuadraticTruncator(truncation(0), truncation(1), truncation(2), truncation(3))));
+    r->integrator.SetWeighter(chisel::WeighterPtr(new chisel::ConstantWeighter(weight)));
+    r->integrator.SetCarvingDist(p.carving_dist);
+    r->integrator.SetCarvingEnabled(p.use_carving != 0);
+}
+
+chisel::PinholeCamera to_camera(double fx, double fy, double cx, double cy, int w, int h)
+{
+    chisel::PinholeCamera cam;
+    chisel::Intrinsics in;
+    in.SetFx(fx); in.SetFy(fy); in.SetCx(cx); in.SetCy(cy);
+    cam.SetIntrinsics(in);
+    cam.SetWidth(w); cam.SetHeight(h);
+    return cam;
+}
+
+chisel::Transform to_transform(const float* Twc)
+{
+    chisel::Transform T = chisel::Transform::Identity();
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) T(i, j) = Twc[4 * i + j]; T(i, 3) = Twc[4 * i + 3]; }
+    return T;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* ref_tsdf_create(const Params* p, int /*threads*/)
+{
+    Ref* r = new Ref();
+    r->p = *p;
+    make_map(r);
+    return r;
+}
+void ref_tsdf_destroy(void* h) { delete (Ref*)h; }
+void ref_tsdf_reset(void* h) { ((Ref*)h)->map->Reset(); }
+
+void ref_tsdf_set_camera(void* h, double fx, double fy, double cx, double cy, int w, int ht)
+{
+    Ref* r = (Ref*)h;
+    r->depthCam = to_camera(fx, fy, cx, cy, w, ht);
+    r->depthCam.SetNearPlane(r->p.near_plane); r->depthCam.SetFarPlane(r->p.far_plane);
+    r->colorCam = r->depthCam;
+    r->got_camera = true;
+}
+
+int ref_tsdf_integrate(void* h, const float* depth, int w, int ht, const uint8_t* bgr, int nch, const float* Twc, int mode)
+{
+    Ref* r = (Ref*)h;
+    if (!r->got_camera || !depth) return -5;
+    std::shared_ptr<chisel::DepthImage<float>> d(new chisel::DepthImage<float>(w, ht));
+    std::memcpy(d->GetMutableData(), depth, sizeof(float) * (size_t)w * ht);
+    const chisel::Transform T = to_transform(Twc);
+    {   // statistic only: size of the reference's chunk list for this scan (same calls as the integrate functions make)
+        chisel::Frustum fr; chisel::PinholeCamera c = r->depthCam;
+        if (mode == 0) { float mn, mx, mean; d->GetStats(mn, mx, mean); c.SetNearPlane(mn); c.SetFarPlane(mx); }
+        c.SetupFrustum(T, &fr);
+        chisel::ChunkIDList ids; r->map->GetMutableChunkManager().GetChunkIDsIntersecting(fr, &ids);
+        r->n_range = (int)ids.size();
+    }
+    if (mode == 1) {
+        std::shared_ptr<chisel::ColorImage<uint8_t>> c(new chisel::ColorImage<uint8_t>(w, ht, nch));
+        std::memcpy(c->GetMutableData(), bgr, (size_t)w * ht * nch);
+        r->map->IntegrateDepthScanColorWithOneCameraModelBGR<float, uint8_t>(r->integrator, d, T, r->depthCam, c, T, r->colorCam);
+    } else {
+        r->map->IntegrateDepthScan<float>(r->integrator, d, T, r->depthCam);
+    }
+    return 0;
+}
+
+int ref_tsdf_integrate_cloud(void* h, const float* xyz, const float* rgb, int n, const float* depth, int w, int ht, const float* Twc)
+{
+    Ref* r = (Ref*)h;
+    chisel::PointCloud cloud;
+    for (int i = 0; i < n; ++i) {
+        cloud.AddPoint(chisel::Vec3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+        cloud.AddColor(rgb ? chisel::Vec3(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]) : chisel::Vec3(0.f, 0.f, 0.f));
+        cloud.GetMutableKfids().push_back(0u);
+    }
+    std::shared_ptr<chisel::DepthImage<float>> d;
+    if (depth) { d.reset(new chisel::DepthImage<float>(w, ht)); std::memcpy(d->GetMutableData(), depth, sizeof(float) * (size_t)w * ht); }
+    const chisel::Transform T = to_transform(Twc);
+    const bool carve = r->integrator.IsCarvingEnabled();
+    if (!(depth && r->got_camera)) r->integrator.SetCarvingEnabled(false);      // the oracle/product skip carving without a depth image
+    r->map->IntegratePointCloudWidthDepth<float>(r->integrator, cloud, T, d, r->depthCam, r->p.far_plane);
+    r->integrator.SetCarvingEnabled(carve);
+    return 0;
+}
+
+void ref_tsdf_stats(void* h, int32_t* out)
+{
+    Ref* r = (Ref*)h;
+    out[0] = (int)r->map->GetChunkManager().GetChunks().size(); out[1] = r->n_range; out[2] = out[3] = out[4] = -1;
+}
+
+int ref_tsdf_download(void* h, int32_t* keys, float* sdf, float* weight, uint8_t* rgba, int cap)
+{
+    Ref* r = (Ref*)h;
+    std::map<std::tuple<int, int, int>, chisel::ChunkPtr> ord;
+    for (auto& kv : r->map->GetChunkManager().GetChunks()) ord[{kv.first(0), kv.first(1), kv.first(2)}] = kv.second;
+    int n = 0;
+    for (auto& kv : ord) {
+        if (n >= cap) break;
+        const chisel::Chunk& c = *kv.second;
+        if (keys) { keys[3 * n] = std::get<0>(kv.first); keys[3 * n + 1] = std::get<1>(kv.first); keys[3 * n + 2] = std::get<2>(kv.first); }
+        for (int i = 0; i < 4096; ++i) {
+            const chisel::DistVoxel& v = c.GetDistVoxel(i);
+            if (sdf) sdf[(size_t)n * 4096 + i] = v.GetSDF();
+            if (weight) weight[(size_t)n * 4096 + i] = v.GetWeight();
+            if (rgba) {
+                uint8_t* o = rgba + ((size_t)n * 4096 + i) * 4;
+                if (c.HasColors()) { const chisel::ColorVoxel& cv = c.GetColorVoxel(i); o[0] = cv.GetRed(); o[1] = cv.GetGreen(); o[2] = cv.GetBlue(); o[3] = cv.GetWeight(); }
+                else o[0] = o[1] = o[2] = o[3] = 0;
+            }
+        }
+        ++n;
+    }
+    return (int)ord.size();
+}
+
+}  // extern "C"

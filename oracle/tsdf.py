@@ -7,9 +7,22 @@ from .orb import lib
 from plvs_b200 import _lib as _abi
 
 
+class _Prefixed:
+    """view of a ctypes library that prepends a prefix to every symbol (orc_ = restatement, ref_ = compiled reference)"""
+    def __init__(self, l, prefix):
+        object.__setattr__(self, "_l", l); object.__setattr__(self, "_p", prefix)
+
+    def __getattr__(self, name):
+        assert name.startswith("orc_")
+        return getattr(self._l, self._p + name[4:])
+
+
 class Map:
+    def _library(self):
+        return lib()
+
     def __init__(self, params, threads=1):
-        self._l = lib()
+        self._l = self._library()
         self._l.orc_tsdf_create.restype = C.c_void_p
         self._l.orc_tsdf_create.argtypes = [C.c_void_p, C.c_int]
         self._l.orc_tsdf_destroy.argtypes = [C.c_void_p]
@@ -66,3 +79,24 @@ class Map:
             self._l.orc_tsdf_download(self._h, keys.ctypes.data_as(C.c_void_p), sdf.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p),
                                       rgba.ctypes.data_as(C.c_void_p), n)
         return keys, sdf, w, rgba
+
+
+def ref_available():
+    """oracle/_ref/libchisel_ref.so = the reference's own open_chisel sources (oracle/ref_build.py)."""
+    from . import ref_build
+    return ref_build.build() is not None
+
+
+class RefMap(Map):
+    """Same interface, backed by the REFERENCE's open_chisel compiled from /root/reference (against the Eigen stand-in).
+    stats() only fills n_blocks and n_range (the reference does not count updates)."""
+    _lib = None
+
+    def _library(self):
+        if RefMap._lib is None:
+            from . import ref_build
+            so = ref_build.build()
+            if so is None:
+                raise RuntimeError("oracle/_ref/libchisel_ref.so missing and /root/reference not present")
+            RefMap._lib = C.CDLL(so)
+        return _Prefixed(RefMap._lib, "ref_")
