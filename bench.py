@@ -178,10 +178,15 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        """one nvidia-smi process for the whole bench, started BEFORE any timed region: its start-up (NVML initialisation,
+        a few hundred ms during which driver calls of this process can stall) must not fall into a timed window"""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 5.0:       # wait for the first sample = start-up is over
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
@@ -189,13 +194,20 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
+    def mark(self):
+        return len(self.lines)
+
+    def window(self, i0):
+        """clock statistics of the samples taken since mark() returned i0 (waits for one more sample: a timed region
+        shorter than the sampling period still gets the reading taken right as it ends)"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        n0 = len(self.lines)
+        t0 = time.perf_counter()
+        while len(self.lines) == n0 and time.perf_counter() - t0 < 0.3:
+            time.sleep(0.01)
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[i0:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -207,6 +219,11 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            self.proc = None
 
 
 def peaks():
@@ -238,6 +255,7 @@ def run_b200_arm(a):
     hp = HotPath(data, a.nfeatures, a.voxel, a.far, max_blocks=49152, device=local, batch=B)
     hp.prepare()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    sampler = ClockSampler(local); sampler.start()
 
     def barrier():
         if world > 1:
@@ -255,8 +273,8 @@ def run_b200_arm(a):
                 lib.plvs_orb_kernel_times(ex._h, None, None, 1)
         for m in (hp.m_track, hp.m_map, hp.m_tri):
             lib.plvs_match_kernel_times(m._h, None, None, 1)
-        sampler = ClockSampler(local); sampler.start()
         barrier()
+        mark = sampler.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
@@ -265,7 +283,7 @@ def run_b200_arm(a):
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
-        clocks = sampler.stop()
+        clocks = sampler.window(mark)
         t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -335,6 +353,7 @@ def run_b200_arm(a):
     h2d = B * data.input_bytes_per_frame()
     d2h = int(B * (agg2.get("keypoints", 0) / max(frames, 1)) * 60 + B * 3 * a.nfeatures * 4)
 
+    sampler.stop()
     if world > 1:
         dist.barrier()
     if rank != 0:

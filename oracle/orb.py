@@ -283,3 +283,66 @@ def _ic_angle_cv2(img, x, y, umax):
         m01 += v * int((lo - hi).sum())
         m10 += int((uu * (lo + hi)).sum())
     return cv2.fastAtan2(float(np.float32(m01)), float(np.float32(m10)))
+
+
+# ---- the REFERENCE's own ORBextractor.cc, compiled by oracle/ref_build.py (oracle/_ref/liborb_ref.so) -----------------
+
+def ref_available():
+    from . import ref_build
+    return ref_build.build_orb() is not None
+
+
+class RefExtractor:
+    """PLVS2::ORBextractor from /root/reference/src/ORBextractor.cc (OpenCV stand-in: oracle/cv_standin)."""
+    _lib = None
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        if RefExtractor._lib is None:
+            from . import ref_build
+            so = ref_build.build_orb()
+            if so is None:
+                raise RuntimeError("oracle/_ref/liborb_ref.so missing and /root/reference not present")
+            lib()                                                  # liboracle.so first: liborb_ref.so resolves the primitives there
+            RefExtractor._lib = C.CDLL(so, mode=C.RTLD_GLOBAL)
+            RefExtractor._lib.ref_orb_create.restype = C.c_void_p
+            RefExtractor._lib.ref_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+            RefExtractor._lib.ref_orb_destroy.argtypes = [C.c_void_p]
+            RefExtractor._lib.ref_orb_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            RefExtractor._lib.ref_orb_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+            RefExtractor._lib.ref_orb_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self._h = RefExtractor._lib.ref_orb_create(nfeatures, C.c_float(scale_factor), nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            RefExtractor._lib.ref_orb_destroy(self._h)
+            self._h = None
+
+    def tables(self):
+        out = [np.zeros(self.nlevels, np.float32) for _ in range(4)]
+        RefExtractor._lib.ref_orb_tables(self._h, *[_p(a) for a in out])
+        return dict(scale=out[0], inv_scale=out[1], sigma2=out[2], inv_sigma2=out[3])
+
+    def __call__(self, gray, lapping=(0, 0)):
+        """returns (keypoints[KP_DTYPE], descriptors[n,32], mono_index) like extract_port"""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        cap = max(4 * self.nfeatures, 1024)
+        kps = np.empty((cap, 7), np.float32); desc = np.empty((cap, 32), np.uint8)
+        mono = C.c_int()
+        n = RefExtractor._lib.ref_orb_extract(self._h, _p(gray), gray.shape[1], gray.shape[0], gray.strides[0], lapping[0], lapping[1],
+                                              _p(kps), _p(desc), cap, C.byref(mono))
+        assert n >= 0
+        out = np.zeros(n, KP_DTYPE)
+        for i, f in enumerate(("x", "y", "size", "angle", "response")):
+            out[f] = kps[:n, i]
+        out["octave"] = kps[:n, 5].astype(np.int32)
+        out["class_id"] = kps[:n, 6].astype(np.int32)
+        return out, desc[:n].copy(), mono.value
+
+    def level(self, l, filtered=False):
+        w, h = C.c_int(), C.c_int()
+        RefExtractor._lib.ref_orb_level(self._h, l, int(filtered), None, 0, C.byref(w), C.byref(h))
+        out = np.empty((h.value, w.value), np.uint8)
+        rc = RefExtractor._lib.ref_orb_level(self._h, l, int(filtered), _p(out), out.size, C.byref(w), C.byref(h))
+        assert rc == 0
+        return out

@@ -1,4 +1,7 @@
-"""TEST INFRASTRUCTURE ONLY -- compile the reference's own open_chisel (TSDF) sources into oracle/_ref/libchisel_ref.so.
+"""TEST INFRASTRUCTURE ONLY -- compile the reference's own sources for the hot path into oracle/_ref/:
+  libchisel_ref.so  Thirdparty/open_chisel/src/**/*.cpp (TSDF) against oracle/eigen_standin (Eigen is not installed)
+  liborb_ref.so     src/ORBextractor.cc against oracle/cv_standin (OpenCV's C++ headers are not installed); its four
+                    OpenCV primitives resolve to the C restatements in liboracle.so that are pinned bit-exactly to cv2
 
 The sources are compiled where they lie under /root/reference/Thirdparty/open_chisel (nothing is copied into this
 repository); outputs go only to oracle/_ref/ (git-ignored, but it travels to the GPU box with gpurun).  open_chisel's
@@ -43,5 +46,27 @@ def build(force=False):
     return str(OUT)
 
 
+ORB_OUT = OUTDIR / "liborb_ref.so"
+
+
+def build_orb(force=False):
+    """src/ORBextractor.cc + oracle/ref_orb_harness.cpp -> oracle/_ref/liborb_ref.so (links oracle/liboracle.so)."""
+    from . import build as oracle_build
+    src = pathlib.Path("/root/reference/src/ORBextractor.cc")
+    if not src.exists():
+        return str(ORB_OUT) if ORB_OUT.exists() else None
+    oracle_so = pathlib.Path(oracle_build.build())
+    deps = [src, HERE / "ref_orb_harness.cpp", HERE / "cv_standin" / "opencv2" / "opencv.hpp", oracle_so]
+    if ORB_OUT.exists() and not force and all(ORB_OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return str(ORB_OUT)
+    OUTDIR.mkdir(parents=True, exist_ok=True)
+    flags = ["-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w",
+             "-I", str(HERE / "cv_standin"), "-I", "/root/reference/include"]
+    subprocess.check_call(["g++"] + flags + ["-shared", "-o", str(ORB_OUT), str(src), str(HERE / "ref_orb_harness.cpp"),
+                           "-L", str(HERE), "-l:liboracle.so", "-Wl,-rpath,$ORIGIN/..", "-lm"])
+    return str(ORB_OUT)
+
+
 if __name__ == "__main__":
     print(build(force="-f" in sys.argv))
+    print(build_orb(force="-f" in sys.argv))

@@ -121,3 +121,22 @@ def test_device_distributor_equals_host_distributor(gpu, monkeypatch, nfeat):
         m2, k2, d2 = host(img)
         assert m1 == m2 and len(k1) == len(k2)
         assert np.array_equal(k1, k2) and np.array_equal(d1, d2)
+
+
+def test_cuda_vs_compiled_reference_live(gpu):
+    """the CUDA extractor against the REFERENCE's own ORBextractor.cc (oracle/_ref/liborb_ref.so, prebuilt in the build
+    container by oracle/ref_build.py; it travels to the GPU box with the snapshot)"""
+    if not O.ref_available():
+        pytest.skip("oracle/_ref/liborb_ref.so did not travel to this box")
+    for (w, h, nfeat, frame, lap) in [(640, 480, 2000, 5, (0, 0)), (752, 480, 1200, 1, (0, 0)), (640, 480, 1000, 2, (0, 1000))]:
+        img = synth.gray_frame(frame, w, h)
+        ex = ORBextractor(nfeat, 1.2, 8, 20, 7)
+        mono, kp, desc = ex(img, None, lap)
+        ref = O.RefExtractor(nfeat)
+        rkp, rdesc, rmono = ref(img, lap)
+        assert mono == rmono and len(kp) == len(rkp)
+        for f in FIELDS:
+            assert np.array_equal(kp[f], rkp[f]), f
+        assert np.array_equal(desc, rdesc)
+        for l in range(8):
+            assert np.array_equal(ex.pyramid_level(l), ref.level(l))
