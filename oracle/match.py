@@ -78,3 +78,79 @@ def compute_stereo_matches(left, right, pyr_left, pyr_right, scale, inv_scale, m
                                         C.cast(L, C.c_void_p), C.cast(R, C.c_void_p), sc.ctypes.data, isc.ctypes.data, mb, mbf,
                                         ur.ctypes.data, dp.ctypes.data)
     return ur[:left.n], dp[:left.n], kept
+
+
+# ---- the REFERENCE's own ORBmatcher.cc, compiled by oracle/ref_build.py (oracle/_ref/libmatch_ref.so) -----------------
+_ref = None
+
+
+def ref_available():
+    from . import ref_build
+    return ref_build.build_match() is not None
+
+
+def _ref_lib():
+    global _ref
+    if _ref is None:
+        from . import ref_build
+        so = ref_build.build_match()
+        if so is None:
+            raise RuntimeError("oracle/_ref/libmatch_ref.so missing and /root/reference not present")
+        lib()
+        _ref = C.CDLL(so)
+        _ref.ref_search_by_projection_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+        _ref.ref_search_by_projection_last.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        _ref.ref_search_for_triangulation.argtypes = [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _ref.ref_hamming256.argtypes = [C.c_void_p, C.c_void_p]
+    return _ref
+
+
+def ref_hamming256(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return _ref_lib().ref_hamming256(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+
+
+def ref_search_by_projection_map(F, queries, th, nn_ratio, far_points=False, th_far=50.0, claimed=None):
+    l = _ref_lib()
+    q = np.ascontiguousarray(queries, MP_QUERY)
+    v = F.view()
+    assign = np.full(max(F.n, 1), -1, np.int32)
+    cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+    n = l.ref_search_by_projection_map(C.byref(v), q.ctypes.data_as(C.c_void_p), len(q), th, nn_ratio, int(far_points), th_far,
+                                       cl.ctypes.data_as(C.c_void_p) if cl is not None else None, assign.ctypes.data_as(C.c_void_p))
+    return n, assign[:F.n]
+
+
+def canonical_last_queries(queries):
+    """The reference derives invzc from the camera-frame depth (`1.0/x3Dc(2)`, src/ORBmatcher.cc:1811); the flat query carries
+    invz.  Returns (queries', z) with z a float depth and queries'.invz == float(1.0/z), so both sides see the same numbers."""
+    q = np.array(queries, LAST_QUERY, copy=True)
+    with np.errstate(divide="ignore"):
+        z = (1.0 / q["invz"].astype(np.float64)).astype(np.float32)
+        q["invz"] = (1.0 / z.astype(np.float64)).astype(np.float32)
+    return q, z
+
+
+def ref_search_by_projection_last(Cur, queries, z, th, forward=False, backward=False, check_ori=True, claimed=None):
+    l = _ref_lib()
+    q = np.ascontiguousarray(queries, LAST_QUERY)
+    z = np.ascontiguousarray(z, np.float32)
+    v = Cur.view()
+    assign = np.full(max(Cur.n, 1), -1, np.int32)
+    cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+    n = l.ref_search_by_projection_last(C.byref(v), q.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), len(q), th, int(forward), int(backward),
+                                        int(check_ori), cl.ctypes.data_as(C.c_void_p) if cl is not None else None, assign.ctypes.data_as(C.c_void_p))
+    return n, assign[:Cur.n]
+
+
+def ref_search_for_triangulation(K1, K2, fv1, fv2, has1, has2, F12, ep, only_stereo=False, coarse=False, check_ori=True):
+    l = _ref_lib()
+    v1, v2 = K1.view(), K2.view()
+    s1, s2 = featvec_struct(fv1), featvec_struct(fv2)
+    h1 = np.ascontiguousarray(has1, np.uint8); h2 = np.ascontiguousarray(has2, np.uint8)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9); e = np.ascontiguousarray(ep, np.float32)
+    m12 = np.full(max(K1.n, 1), -1, np.int32)
+    n = l.ref_search_for_triangulation(C.byref(v1), C.byref(v2), C.byref(s1), C.byref(s2), h1.ctypes.data_as(C.c_void_p),
+                                       h2.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p),
+                                       int(only_stereo), int(coarse), int(check_ori), m12.ctypes.data_as(C.c_void_p))
+    return n, m12[:K1.n]

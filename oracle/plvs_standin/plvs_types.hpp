@@ -1,0 +1,195 @@
+// TEST INFRASTRUCTURE ONLY -- stand-ins for the PLVS data model classes that the reference's src/ORBmatcher.cc reads
+// (Frame, KeyFrame, MapPoint, GeometricCamera), so that ORBmatcher.cc can be compiled UNMODIFIED, where it lies, into
+// oracle/_ref/libmatch_ref.so.  The real headers pull in the whole system (g2o, DBoW2 vocabulary, Boost serialization,
+// Sophus -> Eigen, OpenCV); this file is force-included (-include) and pre-defines their include guards, so the
+// `#include "MapPoint.h"` etc. inside the reference's ORBmatcher.h become empty.  Pointers.h and DBoW2's FeatureVector.h
+// are the reference's own files.
+//
+// What is the reference's own code after this: every search in ORBmatcher.cc -- windows and level ranges, the claim checks
+// on mvpMapPoints (Observations()>0), the right-coordinate gate, best/second-best bookkeeping and ratio test, the
+// immediate claim writes, the rotation histogram with ComputeThreeMaxima, the FeatureVector merge-walk, epipole and
+// distance gates of SearchForTriangulation, DescriptorDistance.  What is restated HERE (with the lines it follows):
+//   Frame::GetFeaturesInArea / PosInGrid / AssignFeaturesToGrid        src/Frame.cc:1231-1316, 716-746
+//   Pinhole::epipolarConstrain (distance of kp2 to the epipolar line of kp1; the fundamental-matrix product is given)
+//                                                                      src/CameraModels/Pinhole.cpp:125-147
+// Poses and the camera are trivial on purpose: the parity harness passes world points that ARE the wanted projections
+// (identity pose, project(p) = (p.x, p.y)), because the drop-in C ABI receives projected queries too (the caller-side
+// shim projects with the reference's own Sophus/camera code, include/plvs_b200.h plvs_last_query).
+#ifndef PLVS_B200_PLVS_TYPES_STANDIN
+#define PLVS_B200_PLVS_TYPES_STANDIN
+#define MAPPOINT_H
+#define KEYFRAME_H
+#define FRAME_H
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <set>
+#include <tuple>
+#include <unordered_set>
+#include <utility>
+#include <vector>
+#include <opencv2/opencv.hpp>
+#include <Eigen/Core>
+#include <Eigen/Geometry>
+#include "sophus/se3.hpp"
+#include "sophus/sim3.hpp"
+#include "Pointers.h"
+#include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
+
+#define FRAME_GRID_ROWS 48
+#define FRAME_GRID_COLS 64
+
+namespace PLVS2 {
+
+using std::vector; using std::pair; using std::set; using std::unordered_set; using std::tuple; using std::get;     // the reference's headers are written inside `using namespace std`-style code (Fuse's signature uses bare `vector`)
+
+class GeometricCamera {
+public:
+    float F12[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};      // row-major fundamental matrix, set by the harness
+    virtual ~GeometricCamera() {}
+    virtual Eigen::Vector2f project(const Eigen::Vector3f& p) { return Eigen::Vector2f(p(0), p(1)); }
+    virtual float uncertainty2(const Eigen::Matrix<double, 2, 1>&) { return 1.0f; }
+    // src/CameraModels/Pinhole.cpp:125-147 with F12 precomputed
+    virtual bool epipolarConstrain(GeometricCamera*, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const Eigen::Matrix3f&, const Eigen::Vector3f&,
+                                   const float sigmaLevel, const float unc)
+    {
+        const float a = kp1.pt.x * F12[0] + kp1.pt.y * F12[3] + F12[6];
+        const float b = kp1.pt.x * F12[1] + kp1.pt.y * F12[4] + F12[7];
+        const float c = kp1.pt.x * F12[2] + kp1.pt.y * F12[5] + F12[8];
+        const float num = a * kp2.pt.x + b * kp2.pt.y + c;
+        const float den = a * a + b * b;
+        if (den == 0) return false;
+        const float dsqr = num * num / den;
+        return dsqr < 3.84 * unc;
+        (void)sigmaLevel;
+    }
+};
+
+class MapPoint {
+public:
+    // tracking variables written by Frame::isInFrustum (include/MapPoint.h)
+    float mTrackProjX = 0, mTrackProjY = 0, mTrackDepth = 0, mTrackDepthR = 0, mTrackProjXR = 0, mTrackProjYR = 0;
+    bool mbTrackInView = false, mbTrackInViewR = false;
+    int mnTrackScaleLevel = 0, mnTrackScaleLevelR = 0;
+    float mTrackViewCos = 1, mTrackViewCosR = 1;
+    long unsigned int mnId = 0, mnFuseCandidateForKF = 0, mnLastFrameSeen = 0;
+    // harness state
+    Eigen::Vector3f pos = Eigen::Vector3f::Zero(), normal = Eigen::Vector3f(0, 0, 1);
+    cv::Mat desc;
+    int nObs = 1; bool bad = false;
+    float minDist = 0, maxDist = 1e9f;
+
+    Eigen::Vector3f GetWorldPos() { return pos; }
+    Eigen::Vector3f GetNormal() { return normal; }
+    cv::Mat GetDescriptor() { return desc; }
+    int Observations() { return nObs; }
+    bool isBad() { return bad; }
+    float GetMinDistanceInvariance() { return minDist; }
+    float GetMaxDistanceInvariance() { return maxDist; }
+    int PredictScale(const float&, KeyFramePtr) { return 0; }
+    int PredictScale(const float&, Frame*) { return 0; }
+    bool IsInKeyFrame(KeyFramePtr) { return false; }
+    std::tuple<int, int> GetIndexInKeyFrame(const KeyFramePtr&) { return std::tuple<int, int>(-1, -1); }
+    void AddObservation(KeyFramePtr, size_t) {}
+    void Replace(MapPointPtr) {}
+    std::map<KeyFramePtr, std::tuple<int, int>> GetObservations() { return {}; }
+};
+
+class FrameBase {          // what Frame and KeyFrame share for the matcher
+public:
+    int N = 0, Nleft = -1, NLeft = -1;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
+    std::vector<float> mvuRight, mvDepth;
+    cv::Mat mDescriptors;
+    std::vector<float> mvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
+    std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
+    GeometricCamera* mpCamera = nullptr; GeometricCamera* mpCamera2 = nullptr;
+    float fx = 1, fy = 1, cx = 0, cy = 0, mbf = 0, mb = 0;
+    float mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;                     // Frame: static members, set once (src/Frame.cc:444-462)
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    DBoW2::FeatureVector mFeatVec;
+    Sophus::SE3f mTcw, mTrl;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+
+    // src/Frame.cc:1305-1316
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY)
+    {
+        posX = round((kp.pt.x - mnMinX) * mfGridElementWidthInv);
+        posY = round((kp.pt.y - mnMinY) * mfGridElementHeightInv);
+        if (posX < 0 || posX >= FRAME_GRID_COLS || posY < 0 || posY >= FRAME_GRID_ROWS) return false;
+        return true;
+    }
+    // src/Frame.cc:716-746 (RGB-D / rectified stereo: Nleft == -1)
+    void AssignFeaturesToGrid()
+    {
+        for (int i = 0; i < FRAME_GRID_COLS; i++) for (int j = 0; j < FRAME_GRID_ROWS; j++) mGrid[i][j].clear();
+        for (int i = 0; i < N; i++) {
+            const cv::KeyPoint& kp = mvKeysUn[i];
+            int nGridPosX, nGridPosY;
+            if (PosInGrid(kp, nGridPosX, nGridPosY)) mGrid[nGridPosX][nGridPosY].push_back(i);
+        }
+    }
+    // src/Frame.cc:1231-1303 (Nleft == -1 branch)
+    std::vector<std::size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1, const bool bRight = false) const
+    {
+        std::vector<std::size_t> vIndices;
+        vIndices.reserve(N);
+        float factorX = r, factorY = r;
+        const int nMinCellX = std::max(0, (int)floor((x - mnMinX - factorX) * mfGridElementWidthInv));
+        if (nMinCellX >= FRAME_GRID_COLS) return vIndices;
+        const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)ceil((x - mnMinX + factorX) * mfGridElementWidthInv));
+        if (nMaxCellX < 0) return vIndices;
+        const int nMinCellY = std::max(0, (int)floor((y - mnMinY - factorY) * mfGridElementHeightInv));
+        if (nMinCellY >= FRAME_GRID_ROWS) return vIndices;
+        const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)ceil((y - mnMinY + factorY) * mfGridElementHeightInv));
+        if (nMaxCellY < 0) return vIndices;
+        const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+            for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+                const std::vector<std::size_t>& vCell = mGrid[ix][iy];
+                if (vCell.empty()) continue;
+                for (size_t j = 0, jend = vCell.size(); j < jend; j++) {
+                    const cv::KeyPoint& kpUn = mvKeysUn[vCell[j]];
+                    if (bCheckLevels) {
+                        if (kpUn.octave < minLevel) continue;
+                        if (kpUn.octave > maxLevel) continue;        // PLVS has ORB-SLAM3's `if(maxLevel>=0)` commented out (src/Frame.cc:1283-1286)
+                    }
+                    const float distx = kpUn.pt.x - x;
+                    const float disty = kpUn.pt.y - y;
+                    if (fabs(distx) < factorX && fabs(disty) < factorY) vIndices.push_back(vCell[j]);
+                }
+            }
+        (void)bRight;
+        return vIndices;
+    }
+    bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }      // include/Frame.h / KeyFrame.cc
+};
+
+class Frame : public FrameBase {
+public:
+    std::vector<MapPointPtr> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    Sophus::SE3f GetPose() const { return mTcw; }
+    Sophus::SE3f GetRelativePoseTrl() { return mTrl; }
+    Sophus::SE3f GetRelativePoseTlr() { return mTrl.inverse(); }
+};
+
+class KeyFrame : public FrameBase {
+public:
+    std::vector<MapPointPtr> mvpMapPoints;
+    long unsigned int mnId = 0;
+    Sophus::SE3f GetPose() { return mTcw; }
+    Sophus::SE3f GetPoseInverse() { return mTcw.inverse(); }
+    Sophus::SE3f GetRightPose() { return mTrl * mTcw; }
+    Sophus::SE3f GetRightPoseInverse() { return (mTrl * mTcw).inverse(); }
+    Eigen::Vector3f GetCameraCenter() { return mTcw.inverse().translation(); }
+    Eigen::Vector3f GetRightCameraCenter() { return (mTrl * mTcw).inverse().translation(); }
+    MapPointPtr GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    std::vector<MapPointPtr> GetMapPointMatches() { return mvpMapPoints; }
+    std::set<MapPointPtr> GetMapPoints() { std::set<MapPointPtr> s; for (MapPointPtr p : mvpMapPoints) if (p) s.insert(p); return s; }
+    std::unordered_set<MapPointPtr> GetMapPointsUnordered() { std::unordered_set<MapPointPtr> s; for (MapPointPtr p : mvpMapPoints) if (p) s.insert(p); return s; }
+    void AddMapPoint(MapPointPtr p, const size_t& idx) { mvpMapPoints[idx] = p; }
+};
+
+}  // namespace PLVS2
+#endif

@@ -67,6 +67,34 @@ def build_orb(force=False):
     return str(ORB_OUT)
 
 
+MATCH_OUT = OUTDIR / "libmatch_ref.so"
+
+
+def build_match(force=False):
+    """src/ORBmatcher.cc + Thirdparty/DBoW2/DBoW2/FeatureVector.cpp + oracle/ref_match_harness.cpp -> oracle/_ref/libmatch_ref.so.
+    The PLVS data model (Frame/KeyFrame/MapPoint/GeometricCamera) comes from oracle/plvs_standin/plvs_types.hpp, force-included
+    with the include guards of the real headers pre-defined."""
+    ref = pathlib.Path("/root/reference")
+    src = ref / "src" / "ORBmatcher.cc"
+    if not src.exists():
+        return str(MATCH_OUT) if MATCH_OUT.exists() else None
+    srcs = [src, ref / "Thirdparty" / "DBoW2" / "DBoW2" / "FeatureVector.cpp", HERE / "ref_match_harness.cpp"]
+    deps = srcs + [HERE / "plvs_standin" / "plvs_types.hpp", HERE / "plvs_standin" / "sophus" / "se3.hpp",
+                   HERE / "cv_standin" / "opencv2" / "opencv.hpp", HERE / "eigen_standin" / "Eigen" / "Core", HERE / "eigen_standin" / "Eigen" / "Geometry"]
+    if MATCH_OUT.exists() and not force and all(MATCH_OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return str(MATCH_OUT)
+    from . import build as oracle_build
+    oracle_build.build()
+    OUTDIR.mkdir(parents=True, exist_ok=True)
+    flags = ["-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w",
+             "-I", str(HERE / "plvs_standin"), "-I", str(HERE / "cv_standin"), "-I", str(HERE / "eigen_standin"),
+             "-I", str(ref / "include"), "-I", str(ref), "-include", str(HERE / "plvs_standin" / "plvs_types.hpp")]
+    subprocess.check_call(["g++"] + flags + ["-shared", "-o", str(MATCH_OUT)] + [str(x) for x in srcs] +
+                          ["-L", str(HERE), "-l:liboracle.so", "-Wl,-rpath,$ORIGIN/..", "-lm"])
+    return str(MATCH_OUT)
+
+
 if __name__ == "__main__":
     print(build(force="-f" in sys.argv))
     print(build_orb(force="-f" in sys.argv))
+    print(build_match(force="-f" in sys.argv))

@@ -1,0 +1,152 @@
+// TEST INFRASTRUCTURE ONLY -- C driver around the REFERENCE's own src/ORBmatcher.cc.
+//
+// oracle/ref_build.py compiles /root/reference/src/ORBmatcher.cc where it lies (nothing is copied), DBoW2's FeatureVector.cpp
+// and this file into oracle/_ref/libmatch_ref.so; the data-model classes come from oracle/plvs_standin/plvs_types.hpp (see
+// its header for what is restated there: the frame grid and the epipolar line distance; everything in ORBmatcher.cc is the
+// reference's own).  This file builds Frame / KeyFrame / MapPoint objects from the flat views of the drop-in C ABI
+// (include/plvs_b200.h), calls the three searches, and flattens the side effects (Frame::mvpMapPoints, vMatchedPairs)
+// back into the arrays the oracle and the CUDA path return.  Entry points mirror oracle/match_oracle.cpp with the prefix ref_.
+#include "ORBmatcher.h"
+
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <unordered_map>
+#include <vector>
+
+using namespace PLVS2;
+
+namespace {
+
+struct KeyPointC { float x, y, size, angle, response; int32_t octave, class_id; };
+struct FrameView {
+    int32_t n; const KeyPointC* keys; const uint8_t* desc; const float* uright;
+    float min_x, min_y, max_x, max_y, grid_inv_w, grid_inv_h;
+    float scale_factors[16], level_sigma2[16];
+    int32_t nlevels; float bf; int32_t on_device; uint64_t cache_key;
+};
+struct MpQuery { float proj_x, proj_y, proj_xr, track_depth, view_cos; int32_t level; uint32_t flags; uint8_t desc[32]; };
+struct LastQuery { float u, v, invz; int32_t last_octave; float angle; uint32_t flags; uint8_t desc[32]; };
+struct FeatVec { int32_t n_nodes; const uint32_t* node_ids; const int32_t* offsets; const int32_t* features; };
+
+void fill(FrameBase& f, const FrameView* v)
+{
+    f.N = v->n; f.Nleft = -1; f.NLeft = -1;
+    f.mvKeysUn.resize(v->n);
+    for (int i = 0; i < v->n; ++i) {
+        const KeyPointC& k = v->keys[i];
+        f.mvKeysUn[i] = cv::KeyPoint(k.x, k.y, k.size, k.angle, k.response, k.octave, k.class_id);
+    }
+    f.mvKeys = f.mvKeysUn;
+    f.mvuRight.assign(v->n, -1.f);
+    if (v->uright) for (int i = 0; i < v->n; ++i) f.mvuRight[i] = v->uright[i];
+    f.mDescriptors = cv::Mat(v->n, 32, CV_8U, (void*)v->desc, 32);
+    f.mvScaleFactors.assign(v->scale_factors, v->scale_factors + 16);
+    f.mvLevelSigma2.assign(v->level_sigma2, v->level_sigma2 + 16);
+    f.mnMinX = v->min_x; f.mnMinY = v->min_y; f.mnMaxX = v->max_x; f.mnMaxY = v->max_y;
+    f.mfGridElementWidthInv = v->grid_inv_w; f.mfGridElementHeightInv = v->grid_inv_h;
+    f.mbf = v->bf; f.mb = 0.08f;
+    f.AssignFeaturesToGrid();
+}
+
+cv::Mat desc_mat(const uint8_t* d) { cv::Mat m(1, 32, CV_8U); std::memcpy(m.data, d, 32); return m; }
+
+}  // namespace
+
+extern "C" {
+
+int ref_hamming256(const uint8_t* a, const uint8_t* b)
+{
+    return ORBmatcher::DescriptorDistance(cv::Mat(1, 32, CV_8U, (void*)a, 32), cv::Mat(1, 32, CV_8U, (void*)b, 32));
+}
+
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPointPtr>&, th, bFarPoints, thFarPoints)   src/ORBmatcher.cc:71-244
+int ref_search_by_projection_map(const FrameView* Fv, const MpQuery* q, int nq, float th, float nn_ratio, int far_points, float th_far,
+                                 const uint8_t* claimed_in, int32_t* assign)
+{
+    GeometricCamera cam;
+    Frame F; fill(F, Fv); F.mpCamera = &cam;
+    MapPoint pre; pre.nObs = 1;                                   // a map point that already has observations
+    F.mvpMapPoints.assign(Fv->n, nullptr);
+    if (claimed_in) for (int i = 0; i < Fv->n; ++i) if (claimed_in[i]) F.mvpMapPoints[i] = &pre;
+    std::vector<std::unique_ptr<MapPoint>> mps(nq);
+    std::vector<MapPointPtr> vp(nq);
+    std::unordered_map<MapPointPtr, int> index;
+    for (int i = 0; i < nq; ++i) {
+        mps[i].reset(new MapPoint());
+        MapPoint& m = *mps[i];
+        m.mbTrackInView = true; m.mbTrackInViewR = false;
+        m.mTrackProjX = q[i].proj_x; m.mTrackProjY = q[i].proj_y; m.mTrackProjXR = q[i].proj_xr; m.mTrackDepth = q[i].track_depth;
+        m.mTrackViewCos = q[i].view_cos; m.mnTrackScaleLevel = q[i].level;
+        m.nObs = (q[i].flags & 1u) ? 1 : 0;
+        m.desc = desc_mat(q[i].desc);
+        vp[i] = &m; index[&m] = i;
+    }
+    ORBmatcher matcher(nn_ratio, true);
+    const int n = matcher.SearchByProjection(F, vp, th, far_points != 0, th_far);
+    for (int i = 0; i < Fv->n; ++i) { auto it = index.find(F.mvpMapPoints[i]); assign[i] = it == index.end() ? -1 : it->second; }
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(Frame& Cur, const Frame& Last, th, bMono)   src/ORBmatcher.cc:1774-1993
+// z[i]: camera-frame depth of query i with (float)(1.0 / z[i]) == q[i].invz (the reference computes invzc from z)
+int ref_search_by_projection_last(const FrameView* Cv, const LastQuery* q, const float* z, int nq, float th, int forward, int backward,
+                                  int check_ori, const uint8_t* claimed_in, int32_t* assign)
+{
+    GeometricCamera cam;
+    Frame Cur; fill(Cur, Cv); Cur.mpCamera = &cam;
+    MapPoint pre; pre.nObs = 1;
+    Cur.mvpMapPoints.assign(Cv->n, nullptr);
+    if (claimed_in) for (int i = 0; i < Cv->n; ++i) if (claimed_in[i]) Cur.mvpMapPoints[i] = &pre;
+    Frame Last; Last.N = nq; Last.Nleft = -1; Last.mpCamera = &cam;
+    Last.mvKeys.resize(nq); Last.mvKeysUn.resize(nq); Last.mvbOutlier.assign(nq, false); Last.mvpMapPoints.assign(nq, nullptr);
+    std::vector<std::unique_ptr<MapPoint>> mps(nq);
+    std::unordered_map<MapPointPtr, int> index;
+    for (int i = 0; i < nq; ++i) {
+        mps[i].reset(new MapPoint());
+        MapPoint& m = *mps[i];
+        m.pos = Eigen::Vector3f(q[i].u, q[i].v, z[i]);             // identity pose + identity camera: project(Tcw * pos) = (u, v)
+        m.nObs = (q[i].flags & 1u) ? 1 : 0;
+        m.desc = desc_mat(q[i].desc);
+        Last.mvpMapPoints[i] = &m; index[&m] = i;
+        Last.mvKeys[i].octave = q[i].last_octave; Last.mvKeysUn[i].octave = q[i].last_octave;
+        Last.mvKeys[i].angle = q[i].angle; Last.mvKeysUn[i].angle = q[i].angle;
+    }
+    // bForward = tlc(2) > mb, bBackward = -tlc(2) > mb with tlc = Tlw * twc = the last frame's translation here (:1788-1795)
+    Last.mTcw.t = Eigen::Vector3f(0.f, 0.f, forward ? 10.f : backward ? -10.f : 0.f);
+    ORBmatcher matcher(0.9f, check_ori != 0);
+    const int n = matcher.SearchByProjection(Cur, Last, th, false);
+    for (int i = 0; i < Cv->n; ++i) { auto it = index.find(Cur.mvpMapPoints[i]); assign[i] = it == index.end() ? -1 : it->second; }
+    return n;
+}
+
+// ORBmatcher::SearchForTriangulation(KF1, KF2, pairs, bOnlyStereo, bCoarse)   src/ORBmatcher.cc:999-1242
+int ref_search_for_triangulation(const FrameView* K1v, const FrameView* K2v, const FeatVec* fv1, const FeatVec* fv2,
+                                 const uint8_t* has_mp1, const uint8_t* has_mp2, const float* F12, const float* ep,
+                                 int only_stereo, int coarse, int check_ori, int32_t* match12)
+{
+    GeometricCamera cam1, cam2;
+    std::memcpy(cam1.F12, F12, sizeof(cam1.F12));
+    KeyFrame K1, K2; fill(K1, K1v); fill(K2, K2v);
+    K1.mpCamera = &cam1; K2.mpCamera = &cam2;
+    MapPoint some;
+    K1.mvpMapPoints.assign(K1v->n, nullptr); K2.mvpMapPoints.assign(K2v->n, nullptr);
+    for (int i = 0; i < K1v->n; ++i) if (has_mp1[i]) K1.mvpMapPoints[i] = &some;
+    for (int i = 0; i < K2v->n; ++i) if (has_mp2[i]) K2.mvpMapPoints[i] = &some;
+    auto load = [](DBoW2::FeatureVector& out, const FeatVec* fv) {
+        for (int a = 0; a < fv->n_nodes; ++a)
+            for (int k = fv->offsets[a]; k < fv->offsets[a + 1]; ++k) out.addFeature(fv->node_ids[a], (unsigned)fv->features[k]);
+    };
+    load(K1.mFeatVec, fv1); load(K2.mFeatVec, fv2);
+    // epipole = project(T2w * Cw) (:1009-1012): camera centre of KF1 placed at (ep, 1), KF2 at the identity
+    K1.mTcw.t = Eigen::Vector3f(-ep[0], -ep[1], -1.f);
+    ORBmatcher matcher(0.6f, check_ori != 0);
+    std::vector<std::pair<size_t, size_t>> pairs;
+    KeyFramePtr p1 = &K1, p2 = &K2;
+    const int n = matcher.SearchForTriangulation(p1, p2, pairs, only_stereo != 0, coarse != 0);
+    for (int i = 0; i < K1v->n; ++i) match12[i] = -1;
+    for (auto& pr : pairs) match12[pr.first] = (int32_t)pr.second;
+    return n;
+}
+
+}  // extern "C"

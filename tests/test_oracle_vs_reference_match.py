@@ -1,0 +1,107 @@
+"""Pins the matcher oracle (oracle/match_oracle.cpp, the restatement the CUDA searches are compared with) to the
+REFERENCE's own src/ORBmatcher.cc, compiled from /root/reference by oracle/ref_build.py into oracle/_ref/libmatch_ref.so
+(data-model stand-ins: oracle/plvs_standin/plvs_types.hpp).  Bit-exact assign arrays / match counts for the three searches
+of SURVEY.md §8a (a11, a14, a15, a16), including claim competition, pre-claimed keypoints, map points without
+observations, far-point gating, forward/backward level windows and the rotation histogram.  Skipped when neither
+/root/reference nor a prebuilt oracle/_ref is present."""
+import numpy as np
+import pytest
+
+from plvs_b200 import synth, scenario
+from plvs_b200.matcher import featvec
+from oracle import match as OM, orb as O
+
+pytestmark = pytest.mark.skipif(not OM.ref_available(), reason="oracle/_ref/libmatch_ref.so not built (/root/reference absent)")
+
+
+@pytest.fixture(scope="module")
+def frames():
+    K = synth.intrinsics(640, 480)
+    tab = O.Tables(2000)
+    out = []
+    for f in (10, 11, 15):
+        kp, desc, mono, _ = O.extract_port(synth.gray_frame(f), 2000)
+        fr = scenario.make_frame(kp, desc, synth.depth_frame(f), K, tab.scale)
+        fr.level_sigma2 = tab.sigma2
+        out.append((fr, synth.pose(f)))
+    return K, out
+
+
+def test_descriptor_distance():
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (500, 32), dtype=np.uint8); b = rng.integers(0, 256, (500, 32), dtype=np.uint8)
+    for i in range(500):
+        want = int(np.unpackbits(a[i] ^ b[i]).sum())
+        assert OM.ref_hamming256(a[i], b[i]) == want == OM.hamming256(a[i], b[i])
+
+
+@pytest.mark.parametrize("th", [1.0, 3.0, 5.0, 15.0])
+def test_projection_map(frames, th):
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    q, _ = scenario.map_queries(last, cur, K, Tl, Tc)
+    rn, ra = OM.ref_search_by_projection_map(cur, q, th, 0.8)
+    on, oa = OM.search_by_projection_map(cur, q, th, 0.8)
+    assert rn == on and np.array_equal(ra, oa)
+    if th >= 3:
+        assert rn > 200
+
+
+def test_projection_map_claims_far_and_unobserved(frames):
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    for seed in (3, 4, 5):
+        q, _ = scenario.map_queries(last, cur, K, Tl, Tc, seed=seed)
+        rng = np.random.default_rng(seed)
+        claimed = (rng.random(cur.n) < 0.3).astype(np.uint8)
+        q["flags"] = (rng.random(len(q)) < 0.9).astype(np.uint32)
+        q = np.concatenate([q, q[::2], q[::3]])                     # duplicated queries fight for the same keypoints
+        rn, ra = OM.ref_search_by_projection_map(cur, q, 5.0, 0.8, True, 3.0, claimed)
+        on, oa = OM.search_by_projection_map(cur, q, 5.0, 0.8, True, 3.0, claimed)
+        assert rn == on and np.array_equal(ra, oa)
+
+
+@pytest.mark.parametrize("th,fwd,bwd", [(15.0, False, False), (7.0, False, False), (15.0, True, False), (15.0, False, True)])
+def test_projection_last(frames, th, fwd, bwd):
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    q, _ = scenario.last_queries(last, cur, K, Tl, Tc)
+    q, z = OM.canonical_last_queries(q)
+    for check in (True, False):
+        rn, ra = OM.ref_search_by_projection_last(cur, q, z, th, fwd, bwd, check)
+        on, oa = OM.search_by_projection_last(cur, q, th, fwd, bwd, check)
+        assert rn == on and np.array_equal(ra, oa)
+    if not fwd:
+        assert rn > 300
+
+
+def test_projection_last_competition_and_claims(frames):
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    q, _ = scenario.last_queries(last, cur, K, Tl, Tc)
+    q = np.concatenate([q, q[::2]])
+    rng = np.random.default_rng(2)
+    q["flags"] = (rng.random(len(q)) < 0.8).astype(np.uint32)
+    q["invz"][::17] *= -1                                           # points behind the camera
+    q, z = OM.canonical_last_queries(q)
+    claimed = (rng.random(cur.n) < 0.2).astype(np.uint8)
+    rn, ra = OM.ref_search_by_projection_last(cur, q, z, 15.0, claimed=claimed)
+    on, oa = OM.search_by_projection_last(cur, q, 15.0, claimed=claimed)
+    assert rn == on and np.array_equal(ra, oa)
+
+
+@pytest.mark.parametrize("coarse,only_stereo", [(False, False), (True, False), (False, True)])
+def test_triangulation(frames, coarse, only_stereo):
+    K, fr = frames
+    (k1, T1), (k2, T2) = fr[0], fr[2]
+    for nodes in (128, 1024):
+        fv1, fv2 = featvec(scenario.node_ids(k1.desc, nodes)), featvec(scenario.node_ids(k2.desc, nodes))
+        rng = np.random.default_rng(4)
+        has1 = (rng.random(k1.n) < 0.4).astype(np.uint8); has2 = (rng.random(k2.n) < 0.4).astype(np.uint8)
+        F12, ep = scenario.fundamental(K, T1, T2)
+        for check in (True, False):
+            rn, rm = OM.ref_search_for_triangulation(k1, k2, fv1, fv2, has1, has2, F12, ep, only_stereo, coarse, check)
+            on, om = OM.search_for_triangulation(k1, k2, fv1, fv2, has1, has2, F12, ep, only_stereo, coarse, check)
+            assert rn == on and np.array_equal(rm, om)
+        if coarse and nodes == 128:
+            assert rn > 20
