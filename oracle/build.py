@@ -2,8 +2,8 @@
 
 Flags mirror the reference's Ubuntu-24.04 configuration (config.sh:19-21: no
 -march=native => no FMA contraction); -ffp-contract=off makes that explicit.
-The reference itself cannot be compiled in this image (needs OpenCV C++, Eigen,
-PCL, Boost -- SURVEY.md §8c), so there is no oracle/_ref.
+The reference's own sources for the path are compiled separately by oracle/ref_build.py
+(against stand-in headers for the libraries this image lacks) into oracle/_ref/.
 """
 import os, subprocess, sys, pathlib
 

@@ -9,8 +9,11 @@
 // exactly in the reference's iteration order.  The structs below mirror include/plvs_b200.h so the
 // tests hand the same buffers to the oracle and to the CUDA path.
 //
-// Parity status: the reference has no test vectors for these functions ("parity unpinned");
-// the Hamming kernel is pinned against numpy's bit counting in tests/test_oracle_match.py.
+// Parity status: the three searches and DescriptorDistance are PINNED -- tests/test_oracle_vs_reference_match.py checks them
+// bit-exactly against the reference's own src/ORBmatcher.cc, compiled into oracle/_ref/libmatch_ref.so by oracle/ref_build.py
+// (data-model stand-ins in oracle/plvs_standin), and tests/golden/match_ref.npz holds outputs recorded from it.
+// ComputeStereoMatches (below, src/Frame.cc) is "parity unpinned": Frame.cc cannot be compiled without the whole system and
+// the reference has no test vectors for it; known-answer tests only.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

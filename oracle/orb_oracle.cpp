@@ -7,11 +7,13 @@
 // only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load it.  The product (plvs_b200/) never links or calls it.
 //
-// Parity status: the reference ships no golden vectors for this path
-// ("parity unpinned").  The OpenCV primitives restated here
-// ARE pinned: tests/test_oracle_orb.py checks each of them bit-exactly against
-// the cv2 4.13 build in this image (resize, blur, per-cell FAST incl. order,
-// fastAtan2), and the whole-extractor port against the cv2-driven pipeline.
+// Parity status: PINNED.  The reference ships no golden vectors for this path
+// (SURVEY.md §4/§8c), so it is pinned to the reference itself: the OpenCV
+// primitives restated here are checked bit-exactly against the cv2 4.13 build in
+// this image (tests/test_oracle_orb.py: resize, blur, per-cell FAST incl. order,
+// fastAtan2), and the whole extractor against the reference's own
+// src/ORBextractor.cc compiled into oracle/_ref/liborb_ref.so by
+// oracle/ref_build.py (tests/test_oracle_vs_reference_orb.py).
 //
 // Build: g++ -O2 -ffp-contract=off (no -march=native: the reference's Ubuntu
 // 24.04 configuration, config.sh:19-21, so no FMA contraction).

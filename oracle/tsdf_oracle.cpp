@@ -15,9 +15,10 @@
 // reference's (brute-force) control flow.  Eigen is not available here; 3-vector reductions follow
 // Eigen's unrolled order e0 + (e1 + e2) and fp contraction is off (DESIGN.md "TSDF float order").
 //
-// Parity status: "parity unpinned" -- the reference has no test for this path and cannot be built
-// in this image (needs Eigen/PCL); tolerance for the CUDA path is |d| <= 1e-4 on sdf/weight and an
-// identical chunk-key set.
+// Parity status: PINNED -- tests/test_oracle_vs_reference_tsdf.py checks this file bit-exactly (chunk keys, sdf, weight,
+// colour, chunk-range size) against the reference's own open_chisel sources, compiled into oracle/_ref/libchisel_ref.so by
+// oracle/ref_build.py against the Eigen stand-in of oracle/eigen_standin (Eigen is not installed); goldens recorded from it
+// are in tests/golden/tsdf_ref_*.npz.  Tolerance for the CUDA path: |d| <= 1e-4 on sdf/weight and an identical chunk-key set.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
