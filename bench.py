@@ -295,10 +295,8 @@ def run_b200_arm(a):
     hp.upload_inputs()
     # timed run: only the roofline kernel (k_integrate) carries events (2 per frame); the per-kernel table comes from a
     # second, untimed pass with all events on
-    t_ms, wall, clocks, agg = run(resident=True, timed_profile=4 | 8)
-    ms = np.zeros(12, np.float32); cnt = np.zeros(12, np.int32)
-    lib.plvs_tsdf_kernel_times(hp.tsdf._h, ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 0)
-    integ_live = (float(ms[2]), int(cnt[2]))
+    # order: the per-kernel profile pass runs first (its result is not a bench value; it also settles every data-dependent
+    # buffer size and the clocks), then the timed passes
     run(resident=True, timed_profile=7)
     ktimes = {}
     ms = np.zeros(12, np.float32); cnt = np.zeros(12, np.int32)
@@ -318,6 +316,10 @@ def run_b200_arm(a):
         mm += ms; mc += cnt
     for i, nme in enumerate(("match.grid", "match.candidates", "match.resolve", "match.triangulate")):
         ktimes[nme] = (float(mm[i]), int(mc[i]))
+    t_ms, wall, clocks, agg = run(resident=True, timed_profile=4 | 8)
+    ms = np.zeros(12, np.float32); cnt = np.zeros(12, np.int32)
+    lib.plvs_tsdf_kernel_times(hp.tsdf._h, ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 0)
+    integ_live = (float(ms[2]), int(cnt[2]))
     frames = K * B
     value = world * frames / (t_ms / 1000.0)
     launches_per_step = hp.launches_per_frame() * B

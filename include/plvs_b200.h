@@ -55,6 +55,7 @@ int plvs_set_profiling(int mask);
 #define PLVS_MATCH_K_CANDIDATES 1
 #define PLVS_MATCH_K_RESOLVE 2
 #define PLVS_MATCH_K_TRIANGULATE 3
+#define PLVS_MATCH_K_FUSE 4
 #define PLVS_TSDF_K_TILES 0
 #define PLVS_TSDF_K_CLASSIFY 1
 #define PLVS_TSDF_K_INTEGRATE 2
@@ -233,6 +234,24 @@ int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const pl
                              const float F12[9], const float ep[2],
                              int only_stereo, int coarse, int check_orientation,
                              int32_t* match12, int* nmatches);
+
+/* ORBmatcher::Fuse(KeyFramePtr& pKF, const vector<MapPointPtr>&, th, bRight=false) (src/ORBmatcher.cc:1244-1435), the
+ * search part (:1340-1406).  One query = one map point that passed the caller-side gates (:1277-1338: not bad, not already in
+ * the keyframe, positive depth, inside the image, distance range, viewing angle), projected with the reference's own
+ * expressions: (u, v) = pCamera->project(Tcw * Xw), ur = u - bf / z, level = pMP->PredictScale(dist3D, pKF), desc =
+ * pMP->GetDescriptor().  The search does not read the keyframe's map points, so queries are independent; per query it
+ * returns the keypoint the reference selects -- best_idx[i] (-1 if no candidate passed the level / chi-square gates) and
+ * best_dist[i] (256 then).  The caller applies `bestDist <= TH_LOW` and the Replace / AddObservation / AddMapPoint
+ * bookkeeping in query order (:1409-1427; pointer graph, stays on the host).  *nfused = number of queries with
+ * best_dist <= 50 (== the value Fuse returns).  inv_level_sigma2 = KeyFrame::mvInvLevelSigma2 (nlevels entries). */
+typedef struct {
+    float u, v, ur;
+    int32_t level;                   /* nPredictedLevel */
+    uint8_t desc[32];
+} plvs_fuse_query;
+int plvs_match_fuse(plvs_match* h, const plvs_frame_view* kf, const float* inv_level_sigma2,
+                    const plvs_fuse_query* q, int nq, float th,
+                    int32_t* best_idx, int32_t* best_dist, int* nfused);
 
 /* Device view of one frame's pyramid (all levels) of an extractor handle: what Frame::ComputeStereoMatches
  * reads through mpORBextractorLeft/Right->mvImagePyramid (src/Frame.cc:1886,1914). */

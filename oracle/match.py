@@ -5,7 +5,7 @@ import numpy as np
 
 from .orb import lib
 from plvs_b200 import _lib as _abi
-from plvs_b200.matcher import MP_QUERY, LAST_QUERY, featvec_struct
+from plvs_b200.matcher import MP_QUERY, LAST_QUERY, FUSE_QUERY, featvec_struct
 
 
 def _setup():
@@ -154,3 +154,38 @@ def ref_search_for_triangulation(K1, K2, fv1, fv2, has1, has2, F12, ep, only_ste
                                        h2.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p),
                                        int(only_stereo), int(coarse), int(check_ori), m12.ctypes.data_as(C.c_void_p))
     return n, m12[:K1.n]
+
+
+# ---- ORBmatcher::Fuse (search part) ------------------------------------------------------------------------------------
+
+def fuse_queries(u, v, z, level, desc, bf):
+    """queries as the caller-side shim builds them: ur = u - bf * invz with `const float invz = 1/p3Dc(2)` (src/ORBmatcher.cc:1303,1315)"""
+    q = np.zeros(len(u), FUSE_QUERY)
+    z = np.asarray(z, np.float32)
+    invz = np.float32(1) / z
+    q["u"] = u; q["v"] = v; q["ur"] = np.asarray(u, np.float32) - np.float32(bf) * invz
+    q["level"] = level; q["desc"] = desc
+    return q
+
+
+def fuse(K, queries, th, inv_level_sigma2):
+    l = _setup()
+    q = np.ascontiguousarray(queries, FUSE_QUERY)
+    inv = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    v = K.view()
+    bi = np.full(max(len(q), 1), -1, np.int32); bd = np.full(max(len(q), 1), 256, np.int32)
+    l.orc_fuse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    n = l.orc_fuse(C.byref(v), inv.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), len(q), th, bi.ctypes.data_as(C.c_void_p), bd.ctypes.data_as(C.c_void_p))
+    return n, bi[:len(q)], bd[:len(q)]
+
+
+def ref_fuse(K, queries, z, bf, th, inv_level_sigma2):
+    """the reference's own Fuse: returns (nFused, fused_idx[nq]) with fused_idx = keypoint the map point was fused into or -1"""
+    l = _ref_lib()
+    q = np.ascontiguousarray(queries, FUSE_QUERY)
+    inv = np.ascontiguousarray(inv_level_sigma2, np.float32); z = np.ascontiguousarray(z, np.float32)
+    v = K.view()
+    out = np.full(max(len(q), 1), -1, np.int32)
+    l.ref_fuse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_void_p]
+    n = l.ref_fuse(C.byref(v), inv.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), bf, len(q), th, out.ctypes.data_as(C.c_void_p))
+    return n, out[:len(q)]

@@ -283,6 +283,46 @@ int orc_search_for_triangulation(const FrameView* K1, const FrameView* K2, const
     return nmatches;
 }
 
+// ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight=false) (src/ORBmatcher.cc:1244-1435), the search part (:1340-1406): window from
+// KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:1179-1229, no level filter), level gate [l-1, l], chi-square gate on the
+// reprojection error (7.8 with a right coordinate, 5.99 without), best distance, first wins ties.  The gates before the search
+// and the Replace / AddObservation bookkeeping after it are the caller's (pointer graph); the search does not read map points,
+// so the queries are independent of each other.
+struct FuseQuery { float u, v, ur; int32_t level; uint8_t desc[32]; };
+
+int orc_fuse(const FrameView* K, const float* inv_level_sigma2, const FuseQuery* q, int nq, float th, int32_t* best_idx, int32_t* best_dist)
+{
+    Grid grid(K);
+    std::vector<int> cand;
+    int nfused = 0;
+    for (int iq = 0; iq < nq; ++iq) {
+        const FuseQuery& m = q[iq];
+        const int lvl = m.level;
+        const float radius = th * K->scale_factors[lvl];
+        grid.in_area(m.u, m.v, radius, -1, -1, cand);            // minLevel <= 0 and maxLevel < 0: no level filter
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : cand) {
+            const KeyPoint& kp = K->keys[idx];
+            const int kpLevel = kp.octave;
+            if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+            if (K->uright && K->uright[idx] >= 0) {
+                const float ex = m.u - kp.x, ey = m.v - kp.y, er = m.ur - K->uright[idx];
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+            } else {
+                const float ex = m.u - kp.x, ey = m.v - kp.y;
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+            }
+            const int dist = hamming(m.desc, K->desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        best_idx[iq] = bestIdx; best_dist[iq] = bestDist;
+        if (bestDist <= TH_LOW) ++nfused;
+    }
+    return nfused;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------

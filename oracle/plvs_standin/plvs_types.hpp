@@ -78,6 +78,9 @@ public:
     cv::Mat desc;
     int nObs = 1; bool bad = false;
     float minDist = 0, maxDist = 1e9f;
+    int predictedLevel = 0;              // what PredictScale returns (the caller-side shim evaluates the real one)
+    int addedIdx = -1;                   // Fuse: AddObservation(pKF, idx) was called with this idx
+    MapPoint* fusedWith = nullptr;       // Fuse: the keyframe's map point this one was merged with (either Replace direction)
 
     Eigen::Vector3f GetWorldPos() { return pos; }
     Eigen::Vector3f GetNormal() { return normal; }
@@ -86,12 +89,12 @@ public:
     bool isBad() { return bad; }
     float GetMinDistanceInvariance() { return minDist; }
     float GetMaxDistanceInvariance() { return maxDist; }
-    int PredictScale(const float&, KeyFramePtr) { return 0; }
-    int PredictScale(const float&, Frame*) { return 0; }
+    int PredictScale(const float&, KeyFramePtr) { return predictedLevel; }
+    int PredictScale(const float&, Frame*) { return predictedLevel; }
     bool IsInKeyFrame(KeyFramePtr) { return false; }
     std::tuple<int, int> GetIndexInKeyFrame(const KeyFramePtr&) { return std::tuple<int, int>(-1, -1); }
-    void AddObservation(KeyFramePtr, size_t) {}
-    void Replace(MapPointPtr) {}
+    void AddObservation(KeyFramePtr, size_t idx) { addedIdx = (int)idx; }
+    void Replace(MapPointPtr other) { fusedWith = other; other->fusedWith = this; }
     std::map<KeyFramePtr, std::tuple<int, int>> GetObservations() { return {}; }
 };
 
@@ -178,6 +181,33 @@ class KeyFrame : public FrameBase {
 public:
     std::vector<MapPointPtr> mvpMapPoints;
     long unsigned int mnId = 0;
+    // src/KeyFrame.cc:1179-1229 (NLeft == -1): the KeyFrame overload has no level filter
+    std::vector<std::size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const
+    {
+        std::vector<std::size_t> vIndices;
+        vIndices.reserve(N);
+        float factorX = r, factorY = r;
+        const int nMinCellX = std::max(0, (int)floor((x - mnMinX - factorX) * mfGridElementWidthInv));
+        if (nMinCellX >= FRAME_GRID_COLS) return vIndices;
+        const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)ceil((x - mnMinX + factorX) * mfGridElementWidthInv));
+        if (nMaxCellX < 0) return vIndices;
+        const int nMinCellY = std::max(0, (int)floor((y - mnMinY - factorY) * mfGridElementHeightInv));
+        if (nMinCellY >= FRAME_GRID_ROWS) return vIndices;
+        const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)ceil((y - mnMinY + factorY) * mfGridElementHeightInv));
+        if (nMaxCellY < 0) return vIndices;
+        for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+            for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+                const std::vector<std::size_t>& vCell = mGrid[ix][iy];
+                for (size_t j = 0, jend = vCell.size(); j < jend; j++) {
+                    const cv::KeyPoint& kpUn = mvKeysUn[vCell[j]];
+                    const float distx = kpUn.pt.x - x;
+                    const float disty = kpUn.pt.y - y;
+                    if (fabs(distx) < r && fabs(disty) < r) vIndices.push_back(vCell[j]);
+                }
+            }
+        (void)bRight;
+        return vIndices;
+    }
     Sophus::SE3f GetPose() { return mTcw; }
     Sophus::SE3f GetPoseInverse() { return mTcw.inverse(); }
     Sophus::SE3f GetRightPose() { return mTrl * mTcw; }

@@ -27,6 +27,7 @@ struct FrameView {
 };
 struct MpQuery { float proj_x, proj_y, proj_xr, track_depth, view_cos; int32_t level; uint32_t flags; uint8_t desc[32]; };
 struct LastQuery { float u, v, invz; int32_t last_octave; float angle; uint32_t flags; uint8_t desc[32]; };
+struct FuseQuery { float u, v, ur; int32_t level; uint8_t desc[32]; };
 struct FeatVec { int32_t n_nodes; const uint32_t* node_ids; const int32_t* offsets; const int32_t* features; };
 
 void fill(FrameBase& f, const FrameView* v)
@@ -146,6 +147,42 @@ int ref_search_for_triangulation(const FrameView* K1v, const FrameView* K2v, con
     const int n = matcher.SearchForTriangulation(p1, p2, pairs, only_stereo != 0, coarse != 0);
     for (int i = 0; i < K1v->n; ++i) match12[i] = -1;
     for (auto& pr : pairs) match12[pr.first] = (int32_t)pr.second;
+    return n;
+}
+
+// ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight=false)   src/ORBmatcher.cc:1244-1435
+// z[i]: camera-frame depth of query i; the harness camera has bf = `bf` and the reference computes ur = u - bf * (1/z), which the
+// caller made equal to q[i].ur.  fused_idx[i] = keypoint the map point was fused into (bestDist <= TH_LOW), else -1.
+int ref_fuse(const FrameView* Kv, const float* inv_level_sigma2, const FuseQuery* q, const float* z, float bf, int nq, float th, int32_t* fused_idx)
+{
+    GeometricCamera cam;
+    KeyFrame K; fill(K, Kv); K.mpCamera = &cam; K.mbf = bf;
+    K.mvInvLevelSigma2.assign(inv_level_sigma2, inv_level_sigma2 + Kv->nlevels);
+    K.mvInvLevelSigma2.resize(16, 1.f);
+    K.mvpMapPoints.assign(Kv->n, nullptr);
+    std::vector<std::unique_ptr<MapPoint>> mps(nq);
+    std::vector<MapPointPtr> vp(nq);
+    for (int i = 0; i < nq; ++i) {
+        mps[i].reset(new MapPoint());
+        MapPoint& m = *mps[i];
+        m.pos = Eigen::Vector3f(q[i].u, q[i].v, z[i]);
+        m.normal = m.pos.normalized();                            // passes the viewing-angle gate (:1331-1338), a caller-side gate of the C ABI
+        m.predictedLevel = q[i].level;
+        m.nObs = 1 + (i % 3);
+        m.desc = desc_mat(q[i].desc);
+        vp[i] = &m;
+    }
+    ORBmatcher matcher(0.6f, true);
+    KeyFramePtr pk = &K;
+    const int n = matcher.Fuse(pk, vp, th, false);
+    std::unordered_map<MapPointPtr, int> where;                   // map point held by the keyframe -> keypoint index
+    for (int i = 0; i < Kv->n; ++i) if (K.mvpMapPoints[i]) where[K.mvpMapPoints[i]] = i;
+    for (int i = 0; i < nq; ++i) {
+        const MapPoint& m = *mps[i];
+        if (m.addedIdx >= 0) fused_idx[i] = m.addedIdx;
+        else if (m.fusedWith && where.count(m.fusedWith)) fused_idx[i] = where[m.fusedWith];
+        else fused_idx[i] = -1;
+    }
     return n;
 }
 

@@ -188,6 +188,67 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// ORBmatcher::Fuse, search part (src/ORBmatcher.cc:1340-1406): one warp per map point.  Window from
+// KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:1179-1229: no level filter, strict |dx|,|dy| < r), then the level gate
+// [l-1, l], the chi-square gate on the reprojection error and the best Hamming distance; `dist < bestDist` is strict, so the
+// first candidate in the reference's order (cell-column-major, insertion order inside a cell) wins ties: lanes keep
+// (dist, position) keys and the warp takes the minimum.
+// ---------------------------------------------------------------------------------------------
+struct FuseSigma { float inv[PLVS_MAX_LEVELS]; };
+
+__global__ void __launch_bounds__(256)
+k_fuse(ViewDev K, FuseSigma sg, const int* __restrict__ cell_start, const int* __restrict__ sorted,
+       const plvs_fuse_query* __restrict__ queries, int nq, float th, int32_t* __restrict__ best_idx, int32_t* __restrict__ best_dist,
+       int* __restrict__ nfused)
+{
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const plvs_fuse_query& m = queries[q];
+    const int lvl = m.level;
+    const float u = m.u, v = m.v, ur = m.ur;
+    const float radius = th * K.scale[lvl];
+    uint32_t best = 0xffffffffu;          // dist:9 << 20 | position:20
+    int best_i = -1;
+    int c0, c1, r0, r1;
+    if (cell_window(K.gp, u, v, radius, c0, c1, r0, r1)) {
+        const uint32_t* qw = reinterpret_cast<const uint32_t*>(m.desc);
+        const uint4 a0 = make_uint4(qw[0], qw[1], qw[2], qw[3]), a1 = make_uint4(qw[4], qw[5], qw[6], qw[7]);
+        int pos0 = 0;
+        for (int ix = c0; ix <= c1; ++ix) {
+            const int pbeg = cell_start[ix * GRID_ROWS + r0], pend = cell_start[ix * GRID_ROWS + r1 + 1];
+            for (int p = pbeg + lane; p < pend; p += 32) {
+                const int idx = sorted[p];
+                const plvs_keypoint kp = K.keys[idx];
+                if (!(fabsf(kp.x - u) < radius && fabsf(kp.y - v) < radius)) continue;
+                const int kl = kp.octave;
+                if (kl < lvl - 1 || kl > lvl) continue;
+                const float ex = u - kp.x, ey = v - kp.y;
+                const float kr = K.uright ? K.uright[idx] : -1.f;
+                if (kr >= 0) {
+                    const float er = ur - kr;
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if ((double)(e2 * sg.inv[kl]) > 7.8) continue;
+                } else {
+                    const float e2 = ex * ex + ey * ey;
+                    if ((double)(e2 * sg.inv[kl]) > 5.99) continue;
+                }
+                const uint32_t key = ((uint32_t)hamming256(a0, a1, K.desc + (size_t)idx * 32) << 20) | (uint32_t)(pos0 + (p - pbeg));
+                if (key < best) { best = key; best_i = idx; }
+            }
+            pos0 += pend - pbeg;
+        }
+    }
+    const uint32_t wmin = __reduce_min_sync(0xffffffffu, best);
+    const uint32_t who = __ballot_sync(0xffffffffu, best == wmin && best != 0xffffffffu);
+    if (who) {
+        const int src = __ffs(who) - 1;
+        const int idx = __shfl_sync(0xffffffffu, best_i, src);
+        if (lane == 0) { best_idx[q] = idx; best_dist[q] = (int)(wmin >> 20); if ((int)(wmin >> 20) <= TH_LOW) atomicAdd(nfused, 1); }
+    } else if (lane == 0) { best_idx[q] = -1; best_dist[q] = 256; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Phase B: claim resolution.  The reference walks the queries in order and a keypoint taken by an earlier query
 // (one whose map point has Observations() > 0) is skipped by the later ones (src/ORBmatcher.cc:113-115,1848-1850), so
 // target(q) is a function of target(0..q-1).  It is evaluated as a fixed-point (Jacobi) iteration on ONE thread-block
@@ -888,6 +949,51 @@ int plvs_match_projection_last(plvs_match* h, const plvs_frame_view* cur, const 
                                int forward, int backward, int check_orientation, const uint8_t* claimed_in, int32_t* assign, int* nmatches)
 {
     return run_projection<1>(h, cur, q, sizeof(plvs_last_query), nq, th, 0.f, 0, 0.f, forward, backward, check_orientation, claimed_in, assign, nmatches);
+}
+
+int plvs_match_fuse(plvs_match* h, const plvs_frame_view* kf, const float* inv_level_sigma2, const plvs_fuse_query* q, int nq, float th,
+                    int32_t* best_idx, int32_t* best_dist, int* nfused)
+{
+    if (!h || !kf || !inv_level_sigma2 || !best_idx || !best_dist || !nfused || nq < 0 || (nq && !q)) { set_error("null/invalid argument"); return PLVS_EINVAL; }
+    std::lock_guard<std::mutex> lock(h->mu);
+    PLVS_CUDA(cudaSetDevice(h->device));
+    ViewDev V;
+    int rc = stage_view(h, 0, kf, &V);
+    if (rc) return rc;
+    *nfused = 0;
+    for (int i = 0; i < nq; ++i) { best_idx[i] = -1; best_dist[i] = 256; }
+    const int n = kf->n;
+    if (n == 0 || nq == 0) return PLVS_OK;
+    for (int i = 0; i < nq; ++i) if (q[i].level < 0 || q[i].level >= kf->nlevels) { set_error("fuse query %d: level %d outside the pyramid", i, q[i].level); return PLVS_EINVAL; }
+    cudaStream_t st = h->stream;
+    if ((rc = h->d_query.alloc(sizeof(plvs_fuse_query) * (size_t)nq)) || (rc = h->d_cell_start.alloc(GRID_CELLS + 1)) || (rc = h->d_sorted.alloc(n)) ||
+        (rc = h->d_kp_cell.alloc(n)) || (rc = h->d_assign.alloc((size_t)2 * nq + 1)) || (rc = h->p_assign.alloc((size_t)2 * nq + 1))) return rc;
+    PLVS_CUDA(cudaMemcpyAsync(h->d_query.p, q, sizeof(plvs_fuse_query) * (size_t)nq, cudaMemcpyHostToDevice, st));
+    int launches = 0;
+    if (!(kf->cache_key != 0 && kf->cache_key == h->grid_key && n == h->grid_n)) {
+        h->timer.begin(PLVS_MATCH_K_GRID, st);
+        k_build_grid<<<1, 1024, 0, st>>>(V.keys, n, V.gp, h->d_cell_start.p, h->d_sorted.p, h->d_kp_cell.p);
+        h->timer.end(st);
+        ++launches;
+        h->grid_key = kf->cache_key; h->grid_n = n;
+    }
+    FuseSigma sg{};
+    for (int i = 0; i < kf->nlevels; ++i) sg.inv[i] = inv_level_sigma2[i];
+    int32_t* d_idx = h->d_assign.p; int32_t* d_dist = d_idx + nq; int* d_nf = reinterpret_cast<int*>(d_dist + nq);
+    PLVS_CUDA(cudaMemsetAsync(d_nf, 0, sizeof(int), st));
+    h->timer.begin(PLVS_MATCH_K_FUSE, st);
+    k_fuse<<<div_up(nq, 8), 256, 0, st>>>(V, sg, h->d_cell_start.p, h->d_sorted.p, reinterpret_cast<const plvs_fuse_query*>(h->d_query.p), nq, th, d_idx, d_dist, d_nf);
+    h->timer.end(st);
+    ++launches;
+    PLVS_CUDA(cudaMemcpyAsync(h->p_assign.h, h->d_assign.p, ((size_t)2 * nq + 1) * 4, cudaMemcpyDeviceToHost, st));
+    PLVS_CUDA(cudaGetLastError());
+    PLVS_CUDA(cudaStreamSynchronize(st));
+    h->timer.collect();
+    std::memcpy(best_idx, h->p_assign.h, (size_t)nq * 4);
+    std::memcpy(best_dist, h->p_assign.h + nq, (size_t)nq * 4);
+    *nfused = h->p_assign.h[2 * nq];
+    h->last_launches = launches;
+    return PLVS_OK;
 }
 
 int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const plvs_frame_view* kf2,

@@ -12,7 +12,8 @@ MP_QUERY = np.dtype([("proj_x", "f4"), ("proj_y", "f4"), ("proj_xr", "f4"), ("tr
                      ("level", "i4"), ("flags", "u4"), ("desc", "u1", 32)])
 LAST_QUERY = np.dtype([("u", "f4"), ("v", "f4"), ("invz", "f4"), ("last_octave", "i4"), ("angle", "f4"),
                        ("flags", "u4"), ("desc", "u1", 32)])
-assert MP_QUERY.itemsize == 60 and LAST_QUERY.itemsize == 56
+FUSE_QUERY = np.dtype([("u", "f4"), ("v", "f4"), ("ur", "f4"), ("level", "i4"), ("desc", "u1", 32)])
+assert MP_QUERY.itemsize == 60 and LAST_QUERY.itemsize == 56 and FUSE_QUERY.itemsize == 48
 Q_OBS_POSITIVE = 1
 FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48
 
@@ -125,6 +126,18 @@ class ORBmatcher:
                                                   assign.ctypes.data_as(C.c_void_p), C.byref(nm))
         _lib.check(rc, "plvs_match_projection_last")
         return nm.value, assign[:Cur.n]
+
+    def Fuse(self, KF, queries, th=3.0, inv_level_sigma2=None):
+        """Search part of Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:1340-1406) -> (nFused, best_idx[nq], best_dist[nq]).
+        The caller applies bestDist<=TH_LOW and the Replace/AddObservation bookkeeping in query order."""
+        q = np.ascontiguousarray(queries, FUSE_QUERY)
+        inv = np.ascontiguousarray(inv_level_sigma2 if inv_level_sigma2 is not None else 1.0 / KF.level_sigma2, np.float32)
+        bi = np.full(max(len(q), 1), -1, np.int32); bd = np.full(max(len(q), 1), 256, np.int32)
+        nf = C.c_int()
+        v = KF.view()
+        _lib.check(self._lib.plvs_match_fuse(self._h, C.byref(v), inv.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), len(q), th,
+                                             bi.ctypes.data_as(C.c_void_p), bd.ctypes.data_as(C.c_void_p), C.byref(nf)), "plvs_match_fuse")
+        return nf.value, bi[:len(q)], bd[:len(q)]
 
     def SearchForTriangulation(self, KF1, KF2, fv1, fv2, has_mp1, has_mp2, F12, ep, bOnlyStereo=False, bCoarse=False):
         """-> (nmatches, vMatches12[N1]); vMatchedPairs = [(i, m) for i, m in enumerate(vMatches12) if m >= 0]."""

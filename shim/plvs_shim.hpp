@@ -272,6 +272,76 @@ public:
         return nmatches;
     }
 
+    // int Fuse(KeyFramePtr& pKF, const vector<MapPointPtr>& vpMapPoints, const float th=3.0, const bool bRight=false)
+    // (src/ORBmatcher.cc:1244-1435).  The gates before the search run here with the reference's own expressions (:1277-1338),
+    // the window search runs on the device (plvs_match_fuse, independent per map point), and the Replace / AddObservation /
+    // AddMapPoint bookkeeping is applied here in the reference's order (:1409-1427).  RGB-D / rectified stereo: bRight == false.
+    template <class KeyFramePtr, class MapPointPtr>
+    int Fuse(KeyFramePtr& pKF, const std::vector<MapPointPtr>& vpMapPoints, const float th = 3.0f, const bool bRight = false)
+    {
+        (void)bRight;
+        const auto Tcw = pKF->GetPose();
+        const auto Ow = pKF->GetCameraCenter();
+        const float bf = pKF->mbf;
+        std::vector<plvs_fuse_query> q;
+        std::vector<size_t> src;
+        for (size_t i = 0; i < vpMapPoints.size(); ++i) {
+            MapPointPtr pMP = vpMapPoints[i];
+            if (!pMP) continue;
+            if (pMP->isBad()) continue;
+            else if (pMP->IsInKeyFrame(pKF)) continue;
+            const auto p3Dw = pMP->GetWorldPos();
+            const auto p3Dc = Tcw * p3Dw;
+            if (p3Dc(2) < 0.0f) continue;
+            const float invz = 1 / p3Dc(2);
+            const auto uv = pKF->mpCamera->project(p3Dc);
+            if (!pKF->IsInImage(uv(0), uv(1))) continue;
+            const float ur = uv(0) - bf * invz;
+            const float maxDistance = pMP->GetMaxDistanceInvariance();
+            const float minDistance = pMP->GetMinDistanceInvariance();
+#ifdef PLVS_SHIM_STANDIN
+            const float dist3D = standin_dist(p3Dw, Ow);
+            if (dist3D < minDistance || dist3D > maxDistance) continue;
+            if (standin_view_gate(p3Dw, Ow, pMP->GetNormal(), dist3D)) continue;
+#else
+            const Eigen::Vector3f PO = p3Dw - Ow;
+            const float dist3D = PO.norm();
+            if (dist3D < minDistance || dist3D > maxDistance) continue;
+            const Eigen::Vector3f Pn = pMP->GetNormal();
+            if (PO.dot(Pn) < 0.5 * dist3D) continue;
+#endif
+            plvs_fuse_query e{};
+            e.u = uv(0); e.v = uv(1); e.ur = ur;
+            e.level = pMP->PredictScale(dist3D, pKF);
+            const cv::Mat d = pMP->GetDescriptor();
+            std::memcpy(e.desc, d.data, 32);
+            q.push_back(e); src.push_back(i);
+        }
+        std::vector<int32_t> best_idx(q.size() + 1, -1), best_dist(q.size() + 1, 256);
+        int nsearch = 0;
+        const plvs_frame_view v = view_of(*pKF, pKF->mvKeysUn, pKF->mDescriptors);
+        plvs_shim::check(plvs_match_fuse(h_, &v, pKF->mvInvLevelSigma2.data(), q.data(), (int)q.size(), th, best_idx.data(), best_dist.data(), &nsearch),
+                         "plvs_match_fuse");
+        int nFused = 0;
+        for (size_t k = 0; k < q.size(); ++k) {
+            if (best_dist[k] > TH_LOW) continue;
+            MapPointPtr pMP = vpMapPoints[src[k]];
+            const int bestIdx = best_idx[k];
+            MapPointPtr pMPinKF = pKF->GetMapPoint(bestIdx);
+            if (pMPinKF) {
+                if (!pMPinKF->isBad()) {
+                    if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                    else pMPinKF->Replace(pMP);
+                }
+            } else {
+                pMP->AddObservation(pKF, bestIdx);
+                pKF->AddMapPoint(pMP, bestIdx);
+            }
+            nFused++;
+        }
+        return nFused;
+    }
+
     static const int TH_LOW = 50, TH_HIGH = 100, HISTO_LENGTH = 12;
 
 protected:

@@ -15,6 +15,7 @@ struct Pose {
     V3 operator*(const V3& p) const { return V3{{p.v[0] + t.v[0], p.v[1] + t.v[1], p.v[2] + t.v[2]}}; }
 };
 struct Camera { V2 project(const V3& p) const { return V2{{500.f * p.v[0] / p.v[2] + 320.f, 500.f * p.v[1] / p.v[2] + 240.f}}; } };
+struct KeyFrame;
 struct MapPoint {
     bool mbTrackInView = true; float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackDepth = 1, mTrackViewCos = 1; int mnTrackScaleLevel = 0;
     cv::Mat desc{1, 32, CV_8U}; V3 pos{{0, 0, 2}};
@@ -22,8 +23,17 @@ struct MapPoint {
     int Observations() const { return 1; }
     cv::Mat GetDescriptor() const { return desc; }
     V3 GetWorldPos() const { return pos; }
+    V3 GetNormal() const { return V3{{0, 0, 1}}; }
+    float GetMinDistanceInvariance() const { return 0.f; }
+    float GetMaxDistanceInvariance() const { return 1e9f; }
+    bool IsInKeyFrame(const std::shared_ptr<KeyFrame>&) const { return false; }
+    int PredictScale(float, const std::shared_ptr<KeyFrame>&) const { return 0; }
+    void Replace(const std::shared_ptr<MapPoint>&) {}
+    void AddObservation(const std::shared_ptr<KeyFrame>&, int) {}
 };
 typedef std::shared_ptr<MapPoint> MapPointPtr;
+static float standin_dist(const V3& p, const V3& o) { const float d[3] = {p.v[0] - o.v[0], p.v[1] - o.v[1], p.v[2] - o.v[2]}; return d[0] * d[0] + d[1] * d[1] + d[2] * d[2]; }
+static bool standin_view_gate(const V3&, const V3&, const V3&, float) { return false; }
 struct Frame {
     int N = 0; std::vector<cv::KeyPoint> mvKeys, mvKeysUn; cv::Mat mDescriptors; std::vector<float> mvuRight, mvScaleFactors, mvLevelSigma2;
     std::vector<MapPointPtr> mvpMapPoints; std::vector<bool> mvbOutlier; float mbf = 40, mb = 0.08f; Camera* mpCamera = nullptr; Pose pose;
@@ -34,6 +44,10 @@ float Frame::mnMinX = 0, Frame::mnMinY = 0, Frame::mnMaxX = 640, Frame::mnMaxY =
 struct KeyFrame : Frame {
     std::map<unsigned, std::vector<unsigned>> mFeatVec;
     MapPointPtr GetMapPoint(int i) const { return mvpMapPoints[i]; }
+    std::vector<float> mvInvLevelSigma2 = std::vector<float>(8, 1.f);
+    V3 GetCameraCenter() const { return V3{{0, 0, 0}}; }
+    bool IsInImage(float x, float y) const { return x >= 0 && x < 640 && y >= 0 && y < 480; }
+    void AddMapPoint(const MapPointPtr& p, int i) { mvpMapPoints[i] = p; }
 };
 static void standin_fundamental(const KeyFrame&, const KeyFrame&, float* F12, float* ep) { for (int i = 0; i < 9; ++i) F12[i] = 0; ep[0] = ep[1] = 0; }
 
@@ -54,6 +68,7 @@ extern "C" int shim_instantiate(int run)
     auto k1 = std::make_shared<KeyFrame>(), k2 = std::make_shared<KeyFrame>();
     std::vector<std::pair<size_t, size_t>> pairs;
     int c = m.SearchForTriangulation(k1, k2, pairs, false, false);
+    c += m.Fuse(k1, mps, 3.0f, false);
     chisel_server::ChiselServerParams p; chisel_server::ChiselServer cs(p);
     cs.SetDepthCameraInfo(500, 500, 320, 240, 640, 480);
     Eigen::Affine3f T; cs.SetDepthPose(T);

@@ -180,3 +180,31 @@ def test_grid_cache_key_reuses_grid_and_stays_exact(frames):
     # a new extraction gets a new key: no stale grid
     mono, kp, desc = ex(synth.gray_frame(12))
     assert ex.device_result(0).cache_key != dv.cache_key
+
+
+@pytest.mark.parametrize("with_uright,dup,th", [(True, False, 3.0), (True, True, 4.0), (False, False, 3.0), (False, True, 2.5)])
+def test_fuse(frames, with_uright, dup, th):
+    """search part of ORBmatcher::Fuse (a "next" row of SURVEY.md §8f rank 1): CUDA == oracle (bit-exact best index and
+    distance per map point) == the reference's own Fuse where it is observable (fused pairs)"""
+    import copy
+    from oracle import orb as O
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    qm, _ = scenario.map_queries(last, cur, K, Tl, Tc, seed=7)
+    z = np.maximum(qm["track_depth"], 0.3).astype(np.float32)
+    q = OM.fuse_queries(qm["proj_x"], qm["proj_y"], z, qm["level"], qm["desc"], K["bf"])
+    if dup:
+        q = np.concatenate([q, q[::2]]); z = np.concatenate([z, z[::2]])
+    kf = cur
+    if not with_uright:
+        kf = copy.copy(cur); kf.uright = None
+    inv = O.Tables(2000).inv_sigma2
+    n, bi, bd = ORBmatcher(0.6, True).Fuse(kf, q, th, inv)
+    on, obi, obd = OM.fuse(kf, q, th, inv)
+    assert n == on and np.array_equal(bi, obi) and np.array_equal(bd, obd)
+    assert n > 300
+    if OM.ref_available():
+        rn, ridx = OM.ref_fuse(kf, q, z, K["bf"], th, inv)
+        assert n == rn and np.array_equal(np.where(bd <= 50, bi, -1), ridx)
+    n0, bi0, bd0 = ORBmatcher(0.6, True).Fuse(kf, q[:0], th, inv)
+    assert n0 == 0 and len(bi0) == 0

@@ -105,3 +105,28 @@ def test_triangulation(frames, coarse, only_stereo):
             assert rn == on and np.array_equal(rm, om)
         if coarse and nodes == 128:
             assert rn > 20
+
+
+def _fuse_case(frames, seed, with_uright, dup):
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    qm, _ = scenario.map_queries(last, cur, K, Tl, Tc, seed=seed)
+    z = np.maximum(qm["track_depth"], 0.3).astype(np.float32)
+    q = OM.fuse_queries(qm["proj_x"], qm["proj_y"], z, qm["level"], qm["desc"], K["bf"])
+    if dup:                                       # several map points landing on the same keypoint: the Replace branches (:1412-1419)
+        q = np.concatenate([q, q[::2]]); z = np.concatenate([z, z[::2]])
+    kf = cur
+    if not with_uright:                           # monocular keyframe: the 5.99 branch of the chi-square gate
+        import copy
+        kf = copy.copy(cur); kf.uright = None
+    return K, kf, q, z
+
+
+@pytest.mark.parametrize("with_uright,dup,th", [(True, False, 3.0), (True, True, 4.0), (False, False, 3.0), (False, True, 2.5)])
+def test_fuse(frames, with_uright, dup, th):
+    tab = O.Tables(2000)
+    K, kf, q, z = _fuse_case(frames, 7, with_uright, dup)
+    n, bi, bd = OM.fuse(kf, q, th, tab.inv_sigma2)
+    rn, ridx = OM.ref_fuse(kf, q, z, K["bf"], th, tab.inv_sigma2)
+    assert n == rn and np.array_equal(np.where(bd <= 50, bi, -1), ridx)
+    assert n > 300
