@@ -56,6 +56,7 @@ int plvs_set_profiling(int mask);
 #define PLVS_MATCH_K_RESOLVE 2
 #define PLVS_MATCH_K_TRIANGULATE 3
 #define PLVS_MATCH_K_FUSE 4
+#define PLVS_MATCH_K_BOW 5
 #define PLVS_TSDF_K_TILES 0
 #define PLVS_TSDF_K_CLASSIFY 1
 #define PLVS_TSDF_K_INTEGRATE 2
@@ -234,6 +235,15 @@ int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const pl
                              const float F12[9], const float ep[2],
                              int only_stereo, int coarse, int check_orientation,
                              int32_t* match12, int* nmatches);
+
+/* ORBmatcher::SearchByBoW(KeyFramePtr& pKF, Frame& F, vector<MapPointPtr>& vpMapPointMatches) (src/ORBmatcher.cc:300-506),
+ * RGB-D / rectified stereo (Nleft == -1): Tracking::TrackReferenceKeyFrame and Relocalization.  fv_kf / fv_f = pKF->mFeatVec /
+ * F.mFeatVec flattened; has_mp_kf[i] != 0 <=> pKF->GetMapPointMatches()[i] is non-null and not bad; nn_ratio / check_orientation
+ * = the ORBmatcher constructor arguments.  match_f[i] (f->n entries) = keyframe feature whose map point was assigned to frame
+ * feature i (== vpMapPointMatches[i] = vpMapPointsKF[match_f[i]]) or -1; *nmatches = the value SearchByBoW returns. */
+int plvs_match_bow(plvs_match* h, const plvs_frame_view* kf, const plvs_frame_view* f,
+                   const plvs_featvec* fv_kf, const plvs_featvec* fv_f, const uint8_t* has_mp_kf,
+                   float nn_ratio, int check_orientation, int32_t* match_f, int* nmatches);
 
 /* ORBmatcher::Fuse(KeyFramePtr& pKF, const vector<MapPointPtr>&, th, bRight=false) (src/ORBmatcher.cc:1244-1435), the
  * search part (:1340-1406).  One query = one map point that passed the caller-side gates (:1277-1338: not bad, not already in

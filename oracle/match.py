@@ -189,3 +189,23 @@ def ref_fuse(K, queries, z, bf, th, inv_level_sigma2):
     l.ref_fuse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_float, C.c_void_p]
     n = l.ref_fuse(C.byref(v), inv.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), bf, len(q), th, out.ctypes.data_as(C.c_void_p))
     return n, out[:len(q)]
+
+
+# ---- ORBmatcher::SearchByBoW(KF, F) ------------------------------------------------------------------------------------
+
+def _bow_call(fn, K, F, fvK, fvF, has_mp, nn_ratio, check_ori):
+    vK, vF = K.view(), F.view()
+    sK, sF = featvec_struct(fvK), featvec_struct(fvF)
+    h = np.ascontiguousarray(has_mp, np.uint8)
+    m = np.full(max(F.n, 1), -1, np.int32)
+    fn.argtypes = [C.c_void_p] * 5 + [C.c_float, C.c_int, C.c_void_p]
+    n = fn(C.byref(vK), C.byref(vF), C.byref(sK), C.byref(sF), h.ctypes.data_as(C.c_void_p), nn_ratio, int(check_ori), m.ctypes.data_as(C.c_void_p))
+    return n, m[:F.n]
+
+
+def search_by_bow(K, F, fvK, fvF, has_mp, nn_ratio=0.7, check_ori=True):
+    return _bow_call(_setup().orc_search_by_bow, K, F, fvK, fvF, has_mp, nn_ratio, check_ori)
+
+
+def ref_search_by_bow(K, F, fvK, fvF, has_mp, nn_ratio=0.7, check_ori=True):
+    return _bow_call(_ref_lib().ref_search_by_bow, K, F, fvK, fvF, has_mp, nn_ratio, check_ori)

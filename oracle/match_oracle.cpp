@@ -283,6 +283,58 @@ int orc_search_for_triangulation(const FrameView* K1, const FrameView* K2, const
     return nmatches;
 }
 
+// ORBmatcher::SearchByBoW(KeyFramePtr& pKF, Frame& F, vector<MapPointPtr>& vpMapPointMatches) (src/ORBmatcher.cc:300-506),
+// Nleft == -1 branch: merge-walk of the two FeatureVectors; inside a shared node the keyframe features that carry a (good)
+// map point are visited in order, each takes the best frame feature of the node that is still unmatched (best/second with
+// the multiset semantics of the if / else-if pair, strict `<` so the first index wins ties), claims it if
+// best <= TH_LOW and best < ratio * second; rotation histogram over the claimed frame features at the end.
+// has_mp[i] != 0 <=> vpMapPointsKF[i] && !isBad().  match_f[iF] = keyframe feature whose map point went to frame feature iF.
+int orc_search_by_bow(const FrameView* K, const FrameView* F, const FeatVec* fvK, const FeatVec* fvF, const uint8_t* has_mp,
+                      float nn_ratio, int check_ori, int32_t* match_f)
+{
+    int nmatches = 0;
+    for (int i = 0; i < F->n; ++i) match_f[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int a = 0, b = 0;
+    while (a < fvK->n_nodes && b < fvF->n_nodes) {
+        if (fvK->node_ids[a] == fvF->node_ids[b]) {
+            for (int iK = fvK->offsets[a]; iK < fvK->offsets[a + 1]; ++iK) {
+                const int idxK = fvK->features[iK];
+                if (!has_mp[idxK]) continue;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int iF = fvF->offsets[b]; iF < fvF->offsets[b + 1]; ++iF) {
+                    const int idxF = fvF->features[iF];
+                    if (match_f[idxF] >= 0) continue;
+                    const int dist = hamming(K->desc + (size_t)idxK * 32, F->desc + (size_t)idxF * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = idxF; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 <= TH_LOW) {
+                    if ((float)bestDist1 < nn_ratio * (float)bestDist2) {
+                        match_f[bestIdxF] = idxK;
+                        if (check_ori) rotHist[rot_bin(K->keys[idxK].angle, F->keys[bestIdxF].angle)].push_back(bestIdxF);
+                        ++nmatches;
+                    }
+                }
+            }
+            ++a; ++b;
+        } else if (fvK->node_ids[a] < fvF->node_ids[b]) {
+            while (a < fvK->n_nodes && fvK->node_ids[a] < fvF->node_ids[b]) ++a;
+        } else {
+            while (b < fvF->n_nodes && fvF->node_ids[b] < fvK->node_ids[a]) ++b;
+        }
+    }
+    if (check_ori) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int idx : rotHist[i]) { match_f[idx] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
 // ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight=false) (src/ORBmatcher.cc:1244-1435), the search part (:1340-1406): window from
 // KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:1179-1229, no level filter), level gate [l-1, l], chi-square gate on the
 // reprojection error (7.8 with a right coordinate, 5.99 without), best distance, first wins ties.  The gates before the search

@@ -150,6 +150,30 @@ int ref_search_for_triangulation(const FrameView* K1v, const FrameView* K2v, con
     return n;
 }
 
+// ORBmatcher::SearchByBoW(KeyFramePtr& pKF, Frame& F, vector<MapPointPtr>& vpMapPointMatches)   src/ORBmatcher.cc:300-506
+int ref_search_by_bow(const FrameView* Kv, const FrameView* Fv, const FeatVec* fvK, const FeatVec* fvF, const uint8_t* has_mp,
+                      float nn_ratio, int check_ori, int32_t* match_f)
+{
+    GeometricCamera cam;
+    KeyFrame K; fill(K, Kv); K.mpCamera = &cam;
+    Frame F; fill(F, Fv); F.mpCamera = &cam;
+    std::vector<std::unique_ptr<MapPoint>> mps(Kv->n);
+    std::unordered_map<MapPointPtr, int> index;
+    K.mvpMapPoints.assign(Kv->n, nullptr);
+    for (int i = 0; i < Kv->n; ++i) if (has_mp[i]) { mps[i].reset(new MapPoint()); K.mvpMapPoints[i] = mps[i].get(); index[mps[i].get()] = i; }
+    auto load = [](DBoW2::FeatureVector& out, const FeatVec* fv) {
+        for (int a = 0; a < fv->n_nodes; ++a)
+            for (int k = fv->offsets[a]; k < fv->offsets[a + 1]; ++k) out.addFeature(fv->node_ids[a], (unsigned)fv->features[k]);
+    };
+    load(K.mFeatVec, fvK); load(F.mFeatVec, fvF);
+    ORBmatcher matcher(nn_ratio, check_ori != 0);
+    std::vector<MapPointPtr> matches;
+    KeyFramePtr pk = &K;
+    const int n = matcher.SearchByBoW(pk, F, matches);
+    for (int i = 0; i < Fv->n; ++i) { auto it = index.find(matches[i]); match_f[i] = it == index.end() ? -1 : it->second; }
+    return n;
+}
+
 // ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight=false)   src/ORBmatcher.cc:1244-1435
 // z[i]: camera-frame depth of query i; the harness camera has bf = `bf` and the reference computes ur = u - bf * (1/z), which the
 // caller made equal to q[i].ur.  fused_idx[i] = keypoint the map point was fused into (bestDist <= TH_LOW), else -1.

@@ -521,8 +521,9 @@ k_triangulate(ViewDev K1, ViewDev K2, FvDev f1, FvDev f2, const uint8_t* __restr
 
 __global__ void __launch_bounds__(1024)
 k_tri_finish(const plvs_keypoint* __restrict__ k1, const plvs_keypoint* __restrict__ k2, int n1, int check_ori,
-             int32_t* __restrict__ match12, int32_t* __restrict__ match_out, int* __restrict__ result)
+             int32_t* __restrict__ match12, int32_t* __restrict__ match_out, int* __restrict__ result, int reverse = 0)
 {
+    // reverse: rot = k2[j].angle - k1[i].angle (SearchByBoW indexes the matches by the FRAME feature, rot = kpKF - kpF)
     __shared__ int s_hist[HISTO], s_keep[HISTO], s_count;
     const int tid = threadIdx.x;
     if (tid < HISTO) { s_hist[tid] = 0; s_keep[tid] = 1; }
@@ -535,7 +536,7 @@ k_tri_finish(const plvs_keypoint* __restrict__ k1, const plvs_keypoint* __restri
         if (j < 0) continue;
         ++local;
         if (check_ori) {
-            float rot = k1[i].angle - k2[j].angle;
+            float rot = reverse ? k2[j].angle - k1[i].angle : k1[i].angle - k2[j].angle;
             if (rot < 0.0f) rot += 360.0f;
             int bin = (int)roundf(rot * factor);
             if (bin == HISTO) bin = 0;
@@ -562,7 +563,7 @@ k_tri_finish(const plvs_keypoint* __restrict__ k1, const plvs_keypoint* __restri
         for (int i = tid; i < n1; i += 1024) {
             const int j = match12[i];
             if (j < 0) continue;
-            float rot = k1[i].angle - k2[j].angle;
+            float rot = reverse ? k2[j].angle - k1[i].angle : k1[i].angle - k2[j].angle;
             if (rot < 0.0f) rot += 360.0f;
             int bin = (int)roundf(rot * factor);
             if (bin == HISTO) bin = 0;
@@ -573,6 +574,51 @@ k_tri_finish(const plvs_keypoint* __restrict__ k1, const plvs_keypoint* __restri
     __syncthreads();
     for (int i = tid; i < n1; i += 1024) match_out[i] = match12[i];
     if (tid == 0) result[0] = s_count;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:300-506, Nleft == -1).  The claim
+// `if(vpMapPointMatches[realIdxF]) continue` only couples keyframe features of the SAME vocabulary node (a frame feature
+// sits in exactly one node), so nodes are independent: one warp per keyframe node, the keyframe features of the node in
+// sequence, lanes over the frame features of the node.  best = first index with the smallest distance, second = second
+// smallest of the multiset (what the if / else-if pair computes, order-independent).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_bow(ViewDev K, ViewDev F, FvDev fK, FvDev fF, const uint8_t* __restrict__ has_mp, float ratio, int32_t* match_f)
+{
+    const int a = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (a >= fK.n_nodes) return;
+    const uint32_t id = fK.ids[a];
+    int b = -1, lo = 0, hi = fF.n_nodes - 1;
+    while (lo <= hi) { const int mid = (lo + hi) >> 1; const uint32_t v = fF.ids[mid]; if (v == id) { b = mid; break; } if (v < id) lo = mid + 1; else hi = mid - 1; }
+    if (b < 0) return;
+    const int k0 = fK.off[a], k1 = fK.off[a + 1], b0 = fF.off[b], b1 = fF.off[b + 1];
+    volatile int32_t* mf = match_f;
+    for (int iK = k0; iK < k1; ++iK) {
+        const int idxK = fK.feat[iK];
+        if (!has_mp[idxK]) continue;
+        const uint8_t* dK = K.desc + (size_t)idxK * 32;
+        const uint4 a0 = *reinterpret_cast<const uint4*>(dK), a1 = *reinterpret_cast<const uint4*>(dK + 16);
+        uint32_t bestkey = 0xffffffffu;      // dist << 16 | position in the node list
+        int bi = -1, d1 = 256, d2 = 256;
+        for (int p = b0 + lane; p < b1; p += 32) {
+            const int idxF = fF.feat[p];
+            if (mf[idxF] >= 0) continue;
+            const int dist = hamming256(a0, a1, F.desc + (size_t)idxF * 32);
+            const uint32_t key = ((uint32_t)dist << 16) | (uint32_t)min(p - b0, 65535);
+            if (key < bestkey) { bestkey = key; bi = idxF; }
+            if (dist < d1) { d2 = d1; d1 = dist; } else if (dist < d2) d2 = dist;
+        }
+        const int m1 = __reduce_min_sync(0xffffffffu, d1);
+        const int winner = __ffs(__ballot_sync(0xffffffffu, d1 == m1)) - 1;
+        const int m2 = __reduce_min_sync(0xffffffffu, lane == winner ? d2 : d1);
+        const uint32_t wk = __reduce_min_sync(0xffffffffu, bestkey);
+        const int src = __ffs(__ballot_sync(0xffffffffu, bestkey == wk)) - 1;
+        const int idx = __shfl_sync(0xffffffffu, bi, src);
+        if (lane == 0 && m1 <= TH_LOW && (float)m1 < ratio * (float)m2) mf[idx] = idxK;
+        __syncwarp();
+    }
 }
 
 __global__ void k_fill_i32(int32_t* p, int n, int32_t v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
@@ -1035,6 +1081,41 @@ int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const pl
     PLVS_CUDA(cudaStreamSynchronize(st));
     h->timer.collect();
     std::memcpy(match12, h->p_assign.h, (size_t)n1 * 4);
+    *nmatches = h->p_result.h[0];
+    h->last_launches = 3;
+    return PLVS_OK;
+}
+
+int plvs_match_bow(plvs_match* h, const plvs_frame_view* kf, const plvs_frame_view* f, const plvs_featvec* fv_kf, const plvs_featvec* fv_f,
+                   const uint8_t* has_mp_kf, float nn_ratio, int check_orientation, int32_t* match_f, int* nmatches)
+{
+    if (!h || !kf || !f || !fv_kf || !fv_f || !has_mp_kf || !match_f || !nmatches) { set_error("null argument"); return PLVS_EINVAL; }
+    std::lock_guard<std::mutex> lock(h->mu);
+    PLVS_CUDA(cudaSetDevice(h->device));
+    ViewDev VK, VF; FvDev DK, DF;
+    int rc;
+    if ((rc = stage_view(h, 0, kf, &VK)) || (rc = stage_view(h, 1, f, &VF))) return rc;
+    if ((rc = stage_fv(h, 0, fv_kf, kf->on_device, &DK)) || (rc = stage_fv(h, 1, fv_f, f->on_device, &DF))) return rc;
+    const int nk = kf->n, nf = f->n;
+    *nmatches = 0;
+    for (int i = 0; i < nf; ++i) match_f[i] = -1;
+    if (nk == 0 || nf == 0 || DK.n_nodes == 0 || DF.n_nodes == 0) return PLVS_OK;
+    cudaStream_t st = h->stream;
+    const uint8_t* dh = has_mp_kf;
+    if (!kf->on_device) {
+        if ((rc = h->d_has[0].alloc(nk))) return rc;
+        PLVS_CUDA(cudaMemcpyAsync(h->d_has[0].p, has_mp_kf, nk, cudaMemcpyHostToDevice, st)); dh = h->d_has[0].p;
+    }
+    if ((rc = h->p_assign.alloc(nf)) || (rc = h->d_assign.alloc(nf)) || (rc = h->p_result.alloc(4))) return rc;
+    h->timer.begin(PLVS_MATCH_K_BOW, st);
+    k_fill_i32<<<div_up(nf, 256), 256, 0, st>>>(h->d_assign.p, nf, -1);
+    k_bow<<<div_up(DK.n_nodes, 8), 256, 0, st>>>(VK, VF, DK, DF, dh, nn_ratio, h->d_assign.p);
+    k_tri_finish<<<1, 1024, 0, st>>>(VF.keys, VK.keys, nf, check_orientation, h->d_assign.p, h->p_assign.d, h->p_result.d, 1);
+    h->timer.end(st);
+    PLVS_CUDA(cudaGetLastError());
+    PLVS_CUDA(cudaStreamSynchronize(st));
+    h->timer.collect();
+    std::memcpy(match_f, h->p_assign.h, (size_t)nf * 4);
     *nmatches = h->p_result.h[0];
     h->last_launches = 3;
     return PLVS_OK;

@@ -127,6 +127,18 @@ class ORBmatcher:
         _lib.check(rc, "plvs_match_projection_last")
         return nm.value, assign[:Cur.n]
 
+    def SearchByBoW(self, KF, F, fv_kf, fv_f, has_mp_kf):
+        """SearchByBoW(KeyFramePtr&, Frame&, vector<MapPointPtr>&) (src/ORBmatcher.cc:300-506) -> (nmatches, match_f[F.N]) with
+        match_f[i] = keyframe feature whose map point goes to frame feature i, or -1."""
+        m = np.full(max(F.n, 1), -1, np.int32)
+        nm = C.c_int()
+        vk, vf = KF.view(), F.view()
+        sk, sf = featvec_struct(fv_kf), featvec_struct(fv_f)
+        h = np.ascontiguousarray(has_mp_kf, np.uint8)
+        _lib.check(self._lib.plvs_match_bow(self._h, C.byref(vk), C.byref(vf), C.byref(sk), C.byref(sf), h.ctypes.data_as(C.c_void_p),
+                                            self.mfNNratio, int(self.mbCheckOrientation), m.ctypes.data_as(C.c_void_p), C.byref(nm)), "plvs_match_bow")
+        return nm.value, m[:F.n]
+
     def Fuse(self, KF, queries, th=3.0, inv_level_sigma2=None):
         """Search part of Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:1340-1406) -> (nFused, best_idx[nq], best_dist[nq]).
         The caller applies bestDist<=TH_LOW and the Replace/AddObservation bookkeeping in query order."""

@@ -272,6 +272,34 @@ public:
         return nmatches;
     }
 
+    // int SearchByBoW(KeyFramePtr& pKF, Frame& F, std::vector<MapPointPtr>& vpMapPointMatches)   (src/ORBmatcher.cc:300-506)
+    template <class KeyFramePtr, class FrameT, class MapPointPtr>
+    int SearchByBoW(KeyFramePtr& pKF, FrameT& F, std::vector<MapPointPtr>& vpMapPointMatches)
+    {
+        struct Flat { std::vector<uint32_t> ids; std::vector<int32_t> off, feat; plvs_featvec fv; };
+        auto flatten = [](const auto& featVec, Flat& f) {
+            f.off.push_back(0);
+            for (const auto& kv : featVec) {
+                f.ids.push_back(kv.first);
+                for (unsigned i : kv.second) f.feat.push_back((int32_t)i);
+                f.off.push_back((int32_t)f.feat.size());
+            }
+            f.fv = plvs_featvec{(int32_t)f.ids.size(), f.ids.data(), f.off.data(), f.feat.data()};
+        };
+        Flat fk, ff;
+        flatten(pKF->mFeatVec, fk); flatten(F.mFeatVec, ff);
+        const std::vector<MapPointPtr> vpMapPointsKF = pKF->GetMapPointMatches();
+        std::vector<uint8_t> has(pKF->N);
+        for (int i = 0; i < pKF->N; ++i) has[i] = (vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad()) ? 1 : 0;
+        const plvs_frame_view vk = view_of(*pKF, pKF->mvKeysUn, pKF->mDescriptors), vf = view_of(F, F.mvKeysUn, F.mDescriptors);
+        std::vector<int32_t> m(F.N + 1, -1);
+        int nmatches = 0;
+        plvs_shim::check(plvs_match_bow(h_, &vk, &vf, &fk.fv, &ff.fv, has.data(), mfNNratio, mbCheckOrientation ? 1 : 0, m.data(), &nmatches), "plvs_match_bow");
+        vpMapPointMatches = std::vector<MapPointPtr>(F.N, static_cast<MapPointPtr>(nullptr));
+        for (int i = 0; i < F.N; ++i) if (m[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[m[i]];
+        return nmatches;
+    }
+
     // int Fuse(KeyFramePtr& pKF, const vector<MapPointPtr>& vpMapPoints, const float th=3.0, const bool bRight=false)
     // (src/ORBmatcher.cc:1244-1435).  The gates before the search run here with the reference's own expressions (:1277-1338),
     // the window search runs on the device (plvs_match_fuse, independent per map point), and the Replace / AddObservation /

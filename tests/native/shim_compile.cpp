@@ -35,6 +35,7 @@ typedef std::shared_ptr<MapPoint> MapPointPtr;
 static float standin_dist(const V3& p, const V3& o) { const float d[3] = {p.v[0] - o.v[0], p.v[1] - o.v[1], p.v[2] - o.v[2]}; return d[0] * d[0] + d[1] * d[1] + d[2] * d[2]; }
 static bool standin_view_gate(const V3&, const V3&, const V3&, float) { return false; }
 struct Frame {
+    std::map<unsigned, std::vector<unsigned>> mFeatVec;
     int N = 0; std::vector<cv::KeyPoint> mvKeys, mvKeysUn; cv::Mat mDescriptors; std::vector<float> mvuRight, mvScaleFactors, mvLevelSigma2;
     std::vector<MapPointPtr> mvpMapPoints; std::vector<bool> mvbOutlier; float mbf = 40, mb = 0.08f; Camera* mpCamera = nullptr; Pose pose;
     static float mnMinX, mnMinY, mnMaxX, mnMaxY, mfGridElementWidthInv, mfGridElementHeightInv;
@@ -42,7 +43,7 @@ struct Frame {
 };
 float Frame::mnMinX = 0, Frame::mnMinY = 0, Frame::mnMaxX = 640, Frame::mnMaxY = 480, Frame::mfGridElementWidthInv = 0.1f, Frame::mfGridElementHeightInv = 0.1f;
 struct KeyFrame : Frame {
-    std::map<unsigned, std::vector<unsigned>> mFeatVec;
+    std::vector<MapPointPtr> GetMapPointMatches() const { return mvpMapPoints; }
     MapPointPtr GetMapPoint(int i) const { return mvpMapPoints[i]; }
     std::vector<float> mvInvLevelSigma2 = std::vector<float>(8, 1.f);
     V3 GetCameraCenter() const { return V3{{0, 0, 0}}; }
@@ -69,6 +70,7 @@ extern "C" int shim_instantiate(int run)
     std::vector<std::pair<size_t, size_t>> pairs;
     int c = m.SearchForTriangulation(k1, k2, pairs, false, false);
     c += m.Fuse(k1, mps, 3.0f, false);
+    c += m.SearchByBoW(k1, F, mps);
     chisel_server::ChiselServerParams p; chisel_server::ChiselServer cs(p);
     cs.SetDepthCameraInfo(500, 500, 320, 240, 640, 480);
     Eigen::Affine3f T; cs.SetDepthPose(T);

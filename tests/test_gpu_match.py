@@ -208,3 +208,22 @@ def test_fuse(frames, with_uright, dup, th):
         assert n == rn and np.array_equal(np.where(bd <= 50, bi, -1), ridx)
     n0, bi0, bd0 = ORBmatcher(0.6, True).Fuse(kf, q[:0], th, inv)
     assert n0 == 0 and len(bi0) == 0
+
+
+@pytest.mark.parametrize("nodes", [16, 128, 1024])
+def test_search_by_bow(frames, nodes):
+    """ORBmatcher::SearchByBoW(KF, F) (§8f rank 1): CUDA == oracle == the reference's own ORBmatcher.cc"""
+    K, fr = frames
+    for a, b in ((0, 1), (0, 2)):
+        kf, f = fr[a][0], fr[b][0]
+        fvK, fvF = featvec(scenario.node_ids(kf.desc, nodes)), featvec(scenario.node_ids(f.desc, nodes))
+        has = (np.random.default_rng(nodes + a + b).random(kf.n) < 0.7).astype(np.uint8)
+        for ratio in (0.7, 0.9):
+            for check in (True, False):
+                n, m = ORBmatcher(ratio, check).SearchByBoW(kf, f, fvK, fvF, has)
+                on, om = OM.search_by_bow(kf, f, fvK, fvF, has, ratio, check)
+                assert n == on and np.array_equal(m, om)
+                if OM.ref_available():
+                    rn, rm = OM.ref_search_by_bow(kf, f, fvK, fvF, has, ratio, check)
+                    assert n == rn and np.array_equal(m, rm)
+        assert n > 100

@@ -130,3 +130,19 @@ def test_fuse(frames, with_uright, dup, th):
     rn, ridx = OM.ref_fuse(kf, q, z, K["bf"], th, tab.inv_sigma2)
     assert n == rn and np.array_equal(np.where(bd <= 50, bi, -1), ridx)
     assert n > 300
+
+
+@pytest.mark.parametrize("nodes", [16, 128, 1024])
+def test_search_by_bow(frames, nodes):
+    """SearchByBoW(KF, F): 16 nodes => ~125 features per node, i.e. long chains of claims inside a node"""
+    K, fr = frames
+    for a, b in ((0, 1), (0, 2)):
+        kf, f = fr[a][0], fr[b][0]
+        fvK, fvF = featvec(scenario.node_ids(kf.desc, nodes)), featvec(scenario.node_ids(f.desc, nodes))
+        has = (np.random.default_rng(nodes + a + b).random(kf.n) < 0.7).astype(np.uint8)
+        for ratio in (0.7, 0.9):
+            for check in (True, False):
+                n, m = OM.search_by_bow(kf, f, fvK, fvF, has, ratio, check)
+                rn, rm = OM.ref_search_by_bow(kf, f, fvK, fvF, has, ratio, check)
+                assert n == rn and np.array_equal(m, rm)
+        assert n > 100
