@@ -236,6 +236,15 @@ int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const pl
                              int only_stereo, int coarse, int check_orientation,
                              int32_t* match12, int* nmatches);
 
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFramePtr& pKF, const set<MapPointPtr>& sAlreadyFound, th, ORBdist)
+ * (src/ORBmatcher.cc:1996-2122), Tracking::Relocalization.  One query per keyframe map point that is not bad, not in
+ * sAlreadyFound and passed the caller-side projection / distance gates (:2024-2046): u, v = project(Tcw * Xw), invz unused (set
+ * it >= 0), last_octave = PredictScale(dist3D, &CurrentFrame), angle = pKF->mvKeysUn[i].angle, flags = PLVS_Q_OBS_POSITIVE.
+ * claimed_in[i] != 0 <=> CurrentFrame.mvpMapPoints[i] is non-null (ANY map point blocks here, :2066).  assign / nmatches as in
+ * plvs_match_projection_last. */
+int plvs_match_projection_reloc(plvs_match* h, const plvs_frame_view* cur, const plvs_last_query* q, int nq, float th, int orb_dist,
+                                int check_orientation, const uint8_t* claimed_in, int32_t* assign, int* nmatches);
+
 /* ORBmatcher::SearchByBoW(KeyFramePtr& pKF, Frame& F, vector<MapPointPtr>& vpMapPointMatches) (src/ORBmatcher.cc:300-506),
  * RGB-D / rectified stereo (Nleft == -1): Tracking::TrackReferenceKeyFrame and Relocalization.  fv_kf / fv_f = pKF->mFeatVec /
  * F.mFeatVec flattened; has_mp_kf[i] != 0 <=> pKF->GetMapPointMatches()[i] is non-null and not bad; nn_ratio / check_orientation

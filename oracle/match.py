@@ -209,3 +209,24 @@ def search_by_bow(K, F, fvK, fvF, has_mp, nn_ratio=0.7, check_ori=True):
 
 def ref_search_by_bow(K, F, fvK, fvF, has_mp, nn_ratio=0.7, check_ori=True):
     return _bow_call(_ref_lib().ref_search_by_bow, K, F, fvK, fvF, has_mp, nn_ratio, check_ori)
+
+
+# ---- ORBmatcher::SearchByProjection(Cur, KF, sAlreadyFound, th, ORBdist) (relocalisation) -----------------------------
+
+def _reloc_call(fn, Cur, queries, th, orb_dist, check_ori, claimed):
+    q = np.ascontiguousarray(queries, LAST_QUERY)
+    v = Cur.view()
+    assign = np.full(max(Cur.n, 1), -1, np.int32)
+    cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    n = fn(C.byref(v), q.ctypes.data_as(C.c_void_p), len(q), th, int(orb_dist), int(check_ori), cl.ctypes.data_as(C.c_void_p) if cl is not None else None,
+           assign.ctypes.data_as(C.c_void_p))
+    return n, assign[:Cur.n]
+
+
+def search_by_projection_reloc(Cur, queries, th, orb_dist, check_ori=True, claimed=None):
+    return _reloc_call(_setup().orc_search_by_projection_reloc, Cur, queries, th, orb_dist, check_ori, claimed)
+
+
+def ref_search_by_projection_reloc(Cur, queries, th, orb_dist, check_ori=True, claimed=None):
+    return _reloc_call(_ref_lib().ref_search_by_projection_reloc, Cur, queries, th, orb_dist, check_ori, claimed)

@@ -283,6 +283,49 @@ int orc_search_for_triangulation(const FrameView* K1, const FrameView* K2, const
     return nmatches;
 }
 
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFramePtr& pKF, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1996-2122):
+// queries = the keyframe's map points that passed the caller-side gates, pre-projected (LastQuery records, last_octave = predicted
+// level).  Level window [l-1, l+1], no right-coordinate gate, ANY non-null mvpMapPoints entry blocks, accept if best <= ORBdist.
+int orc_search_by_projection_reloc(const FrameView* C, const LastQuery* q, int nq, float th, int orb_dist, int check_ori,
+                                   const uint8_t* claimed_in, int32_t* assign)
+{
+    Grid grid(C);
+    std::vector<int> holder(C->n, -1);
+    if (claimed_in) for (int i = 0; i < C->n; ++i) if (claimed_in[i]) holder[i] = -2;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = 0;
+    std::vector<int> cand;
+    for (int iq = 0; iq < nq; ++iq) {
+        const LastQuery& m = q[iq];
+        if (m.u < C->min_x || m.u > C->max_x) continue;
+        if (m.v < C->min_y || m.v > C->max_y) continue;
+        const int lvl = m.last_octave;
+        const float radius = th * C->scale_factors[lvl];
+        grid.in_area(m.u, m.v, radius, lvl - 1, lvl + 1, cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : cand) {
+            if (holder[i2] != -1) continue;
+            const int dist = hamming(m.desc, C->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= orb_dist) {
+            holder[bestIdx2] = iq;
+            ++nmatches;
+            if (check_ori) rotHist[rot_bin(m.angle, C->keys[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (check_ori) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i)
+            if (i != i1 && i != i2 && i != i3)
+                for (int idx : rotHist[i]) { holder[idx] = -1; --nmatches; }
+    }
+    for (int i = 0; i < C->n; ++i) assign[i] = holder[i] >= 0 ? holder[i] : -1;
+    return nmatches;
+}
+
 // ORBmatcher::SearchByBoW(KeyFramePtr& pKF, Frame& F, vector<MapPointPtr>& vpMapPointMatches) (src/ORBmatcher.cc:300-506),
 // Nleft == -1 branch: merge-walk of the two FeatureVectors; inside a shared node the keyframe features that carry a (good)
 // map point are visited in order, each takes the best frame feature of the node that is still unmatched (best/second with

@@ -150,6 +150,37 @@ int ref_search_for_triangulation(const FrameView* K1v, const FrameView* K2v, con
     return n;
 }
 
+// ORBmatcher::SearchByProjection(Frame& Cur, KeyFramePtr& pKF, const set<MapPointPtr>& sAlreadyFound, th, ORBdist)   src/ORBmatcher.cc:1996-2122
+// every third query is handed over as "already found" when skip_found != 0 (it must then not appear in the result)
+int ref_search_by_projection_reloc(const FrameView* Cv, const LastQuery* q, int nq, float th, int orb_dist, int check_ori,
+                                   const uint8_t* claimed_in, int32_t* assign)
+{
+    GeometricCamera cam;
+    Frame Cur; fill(Cur, Cv); Cur.mpCamera = &cam;
+    MapPoint pre;
+    Cur.mvpMapPoints.assign(Cv->n, nullptr);
+    if (claimed_in) for (int i = 0; i < Cv->n; ++i) if (claimed_in[i]) Cur.mvpMapPoints[i] = &pre;
+    KeyFrame K; K.N = nq; K.mpCamera = &cam;
+    K.mvKeysUn.resize(nq); K.mvpMapPoints.assign(nq, nullptr);
+    std::vector<std::unique_ptr<MapPoint>> mps(nq);
+    std::unordered_map<MapPointPtr, int> index;
+    for (int i = 0; i < nq; ++i) {
+        mps[i].reset(new MapPoint());
+        MapPoint& m = *mps[i];
+        m.pos = Eigen::Vector3f(q[i].u, q[i].v, 1.f);
+        m.predictedLevel = q[i].last_octave;
+        m.desc = desc_mat(q[i].desc);
+        K.mvpMapPoints[i] = &m; index[&m] = i;
+        K.mvKeysUn[i].angle = q[i].angle;
+    }
+    ORBmatcher matcher(0.9f, check_ori != 0);
+    std::set<MapPointPtr> found;
+    KeyFramePtr pk = &K;
+    const int n = matcher.SearchByProjection(Cur, pk, found, th, orb_dist);
+    for (int i = 0; i < Cv->n; ++i) { auto it = index.find(Cur.mvpMapPoints[i]); assign[i] = it == index.end() ? -1 : it->second; }
+    return n;
+}
+
 // ORBmatcher::SearchByBoW(KeyFramePtr& pKF, Frame& F, vector<MapPointPtr>& vpMapPointMatches)   src/ORBmatcher.cc:300-506
 int ref_search_by_bow(const FrameView* Kv, const FrameView* Fv, const FeatVec* fvK, const FeatVec* fvF, const uint8_t* has_mp,
                       float nn_ratio, int check_ori, int32_t* match_f)

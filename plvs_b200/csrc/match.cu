@@ -279,7 +279,7 @@ __device__ __forceinline__ void cluster_sync_all()
 template <int MODE, bool SMEM>
 __global__ void __cluster_dims__(kResolveCtas, 1, 1) __launch_bounds__(1024)
 k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int cap, const void* __restrict__ queries, int nq,
-          const plvs_keypoint* __restrict__ keys, int n, const uint8_t* __restrict__ claimed_in, float nn_ratio, int check_ori,
+          const plvs_keypoint* __restrict__ keys, int n, const uint8_t* __restrict__ claimed_in, float nn_ratio, int check_ori, int th_high,
           int* claims /*3*n, L2*/, int* target /*nq*/, int* flags /*[4] rotating change flags, zeroed by the host*/,
           int32_t* assign /*n, device*/, int32_t* assign_out /*n, mapped host*/, int* result /*[0]=nmatches,[1]=rounds*/, int per_cta,
           int lpq /*lanes per query: power of two <= 32, per_cta * lpq <= 1024*/, long long* trace /*dev tool: 32 clock64 stamps per CTA, or null*/)
@@ -371,7 +371,7 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
         if (mine && lane == 0) {
             int t = -1;
             const int bestDist = k1 == 0xffffffffu ? 256 : (int)(k1 >> 16);
-            if (bestDist <= TH_HIGH) {
+            if (bestDist <= th_high) {
                 const uint32_t e1 = SMEM ? s_list[qi * stride + (k1 & 0xffffu)] : cand[(size_t)q * cap + (k1 & 0xffffu)];
                 if (MODE == 0) {
                     int bestDist2 = 256, bestLevel2 = -1;
@@ -824,7 +824,7 @@ int stage_view(plvs_match* h, int slot, const plvs_frame_view* v, ViewDev* out)
 template <int MODE>
 int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_t qsize, int nq, float th, float nn_ratio,
                    int far_points, float th_far, int forward, int backward, int check_ori,
-                   const uint8_t* claimed_in, int32_t* assign, int* nmatches)
+                   const uint8_t* claimed_in, int32_t* assign, int* nmatches, int th_high = TH_HIGH)
 {
     if (!h || !F || !assign || !nmatches || nq < 0 || (nq && !q)) { set_error("null/invalid argument"); return PLVS_EINVAL; }
     std::lock_guard<std::mutex> lock(h->mu);
@@ -881,10 +881,10 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
                     PLVS_CUDA(cudaFuncSetAttribute(k_resolve<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     attr_set[MODE] = true;
                 }
-                k_resolve<MODE, true><<<kResolveCtas, 1024, smem, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
+                k_resolve<MODE, true><<<kResolveCtas, 1024, smem, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori, th_high,
                                                                         h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta, lpq, h->d_trace.p);
             } else if (per_cta <= 1024) {
-                k_resolve<MODE, false><<<kResolveCtas, 1024, smem_small, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori,
+                k_resolve<MODE, false><<<kResolveCtas, 1024, smem_small, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori, th_high,
                                                                       h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta, lpq, h->d_trace.p);
             } else { set_error("more than %d queries per search are not supported", kResolveCtas * 1024); return PLVS_EINVAL; }
         }
@@ -995,6 +995,19 @@ int plvs_match_projection_last(plvs_match* h, const plvs_frame_view* cur, const 
                                int forward, int backward, int check_orientation, const uint8_t* claimed_in, int32_t* assign, int* nmatches)
 {
     return run_projection<1>(h, cur, q, sizeof(plvs_last_query), nq, th, 0.f, 0, 0.f, forward, backward, check_orientation, claimed_in, assign, nmatches);
+}
+
+int plvs_match_projection_reloc(plvs_match* h, const plvs_frame_view* cur, const plvs_last_query* q, int nq, float th, int orb_dist,
+                                int check_orientation, const uint8_t* claimed_in, int32_t* assign, int* nmatches)
+{
+    // the relocalisation search is the last-frame search with: level window [l-1, l+1] around the PREDICTED level, no right-coordinate
+    // gate (src/ORBmatcher.cc:2062-2076 has none), every non-null mvpMapPoints entry blocking, and ORBdist instead of TH_HIGH
+    if (!cur) { set_error("null argument"); return PLVS_EINVAL; }
+    if (orb_dist < 0 || orb_dist > 256) { set_error("ORBdist out of range"); return PLVS_EINVAL; }
+    for (int i = 0; i < nq; ++i) if (q && !(q[i].flags & PLVS_Q_OBS_POSITIVE)) { set_error("reloc query %d: PLVS_Q_OBS_POSITIVE must be set (any claim blocks)", i); return PLVS_EINVAL; }
+    plvs_frame_view v = *cur;
+    v.uright = nullptr;
+    return run_projection<1>(h, &v, q, sizeof(plvs_last_query), nq, th, 0.f, 0, 0.f, 0, 0, check_orientation, claimed_in, assign, nmatches, orb_dist);
 }
 
 int plvs_match_fuse(plvs_match* h, const plvs_frame_view* kf, const float* inv_level_sigma2, const plvs_fuse_query* q, int nq, float th,

@@ -127,6 +127,19 @@ class ORBmatcher:
         _lib.check(rc, "plvs_match_projection_last")
         return nm.value, assign[:Cur.n]
 
+    def SearchByProjectionReloc(self, Cur, queries, th, ORBdist, claimed=None):
+        """SearchByProjection(Frame& Cur, KeyFramePtr& pKF, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1996-2122) with the
+        keyframe's map points pre-projected (LAST_QUERY records: last_octave = predicted level, flags = 1)."""
+        q = np.ascontiguousarray(queries, LAST_QUERY)
+        assign = np.full(max(Cur.n, 1), -1, np.int32)
+        nm = C.c_int()
+        v = Cur.view()
+        cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+        _lib.check(self._lib.plvs_match_projection_reloc(self._h, C.byref(v), q.ctypes.data_as(C.c_void_p), len(q), th, int(ORBdist), int(self.mbCheckOrientation),
+                                                         cl.ctypes.data_as(C.c_void_p) if cl is not None else None, assign.ctypes.data_as(C.c_void_p), C.byref(nm)),
+                   "plvs_match_projection_reloc")
+        return nm.value, assign[:Cur.n]
+
     def SearchByBoW(self, KF, F, fv_kf, fv_f, has_mp_kf):
         """SearchByBoW(KeyFramePtr&, Frame&, vector<MapPointPtr>&) (src/ORBmatcher.cc:300-506) -> (nmatches, match_f[F.N]) with
         match_f[i] = keyframe feature whose map point goes to frame feature i, or -1."""

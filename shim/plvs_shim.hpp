@@ -272,6 +272,51 @@ public:
         return nmatches;
     }
 
+    // int SearchByProjection(Frame& CurrentFrame, KeyFramePtr& pKF, const std::set<MapPointPtr>& sAlreadyFound, const float th, const int ORBdist)
+    // (src/ORBmatcher.cc:1996-2122, Tracking::Relocalization)
+    template <class FrameT, class KeyFramePtr, class SetT>
+    int SearchByProjection(FrameT& CurrentFrame, KeyFramePtr& pKF, const SetT& sAlreadyFound, const float th, const int ORBdist)
+    {
+        const auto Tcw = CurrentFrame.GetPose();
+        const auto Ow = Tcw.inverse().translation();
+        const auto vpMPs = pKF->GetMapPointMatches();
+        std::vector<plvs_last_query> q;
+        std::vector<size_t> src;
+        for (size_t i = 0; i < vpMPs.size(); ++i) {
+            auto pMP = vpMPs[i];
+            if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+            const auto x3Dw = pMP->GetWorldPos();
+            const auto x3Dc = Tcw * x3Dw;
+            const auto uv = CurrentFrame.mpCamera->project(x3Dc);
+            if (uv(0) < FrameT::mnMinX || uv(0) > FrameT::mnMaxX) continue;
+            if (uv(1) < FrameT::mnMinY || uv(1) > FrameT::mnMaxY) continue;
+#ifdef PLVS_SHIM_STANDIN
+            const float dist3D = standin_dist(x3Dw, Ow);
+#else
+            const Eigen::Vector3f PO = x3Dw - Ow;
+            const float dist3D = PO.norm();
+#endif
+            if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+            plvs_last_query e{};
+            e.u = uv(0); e.v = uv(1); e.invz = 1.f;
+            e.last_octave = pMP->PredictScale(dist3D, &CurrentFrame);
+            e.angle = pKF->mvKeysUn[i].angle;
+            e.flags = PLVS_Q_OBS_POSITIVE;                      // any map point written here blocks later ones (:2066)
+            const cv::Mat d = pMP->GetDescriptor();
+            std::memcpy(e.desc, d.data, 32);
+            q.push_back(e); src.push_back(i);
+        }
+        std::vector<uint8_t> claimed(CurrentFrame.N, 0);
+        for (int i = 0; i < CurrentFrame.N; ++i) claimed[i] = CurrentFrame.mvpMapPoints[i] ? 1 : 0;
+        std::vector<int32_t> assign(CurrentFrame.N + 1, -1);
+        int nmatches = 0;
+        const plvs_frame_view v = view_of(CurrentFrame, CurrentFrame.mvKeysUn, CurrentFrame.mDescriptors);
+        plvs_shim::check(plvs_match_projection_reloc(h_, &v, q.data(), (int)q.size(), th, ORBdist, mbCheckOrientation ? 1 : 0, claimed.data(), assign.data(), &nmatches),
+                         "plvs_match_projection_reloc");
+        for (int i = 0; i < CurrentFrame.N; ++i) if (assign[i] >= 0) CurrentFrame.mvpMapPoints[i] = vpMPs[src[assign[i]]];
+        return nmatches;
+    }
+
     // int SearchByBoW(KeyFramePtr& pKF, Frame& F, std::vector<MapPointPtr>& vpMapPointMatches)   (src/ORBmatcher.cc:300-506)
     template <class KeyFramePtr, class FrameT, class MapPointPtr>
     int SearchByBoW(KeyFramePtr& pKF, FrameT& F, std::vector<MapPointPtr>& vpMapPointMatches)

@@ -3,6 +3,7 @@
 #define PLVS_SHIM_STANDIN
 #include <map>
 #include <memory>
+#include <set>
 #include <vector>
 #include "../../shim/standin.hpp"
 
@@ -28,6 +29,7 @@ struct MapPoint {
     float GetMaxDistanceInvariance() const { return 1e9f; }
     bool IsInKeyFrame(const std::shared_ptr<KeyFrame>&) const { return false; }
     int PredictScale(float, const std::shared_ptr<KeyFrame>&) const { return 0; }
+    int PredictScale(float, const void*) const { return 0; }
     void Replace(const std::shared_ptr<MapPoint>&) {}
     void AddObservation(const std::shared_ptr<KeyFrame>&, int) {}
 };
@@ -71,6 +73,8 @@ extern "C" int shim_instantiate(int run)
     int c = m.SearchForTriangulation(k1, k2, pairs, false, false);
     c += m.Fuse(k1, mps, 3.0f, false);
     c += m.SearchByBoW(k1, F, mps);
+    std::set<MapPointPtr> found;
+    c += m.SearchByProjection(F, k1, found, 10.f, 100);
     chisel_server::ChiselServerParams p; chisel_server::ChiselServer cs(p);
     cs.SetDepthCameraInfo(500, 500, 320, 240, 640, 480);
     Eigen::Affine3f T; cs.SetDepthPose(T);

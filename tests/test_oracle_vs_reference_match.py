@@ -146,3 +146,18 @@ def test_search_by_bow(frames, nodes):
                 rn, rm = OM.ref_search_by_bow(kf, f, fvK, fvF, has, ratio, check)
                 assert n == rn and np.array_equal(m, rm)
         assert n > 100
+
+
+@pytest.mark.parametrize("th,orb_dist", [(10.0, 100), (3.0, 64), (15.0, 50)])
+def test_projection_reloc(frames, th, orb_dist):
+    """SearchByProjection(Cur, KF, sAlreadyFound, th, ORBdist): any non-null map point blocks, window [l-1, l+1], no xR gate"""
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    q, _ = scenario.last_queries(last, cur, K, Tl, Tc)
+    q = np.concatenate([q, q[::2]]); q["flags"] = 1; q["invz"] = 1
+    claimed = (np.random.default_rng(0).random(cur.n) < 0.2).astype(np.uint8)
+    for check in (True, False):
+        n, a = OM.search_by_projection_reloc(cur, q, th, orb_dist, check, claimed)
+        rn, ra = OM.ref_search_by_projection_reloc(cur, q, th, orb_dist, check, claimed)
+        assert n == rn and np.array_equal(a, ra)
+    assert n > 300
