@@ -271,6 +271,12 @@ typedef struct {
 int plvs_match_fuse(plvs_match* h, const plvs_frame_view* kf, const float* inv_level_sigma2,
                     const plvs_fuse_query* q, int nq, float th,
                     int32_t* best_idx, int32_t* best_dist, int* nfused);
+/* ORBmatcher::Fuse(KeyFramePtr& pKF, Sophus::Sim3f& Scw, const vector<MapPointPtr>& vpPoints, float th, vector<MapPointPtr>&
+ * vpReplacePoint) (src/ORBmatcher.cc:1437-1553, LoopClosing::SearchAndFuse): the same search without the chi-square gate
+ * (:1514-1531); `ur` of the queries is ignored.  The caller applies bestDist <= TH_LOW and fills vpReplacePoint / adds the
+ * observation (:1534-1548). */
+int plvs_match_fuse_sim3(plvs_match* h, const plvs_frame_view* kf, const plvs_fuse_query* q, int nq, float th,
+                         int32_t* best_idx, int32_t* best_dist, int* nfused);
 
 /* Device view of one frame's pyramid (all levels) of an extractor handle: what Frame::ComputeStereoMatches
  * reads through mpORBextractorLeft/Right->mvImagePyramid (src/Frame.cc:1886,1914). */

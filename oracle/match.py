@@ -230,3 +230,25 @@ def search_by_projection_reloc(Cur, queries, th, orb_dist, check_ori=True, claim
 
 def ref_search_by_projection_reloc(Cur, queries, th, orb_dist, check_ori=True, claimed=None):
     return _reloc_call(_ref_lib().ref_search_by_projection_reloc, Cur, queries, th, orb_dist, check_ori, claimed)
+
+
+def fuse_sim3(K, queries, th):
+    l = _setup()
+    q = np.ascontiguousarray(queries, FUSE_QUERY)
+    v = K.view()
+    bi = np.full(max(len(q), 1), -1, np.int32); bd = np.full(max(len(q), 1), 256, np.int32)
+    l.orc_fuse_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    n = l.orc_fuse_sim3(C.byref(v), q.ctypes.data_as(C.c_void_p), len(q), th, bi.ctypes.data_as(C.c_void_p), bd.ctypes.data_as(C.c_void_p))
+    return n, bi[:len(q)], bd[:len(q)]
+
+
+def ref_fuse_sim3(K, queries, z, th, pre_mp=None):
+    l = _ref_lib()
+    q = np.ascontiguousarray(queries, FUSE_QUERY); z = np.ascontiguousarray(z, np.float32)
+    v = K.view()
+    out = np.full(max(len(q), 1), -1, np.int32)
+    pm = None if pre_mp is None else np.ascontiguousarray(pre_mp, np.uint8)
+    l.ref_fuse_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    n = l.ref_fuse_sim3(C.byref(v), q.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), len(q), th,
+                        pm.ctypes.data_as(C.c_void_p) if pm is not None else None, out.ctypes.data_as(C.c_void_p))
+    return n, out[:len(q)]

@@ -385,7 +385,17 @@ int orc_search_by_bow(const FrameView* K, const FrameView* F, const FeatVec* fvK
 // so the queries are independent of each other.
 struct FuseQuery { float u, v, ur; int32_t level; uint8_t desc[32]; };
 
+static int fuse_search(const FrameView* K, const float* inv_level_sigma2, const FuseQuery* q, int nq, float th, int32_t* best_idx, int32_t* best_dist, bool chi2);
 int orc_fuse(const FrameView* K, const float* inv_level_sigma2, const FuseQuery* q, int nq, float th, int32_t* best_idx, int32_t* best_dist)
+{
+    return fuse_search(K, inv_level_sigma2, q, nq, th, best_idx, best_dist, true);
+}
+// Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:1437-1553): the same search without the chi-square gate
+int orc_fuse_sim3(const FrameView* K, const FuseQuery* q, int nq, float th, int32_t* best_idx, int32_t* best_dist)
+{
+    return fuse_search(K, nullptr, q, nq, th, best_idx, best_dist, false);
+}
+static int fuse_search(const FrameView* K, const float* inv_level_sigma2, const FuseQuery* q, int nq, float th, int32_t* best_idx, int32_t* best_dist, bool chi2)
 {
     Grid grid(K);
     std::vector<int> cand;
@@ -400,7 +410,8 @@ int orc_fuse(const FrameView* K, const float* inv_level_sigma2, const FuseQuery*
             const KeyPoint& kp = K->keys[idx];
             const int kpLevel = kp.octave;
             if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
-            if (K->uright && K->uright[idx] >= 0) {
+            if (!chi2) {
+            } else if (K->uright && K->uright[idx] >= 0) {
                 const float ex = m.u - kp.x, ey = m.v - kp.y, er = m.ur - K->uright[idx];
                 const float e2 = ex * ex + ey * ey + er * er;
                 if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;

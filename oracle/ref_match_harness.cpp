@@ -241,4 +241,38 @@ int ref_fuse(const FrameView* Kv, const float* inv_level_sigma2, const FuseQuery
     return n;
 }
 
+// ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint)   src/ORBmatcher.cc:1437-1553   (Scw = identity similarity)
+// pre_mp[i] != 0: the keyframe already holds a map point at keypoint i (=> the vpReplacePoint branch)
+int ref_fuse_sim3(const FrameView* Kv, const FuseQuery* q, const float* z, int nq, float th, const uint8_t* pre_mp, int32_t* fused_idx)
+{
+    GeometricCamera cam;
+    KeyFrame K; fill(K, Kv); K.mpCamera = &cam;
+    K.mvpMapPoints.assign(Kv->n, nullptr);
+    std::vector<std::unique_ptr<MapPoint>> held(Kv->n);
+    std::unordered_map<MapPointPtr, int> where;
+    if (pre_mp) for (int i = 0; i < Kv->n; ++i) if (pre_mp[i]) { held[i].reset(new MapPoint()); K.mvpMapPoints[i] = held[i].get(); where[held[i].get()] = i; }
+    std::vector<std::unique_ptr<MapPoint>> mps(nq);
+    std::vector<MapPointPtr> vp(nq), repl(nq, nullptr);
+    for (int i = 0; i < nq; ++i) {
+        mps[i].reset(new MapPoint());
+        MapPoint& m = *mps[i];
+        m.pos = Eigen::Vector3f(q[i].u, q[i].v, z[i]);
+        m.normal = m.pos.normalized();
+        m.predictedLevel = q[i].level;
+        m.desc = desc_mat(q[i].desc);
+        vp[i] = &m;
+    }
+    ORBmatcher matcher(0.8f, true);
+    Sophus::Sim3f Scw;
+    KeyFramePtr pk = &K;
+    const int n = matcher.Fuse(pk, Scw, vp, th, repl);
+    for (int i = 0; i < Kv->n; ++i) if (K.mvpMapPoints[i] && !where.count(K.mvpMapPoints[i])) where[K.mvpMapPoints[i]] = i;   // added during the call
+    for (int i = 0; i < nq; ++i) {
+        if (mps[i]->addedIdx >= 0) fused_idx[i] = mps[i]->addedIdx;
+        else if (repl[i] && where.count(repl[i])) fused_idx[i] = where[repl[i]];
+        else fused_idx[i] = -1;
+    }
+    return n;
+}
+
 }  // extern "C"

@@ -196,6 +196,7 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
 // ---------------------------------------------------------------------------------------------
 struct FuseSigma { float inv[PLVS_MAX_LEVELS]; };
 
+template <bool CHI2>
 __global__ void __launch_bounds__(256)
 k_fuse(ViewDev K, FuseSigma sg, const int* __restrict__ cell_start, const int* __restrict__ sorted,
        const plvs_fuse_query* __restrict__ queries, int nq, float th, int32_t* __restrict__ best_idx, int32_t* __restrict__ best_dist,
@@ -223,15 +224,17 @@ k_fuse(ViewDev K, FuseSigma sg, const int* __restrict__ cell_start, const int* _
                 if (!(fabsf(kp.x - u) < radius && fabsf(kp.y - v) < radius)) continue;
                 const int kl = kp.octave;
                 if (kl < lvl - 1 || kl > lvl) continue;
-                const float ex = u - kp.x, ey = v - kp.y;
-                const float kr = K.uright ? K.uright[idx] : -1.f;
-                if (kr >= 0) {
-                    const float er = ur - kr;
-                    const float e2 = ex * ex + ey * ey + er * er;
-                    if ((double)(e2 * sg.inv[kl]) > 7.8) continue;
-                } else {
-                    const float e2 = ex * ex + ey * ey;
-                    if ((double)(e2 * sg.inv[kl]) > 5.99) continue;
+                if (CHI2) {                                  // Fuse(pKF, vpMapPoints, ...) only; the Sim3 overload has no such gate (:1514-1531)
+                    const float ex = u - kp.x, ey = v - kp.y;
+                    const float kr = K.uright ? K.uright[idx] : -1.f;
+                    if (kr >= 0) {
+                        const float er = ur - kr;
+                        const float e2 = ex * ex + ey * ey + er * er;
+                        if ((double)(e2 * sg.inv[kl]) > 7.8) continue;
+                    } else {
+                        const float e2 = ex * ex + ey * ey;
+                        if ((double)(e2 * sg.inv[kl]) > 5.99) continue;
+                    }
                 }
                 const uint32_t key = ((uint32_t)hamming256(a0, a1, K.desc + (size_t)idx * 32) << 20) | (uint32_t)(pos0 + (p - pbeg));
                 if (key < best) { best = key; best_i = idx; }
@@ -1010,10 +1013,10 @@ int plvs_match_projection_reloc(plvs_match* h, const plvs_frame_view* cur, const
     return run_projection<1>(h, &v, q, sizeof(plvs_last_query), nq, th, 0.f, 0, 0.f, 0, 0, check_orientation, claimed_in, assign, nmatches, orb_dist);
 }
 
-int plvs_match_fuse(plvs_match* h, const plvs_frame_view* kf, const float* inv_level_sigma2, const plvs_fuse_query* q, int nq, float th,
-                    int32_t* best_idx, int32_t* best_dist, int* nfused)
+static int fuse_impl(plvs_match* h, const plvs_frame_view* kf, const float* inv_level_sigma2, const plvs_fuse_query* q, int nq, float th,
+                     int32_t* best_idx, int32_t* best_dist, int* nfused, bool chi2)
 {
-    if (!h || !kf || !inv_level_sigma2 || !best_idx || !best_dist || !nfused || nq < 0 || (nq && !q)) { set_error("null/invalid argument"); return PLVS_EINVAL; }
+    if (!h || !kf || (chi2 && !inv_level_sigma2) || !best_idx || !best_dist || !nfused || nq < 0 || (nq && !q)) { set_error("null/invalid argument"); return PLVS_EINVAL; }
     std::lock_guard<std::mutex> lock(h->mu);
     PLVS_CUDA(cudaSetDevice(h->device));
     ViewDev V;
@@ -1037,11 +1040,12 @@ int plvs_match_fuse(plvs_match* h, const plvs_frame_view* kf, const float* inv_l
         h->grid_key = kf->cache_key; h->grid_n = n;
     }
     FuseSigma sg{};
-    for (int i = 0; i < kf->nlevels; ++i) sg.inv[i] = inv_level_sigma2[i];
+    for (int i = 0; i < kf->nlevels; ++i) sg.inv[i] = chi2 ? inv_level_sigma2[i] : 0.f;
     int32_t* d_idx = h->d_assign.p; int32_t* d_dist = d_idx + nq; int* d_nf = reinterpret_cast<int*>(d_dist + nq);
     PLVS_CUDA(cudaMemsetAsync(d_nf, 0, sizeof(int), st));
     h->timer.begin(PLVS_MATCH_K_FUSE, st);
-    k_fuse<<<div_up(nq, 8), 256, 0, st>>>(V, sg, h->d_cell_start.p, h->d_sorted.p, reinterpret_cast<const plvs_fuse_query*>(h->d_query.p), nq, th, d_idx, d_dist, d_nf);
+    if (chi2) k_fuse<true><<<div_up(nq, 8), 256, 0, st>>>(V, sg, h->d_cell_start.p, h->d_sorted.p, reinterpret_cast<const plvs_fuse_query*>(h->d_query.p), nq, th, d_idx, d_dist, d_nf);
+    else k_fuse<false><<<div_up(nq, 8), 256, 0, st>>>(V, sg, h->d_cell_start.p, h->d_sorted.p, reinterpret_cast<const plvs_fuse_query*>(h->d_query.p), nq, th, d_idx, d_dist, d_nf);
     h->timer.end(st);
     ++launches;
     PLVS_CUDA(cudaMemcpyAsync(h->p_assign.h, h->d_assign.p, ((size_t)2 * nq + 1) * 4, cudaMemcpyDeviceToHost, st));
@@ -1097,6 +1101,18 @@ int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const pl
     *nmatches = h->p_result.h[0];
     h->last_launches = 3;
     return PLVS_OK;
+}
+
+int plvs_match_fuse(plvs_match* h, const plvs_frame_view* kf, const float* inv_level_sigma2, const plvs_fuse_query* q, int nq, float th,
+                    int32_t* best_idx, int32_t* best_dist, int* nfused)
+{
+    return fuse_impl(h, kf, inv_level_sigma2, q, nq, th, best_idx, best_dist, nfused, true);
+}
+
+int plvs_match_fuse_sim3(plvs_match* h, const plvs_frame_view* kf, const plvs_fuse_query* q, int nq, float th,
+                         int32_t* best_idx, int32_t* best_dist, int* nfused)
+{
+    return fuse_impl(h, kf, nullptr, q, nq, th, best_idx, best_dist, nfused, false);
 }
 
 int plvs_match_bow(plvs_match* h, const plvs_frame_view* kf, const plvs_frame_view* f, const plvs_featvec* fv_kf, const plvs_featvec* fv_f,

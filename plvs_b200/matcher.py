@@ -152,6 +152,16 @@ class ORBmatcher:
                                             self.mfNNratio, int(self.mbCheckOrientation), m.ctypes.data_as(C.c_void_p), C.byref(nm)), "plvs_match_bow")
         return nm.value, m[:F.n]
 
+    def FuseSim3(self, KF, queries, th):
+        """Search part of Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:1437-1553): no chi-square gate."""
+        q = np.ascontiguousarray(queries, FUSE_QUERY)
+        bi = np.full(max(len(q), 1), -1, np.int32); bd = np.full(max(len(q), 1), 256, np.int32)
+        nf = C.c_int()
+        v = KF.view()
+        _lib.check(self._lib.plvs_match_fuse_sim3(self._h, C.byref(v), q.ctypes.data_as(C.c_void_p), len(q), th,
+                                                  bi.ctypes.data_as(C.c_void_p), bd.ctypes.data_as(C.c_void_p), C.byref(nf)), "plvs_match_fuse_sim3")
+        return nf.value, bi[:len(q)], bd[:len(q)]
+
     def Fuse(self, KF, queries, th=3.0, inv_level_sigma2=None):
         """Search part of Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:1340-1406) -> (nFused, best_idx[nq], best_dist[nq]).
         The caller applies bestDist<=TH_LOW and the Replace/AddObservation bookkeeping in query order."""

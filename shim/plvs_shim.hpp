@@ -30,6 +30,12 @@
 #endif
 
 namespace plvs_shim {
+#ifndef PLVS_SHIM_STANDIN
+template <class Sim3T> inline auto se3_of_sim3(const Sim3T& Scw) { return Sophus::SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale()); }
+#else
+template <class Sim3T> inline auto se3_of_sim3(const Sim3T& Scw) { return standin_se3_of_sim3(Scw); }
+#endif
+
 // colours of a cloud point, when it has them (PointXYZ has none: SetPointsAndColors is a no-op for it, Conversions.h:63-67)
 template <class P> auto point_rgb_impl(const P& pt, float k, float* out, int) -> decltype((void)pt.r, true) { out[0] = pt.r * k; out[1] = pt.g * k; out[2] = pt.b * k; return true; }
 template <class P> bool point_rgb_impl(const P&, float, float*, long) { return false; }
@@ -409,6 +415,62 @@ public:
             } else {
                 pMP->AddObservation(pKF, bestIdx);
                 pKF->AddMapPoint(pMP, bestIdx);
+            }
+            nFused++;
+        }
+        return nFused;
+    }
+
+    // int Fuse(KeyFramePtr& pKF, Sophus::Sim3f& Scw, const vector<MapPointPtr>& vpPoints, float th, vector<MapPointPtr>& vpReplacePoint)
+    // (src/ORBmatcher.cc:1437-1553, LoopClosing::SearchAndFuse): gates here, search on the device (no chi-square gate), bookkeeping here
+    template <class KeyFramePtr, class Sim3T, class MapPointPtr>
+    int Fuse(KeyFramePtr& pKF, Sim3T& Scw, const std::vector<MapPointPtr>& vpPoints, float th, std::vector<MapPointPtr>& vpReplacePoint)
+    {
+        const auto Tcw = plvs_shim::se3_of_sim3(Scw);             // Sophus::SE3f(Scw.rotationMatrix(), Scw.translation()/Scw.scale()) (:1446)
+        const auto Ow = Tcw.inverse().translation();
+        const auto spAlreadyFound = pKF->GetMapPointsUnordered();
+        std::vector<plvs_fuse_query> q;
+        std::vector<size_t> src;
+        for (size_t i = 0; i < vpPoints.size(); ++i) {
+            MapPointPtr pMP = vpPoints[i];
+            if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+            const auto p3Dw = pMP->GetWorldPos();
+            const auto p3Dc = Tcw * p3Dw;
+            if (p3Dc(2) < 0.0f) continue;
+            const auto uv = pKF->mpCamera->project(p3Dc);
+            if (!pKF->IsInImage(uv(0), uv(1))) continue;
+#ifdef PLVS_SHIM_STANDIN
+            const float dist3D = standin_dist(p3Dw, Ow);
+            if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+            if (standin_view_gate(p3Dw, Ow, pMP->GetNormal(), dist3D)) continue;
+#else
+            const Eigen::Vector3f PO = p3Dw - Ow;
+            const float dist3D = PO.norm();
+            if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+            const Eigen::Vector3f Pn = pMP->GetNormal();
+            if (PO.dot(Pn) < 0.5 * dist3D) continue;
+#endif
+            plvs_fuse_query e{};
+            e.u = uv(0); e.v = uv(1); e.ur = 0.f;
+            e.level = pMP->PredictScale(dist3D, pKF);
+            const cv::Mat d = pMP->GetDescriptor();
+            std::memcpy(e.desc, d.data, 32);
+            q.push_back(e); src.push_back(i);
+        }
+        std::vector<int32_t> best_idx(q.size() + 1, -1), best_dist(q.size() + 1, 256);
+        int nsearch = 0;
+        const plvs_frame_view v = view_of(*pKF, pKF->mvKeysUn, pKF->mDescriptors);
+        plvs_shim::check(plvs_match_fuse_sim3(h_, &v, q.data(), (int)q.size(), th, best_idx.data(), best_dist.data(), &nsearch), "plvs_match_fuse_sim3");
+        int nFused = 0;
+        for (size_t k = 0; k < q.size(); ++k) {
+            if (best_dist[k] > TH_LOW) continue;
+            MapPointPtr pMP = vpPoints[src[k]];
+            MapPointPtr pMPinKF = pKF->GetMapPoint(best_idx[k]);
+            if (pMPinKF) {
+                if (!pMPinKF->isBad()) vpReplacePoint[src[k]] = pMPinKF;
+            } else {
+                pMP->AddObservation(pKF, best_idx[k]);
+                pKF->AddMapPoint(pMP, best_idx[k]);
             }
             nFused++;
         }

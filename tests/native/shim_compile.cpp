@@ -46,12 +46,15 @@ struct Frame {
 float Frame::mnMinX = 0, Frame::mnMinY = 0, Frame::mnMaxX = 640, Frame::mnMaxY = 480, Frame::mfGridElementWidthInv = 0.1f, Frame::mfGridElementHeightInv = 0.1f;
 struct KeyFrame : Frame {
     std::vector<MapPointPtr> GetMapPointMatches() const { return mvpMapPoints; }
+    std::set<MapPointPtr> GetMapPointsUnordered() const { return std::set<MapPointPtr>(); }
     MapPointPtr GetMapPoint(int i) const { return mvpMapPoints[i]; }
     std::vector<float> mvInvLevelSigma2 = std::vector<float>(8, 1.f);
     V3 GetCameraCenter() const { return V3{{0, 0, 0}}; }
     bool IsInImage(float x, float y) const { return x >= 0 && x < 640 && y >= 0 && y < 480; }
     void AddMapPoint(const MapPointPtr& p, int i) { mvpMapPoints[i] = p; }
 };
+struct Sim3 { Pose pose; };
+static Pose standin_se3_of_sim3(const Sim3& s) { return s.pose; }
 static void standin_fundamental(const KeyFrame&, const KeyFrame&, float* F12, float* ep) { for (int i = 0; i < 9; ++i) F12[i] = 0; ep[0] = ep[1] = 0; }
 
 #include "../../shim/plvs_shim.hpp"
@@ -73,6 +76,8 @@ extern "C" int shim_instantiate(int run)
     int c = m.SearchForTriangulation(k1, k2, pairs, false, false);
     c += m.Fuse(k1, mps, 3.0f, false);
     c += m.SearchByBoW(k1, F, mps);
+    Sim3 scw; std::vector<MapPointPtr> repl(mps.size());
+    c += m.Fuse(k1, scw, mps, 4.f, repl);
     std::set<MapPointPtr> found;
     c += m.SearchByProjection(F, k1, found, 10.f, 100);
     chisel_server::ChiselServerParams p; chisel_server::ChiselServer cs(p);

@@ -245,3 +245,22 @@ def test_projection_reloc(frames, th, orb_dist):
             rn, ra = OM.ref_search_by_projection_reloc(cur, q, th, orb_dist, check, claimed)
             assert n == rn and np.array_equal(a, ra)
     assert n > 300
+
+
+@pytest.mark.parametrize("dup,th", [(False, 4.0), (True, 3.0), (True, 10.0)])
+def test_fuse_sim3(frames, dup, th):
+    """loop-closing overload Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (§8f rank 1)"""
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    qm, _ = scenario.map_queries(last, cur, K, Tl, Tc, seed=9)
+    z = np.maximum(qm["track_depth"], 0.3).astype(np.float32)
+    q = OM.fuse_queries(qm["proj_x"], qm["proj_y"], z, qm["level"], qm["desc"], K["bf"])
+    if dup:
+        q = np.concatenate([q, q[::2]]); z = np.concatenate([z, z[::2]])
+    n, bi, bd = ORBmatcher(0.8, True).FuseSim3(cur, q, th)
+    on, obi, obd = OM.fuse_sim3(cur, q, th)
+    assert n == on and np.array_equal(bi, obi) and np.array_equal(bd, obd)
+    if OM.ref_available():
+        pre = (np.random.default_rng(5).random(cur.n) < 0.3).astype(np.uint8)
+        rn, ridx = OM.ref_fuse_sim3(cur, q, z, th, pre)
+        assert n == rn and np.array_equal(np.where(bd <= 50, bi, -1), ridx)

@@ -161,3 +161,14 @@ def test_projection_reloc(frames, th, orb_dist):
         rn, ra = OM.ref_search_by_projection_reloc(cur, q, th, orb_dist, check, claimed)
         assert n == rn and np.array_equal(a, ra)
     assert n > 300
+
+
+@pytest.mark.parametrize("dup,th", [(False, 4.0), (True, 3.0), (True, 10.0)])
+def test_fuse_sim3(frames, dup, th):
+    """Fuse(pKF, Scw, vpPoints, th, vpReplacePoint): no chi-square gate; keypoints that already hold a map point => vpReplacePoint"""
+    K, kf, q, z = _fuse_case(frames, 9, True, dup)
+    pre = (np.random.default_rng(5).random(kf.n) < 0.3).astype(np.uint8)
+    n, bi, bd = OM.fuse_sim3(kf, q, th)
+    rn, ridx = OM.ref_fuse_sim3(kf, q, z, th, pre)
+    assert n == rn and np.array_equal(np.where(bd <= 50, bi, -1), ridx)
+    assert n > 300
