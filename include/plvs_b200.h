@@ -245,6 +245,14 @@ int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const pl
 int plvs_match_projection_reloc(plvs_match* h, const plvs_frame_view* cur, const plvs_last_query* q, int nq, float th, int orb_dist,
                                 int check_orientation, const uint8_t* claimed_in, int32_t* assign, int* nmatches);
 
+/* ORBmatcher::SearchByProjection(KeyFramePtr& pKF, Sophus::Sim3f& Scw, const vector<MapPointPtr>& vpPoints, vector<MapPointPtr>&
+ * vpMatched, int th, float ratioHamming) (src/ORBmatcher.cc:509-615) and its sibling with vpPointsKFs / vpMatchedKF (:617-730),
+ * LoopClosing.  One query per candidate map point that passed the caller-side gates (:531-566): u, v, last_octave = predicted
+ * level, flags = PLVS_Q_OBS_POSITIVE, invz >= 0, angle unused.  matched_in[i] != 0 <=> vpMatched[i] is non-null on entry.
+ * assign[i] = query written into vpMatched[i] during the call or -1; *nmatches = the return value. */
+int plvs_match_projection_sim3(plvs_match* h, const plvs_frame_view* kf, const plvs_last_query* q, int nq, float th, float ratio_hamming,
+                               const uint8_t* matched_in, int32_t* assign, int* nmatches);
+
 /* ORBmatcher::SearchByBoW(KeyFramePtr& pKF, Frame& F, vector<MapPointPtr>& vpMapPointMatches) (src/ORBmatcher.cc:300-506),
  * RGB-D / rectified stereo (Nleft == -1): Tracking::TrackReferenceKeyFrame and Relocalization.  fv_kf / fv_f = pKF->mFeatVec /
  * F.mFeatVec flattened; has_mp_kf[i] != 0 <=> pKF->GetMapPointMatches()[i] is non-null and not bad; nn_ratio / check_orientation

@@ -252,3 +252,22 @@ def ref_fuse_sim3(K, queries, z, th, pre_mp=None):
     n = l.ref_fuse_sim3(C.byref(v), q.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), len(q), th,
                         pm.ctypes.data_as(C.c_void_p) if pm is not None else None, out.ctypes.data_as(C.c_void_p))
     return n, out[:len(q)]
+
+
+def _sim3_call(fn, K, queries, th, ratio, matched):
+    q = np.ascontiguousarray(queries, LAST_QUERY)
+    v = K.view()
+    assign = np.full(max(K.n, 1), -1, np.int32)
+    ml = None if matched is None else np.ascontiguousarray(matched, np.uint8)
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    n = fn(C.byref(v), q.ctypes.data_as(C.c_void_p), len(q), th, ratio, ml.ctypes.data_as(C.c_void_p) if ml is not None else None, assign.ctypes.data_as(C.c_void_p))
+    return n, assign[:K.n]
+
+
+def search_by_projection_sim3(K, queries, th, ratio=1.0, matched=None):
+    return _sim3_call(_setup().orc_search_by_projection_sim3, K, queries, th, ratio, matched)
+
+
+def ref_search_by_projection_sim3(K, queries, th, ratio=1.0, matched=None):
+    """th is an int in the reference's signature (src/ORBmatcher.cc:509)"""
+    return _sim3_call(_ref_lib().ref_search_by_projection_sim3, K, queries, th, ratio, matched)

@@ -326,6 +326,35 @@ int orc_search_by_projection_reloc(const FrameView* C, const LastQuery* q, int n
     return nmatches;
 }
 
+// ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (src/ORBmatcher.cc:509-615; :617-730 is the same
+// search): window of KeyFrame::GetFeaturesInArea (no level filter), level gate [l-1, l], any non-null vpMatched entry blocks,
+// accept if best <= TH_LOW * ratioHamming.
+int orc_search_by_projection_sim3(const FrameView* K, const LastQuery* q, int nq, float th, float ratio_hamming, const uint8_t* matched_in, int32_t* assign)
+{
+    Grid grid(K);
+    std::vector<int> holder(K->n, -1);
+    if (matched_in) for (int i = 0; i < K->n; ++i) if (matched_in[i]) holder[i] = -2;
+    int nmatches = 0;
+    std::vector<int> cand;
+    for (int iq = 0; iq < nq; ++iq) {
+        const LastQuery& m = q[iq];
+        const int lvl = m.last_octave;
+        const float radius = th * K->scale_factors[lvl];
+        grid.in_area(m.u, m.v, radius, -1, -1, cand);
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : cand) {
+            if (holder[idx] != -1) continue;
+            const int kpLevel = K->keys[idx].octave;
+            if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+            const int dist = hamming(m.desc, K->desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW * ratio_hamming) { holder[bestIdx] = iq; ++nmatches; }
+    }
+    for (int i = 0; i < K->n; ++i) assign[i] = holder[i] >= 0 ? holder[i] : -1;
+    return nmatches;
+}
+
 // ORBmatcher::SearchByBoW(KeyFramePtr& pKF, Frame& F, vector<MapPointPtr>& vpMapPointMatches) (src/ORBmatcher.cc:300-506),
 // Nleft == -1 branch: merge-walk of the two FeatureVectors; inside a shared node the keyframe features that carry a (good)
 // map point are visited in order, each takes the best frame feature of the node that is still unmatched (best/second with

@@ -241,6 +241,35 @@ int ref_fuse(const FrameView* Kv, const float* inv_level_sigma2, const FuseQuery
     return n;
 }
 
+// ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming)   src/ORBmatcher.cc:509-615   (Scw = identity)
+int ref_search_by_projection_sim3(const FrameView* Kv, const LastQuery* q, int nq, float th, float ratio_hamming, const uint8_t* matched_in, int32_t* assign)
+{
+    GeometricCamera cam;
+    KeyFrame K; fill(K, Kv); K.mpCamera = &cam;
+    K.mvpMapPoints.assign(Kv->n, nullptr);
+    MapPoint pre;
+    std::vector<MapPointPtr> matched(Kv->n, nullptr);
+    if (matched_in) for (int i = 0; i < Kv->n; ++i) if (matched_in[i]) matched[i] = &pre;
+    std::vector<std::unique_ptr<MapPoint>> mps(nq);
+    std::vector<MapPointPtr> vp(nq);
+    std::unordered_map<MapPointPtr, int> index;
+    for (int i = 0; i < nq; ++i) {
+        mps[i].reset(new MapPoint());
+        MapPoint& m = *mps[i];
+        m.pos = Eigen::Vector3f(q[i].u, q[i].v, 1.f);
+        m.normal = m.pos.normalized();
+        m.predictedLevel = q[i].last_octave;
+        m.desc = desc_mat(q[i].desc);
+        vp[i] = &m; index[&m] = i;
+    }
+    ORBmatcher matcher(0.75f, true);
+    Sophus::Sim3f Scw;
+    KeyFramePtr pk = &K;
+    const int n = matcher.SearchByProjection(pk, Scw, vp, matched, (int)th, ratio_hamming);
+    for (int i = 0; i < Kv->n; ++i) { auto it = index.find(matched[i]); assign[i] = it == index.end() ? -1 : it->second; }
+    return n;
+}
+
 // ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint)   src/ORBmatcher.cc:1437-1553   (Scw = identity similarity)
 // pre_mp[i] != 0: the keyframe already holds a map point at keypoint i (=> the vpReplacePoint branch)
 int ref_fuse_sim3(const FrameView* Kv, const FuseQuery* q, const float* z, int nq, float th, const uint8_t* pre_mp, int32_t* fused_idx)

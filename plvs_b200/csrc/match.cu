@@ -151,7 +151,8 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
         if (m.u < F.gp.min_x || m.u > F.gp.max_x || m.v < F.gp.min_y || m.v > F.gp.max_y) active = false;
         radius = th * F.scale[m.last_octave];
         px = m.u; py = m.v;
-        if (forward) { minL = m.last_octave; maxL = -1; }
+        if (forward && backward) { minL = m.last_octave - 1; maxL = m.last_octave; }      // Sim3 searches: [l-1, l] around the predicted level (:588-590)
+        else if (forward) { minL = m.last_octave; maxL = -1; }
         else if (backward) { minL = 0; maxL = m.last_octave; }
         else { minL = m.last_octave - 1; maxL = m.last_octave + 1; }
         xr_ref = m.u - F.bf * m.invz; xr_tol = radius; qd = m.desc;
@@ -1011,6 +1012,17 @@ int plvs_match_projection_reloc(plvs_match* h, const plvs_frame_view* cur, const
     plvs_frame_view v = *cur;
     v.uright = nullptr;
     return run_projection<1>(h, &v, q, sizeof(plvs_last_query), nq, th, 0.f, 0, 0.f, 0, 0, check_orientation, claimed_in, assign, nmatches, orb_dist);
+}
+
+int plvs_match_projection_sim3(plvs_match* h, const plvs_frame_view* kf, const plvs_last_query* q, int nq, float th, float ratio_hamming,
+                               const uint8_t* matched_in, int32_t* assign, int* nmatches)
+{
+    if (!kf) { set_error("null argument"); return PLVS_EINVAL; }
+    for (int i = 0; i < nq; ++i) if (q && !(q[i].flags & PLVS_Q_OBS_POSITIVE)) { set_error("sim3 query %d: PLVS_Q_OBS_POSITIVE must be set (any match blocks)", i); return PLVS_EINVAL; }
+    plvs_frame_view v = *kf;
+    v.uright = nullptr;
+    const int th_high = (int)floorf((float)TH_LOW * ratio_hamming);           // `bestDist <= TH_LOW*ratioHamming` with an integer bestDist (:606)
+    return run_projection<1>(h, &v, q, sizeof(plvs_last_query), nq, th, 0.f, 0, 0.f, 1, 1, 0, matched_in, assign, nmatches, th_high);
 }
 
 static int fuse_impl(plvs_match* h, const plvs_frame_view* kf, const float* inv_level_sigma2, const plvs_fuse_query* q, int nq, float th,

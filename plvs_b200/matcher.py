@@ -140,6 +140,18 @@ class ORBmatcher:
                    "plvs_match_projection_reloc")
         return nm.value, assign[:Cur.n]
 
+    def SearchByProjectionSim3(self, KF, queries, th, ratioHamming=1.0, matched=None):
+        """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (src/ORBmatcher.cc:509-615) with pre-projected points."""
+        q = np.ascontiguousarray(queries, LAST_QUERY)
+        assign = np.full(max(KF.n, 1), -1, np.int32)
+        nm = C.c_int()
+        v = KF.view()
+        ml = None if matched is None else np.ascontiguousarray(matched, np.uint8)
+        _lib.check(self._lib.plvs_match_projection_sim3(self._h, C.byref(v), q.ctypes.data_as(C.c_void_p), len(q), th, ratioHamming,
+                                                        ml.ctypes.data_as(C.c_void_p) if ml is not None else None, assign.ctypes.data_as(C.c_void_p), C.byref(nm)),
+                   "plvs_match_projection_sim3")
+        return nm.value, assign[:KF.n]
+
     def SearchByBoW(self, KF, F, fv_kf, fv_f, has_mp_kf):
         """SearchByBoW(KeyFramePtr&, Frame&, vector<MapPointPtr>&) (src/ORBmatcher.cc:300-506) -> (nmatches, match_f[F.N]) with
         match_f[i] = keyframe feature whose map point goes to frame feature i, or -1."""

@@ -19,6 +19,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <set>
 #include <vector>
 #include "../include/plvs_b200.h"
 
@@ -419,6 +420,59 @@ public:
             nFused++;
         }
         return nFused;
+    }
+
+    // int SearchByProjection(KeyFramePtr& pKF, Sophus::Sim3f& Scw, const vector<MapPointPtr>& vpPoints, vector<MapPointPtr>& vpMatched, int th, float ratioHamming=1.0)
+    // (src/ORBmatcher.cc:509-615) and, with vpPointsKFs / vpMatchedKF non-null, its sibling (:617-730)
+    template <class KeyFramePtr, class Sim3T, class MapPointPtr>
+    int SearchByProjection(KeyFramePtr& pKF, Sim3T& Scw, const std::vector<MapPointPtr>& vpPoints, std::vector<MapPointPtr>& vpMatched, int th,
+                           float ratioHamming = 1.0f, const std::vector<KeyFramePtr>* vpPointsKFs = nullptr, std::vector<KeyFramePtr>* vpMatchedKF = nullptr)
+    {
+        const auto Tcw = plvs_shim::se3_of_sim3(Scw);
+        const auto Ow = Tcw.inverse().translation();
+        std::set<MapPointPtr> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+        spAlreadyFound.erase(static_cast<MapPointPtr>(nullptr));
+        std::vector<plvs_last_query> q;
+        std::vector<size_t> src;
+        for (size_t i = 0; i < vpPoints.size(); ++i) {
+            MapPointPtr pMP = vpPoints[i];
+            if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+            const auto p3Dw = pMP->GetWorldPos();
+            const auto p3Dc = Tcw * p3Dw;
+            if (p3Dc(2) < 0.0) continue;
+            const auto uv = pKF->mpCamera->project(p3Dc);
+            if (!pKF->IsInImage(uv(0), uv(1))) continue;
+#ifdef PLVS_SHIM_STANDIN
+            const float dist = standin_dist(p3Dw, Ow);
+            if (dist < pMP->GetMinDistanceInvariance() || dist > pMP->GetMaxDistanceInvariance()) continue;
+            if (standin_view_gate(p3Dw, Ow, pMP->GetNormal(), dist)) continue;
+#else
+            const Eigen::Vector3f PO = p3Dw - Ow;
+            const float dist = PO.norm();
+            if (dist < pMP->GetMinDistanceInvariance() || dist > pMP->GetMaxDistanceInvariance()) continue;
+            const Eigen::Vector3f Pn = pMP->GetNormal();
+            if (PO.dot(Pn) < 0.5 * dist) continue;
+#endif
+            plvs_last_query e{};
+            e.u = uv(0); e.v = uv(1); e.invz = 1.f;
+            e.last_octave = pMP->PredictScale(dist, pKF);
+            e.flags = PLVS_Q_OBS_POSITIVE;
+            const cv::Mat d = pMP->GetDescriptor();
+            std::memcpy(e.desc, d.data, 32);
+            q.push_back(e); src.push_back(i);
+        }
+        std::vector<uint8_t> matched(pKF->N, 0);
+        for (int i = 0; i < pKF->N; ++i) matched[i] = vpMatched[i] ? 1 : 0;
+        std::vector<int32_t> assign(pKF->N + 1, -1);
+        int nmatches = 0;
+        const plvs_frame_view v = view_of(*pKF, pKF->mvKeysUn, pKF->mDescriptors);
+        plvs_shim::check(plvs_match_projection_sim3(h_, &v, q.data(), (int)q.size(), (float)th, ratioHamming, matched.data(), assign.data(), &nmatches),
+                         "plvs_match_projection_sim3");
+        for (int i = 0; i < pKF->N; ++i) if (assign[i] >= 0) {
+            vpMatched[i] = vpPoints[src[assign[i]]];
+            if (vpPointsKFs && vpMatchedKF) (*vpMatchedKF)[i] = (*vpPointsKFs)[src[assign[i]]];
+        }
+        return nmatches;
     }
 
     // int Fuse(KeyFramePtr& pKF, Sophus::Sim3f& Scw, const vector<MapPointPtr>& vpPoints, float th, vector<MapPointPtr>& vpReplacePoint)

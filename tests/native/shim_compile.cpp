@@ -78,6 +78,8 @@ extern "C" int shim_instantiate(int run)
     c += m.SearchByBoW(k1, F, mps);
     Sim3 scw; std::vector<MapPointPtr> repl(mps.size());
     c += m.Fuse(k1, scw, mps, 4.f, repl);
+    std::vector<MapPointPtr> vm(k1->N);
+    c += m.SearchByProjection(k1, scw, mps, vm, 8, 1.5f);
     std::set<MapPointPtr> found;
     c += m.SearchByProjection(F, k1, found, 10.f, 100);
     chisel_server::ChiselServerParams p; chisel_server::ChiselServer cs(p);

@@ -172,3 +172,17 @@ def test_fuse_sim3(frames, dup, th):
     rn, ridx = OM.ref_fuse_sim3(kf, q, z, th, pre)
     assert n == rn and np.array_equal(np.where(bd <= 50, bi, -1), ridx)
     assert n > 300
+
+
+@pytest.mark.parametrize("th,ratio", [(8, 1.5), (4, 1.0), (10, 0.9)])
+def test_projection_sim3(frames, th, ratio):
+    """loop-closing SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming)"""
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    q, _ = scenario.last_queries(last, cur, K, Tl, Tc)
+    q = np.concatenate([q, q[::2]]); q["flags"] = 1; q["invz"] = 1
+    matched = (np.random.default_rng(3).random(cur.n) < 0.25).astype(np.uint8)
+    n, a = OM.search_by_projection_sim3(cur, q, float(th), ratio, matched)
+    rn, ra = OM.ref_search_by_projection_sim3(cur, q, float(th), ratio, matched)
+    assert n == rn and np.array_equal(a, ra)
+    assert n > 300
