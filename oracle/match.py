@@ -271,3 +271,35 @@ def search_by_projection_sim3(K, queries, th, ratio=1.0, matched=None):
 def ref_search_by_projection_sim3(K, queries, th, ratio=1.0, matched=None):
     """th is an int in the reference's signature (src/ORBmatcher.cc:509)"""
     return _sim3_call(_ref_lib().ref_search_by_projection_sim3, K, queries, th, ratio, matched)
+
+
+# ---- ORBmatcher::SearchBySim3: two projection searches (the Fuse-Sim3 search with TH_HIGH) + mutual agreement --------------
+
+def sim3_agreement(bi12, bd12, bi21, bd21, valid1, valid2):
+    """the host part of SearchBySim3 (src/ORBmatcher.cc:1590-1769): vnMatch1/2 from the two searches (accepted if <= TH_HIGH),
+    then the mutual-consistency check.  valid* = map point present (and not already matched)."""
+    vn1 = np.where(valid1 & (bd12 <= 100), bi12, -1)
+    vn2 = np.where(valid2 & (bd21 <= 100), bi21, -1)
+    m12 = np.full(len(vn1), -1, np.int32)
+    for i1, i2 in enumerate(vn1):
+        if i2 >= 0 and vn2[i2] == i1:
+            m12[i1] = i2
+    return int((m12 >= 0).sum()), m12
+
+
+def search_by_sim3(K1, K2, q12, q21, has1, has2, th, fuse=fuse_sim3):
+    _, bi12, bd12 = fuse(K2, q12, th)
+    _, bi21, bd21 = fuse(K1, q21, th)
+    return sim3_agreement(bi12, bd12, bi21, bd21, np.asarray(has1, bool), np.asarray(has2, bool))
+
+
+def ref_search_by_sim3(K1, K2, q12, q21, has1, has2, th):
+    l = _ref_lib()
+    a = np.ascontiguousarray(q12, FUSE_QUERY); b = np.ascontiguousarray(q21, FUSE_QUERY)
+    h1 = np.ascontiguousarray(has1, np.uint8); h2 = np.ascontiguousarray(has2, np.uint8)
+    v1, v2 = K1.view(), K2.view()
+    m = np.full(max(K1.n, 1), -1, np.int32)
+    l.ref_search_by_sim3.argtypes = [C.c_void_p] * 6 + [C.c_float, C.c_void_p]
+    n = l.ref_search_by_sim3(C.byref(v1), C.byref(v2), a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), h1.ctypes.data_as(C.c_void_p),
+                             h2.ctypes.data_as(C.c_void_p), th, m.ctypes.data_as(C.c_void_p))
+    return n, m[:K1.n]

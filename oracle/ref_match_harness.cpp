@@ -304,4 +304,37 @@ int ref_fuse_sim3(const FrameView* Kv, const FuseQuery* q, const float* z, int n
     return n;
 }
 
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th)   src/ORBmatcher.cc:1555-1772   (identity poses / similarity, fx = fy = 1,
+// cx = cy = 0 and depth 1, so a map point's position IS its projection into the other keyframe).  q12[i1] describes map point i1 of
+// KF1 projected into KF2 (u, v, level, desc), q21[i2] the reverse; has1 / has2: the keyframe holds a map point there.
+// match12[i1] = index in KF2 of the mutually consistent match or -1.
+int ref_search_by_sim3(const FrameView* K1v, const FrameView* K2v, const FuseQuery* q12, const FuseQuery* q21, const uint8_t* has1, const uint8_t* has2,
+                       float th, int32_t* match12)
+{
+    GeometricCamera cam;
+    KeyFrame K1, K2; fill(K1, K1v); fill(K2, K2v);
+    K1.mpCamera = &cam; K2.mpCamera = &cam;
+    K1.fx = K1.fy = 1.f; K1.cx = K1.cy = 0.f;
+    std::vector<std::unique_ptr<MapPoint>> m1(K1v->n), m2(K2v->n);
+    K1.mvpMapPoints.assign(K1v->n, nullptr); K2.mvpMapPoints.assign(K2v->n, nullptr);
+    std::unordered_map<MapPointPtr, int> idx2;
+    for (int i = 0; i < K1v->n; ++i) if (has1[i]) {
+        m1[i].reset(new MapPoint()); MapPoint& m = *m1[i];
+        m.pos = Eigen::Vector3f(q12[i].u, q12[i].v, 1.f); m.predictedLevel = q12[i].level; m.desc = desc_mat(q12[i].desc);
+        K1.mvpMapPoints[i] = &m;
+    }
+    for (int i = 0; i < K2v->n; ++i) if (has2[i]) {
+        m2[i].reset(new MapPoint()); MapPoint& m = *m2[i];
+        m.pos = Eigen::Vector3f(q21[i].u, q21[i].v, 1.f); m.predictedLevel = q21[i].level; m.desc = desc_mat(q21[i].desc);
+        K2.mvpMapPoints[i] = &m; idx2[&m] = i;
+    }
+    ORBmatcher matcher(0.75f, true);
+    std::vector<MapPointPtr> matches(K1v->n, nullptr);
+    Sophus::Sim3f S12;
+    KeyFramePtr p1 = &K1, p2 = &K2;
+    const int n = matcher.SearchBySim3(p1, p2, matches, S12, th);
+    for (int i = 0; i < K1v->n; ++i) { auto it = idx2.find(matches[i]); match12[i] = it == idx2.end() ? -1 : it->second; }
+    return n;
+}
+
 }  // extern "C"

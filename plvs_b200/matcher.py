@@ -174,6 +174,21 @@ class ORBmatcher:
                                                   bi.ctypes.data_as(C.c_void_p), bd.ctypes.data_as(C.c_void_p), C.byref(nf)), "plvs_match_fuse_sim3")
         return nf.value, bi[:len(q)], bd[:len(q)]
 
+    def SearchBySim3(self, KF1, KF2, q12, q21, valid1, valid2, th):
+        """SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (src/ORBmatcher.cc:1555-1772): q12[i1] = map point i1 of KF1 projected into
+        KF2 (FUSE_QUERY; `ur` unused), q21 the reverse; valid* = map point present, not bad, not already matched.  Two device searches
+        (the Fuse-Sim3 search, accepted if <= TH_HIGH) and the mutual-agreement check -> (nFound, match12[N1])."""
+        _, bi12, bd12 = self.FuseSim3(KF2, q12, th)
+        _, bi21, bd21 = self.FuseSim3(KF1, q21, th)
+        vn1 = np.where(np.asarray(valid1, bool) & (bd12 <= 100), bi12, -1)
+        vn2 = np.where(np.asarray(valid2, bool) & (bd21 <= 100), bi21, -1)
+        m12 = np.full(len(vn1), -1, np.int32)
+        ok = vn1 >= 0
+        back = np.where(ok, vn2[np.where(ok, vn1, 0)], -2)
+        sel = ok & (back == np.arange(len(vn1)))
+        m12[sel] = vn1[sel]
+        return int(sel.sum()), m12
+
     def Fuse(self, KF, queries, th=3.0, inv_level_sigma2=None):
         """Search part of Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:1340-1406) -> (nFused, best_idx[nq], best_dist[nq]).
         The caller applies bestDist<=TH_LOW and the Replace/AddObservation bookkeeping in query order."""

@@ -20,6 +20,7 @@
 #include <string>
 #include <utility>
 #include <set>
+#include <tuple>
 #include <vector>
 #include "../include/plvs_b200.h"
 
@@ -31,6 +32,11 @@
 #endif
 
 namespace plvs_shim {
+#ifndef PLVS_SHIM_STANDIN
+template <class V> inline float norm3(const V& p) { return p.norm(); }
+#else
+template <class V> inline float norm3(const V& p) { return standin_norm(p); }
+#endif
 #ifndef PLVS_SHIM_STANDIN
 template <class Sim3T> inline auto se3_of_sim3(const Sim3T& Scw) { return Sophus::SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale()); }
 #else
@@ -473,6 +479,63 @@ public:
             if (vpPointsKFs && vpMatchedKF) (*vpMatchedKF)[i] = (*vpPointsKFs)[src[assign[i]]];
         }
         return nmatches;
+    }
+
+    // int SearchBySim3(KeyFramePtr& pKF1, KeyFramePtr& pKF2, std::vector<MapPointPtr>& vpMatches12, const Sophus::Sim3f& S12, const float th)
+    // (src/ORBmatcher.cc:1555-1772): the two projection searches run on the device (plvs_match_fuse_sim3), the gates before them and the
+    // mutual-agreement check after them here, with the reference's own expressions
+    template <class KeyFramePtr, class Sim3T, class MapPointPtr>
+    int SearchBySim3(KeyFramePtr& pKF1, KeyFramePtr& pKF2, std::vector<MapPointPtr>& vpMatches12, const Sim3T& S12, const float th)
+    {
+        const float fx = pKF1->fx, fy = pKF1->fy, cx = pKF1->cx, cy = pKF1->cy;
+        const auto T1w = pKF1->GetPose();
+        const auto T2w = pKF2->GetPose();
+        const auto S21 = S12.inverse();
+        const std::vector<MapPointPtr> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+        const int N1 = (int)vpMapPoints1.size(), N2 = (int)vpMapPoints2.size();
+        std::vector<bool> vbAlreadyMatched1(N1, false), vbAlreadyMatched2(N2, false);
+        for (int i = 0; i < N1; ++i) {
+            MapPointPtr pMP = vpMatches12[i];
+            if (pMP) {
+                vbAlreadyMatched1[i] = true;
+                const int idx2 = std::get<0>(pMP->GetIndexInKeyFrame(pKF2));
+                if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
+            }
+        }
+        auto pass = [&](const std::vector<MapPointPtr>& from, const std::vector<bool>& done, auto&& to_other, KeyFramePtr& other, std::vector<int>& vnMatch) {
+            std::vector<plvs_fuse_query> q; std::vector<int> src;
+            for (int i = 0; i < (int)from.size(); ++i) {
+                MapPointPtr pMP = from[i];
+                if (!pMP || done[i] || pMP->isBad()) continue;
+                const auto p3Dc = to_other(pMP->GetWorldPos());
+                if (p3Dc(2) < 0.0) continue;
+                const float invz = 1.0 / p3Dc(2);
+                const float x = p3Dc(0) * invz, y = p3Dc(1) * invz;
+                const float u = fx * x + cx, v = fy * y + cy;
+                if (!other->IsInImage(u, v)) continue;
+                const float dist3D = plvs_shim::norm3(p3Dc);
+                if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+                plvs_fuse_query e{};
+                e.u = u; e.v = v; e.level = pMP->PredictScale(dist3D, other);
+                const cv::Mat d = pMP->GetDescriptor();
+                std::memcpy(e.desc, d.data, 32);
+                q.push_back(e); src.push_back(i);
+            }
+            std::vector<int32_t> bi(q.size() + 1, -1), bd(q.size() + 1, 256);
+            int n = 0;
+            const plvs_frame_view v = view_of(*other, other->mvKeysUn, other->mDescriptors);
+            plvs_shim::check(plvs_match_fuse_sim3(h_, &v, q.data(), (int)q.size(), th, bi.data(), bd.data(), &n), "plvs_match_fuse_sim3");
+            for (size_t k = 0; k < q.size(); ++k) if (bd[k] <= TH_HIGH) vnMatch[src[k]] = bi[k];
+        };
+        std::vector<int> vnMatch1(N1, -1), vnMatch2(N2, -1);
+        pass(vpMapPoints1, vbAlreadyMatched1, [&](const auto& p3Dw) { return S21 * (T1w * p3Dw); }, pKF2, vnMatch1);
+        pass(vpMapPoints2, vbAlreadyMatched2, [&](const auto& p3Dw) { return S12 * (T2w * p3Dw); }, pKF1, vnMatch2);
+        int nFound = 0;
+        for (int i1 = 0; i1 < N1; ++i1) {
+            const int idx2 = vnMatch1[i1];
+            if (idx2 >= 0 && vnMatch2[idx2] == i1) { vpMatches12[i1] = vpMapPoints2[idx2]; nFound++; }
+        }
+        return nFound;
     }
 
     // int Fuse(KeyFramePtr& pKF, Sophus::Sim3f& Scw, const vector<MapPointPtr>& vpPoints, float th, vector<MapPointPtr>& vpReplacePoint)

@@ -4,6 +4,7 @@
 #include <map>
 #include <memory>
 #include <set>
+#include <tuple>
 #include <vector>
 #include "../../shim/standin.hpp"
 
@@ -32,6 +33,7 @@ struct MapPoint {
     int PredictScale(float, const void*) const { return 0; }
     void Replace(const std::shared_ptr<MapPoint>&) {}
     void AddObservation(const std::shared_ptr<KeyFrame>&, int) {}
+    std::tuple<int, int> GetIndexInKeyFrame(const std::shared_ptr<KeyFrame>&) const { return std::tuple<int, int>(-1, -1); }
 };
 typedef std::shared_ptr<MapPoint> MapPointPtr;
 static float standin_dist(const V3& p, const V3& o) { const float d[3] = {p.v[0] - o.v[0], p.v[1] - o.v[1], p.v[2] - o.v[2]}; return d[0] * d[0] + d[1] * d[1] + d[2] * d[2]; }
@@ -48,12 +50,14 @@ struct KeyFrame : Frame {
     std::vector<MapPointPtr> GetMapPointMatches() const { return mvpMapPoints; }
     std::set<MapPointPtr> GetMapPointsUnordered() const { return std::set<MapPointPtr>(); }
     MapPointPtr GetMapPoint(int i) const { return mvpMapPoints[i]; }
+    float fx = 500, fy = 500, cx = 320, cy = 240;
     std::vector<float> mvInvLevelSigma2 = std::vector<float>(8, 1.f);
     V3 GetCameraCenter() const { return V3{{0, 0, 0}}; }
     bool IsInImage(float x, float y) const { return x >= 0 && x < 640 && y >= 0 && y < 480; }
     void AddMapPoint(const MapPointPtr& p, int i) { mvpMapPoints[i] = p; }
 };
-struct Sim3 { Pose pose; };
+struct Sim3 { Pose pose; Sim3 inverse() const { return *this; } V3 operator*(const V3& p) const { return pose * p; } };
+static float standin_norm(const V3& p) { return p.v[0] * p.v[0] + p.v[1] * p.v[1] + p.v[2] * p.v[2]; }
 static Pose standin_se3_of_sim3(const Sim3& s) { return s.pose; }
 static void standin_fundamental(const KeyFrame&, const KeyFrame&, float* F12, float* ep) { for (int i = 0; i < 9; ++i) F12[i] = 0; ep[0] = ep[1] = 0; }
 
@@ -79,6 +83,7 @@ extern "C" int shim_instantiate(int run)
     Sim3 scw; std::vector<MapPointPtr> repl(mps.size());
     c += m.Fuse(k1, scw, mps, 4.f, repl);
     std::vector<MapPointPtr> vm(k1->N);
+    c += m.SearchBySim3(k1, k2, vm, scw, 7.5f);
     c += m.SearchByProjection(k1, scw, mps, vm, 8, 1.5f);
     std::set<MapPointPtr> found;
     c += m.SearchByProjection(F, k1, found, 10.f, 100);

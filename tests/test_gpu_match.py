@@ -280,3 +280,26 @@ def test_projection_sim3(frames, th, ratio):
     if OM.ref_available():
         rn, ra = OM.ref_search_by_projection_sim3(cur, q, float(th), ratio, matched)
         assert n == rn and np.array_equal(a, ra)
+
+
+def test_search_by_sim3(frames):
+    """SearchBySim3 = two device searches (the Fuse-Sim3 search) + the mutual-agreement check (§8f rank 1)"""
+    K, fr = frames
+    (k1, T1), (k2, T2) = fr[0], fr[1]
+    rng = np.random.default_rng(12)
+    def mk(src):
+        q = np.zeros(src.n, OM.FUSE_QUERY)
+        q["u"] = src.keys["x"] + rng.normal(0, 2.0, src.n).astype(np.float32)
+        q["v"] = src.keys["y"] + rng.normal(0, 2.0, src.n).astype(np.float32)
+        q["level"] = src.keys["octave"]; q["desc"] = src.desc
+        return q
+    q12, q21 = mk(k1), mk(k2)
+    has1 = (rng.random(k1.n) < 0.8).astype(np.uint8); has2 = (rng.random(k2.n) < 0.8).astype(np.uint8)
+    for th in (7.5, 15.0):
+        n, m = ORBmatcher(0.75, True).SearchBySim3(k1, k2, q12, q21, has1, has2, th)
+        on, om = OM.search_by_sim3(k1, k2, q12, q21, has1, has2, th)
+        assert n == on and np.array_equal(m, om)
+        if OM.ref_available():
+            rn, rm = OM.ref_search_by_sim3(k1, k2, q12, q21, has1, has2, th)
+            assert n == rn and np.array_equal(m, rm)
+    assert n > 100

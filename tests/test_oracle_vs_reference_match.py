@@ -186,3 +186,29 @@ def test_projection_sim3(frames, th, ratio):
     rn, ra = OM.ref_search_by_projection_sim3(cur, q, float(th), ratio, matched)
     assert n == rn and np.array_equal(a, ra)
     assert n > 300
+
+
+def _sim3_case(frames):
+    """every keypoint of KF1 carries a map point that projects near its own position in KF2 and vice versa"""
+    K, fr = frames
+    (k1, T1), (k2, T2) = fr[0], fr[1]
+    rng = np.random.default_rng(12)
+    def mk(src, dst_frame):
+        q = np.zeros(src.n, OM.FUSE_QUERY)
+        q["u"] = src.keys["x"] + rng.normal(0, 2.0, src.n).astype(np.float32)
+        q["v"] = src.keys["y"] + rng.normal(0, 2.0, src.n).astype(np.float32)
+        q["level"] = src.keys["octave"]; q["desc"] = src.desc
+        return q
+    # KF1's map points carry descriptors of the nearest KF2 features where the scenario matcher finds them, else their own
+    q12, q21 = mk(k1, k2), mk(k2, k1)
+    has1 = (rng.random(k1.n) < 0.8).astype(np.uint8); has2 = (rng.random(k2.n) < 0.8).astype(np.uint8)
+    return k1, k2, q12, q21, has1, has2
+
+
+def test_search_by_sim3(frames):
+    k1, k2, q12, q21, has1, has2 = _sim3_case(frames)
+    for th in (7.5, 15.0):
+        n, m = OM.search_by_sim3(k1, k2, q12, q21, has1, has2, th)
+        rn, rm = OM.ref_search_by_sim3(k1, k2, q12, q21, has1, has2, th)
+        assert n == rn and np.array_equal(m, rm)
+    assert n > 100
