@@ -262,6 +262,13 @@ int plvs_match_bow(plvs_match* h, const plvs_frame_view* kf, const plvs_frame_vi
                    const plvs_featvec* fv_kf, const plvs_featvec* fv_f, const uint8_t* has_mp_kf,
                    float nn_ratio, int check_orientation, int32_t* match_f, int* nmatches);
 
+/* ORBmatcher::SearchByBoW(KeyFramePtr& pKF1, KeyFramePtr& pKF2, vector<MapPointPtr>& vpMatches12) (src/ORBmatcher.cc:853-997,
+ * LoopClosing / merging): has_mp*[i] != 0 <=> the keyframe's map point i is non-null and not bad.  match12[i1] (kf1->n entries) =
+ * index in KF2 whose map point is assigned to feature i1 (vpMatches12[i1] = vpMapPoints2[match12[i1]]) or -1. */
+int plvs_match_bow_kf(plvs_match* h, const plvs_frame_view* kf1, const plvs_frame_view* kf2,
+                      const plvs_featvec* fv1, const plvs_featvec* fv2, const uint8_t* has_mp1, const uint8_t* has_mp2,
+                      float nn_ratio, int check_orientation, int32_t* match12, int* nmatches);
+
 /* ORBmatcher::Fuse(KeyFramePtr& pKF, const vector<MapPointPtr>&, th, bRight=false) (src/ORBmatcher.cc:1244-1435), the
  * search part (:1340-1406).  One query = one map point that passed the caller-side gates (:1277-1338: not bad, not already in
  * the keyframe, positive depth, inside the image, distance range, viewing angle), projected with the reference's own

@@ -303,3 +303,22 @@ def ref_search_by_sim3(K1, K2, q12, q21, has1, has2, th):
     n = l.ref_search_by_sim3(C.byref(v1), C.byref(v2), a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), h1.ctypes.data_as(C.c_void_p),
                              h2.ctypes.data_as(C.c_void_p), th, m.ctypes.data_as(C.c_void_p))
     return n, m[:K1.n]
+
+
+def _bow_kf_call(fn, K1, K2, fv1, fv2, has1, has2, nn_ratio, check_ori):
+    v1, v2 = K1.view(), K2.view()
+    s1, s2 = featvec_struct(fv1), featvec_struct(fv2)
+    h1 = np.ascontiguousarray(has1, np.uint8); h2 = np.ascontiguousarray(has2, np.uint8)
+    m = np.full(max(K1.n, 1), -1, np.int32)
+    fn.argtypes = [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_void_p]
+    n = fn(C.byref(v1), C.byref(v2), C.byref(s1), C.byref(s2), h1.ctypes.data_as(C.c_void_p), h2.ctypes.data_as(C.c_void_p), nn_ratio, int(check_ori),
+           m.ctypes.data_as(C.c_void_p))
+    return n, m[:K1.n]
+
+
+def search_by_bow_kf(K1, K2, fv1, fv2, has1, has2, nn_ratio=0.8, check_ori=True):
+    return _bow_kf_call(_setup().orc_search_by_bow_kf, K1, K2, fv1, fv2, has1, has2, nn_ratio, check_ori)
+
+
+def ref_search_by_bow_kf(K1, K2, fv1, fv2, has1, has2, nn_ratio=0.8, check_ori=True):
+    return _bow_kf_call(_ref_lib().ref_search_by_bow_kf, K1, K2, fv1, fv2, has1, has2, nn_ratio, check_ori)

@@ -407,6 +407,56 @@ int orc_search_by_bow(const FrameView* K, const FrameView* F, const FeatVec* fvK
     return nmatches;
 }
 
+// ORBmatcher::SearchByBoW(KeyFramePtr& pKF1, KeyFramePtr& pKF2, vector<MapPointPtr>& vpMatches12) (src/ORBmatcher.cc:853-997):
+// like the frame overload, but set-2 features must carry a good map point too, the claim lives in vbMatched2, the acceptance is
+// `bestDist1 < TH_LOW` (strict) and the result is indexed by the KF1 feature.
+int orc_search_by_bow_kf(const FrameView* K1, const FrameView* K2, const FeatVec* fv1, const FeatVec* fv2, const uint8_t* has1, const uint8_t* has2,
+                         float nn_ratio, int check_ori, int32_t* match12)
+{
+    int nmatches = 0;
+    for (int i = 0; i < K1->n; ++i) match12[i] = -1;
+    std::vector<char> matched2(K2->n, 0);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int a = 0, b = 0;
+    while (a < fv1->n_nodes && b < fv2->n_nodes) {
+        if (fv1->node_ids[a] == fv2->node_ids[b]) {
+            for (int i1 = fv1->offsets[a]; i1 < fv1->offsets[a + 1]; ++i1) {
+                const int idx1 = fv1->features[i1];
+                if (!has1[idx1]) continue;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int i2 = fv2->offsets[b]; i2 < fv2->offsets[b + 1]; ++i2) {
+                    const int idx2 = fv2->features[i2];
+                    if (matched2[idx2] || !has2[idx2]) continue;
+                    const int dist = hamming(K1->desc + (size_t)idx1 * 32, K2->desc + (size_t)idx2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW) {
+                    if ((float)bestDist1 < nn_ratio * (float)bestDist2) {
+                        match12[idx1] = bestIdx2; matched2[bestIdx2] = 1;
+                        if (check_ori) rotHist[rot_bin(K1->keys[idx1].angle, K2->keys[bestIdx2].angle)].push_back(idx1);
+                        ++nmatches;
+                    }
+                }
+            }
+            ++a; ++b;
+        } else if (fv1->node_ids[a] < fv2->node_ids[b]) {
+            while (a < fv1->n_nodes && fv1->node_ids[a] < fv2->node_ids[b]) ++a;
+        } else {
+            while (b < fv2->n_nodes && fv2->node_ids[b] < fv1->node_ids[a]) ++b;
+        }
+    }
+    if (check_ori) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int idx : rotHist[i]) { match12[idx] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
 // ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight=false) (src/ORBmatcher.cc:1244-1435), the search part (:1340-1406): window from
 // KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:1179-1229, no level filter), level gate [l-1, l], chi-square gate on the
 // reprojection error (7.8 with a right coordinate, 5.99 without), best distance, first wins ties.  The gates before the search

@@ -205,6 +205,31 @@ int ref_search_by_bow(const FrameView* Kv, const FrameView* Fv, const FeatVec* f
     return n;
 }
 
+// ORBmatcher::SearchByBoW(KeyFramePtr& pKF1, KeyFramePtr& pKF2, vector<MapPointPtr>& vpMatches12)   src/ORBmatcher.cc:853-997
+int ref_search_by_bow_kf(const FrameView* K1v, const FrameView* K2v, const FeatVec* fv1, const FeatVec* fv2, const uint8_t* has1, const uint8_t* has2,
+                         float nn_ratio, int check_ori, int32_t* match12)
+{
+    GeometricCamera cam;
+    KeyFrame K1, K2; fill(K1, K1v); fill(K2, K2v);
+    K1.mpCamera = &cam; K2.mpCamera = &cam;
+    std::vector<std::unique_ptr<MapPoint>> m1(K1v->n), m2(K2v->n);
+    std::unordered_map<MapPointPtr, int> idx2;
+    K1.mvpMapPoints.assign(K1v->n, nullptr); K2.mvpMapPoints.assign(K2v->n, nullptr);
+    for (int i = 0; i < K1v->n; ++i) if (has1[i]) { m1[i].reset(new MapPoint()); K1.mvpMapPoints[i] = m1[i].get(); }
+    for (int i = 0; i < K2v->n; ++i) if (has2[i]) { m2[i].reset(new MapPoint()); K2.mvpMapPoints[i] = m2[i].get(); idx2[m2[i].get()] = i; }
+    auto load = [](DBoW2::FeatureVector& out, const FeatVec* fv) {
+        for (int a = 0; a < fv->n_nodes; ++a)
+            for (int k = fv->offsets[a]; k < fv->offsets[a + 1]; ++k) out.addFeature(fv->node_ids[a], (unsigned)fv->features[k]);
+    };
+    load(K1.mFeatVec, fv1); load(K2.mFeatVec, fv2);
+    ORBmatcher matcher(nn_ratio, check_ori != 0);
+    std::vector<MapPointPtr> matches;
+    KeyFramePtr p1 = &K1, p2 = &K2;
+    const int n = matcher.SearchByBoW(p1, p2, matches);
+    for (int i = 0; i < K1v->n; ++i) { auto it = idx2.find(matches[i]); match12[i] = it == idx2.end() ? -1 : it->second; }
+    return n;
+}
+
 // ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight=false)   src/ORBmatcher.cc:1244-1435
 // z[i]: camera-frame depth of query i; the harness camera has bf = `bf` and the reference computes ur = u - bf * (1/z), which the
 // caller made equal to q[i].ur.  fused_idx[i] = keypoint the map point was fused into (bestDist <= TH_LOW), else -1.

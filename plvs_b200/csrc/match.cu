@@ -588,7 +588,9 @@ k_tri_finish(const plvs_keypoint* __restrict__ k1, const plvs_keypoint* __restri
 // smallest of the multiset (what the if / else-if pair computes, order-independent).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_bow(ViewDev K, ViewDev F, FvDev fK, FvDev fF, const uint8_t* __restrict__ has_mp, float ratio, int32_t* match_f)
+k_bow(ViewDev K, ViewDev F, FvDev fK, FvDev fF, const uint8_t* __restrict__ has_mp, float ratio, int32_t* match_f,
+      const uint8_t* __restrict__ has2 /*KF-KF overload: set-2 features must carry a good map point*/, int strict /*KF-KF: bestDist1 < TH_LOW*/,
+      int32_t* out12 /*KF-KF: out12[idx1] = idx2*/)
 {
     const int a = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -609,6 +611,7 @@ k_bow(ViewDev K, ViewDev F, FvDev fK, FvDev fF, const uint8_t* __restrict__ has_
         for (int p = b0 + lane; p < b1; p += 32) {
             const int idxF = fF.feat[p];
             if (mf[idxF] >= 0) continue;
+            if (has2 && !has2[idxF]) continue;
             const int dist = hamming256(a0, a1, F.desc + (size_t)idxF * 32);
             const uint32_t key = ((uint32_t)dist << 16) | (uint32_t)min(p - b0, 65535);
             if (key < bestkey) { bestkey = key; bi = idxF; }
@@ -620,7 +623,7 @@ k_bow(ViewDev K, ViewDev F, FvDev fK, FvDev fF, const uint8_t* __restrict__ has_
         const uint32_t wk = __reduce_min_sync(0xffffffffu, bestkey);
         const int src = __ffs(__ballot_sync(0xffffffffu, bestkey == wk)) - 1;
         const int idx = __shfl_sync(0xffffffffu, bi, src);
-        if (lane == 0 && m1 <= TH_LOW && (float)m1 < ratio * (float)m2) mf[idx] = idxK;
+        if (lane == 0 && (strict ? m1 < TH_LOW : m1 <= TH_LOW) && (float)m1 < ratio * (float)m2) { mf[idx] = idxK; if (out12) out12[idxK] = idx; }
         __syncwarp();
     }
 }
@@ -1150,13 +1153,47 @@ int plvs_match_bow(plvs_match* h, const plvs_frame_view* kf, const plvs_frame_vi
     if ((rc = h->p_assign.alloc(nf)) || (rc = h->d_assign.alloc(nf)) || (rc = h->p_result.alloc(4))) return rc;
     h->timer.begin(PLVS_MATCH_K_BOW, st);
     k_fill_i32<<<div_up(nf, 256), 256, 0, st>>>(h->d_assign.p, nf, -1);
-    k_bow<<<div_up(DK.n_nodes, 8), 256, 0, st>>>(VK, VF, DK, DF, dh, nn_ratio, h->d_assign.p);
+    k_bow<<<div_up(DK.n_nodes, 8), 256, 0, st>>>(VK, VF, DK, DF, dh, nn_ratio, h->d_assign.p, nullptr, 0, nullptr);
     k_tri_finish<<<1, 1024, 0, st>>>(VF.keys, VK.keys, nf, check_orientation, h->d_assign.p, h->p_assign.d, h->p_result.d, 1);
     h->timer.end(st);
     PLVS_CUDA(cudaGetLastError());
     PLVS_CUDA(cudaStreamSynchronize(st));
     h->timer.collect();
     std::memcpy(match_f, h->p_assign.h, (size_t)nf * 4);
+    *nmatches = h->p_result.h[0];
+    h->last_launches = 3;
+    return PLVS_OK;
+}
+
+int plvs_match_bow_kf(plvs_match* h, const plvs_frame_view* kf1, const plvs_frame_view* kf2, const plvs_featvec* fv1, const plvs_featvec* fv2,
+                      const uint8_t* has_mp1, const uint8_t* has_mp2, float nn_ratio, int check_orientation, int32_t* match12, int* nmatches)
+{
+    if (!h || !kf1 || !kf2 || !fv1 || !fv2 || !has_mp1 || !has_mp2 || !match12 || !nmatches) { set_error("null argument"); return PLVS_EINVAL; }
+    std::lock_guard<std::mutex> lock(h->mu);
+    PLVS_CUDA(cudaSetDevice(h->device));
+    ViewDev V1, V2; FvDev D1, D2;
+    int rc;
+    if ((rc = stage_view(h, 0, kf1, &V1)) || (rc = stage_view(h, 1, kf2, &V2))) return rc;
+    if ((rc = stage_fv(h, 0, fv1, kf1->on_device, &D1)) || (rc = stage_fv(h, 1, fv2, kf2->on_device, &D2))) return rc;
+    const int n1 = kf1->n, n2 = kf2->n;
+    *nmatches = 0;
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    if (n1 == 0 || n2 == 0 || D1.n_nodes == 0 || D2.n_nodes == 0) return PLVS_OK;
+    cudaStream_t st = h->stream;
+    const uint8_t *dh1 = has_mp1, *dh2 = has_mp2;
+    if (!kf1->on_device) { if ((rc = h->d_has[0].alloc(n1))) return rc; PLVS_CUDA(cudaMemcpyAsync(h->d_has[0].p, has_mp1, n1, cudaMemcpyHostToDevice, st)); dh1 = h->d_has[0].p; }
+    if (!kf2->on_device) { if ((rc = h->d_has[1].alloc(n2))) return rc; PLVS_CUDA(cudaMemcpyAsync(h->d_has[1].p, has_mp2, n2, cudaMemcpyHostToDevice, st)); dh2 = h->d_has[1].p; }
+    if ((rc = h->p_assign.alloc(n1)) || (rc = h->d_assign.alloc((size_t)n1 + n2)) || (rc = h->p_result.alloc(4))) return rc;
+    int32_t* d_out12 = h->d_assign.p; int32_t* d_claim2 = h->d_assign.p + n1;
+    h->timer.begin(PLVS_MATCH_K_BOW, st);
+    k_fill_i32<<<div_up(n1 + n2, 256), 256, 0, st>>>(h->d_assign.p, n1 + n2, -1);
+    k_bow<<<div_up(D1.n_nodes, 8), 256, 0, st>>>(V1, V2, D1, D2, dh1, nn_ratio, d_claim2, dh2, 1, d_out12);
+    k_tri_finish<<<1, 1024, 0, st>>>(V1.keys, V2.keys, n1, check_orientation, d_out12, h->p_assign.d, h->p_result.d, 0);
+    h->timer.end(st);
+    PLVS_CUDA(cudaGetLastError());
+    PLVS_CUDA(cudaStreamSynchronize(st));
+    h->timer.collect();
+    std::memcpy(match12, h->p_assign.h, (size_t)n1 * 4);
     *nmatches = h->p_result.h[0];
     h->last_launches = 3;
     return PLVS_OK;

@@ -174,6 +174,18 @@ class ORBmatcher:
                                                   bi.ctypes.data_as(C.c_void_p), bd.ctypes.data_as(C.c_void_p), C.byref(nf)), "plvs_match_fuse_sim3")
         return nf.value, bi[:len(q)], bd[:len(q)]
 
+    def SearchByBoWKF(self, KF1, KF2, fv1, fv2, has_mp1, has_mp2):
+        """SearchByBoW(KeyFramePtr&, KeyFramePtr&, vector<MapPointPtr>&) (src/ORBmatcher.cc:853-997) -> (nmatches, match12[N1])."""
+        m = np.full(max(KF1.n, 1), -1, np.int32)
+        nm = C.c_int()
+        v1, v2 = KF1.view(), KF2.view()
+        s1, s2 = featvec_struct(fv1), featvec_struct(fv2)
+        h1 = np.ascontiguousarray(has_mp1, np.uint8); h2 = np.ascontiguousarray(has_mp2, np.uint8)
+        _lib.check(self._lib.plvs_match_bow_kf(self._h, C.byref(v1), C.byref(v2), C.byref(s1), C.byref(s2), h1.ctypes.data_as(C.c_void_p),
+                                               h2.ctypes.data_as(C.c_void_p), self.mfNNratio, int(self.mbCheckOrientation), m.ctypes.data_as(C.c_void_p),
+                                               C.byref(nm)), "plvs_match_bow_kf")
+        return nm.value, m[:KF1.n]
+
     def SearchBySim3(self, KF1, KF2, q12, q21, valid1, valid2, th):
         """SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (src/ORBmatcher.cc:1555-1772): q12[i1] = map point i1 of KF1 projected into
         KF2 (FUSE_QUERY; `ur` unused), q21 the reverse; valid* = map point present, not bad, not already matched.  Two device searches

@@ -481,6 +481,36 @@ public:
         return nmatches;
     }
 
+    // int SearchByBoW(KeyFramePtr& pKF1, KeyFramePtr& pKF2, std::vector<MapPointPtr>& vpMatches12)   (src/ORBmatcher.cc:853-997)
+    template <class KeyFramePtr, class MapPointPtr>
+    int SearchByBoW(KeyFramePtr& pKF1, KeyFramePtr& pKF2, std::vector<MapPointPtr>& vpMatches12)
+    {
+        struct Flat { std::vector<uint32_t> ids; std::vector<int32_t> off, feat; plvs_featvec fv; };
+        auto flatten = [](const auto& featVec, Flat& f) {
+            f.off.push_back(0);
+            for (const auto& kv : featVec) {
+                f.ids.push_back(kv.first);
+                for (unsigned i : kv.second) f.feat.push_back((int32_t)i);
+                f.off.push_back((int32_t)f.feat.size());
+            }
+            f.fv = plvs_featvec{(int32_t)f.ids.size(), f.ids.data(), f.off.data(), f.feat.data()};
+        };
+        Flat f1, f2;
+        flatten(pKF1->mFeatVec, f1); flatten(pKF2->mFeatVec, f2);
+        const std::vector<MapPointPtr> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
+        std::vector<uint8_t> has1(pKF1->N), has2(pKF2->N);
+        for (int i = 0; i < pKF1->N; ++i) has1[i] = (mp1[i] && !mp1[i]->isBad()) ? 1 : 0;
+        for (int i = 0; i < pKF2->N; ++i) has2[i] = (mp2[i] && !mp2[i]->isBad()) ? 1 : 0;
+        const plvs_frame_view v1 = view_of(*pKF1, pKF1->mvKeysUn, pKF1->mDescriptors), v2 = view_of(*pKF2, pKF2->mvKeysUn, pKF2->mDescriptors);
+        std::vector<int32_t> m(pKF1->N + 1, -1);
+        int nmatches = 0;
+        plvs_shim::check(plvs_match_bow_kf(h_, &v1, &v2, &f1.fv, &f2.fv, has1.data(), has2.data(), mfNNratio, mbCheckOrientation ? 1 : 0, m.data(), &nmatches),
+                         "plvs_match_bow_kf");
+        vpMatches12 = std::vector<MapPointPtr>(mp1.size(), static_cast<MapPointPtr>(nullptr));
+        for (int i = 0; i < pKF1->N; ++i) if (m[i] >= 0) vpMatches12[i] = mp2[m[i]];
+        return nmatches;
+    }
+
     // int SearchBySim3(KeyFramePtr& pKF1, KeyFramePtr& pKF2, std::vector<MapPointPtr>& vpMatches12, const Sophus::Sim3f& S12, const float th)
     // (src/ORBmatcher.cc:1555-1772): the two projection searches run on the device (plvs_match_fuse_sim3), the gates before them and the
     // mutual-agreement check after them here, with the reference's own expressions

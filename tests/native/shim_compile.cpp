@@ -84,6 +84,7 @@ extern "C" int shim_instantiate(int run)
     c += m.Fuse(k1, scw, mps, 4.f, repl);
     std::vector<MapPointPtr> vm(k1->N);
     c += m.SearchBySim3(k1, k2, vm, scw, 7.5f);
+    c += m.SearchByBoW(k1, k2, vm);
     c += m.SearchByProjection(k1, scw, mps, vm, 8, 1.5f);
     std::set<MapPointPtr> found;
     c += m.SearchByProjection(F, k1, found, 10.f, 100);

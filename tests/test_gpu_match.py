@@ -303,3 +303,22 @@ def test_search_by_sim3(frames):
             rn, rm = OM.ref_search_by_sim3(k1, k2, q12, q21, has1, has2, th)
             assert n == rn and np.array_equal(m, rm)
     assert n > 100
+
+
+@pytest.mark.parametrize("nodes", [16, 128, 1024])
+def test_search_by_bow_kf(frames, nodes):
+    """ORBmatcher::SearchByBoW(KF1, KF2) (§8f rank 1)"""
+    K, fr = frames
+    kf1, kf2 = fr[0][0], fr[2][0]
+    fv1, fv2 = featvec(scenario.node_ids(kf1.desc, nodes)), featvec(scenario.node_ids(kf2.desc, nodes))
+    rng = np.random.default_rng(nodes)
+    has1 = (rng.random(kf1.n) < 0.7).astype(np.uint8); has2 = (rng.random(kf2.n) < 0.7).astype(np.uint8)
+    for ratio in (0.8, 0.95):
+        for check in (True, False):
+            n, m = ORBmatcher(ratio, check).SearchByBoWKF(kf1, kf2, fv1, fv2, has1, has2)
+            on, om = OM.search_by_bow_kf(kf1, kf2, fv1, fv2, has1, has2, ratio, check)
+            assert n == on and np.array_equal(m, om)
+            if OM.ref_available():
+                rn, rm = OM.ref_search_by_bow_kf(kf1, kf2, fv1, fv2, has1, has2, ratio, check)
+                assert n == rn and np.array_equal(m, rm)
+    assert n > 50
