@@ -88,28 +88,50 @@ __device__ __forceinline__ int reflect101(int p, int n)
     return p;          // valid for n >= 4 and |overshoot| <= 3 (levels are always > 7 px)
 }
 
+// Staging: the (16+6) x (128+6) input window of a tile.  Tiles whose window lies inside the level in x (no reflection left or
+// right) fetch it with one 1-D bulk asynchronous copy (TMA) per row -- 160 bytes from the 16-byte aligned column x0-16; rows are
+// reflected by choosing the source row -- completed through an mbarrier; tiles at the left / right edge of a level, where
+// BORDER_REFLECT_101 mirrors columns, use byte loads.  Column c of the window (c = 0 <-> x0-3) sits at s_in[r][c + 13].
+constexpr int kBlurSW = 160, kBlurSO = 13;
+
 __global__ void __launch_bounds__(256)
 k_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, long long frame_stride,
        const LevelGeom* __restrict__ levels, const TileDesc* __restrict__ tiles)
 {
-    __shared__ uint8_t s_in[kBlurTH + 6][kBlurTW + 8];
+    __shared__ __align__(128) uint8_t s_in[kBlurTH + 6][kBlurSW];
     __shared__ uint16_t s_row[kBlurTH + 6][kBlurTW];
+    __shared__ __align__(8) unsigned long long s_bar;
     const TileDesc t = tiles[blockIdx.x];
     const LevelGeom g = levels[t.level];
     const uint8_t* src = pyr + (long long)blockIdx.y * frame_stride + g.off;
     uint8_t* dst = blur + (long long)blockIdx.y * frame_stride + g.off;
     const int x0 = t.tx * kBlurTW, y0 = t.ty * kBlurTH;
     const int tid = threadIdx.x;
-    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW + 6); i += 256) {
-        const int r = i / (kBlurTW + 6), c = i - r * (kBlurTW + 6);
-        const int yy = reflect101(min(y0 + r - 3, g.h + 2), g.h);
-        const int xx = reflect101(min(x0 + c - 3, g.w + 2), g.w);
-        s_in[r][c] = src[(long long)yy * g.pitch + xx];
+    const bool interior = x0 >= 16 && x0 + kBlurTW + 3 <= g.w;      // then [x0-16, x0+144) is inside the row pitch (a multiple of 128)
+    if (interior) {
+        const uint32_t bar = tma_smem_u32(&s_bar);
+        if (tid == 0) tma_mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            tma_mbar_expect_tx(bar, (kBlurTH + 6) * kBlurSW);
+            for (int r = 0; r < kBlurTH + 6; ++r) {
+                const int yy = reflect101(min(y0 + r - 3, g.h + 2), g.h);
+                tma_bulk_g2s(tma_smem_u32(&s_in[r][0]), src + (long long)yy * g.pitch + (x0 - 16), kBlurSW, bar);
+            }
+        }
+        tma_mbar_wait(bar, 0);
+    } else {
+        for (int i = tid; i < (kBlurTH + 6) * (kBlurTW + 6); i += 256) {
+            const int r = i / (kBlurTW + 6), c = i - r * (kBlurTW + 6);
+            const int yy = reflect101(min(y0 + r - 3, g.h + 2), g.h);
+            const int xx = reflect101(min(x0 + c - 3, g.w + 2), g.w);
+            s_in[r][c + kBlurSO] = src[(long long)yy * g.pitch + xx];
+        }
     }
     __syncthreads();
     for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256) {
         const int r = i / kBlurTW, c = i - r * kBlurTW;
-        const uint8_t* p = &s_in[r][c];
+        const uint8_t* p = &s_in[r][c + kBlurSO];
         s_row[r][c] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
     }
     __syncthreads();
