@@ -293,6 +293,12 @@ int plvs_match_fuse(plvs_match* h, const plvs_frame_view* kf, const float* inv_l
 int plvs_match_fuse_sim3(plvs_match* h, const plvs_frame_view* kf, const plvs_fuse_query* q, int nq, float th,
                          int32_t* best_idx, int32_t* best_dist, int* nfused);
 
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:395-461), batched (LocalMapping calls it for every new / fused map
+ * point): desc = the observed descriptors of all points back to back (host, 32 bytes each, in the order the caller collected
+ * them from mObservations), offsets[n_points+1] = start of each point's run.  best[i] = index INSIDE the run of the descriptor
+ * with the least median distance to the others (median = sorted[0.5*(N-1)], first minimum wins), -1 for an empty run. */
+int plvs_distinctive_descriptors(plvs_match* h, const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best);
+
 /* Device view of one frame's pyramid (all levels) of an extractor handle: what Frame::ComputeStereoMatches
  * reads through mpORBextractorLeft/Right->mvImagePyramid (src/Frame.cc:1886,1914). */
 typedef struct {

@@ -322,3 +322,16 @@ def search_by_bow_kf(K1, K2, fv1, fv2, has1, has2, nn_ratio=0.8, check_ori=True)
 
 def ref_search_by_bow_kf(K1, K2, fv1, fv2, has1, has2, nn_ratio=0.8, check_ori=True):
     return _bow_kf_call(_ref_lib().ref_search_by_bow_kf, K1, K2, fv1, fv2, has1, has2, nn_ratio, check_ori)
+
+
+def distinctive_descriptor(desc):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:428-455) for one map point, in numpy: pairwise Hamming distances,
+    median = sorted(row)[int(0.5*(N-1))], first descriptor with the smallest median.  ("parity unpinned": MapPoint.cc cannot be
+    compiled without the whole system; this is an independent restatement used as a known-answer check.)"""
+    d = np.asarray(desc, np.uint8).reshape(-1, 32)
+    n = len(d)
+    if n == 0:
+        return -1
+    D = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(2).astype(np.int64)
+    med = np.sort(D, axis=1)[:, int(0.5 * (n - 1))]
+    return int(np.argmin(med))

@@ -628,6 +628,46 @@ k_bow(ViewDev K, ViewDev F, FvDev fK, FvDev fF, const uint8_t* __restrict__ has_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:428-455), batched over map points: all pairwise Hamming distances
+// of a point's observed descriptors, per descriptor the median `sorted[0.5*(N-1)]` of its row, the first descriptor with the
+// smallest median wins (`median < BestMedian`).  One warp per map point, distance matrix in shared memory (u16).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+k_distinctive(const uint8_t* __restrict__ desc, const int32_t* __restrict__ off, int32_t* __restrict__ best)
+{
+    extern __shared__ uint16_t s_d[];
+    const int pt = blockIdx.x, lane = threadIdx.x;
+    const int o = off[pt], n = off[pt + 1] - o;
+    if (n <= 0) { if (lane == 0) best[pt] = -1; return; }
+    for (int e = lane; e < n * n; e += 32) {
+        const int i = e / n, j = e - i * n;
+        if (j < i) continue;
+        int d = 0;
+        if (j > i) {
+            const uint4* a = reinterpret_cast<const uint4*>(desc + (size_t)(o + i) * 32);
+            d = hamming256(a[0], a[1], desc + (size_t)(o + j) * 32);
+        }
+        s_d[i * n + j] = (uint16_t)d; s_d[j * n + i] = (uint16_t)d;
+    }
+    __syncwarp();
+    const int k = (int)(0.5 * (n - 1));
+    uint32_t key = 0xffffffffu;                       // median << 16 | index
+    for (int i = lane; i < n; i += 32) {
+        const uint16_t* row = s_d + i * n;
+        int med = 0;
+        for (int j = 0; j < n; ++j) {
+            const int v = row[j];
+            int less = 0, eq_before = 0;
+            for (int m = 0; m < n; ++m) { const int u = row[m]; less += u < v; eq_before += (u == v) & (m < j); }
+            if (less + eq_before == k) { med = v; break; }
+        }
+        key = min(key, ((uint32_t)med << 16) | (uint32_t)i);
+    }
+    key = __reduce_min_sync(0xffffffffu, key);
+    if (lane == 0) best[pt] = (int)(key & 0xffffu);
+}
+
 __global__ void k_fill_i32(int32_t* p, int n, int32_t v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 }  // namespace
@@ -1196,6 +1236,33 @@ int plvs_match_bow_kf(plvs_match* h, const plvs_frame_view* kf1, const plvs_fram
     std::memcpy(match12, h->p_assign.h, (size_t)n1 * 4);
     *nmatches = h->p_result.h[0];
     h->last_launches = 3;
+    return PLVS_OK;
+}
+
+int plvs_distinctive_descriptors(plvs_match* h, const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best)
+{
+    if (!h || n_points < 0 || (n_points && (!desc || !offsets || !best))) { set_error("null argument"); return PLVS_EINVAL; }
+    if (n_points == 0) return PLVS_OK;
+    std::lock_guard<std::mutex> lock(h->mu);
+    PLVS_CUDA(cudaSetDevice(h->device));
+    const int total = offsets[n_points];
+    int nmax = 0;
+    for (int i = 0; i < n_points; ++i) { const int n = offsets[i + 1] - offsets[i]; if (n < 0) { set_error("offsets must be non-decreasing"); return PLVS_EINVAL; } nmax = std::max(nmax, n); }
+    if (nmax > 320) { set_error("more than 320 observations of one map point are not supported"); return PLVS_ECAP; }
+    int rc;
+    cudaStream_t st = h->stream;
+    if ((rc = h->d_desc[0].alloc((size_t)std::max(total, 1) * 32)) || (rc = h->d_fv_off[0].alloc(n_points + 1)) || (rc = h->d_assign.alloc(n_points)) ||
+        (rc = h->p_assign.alloc(n_points))) return rc;
+    PLVS_CUDA(cudaMemcpyAsync(h->d_desc[0].p, desc, (size_t)total * 32, cudaMemcpyHostToDevice, st));
+    PLVS_CUDA(cudaMemcpyAsync(h->d_fv_off[0].p, offsets, (size_t)(n_points + 1) * 4, cudaMemcpyHostToDevice, st));
+    const size_t smem = (size_t)std::max(nmax, 1) * nmax * sizeof(uint16_t);
+    if (smem > 48 * 1024) PLVS_CUDA(cudaFuncSetAttribute(k_distinctive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->grid_key = 0; h->grid_n = -1;          // d_desc[0] was overwritten: a cached frame grid no longer matches its descriptors
+    k_distinctive<<<n_points, 32, smem, st>>>(h->d_desc[0].p, h->d_fv_off[0].p, h->p_assign.d);
+    PLVS_CUDA(cudaGetLastError());
+    PLVS_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(best, h->p_assign.h, (size_t)n_points * 4);
+    h->last_launches = 1;
     return PLVS_OK;
 }
 

@@ -186,6 +186,17 @@ class ORBmatcher:
                                                C.byref(nm)), "plvs_match_bow_kf")
         return nm.value, m[:KF1.n]
 
+    def ComputeDistinctiveDescriptors(self, desc_lists):
+        """MapPoint::ComputeDistinctiveDescriptors for a batch of map points: desc_lists = one [n_i, 32] uint8 array per point
+        -> best index per point (src/MapPoint.cc:428-455)."""
+        off = np.zeros(len(desc_lists) + 1, np.int32)
+        off[1:] = np.cumsum([len(d) for d in desc_lists])
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(d, np.uint8).reshape(-1, 32) for d in desc_lists]) if off[-1] else np.zeros((0, 32), np.uint8))
+        best = np.full(max(len(desc_lists), 1), -1, np.int32)
+        _lib.check(self._lib.plvs_distinctive_descriptors(self._h, flat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), len(desc_lists),
+                                                          best.ctypes.data_as(C.c_void_p)), "plvs_distinctive_descriptors")
+        return best[:len(desc_lists)]
+
     def SearchBySim3(self, KF1, KF2, q12, q21, valid1, valid2, th):
         """SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (src/ORBmatcher.cc:1555-1772): q12[i1] = map point i1 of KF1 projected into
         KF2 (FUSE_QUERY; `ur` unused), q21 the reverse; valid* = map point present, not bad, not already matched.  Two device searches

@@ -322,3 +322,22 @@ def test_search_by_bow_kf(frames, nodes):
                 rn, rm = OM.ref_search_by_bow_kf(kf1, kf2, fv1, fv2, has1, has2, ratio, check)
                 assert n == rn and np.array_equal(m, rm)
     assert n > 50
+
+
+def test_distinctive_descriptors(gpu):
+    """MapPoint::ComputeDistinctiveDescriptors, batched (§8f rank 1): known-answer check against an independent numpy restatement"""
+    rng = np.random.default_rng(21)
+    lists = []
+    for n in [1, 2, 3, 4, 5, 7, 8, 16, 31, 32, 33, 64, 100, 0, 150]:
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        d = np.repeat(base[None], n, 0).copy()
+        flips = rng.random((n, 256)) < rng.uniform(0.02, 0.3)                  # noisy copies of one descriptor, some outliers
+        d ^= np.packbits(flips, axis=1)
+        lists.append(d)
+    lists.append(np.repeat(rng.integers(0, 256, (1, 32), dtype=np.uint8), 6, 0))  # all identical: every median 0, first wins
+    for _ in range(200):
+        n = int(rng.integers(2, 20))
+        lists.append(rng.integers(0, 256, (n, 32), dtype=np.uint8))
+    got = ORBmatcher(0.6, True).ComputeDistinctiveDescriptors(lists)
+    want = np.array([OM.distinctive_descriptor(d) for d in lists], np.int32)
+    assert np.array_equal(got, want)
