@@ -352,7 +352,8 @@ def run_b200_arm(a):
     # ---- e2e arm: host (pinned) buffers through the public classes, copies inside the timed region ---------
     t2_ms, wall2, clocks2, agg2 = run(resident=False)
     e2e_value = world * frames / (t2_ms / 1000.0)
-    h2d = B * data.input_bytes_per_frame()
+    # every host->device byte of a step: the images (gray u8 + depth f32 + bgr u8x3) and what the searches stage per frame
+    h2d = B * data.input_bytes_per_frame() + int(sum(hp.search_h2d_bytes(f) for f in range(1 + W * B, 1 + (W + K) * B)) / K)
     d2h = int(B * (agg2.get("keypoints", 0) / max(frames, 1)) * 60 + B * 3 * a.nfeatures * 4)
 
     sampler.stop()

@@ -154,7 +154,11 @@ typedef struct plvs_match plvs_match;
 int plvs_hamming256(const uint8_t* a, const uint8_t* b);
 
 /* Flat view of the Frame / KeyFrame members the matchers read (RGB-D / rectified stereo: Nleft==-1).
- * Pointers are host pointers unless on_device != 0. */
+ * Pointers are host pointers unless on_device != 0: on_device = PLVS_VIEW_ON_DEVICE means keys / desc / uright are device
+ * pointers (e.g. plvs_orb_device_result); or-ing PLVS_VIEW_URIGHT_ON_HOST says that `uright` alone is still a host array
+ * (mvuRight as Frame::ComputeStereoFromRGBD leaves it on the CPU), which is then staged per call. */
+#define PLVS_VIEW_ON_DEVICE 1
+#define PLVS_VIEW_URIGHT_ON_HOST 2
 typedef struct {
     int32_t n;                    /* Frame::N */
     const plvs_keypoint* keys;    /* Frame::mvKeysUn */

@@ -851,6 +851,14 @@ int stage_view(plvs_match* h, int slot, const plvs_frame_view* v, ViewDev* out)
     for (int i = 0; i < PLVS_MAX_LEVELS; ++i) { out->scale[i] = v->scale_factors[i]; out->sigma2[i] = v->level_sigma2[i]; }
     if (v->on_device) {
         out->keys = v->keys; out->desc = v->desc; out->uright = v->uright;
+        if (v->uright && (v->on_device & PLVS_VIEW_URIGHT_ON_HOST)) {
+            // keypoints / descriptors stayed on the device after extraction, mvuRight was computed by the caller on the host
+            // (Frame::ComputeStereoFromRGBD, outside the hot path): 4 bytes per keypoint are staged per call
+            int rc;
+            if ((rc = h->d_uright[slot].alloc((size_t)std::max(v->n, 1)))) return rc;
+            PLVS_CUDA(cudaMemcpyAsync(h->d_uright[slot].p, v->uright, (size_t)v->n * 4, cudaMemcpyHostToDevice, h->stream));
+            out->uright = h->d_uright[slot].p;
+        }
         return PLVS_OK;
     }
     int rc;

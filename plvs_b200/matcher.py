@@ -42,6 +42,9 @@ class Frame:
         if self.device_ptrs is not None:
             v.keys, v.desc, v.uright = self.device_ptrs[1], self.device_ptrs[2], self.device_ptrs[3] or None
             v.on_device = 1
+            if not self.device_ptrs[3] and self.uright is not None:      # mvuRight computed by the caller on the host
+                v.uright = self.uright.ctypes.data
+                v.on_device = 1 | 2
             v.cache_key = self.device_ptrs[4] if len(self.device_ptrs) > 4 else 0
         else:
             v.keys = self.keys.ctypes.data

@@ -145,7 +145,7 @@ class HotPath:
             # descriptors/keypoints of the current frame stay on the device for the searches
             dv = self.ex.device_result(b)
             cur_ref = self.frames[f]
-            cur = Frame(None, None, d.w, d.h, sf, s2, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key))
+            cur = Frame(None, None, d.w, d.h, sf, s2, uright=self.frames[f].uright, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key))
             n1, a1 = self.m_track.SearchByProjectionLast(cur, p["ql"], 15.0)
             claimed = (a1 >= 0).astype(np.uint8)
             # same tracking-thread workspace => the feature grid of the frame is built once for both searches
@@ -268,7 +268,7 @@ class HotPath:
                     if p is None:
                         continue
                     dv = exs[i].device_result(b)
-                    cur = Frame(None, None, d.w, d.h, sf, s2, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key))
+                    cur = Frame(None, None, d.w, d.h, sf, s2, uright=self.frames[f].uright, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key))
                     n1, a1 = self.m_track.SearchByProjectionLast(cur, p["ql"], 15.0)
                     claimed = (a1 >= 0).astype(np.uint8)
                     n2, a2 = self.m_track.SearchByProjectionMap(cur, p["qm"], 3.0, claimed=claimed, nnratio=0.8)
@@ -323,6 +323,19 @@ class HotPath:
         lib.plvs_match_last_stats(self.m_track._h, C.byref(r), C.byref(k))
         out.append(r.value)
         return out
+
+    def search_h2d_bytes(self, f):
+        """host->device bytes the three searches of frame f copy besides the images: query records, the frame's mvuRight (twice),
+        the pre-claim array, and for SearchForTriangulation both host-side frame views, their flattened FeatureVectors,
+        map-point flags and F12"""
+        p = self.prepared[f]
+        if p is None:
+            return 0
+        cur, last = self.frames[f], self.frames[f - 1]
+        b = p["ql"].nbytes + p["qm"].nbytes + 2 * cur.n * 4 + cur.n
+        for fr, fv, has in ((cur, p["fv1"], p["has1"]), (last, p["fv2"], p["has2"])):
+            b += fr.n * (28 + 32 + 4) + has.nbytes + sum(np.asarray(a).nbytes for a in fv)
+        return b + 9 * 4
 
     def launches_per_frame(self):
         """kernel launches of the last batch / frame, as counted by the library"""

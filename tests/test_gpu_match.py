@@ -341,3 +341,26 @@ def test_distinctive_descriptors(gpu):
     got = ORBmatcher(0.6, True).ComputeDistinctiveDescriptors(lists)
     want = np.array([OM.distinctive_descriptor(d) for d in lists], np.int32)
     assert np.array_equal(got, want)
+
+
+def test_device_view_with_host_uright(frames):
+    """keypoints / descriptors device-resident from the extractor, mvuRight from the caller's host array (PLVS_VIEW_URIGHT_ON_HOST):
+    the right-coordinate gate is applied exactly as with an all-host view"""
+    K, fr = frames
+    (last, Tl), (cur, Tc) = fr[0], fr[1]
+    ex = ORBextractor(2000, 1.2, 8, 20, 7)
+    mono, kp, desc = ex(synth.gray_frame(11))
+    assert np.array_equal(kp, cur.keys)
+    dv = ex.device_result(0)
+    dcur = Frame(None, None, K["w"], K["h"], ex.GetScaleFactors(), uright=cur.uright, bf=K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key))
+    q, _ = scenario.last_queries(last, cur, K, Tl, Tc)
+    n, assign = ORBmatcher(0.9, True).SearchByProjectionLast(dcur, q, 15.0)
+    on, oassign = OM.search_by_projection_last(cur, q, 15.0)
+    assert on == n and np.array_equal(assign, oassign)
+    nogate = Frame(cur.keys, cur.desc, K["w"], K["h"], ex.GetScaleFactors(), bf=K["bf"])
+    n2, assign2 = OM.search_by_projection_last(nogate, q, 15.0)
+    assert not np.array_equal(assign2, oassign)                 # the gate really changes the result on this stream
+    qm, _ = scenario.map_queries(last, cur, K, Tl, Tc)
+    n3, a3 = ORBmatcher(0.8, True).SearchByProjectionMap(dcur, qm, 3.0)
+    on3, oa3 = OM.search_by_projection_map(cur, qm, 3.0, 0.8)
+    assert n3 == on3 and np.array_equal(a3, oa3)
