@@ -117,6 +117,20 @@ int plvs_orb_download_level(plvs_orb* h, int frame, int level, int blurred, uint
 /* Device-resident result of frame `frame` of the last batch (valid until the next extract on this
  * handle; only when no keypoint fell in the lapping area): lets the matcher run without a
  * device->host->device round trip. */
+/* Step before extraction: the same extraction on 3- or 4-channel 8-bit frames; cv::cvtColor(..,
+ * COLOR_{BGR,RGB,BGRA,RGBA}2GRAY) (src/Tracking.cc:1797-1810, OpenCV 4 fixed point) runs on the device in front of the pyramid.
+ * stride / frame_stride in bytes; is_rgb = Tracking::mbRGB. */
+int plvs_orb_extract_batch_color(plvs_orb* h, int batch, const uint8_t* img, int w, int h_, int stride, size_t frame_stride, int nch, int is_rgb,
+                                 int on_device, int lap0, int lap1, plvs_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_index_out);
+
+/* Step after extraction (§8f rank 2): Frame::ComputeStereoFromRGBD (src/Frame.cc:2251-2279) for frame `frame` of the last batch,
+ * on the device-resident keypoints.  depth: CV_32F image in metres (host, or device when on_device), row stride in bytes.
+ * keys_un_x: mvKeysUn[i].pt.x (host, n floats) or NULL when the camera has no distortion (mvKeysUn == mvKeys).  uright / depth_out
+ * (host, n floats, nullable) receive mvuRight / mvDepth; *d_uright (nullable) the device copy of mvuRight, valid until the next
+ * extraction on this handle: pass it as plvs_frame_view.uright with on_device = PLVS_VIEW_ON_DEVICE. */
+int plvs_orb_stereo_from_rgbd(plvs_orb* h, int frame, const float* depth, int w, int h_, int stride_bytes, int on_device, float bf,
+                              const float* keys_un_x, float* uright, float* depth_out, const float** d_uright);
+
 typedef struct {
     int32_t n;
     const plvs_keypoint* keys;   /* device */

@@ -346,3 +346,14 @@ class RefExtractor:
         rc = RefExtractor._lib.ref_orb_level(self._h, l, int(filtered), _p(out), out.size, C.byref(w), C.byref(h))
         assert rc == 0
         return out
+
+
+# ---- step before extraction: cv::cvtColor(.., COLOR_*2GRAY), src/Tracking.cc:1797-1810 ---------------------
+
+def color_to_gray(img, rgb=False):
+    """OpenCV 4 fixed-point grey conversion of an 8-bit BGR[A] / RGB[A] image: (R*9798 + G*19235 + B*3735 + 2^14) >> 15.
+    Pinned: tests/test_oracle_orb.py compares it with the real cv2.cvtColor for all 2^24 colours."""
+    img = np.asarray(img, np.uint8)
+    c0, c1, c2 = (img[..., i].astype(np.int64) for i in range(3))
+    b, r = (c2, c0) if rgb else (c0, c2)
+    return ((r * 9798 + c1 * 19235 + b * 3735 + (1 << 14)) >> 15).astype(np.uint8)

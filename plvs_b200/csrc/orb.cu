@@ -35,7 +35,9 @@ struct plvs_orb {
     long long frame_stride = 0;      // bytes of one frame's pyramid
     long long slots_per_frame = 0;
     int sel_cap = 0;                 // keypoint capacity per frame
-    DevBuf<uint8_t> d_pyr, d_blur, d_dbg_score;
+    DevBuf<uint8_t> d_pyr, d_blur, d_dbg_score, d_color;
+    DevBuf<float> d_uright, d_kdepth, d_depth_img, d_keys_un_x;
+    PinBuf<float> p_uright;
     bool debug = false;
     DevBuf<LevelGeom> d_lv;
     DevBuf<CellDesc> d_cells;
@@ -308,13 +310,31 @@ int plvs_orb_tables(const plvs_orb* o, float* scale, float* inv_scale, float* si
     return PLVS_OK;
 }
 
+static int extract_impl(plvs_orb* o, int batch, const uint8_t* gray, int w, int h, int stride,
+                        size_t frame_stride_in, int on_device, int lap0, int lap1,
+                        plvs_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_out, int nch, int is_rgb);
+
 int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, int h, int stride,
                            size_t frame_stride_in, int on_device, int lap0, int lap1,
                            plvs_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_out)
 {
+    return extract_impl(o, batch, gray, w, h, stride, frame_stride_in, on_device, lap0, lap1, kps, desc, cap, n_out, mono_out, 1, 0);
+}
+
+int plvs_orb_extract_batch_color(plvs_orb* o, int batch, const uint8_t* img, int w, int h, int stride, size_t frame_stride_in, int nch, int is_rgb,
+                                 int on_device, int lap0, int lap1, plvs_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_out)
+{
+    if (nch != 3 && nch != 4) { set_error("colour extraction takes 3- or 4-channel 8-bit images"); return PLVS_EINVAL; }
+    return extract_impl(o, batch, img, w, h, stride, frame_stride_in, on_device, lap0, lap1, kps, desc, cap, n_out, mono_out, nch, is_rgb);
+}
+
+static int extract_impl(plvs_orb* o, int batch, const uint8_t* gray, int w, int h, int stride,
+                        size_t frame_stride_in, int on_device, int lap0, int lap1,
+                        plvs_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_out, int nch, int is_rgb)
+{
     if (!o || !n_out || batch < 1) { set_error("null/invalid argument"); return PLVS_EINVAL; }
     if (!gray || w <= 0 || h <= 0) { for (int b = 0; b < batch; ++b) { n_out[b] = 0; if (mono_out) mono_out[b] = -1; } return PLVS_OK; }  // operator() returns -1 on empty image
-    if (stride < w) { set_error("stride < width"); return PLVS_EINVAL; }
+    if (stride < w * nch) { set_error("stride < width"); return PLVS_EINVAL; }
     std::lock_guard<std::mutex> lock(o->mu);
     PLVS_CUDA(cudaSetDevice(o->device));
     int rc = setup_geometry(o, w, h, batch);
@@ -325,7 +345,20 @@ int plvs_orb_extract_batch(plvs_orb* o, int batch, const uint8_t* gray, int w, i
 
     // level 0 <- input (ComputePyramid level 0; the 19-px border frame is never read on this path)
     const LevelGeom& g0 = o->lv[0];
-    if (on_device) {
+    if (nch > 1) {
+        // cv::cvtColor(.., COLOR_*2GRAY) (src/Tracking.cc:1797-1810) fused in front of the pyramid: the colour frames are staged once
+        const uint8_t* d_img = gray;
+        long long fs_in = (long long)frame_stride_in;
+        if (!on_device) {
+            const size_t per = (size_t)stride * h;
+            if ((rc = o->d_color.alloc(per * batch))) return rc;
+            for (int b = 0; b < batch; ++b)
+                PLVS_CUDA(cudaMemcpyAsync(o->d_color.p + per * b, gray + b * frame_stride_in, per, cudaMemcpyHostToDevice, st));
+            d_img = o->d_color.p; fs_in = (long long)per;
+        }
+        k_color_to_gray<<<dim3(div_up(w, 256), h, batch), 256, 0, st>>>(d_img, fs_in, stride, nch, is_rgb, o->d_pyr.p, o->frame_stride, g0);
+        ++launches;
+    } else if (on_device) {
         for (int b = 0; b < batch; ++b)
             PLVS_CUDA(cudaMemcpy2DAsync(o->d_pyr.p + (size_t)b * o->frame_stride, g0.pitch, gray + b * frame_stride_in, stride, w, h,
                                         cudaMemcpyDeviceToDevice, st));
@@ -532,6 +565,44 @@ int plvs_orb_download_level(plvs_orb* o, int frame, int level, int blurred, uint
     PLVS_CUDA(cudaSetDevice(o->device));
     PLVS_CUDA(cudaMemcpy2DAsync(host, host_stride, d, pitch, w, h, cudaMemcpyDeviceToHost, o->stream));
     PLVS_CUDA(cudaStreamSynchronize(o->stream));
+    return PLVS_OK;
+}
+
+int plvs_orb_stereo_from_rgbd(plvs_orb* o, int frame, const float* depth, int w, int h, int stride_bytes, int on_device, float bf,
+                              const float* keys_un_x, float* uright, float* depth_out, const float** d_uright)
+{
+    if (!o || !depth || frame < 0 || frame >= o->last_batch || w <= 0 || h <= 0 || stride_bytes < w * 4 || (stride_bytes & 3)) { set_error("bad argument"); return PLVS_EINVAL; }
+    if (o->lapped[frame]) { set_error("device keypoints unavailable: they were reordered by the lapping area"); return PLVS_ESTATE; }
+    std::lock_guard<std::mutex> lock(o->mu);
+    PLVS_CUDA(cudaSetDevice(o->device));
+    cudaStream_t st = o->stream;
+    const int n = o->n_kp[frame];
+    int rc;
+    const size_t cap = (size_t)std::max(o->sel_cap, 1);
+    if ((rc = o->d_uright.alloc(cap * o->last_batch)) || (rc = o->d_kdepth.alloc(cap * o->last_batch)) || (rc = o->p_uright.alloc(2 * cap))) return rc;
+    const float* d_depth = depth;
+    if (!on_device) {
+        if ((rc = o->d_depth_img.alloc((size_t)stride_bytes / 4 * h))) return rc;
+        PLVS_CUDA(cudaMemcpyAsync(o->d_depth_img.p, depth, (size_t)stride_bytes * h, cudaMemcpyHostToDevice, st));
+        d_depth = o->d_depth_img.p;
+    }
+    const float* d_un = nullptr;
+    if (keys_un_x && n) {
+        if ((rc = o->d_keys_un_x.alloc(cap))) return rc;
+        PLVS_CUDA(cudaMemcpyAsync(o->d_keys_un_x.p, keys_un_x, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        d_un = o->d_keys_un_x.p;
+    }
+    float* du = o->d_uright.p + cap * frame; float* dd = o->d_kdepth.p + cap * frame;
+    if (n) k_stereo_from_rgbd<<<div_up(n, 256), 256, 0, st>>>(o->d_kp.p + (size_t)frame * o->sel_cap, n, d_un, d_depth, w, h, stride_bytes / 4, bf, du, dd);
+    if (uright || depth_out) {
+        PLVS_CUDA(cudaMemcpyAsync(o->p_uright.h, du, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        PLVS_CUDA(cudaMemcpyAsync(o->p_uright.h + cap, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    PLVS_CUDA(cudaGetLastError());
+    PLVS_CUDA(cudaStreamSynchronize(st));
+    if (uright) std::memcpy(uright, o->p_uright.h, (size_t)n * 4);
+    if (depth_out) std::memcpy(depth_out, o->p_uright.h + cap, (size_t)n * 4);
+    if (d_uright) *d_uright = du;
     return PLVS_OK;
 }
 

@@ -75,6 +75,41 @@ k_resize_level(uint8_t* __restrict__ pyr, long long frame_stride, LevelGeom src,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Step before extraction: cv::cvtColor(.., COLOR_{BGR,RGB,BGRA,RGBA}2GRAY) on 8-bit images
+// (src/Tracking.cc:1797-1810).  OpenCV 4's fixed point: (R*9798 + G*19235 + B*3735 + 2^14) >> 15 -- checked against the real cv2
+// of this image for all 2^24 colours (tests/test_oracle_orb.py).  Writes level 0 of the pyramid directly.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_color_to_gray(const uint8_t* __restrict__ img, long long frame_stride_in, int stride, int nch, int is_rgb,
+                uint8_t* __restrict__ pyr, long long frame_stride, LevelGeom g0)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= g0.w) return;
+    const uint8_t* p = img + (long long)blockIdx.z * frame_stride_in + (long long)y * stride + (long long)x * nch;
+    const uint32_t c0 = p[0], c1 = p[1], c2 = p[2];
+    const uint32_t b = is_rgb ? c2 : c0, r = is_rgb ? c0 : c2;
+    pyr[(long long)blockIdx.z * frame_stride + g0.off + (long long)y * g0.pitch + x] = (uint8_t)((r * 9798u + c1 * 19235u + b * 3735u + (1u << 14)) >> 15);
+}
+
+// Step after extraction (§8f rank 2): Frame::ComputeStereoFromRGBD (src/Frame.cc:2251-2279) on the device-resident keypoints:
+// d = imDepth.at<float>(v, u) with the float coordinates truncated, mvDepth = d and mvuRight = xUn - bf/d where d > 0, else -1.
+__global__ void __launch_bounds__(256)
+k_stereo_from_rgbd(const plvs_keypoint* __restrict__ keys, int n, const float* __restrict__ keys_un_x, const float* __restrict__ depth, int w, int h,
+                   int stride_f, float bf, float* __restrict__ uright, float* __restrict__ kdepth)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const plvs_keypoint kp = keys[i];
+    const int u = (int)kp.x, v = (int)kp.y;
+    float ur = -1.f, dz = -1.f;
+    if (u >= 0 && u < w && v >= 0 && v < h) {
+        const float d = depth[(size_t)v * stride_f + u];
+        if (d > 0) { dz = d; ur = (keys_un_x ? keys_un_x[i] : kp.x) - bf / d; }
+    }
+    uright[i] = ur; kdepth[i] = dz;
+}
+
+// ---------------------------------------------------------------------------------------------
 // a7  7x7 Gaussian, sigma 2, BORDER_REFLECT_101 of the level itself (src/ORBextractor.cc:1343-1344;
 //     OpenCV u8 fixed point: taps [18,34,48,56,48,34,18]/256, 8.8 row pass, 16.16 column pass,
 //     one rounding).  Tile 128x16 outputs, halo staged in shared memory.

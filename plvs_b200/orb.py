@@ -76,6 +76,35 @@ class ORBextractor:
         _lib.check(rc, "plvs_orb_extract_batch")
         return mono, [kps[b, :n[b]] for b in range(B)], [desc[b, :n[b]] for b in range(B)]
 
+    def extract_batch_color(self, images, rgb=False, vLappingArea=(0, 0)):
+        """images: (B,H,W,3|4) uint8 host array; cv::cvtColor(COLOR_{BGR|RGB}[A]2GRAY) runs on the device in front of the pyramid
+        (src/Tracking.cc:1797-1810)."""
+        assert images.dtype == np.uint8 and images.ndim == 4 and images.shape[3] in (3, 4)
+        images = np.ascontiguousarray(images)
+        B, H, W, nch = images.shape
+        cap = self._cap
+        kps = np.empty((B, cap), KP_DTYPE); desc = np.empty((B, cap, 32), np.uint8)
+        n = np.zeros(B, np.int32); mono = np.zeros(B, np.int32)
+        rc = self._lib.plvs_orb_extract_batch_color(self._h, B, C.c_void_p(images.ctypes.data), W, H, images.strides[1], images.strides[0], nch, int(rgb), 0,
+                                                    int(vLappingArea[0]), int(vLappingArea[1]), kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), cap,
+                                                    n.ctypes.data_as(C.c_void_p), mono.ctypes.data_as(C.c_void_p))
+        _lib.check(rc, "plvs_orb_extract_batch_color")
+        return mono, [kps[b, :n[b]] for b in range(B)], [desc[b, :n[b]] for b in range(B)]
+
+    def ComputeStereoFromRGBD(self, depth, bf, frame=0, n=None, keys_un_x=None):
+        """Frame::ComputeStereoFromRGBD (src/Frame.cc:2251-2279) on the device-resident keypoints of `frame` of the last batch.
+        depth: (H,W) float32 host array.  Returns (mvuRight, mvDepth, device pointer of mvuRight)."""
+        depth = np.ascontiguousarray(depth, np.float32)
+        n = self.device_result(frame).n if n is None else n
+        ur = np.empty(max(n, 1), np.float32); dz = np.empty(max(n, 1), np.float32)
+        dptr = C.c_void_p()
+        un = None if keys_un_x is None else np.ascontiguousarray(keys_un_x, np.float32)
+        rc = self._lib.plvs_orb_stereo_from_rgbd(self._h, frame, depth.ctypes.data_as(C.c_void_p), depth.shape[1], depth.shape[0], depth.strides[0], 0, bf,
+                                                 un.ctypes.data_as(C.c_void_p) if un is not None else None, ur.ctypes.data_as(C.c_void_p), dz.ctypes.data_as(C.c_void_p),
+                                                 C.byref(dptr))
+        _lib.check(rc, "plvs_orb_stereo_from_rgbd")
+        return ur[:n], dz[:n], dptr.value
+
     def pyramid_level(self, level, blurred=False, frame=0):
         """Host copy of mvImagePyramid[level] / mvImagePyramidFiltered[level] of the last extract."""
         w, h, pitch, dptr = C.c_int(), C.c_int(), C.c_int(), C.c_void_p()

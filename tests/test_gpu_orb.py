@@ -140,3 +140,43 @@ def test_cuda_vs_compiled_reference_live(gpu):
         assert np.array_equal(desc, rdesc)
         for l in range(8):
             assert np.array_equal(ex.pyramid_level(l), ref.level(l))
+
+
+def test_color_input_and_stereo_from_rgbd(gpu):
+    """steps either side of the extraction (§8f rank 2): cvtColor fused in front of the pyramid (== the real cv2.cvtColor), and
+    Frame::ComputeStereoFromRGBD on the device-resident keypoints feeding the matcher's right-coordinate gate"""
+    import cv2
+    from plvs_b200 import scenario
+    from plvs_b200.matcher import ORBmatcher, Frame
+    from oracle import match as OM
+    w, h = 640, 480
+    K = synth.intrinsics(w, h)
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    for nch, rgb, code in ((3, False, cv2.COLOR_BGR2GRAY), (3, True, cv2.COLOR_RGB2GRAY), (4, False, cv2.COLOR_BGRA2GRAY)):
+        rng = np.random.default_rng(nch + int(rgb))
+        gray0 = synth.gray_frame(7, w, h)
+        col = np.stack([gray0, np.roll(gray0, 5, 1), (255 - gray0)] + ([gray0] if nch == 4 else []), -1)
+        col = np.ascontiguousarray(np.clip(col.astype(np.int16) + rng.integers(-20, 20, col.shape), 0, 255).astype(np.uint8))
+        want_gray = cv2.cvtColor(col, code)
+        assert np.array_equal(want_gray, O.color_to_gray(col, rgb))
+        mono, kps, descs = ex.extract_batch_color(col[None], rgb=rgb)
+        assert np.array_equal(ex.pyramid_level(0), want_gray)
+        mono2, kp2, desc2 = ORBextractor(1000, 1.2, 8, 20, 7)(want_gray)
+        assert mono[0] == mono2 and np.array_equal(kps[0], kp2) and np.array_equal(descs[0], desc2)
+    # ComputeStereoFromRGBD on the keypoints that are still on the device
+    img = synth.gray_frame(11, w, h); depth = synth.depth_frame(11, w, h)
+    mono, kp, desc = ex(img)
+    ur, dz, dptr = ex.ComputeStereoFromRGBD(depth, K["bf"])
+    our, odz = scenario.uright_from_depth(kp, depth, K["bf"])
+    assert np.array_equal(ur, our) and np.array_equal(dz, odz) and (ur > 0).sum() > 500
+    # ... and the device copy drives the matcher's xR gate exactly like the host array
+    kp0, desc0, _, _ = O.extract_port(synth.gray_frame(10, w, h), 1000)
+    tab = O.Tables(1000)
+    last = scenario.make_frame(kp0, desc0, synth.depth_frame(10, w, h), K, tab.scale)
+    cur = scenario.make_frame(kp, desc, depth, K, tab.scale)
+    q, _ = scenario.last_queries(last, cur, K, synth.pose(10), synth.pose(11))
+    dv = ex.device_result(0)
+    dcur = Frame(None, None, w, h, ex.GetScaleFactors(), bf=K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, dptr, dv.cache_key))
+    n, assign = ORBmatcher(0.9, True).SearchByProjectionLast(dcur, q, 15.0)
+    on, oassign = OM.search_by_projection_last(cur, q, 15.0)
+    assert n == on and np.array_equal(assign, oassign)

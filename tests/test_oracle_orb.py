@@ -110,3 +110,18 @@ def test_descriptor_bit_order_and_steering():
     assert np.array_equal(d, want)
     a, b = O.steer(90.0)
     assert abs(a) < 1e-6 and abs(b - 1) < 1e-6
+
+
+def test_color_to_gray_matches_cv2_for_every_colour():
+    """cv::cvtColor(COLOR_BGR2GRAY / RGB2GRAY / BGRA2GRAY / RGBA2GRAY) (src/Tracking.cc:1797-1810): all 2^24 colours"""
+    vals = np.arange(256, dtype=np.uint8)
+    B, G = np.meshgrid(vals, vals, indexing="ij")
+    for r0 in range(256):
+        cube = np.stack([B, G, np.full_like(B, r0)], -1)
+        assert np.array_equal(cv2.cvtColor(cube, cv2.COLOR_BGR2GRAY), O.color_to_gray(cube))
+        if r0 % 16 == 0:
+            assert np.array_equal(cv2.cvtColor(cube, cv2.COLOR_RGB2GRAY), O.color_to_gray(cube, rgb=True))
+    rng = np.random.default_rng(4)
+    img4 = rng.integers(0, 256, (120, 160, 4), dtype=np.uint8)
+    assert np.array_equal(cv2.cvtColor(img4, cv2.COLOR_BGRA2GRAY), O.color_to_gray(img4))
+    assert np.array_equal(cv2.cvtColor(img4, cv2.COLOR_RGBA2GRAY), O.color_to_gray(img4, rgb=True))
