@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -41,6 +42,22 @@ __device__ __forceinline__ void tma_mbar_wait(uint32_t bar, uint32_t parity)
     asm volatile("{\n.reg .pred P1;\nTMA_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra TMA_DONE;\nbra TMA_WAIT;\nTMA_DONE:\n}" ::"r"(bar), "r"(parity) : "memory");
 }
 #endif
+
+// Stream of a handle.  The three kinds of handle run concurrently in a SLAM process (tracking thread, local mapping, dense mapping) and
+// share the SMs.  The matcher's kernels are short and latency-critical (a thread is blocked on every search), the TSDF update is a long
+// persistent kernel that nobody waits for: `rank` 2 = matcher, 1 = extractor, 0 = TSDF maps to CUDA stream priorities (highest for the
+// matcher) unless PLVS_STREAM_PRIORITIES=0.
+inline cudaError_t create_handle_stream(cudaStream_t* st, int rank)
+{
+    const char* e = std::getenv("PLVS_STREAM_PRIORITIES");
+    if (e && e[0] == '0') return cudaStreamCreateWithFlags(st, cudaStreamNonBlocking);
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return cudaStreamCreateWithFlags(st, cudaStreamNonBlocking);
+    // numerically lower = higher priority; spread the three ranks over the available range
+    int prio = least;
+    if (rank == 2) prio = greatest; else if (rank == 1) prio = (least + greatest) / 2;
+    return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio);
+}
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }

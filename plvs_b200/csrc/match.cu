@@ -1009,7 +1009,7 @@ int plvs_match_create(int device, plvs_match** out)
     PLVS_CUDA(cudaSetDevice(device));
     plvs_match* h = new plvs_match();
     h->device = device; h->timer.component = 2;
-    { cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    { cudaError_t e = create_handle_stream(&h->stream, 2);
       if (e != cudaSuccess) { delete h; set_error("stream creation failed: %s", cudaGetErrorString(e)); return PLVS_ENODEV; } }
     *out = h;
     return PLVS_OK;

@@ -281,7 +281,7 @@ int plvs_orb_create(const plvs_orb_params* p, int device, plvs_orb** out)
     { const char* e = getenv("PLVS_FAST_TREE"); o->fast_tree = e && e[0] == '1'; }     // experiment: min/max-tree corner score (DESIGN.md open issue)
     { const char* e = getenv("PLVS_ORB_HOST_DISTRIBUTE"); o->host_distribute = e && e[0] == '1'; }   // A/B aid: run DistributeOctTree on host threads
     build_tables(o);
-    cudaError_t e1 = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking);
+    cudaError_t e1 = create_handle_stream(&o->stream, 1);
     cudaError_t e2 = e1 == cudaSuccess ? cudaEventCreateWithFlags(&o->ev, cudaEventDisableTiming) : e1;
     if (e2 != cudaSuccess) { delete o; set_error("stream/event creation failed: %s", cudaGetErrorString(e2)); return PLVS_ENODEV; }
     *out = o;
