@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cassert>
 #include <cmath>
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -68,6 +69,7 @@ struct KeyPoint {           // same layout as cv::KeyPoint (28 bytes)
 
 enum { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1, BORDER_REFLECT = 2, BORDER_WRAP = 3, BORDER_REFLECT_101 = 4, BORDER_DEFAULT = 4, BORDER_ISOLATED = 16 };
 enum { INTER_NEAREST = 0, INTER_LINEAR = 1 };
+enum { NORM_INF = 1, NORM_L1 = 2, NORM_L2 = 4 };
 
 class _OutputArray;
 
@@ -100,7 +102,8 @@ public:
     size_t step1() const { return step; }
     bool isContinuous() const { return step == (size_t)cols || rows == 1; }
 
-    Mat operator()(const Rect& r) const { Mat m; m.rows = r.height; m.cols = r.width; m.step = step; m.data = data + (size_t)r.y * step + r.x; m.buf = buf; return m; }
+    // signed offsets: the reference takes windows that reach into the border frame around a pyramid level (src/Frame.cc:1886-1916)
+    Mat operator()(const Rect& r) const { Mat m; m.rows = r.height; m.cols = r.width; m.step = step; m.data = data + (std::ptrdiff_t)r.y * (std::ptrdiff_t)step + r.x; m.buf = buf; return m; }
     Mat rowRange(int a, int b) const { return (*this)(Rect(0, a, cols, b - a)); }
     Mat colRange(int a, int b) const { return (*this)(Rect(a, 0, b - a, rows)); }
     Mat row(int i) const { return (*this)(Rect(0, i, cols, 1)); }
@@ -139,6 +142,19 @@ public:
 typedef const _InputArray& InputArray;
 typedef const _OutputArray& OutputArray;
 inline _InputArray noArray() { return _InputArray(); }
+// cv::norm(a, b, NORM_L1) on 8-bit images: sum of absolute differences (exact in integers; OpenCV returns it as double)
+inline double norm(const _InputArray& a_, const _InputArray& b_, int normType)
+{
+    assert(normType == NORM_L1); (void)normType;
+    const Mat a = a_.getMat(), b = b_.getMat();
+    assert(a.rows == b.rows && a.cols == b.cols);
+    long long s = 0;
+    for (int y = 0; y < a.rows; ++y) {
+        const uchar* pa = a.data + (std::ptrdiff_t)y * (std::ptrdiff_t)a.step; const uchar* pb = b.data + (std::ptrdiff_t)y * (std::ptrdiff_t)b.step;
+        for (int x = 0; x < a.cols; ++x) s += pa[x] > pb[x] ? pa[x] - pb[x] : pb[x] - pa[x];
+    }
+    return (double)s;
+}
 
 inline void Mat::copyTo(const _OutputArray& dst) const
 {

@@ -335,3 +335,36 @@ def distinctive_descriptor(desc):
     D = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(2).astype(np.int64)
     med = np.sort(D, axis=1)[:, int(0.5 * (n - 1))]
     return int(np.argmin(med))
+
+
+# ---- Frame::ComputeStereoMatches through the reference's own text (oracle/_ref/libstereo_ref.so) -------------------------------------
+_stereo = None
+
+
+def stereo_ref_available():
+    from . import ref_build
+    return ref_build.build_stereo() is not None
+
+
+def ref_compute_stereo_matches(left, right, nfeatures, mb, mbf, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    """runs the reference's ORBextractor.cc on both rectified images and the reference's Frame::ComputeStereoMatches body on the result.
+    Returns (left keypoints [n,7] float32, mvuRight, mvDepth, number of right keypoints)."""
+    global _stereo
+    if _stereo is None:
+        from . import ref_build
+        so = ref_build.build_stereo()
+        if so is None:
+            raise RuntimeError("oracle/_ref/libstereo_ref.so missing and /root/reference not present")
+        lib()
+        _stereo = C.CDLL(so)
+        _stereo.ref_compute_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                                       C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    left = np.ascontiguousarray(left, np.uint8); right = np.ascontiguousarray(right, np.uint8)
+    cap = 4 * nfeatures
+    keys = np.zeros((cap, 7), np.float32); ur = np.zeros(cap, np.float32); dp = np.zeros(cap, np.float32)
+    nr = C.c_int()
+    n = _stereo.ref_compute_stereo_matches(left.ctypes.data_as(C.c_void_p), right.ctypes.data_as(C.c_void_p), left.shape[1], left.shape[0], left.strides[0],
+                                           nfeatures, scale_factor, nlevels, ini_th, min_th, mb, mbf, keys.ctypes.data_as(C.c_void_p), cap,
+                                           ur.ctypes.data_as(C.c_void_p), dp.ctypes.data_as(C.c_void_p), C.byref(nr))
+    assert n >= 0
+    return keys[:n], ur[:n], dp[:n], nr.value

@@ -12,8 +12,9 @@
 // Parity status: the three searches and DescriptorDistance are PINNED -- tests/test_oracle_vs_reference_match.py checks them
 // bit-exactly against the reference's own src/ORBmatcher.cc, compiled into oracle/_ref/libmatch_ref.so by oracle/ref_build.py
 // (data-model stand-ins in oracle/plvs_standin), and tests/golden/match_ref.npz holds outputs recorded from it.
-// ComputeStereoMatches (below, src/Frame.cc) is "parity unpinned": Frame.cc cannot be compiled without the whole system and
-// the reference has no test vectors for it; known-answer tests only.
+// ComputeStereoMatches (below, src/Frame.cc:1780-1983) is PINNED as well: Frame.cc as a whole cannot be compiled, so
+// oracle/ref_build.py slices exactly that function definition out of it at build time (into the git-ignored oracle/_ref/gen/) and
+// compiles it with the reference's own ORBextractor.cc; tests/test_oracle_vs_reference_stereo.py compares bit-exactly.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

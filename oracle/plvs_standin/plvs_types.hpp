@@ -43,6 +43,8 @@ namespace PLVS2 {
 
 using std::vector; using std::pair; using std::set; using std::unordered_set; using std::tuple; using std::get;     // the reference's headers are written inside `using namespace std`-style code (Fuse's signature uses bare `vector`)
 
+class ORBextractor;          // the reference's own class (include/ORBextractor.h), used through its public mvImagePyramid
+
 class GeometricCamera {
 public:
     float F12[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};      // row-major fundamental matrix, set by the harness
@@ -172,6 +174,15 @@ class Frame : public FrameBase {
 public:
     std::vector<MapPointPtr> mvpMapPoints;
     std::vector<bool> mvbOutlier;
+    // members read / written by Frame::ComputeStereoMatches (src/Frame.cc:1780-1983); its body is compiled from the reference
+    // (oracle/ref_build.py slices it out of Frame.cc at build time into oracle/_ref/gen/), see oracle/ref_stereo_harness.cpp
+    ORBextractor* mpORBextractorLeft = nullptr; ORBextractor* mpORBextractorRight = nullptr;
+    cv::Mat mDescriptorsRight;
+    std::vector<float> mvInvScaleFactors;
+    float mMedianDepth = 0.f;
+    bool mbUseFovCentersKfGenCriterion = false;
+    float ComputeSceneMedianDepth(int q = 2) { (void)q; return 0.f; }
+    void ComputeStereoMatches();
     Sophus::SE3f GetPose() const { return mTcw; }
     Sophus::SE3f GetRelativePoseTrl() { return mTrl; }
     Sophus::SE3f GetRelativePoseTlr() { return mTrl.inverse(); }
@@ -181,6 +192,7 @@ class KeyFrame : public FrameBase {
 public:
     std::vector<MapPointPtr> mvpMapPoints;
     long unsigned int mnId = 0;
+    static constexpr float skFovCenterDistance = 1.5f;      // include/KeyFrame.h; only copied into mMedianDepth
     // src/KeyFrame.cc:1179-1229 (NLeft == -1): the KeyFrame overload has no level filter
     std::vector<std::size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const
     {

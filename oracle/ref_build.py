@@ -94,7 +94,58 @@ def build_match(force=False):
     return str(MATCH_OUT)
 
 
+STEREO_OUT = OUTDIR / "libstereo_ref.so"
+
+
+def _slice_function(text, signature):
+    """the definition that starts with `signature` up to its matching closing brace (comments / strings in that function hold no braces)"""
+    a = text.index(signature)
+    i = text.index("{", a)
+    depth = 0
+    for j in range(i, len(text)):
+        if text[j] == "{":
+            depth += 1
+        elif text[j] == "}":
+            depth -= 1
+            if depth == 0:
+                return text[a:j + 1]
+    raise RuntimeError("unbalanced braces")
+
+
+def build_stereo(force=False):
+    """Frame::ComputeStereoMatches: sliced out of src/Frame.cc at build time into oracle/_ref/gen/ (git-ignored, never committed) and
+    compiled inside oracle/ref_stereo_harness.cpp, together with the reference's ORBextractor.cc and ORBmatcher.cc
+    -> oracle/_ref/libstereo_ref.so."""
+    ref = pathlib.Path("/root/reference")
+    fsrc = ref / "src" / "Frame.cc"
+    if not fsrc.exists():
+        return str(STEREO_OUT) if STEREO_OUT.exists() else None
+    srcs = [fsrc, ref / "src" / "ORBextractor.cc", ref / "src" / "ORBmatcher.cc", ref / "Thirdparty" / "DBoW2" / "DBoW2" / "FeatureVector.cpp",
+            HERE / "ref_stereo_harness.cpp"]
+    deps = srcs + [HERE / "plvs_standin" / "plvs_types.hpp", HERE / "cv_standin" / "opencv2" / "opencv.hpp"]
+    if STEREO_OUT.exists() and not force and all(STEREO_OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return str(STEREO_OUT)
+    from . import build as oracle_build
+    oracle_build.build()
+    gen = OUTDIR / "gen"; obj = OUTDIR / "obj_stereo"
+    gen.mkdir(parents=True, exist_ok=True); obj.mkdir(parents=True, exist_ok=True)
+    body = _slice_function(fsrc.read_text(), "void Frame::ComputeStereoMatches()")
+    (gen / "frame_stereo_slice.inc").write_text("// generated at build time from /root/reference/src/Frame.cc -- do not commit\n" + body + "\n")
+    base = ["-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w"]
+    inc_cv = ["-I", str(HERE / "cv_standin"), "-I", str(ref / "include")]
+    inc_all = ["-I", str(HERE / "plvs_standin"), "-I", str(HERE / "cv_standin"), "-I", str(HERE / "eigen_standin"), "-I", str(ref / "include"), "-I", str(ref),
+               "-I", str(OUTDIR), "-include", str(HERE / "plvs_standin" / "plvs_types.hpp")]
+    objs = []
+    for src, inc in ((srcs[1], inc_cv), (srcs[2], inc_all), (srcs[3], inc_all), (srcs[4], inc_all)):
+        o = obj / (src.stem + ".o")
+        subprocess.check_call(["g++"] + base + inc + ["-c", str(src), "-o", str(o)])
+        objs.append(str(o))
+    subprocess.check_call(["g++", "-shared", "-o", str(STEREO_OUT)] + objs + ["-L", str(HERE), "-l:liboracle.so", "-Wl,-rpath,$ORIGIN/..", "-lm"])
+    return str(STEREO_OUT)
+
+
 if __name__ == "__main__":
     print(build(force="-f" in sys.argv))
     print(build_orb(force="-f" in sys.argv))
     print(build_match(force="-f" in sys.argv))
+    print(build_stereo(force="-f" in sys.argv))
