@@ -8,10 +8,14 @@
 // What is the reference's own code after this: every search in ORBmatcher.cc -- windows and level ranges, the claim checks
 // on mvpMapPoints (Observations()>0), the right-coordinate gate, best/second-best bookkeeping and ratio test, the
 // immediate claim writes, the rotation histogram with ComputeThreeMaxima, the FeatureVector merge-walk, epipole and
-// distance gates of SearchForTriangulation, DescriptorDistance.  What is restated HERE (with the lines it follows):
-//   Frame::GetFeaturesInArea / PosInGrid / AssignFeaturesToGrid        src/Frame.cc:1231-1316, 716-746
+// distance gates of SearchForTriangulation, DescriptorDistance.  The frame grid is the reference's own text too: the definitions of
+// Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (src/Frame.cc:716-805, 1305-1316, 1231-1303) and
+// KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:1179-1229) are sliced out of the reference at build time (oracle/ref_build.py ->
+// oracle/_ref/gen/, git-ignored) and compiled by oracle/ref_grid_slices.cpp against the classes below, which only DECLARE them.
+// What is restated HERE (with the lines it follows):
 //   Pinhole::epipolarConstrain (distance of kp2 to the epipolar line of kp1; the fundamental-matrix product is given)
 //                                                                      src/CameraModels/Pinhole.cpp:125-147
+//   the grid copy of the KeyFrame constructor (src/KeyFrame.cc:173-183), in the harness
 // Poses and the camera are trivial on purpose: the parity harness passes world points that ARE the wanted projections
 // (identity pose, project(p) = (p.x, p.y)), because the drop-in C ABI receives projected queries too (the caller-side
 // shim projects with the reference's own Sophus/camera code, include/plvs_b200.h plvs_last_query).
@@ -38,6 +42,10 @@
 
 #define FRAME_GRID_ROWS 48
 #define FRAME_GRID_COLS 64
+// line features: only so that the tail of Frame::AssignFeaturesToGrid (src/Frame.cc:748-805) compiles; mpLineExtractorLeft stays null
+#define LINE_THETA_GRID_ROWS 36
+#define LINE_D_GRID_COLS 160
+namespace cv { namespace line_descriptor_c { struct KeyLine { float startPointX, startPointY, endPointX, endPointY; }; } }
 
 namespace PLVS2 {
 
@@ -114,59 +122,7 @@ public:
     float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
     DBoW2::FeatureVector mFeatVec;
     Sophus::SE3f mTcw, mTrl;
-    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
 
-    // src/Frame.cc:1305-1316
-    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY)
-    {
-        posX = round((kp.pt.x - mnMinX) * mfGridElementWidthInv);
-        posY = round((kp.pt.y - mnMinY) * mfGridElementHeightInv);
-        if (posX < 0 || posX >= FRAME_GRID_COLS || posY < 0 || posY >= FRAME_GRID_ROWS) return false;
-        return true;
-    }
-    // src/Frame.cc:716-746 (RGB-D / rectified stereo: Nleft == -1)
-    void AssignFeaturesToGrid()
-    {
-        for (int i = 0; i < FRAME_GRID_COLS; i++) for (int j = 0; j < FRAME_GRID_ROWS; j++) mGrid[i][j].clear();
-        for (int i = 0; i < N; i++) {
-            const cv::KeyPoint& kp = mvKeysUn[i];
-            int nGridPosX, nGridPosY;
-            if (PosInGrid(kp, nGridPosX, nGridPosY)) mGrid[nGridPosX][nGridPosY].push_back(i);
-        }
-    }
-    // src/Frame.cc:1231-1303 (Nleft == -1 branch)
-    std::vector<std::size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1, const bool bRight = false) const
-    {
-        std::vector<std::size_t> vIndices;
-        vIndices.reserve(N);
-        float factorX = r, factorY = r;
-        const int nMinCellX = std::max(0, (int)floor((x - mnMinX - factorX) * mfGridElementWidthInv));
-        if (nMinCellX >= FRAME_GRID_COLS) return vIndices;
-        const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)ceil((x - mnMinX + factorX) * mfGridElementWidthInv));
-        if (nMaxCellX < 0) return vIndices;
-        const int nMinCellY = std::max(0, (int)floor((y - mnMinY - factorY) * mfGridElementHeightInv));
-        if (nMinCellY >= FRAME_GRID_ROWS) return vIndices;
-        const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)ceil((y - mnMinY + factorY) * mfGridElementHeightInv));
-        if (nMaxCellY < 0) return vIndices;
-        const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
-        for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
-            for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
-                const std::vector<std::size_t>& vCell = mGrid[ix][iy];
-                if (vCell.empty()) continue;
-                for (size_t j = 0, jend = vCell.size(); j < jend; j++) {
-                    const cv::KeyPoint& kpUn = mvKeysUn[vCell[j]];
-                    if (bCheckLevels) {
-                        if (kpUn.octave < minLevel) continue;
-                        if (kpUn.octave > maxLevel) continue;        // PLVS has ORB-SLAM3's `if(maxLevel>=0)` commented out (src/Frame.cc:1283-1286)
-                    }
-                    const float distx = kpUn.pt.x - x;
-                    const float disty = kpUn.pt.y - y;
-                    if (fabs(distx) < factorX && fabs(disty) < factorY) vIndices.push_back(vCell[j]);
-                }
-            }
-        (void)bRight;
-        return vIndices;
-    }
     bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }      // include/Frame.h / KeyFrame.cc
 };
 
@@ -174,6 +130,16 @@ class Frame : public FrameBase {
 public:
     std::vector<MapPointPtr> mvpMapPoints;
     std::vector<bool> mvbOutlier;
+    // the frame grid: members as in include/Frame.h:345,383,522-524; the three functions are DEFINED by the reference's own text
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS], mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    void* mpLineExtractorLeft = nullptr;
+    int Nlines = 0, NlinesLeft = -1;
+    std::vector<std::size_t> mLineGrid[LINE_D_GRID_COLS][LINE_THETA_GRID_ROWS], mLineGridRight[LINE_D_GRID_COLS][LINE_THETA_GRID_ROWS];
+    std::vector<cv::line_descriptor_c::KeyLine> mvKeyLinesUn, mvKeyLinesRightUn;
+    bool PosLineInGrid(const cv::line_descriptor_c::KeyLine&, int&, int&) { return false; }
+    void AssignFeaturesToGrid();
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
+    std::vector<std::size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1, const bool bRight = false) const;
     // members read / written by Frame::ComputeStereoMatches (src/Frame.cc:1780-1983); its body is compiled from the reference
     // (oracle/ref_build.py slices it out of Frame.cc at build time into oracle/_ref/gen/), see oracle/ref_stereo_harness.cpp
     ORBextractor* mpORBextractorLeft = nullptr; ORBextractor* mpORBextractorRight = nullptr;
@@ -193,33 +159,10 @@ public:
     std::vector<MapPointPtr> mvpMapPoints;
     long unsigned int mnId = 0;
     static constexpr float skFovCenterDistance = 1.5f;      // include/KeyFrame.h; only copied into mMedianDepth
-    // src/KeyFrame.cc:1179-1229 (NLeft == -1): the KeyFrame overload has no level filter
-    std::vector<std::size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const
-    {
-        std::vector<std::size_t> vIndices;
-        vIndices.reserve(N);
-        float factorX = r, factorY = r;
-        const int nMinCellX = std::max(0, (int)floor((x - mnMinX - factorX) * mfGridElementWidthInv));
-        if (nMinCellX >= FRAME_GRID_COLS) return vIndices;
-        const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)ceil((x - mnMinX + factorX) * mfGridElementWidthInv));
-        if (nMaxCellX < 0) return vIndices;
-        const int nMinCellY = std::max(0, (int)floor((y - mnMinY - factorY) * mfGridElementHeightInv));
-        if (nMinCellY >= FRAME_GRID_ROWS) return vIndices;
-        const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)ceil((y - mnMinY + factorY) * mfGridElementHeightInv));
-        if (nMaxCellY < 0) return vIndices;
-        for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
-            for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
-                const std::vector<std::size_t>& vCell = mGrid[ix][iy];
-                for (size_t j = 0, jend = vCell.size(); j < jend; j++) {
-                    const cv::KeyPoint& kpUn = mvKeysUn[vCell[j]];
-                    const float distx = kpUn.pt.x - x;
-                    const float disty = kpUn.pt.y - y;
-                    if (fabs(distx) < r && fabs(disty) < r) vIndices.push_back(vCell[j]);
-                }
-            }
-        (void)bRight;
-        return vIndices;
-    }
+    // include/KeyFrame.h:252-253,436,505; the search is DEFINED by the reference's own text (src/KeyFrame.cc:1179-1229)
+    const int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
+    std::vector<std::vector<std::vector<std::size_t>>> mGrid, mGridRight;
+    std::vector<std::size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;
     Sophus::SE3f GetPose() { return mTcw; }
     Sophus::SE3f GetPoseInverse() { return mTcw.inverse(); }
     Sophus::SE3f GetRightPose() { return mTrl * mTcw; }

@@ -13,6 +13,7 @@ the header of oracle/eigen_standin/Eigen/Core).  Flags mirror the reference's Ub
 On the GPU box /root/reference does not exist: build() then just returns the prebuilt library (or None).
 """
 import pathlib
+import shutil
 import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
@@ -43,6 +44,7 @@ def build(force=False):
     with ThreadPoolExecutor(8) as ex:
         objs = list(ex.map(cc, srcs))
     subprocess.check_call(["g++", "-shared", "-o", str(OUT)] + objs + ["-lm", "-pthread"])
+    shutil.rmtree(objdir, ignore_errors=True)
     return str(OUT)
 
 
@@ -70,6 +72,20 @@ def build_orb(force=False):
 MATCH_OUT = OUTDIR / "libmatch_ref.so"
 
 
+def _write_grid_slices():
+    """Frame / KeyFrame grid functions -> oracle/_ref/gen/*.inc (build intermediates, git-ignored)"""
+    ref = pathlib.Path("/root/reference")
+    gen = OUTDIR / "gen"
+    gen.mkdir(parents=True, exist_ok=True)
+    ftext = (ref / "src" / "Frame.cc").read_text()
+    parts = [_slice_function(ftext, "void Frame::AssignFeaturesToGrid()"), _slice_function(ftext, "bool Frame::PosInGrid("),
+             _slice_function(ftext, "vector<size_t> Frame::GetFeaturesInArea(")]
+    (gen / "frame_grid_slices.inc").write_text("// generated at build time from /root/reference/src/Frame.cc -- do not commit\n" + "\n\n".join(parts) + "\n")
+    ktext = (ref / "src" / "KeyFrame.cc").read_text()
+    (gen / "keyframe_grid_slice.inc").write_text("// generated at build time from /root/reference/src/KeyFrame.cc -- do not commit\n" +
+                                                 _slice_function(ktext, "vector<size_t> KeyFrame::GetFeaturesInArea(") + "\n")
+
+
 def build_match(force=False):
     """src/ORBmatcher.cc + Thirdparty/DBoW2/DBoW2/FeatureVector.cpp + oracle/ref_match_harness.cpp -> oracle/_ref/libmatch_ref.so.
     The PLVS data model (Frame/KeyFrame/MapPoint/GeometricCamera) comes from oracle/plvs_standin/plvs_types.hpp, force-included
@@ -78,19 +94,21 @@ def build_match(force=False):
     src = ref / "src" / "ORBmatcher.cc"
     if not src.exists():
         return str(MATCH_OUT) if MATCH_OUT.exists() else None
-    srcs = [src, ref / "Thirdparty" / "DBoW2" / "DBoW2" / "FeatureVector.cpp", HERE / "ref_match_harness.cpp"]
-    deps = srcs + [HERE / "plvs_standin" / "plvs_types.hpp", HERE / "plvs_standin" / "sophus" / "se3.hpp",
+    srcs = [src, ref / "Thirdparty" / "DBoW2" / "DBoW2" / "FeatureVector.cpp", HERE / "ref_match_harness.cpp", HERE / "ref_grid_slices.cpp"]
+    deps = srcs + [ref / "src" / "Frame.cc", ref / "src" / "KeyFrame.cc", HERE / "plvs_standin" / "plvs_types.hpp", HERE / "plvs_standin" / "sophus" / "se3.hpp",
                    HERE / "cv_standin" / "opencv2" / "opencv.hpp", HERE / "eigen_standin" / "Eigen" / "Core", HERE / "eigen_standin" / "Eigen" / "Geometry"]
     if MATCH_OUT.exists() and not force and all(MATCH_OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return str(MATCH_OUT)
     from . import build as oracle_build
     oracle_build.build()
     OUTDIR.mkdir(parents=True, exist_ok=True)
+    _write_grid_slices()
     flags = ["-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w",
              "-I", str(HERE / "plvs_standin"), "-I", str(HERE / "cv_standin"), "-I", str(HERE / "eigen_standin"),
-             "-I", str(ref / "include"), "-I", str(ref), "-include", str(HERE / "plvs_standin" / "plvs_types.hpp")]
+             "-I", str(ref / "include"), "-I", str(ref), "-I", str(OUTDIR), "-include", str(HERE / "plvs_standin" / "plvs_types.hpp")]
     subprocess.check_call(["g++"] + flags + ["-shared", "-o", str(MATCH_OUT)] + [str(x) for x in srcs] +
                           ["-L", str(HERE), "-l:liboracle.so", "-Wl,-rpath,$ORIGIN/..", "-lm"])
+    shutil.rmtree(OUTDIR / "gen", ignore_errors=True)        # the slices are build intermediates: nothing of the reference's text stays behind
     return str(MATCH_OUT)
 
 
@@ -121,14 +139,15 @@ def build_stereo(force=False):
     if not fsrc.exists():
         return str(STEREO_OUT) if STEREO_OUT.exists() else None
     srcs = [fsrc, ref / "src" / "ORBextractor.cc", ref / "src" / "ORBmatcher.cc", ref / "Thirdparty" / "DBoW2" / "DBoW2" / "FeatureVector.cpp",
-            HERE / "ref_stereo_harness.cpp"]
-    deps = srcs + [HERE / "plvs_standin" / "plvs_types.hpp", HERE / "cv_standin" / "opencv2" / "opencv.hpp"]
+            HERE / "ref_stereo_harness.cpp", HERE / "ref_grid_slices.cpp"]
+    deps = srcs + [ref / "src" / "KeyFrame.cc", HERE / "plvs_standin" / "plvs_types.hpp", HERE / "cv_standin" / "opencv2" / "opencv.hpp"]
     if STEREO_OUT.exists() and not force and all(STEREO_OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return str(STEREO_OUT)
     from . import build as oracle_build
     oracle_build.build()
     gen = OUTDIR / "gen"; obj = OUTDIR / "obj_stereo"
     gen.mkdir(parents=True, exist_ok=True); obj.mkdir(parents=True, exist_ok=True)
+    _write_grid_slices()
     body = _slice_function(fsrc.read_text(), "void Frame::ComputeStereoMatches()")
     (gen / "frame_stereo_slice.inc").write_text("// generated at build time from /root/reference/src/Frame.cc -- do not commit\n" + body + "\n")
     base = ["-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w"]
@@ -136,11 +155,13 @@ def build_stereo(force=False):
     inc_all = ["-I", str(HERE / "plvs_standin"), "-I", str(HERE / "cv_standin"), "-I", str(HERE / "eigen_standin"), "-I", str(ref / "include"), "-I", str(ref),
                "-I", str(OUTDIR), "-include", str(HERE / "plvs_standin" / "plvs_types.hpp")]
     objs = []
-    for src, inc in ((srcs[1], inc_cv), (srcs[2], inc_all), (srcs[3], inc_all), (srcs[4], inc_all)):
+    for src, inc in ((srcs[1], inc_cv), (srcs[2], inc_all), (srcs[3], inc_all), (srcs[4], inc_all), (srcs[5], inc_all)):
         o = obj / (src.stem + ".o")
         subprocess.check_call(["g++"] + base + inc + ["-c", str(src), "-o", str(o)])
         objs.append(str(o))
     subprocess.check_call(["g++", "-shared", "-o", str(STEREO_OUT)] + objs + ["-L", str(HERE), "-l:liboracle.so", "-Wl,-rpath,$ORIGIN/..", "-lm"])
+    shutil.rmtree(OUTDIR / "gen", ignore_errors=True)
+    shutil.rmtree(obj, ignore_errors=True)
     return str(STEREO_OUT)
 
 

@@ -30,7 +30,7 @@ struct LastQuery { float u, v, invz; int32_t last_octave; float angle; uint32_t 
 struct FuseQuery { float u, v, ur; int32_t level; uint8_t desc[32]; };
 struct FeatVec { int32_t n_nodes; const uint32_t* node_ids; const int32_t* offsets; const int32_t* features; };
 
-void fill(FrameBase& f, const FrameView* v)
+void fill_base(FrameBase& f, const FrameView* v)
 {
     f.N = v->n; f.Nleft = -1; f.NLeft = -1;
     f.mvKeysUn.resize(v->n);
@@ -47,7 +47,21 @@ void fill(FrameBase& f, const FrameView* v)
     f.mnMinX = v->min_x; f.mnMinY = v->min_y; f.mnMaxX = v->max_x; f.mnMaxY = v->max_y;
     f.mfGridElementWidthInv = v->grid_inv_w; f.mfGridElementHeightInv = v->grid_inv_h;
     f.mbf = v->bf; f.mb = 0.08f;
-    f.AssignFeaturesToGrid();
+}
+
+void fill(Frame& f, const FrameView* v) { fill_base(f, v); f.AssignFeaturesToGrid(); }
+
+// the keyframe takes its grid from the frame it is made of (KeyFrame::KeyFrame, src/KeyFrame.cc:173-183)
+void fill(KeyFrame& k, const FrameView* v)
+{
+    fill_base(k, v);
+    std::unique_ptr<Frame> F(new Frame());
+    fill(*F, v);
+    k.mGrid.resize(k.mnGridCols);
+    for (int i = 0; i < k.mnGridCols; i++) {
+        k.mGrid[i].resize(k.mnGridRows);
+        for (int j = 0; j < k.mnGridRows; j++) k.mGrid[i][j] = F->mGrid[i][j];
+    }
 }
 
 cv::Mat desc_mat(const uint8_t* d) { cv::Mat m(1, 32, CV_8U); std::memcpy(m.data, d, 32); return m; }
