@@ -326,8 +326,8 @@ def ref_search_by_bow_kf(K1, K2, fv1, fv2, has1, has2, nn_ratio=0.8, check_ori=T
 
 def distinctive_descriptor(desc):
     """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:428-455) for one map point, in numpy: pairwise Hamming distances,
-    median = sorted(row)[int(0.5*(N-1))], first descriptor with the smallest median.  ("parity unpinned": MapPoint.cc cannot be
-    compiled without the whole system; this is an independent restatement used as a known-answer check.)"""
+    median = sorted(row)[int(0.5*(N-1))], first descriptor with the smallest median.  Pinned: tests/test_oracle_vs_reference_match.py
+    compares it with the reference's own function body (sliced out of MapPoint.cc at build time)."""
     d = np.asarray(desc, np.uint8).reshape(-1, 32)
     n = len(d)
     if n == 0:
@@ -368,3 +368,26 @@ def ref_compute_stereo_matches(left, right, nfeatures, mb, mbf, scale_factor=1.2
                                            ur.ctypes.data_as(C.c_void_p), dp.ctypes.data_as(C.c_void_p), C.byref(nr))
     assert n >= 0
     return keys[:n], ur[:n], dp[:n], nr.value
+
+
+def ref_distinctive_descriptor(desc):
+    """the reference's own MapPoint::ComputeDistinctiveDescriptors on an [n,32] uint8 array -> the chosen descriptor (32 bytes)"""
+    l = _ref_lib()
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    out = np.zeros(32, np.uint8)
+    l.ref_distinctive_descriptor.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    l.ref_distinctive_descriptor(d.ctypes.data_as(C.c_void_p), len(d), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def ref_stereo_from_rgbd(keys, depth, bf):
+    """the reference's own Frame::ComputeStereoFromRGBD: keys = KP_DTYPE array, depth [h,w] float32 -> (mvuRight, mvDepth)"""
+    l = _ref_lib()
+    k = np.zeros((len(keys), 7), np.float32)
+    k[:, 0] = keys["x"]; k[:, 1] = keys["y"]; k[:, 2] = keys["size"]
+    d = np.ascontiguousarray(depth, np.float32)
+    ur = np.zeros(max(len(keys), 1), np.float32); dz = np.zeros(max(len(keys), 1), np.float32)
+    l.ref_stereo_from_rgbd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    l.ref_stereo_from_rgbd(k.ctypes.data_as(C.c_void_p), len(keys), d.ctypes.data_as(C.c_void_p), d.shape[1], d.shape[0], bf, ur.ctypes.data_as(C.c_void_p),
+                           dz.ctypes.data_as(C.c_void_p))
+    return ur[:len(keys)], dz[:len(keys)]

@@ -88,6 +88,12 @@ public:
     cv::Mat desc;
     int nObs = 1; bool bad = false;
     float minDist = 0, maxDist = 1e9f;
+    // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:389-461) is DEFINED by the reference's own text (oracle/ref_build.py slices it)
+    std::map<KeyFramePtr, std::tuple<int, int>> mObservations;
+    bool mbBad = false;
+    std::mutex mMutexFeatures;
+    cv::Mat mDescriptor;
+    void ComputeDistinctiveDescriptors();
     int predictedLevel = 0;              // what PredictScale returns (the caller-side shim evaluates the real one)
     int addedIdx = -1;                   // Fuse: AddObservation(pKF, idx) was called with this idx
     MapPoint* fusedWith = nullptr;       // Fuse: the keyframe's map point this one was merged with (either Replace direction)
@@ -149,6 +155,7 @@ public:
     bool mbUseFovCentersKfGenCriterion = false;
     float ComputeSceneMedianDepth(int q = 2) { (void)q; return 0.f; }
     void ComputeStereoMatches();
+    void ComputeStereoFromRGBD(const cv::Mat& imDepth);      // src/Frame.cc:2251-2279, defined by the reference's own text as well
     Sophus::SE3f GetPose() const { return mTcw; }
     Sophus::SE3f GetRelativePoseTrl() { return mTrl; }
     Sophus::SE3f GetRelativePoseTlr() { return mTrl.inverse(); }
@@ -163,6 +170,7 @@ public:
     const int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
     std::vector<std::vector<std::vector<std::size_t>>> mGrid, mGridRight;
     std::vector<std::size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;
+    bool isBad() { return false; }
     Sophus::SE3f GetPose() { return mTcw; }
     Sophus::SE3f GetPoseInverse() { return mTcw.inverse(); }
     Sophus::SE3f GetRightPose() { return mTrl * mTcw; }

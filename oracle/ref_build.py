@@ -79,9 +79,12 @@ def _write_grid_slices():
     gen.mkdir(parents=True, exist_ok=True)
     ftext = (ref / "src" / "Frame.cc").read_text()
     parts = [_slice_function(ftext, "void Frame::AssignFeaturesToGrid()"), _slice_function(ftext, "bool Frame::PosInGrid("),
-             _slice_function(ftext, "vector<size_t> Frame::GetFeaturesInArea(")]
+             _slice_function(ftext, "vector<size_t> Frame::GetFeaturesInArea("), _slice_function(ftext, "void Frame::ComputeStereoFromRGBD(")]
     (gen / "frame_grid_slices.inc").write_text("// generated at build time from /root/reference/src/Frame.cc -- do not commit\n" + "\n\n".join(parts) + "\n")
     ktext = (ref / "src" / "KeyFrame.cc").read_text()
+    mtext = (ref / "src" / "MapPoint.cc").read_text()
+    (gen / "mappoint_slice.inc").write_text("// generated at build time from /root/reference/src/MapPoint.cc -- do not commit\n" +
+                                            _slice_function(mtext, "void MapPoint::ComputeDistinctiveDescriptors()") + "\n")
     (gen / "keyframe_grid_slice.inc").write_text("// generated at build time from /root/reference/src/KeyFrame.cc -- do not commit\n" +
                                                  _slice_function(ktext, "vector<size_t> KeyFrame::GetFeaturesInArea(") + "\n")
 
@@ -95,7 +98,7 @@ def build_match(force=False):
     if not src.exists():
         return str(MATCH_OUT) if MATCH_OUT.exists() else None
     srcs = [src, ref / "Thirdparty" / "DBoW2" / "DBoW2" / "FeatureVector.cpp", HERE / "ref_match_harness.cpp", HERE / "ref_grid_slices.cpp"]
-    deps = srcs + [ref / "src" / "Frame.cc", ref / "src" / "KeyFrame.cc", HERE / "plvs_standin" / "plvs_types.hpp", HERE / "plvs_standin" / "sophus" / "se3.hpp",
+    deps = srcs + [ref / "src" / "Frame.cc", ref / "src" / "KeyFrame.cc", ref / "src" / "MapPoint.cc", HERE / "plvs_standin" / "plvs_types.hpp", HERE / "plvs_standin" / "sophus" / "se3.hpp",
                    HERE / "cv_standin" / "opencv2" / "opencv.hpp", HERE / "eigen_standin" / "Eigen" / "Core", HERE / "eigen_standin" / "Eigen" / "Geometry"]
     if MATCH_OUT.exists() and not force and all(MATCH_OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return str(MATCH_OUT)

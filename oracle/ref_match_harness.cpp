@@ -376,4 +376,31 @@ int ref_search_by_sim3(const FrameView* K1v, const FrameView* K2v, const FuseQue
     return n;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:389-461) on n observed descriptors (one keyframe per observation; the
+// keyframes sit in one array, so the std::map keyed by KeyFrame* iterates them in index order).  Writes the chosen descriptor.
+void ref_distinctive_descriptor(const uint8_t* desc, int n, uint8_t* chosen)
+{
+    std::unique_ptr<KeyFrame[]> kfs(new KeyFrame[n > 0 ? n : 1]);
+    MapPoint mp;
+    for (int i = 0; i < n; ++i) {
+        kfs[i].mDescriptors = desc_mat(desc + (size_t)32 * i);
+        mp.mObservations[&kfs[i]] = std::tuple<int, int>(0, -1);
+    }
+    mp.mDescriptor = cv::Mat(1, 32, CV_8U); std::memset(mp.mDescriptor.data, 0, 32);
+    mp.ComputeDistinctiveDescriptors();
+    std::memcpy(chosen, mp.mDescriptor.data, 32);
+}
+
+// Frame::ComputeStereoFromRGBD (src/Frame.cc:2251-2279): keys = 7 floats per keypoint (mvKeys == mvKeysUn: no distortion)
+void ref_stereo_from_rgbd(const float* keys, int n, const float* depth, int w, int h, float bf, float* uright, float* kdepth)
+{
+    Frame F; F.N = n; F.mbf = bf;
+    F.mvKeys.resize(n);
+    for (int i = 0; i < n; ++i) F.mvKeys[i] = cv::KeyPoint(keys[7 * i], keys[7 * i + 1], keys[7 * i + 2]);
+    F.mvKeysUn = F.mvKeys;
+    cv::Mat im(h, w, 0, (void*)depth, (size_t)w * 4);
+    F.ComputeStereoFromRGBD(im);
+    for (int i = 0; i < n; ++i) { uright[i] = F.mvuRight[i]; kdepth[i] = F.mvDepth[i]; }
+}
+
 }  // extern "C"

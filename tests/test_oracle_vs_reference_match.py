@@ -228,3 +228,33 @@ def test_search_by_bow_kf(frames, nodes):
             rn, rm = OM.ref_search_by_bow_kf(kf1, kf2, fv1, fv2, has1, has2, ratio, check)
             assert n == rn and np.array_equal(m, rm)
     assert n > 50
+
+
+def test_distinctive_descriptor_against_reference_text():
+    """MapPoint::ComputeDistinctiveDescriptors: the numpy restatement (the known-answer check of the CUDA kernel) equals the reference's own
+    function body (sliced out of src/MapPoint.cc at build time) on the chosen descriptor"""
+    rng = np.random.default_rng(21)
+    lists = []
+    for n in [1, 2, 3, 4, 5, 7, 8, 16, 31, 32, 33, 64, 100, 150]:
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        d = np.repeat(base[None], n, 0).copy()
+        d ^= np.packbits(rng.random((n, 256)) < rng.uniform(0.02, 0.3), axis=1)
+        lists.append(d)
+    lists.append(np.repeat(rng.integers(0, 256, (1, 32), dtype=np.uint8), 6, 0))
+    for _ in range(200):
+        lists.append(rng.integers(0, 256, (int(rng.integers(2, 20)), 32), dtype=np.uint8))
+    for d in lists:
+        assert np.array_equal(d[OM.distinctive_descriptor(d)], OM.ref_distinctive_descriptor(d))
+
+
+def test_stereo_from_rgbd_against_reference_text(frames):
+    """Frame::ComputeStereoFromRGBD: scenario.uright_from_depth (what the GPU test compares the kernel with) == the reference's own body"""
+    K, fr = frames
+    for i, f in enumerate((10, 11, 15)):
+        depth = synth.depth_frame(f).copy()
+        depth[::7, ::5] = 0.0                                   # invalid readings
+        keys = fr[i][0].keys
+        ur, dz = scenario.uright_from_depth(keys, depth, K["bf"])
+        rur, rdz = OM.ref_stereo_from_rgbd(keys, depth, K["bf"])
+        assert np.array_equal(ur.view(np.uint32), rur.view(np.uint32)) and np.array_equal(dz.view(np.uint32), rdz.view(np.uint32))
+        assert (ur > 0).sum() > 500 and (ur < 0).sum() > 10
