@@ -359,9 +359,8 @@ def run_b200_arm(a):
     sampler.stop()
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()      # every rank leaves the group here; rank 0 still has the (CPU-only) baseline to time
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32+f32", "data": "synthetic",
@@ -392,8 +391,6 @@ def run_b200_arm(a):
                                              if have_ref else "restatement") +
                                           f"; seconds/frame {json.dumps({k: round(v, 4) for k, v in stages.items()})}; host has {os.cpu_count()} cpus"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
