@@ -65,3 +65,12 @@ def test_reference_reproduces_committed_goldens(name):
     for f in FIELDS:
         assert np.array_equal(kp[f], g["keypoints"][f]), f
     assert np.array_equal(desc, g["descriptors"])
+
+
+@pytest.mark.parametrize("nfeat,sf,nl,ini,mn", [(800, 1.3, 5, 12, 5), (1500, 1.1, 8, 30, 10), (300, 1.2, 3, 20, 7), (600, 1.5, 6, 25, 7)])
+def test_other_extractor_settings(nfeat, sf, nl, ini, mn):
+    """scale factors / level counts / FAST thresholds other than PLVS's defaults: tables, quotas and the per-level geometry follow the constructor"""
+    img = synth.gray_frame(8, 512, 384)
+    r = O.RefExtractor(nfeat, sf, nl, ini, mn)(img)
+    same(r, O.extract_port(img, nfeat, sf, nl, ini, mn)[:3])
+    assert len(r[0]) > 0.5 * nfeat

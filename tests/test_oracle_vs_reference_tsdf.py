@@ -133,3 +133,29 @@ def test_mixed_routes_on_one_map():
             else:
                 o.integrate(d, synth.pose(f), c); r.integrate(d, synth.pose(f), c)
         same(o, r)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(voxel_resolution=0.08, trunc_scale=4.0, weight=2.0, carving_dist=0.1),
+    dict(voxel_resolution=0.03, trunc_scale=8.0, weight=1.0, carving_dist=0.0, trunc_const=0.003),
+    dict(voxel_resolution=0.05, trunc_quad=0.0, trunc_linear=0.0, trunc_const=0.02, trunc_scale=1.0, weight=3.0),     # constant truncation
+])
+def test_parameter_variants(kw):
+    """truncation polynomial, weight (ChiselServer casts it to uint16, ChiselServer.cpp:108), carving distance and resolution other than
+    the bench's: scan with colour, then the point-cloud route on the same map"""
+    w, h = 128, 96
+    K, o, r = pair(w, h, near_plane=0.1, far_plane=3.5, use_color=1, use_carving=1, **kw)
+    for f in (0, 2, 3):
+        d = synth.depth_frame(f, w, h); c = synth.bgr_frame(f, w, h)
+        if f == 3:
+            d = np.maximum(d - np.float32(0.4), 0).astype(np.float32)
+        o.integrate(d, synth.pose(f), c)
+        with quiet():
+            r.integrate(d, synth.pose(f), c)
+        same(o, r)
+    d = synth.depth_frame(5, w, h); c = synth.bgr_frame(5, w, h)
+    xyz, rgb = scenario.cloud_from_depth(d, c, K, step=2)
+    o.integrate_cloud(xyz, rgb, synth.pose(5), d)
+    with quiet():
+        r.integrate_cloud(xyz, rgb, synth.pose(5), d)
+    same(o, r)
