@@ -254,6 +254,30 @@ int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const pl
                              int only_stereo, int coarse, int check_orientation,
                              int32_t* match12, int* nmatches);
 
+/* Frame::isInFrustum(MapPointPtr&, viewingCosLimit) (src/Frame.cc:955-1017, RGB-D / rectified stereo) for a whole local map at once --
+ * the loop of Tracking::SearchLocalPoints that produces the queries of plvs_match_projection_map.
+ * plvs_map_point: GetWorldPos(), GetNormal(), mfMinDistance, mfMaxDistance (the 0.8 / 1.2 factors of Get{Min,Max}DistanceInvariance are
+ * applied inside, src/MapPoint.cc:569-579), flags = PLVS_Q_*, desc = GetDescriptor().  plvs_frustum: mRcw (row-major), mtcw, mOw,
+ * Pinhole parameters, mbf, the viewing-cosine limit, mfScaleFactor / mnScaleLevels (PredictScale, src/MapPoint.cc:598-613; evaluated
+ * without a device logarithm: level thresholds are computed on the host with the host's logf), image bounds mnMinX..mnMaxY.
+ * queries[i] receives mTrackProjX/Y/XR, mTrackDepth, mTrackViewCos, mnTrackScaleLevel of point i; in_view[i] = mbTrackInView; the
+ * caller hands the in-view entries to plvs_match_projection_map in order.  *n_in_view = number of points in view. */
+typedef struct {
+    float xw[3], normal[3];
+    float min_dist, max_dist;
+    uint32_t flags;
+    uint8_t desc[32];
+} plvs_map_point;
+typedef struct {
+    float Rcw[9], tcw[3], Ow[3];
+    float fx, fy, cx, cy;
+    float bf, viewing_cos_limit, scale_factor;
+    int32_t nlevels;
+    float min_x, min_y, max_x, max_y;
+} plvs_frustum;
+int plvs_match_in_frustum(plvs_match* h, const plvs_frustum* fr, const plvs_map_point* pts, int n,
+                          plvs_mp_query* queries, uint8_t* in_view, int* n_in_view);
+
 /* ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFramePtr& pKF, const set<MapPointPtr>& sAlreadyFound, th, ORBdist)
  * (src/ORBmatcher.cc:1996-2122), Tracking::Relocalization.  One query per keyframe map point that is not bad, not in
  * sAlreadyFound and passed the caller-side projection / distance gates (:2024-2046): u, v = project(Tcw * Xw), invz unused (set

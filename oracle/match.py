@@ -391,3 +391,62 @@ def ref_stereo_from_rgbd(keys, depth, bf):
     l.ref_stereo_from_rgbd(k.ctypes.data_as(C.c_void_p), len(keys), d.ctypes.data_as(C.c_void_p), d.shape[1], d.shape[0], bf, ur.ctypes.data_as(C.c_void_p),
                            dz.ctypes.data_as(C.c_void_p))
     return ur[:len(keys)], dz[:len(keys)]
+
+
+# ---- Frame::isInFrustum + MapPoint::PredictScale + Pinhole::project (the query builder of SearchLocalPoints) --------------------------
+MAP_POINT = np.dtype([("xw", "f4", 3), ("normal", "f4", 3), ("min_dist", "f4"), ("max_dist", "f4"), ("flags", "u4"), ("desc", "u1", 32)])
+assert MAP_POINT.itemsize == 68
+
+
+class FrustumC(C.Structure):
+    _fields_ = [("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Ow", C.c_float * 3), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("bf", C.c_float), ("viewing_cos_limit", C.c_float), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float)]
+
+
+def make_frustum(Twc, K, bounds, bf, viewing_cos_limit=0.5, scale_factor=1.2, nlevels=8):
+    """Twc [3,4] float32 -> the members Frame::UpdatePoseMatrices keeps (mRcw = Rwc^T, mtcw = -Rcw*twc, mOw = twc), computed in float64 and rounded"""
+    T = np.asarray(Twc, np.float64).reshape(3, 4)
+    Rcw = T[:, :3].T; tcw = -Rcw @ T[:, 3]
+    f = FrustumC()
+    f.Rcw[:] = [float(np.float32(x)) for x in Rcw.reshape(9)]; f.tcw[:] = [float(np.float32(x)) for x in tcw]; f.Ow[:] = [float(np.float32(x)) for x in T[:, 3]]
+    f.fx, f.fy, f.cx, f.cy = K["fx"], K["fy"], K["cx"], K["cy"]
+    f.bf, f.viewing_cos_limit, f.scale_factor, f.nlevels = bf, viewing_cos_limit, scale_factor, nlevels
+    f.min_x, f.min_y, f.max_x, f.max_y = bounds
+    return f
+
+
+def _frustum_call(fn, fr, pts):
+    p = np.ascontiguousarray(pts, MAP_POINT)
+    q = np.zeros(max(len(p), 1), MP_QUERY); iv = np.zeros(max(len(p), 1), np.uint8)
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    n = fn(C.byref(fr), p.ctypes.data_as(C.c_void_p), len(p), q.ctypes.data_as(C.c_void_p), iv.ctypes.data_as(C.c_void_p))
+    return n, q[:len(p)], iv[:len(p)]
+
+
+def in_frustum(fr, pts):
+    return _frustum_call(_setup().orc_in_frustum, fr, pts)
+
+
+_frustum = None
+
+
+def frustum_ref_available():
+    from . import ref_build
+    return ref_build.build_frustum() is not None
+
+
+def ref_in_frustum(fr, pts):
+    global _frustum
+    if _frustum is None:
+        from . import ref_build
+        _frustum = C.CDLL(ref_build.build_frustum())
+    return _frustum_call(_frustum.ref_in_frustum, fr, pts)
+
+
+def scale_thresholds(scale_factor, nlevels):
+    l = _setup()
+    T = np.zeros(max(nlevels - 1, 1), np.float32)
+    l.orc_scale_thresholds.argtypes = [C.c_float, C.c_int, C.c_void_p]
+    l.orc_scale_thresholds(scale_factor, nlevels, T.ctypes.data_as(C.c_void_p))
+    return T[:nlevels - 1]

@@ -284,6 +284,94 @@ int orc_search_for_triangulation(const FrameView* K1, const FrameView* K2, const
     return nmatches;
 }
 
+// Frame::isInFrustum(MapPointPtr&, viewingCosLimit) (src/Frame.cc:955-1017, Nleft == -1) with MapPoint::PredictScale(dist, Frame*)
+// (src/MapPoint.cc:598-613) and Pinhole::project (src/CameraModels/Pinhole.cpp:61-67): the step that turns the local map into the
+// queries of SearchByProjection(F, vpMapPoints) (Tracking::SearchLocalPoints).  Eigen's 3-term order e0 + (e1 + e2); `log` / `ceil` are the
+// float overloads (`using namespace std` reaches MapPoint.cc).  min_dist / max_dist are mfMinDistance / mfMaxDistance.
+struct MapPointIn { float xw[3], normal[3], min_dist, max_dist; uint32_t flags; uint8_t desc[32]; };
+struct FrustumIn { float Rcw[9], tcw[3], Ow[3], fx, fy, cx, cy, bf, viewing_cos_limit, scale_factor; int32_t nlevels; float min_x, min_y, max_x, max_y; };
+
+static inline int predict_scale(float max_distance, float current_dist, float log_scale_factor, int nlevels)
+{
+    const float ratio = max_distance / current_dist;
+    int nScale = (int)std::ceil(std::log(ratio) / log_scale_factor);        // float log, float division, float ceil
+    if (nScale < 0) nScale = 0; else if (nScale >= nlevels) nScale = nlevels - 1;
+    return nScale;
+}
+
+int orc_in_frustum(const FrustumIn* fr, const MapPointIn* pts, int n, MpQuery* q, uint8_t* in_view)
+{
+    const float L = std::log(fr->scale_factor);
+    const float* R = fr->Rcw;
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) {
+        const MapPointIn& p = pts[i];
+        MpQuery& o = q[i];
+        std::memset(&o, 0, sizeof(o));
+        o.proj_x = -1; o.proj_y = -1; o.flags = p.flags; std::memcpy(o.desc, p.desc, 32);
+        in_view[i] = 0;
+        const float X = p.xw[0], Y = p.xw[1], Z = p.xw[2];
+        const float pcx = (R[0] * X + (R[1] * Y + R[2] * Z)) + fr->tcw[0];
+        const float pcy = (R[3] * X + (R[4] * Y + R[5] * Z)) + fr->tcw[1];
+        const float pcz = (R[6] * X + (R[7] * Y + R[8] * Z)) + fr->tcw[2];
+        const float pc_dist = std::sqrt(pcx * pcx + (pcy * pcy + pcz * pcz));
+        const float invz = 1.0f / pcz;
+        if (pcz < 0.0f) continue;
+        const float u = fr->fx * pcx / pcz + fr->cx, v = fr->fy * pcy / pcz + fr->cy;
+        if (u < fr->min_x || u > fr->max_x) continue;
+        if (v < fr->min_y || v > fr->max_y) continue;
+        o.proj_x = u; o.proj_y = v;
+        const float maxDistance = 1.2f * p.max_dist, minDistance = 0.8f * p.min_dist;
+        const float pox = X - fr->Ow[0], poy = Y - fr->Ow[1], poz = Z - fr->Ow[2];
+        const float dist = std::sqrt(pox * pox + (poy * poy + poz * poz));
+        if (dist < minDistance || dist > maxDistance) continue;
+        const float viewCos = (pox * p.normal[0] + (poy * p.normal[1] + poz * p.normal[2])) / dist;
+        if (viewCos < fr->viewing_cos_limit) continue;
+        o.level = predict_scale(p.max_dist, dist, L, fr->nlevels);
+        o.proj_xr = u - fr->bf * invz;
+        o.track_depth = pc_dist;
+        o.view_cos = viewCos;
+        in_view[i] = 1; ++cnt;
+    }
+    return cnt;
+}
+
+// The device evaluates PredictScale without a logarithm: with g(ratio) = logf(ratio) / L non-decreasing, level = #{k in [0, nlevels-2] : ratio >= T_k}
+// where T_k = the smallest float with ceil(g) > k, found on the HOST with the host's libm (bisection over the ordered positive floats).
+void orc_scale_thresholds(float scale_factor, int nlevels, float* T /*nlevels-1*/)
+{
+    const float L = std::log(scale_factor);
+    for (int k = 0; k + 1 < nlevels; ++k) {
+        uint32_t lo = 0x00800000u, hi = 0x7f7fffffu;            // positive normal floats; predicate false at lo, true at hi
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            float r; std::memcpy(&r, &mid, 4);
+            if (std::ceil(std::log(r) / L) > (float)k) hi = mid; else lo = mid;
+        }
+        std::memcpy(&T[k], &hi, 4);
+    }
+}
+
+// exhaustive check of that equivalence for every float in [lo, hi]: returns the number of ratios where the threshold count differs from
+// the direct formula (0 unless logf is non-monotonic somewhere in the range)
+long long orc_scale_threshold_mismatches(float scale_factor, int nlevels, float lo, float hi)
+{
+    std::vector<float> T(nlevels > 1 ? nlevels - 1 : 1);
+    orc_scale_thresholds(scale_factor, nlevels, T.data());
+    const float L = std::log(scale_factor);
+    uint32_t a, b; std::memcpy(&a, &lo, 4); std::memcpy(&b, &hi, 4);
+    long long bad = 0;
+    for (uint32_t u = a; u <= b; ++u) {
+        float r; std::memcpy(&r, &u, 4);
+        int direct = (int)std::ceil(std::log(r) / L);
+        if (direct < 0) direct = 0; else if (direct >= nlevels) direct = nlevels - 1;
+        int cnt = 0;
+        for (int k = 0; k + 1 < nlevels; ++k) cnt += r >= T[k];
+        bad += cnt != direct;
+    }
+    return bad;
+}
+
 // ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFramePtr& pKF, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1996-2122):
 // queries = the keyframe's map points that passed the caller-side gates, pre-projected (LastQuery records, last_octave = predicted
 // level).  Level window [l-1, l+1], no right-coordinate gate, ANY non-null mvpMapPoints entry blocks, accept if best <= ORBdist.

@@ -168,8 +168,40 @@ def build_stereo(force=False):
     return str(STEREO_OUT)
 
 
+FRUSTUM_OUT = OUTDIR / "libfrustum_ref.so"
+
+
+def build_frustum(force=False):
+    """Frame::isInFrustum + MapPoint::PredictScale / getters + Pinhole::project, sliced out of the reference at build time and compiled
+    against oracle/plvs_standin/plvs_frustum_types.hpp -> oracle/_ref/libfrustum_ref.so"""
+    ref = pathlib.Path("/root/reference")
+    files = [ref / "src" / "Frame.cc", ref / "src" / "MapPoint.cc", ref / "src" / "CameraModels" / "Pinhole.cpp"]
+    if not all(f.exists() for f in files):
+        return str(FRUSTUM_OUT) if FRUSTUM_OUT.exists() else None
+    deps = files + [HERE / "ref_frustum_harness.cpp", HERE / "plvs_standin" / "plvs_frustum_types.hpp", HERE / "eigen_standin" / "Eigen" / "Core"]
+    if FRUSTUM_OUT.exists() and not force and all(FRUSTUM_OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return str(FRUSTUM_OUT)
+    gen = OUTDIR / "gen"
+    gen.mkdir(parents=True, exist_ok=True)
+    ftext, mtext, ptext = (f.read_text() for f in files)
+    parts = [_slice_function(ftext, "bool Frame::isInFrustum(MapPointPtr& pMP, float viewingCosLimit)"),
+             _slice_function(mtext, "int MapPoint::PredictScale(const float &currentDist, Frame* pF)"),
+             _slice_function(mtext, "Eigen::Vector3f MapPoint::GetWorldPos()"), _slice_function(mtext, "Eigen::Vector3f MapPoint::GetNormal()"),
+             _slice_function(mtext, "float MapPoint::GetMinDistanceInvariance()"), _slice_function(mtext, "float MapPoint::GetMaxDistanceInvariance()"),
+             _slice_function(ptext, "Eigen::Vector2f Pinhole::project(const Eigen::Vector3f &v3D) const")]
+    (gen / "frustum_slices.inc").write_text("// generated at build time from the reference -- do not commit\n" + "\n\n".join(parts) + "\n")
+    flags = ["-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w", "-I", str(HERE / "plvs_standin"), "-I", str(HERE / "eigen_standin"),
+             "-I", str(OUTDIR), "-include", str(HERE / "plvs_standin" / "plvs_frustum_types.hpp")]
+    try:
+        subprocess.check_call(["g++"] + flags + ["-shared", "-o", str(FRUSTUM_OUT), str(HERE / "ref_frustum_harness.cpp"), "-lm"])
+    finally:
+        shutil.rmtree(gen, ignore_errors=True)
+    return str(FRUSTUM_OUT)
+
+
 if __name__ == "__main__":
     print(build(force="-f" in sys.argv))
     print(build_orb(force="-f" in sys.argv))
     print(build_match(force="-f" in sys.argv))
     print(build_stereo(force="-f" in sys.argv))
+    print(build_frustum(force="-f" in sys.argv))

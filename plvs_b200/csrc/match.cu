@@ -668,6 +668,57 @@ k_distinctive(const uint8_t* __restrict__ desc, const int32_t* __restrict__ off,
     if (lane == 0) best[pt] = (int)(key & 0xffffu);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Frame::isInFrustum (src/Frame.cc:955-1017) + Pinhole::project (Pinhole.cpp:61-67) + MapPoint::PredictScale (MapPoint.cc:598-613), one thread
+// per map point.  fp32 in the reference's operation order (Eigen's e0 + (e1 + e2), IEEE sqrt and divisions, no contraction).  PredictScale's
+// ceil(logf(ratio) / logf(scaleFactor)) is evaluated as a count of host-computed thresholds (see plvs_match_in_frustum), so no device logarithm
+// has to match glibc's.
+// ---------------------------------------------------------------------------------------------
+struct FrustumDev { plvs_frustum f; float T[PLVS_MAX_LEVELS]; };
+
+__global__ void __launch_bounds__(256)
+k_in_frustum(FrustumDev D, const plvs_map_point* __restrict__ pts, int n, plvs_mp_query* __restrict__ q, uint8_t* __restrict__ in_view, int* __restrict__ count)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const plvs_frustum& fr = D.f;
+    const plvs_map_point p = pts[i];
+    plvs_mp_query o;
+    o.proj_x = -1.f; o.proj_y = -1.f; o.proj_xr = 0.f; o.track_depth = 0.f; o.view_cos = 0.f; o.level = 0; o.flags = p.flags;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) o.desc[k] = p.desc[k];
+    bool in = false;
+    const float X = p.xw[0], Y = p.xw[1], Z = p.xw[2];
+    const float pcx = (fr.Rcw[0] * X + (fr.Rcw[1] * Y + fr.Rcw[2] * Z)) + fr.tcw[0];
+    const float pcy = (fr.Rcw[3] * X + (fr.Rcw[4] * Y + fr.Rcw[5] * Z)) + fr.tcw[1];
+    const float pcz = (fr.Rcw[6] * X + (fr.Rcw[7] * Y + fr.Rcw[8] * Z)) + fr.tcw[2];
+    if (!(pcz < 0.0f)) {
+        const float u = fr.fx * pcx / pcz + fr.cx, v = fr.fy * pcy / pcz + fr.cy;
+        if (!(u < fr.min_x || u > fr.max_x) && !(v < fr.min_y || v > fr.max_y)) {
+            o.proj_x = u; o.proj_y = v;
+            const float maxDistance = 1.2f * p.max_dist, minDistance = 0.8f * p.min_dist;
+            const float pox = X - fr.Ow[0], poy = Y - fr.Ow[1], poz = Z - fr.Ow[2];
+            const float dist = sqrtf(pox * pox + (poy * poy + poz * poz));
+            if (!(dist < minDistance || dist > maxDistance)) {
+                const float viewCos = (pox * p.normal[0] + (poy * p.normal[1] + poz * p.normal[2])) / dist;
+                if (!(viewCos < fr.viewing_cos_limit)) {
+                    const float ratio = p.max_dist / dist;
+                    int lvl = 0;
+                    for (int k = 0; k + 1 < fr.nlevels; ++k) lvl += ratio >= D.T[k];
+                    o.level = lvl;
+                    o.proj_xr = u - fr.bf * (1.0f / pcz);
+                    o.track_depth = sqrtf(pcx * pcx + (pcy * pcy + pcz * pcz));
+                    o.view_cos = viewCos;
+                    in = true;
+                }
+            }
+        }
+    }
+    q[i] = o;
+    in_view[i] = in ? 1 : 0;
+    if (in) atomicAdd(count, 1);
+}
+
 __global__ void k_fill_i32(int32_t* p, int n, int32_t v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 }  // namespace
@@ -821,7 +872,8 @@ struct plvs_match {
     DevBuf<plvs_keypoint> d_keys[2];
     DevBuf<uint8_t> d_desc[2], d_has[2], d_claimed;
     DevBuf<float> d_uright[2], d_f12;
-    DevBuf<uint8_t> d_query;
+    DevBuf<uint8_t> d_query, d_mpts;
+    PinBuf<uint8_t> p_frustum;
     DevBuf<long long> d_trace;        // PLVS_RESOLVE_TRACE=1: phase stamps of k_resolve (development)
     DevBuf<int> d_cell_start, d_sorted, d_kp_cell, d_cand_n, d_claim_a, d_claim_b, d_target, d_state;
     DevBuf<uint32_t> d_cand;
@@ -1063,6 +1115,46 @@ int plvs_match_projection_reloc(plvs_match* h, const plvs_frame_view* cur, const
     plvs_frame_view v = *cur;
     v.uright = nullptr;
     return run_projection<1>(h, &v, q, sizeof(plvs_last_query), nq, th, 0.f, 0, 0.f, 0, 0, check_orientation, claimed_in, assign, nmatches, orb_dist);
+}
+
+int plvs_match_in_frustum(plvs_match* h, const plvs_frustum* fr, const plvs_map_point* pts, int n, plvs_mp_query* queries, uint8_t* in_view, int* n_in_view)
+{
+    if (!h || !fr || !n_in_view || n < 0 || (n && (!pts || !queries || !in_view))) { set_error("null argument"); return PLVS_EINVAL; }
+    if (fr->nlevels < 1 || fr->nlevels > PLVS_MAX_LEVELS || !(fr->scale_factor > 1.0f)) { set_error("bad pyramid parameters"); return PLVS_EINVAL; }
+    *n_in_view = 0;
+    if (n == 0) return PLVS_OK;
+    std::lock_guard<std::mutex> lock(h->mu);
+    PLVS_CUDA(cudaSetDevice(h->device));
+    FrustumDev D{};
+    D.f = *fr;
+    {   // T[k] = smallest float ratio with ceil(logf(ratio) / logf(scaleFactor)) > k: bisection over the ordered positive floats with the HOST's logf
+        const float L = std::log(fr->scale_factor);
+        for (int k = 0; k + 1 < fr->nlevels; ++k) {
+            uint32_t lo = 0x00800000u, hi = 0x7f7fffffu;
+            while (hi - lo > 1) {
+                const uint32_t mid = lo + (hi - lo) / 2;
+                float r; std::memcpy(&r, &mid, 4);
+                if (std::ceil(std::log(r) / L) > (float)k) hi = mid; else lo = mid;
+            }
+            std::memcpy(&D.T[k], &hi, 4);
+        }
+    }
+    int rc;
+    cudaStream_t st = h->stream;
+    const size_t qb = sizeof(plvs_mp_query) * (size_t)n;
+    if ((rc = h->d_mpts.alloc(sizeof(plvs_map_point) * (size_t)n)) || (rc = h->d_query.alloc(qb + n + 8)) || (rc = h->p_frustum.alloc(qb + n + 8))) return rc;
+    uint8_t* d_q = h->d_query.p; uint8_t* d_iv = d_q + qb; int* d_cnt = reinterpret_cast<int*>(d_q + ((qb + n + 3) & ~(size_t)3));
+    PLVS_CUDA(cudaMemcpyAsync(h->d_mpts.p, pts, sizeof(plvs_map_point) * (size_t)n, cudaMemcpyHostToDevice, st));
+    PLVS_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
+    k_in_frustum<<<div_up(n, 256), 256, 0, st>>>(D, reinterpret_cast<const plvs_map_point*>(h->d_mpts.p), n, reinterpret_cast<plvs_mp_query*>(d_q), d_iv, d_cnt);
+    PLVS_CUDA(cudaMemcpyAsync(h->p_frustum.h, d_q, ((qb + n + 3) & ~(size_t)3) + 4, cudaMemcpyDeviceToHost, st));
+    PLVS_CUDA(cudaGetLastError());
+    PLVS_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(queries, h->p_frustum.h, qb);
+    std::memcpy(in_view, h->p_frustum.h + qb, (size_t)n);
+    std::memcpy(n_in_view, h->p_frustum.h + ((qb + n + 3) & ~(size_t)3), sizeof(int));
+    h->last_launches = 1;
+    return PLVS_OK;
 }
 
 int plvs_match_projection_sim3(plvs_match* h, const plvs_frame_view* kf, const plvs_last_query* q, int nq, float th, float ratio_hamming,

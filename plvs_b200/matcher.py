@@ -200,6 +200,17 @@ class ORBmatcher:
                                                           best.ctypes.data_as(C.c_void_p)), "plvs_distinctive_descriptors")
         return best[:len(desc_lists)]
 
+    def InFrustum(self, frustum, map_points):
+        """Frame::isInFrustum over a local map (src/Frame.cc:955-1017): `frustum` = a ctypes struct laid out like plvs_frustum, map_points =
+        array of plvs_map_point records -> (n_in_view, queries[MP_QUERY], in_view[uint8])."""
+        pts = np.ascontiguousarray(map_points)
+        assert pts.dtype.itemsize == 68
+        q = np.zeros(max(len(pts), 1), MP_QUERY); iv = np.zeros(max(len(pts), 1), np.uint8)
+        n = C.c_int()
+        _lib.check(self._lib.plvs_match_in_frustum(self._h, C.byref(frustum), pts.ctypes.data_as(C.c_void_p), len(pts), q.ctypes.data_as(C.c_void_p),
+                                                   iv.ctypes.data_as(C.c_void_p), C.byref(n)), "plvs_match_in_frustum")
+        return n.value, q[:len(pts)], iv[:len(pts)]
+
     def SearchBySim3(self, KF1, KF2, q12, q21, valid1, valid2, th):
         """SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (src/ORBmatcher.cc:1555-1772): q12[i1] = map point i1 of KF1 projected into
         KF2 (FUSE_QUERY; `ur` unused), q21 the reverse; valid* = map point present, not bad, not already matched.  Two device searches
