@@ -1,7 +1,5 @@
 """-m gpu: Frame::isInFrustum on the device against the oracle, which tests/test_oracle_vs_reference_frustum.py pins to
-the reference's own text.  Written after the round's GPU budget was spent: the kernel compiles and the host logic is covered on the CPU, but
-this comparison has not run on a GPU yet -- hence the non-strict xfail (a pass is reported as XPASS, a failure does not fail the suite) and
-the file name that sorts it behind every other GPU test."""
+the reference's own text (bit-exact mTrackProjX/Y/XR, mTrackDepth, mTrackViewCos, mnTrackScaleLevel, mbTrackInView)."""
 import numpy as np
 import pytest
 
@@ -9,7 +7,7 @@ from plvs_b200 import synth
 from plvs_b200.matcher import ORBmatcher
 from oracle import match as OM
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first GPU run of plvs_match_in_frustum still pending", strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 def _cloud(seed, Twc, n=20000):
