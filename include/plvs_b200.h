@@ -131,6 +131,12 @@ int plvs_orb_extract_batch_color(plvs_orb* h, int batch, const uint8_t* img, int
 int plvs_orb_stereo_from_rgbd(plvs_orb* h, int frame, const float* depth, int w, int h_, int stride_bytes, int on_device, float bf,
                               const float* keys_un_x, float* uright, float* depth_out, const float** d_uright);
 
+/* Step after extraction (§8f rank 2): Frame::UndistortKeyPoints (src/Frame.cc:1507-1553) on the device-resident keypoints of frame `frame`:
+ * cv::undistortPoints(pts, K, distCoef, Mat(), K) (five iterations in double, pinhole model).  K = fx, fy, cx, cy; dist = the ndist <= 14 float
+ * coefficients of mDistCoef (k1 k2 p1 p2 [k3 [k4 k5 k6 [s1..s4]]]); dist[0] == 0 copies the keypoints like the reference.  keys_un (host, n
+ * records, nullable) receives mvKeysUn; *d_keys_un (nullable) the device copy, valid until the next extraction: use it as plvs_frame_view.keys. */
+int plvs_orb_undistort(plvs_orb* h, int frame, const float K[4], const float* dist, int ndist, plvs_keypoint* keys_un, const plvs_keypoint** d_keys_un);
+
 typedef struct {
     int32_t n;
     const plvs_keypoint* keys;   /* device */

@@ -357,3 +357,13 @@ def color_to_gray(img, rgb=False):
     c0, c1, c2 = (img[..., i].astype(np.int64) for i in range(3))
     b, r = (c2, c0) if rgb else (c0, c2)
     return ((r * 9798 + c1 * 19235 + b * 3735 + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def undistort_points(xy, K4, dist):
+    """Frame::UndistortKeyPoints = cv::undistortPoints(pts, K, dist, None, K): xy [n,2] float32, K4 = (fx, fy, cx, cy), dist = float32 coefficients"""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    k = np.ascontiguousarray(K4, np.float32); d = np.ascontiguousarray(dist, np.float32)
+    out = np.empty_like(xy)
+    lib().orc_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib().orc_undistort_points(_p(xy), len(xy), _p(k), _p(d), len(d), _p(out))
+    return out

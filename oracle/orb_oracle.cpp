@@ -534,4 +534,37 @@ int orc_orb_extract(const uint8_t* gray, int w0, int h0, int stride0,
     return total;
 }
 
+// ---------------------------------------------------------------------------
+// Step after extraction: Frame::UndistortKeyPoints (src/Frame.cc:1507-1553) =
+// cv::undistortPoints(mat, mat, K, distCoef, Mat(), K) on the N x 2 float matrix of keypoint coordinates.
+// OpenCV's routine (cvUndistortPointsInternal, criteria = 5 iterations, no tilt): everything in double,
+// results rounded to float.  Pinned: tests/test_oracle_orb.py compares with the real cv2.undistortPoints.
+// K = fx, fy, cx, cy and dist = k1, k2, p1, p2[, k3[, k4, k5, k6[, s1..s4]]] as the FLOAT values PLVS keeps in
+// its CV_32F matrices.  dist[0] == 0 means "no distortion": the keypoints are copied (Frame.cc:1510-1514).
+// ---------------------------------------------------------------------------
+void orc_undistort_points(const float* xy, int n, const float* K, const float* dist, int ndist, float* out)
+{
+    if (ndist <= 0 || dist[0] == 0.0f) { std::memcpy(out, xy, sizeof(float) * 2 * (size_t)n); return; }
+    const double fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    double k[14] = {0};
+    for (int i = 0; i < ndist && i < 14; ++i) k[i] = dist[i];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    for (int i = 0; i < n; ++i) {
+        const double u = xy[2 * i], v = xy[2 * i + 1];
+        double x = (u - cx) * ifx, y = (v - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; ++j) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        const double xx = fx * x + 0 * y + cx, yy = 0 * x + fy * y + cy, ww = 1. / (0 * x + 0 * y + 1);
+        out[2 * i] = (float)(xx * ww); out[2 * i + 1] = (float)(yy * ww);
+    }
+}
+
 }  // extern "C"

@@ -37,6 +37,8 @@ struct plvs_orb {
     int sel_cap = 0;                 // keypoint capacity per frame
     DevBuf<uint8_t> d_pyr, d_blur, d_dbg_score, d_color;
     DevBuf<float> d_uright, d_kdepth, d_depth_img, d_keys_un_x;
+    DevBuf<plvs_keypoint> d_kp_un;       // mvKeysUn of the last batch (plvs_orb_undistort)
+    PinBuf<plvs_keypoint> p_kp_un;
     PinBuf<float> p_uright;
     bool debug = false;
     DevBuf<LevelGeom> d_lv;
@@ -603,6 +605,35 @@ int plvs_orb_stereo_from_rgbd(plvs_orb* o, int frame, const float* depth, int w,
     if (uright) std::memcpy(uright, o->p_uright.h, (size_t)n * 4);
     if (depth_out) std::memcpy(depth_out, o->p_uright.h + cap, (size_t)n * 4);
     if (d_uright) *d_uright = du;
+    return PLVS_OK;
+}
+
+int plvs_orb_undistort(plvs_orb* o, int frame, const float K[4], const float* dist, int ndist, plvs_keypoint* keys_un, const plvs_keypoint** d_keys_un)
+{
+    if (!o || !K || frame < 0 || frame >= o->last_batch || ndist < 0 || ndist > 14 || (ndist && !dist)) { set_error("bad argument"); return PLVS_EINVAL; }
+    if (o->lapped[frame]) { set_error("device keypoints unavailable: they were reordered by the lapping area"); return PLVS_ESTATE; }
+    std::lock_guard<std::mutex> lock(o->mu);
+    PLVS_CUDA(cudaSetDevice(o->device));
+    cudaStream_t st = o->stream;
+    const int n = o->n_kp[frame];
+    const size_t cap = (size_t)std::max(o->sel_cap, 1);
+    int rc;
+    if ((rc = o->d_kp_un.alloc(cap * o->last_batch)) || (rc = o->p_kp_un.alloc(cap))) return rc;
+    const plvs_keypoint* src = o->d_kp.p + (size_t)frame * o->sel_cap;
+    plvs_keypoint* dst = o->d_kp_un.p + cap * frame;
+    if (ndist == 0 || dist[0] == 0.0f) {           // mDistCoef(0) == 0: mvKeysUn = mvKeys (src/Frame.cc:1510-1514)
+        if (n) PLVS_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(plvs_keypoint), cudaMemcpyDeviceToDevice, st));
+    } else if (n) {
+        UndistortParams P{};
+        P.fx = K[0]; P.fy = K[1]; P.cx = K[2]; P.cy = K[3];
+        for (int i = 0; i < ndist; ++i) P.k[i] = dist[i];
+        k_undistort_keypoints<<<div_up(n, 256), 256, 0, st>>>(src, n, P, dst);
+    }
+    if (keys_un && n) PLVS_CUDA(cudaMemcpyAsync(o->p_kp_un.h, dst, (size_t)n * sizeof(plvs_keypoint), cudaMemcpyDeviceToHost, st));
+    PLVS_CUDA(cudaGetLastError());
+    PLVS_CUDA(cudaStreamSynchronize(st));
+    if (keys_un && n) std::memcpy(keys_un, o->p_kp_un.h, (size_t)n * sizeof(plvs_keypoint));
+    if (d_keys_un) *d_keys_un = dst;
     return PLVS_OK;
 }
 

@@ -105,6 +105,17 @@ class ORBextractor:
         _lib.check(rc, "plvs_orb_stereo_from_rgbd")
         return ur[:n], dz[:n], dptr.value
 
+    def UndistortKeyPoints(self, K4, dist, frame=0):
+        """Frame::UndistortKeyPoints (src/Frame.cc:1507-1553) on the device-resident keypoints of `frame`: K4 = (fx, fy, cx, cy), dist = mDistCoef.
+        Returns (mvKeysUn[KP_DTYPE], device pointer of mvKeysUn)."""
+        n = self.device_result(frame).n
+        k = np.ascontiguousarray(K4, np.float32); d = np.ascontiguousarray(dist, np.float32)
+        out = np.empty(max(n, 1), KP_DTYPE)
+        dptr = C.c_void_p()
+        _lib.check(self._lib.plvs_orb_undistort(self._h, frame, k.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), len(d), out.ctypes.data_as(C.c_void_p),
+                                                C.byref(dptr)), "plvs_orb_undistort")
+        return out[:n], dptr.value
+
     def pyramid_level(self, level, blurred=False, frame=0):
         """Host copy of mvImagePyramid[level] / mvImagePyramidFiltered[level] of the last extract."""
         w, h, pitch, dptr = C.c_int(), C.c_int(), C.c_int(), C.c_void_p()

@@ -125,3 +125,20 @@ def test_color_to_gray_matches_cv2_for_every_colour():
     img4 = rng.integers(0, 256, (120, 160, 4), dtype=np.uint8)
     assert np.array_equal(cv2.cvtColor(img4, cv2.COLOR_BGRA2GRAY), O.color_to_gray(img4))
     assert np.array_equal(cv2.cvtColor(img4, cv2.COLOR_RGBA2GRAY), O.color_to_gray(img4, rgb=True))
+
+
+def test_undistort_points_matches_cv2():
+    """Frame::UndistortKeyPoints (src/Frame.cc:1507-1553): the restatement of cv::undistortPoints against the real one, bit for bit"""
+    rng = np.random.default_rng(3)
+    pts = np.stack([rng.uniform(-20, 660, 50000), rng.uniform(-20, 500, 50000)], 1).astype(np.float32)
+    cams = [((517.306408, 516.469215, 318.643040, 255.313989), (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)),        # TUM1.yaml
+            ((520.908620, 521.007327, 325.141442, 249.701764), (0.231222, -0.784899, -0.003257, -0.000105, 0.917205)),       # TUM2.yaml
+            ((458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)),                   # EuRoC, 4 coefficients
+            ((500.0, 500.0, 320.0, 240.0), (0.1, -0.2, 0.001, -0.002, 0.05, 0.01, -0.02, 0.003))]                            # rational model
+    for K4, dist in cams:
+        K = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], np.float32)
+        d = np.array(dist, np.float32)
+        want = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, d, None, K).reshape(-1, 2)
+        got = O.undistort_points(pts, K4, d)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(O.undistort_points(pts, cams[0][0], np.zeros(5, np.float32)), pts)      # mDistCoef(0) == 0: copy
