@@ -283,6 +283,11 @@ typedef struct {
 } plvs_frustum;
 int plvs_match_in_frustum(plvs_match* h, const plvs_frustum* fr, const plvs_map_point* pts, int n,
                           plvs_mp_query* queries, uint8_t* in_view, int* n_in_view);
+/* ORBmatcher::SearchByProjection(Frame&, vpMapPoints, th, bFarPoints, thFarPoints) on the queries the last plvs_match_in_frustum call of this
+ * handle left on the device (the in-view points, in order): no host round trip between the two steps of Tracking::SearchLocalPoints.
+ * assign[i] = index into the map-point array given to plvs_match_in_frustum, or -1.  Otherwise as plvs_match_projection_map. */
+int plvs_match_projection_map_resident(plvs_match* h, const plvs_frame_view* F, float th, float nn_ratio, int far_points, float th_far,
+                                       const uint8_t* claimed_in, int32_t* assign, int* nmatches);
 
 /* ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFramePtr& pKF, const set<MapPointPtr>& sAlreadyFound, th, ORBdist)
  * (src/ORBmatcher.cc:1996-2122), Tracking::Relocalization.  One query per keyframe map point that is not bad, not in

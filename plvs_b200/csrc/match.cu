@@ -719,6 +719,38 @@ k_in_frustum(FrustumDev D, const plvs_map_point* __restrict__ pts, int n, plvs_m
     if (in) atomicAdd(count, 1);
 }
 
+// stable compaction of the in-view queries (the order SearchByProjection walks vpMapPoints in): one CTA, block-wide scan in chunks of 1024
+__global__ void __launch_bounds__(1024)
+k_compact_queries(const plvs_mp_query* __restrict__ q, const uint8_t* __restrict__ in_view, int n, plvs_mp_query* __restrict__ out, int32_t* __restrict__ src_index)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += 1024) {
+        const int i = c0 + tid;
+        const int f = (i < n && in_view[i]) ? 1 : 0;
+        int x = f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int pos = s_base + (wid ? s_warp[wid - 1] : 0) + x - f;
+        if (f) { out[pos] = q[i]; src_index[pos] = i; }
+        __syncthreads();
+        if (tid == 1023) s_base += s_warp[31];
+        __syncthreads();
+    }
+}
+
 __global__ void k_fill_i32(int32_t* p, int n, int32_t v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 }  // namespace
@@ -872,8 +904,11 @@ struct plvs_match {
     DevBuf<plvs_keypoint> d_keys[2];
     DevBuf<uint8_t> d_desc[2], d_has[2], d_claimed;
     DevBuf<float> d_uright[2], d_f12;
-    DevBuf<uint8_t> d_query, d_mpts;
+    DevBuf<uint8_t> d_query, d_mpts, d_res_q;
+    DevBuf<int32_t> d_res_src;
+    PinBuf<int32_t> p_res_src;
     PinBuf<uint8_t> p_frustum;
+    int res_n = -1;                   // number of resident (in-view, compacted) queries left by plvs_match_in_frustum
     DevBuf<long long> d_trace;        // PLVS_RESOLVE_TRACE=1: phase stamps of k_resolve (development)
     DevBuf<int> d_cell_start, d_sorted, d_kp_cell, d_cand_n, d_claim_a, d_claim_b, d_target, d_state;
     DevBuf<uint32_t> d_cand;
@@ -931,10 +966,11 @@ int stage_view(plvs_match* h, int slot, const plvs_frame_view* v, ViewDev* out)
 template <int MODE>
 int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_t qsize, int nq, float th, float nn_ratio,
                    int far_points, float th_far, int forward, int backward, int check_ori,
-                   const uint8_t* claimed_in, int32_t* assign, int* nmatches, int th_high = TH_HIGH)
+                   const uint8_t* claimed_in, int32_t* assign, int* nmatches, int th_high = TH_HIGH, bool q_on_device = false)
 {
     if (!h || !F || !assign || !nmatches || nq < 0 || (nq && !q)) { set_error("null/invalid argument"); return PLVS_EINVAL; }
-    std::lock_guard<std::mutex> lock(h->mu);
+    std::unique_lock<std::mutex> lock(h->mu, std::defer_lock);
+    if (!q_on_device) lock.lock();            // the resident entry point already holds the handle's mutex
     PLVS_CUDA(cudaSetDevice(h->device));
     ViewDev V;
     int rc = stage_view(h, 0, F, &V);
@@ -944,8 +980,12 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
     for (int i = 0; i < n; ++i) assign[i] = -1;
     if (n == 0 || nq == 0) return PLVS_OK;
     cudaStream_t st = h->stream;
-    if ((rc = h->d_query.alloc(qsize * nq))) return rc;
-    PLVS_CUDA(cudaMemcpyAsync(h->d_query.p, q, qsize * nq, cudaMemcpyHostToDevice, st));
+    const void* dq = q;                        // device-resident queries (plvs_match_in_frustum) are used where they are
+    if (!q_on_device) {
+        if ((rc = h->d_query.alloc(qsize * nq))) return rc;
+        PLVS_CUDA(cudaMemcpyAsync(h->d_query.p, q, qsize * nq, cudaMemcpyHostToDevice, st));
+        dq = h->d_query.p;
+    }
     const uint8_t* d_claimed = nullptr;
     if (claimed_in) {
         if ((rc = h->d_claimed.alloc(n))) return rc;
@@ -967,7 +1007,7 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
     for (;;) {
         if ((rc = h->d_cand.alloc((size_t)nq * h->cap))) return rc;
         h->timer.begin(PLVS_MATCH_K_CANDIDATES, st);
-        k_candidates<MODE><<<div_up(nq, 8), 256, 0, st>>>(V, h->d_cell_start.p, h->d_sorted.p, h->d_query.p, nq, th, far_points, th_far, forward, backward,
+        k_candidates<MODE><<<div_up(nq, 8), 256, 0, st>>>(V, h->d_cell_start.p, h->d_sorted.p, dq, nq, th, far_points, th_far, forward, backward,
                                                            h->d_cand.p, h->d_cand_n.p, h->cap);
         h->timer.end(st);
         ++launches;
@@ -988,10 +1028,10 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
                     PLVS_CUDA(cudaFuncSetAttribute(k_resolve<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     attr_set[MODE] = true;
                 }
-                k_resolve<MODE, true><<<kResolveCtas, 1024, smem, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori, th_high,
+                k_resolve<MODE, true><<<kResolveCtas, 1024, smem, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, dq, nq, V.keys, n, d_claimed, nn_ratio, check_ori, th_high,
                                                                         h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta, lpq, h->d_trace.p);
             } else if (per_cta <= 1024) {
-                k_resolve<MODE, false><<<kResolveCtas, 1024, smem_small, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, h->d_query.p, nq, V.keys, n, d_claimed, nn_ratio, check_ori, th_high,
+                k_resolve<MODE, false><<<kResolveCtas, 1024, smem_small, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, dq, nq, V.keys, n, d_claimed, nn_ratio, check_ori, th_high,
                                                                       h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta, lpq, h->d_trace.p);
             } else { set_error("more than %d queries per search are not supported", kResolveCtas * 1024); return PLVS_EINVAL; }
         }
@@ -1147,13 +1187,33 @@ int plvs_match_in_frustum(plvs_match* h, const plvs_frustum* fr, const plvs_map_
     PLVS_CUDA(cudaMemcpyAsync(h->d_mpts.p, pts, sizeof(plvs_map_point) * (size_t)n, cudaMemcpyHostToDevice, st));
     PLVS_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
     k_in_frustum<<<div_up(n, 256), 256, 0, st>>>(D, reinterpret_cast<const plvs_map_point*>(h->d_mpts.p), n, reinterpret_cast<plvs_mp_query*>(d_q), d_iv, d_cnt);
+    // the in-view queries stay on the device, compacted in order, for plvs_match_projection_map_resident
+    if ((rc = h->d_res_q.alloc(qb)) || (rc = h->d_res_src.alloc(n)) || (rc = h->p_res_src.alloc(n))) return rc;
+    k_compact_queries<<<1, 1024, 0, st>>>(reinterpret_cast<const plvs_mp_query*>(d_q), d_iv, n, reinterpret_cast<plvs_mp_query*>(h->d_res_q.p), h->d_res_src.p);
+    PLVS_CUDA(cudaMemcpyAsync(h->p_res_src.h, h->d_res_src.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     PLVS_CUDA(cudaMemcpyAsync(h->p_frustum.h, d_q, ((qb + n + 3) & ~(size_t)3) + 4, cudaMemcpyDeviceToHost, st));
     PLVS_CUDA(cudaGetLastError());
     PLVS_CUDA(cudaStreamSynchronize(st));
     std::memcpy(queries, h->p_frustum.h, qb);
     std::memcpy(in_view, h->p_frustum.h + qb, (size_t)n);
     std::memcpy(n_in_view, h->p_frustum.h + ((qb + n + 3) & ~(size_t)3), sizeof(int));
-    h->last_launches = 1;
+    h->res_n = *n_in_view;
+    h->last_launches = 2;
+    return PLVS_OK;
+}
+
+int plvs_match_projection_map_resident(plvs_match* h, const plvs_frame_view* F, float th, float nn_ratio, int far_points, float th_far,
+                                       const uint8_t* claimed_in, int32_t* assign, int* nmatches)
+{
+    if (!h || !F || !assign || !nmatches) { set_error("null argument"); return PLVS_EINVAL; }
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (h->res_n < 0) { set_error("no resident queries: call plvs_match_in_frustum on this handle first"); return PLVS_ESTATE; }
+    if (h->res_n == 0) { *nmatches = 0; for (int i = 0; i < F->n; ++i) assign[i] = -1; return PLVS_OK; }
+    const int rc = run_projection<0>(h, F, h->d_res_q.p, sizeof(plvs_mp_query), h->res_n, th, nn_ratio, far_points, th_far, 0, 0, 1, claimed_in, assign, nmatches,
+                                     TH_HIGH, true);
+    if (rc) return rc;
+    // assign[] holds positions in the compacted list: map them back to indices of the caller's map-point array
+    for (int i = 0; i < F->n; ++i) if (assign[i] >= 0) assign[i] = h->p_res_src.h[assign[i]];
     return PLVS_OK;
 }
 

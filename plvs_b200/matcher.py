@@ -211,6 +211,18 @@ class ORBmatcher:
                                                    iv.ctypes.data_as(C.c_void_p), C.byref(n)), "plvs_match_in_frustum")
         return n.value, q[:len(pts)], iv[:len(pts)]
 
+    def SearchByProjectionMapResident(self, F, th=3.0, bFarPoints=False, thFarPoints=50.0, claimed=None, nnratio=None):
+        """SearchByProjection(F, vpMapPoints, ...) on the queries the last InFrustum call of this matcher left on the device.
+        -> (nmatches, assign[N]) with assign[i] = index into the map-point array given to InFrustum."""
+        assign = np.full(max(F.n, 1), -1, np.int32)
+        nm = C.c_int()
+        v = F.view()
+        cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+        _lib.check(self._lib.plvs_match_projection_map_resident(self._h, C.byref(v), th, self.mfNNratio if nnratio is None else nnratio, int(bFarPoints), thFarPoints,
+                                                                cl.ctypes.data_as(C.c_void_p) if cl is not None else None, assign.ctypes.data_as(C.c_void_p), C.byref(nm)),
+                   "plvs_match_projection_map_resident")
+        return nm.value, assign[:F.n]
+
     def SearchBySim3(self, KF1, KF2, q12, q21, valid1, valid2, th):
         """SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (src/ORBmatcher.cc:1555-1772): q12[i1] = map point i1 of KF1 projected into
         KF2 (FUSE_QUERY; `ur` unused), q21 the reverse; valid* = map point present, not bad, not already matched.  Two device searches

@@ -31,3 +31,46 @@ def test_undistort_keypoints_on_device(gpu):
         assert dptr
     un, _ = ex.UndistortKeyPoints((517.3, 516.5, 318.6, 255.3), np.zeros(5, np.float32))
     assert np.array_equal(un, kp)
+
+
+def test_search_local_points_resident(gpu):
+    """Tracking::SearchLocalPoints without a host round trip: plvs_match_in_frustum leaves the in-view queries on the device (compacted in order)
+    and plvs_match_projection_map_resident searches with them; result == oracle isInFrustum -> host compaction -> oracle SearchByProjection"""
+    from plvs_b200 import scenario
+    from plvs_b200.matcher import ORBmatcher
+    from oracle import match as OM
+    w, h = 640, 480
+    K = synth.intrinsics(w, h)
+    tab = O.Tables(2000)
+    fr = []
+    for f in (10, 11):
+        kp, desc, _, _ = O.extract_port(synth.gray_frame(f), 2000)
+        x = scenario.make_frame(kp, desc, synth.depth_frame(f), K, tab.scale); fr.append(x)
+    last, cur = fr
+    Tl, Tc = synth.pose(10), synth.pose(11)
+    ok = last.depth_at_kp > 0
+    Pw = scenario.backproject(last.keys[ok], last.depth_at_kp[ok], K, Tl)
+    n = len(Pw)
+    pts = np.zeros(n, OM.MAP_POINT)
+    pts["xw"] = Pw
+    Ow = np.asarray(Tl, np.float64).reshape(3, 4)[:, 3]
+    v = Pw.astype(np.float64) - Ow; d = np.linalg.norm(v, axis=1)
+    pts["normal"] = (v / d[:, None]).astype(np.float32)
+    lvl = last.keys["octave"][ok]
+    pts["max_dist"] = (d * tab.scale[lvl]).astype(np.float32); pts["min_dist"] = (pts["max_dist"] / tab.scale[7]).astype(np.float32)
+    rng = np.random.default_rng(1)
+    pts["flags"] = (rng.random(n) < 0.9).astype(np.uint32); pts["desc"] = last.desc[ok]
+    frm = OM.make_frustum(Tc, K, (0.0, 0.0, float(w), float(h)), K["bf"], 0.5, 1.2, 8)
+    claimed = (rng.random(cur.n) < 0.2).astype(np.uint8)
+    m = ORBmatcher(0.8, True)
+    nin, q, iv = m.InFrustum(frm, pts)
+    nm, assign = m.SearchByProjectionMapResident(cur, 3.0, claimed=claimed)
+    on, oq, oiv = OM.in_frustum(frm, pts)
+    assert nin == on and np.array_equal(iv, oiv) and nin > 500
+    src = np.nonzero(oiv)[0]
+    onm, oassign = OM.search_by_projection_map(cur, oq[src], 3.0, 0.8, claimed=claimed)
+    want = np.where(oassign >= 0, src[np.maximum(oassign, 0)], -1)
+    assert nm == onm and np.array_equal(assign, want) and nm > 200
+    # the ordinary entry point with the same (downloaded) queries agrees as well
+    nm2, assign2 = m.SearchByProjectionMap(cur, q[src], 3.0, claimed=claimed)
+    assert nm2 == onm and np.array_equal(assign2, oassign)
