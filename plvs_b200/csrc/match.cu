@@ -904,11 +904,12 @@ struct plvs_match {
     DevBuf<plvs_keypoint> d_keys[2];
     DevBuf<uint8_t> d_desc[2], d_has[2], d_claimed;
     DevBuf<float> d_uright[2], d_f12;
-    DevBuf<uint8_t> d_query, d_mpts, d_res_q;
+    DevBuf<uint8_t> d_query, d_mpts, d_res_q, d_res_raw;
     DevBuf<int32_t> d_res_src;
     PinBuf<int32_t> p_res_src;
     PinBuf<uint8_t> p_frustum;
-    int res_n = -1;                   // number of resident (in-view, compacted) queries left by plvs_match_in_frustum
+    int res_n = -1, res_total = 0;    // in-view / all queries left on the device by plvs_match_in_frustum
+    bool res_compacted = false;
     DevBuf<long long> d_trace;        // PLVS_RESOLVE_TRACE=1: phase stamps of k_resolve (development)
     DevBuf<int> d_cell_start, d_sorted, d_kp_cell, d_cand_n, d_claim_a, d_claim_b, d_target, d_state;
     DevBuf<uint32_t> d_cand;
@@ -1187,18 +1188,17 @@ int plvs_match_in_frustum(plvs_match* h, const plvs_frustum* fr, const plvs_map_
     PLVS_CUDA(cudaMemcpyAsync(h->d_mpts.p, pts, sizeof(plvs_map_point) * (size_t)n, cudaMemcpyHostToDevice, st));
     PLVS_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
     k_in_frustum<<<div_up(n, 256), 256, 0, st>>>(D, reinterpret_cast<const plvs_map_point*>(h->d_mpts.p), n, reinterpret_cast<plvs_mp_query*>(d_q), d_iv, d_cnt);
-    // the in-view queries stay on the device, compacted in order, for plvs_match_projection_map_resident
-    if ((rc = h->d_res_q.alloc(qb)) || (rc = h->d_res_src.alloc(n)) || (rc = h->p_res_src.alloc(n))) return rc;
-    k_compact_queries<<<1, 1024, 0, st>>>(reinterpret_cast<const plvs_mp_query*>(d_q), d_iv, n, reinterpret_cast<plvs_mp_query*>(h->d_res_q.p), h->d_res_src.p);
-    PLVS_CUDA(cudaMemcpyAsync(h->p_res_src.h, h->d_res_src.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    // the queries and flags stay on the device for plvs_match_projection_map_resident (which compacts them on first use)
+    if ((rc = h->d_res_raw.alloc(qb + n))) return rc;
+    PLVS_CUDA(cudaMemcpyAsync(h->d_res_raw.p, d_q, qb + n, cudaMemcpyDeviceToDevice, st));
     PLVS_CUDA(cudaMemcpyAsync(h->p_frustum.h, d_q, ((qb + n + 3) & ~(size_t)3) + 4, cudaMemcpyDeviceToHost, st));
     PLVS_CUDA(cudaGetLastError());
     PLVS_CUDA(cudaStreamSynchronize(st));
     std::memcpy(queries, h->p_frustum.h, qb);
     std::memcpy(in_view, h->p_frustum.h + qb, (size_t)n);
     std::memcpy(n_in_view, h->p_frustum.h + ((qb + n + 3) & ~(size_t)3), sizeof(int));
-    h->res_n = *n_in_view;
-    h->last_launches = 2;
+    h->res_n = *n_in_view; h->res_total = n; h->res_compacted = false;
+    h->last_launches = 1;
     return PLVS_OK;
 }
 
@@ -1209,6 +1209,19 @@ int plvs_match_projection_map_resident(plvs_match* h, const plvs_frame_view* F, 
     std::lock_guard<std::mutex> lock(h->mu);
     if (h->res_n < 0) { set_error("no resident queries: call plvs_match_in_frustum on this handle first"); return PLVS_ESTATE; }
     if (h->res_n == 0) { *nmatches = 0; for (int i = 0; i < F->n; ++i) assign[i] = -1; return PLVS_OK; }
+    if (!h->res_compacted) {       // stable compaction of the in-view queries, once per plvs_match_in_frustum call
+        PLVS_CUDA(cudaSetDevice(h->device));
+        const int n = h->res_total;
+        const size_t qb = sizeof(plvs_mp_query) * (size_t)n;
+        int rc0;
+        if ((rc0 = h->d_res_q.alloc(qb)) || (rc0 = h->d_res_src.alloc(n)) || (rc0 = h->p_res_src.alloc(n))) return rc0;
+        k_compact_queries<<<1, 1024, 0, h->stream>>>(reinterpret_cast<const plvs_mp_query*>(h->d_res_raw.p), h->d_res_raw.p + qb, n,
+                                                     reinterpret_cast<plvs_mp_query*>(h->d_res_q.p), h->d_res_src.p);
+        PLVS_CUDA(cudaMemcpyAsync(h->p_res_src.h, h->d_res_src.p, (size_t)h->res_n * 4, cudaMemcpyDeviceToHost, h->stream));
+        PLVS_CUDA(cudaGetLastError());
+        PLVS_CUDA(cudaStreamSynchronize(h->stream));
+        h->res_compacted = true;
+    }
     const int rc = run_projection<0>(h, F, h->d_res_q.p, sizeof(plvs_mp_query), h->res_n, th, nn_ratio, far_points, th_far, 0, 0, 1, claimed_in, assign, nmatches,
                                      TH_HIGH, true);
     if (rc) return rc;
