@@ -410,6 +410,13 @@ int plvs_tsdf_integrate_depth(plvs_tsdf* h, const float* depth, int w, int h_,
                               const uint8_t* bgr, int bgr_step, int nch,
                               const float Twc[12], int mode, int on_device);
 
+/* Step before the TSDF: the same scan from a 16-bit depth map (TUM / RealSense PNGs) without the host-side
+ * `mImDepth.convertTo(mImDepth, CV_32F, mDepthMapFactor)` of src/Tracking.cc:1812-1813: the raw image goes over the bus (2 bytes per pixel),
+ * `(float)d * depth_factor` runs on the device.  Host pointers only; otherwise as plvs_tsdf_integrate_depth (bgr rows are dense, bgr_stride is
+ * unused as in chisel::ColorImage).  Two steps under the handle's lock: do not interleave with calls on the same handle from another thread. */
+int plvs_tsdf_integrate_depth_u16(plvs_tsdf* h, const uint16_t* depth, int w, int h_, int stride_bytes, float depth_factor,
+                                  const uint8_t* bgr, int bgr_stride, int nch, const float Twc[12], int mode);
+
 /* Chisel::IntegratePointCloudWidthDepth (Thirdparty/open_chisel/src/Chisel.cpp:382-585) as reached through
  * ChiselServer::SetPointCloud + IntegrateLastPointCloud (PLVS's default Chisel route, src/PointCloudMapChisel.cc:100-131):
  * xyz = n camera-frame points (x,y,z float triples), rgb = n colour triples in [0,1] (r,g,b; NULL = no colour),

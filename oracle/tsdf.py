@@ -81,6 +81,13 @@ class Map:
         return keys, sdf, w, rgba
 
 
+def depth_u16_to_f32(d16, factor):
+    """`mImDepth.convertTo(mImDepth, CV_32F, mDepthMapFactor)` (src/Tracking.cc:1812-1813): OpenCV's scaled 16u -> 32f conversion is
+    `(float)src * (float)alpha` with one rounding (beta = 0).  Pinned against cv2's scaled 16u->32f arithmetic in tests/test_oracle_match_tsdf.py
+    (every u16 value); cv::Mat::convertTo itself has no Python binding, so this row is otherwise "parity unpinned"."""
+    return np.asarray(d16, np.uint16).astype(np.float32) * np.float32(factor)
+
+
 def ref_available():
     """oracle/_ref/libchisel_ref.so = the reference's own open_chisel sources (oracle/ref_build.py)."""
     from . import ref_build

@@ -110,6 +110,7 @@ def load():
                                                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.plvs_orb_stereo_from_rgbd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.plvs_match_projection_map_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    lib.plvs_tsdf_integrate_depth_u16.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
     lib.plvs_orb_undistort.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.plvs_match_in_frustum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     lib.plvs_match_fuse_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]

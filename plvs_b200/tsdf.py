@@ -74,6 +74,18 @@ class ChiselServer:
         self._color = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
         self.IntegrateLastDepthImage(False)
 
+    def integrate_u16(self, depth_u16, depth_factor, Twc, bgr=None):
+        """IntegrateLastDepthImage on a raw 16-bit depth map: `convertTo(CV_32F, mDepthMapFactor)` (src/Tracking.cc:1812-1813) runs on the device."""
+        d = np.asarray(depth_u16)
+        if d.dtype != np.uint16 or d.ndim != 2 or d.strides[1] != 2 or d.strides[0] < 2 * d.shape[1]:      # padded rows are passed through as they are
+            d = np.ascontiguousarray(d, np.uint16)
+        T = np.ascontiguousarray(Twc, np.float32).reshape(12)
+        c = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
+        rc = self._lib.plvs_tsdf_integrate_depth_u16(self._h, d.ctypes.data_as(C.c_void_p), d.shape[1], d.shape[0], d.strides[0], depth_factor,
+                                                     c.ctypes.data_as(C.c_void_p) if c is not None else None, c.strides[0] if c is not None else 0, c.shape[2] if c is not None else 0,
+                                                     T.ctypes.data_as(C.c_void_p), SCAN_COLOR if c is not None else SCAN)
+        _lib.check(rc, "plvs_tsdf_integrate_depth_u16")
+
     def integrate_cloud(self, xyz, rgb, Twc, depth=None):
         """SetPointCloud + (SetDepthImageMemorySharing) + IntegrateLastPointCloud(false): Chisel::IntegratePointCloudWidthDepth."""
         xyz = np.ascontiguousarray(xyz, np.float32)

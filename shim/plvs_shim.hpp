@@ -681,13 +681,25 @@ public:
     }
     void SetColorPose(const Eigen::Affine3f& tf) { SetDepthPose(tf); }
     // borrowed buffers: must stay valid until IntegrateLastDepthImage returns (as in the reference)
-    void SetDepthImageMemorySharing(float* img, int width, int height, int /*step*/, uint64_t /*timestamp*/) { depth_ = img; dw_ = width; dh_ = height; }
+    void SetDepthImageMemorySharing(float* img, int width, int height, int /*step*/, uint64_t /*timestamp*/) { depth_ = img; dw_ = width; dh_ = height; depth16_ = nullptr; }
     void SetColorImageMemorySharing(unsigned char* img, int width, int height, int step, int num_channels, uint64_t /*timestamp*/)
     {
         color_ = img; cw_ = width; ch_ = height; cstep_ = step; cn_ = num_channels;
     }
+    // Extension: the raw 16-bit depth map of the sensor; `convertTo(CV_32F, mDepthMapFactor)` (src/Tracking.cc:1812-1813)
+    // then runs on the device.  `depthMapFactor` is Tracking's member after its own `1.0f / factor`.
+    void SetRawDepthImageMemorySharing(const uint16_t* img, int width, int height, int step_bytes, float depthMapFactor, uint64_t /*timestamp*/)
+    {
+        depth16_ = img; dw_ = width; dh_ = height; dstep16_ = step_bytes; dfactor_ = depthMapFactor; depth_ = nullptr;
+    }
     void IntegrateLastDepthImage(bool /*updateMesh*/ = true)
     {
+        if (gotInfo && gotPose && depth16_ && !depth_) {
+            const bool color16 = useColor && color_;
+            plvs_shim::check(plvs_tsdf_integrate_depth_u16(h_, depth16_, dw_, dh_, dstep16_, dfactor_, color16 ? color_ : nullptr, cstep_, cn_, Twc_,
+                                                           color16 ? PLVS_TSDF_SCAN_COLOR : PLVS_TSDF_SCAN), "plvs_tsdf_integrate_depth_u16");
+            return;
+        }
         if (!gotInfo || !gotPose || !depth_) { std::fprintf(stderr, "ChiselServer - PROBLEM in integrating depth scan!!! ************\n"); return; }
         const bool color = useColor && color_;
         plvs_shim::check(plvs_tsdf_integrate_depth(h_, depth_, dw_, dh_, color ? color_ : nullptr, cstep_, cn_, Twc_,
@@ -730,6 +742,7 @@ protected:
     float cloudTwc_[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     float Twc_[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     float* depth_ = nullptr; int dw_ = 0, dh_ = 0;
+    const uint16_t* depth16_ = nullptr; int dstep16_ = 0; float dfactor_ = 1.0f;
     unsigned char* color_ = nullptr; int cw_ = 0, ch_ = 0, cstep_ = 0, cn_ = 0;
     plvs_tsdf* h_ = nullptr;
 };

@@ -102,3 +102,14 @@ def test_tsdf_running_mean_and_block_set():
     assert both.any() and np.allclose(sdf2[both], (1.01 - zc)[both], atol=1e-5)      # mean of the two observations
     st = m.stats()
     assert st["n_collected"] > 0 and st["n_blocks"] == len(keys) + st["n_new"]
+
+
+def test_depth_u16_scale_matches_cv2_for_every_value():
+    """the u16 -> f32 depth scaling in front of the TSDF (src/Tracking.cc:1812-1813): all 65536 values x the factors of the shipped yamls"""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import tsdf as OT
+    v = np.arange(65536, dtype=np.uint16).reshape(256, 256)
+    for yaml_factor in (5000.0, 1000.0, 1.0, 5208.0, 1031.0):
+        f = np.float32(1.0) / np.float32(yaml_factor)                 # Tracking: mDepthMapFactor = 1.0f / mDepthMapFactor
+        want = cv2.multiply(v, float(f), dtype=cv2.CV_32F)
+        assert np.array_equal(OT.depth_u16_to_f32(v, f).view(np.uint32), want.view(np.uint32))

@@ -74,3 +74,28 @@ def test_search_local_points_resident(gpu):
     # the ordinary entry point with the same (downloaded) queries agrees as well
     nm2, assign2 = m.SearchByProjectionMap(cur, q[src], 3.0, claimed=claimed)
     assert nm2 == onm and np.array_equal(assign2, oassign)
+
+
+def test_tsdf_from_raw_u16_depth(gpu):
+    """§8f rank 2: `mImDepth.convertTo(CV_32F, mDepthMapFactor)` (src/Tracking.cc:1812-1813) on the device: the map built from the raw 16-bit
+    image (TUM factor 5000, row padding) is the map built from the host-converted float image, bit for bit, with and without colour"""
+    from plvs_b200 import tsdf as T
+    from oracle import tsdf as OT
+    w, h = 160, 120
+    K = synth.intrinsics(w, h)
+    factor = np.float32(1.0) / np.float32(5000.0)                     # Tracking's `mDepthMapFactor = 1.0f / mDepthMapFactor`
+    for color in (0, 1):
+        p = T.default_params(voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=4096, use_color=color)
+        a, b = T.ChiselServer(p), T.ChiselServer(p)
+        for g in (a, b):
+            g.SetDepthCameraInfo(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
+        for f in (0, 1, 2, 3, 4):
+            padded = np.zeros((h, w + 6), np.uint16)
+            padded[:, :w] = np.clip(synth.depth_frame(f, w, h) * 5000.0, 0, 65535).astype(np.uint16)
+            d16 = padded[:, :w]                                       # a view with a row stride of 2*(w+6) bytes
+            c = synth.bgr_frame(f, w, h) if color else None
+            a.integrate_u16(d16, float(factor), synth.pose(f), c)
+            b.integrate(OT.depth_u16_to_f32(d16, factor), synth.pose(f), c)
+        ka, sa, wa, ca = a.download(); kb, sb, wb, cb = b.download()
+        assert len(ka) > 50 and np.array_equal(ka, kb)
+        assert np.array_equal(sa.view(np.uint32), sb.view(np.uint32)) and np.array_equal(wa.view(np.uint32), wb.view(np.uint32)) and np.array_equal(ca, cb)
