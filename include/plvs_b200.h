@@ -57,6 +57,7 @@ int plvs_set_profiling(int mask);
 #define PLVS_MATCH_K_TRIANGULATE 3
 #define PLVS_MATCH_K_FUSE 4
 #define PLVS_MATCH_K_BOW 5
+#define PLVS_MATCH_K_INIT 6
 #define PLVS_TSDF_K_TILES 0
 #define PLVS_TSDF_K_CLASSIFY 1
 #define PLVS_TSDF_K_INTEGRATE 2
@@ -305,6 +306,13 @@ int plvs_match_projection_reloc(plvs_match* h, const plvs_frame_view* cur, const
  * assign[i] = query written into vpMatched[i] during the call or -1; *nmatches = the return value. */
 int plvs_match_projection_sim3(plvs_match* h, const plvs_frame_view* kf, const plvs_last_query* q, int nq, float th, float ratio_hamming,
                                const uint8_t* matched_in, int32_t* assign, int* nmatches);
+
+/* ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched, vector<int>& vnMatches12, int windowSize)
+ * (src/ORBmatcher.cc:732-852; Tracking::MonocularInitialization, src/Tracking.cc:3003-3004, matcher (0.9, true), window 100).
+ * prev_matched: f1->n cv::Point2f (x, y), in/out -- the positions of the final matches are written back like the reference does;
+ * matches12[i1] (f1->n entries) = index in F2 or -1; *nmatches = the return value. */
+int plvs_match_initialization(plvs_match* h, const plvs_frame_view* f1, const plvs_frame_view* f2, float* prev_matched, int window_size,
+                              float nn_ratio, int check_orientation, int32_t* matches12, int* nmatches);
 
 /* ORBmatcher::SearchByBoW(KeyFramePtr& pKF, Frame& F, vector<MapPointPtr>& vpMapPointMatches) (src/ORBmatcher.cc:300-506),
  * RGB-D / rectified stereo (Nleft == -1): Tracking::TrackReferenceKeyFrame and Relocalization.  fv_kf / fv_f = pKF->mFeatVec /

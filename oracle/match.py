@@ -324,6 +324,26 @@ def ref_search_by_bow_kf(K1, K2, fv1, fv2, has1, has2, nn_ratio=0.8, check_ori=T
     return _bow_kf_call(_ref_lib().ref_search_by_bow_kf, K1, K2, fv1, fv2, has1, has2, nn_ratio, check_ori)
 
 
+def _init_call(fn, F1, F2, prev_matched, window_size, nn_ratio, check_ori):
+    v1, v2 = F1.view(), F2.view()
+    prev = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+    assert len(prev) == F1.n
+    m = np.full(max(F1.n, 1), -1, np.int32)
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    n = fn(C.byref(v1), C.byref(v2), prev.ctypes.data_as(C.c_void_p), int(window_size), nn_ratio, int(check_ori), m.ctypes.data_as(C.c_void_p))
+    return n, m[:F1.n], prev
+
+
+def search_for_initialization(F1, F2, prev_matched, window_size=100, nn_ratio=0.9, check_ori=True):
+    """ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:732-852); Tracking::MonocularInitialization builds the matcher with (0.9, true) and
+    calls it with windowSize 100 (src/Tracking.cc).  Returns (nmatches, vnMatches12, updated vbPrevMatched)."""
+    return _init_call(_setup().orc_search_for_initialization, F1, F2, prev_matched, window_size, nn_ratio, check_ori)
+
+
+def ref_search_for_initialization(F1, F2, prev_matched, window_size=100, nn_ratio=0.9, check_ori=True):
+    return _init_call(_ref_lib().ref_search_for_initialization, F1, F2, prev_matched, window_size, nn_ratio, check_ori)
+
+
 def distinctive_descriptor(desc):
     """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:428-455) for one map point, in numpy: pairwise Hamming distances,
     median = sorted(row)[int(0.5*(N-1))], first descriptor with the smallest median.  Pinned: tests/test_oracle_vs_reference_match.py

@@ -597,6 +597,56 @@ static int fuse_search(const FrameView* K, const float* inv_level_sigma2, const 
     return nfused;
 }
 
+// ---------------------------------------------------------------------------------------------
+// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:732-852): monocular start-up.  Level-0 keypoints of F1 search a square
+// window of F2 around their previously matched position; a candidate is skipped when an earlier accepted match on it was at least
+// as good (vMatchedDistance), the winner may steal a feature from an earlier query (vnMatches21), the rotation histogram keeps every
+// accepted i1 (also the ones stolen later).  prev_matched (cv::Point2f per F1 keypoint) is updated for the final matches.
+// PINNED: tests/test_oracle_vs_reference_match.py runs the reference's own function on the same inputs.
+// ---------------------------------------------------------------------------------------------
+int orc_search_for_initialization(const FrameView* F1, const FrameView* F2, float* prev_matched, int window_size, float nn_ratio, int check_ori,
+                                  int32_t* matches12)
+{
+    int nmatches = 0;
+    for (int i = 0; i < F1->n; ++i) matches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<int> matched_distance(F2->n, INT32_MAX), matches21(F2->n, -1);
+    Grid grid(F2);
+    std::vector<int> cand;
+    for (int i1 = 0; i1 < F1->n; ++i1) {
+        const KeyPoint& kp1 = F1->keys[i1];
+        const int level1 = kp1.octave;
+        if (level1 > 0) continue;
+        grid.in_area(prev_matched[2 * i1], prev_matched[2 * i1 + 1], (float)window_size, level1, level1, cand);
+        if (cand.empty()) continue;
+        const uint8_t* d1 = F1->desc + (size_t)i1 * 32;
+        int bestDist = INT32_MAX, bestDist2 = INT32_MAX, bestIdx2 = -1;
+        for (int i2 : cand) {
+            const int dist = hamming(d1, F2->desc + (size_t)i2 * 32);
+            if (matched_distance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW && bestDist < (float)bestDist2 * nn_ratio) {
+            if (matches21[bestIdx2] >= 0) { matches12[matches21[bestIdx2]] = -1; nmatches--; }
+            matches12[i1] = bestIdx2; matches21[bestIdx2] = i1; matched_distance[bestIdx2] = bestDist;
+            nmatches++;
+            if (check_ori) rotHist[rot_bin(F1->keys[i1].angle, F2->keys[bestIdx2].angle)].push_back(i1);
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i]) if (matches12[idx1] >= 0) { matches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < F1->n; ++i1)
+        if (matches12[i1] >= 0) { prev_matched[2 * i1] = F2->keys[matches12[i1]].x; prev_matched[2 * i1 + 1] = F2->keys[matches12[i1]].y; }
+    return nmatches;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------

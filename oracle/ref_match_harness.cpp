@@ -376,6 +376,21 @@ int ref_search_by_sim3(const FrameView* K1v, const FrameView* K2v, const FuseQue
     return n;
 }
 
+// ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)   src/ORBmatcher.cc:732-852
+int ref_search_for_initialization(const FrameView* F1v, const FrameView* F2v, float* prev_matched, int window_size, float nn_ratio, int check_ori,
+                                  int32_t* matches12)
+{
+    Frame F1; fill(F1, F1v);
+    Frame F2; fill(F2, F2v);
+    std::vector<cv::Point2f> prev(F1v->n);
+    for (int i = 0; i < F1v->n; ++i) prev[i] = cv::Point2f(prev_matched[2 * i], prev_matched[2 * i + 1]);
+    std::vector<int> m12;
+    ORBmatcher matcher(nn_ratio, check_ori != 0);
+    const int n = matcher.SearchForInitialization(F1, F2, prev, m12, window_size);
+    for (int i = 0; i < F1v->n; ++i) { matches12[i] = m12[i]; prev_matched[2 * i] = prev[i].x; prev_matched[2 * i + 1] = prev[i].y; }
+    return n;
+}
+
 // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:389-461) on n observed descriptors (one keyframe per observation; the
 // keyframes sit in one array, so the std::map keyed by KeyFrame* iterates them in index order).  Writes the chosen descriptor.
 void ref_distinctive_descriptor(const uint8_t* desc, int n, uint8_t* chosen)

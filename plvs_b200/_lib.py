@@ -116,6 +116,7 @@ def load():
     lib.plvs_match_fuse_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     lib.plvs_match_projection_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     lib.plvs_match_bow.argtypes = [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    lib.plvs_match_initialization.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
     lib.plvs_match_bow_kf.argtypes = [C.c_void_p] * 7 + [C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
     lib.plvs_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.plvs_match_fuse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]

@@ -189,6 +189,19 @@ class ORBmatcher:
                                                C.byref(nm)), "plvs_match_bow_kf")
         return nm.value, m[:KF1.n]
 
+    def SearchForInitialization(self, F1, F2, vbPrevMatched, windowSize=100):
+        """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:732-852)
+        -> (nmatches, vnMatches12[N1], updated vbPrevMatched [N1, 2])."""
+        prev = np.array(vbPrevMatched, np.float32).reshape(-1, 2).copy()
+        if len(prev) != F1.n:
+            raise ValueError("vbPrevMatched needs one point per F1 keypoint")
+        m = np.full(max(F1.n, 1), -1, np.int32)
+        nm = C.c_int()
+        v1, v2 = F1.view(), F2.view()
+        _lib.check(self._lib.plvs_match_initialization(self._h, C.byref(v1), C.byref(v2), prev.ctypes.data_as(C.c_void_p), int(windowSize), self.mfNNratio,
+                                                       int(self.mbCheckOrientation), m.ctypes.data_as(C.c_void_p), C.byref(nm)), "plvs_match_initialization")
+        return nm.value, m[:F1.n], prev
+
     def ComputeDistinctiveDescriptors(self, desc_lists):
         """MapPoint::ComputeDistinctiveDescriptors for a batch of map points: desc_lists = one [n_i, 32] uint8 array per point
         -> best index per point (src/MapPoint.cc:428-455)."""

@@ -481,6 +481,21 @@ public:
         return nmatches;
     }
 
+    // int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize=10)
+    // (src/ORBmatcher.cc:732-852): cv::Point2f is two floats, so the vector's storage is handed over as it is and updated in place
+    template <class FrameT, class Point2fT>
+    int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<Point2fT>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10)
+    {
+        static_assert(sizeof(Point2fT) == 2 * sizeof(float), "cv::Point2f layout");
+        const plvs_frame_view v1 = view_of(F1, F1.mvKeysUn, F1.mDescriptors), v2 = view_of(F2, F2.mvKeysUn, F2.mDescriptors);
+        std::vector<int32_t> m(F1.mvKeysUn.size() + 1, -1);
+        int nmatches = 0;
+        plvs_shim::check(plvs_match_initialization(h_, &v1, &v2, reinterpret_cast<float*>(vbPrevMatched.data()), windowSize, mfNNratio,
+                                                   mbCheckOrientation ? 1 : 0, m.data(), &nmatches), "plvs_match_initialization");
+        vnMatches12.assign(m.begin(), m.begin() + F1.mvKeysUn.size());
+        return nmatches;
+    }
+
     // int SearchByBoW(KeyFramePtr& pKF1, KeyFramePtr& pKF2, std::vector<MapPointPtr>& vpMatches12)   (src/ORBmatcher.cc:853-997)
     template <class KeyFramePtr, class MapPointPtr>
     int SearchByBoW(KeyFramePtr& pKF1, KeyFramePtr& pKF2, std::vector<MapPointPtr>& vpMatches12)

@@ -88,10 +88,15 @@ extern "C" int shim_instantiate(int run)
     c += m.SearchByProjection(k1, scw, mps, vm, 8, 1.5f);
     std::set<MapPointPtr> found;
     c += m.SearchByProjection(F, k1, found, 10.f, 100);
+    struct P2f { float x, y; };
+    std::vector<P2f> prevMatched(F.mvKeysUn.size()); std::vector<int> m12;
+    c += m.SearchForInitialization(F, L, prevMatched, m12, 100);
     chisel_server::ChiselServerParams p; chisel_server::ChiselServer cs(p);
     cs.SetDepthCameraInfo(500, 500, 320, 240, 640, 480);
     Eigen::Affine3f T; cs.SetDepthPose(T);
     std::vector<float> d(640 * 480, 1.f); cs.SetDepthImageMemorySharing(d.data(), 640, 480, 640 * 4, 0);
+    cs.IntegrateLastDepthImage(false);
+    std::vector<uint16_t> d16(640 * 480, 5000); cs.SetRawDepthImageMemorySharing(d16.data(), 640, 480, 640 * 2, 1.0f / 5000.0f, 0);
     cs.IntegrateLastDepthImage(false);
     // a26: SetPointCloud + IntegrateLastPointCloud with a coloured and a colourless PCL-like cloud
     struct PointXYZRGBA { float x, y, z; unsigned char b, g, r, a; };

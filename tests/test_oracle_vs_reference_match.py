@@ -258,3 +258,48 @@ def test_stereo_from_rgbd_against_reference_text(frames):
         rur, rdz = OM.ref_stereo_from_rgbd(keys, depth, K["bf"])
         assert np.array_equal(ur.view(np.uint32), rur.view(np.uint32)) and np.array_equal(dz.view(np.uint32), rdz.view(np.uint32))
         assert (ur > 0).sum() > 500 and (ur < 0).sum() > 10
+
+
+@pytest.mark.parametrize("window,ratio,check", [(100, 0.9, True), (100, 0.9, False), (30, 0.7, True), (10, 0.9, True), (250, 1.0, True)])
+def test_search_for_initialization(frames, window, ratio, check):
+    """SearchForInitialization: vMatchedDistance gate, stolen matches (vnMatches21), histogram entries of stolen queries, vbPrevMatched update;
+    two calls in a row like Tracking::MonocularInitialization (the second starts from the updated positions)"""
+    K, fr = frames
+    f1, f2, f3 = fr[0][0], fr[1][0], fr[2][0]
+    prev = np.stack([f1.keys["x"], f1.keys["y"]], 1)
+    n, m, p = OM.search_for_initialization(f1, f2, prev, window, ratio, check)
+    rn, rm, rp = OM.ref_search_for_initialization(f1, f2, prev, window, ratio, check)
+    assert n == rn and np.array_equal(m, rm) and np.array_equal(p.view(np.uint32), rp.view(np.uint32))
+    assert n == (m >= 0).sum() and (f1.keys["octave"][m >= 0] == 0).all() and (f2.keys["octave"][m[m >= 0]] == 0).all()
+    if window >= 30:
+        assert n > 50
+    n2, m2, p2 = OM.search_for_initialization(f1, f3, p, window, ratio, check)
+    rn2, rm2, rp2 = OM.ref_search_for_initialization(f1, f3, rp, window, ratio, check)
+    assert n2 == rn2 and np.array_equal(m2, rm2) and np.array_equal(p2.view(np.uint32), rp2.view(np.uint32))
+
+
+def test_search_for_initialization_steals_and_empty():
+    """hand-made case: two queries want the same feature, the later and better one takes it over; the loser stays in the rotation histogram"""
+    from plvs_b200.matcher import Frame
+    from plvs_b200.orb import KP_DTYPE
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 256, 32, dtype=np.uint8)
+    def flip(d, k):
+        d = d.copy(); bits = np.unpackbits(d); bits[:k] ^= 1; return np.packbits(bits)
+    k1 = np.zeros(4, KP_DTYPE); k1["x"] = [100, 104, 300, 500]; k1["y"] = [100, 100, 300, 50]; k1["octave"] = [0, 0, 0, 1]; k1["angle"] = [10, 200, 10, 10]
+    d1 = np.stack([flip(base, 20), flip(base, 3), rng.integers(0, 256, 32, dtype=np.uint8), base])
+    k2 = np.zeros(3, KP_DTYPE); k2["x"] = [102, 400, 300]; k2["y"] = [101, 400, 302]; k2["octave"] = [0, 0, 1]; k2["angle"] = [10, 10, 10]
+    d2 = np.stack([base, rng.integers(0, 256, 32, dtype=np.uint8), d1[2]])
+    tab = O.Tables(1000)
+    F1 = Frame(k1, d1, 640, 480, tab.scale, tab.sigma2); F2 = Frame(k2, d2, 640, 480, tab.scale, tab.sigma2)
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    for check in (False, True):
+        n, m, p = OM.search_for_initialization(F1, F2, prev, 20, 0.9, check)
+        rn, rm, rp = OM.ref_search_for_initialization(F1, F2, prev, 20, 0.9, check)
+        assert n == rn and np.array_equal(m, rm) and np.array_equal(p, rp)
+        assert list(m) == [-1, 0, -1, -1] and n == 1                   # query 0 matched first (dist 20), query 1 (dist 3) stole feature 0
+        assert tuple(p[1]) == (102.0, 101.0) and tuple(p[0]) == (100.0, 100.0)
+    E = Frame(k2[:0], d2[:0], 640, 480, tab.scale, tab.sigma2)
+    n, m, p = OM.search_for_initialization(F1, E, prev, 20, 0.9, True)
+    rn, rm, rp = OM.ref_search_for_initialization(F1, E, prev, 20, 0.9, True)
+    assert n == rn == 0 and np.array_equal(m, rm) and (m == -1).all()

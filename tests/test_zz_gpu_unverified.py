@@ -99,3 +99,32 @@ def test_tsdf_from_raw_u16_depth(gpu):
         ka, sa, wa, ca = a.download(); kb, sb, wb, cb = b.download()
         assert len(ka) > 50 and np.array_equal(ka, kb)
         assert np.array_equal(sa.view(np.uint32), sb.view(np.uint32)) and np.array_equal(wa.view(np.uint32), wb.view(np.uint32)) and np.array_equal(ca, cb)
+
+
+def test_search_for_initialization(gpu):
+    """ORBmatcher::SearchForInitialization (§8f rank 1, the last overload): device == oracle (itself pinned to the reference's compiled function) for
+    the matches, the count and the updated vbPrevMatched, two calls in a row as Tracking::MonocularInitialization makes them; the mono
+    initialisation extractor asks for 5x the features, so ~2000 level-0 keypoints compete"""
+    from plvs_b200 import scenario
+    from plvs_b200.matcher import ORBmatcher
+    from oracle import match as OM
+    K = synth.intrinsics(640, 480)
+    tab = O.Tables(5000)
+    fr = []
+    for f in (10, 11, 14):
+        kp, desc, _, _ = O.extract_port(synth.gray_frame(f), 5000)
+        fr.append(scenario.make_frame(kp, desc, synth.depth_frame(f), K, tab.scale))
+    f1, f2, f3 = fr
+    for window, ratio, check in ((100, 0.9, True), (100, 0.9, False), (30, 0.7, True), (400, 1.0, True)):
+        m = ORBmatcher(ratio, check)
+        prev = np.stack([f1.keys["x"], f1.keys["y"]], 1)
+        n, a, p = m.SearchForInitialization(f1, f2, prev, window)
+        on, oa, op = OM.search_for_initialization(f1, f2, prev, window, ratio, check)
+        assert n == on and np.array_equal(a, oa) and np.array_equal(p.view(np.uint32), op.view(np.uint32))
+        assert n > 100
+        n, a, p = m.SearchForInitialization(f1, f3, p, window)
+        on, oa, op = OM.search_for_initialization(f1, f3, op, window, ratio, check)
+        assert n == on and np.array_equal(a, oa) and np.array_equal(p.view(np.uint32), op.view(np.uint32))
+    e = scenario.make_frame(f2.keys[:0], f2.desc[:0], synth.depth_frame(11), K, tab.scale)
+    n, a, p = ORBmatcher(0.9, True).SearchForInitialization(f1, e, prev, 100)
+    assert n == 0 and (a == -1).all() and np.array_equal(p, prev)
