@@ -169,4 +169,45 @@ int ref_tsdf_download(void* h, int32_t* keys, float* sdf, float* weight, uint8_t
     return (int)ord.size();
 }
 
+// Chisel::UpdateMeshes (src/Chisel.cpp:57-65: the chunks flagged by the integrations since the last call) or, with all != 0,
+// ChunkManager::RecomputeMeshes over every chunk
+void ref_tsdf_update_meshes(void* h, int all)
+{
+    Ref* r = (Ref*)h;
+    if (!all) { r->map->UpdateMeshes(); return; }
+    chisel::ChunkSet every;
+    for (auto& kv : r->map->GetChunkManager().GetChunks()) every[kv.first] = true;
+    r->map->GetMutableChunkManager().RecomputeMeshes(every);
+}
+
+// ChunkManager::GetAllMeshes, non-empty ones, in (x,y,z) key order; same layout as orc_tsdf_extract_mesh
+int ref_tsdf_mesh_download(void* h, int32_t* keys, int32_t* counts, int cap_meshes, float* verts, float* normals, float* colors, long cap_verts, long* total_verts)
+{
+    Ref* r = (Ref*)h;
+    std::map<std::tuple<int, int, int>, chisel::MeshPtr> ord;
+    for (auto& kv : r->map->GetChunkManager().GetAllMeshes())
+        if (kv.second && !kv.second->vertices.empty()) ord[{kv.first(0), kv.first(1), kv.first(2)}] = kv.second;
+    int nm = 0; long nv = 0;
+    for (auto& kv : ord) {
+        const chisel::Mesh& m = *kv.second;
+        if (nm < cap_meshes) {
+            if (keys) { keys[3 * nm] = std::get<0>(kv.first); keys[3 * nm + 1] = std::get<1>(kv.first); keys[3 * nm + 2] = std::get<2>(kv.first); }
+            if (counts) counts[nm] = (int)m.vertices.size();
+        }
+        for (size_t i = 0; i < m.vertices.size(); ++i) {
+            if (nv < cap_verts) {
+                for (int k = 0; k < 3; ++k) {
+                    if (verts) verts[3 * nv + k] = m.vertices[i](k);
+                    if (normals) normals[3 * nv + k] = m.normals[i](k);
+                    if (colors) colors[3 * nv + k] = m.HasColors() ? m.colors[i](k) : 0.f;
+                }
+            }
+            ++nv;
+        }
+        ++nm;
+    }
+    if (total_verts) *total_verts = nv;
+    return nm;
+}
+
 }  // extern "C"

@@ -81,6 +81,28 @@ class Map:
         return keys, sdf, w, rgba
 
 
+def _mesh_call(fn, h):
+    """(keys [m,3], counts [m], verts [v,3], normals [v,3], colors [v,3]) of the non-empty chunk meshes in key order"""
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+    tot = C.c_long()
+    nm = fn(h, None, None, 0, None, None, None, 0, C.byref(tot))
+    nv = tot.value
+    keys = np.zeros((nm, 3), np.int32); counts = np.zeros(nm, np.int32)
+    V = np.zeros((nv, 3), np.float32); N = np.zeros((nv, 3), np.float32); Cc = np.zeros((nv, 3), np.float32)
+    if nm:
+        fn(h, keys.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), nm, V.ctypes.data_as(C.c_void_p), N.ctypes.data_as(C.c_void_p),
+           Cc.ctypes.data_as(C.c_void_p), nv, C.byref(tot))
+    return keys, counts, V, N, Cc
+
+
+def _extract_mesh(self):
+    """ChunkManager::RecomputeMesh for every chunk of the current map (GenerateMesh + ColorizeMesh + ComputeNormalsFromGradients)."""
+    return _mesh_call(self._l.orc_tsdf_extract_mesh, self._h)
+
+
+Map.extract_mesh = _extract_mesh
+
+
 def depth_u16_to_f32(d16, factor):
     """`mImDepth.convertTo(mImDepth, CV_32F, mDepthMapFactor)` (src/Tracking.cc:1812-1813): OpenCV's scaled 16u -> 32f conversion is
     `(float)src * (float)alpha` with one rounding (beta = 0).  Pinned against cv2's scaled 16u->32f arithmetic in tests/test_oracle_match_tsdf.py
@@ -107,3 +129,16 @@ class RefMap(Map):
                 raise RuntimeError("oracle/_ref/libchisel_ref.so missing and /root/reference not present")
             RefMap._lib = C.CDLL(so)
         return _Prefixed(RefMap._lib, "ref_")
+
+    def update_meshes(self, all_chunks=False):
+        """Chisel::UpdateMeshes (the chunks flagged since the last call), or every chunk"""
+        RefMap._lib.ref_tsdf_update_meshes.argtypes = [C.c_void_p, C.c_int]
+        RefMap._lib.ref_tsdf_update_meshes(self._h, int(all_chunks))
+
+    def meshes(self):
+        """ChunkManager::GetAllMeshes as they are now (non-empty ones, key order)"""
+        return _mesh_call(RefMap._lib.ref_tsdf_mesh_download, self._h)
+
+    def extract_mesh(self):
+        self.update_meshes(True)
+        return self.meshes()

@@ -441,3 +441,216 @@ int orc_tsdf_integrate_cloud(void* h, const float* xyz, const float* rgb, int n,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// SURVEY.md §8f rank 3 -- read-out: ChunkManager::RecomputeMesh (Thirdparty/open_chisel/src/ChunkManager.cpp:116-172) for every chunk:
+//   GenerateMesh (:577-664: inside voxels in z,y,x order, then the max-X, max-Y and max-Z planes, whose cube corners reach into the
+//   +x/+y/+z neighbour chunks, ExtractInside/BorderVoxelMeshKfid :438-575), MarchingCubes::MeshCube / InterpolateEdgeVertices /
+//   InterpolateVertex (include/open_chisel/marching_cubes/MarchingCubes.h:76-271: triangle vertices in reversed table order, face
+//   normal, `vertex1 + 0.5f * vertex2` for |sdf1 - sdf2| < 1e-6 as written), ColorizeMesh / InterpolateColor (:715-806, INCLUDING its
+//   quirk: the eight GetColorVoxel look-ups are made with integer voxel indices passed as metric positions, so in practice the
+//   nearest-voxel fallback Chunk::GetColorAt (src/Chunk.cpp:136-155) supplies the colour), ComputeNormalsFromGradients /
+//   GetSDFAndGradient / GetSDF (:666-713, :838-856).  Stateless: the reference re-meshes the 27-neighbourhood of every updated chunk
+//   after each integration (Chisel.h:108-118, Chisel::UpdateMeshes), which leaves exactly the meshes a full pass over the current voxels
+//   produces; tests/test_oracle_vs_reference_mesh.py checks both flows of the compiled reference against this function.
+//   kfids are not carried (the depth-scan path never sets them).  PINNED bit-exactly (vertex order, positions, normals, colours).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+const uint64_t kTriTable[256] = {
+#include "../plvs_b200/csrc/mc_tables.inc"
+};
+const int kEdgePairs[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {4, 5}, {5, 6}, {6, 7}, {7, 4}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+const int kCubeOff[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+
+struct MeshCtx {
+    const Map* m; float res, inv, half, rounding;
+    const Block* find(int x, int y, int z) const { auto it = m->blocks.find(Key{x, y, z}); return it == m->blocks.end() ? nullptr : it->second.get(); }
+    // ChunkManager::GetIDAt (ChunkManager.h:192-201)
+    Key id_at(V3 p) const { return Key{(int)std::floor(p.x * rounding), (int)std::floor(p.y * rounding), (int)std::floor(p.z * rounding)}; }
+    static V3 origin(const Key& k, float res) { return V3{(float)(16 * k.x) * res, (float)(16 * k.y) * res, (float)(16 * k.z) * res}; }
+    // chunk->GetVoxelID(rel) with Chunk::GetVoxelCoords (src/Chunk.cpp:80-94): no range check on the coordinates, only on the id
+    long voxel_id(V3 rel) const
+    {
+        const int x = (int)std::floor(rel.x * inv), y = (int)std::floor(rel.y * inv), z = (int)std::floor(rel.z * inv);
+        return ((long)z * 16 + y) * 16 + x;
+    }
+    // ChunkManager::GetSDF (:692-713)
+    bool sdf_at(V3 posf, double* dist) const
+    {
+        const Key k = id_at(posf);
+        const Block* b = find(k.x, k.y, k.z);
+        if (!b) return false;
+        const long id = voxel_id(posf - origin(k, res));
+        if (id >= 0 && id < 4096 && b->w[id] > 1e-12) { *dist = b->sdf[id]; return true; }
+        return false;
+    }
+    // ChunkManager::GetColorVoxel (:822-841)
+    const uint8_t* color_voxel(V3 pos) const
+    {
+        const Key k = id_at(pos);
+        const Block* b = find(k.x, k.y, k.z);
+        if (!b) return nullptr;
+        const long id = voxel_id(pos - origin(k, res));
+        return (id >= 0 && id < 4096) ? &b->rgba[4 * id] : nullptr;
+    }
+    V3 interpolate_color(V3 p) const
+    {
+        const float x = p.x, y = p.y, z = p.z;
+        const int x_0 = (int)std::floor(x * inv), y_0 = (int)std::floor(y * inv), z_0 = (int)std::floor(z * inv);
+        const int x_1 = x_0 + 1, y_1 = y_0 + 1, z_1 = z_0 + 1;
+        const uint8_t* v_000 = color_voxel(V3{(float)x_0, (float)y_0, (float)z_0});
+        const uint8_t* v_001 = color_voxel(V3{(float)x_0, (float)y_0, (float)z_1});
+        const uint8_t* v_011 = color_voxel(V3{(float)x_0, (float)y_1, (float)z_1});
+        const uint8_t* v_111 = color_voxel(V3{(float)x_1, (float)y_1, (float)z_1});
+        const uint8_t* v_110 = color_voxel(V3{(float)x_1, (float)y_1, (float)z_0});
+        const uint8_t* v_100 = color_voxel(V3{(float)x_1, (float)y_0, (float)z_0});
+        const uint8_t* v_010 = color_voxel(V3{(float)x_0, (float)y_1, (float)z_0});
+        const uint8_t* v_101 = color_voxel(V3{(float)x_1, (float)y_0, (float)z_1});
+        if (!v_000 || !v_001 || !v_011 || !v_111 || !v_110 || !v_100 || !v_010 || !v_101) {
+            const Key k = id_at(p);
+            const Block* b = find(k.x, k.y, k.z);
+            if (!b) return V3{0, 0, 0};
+            // Chunk::GetColorAt (src/Chunk.cpp:136-155)
+            const V3 o = origin(k, res);
+            const float size = (float)16 * res;
+            if (p.x >= o.x && p.y >= o.y && p.z >= o.z && p.x <= o.x + size && p.y <= o.y + size && p.z <= o.z + size) {
+                const V3 cp = (p - o) * inv;
+                const int cx = (int)cp.x, cy = (int)cp.y, cz = (int)cp.z;
+                if (cx >= 0 && cx < 16 && cy >= 0 && cy < 16 && cz >= 0 && cz < 16) {
+                    const uint8_t* c = &b->rgba[4 * ((cz * 16 + cy) * 16 + cx)];
+                    const float invMax = 1.f / 255.f;
+                    return V3{(float)c[0] * invMax, (float)c[1] * invMax, (float)c[2] * invMax};
+                }
+            }
+            return V3{0, 0, 0};
+        }
+        const float xd = (x - x_0) / (x_1 - x_0), yd = (y - y_0) / (y_1 - y_0), zd = (z - z_0) / (z_1 - z_0);
+        float out[3];
+        for (int ch = 0; ch < 3; ++ch) {
+            const float c_00 = v_000[ch] * (1 - xd) + v_100[ch] * xd;
+            const float c_10 = v_010[ch] * (1 - xd) + v_110[ch] * xd;
+            const float c_01 = v_001[ch] * (1 - xd) + v_101[ch] * xd;
+            const float c_11 = v_011[ch] * (1 - xd) + v_111[ch] * xd;
+            const float c_0 = c_00 * (1 - yd) + c_10 * yd;
+            const float c_1 = c_01 * (1 - yd) + c_11 * yd;
+            const float c = c_0 * (1 - zd) + c_1 * zd;
+            out[ch] = c / 255.0f;
+        }
+        return V3{out[0], out[1], out[2]};
+    }
+    // ChunkManager::GetSDFAndGradient (:666-690) + the renormalisation of ComputeNormalsFromGradients (:838-856)
+    bool gradient_normal(V3 pos, V3* n) const
+    {
+        const V3 posf{std::floor(pos.x * inv) * res + half, std::floor(pos.y * inv) * res + half, std::floor(pos.z * inv) * res + half};
+        double dist, xp, yp, zp, xm, ym, zm;
+        if (!sdf_at(posf, &dist)) return false;
+        if (!sdf_at(posf + V3{res, 0, 0}, &xp)) return false;
+        if (!sdf_at(posf + V3{0, res, 0}, &yp)) return false;
+        if (!sdf_at(posf + V3{0, 0, res}, &zp)) return false;
+        if (!sdf_at(posf - V3{res, 0, 0}, &xm)) return false;
+        if (!sdf_at(posf - V3{0, res, 0}, &ym)) return false;
+        if (!sdf_at(posf - V3{0, 0, res}, &zm)) return false;
+        V3 g{(float)(xp - xm), (float)(yp - ym), (float)(zp - zm)};
+        const float sq = dot(g, g);
+        if (sq > 0.f) { const float s = std::sqrt(sq); g = V3{g.x / s, g.y / s, g.z / s}; }      // Eigen normalize()
+        const float mag = std::sqrt(dot(g, g));
+        if (mag > 1e-12) { *n = g * (1.0f / mag); return true; }
+        return false;
+    }
+};
+
+void mesh_voxel(const MeshCtx& c, const Key& key, const Block* blk, int ix, int iy, int iz, bool border, std::vector<V3>& verts, std::vector<V3>& normals)
+{
+    const float res = c.res;
+    const V3 halfVoxel = V3{res, res, res} * 0.5f;
+    const V3 centroid = V3{(float)ix, (float)iy, (float)iz} * res + halfVoxel;
+    const V3 coords = centroid + MeshCtx::origin(key, res);
+    V3 cc[8]; float sdf[8];
+    for (int i = 0; i < 8; ++i) {
+        int x = ix + kCubeOff[i][0], y = iy + kCubeOff[i][1], z = iz + kCubeOff[i][2];
+        const Block* b = blk;
+        if (border && !(x < 16 && y < 16 && z < 16)) {
+            int off[3] = {0, 0, 0};
+            if (x >= 16) { off[0] = 1; x = 0; }
+            if (y >= 16) { off[1] = 1; y = 0; }
+            if (z >= 16) { off[2] = 1; z = 0; }
+            b = c.find(key.x + off[0], key.y + off[1], key.z + off[2]);
+            if (!b) return;
+        }
+        const int id = (z * 16 + y) * 16 + x;
+        if (b->w[id] <= 1e-15) return;
+        cc[i] = coords + V3{(float)kCubeOff[i][0] * res, (float)kCubeOff[i][1] * res, (float)kCubeOff[i][2] * res};
+        sdf[i] = b->sdf[id];
+    }
+    int cfg = 0;
+    for (int i = 0; i < 8; ++i) if (sdf[i] < 0) cfg |= 1 << i;
+    if (cfg == 0) return;
+    V3 edge[12];
+    for (int e = 0; e < 12; ++e) {
+        const int a = kEdgePairs[e][0], b = kEdgePairs[e][1];
+        if ((sdf[a] < 0 && sdf[b] >= 0) || (sdf[a] >= 0 && sdf[b] < 0)) {
+            const float diff = sdf[a] - sdf[b];
+            if (std::fabs(diff) < 1e-6f) edge[e] = cc[a] + cc[b] * 0.5f;
+            else { const float t = sdf[a] / diff; edge[e] = cc[a] + (cc[b] - cc[a]) * t; }
+        }
+    }
+    const uint64_t row = kTriTable[cfg];
+    const int ntri = (int)(row >> 60);
+    for (int t = 0; t < ntri; ++t) {
+        const V3 p0 = edge[(row >> (4 * (3 * t + 2))) & 15], p1 = edge[(row >> (4 * (3 * t + 1))) & 15], p2 = edge[(row >> (4 * (3 * t))) & 15];
+        V3 n = cross(p1 - p0, p2 - p0);
+        const float sq = dot(n, n);
+        if (sq > 0.f) { const float s = std::sqrt(sq); n = V3{n.x / s, n.y / s, n.z / s}; }
+        verts.push_back(p0); verts.push_back(p1); verts.push_back(p2);
+        normals.push_back(n); normals.push_back(n); normals.push_back(n);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// meshes of all chunks in (x,y,z) key order; chunks without triangles are left out like ChunkManager::RecomputeMesh does (:165-167).
+// keys[3*i], counts[i] = vertices of mesh i; verts / normals / colors = 3 floats per vertex, concatenated.  Returns the number of
+// meshes, *total_verts the number of vertices; arrays may be null (counting pass) and are filled up to the caps.
+int orc_tsdf_extract_mesh(void* h, int32_t* keys, int32_t* counts, int cap_meshes, float* verts, float* normals, float* colors, long cap_verts, long* total_verts)
+{
+    Map* m = (Map*)h;
+    MeshCtx c{m, m->p.voxel_resolution, 1.f / m->p.voxel_resolution, 0.5f * m->p.voxel_resolution, 1.0f / ((float)16 * m->p.voxel_resolution)};
+    std::map<std::tuple<int, int, int>, const Block*> ord;
+    for (auto& kv : m->blocks) ord[{kv.first.x, kv.first.y, kv.first.z}] = kv.second.get();
+    int nm = 0; long nv = 0;
+    std::vector<V3> V, N;
+    for (auto& kv : ord) {
+        const Key key{std::get<0>(kv.first), std::get<1>(kv.first), std::get<2>(kv.first)};
+        const Block* b = kv.second;
+        V.clear(); N.clear();
+        for (int z = 0; z < 15; ++z) for (int y = 0; y < 15; ++y) for (int x = 0; x < 15; ++x) mesh_voxel(c, key, b, x, y, z, false, V, N);
+        for (int z = 0; z < 15; ++z) for (int y = 0; y < 16; ++y) mesh_voxel(c, key, b, 15, y, z, true, V, N);
+        for (int z = 0; z < 15; ++z) for (int x = 0; x < 15; ++x) mesh_voxel(c, key, b, x, 15, z, true, V, N);
+        for (int y = 0; y < 16; ++y) for (int x = 0; x < 16; ++x) mesh_voxel(c, key, b, x, y, 15, true, V, N);
+        if (V.empty()) continue;
+        if (nm < cap_meshes) {
+            if (keys) { keys[3 * nm] = key.x; keys[3 * nm + 1] = key.y; keys[3 * nm + 2] = key.z; }
+            if (counts) counts[nm] = (int)V.size();
+        }
+        for (size_t i = 0; i < V.size(); ++i) {
+            V3 col{0, 0, 0};
+            if (m->p.use_color) col = c.interpolate_color(V[i]);
+            V3 n = N[i];
+            c.gradient_normal(V[i], &n);
+            if (nv < cap_verts) {
+                if (verts) { verts[3 * nv] = V[i].x; verts[3 * nv + 1] = V[i].y; verts[3 * nv + 2] = V[i].z; }
+                if (normals) { normals[3 * nv] = n.x; normals[3 * nv + 1] = n.y; normals[3 * nv + 2] = n.z; }
+                if (colors) { colors[3 * nv] = col.x; colors[3 * nv + 1] = col.y; colors[3 * nv + 2] = col.z; }
+            }
+            ++nv;
+        }
+        ++nm;
+    }
+    if (total_verts) *total_verts = nv;
+    return nm;
+}
+
+}  // extern "C"
