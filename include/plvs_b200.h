@@ -62,6 +62,7 @@ int plvs_set_profiling(int mask);
 #define PLVS_TSDF_K_CLASSIFY 1
 #define PLVS_TSDF_K_INTEGRATE 2
 #define PLVS_TSDF_K_COMMIT 3
+#define PLVS_TSDF_K_MESH 4
 #define PLVS_K_SLOTS 12
 /* pinned host memory for the e2e path (cudaHostAlloc / cudaFreeHost) */
 int plvs_host_alloc(void** p, size_t bytes);
@@ -448,6 +449,20 @@ typedef struct {
 } plvs_tsdf_stats;
 int plvs_tsdf_last_stats(const plvs_tsdf* h, plvs_tsdf_stats* out);
 int plvs_tsdf_kernel_times(plvs_tsdf* h, float* ms, int32_t* launches, int reset);
+
+/* Read-out: what PointCloudMapChisel::UpdateMap does after the integrations (src/PointCloudMapChisel.cc:233-250).
+ * plvs_tsdf_update_meshes = ChiselServer::UpdateMesh -> Chisel::UpdateMeshes -> ChunkManager::RecomputeMesh (Thirdparty/open_chisel/src/
+ * ChunkManager.cpp:116-172): marching cubes over every chunk (GenerateMesh :577-664), ColorizeMesh (:858-870) when the map has colour,
+ * ComputeNormalsFromGradients (:838-856).  The meshes stay on the device; every chunk is re-meshed from the current voxels, which is what
+ * the reference's dirty-set bookkeeping (27-neighbourhood of every updated chunk) amounts to.  *n_meshes = chunks with a non-empty mesh,
+ * *n_verts = vertices over all of them (3 per triangle, not shared -- as chisel::Mesh stores them).
+ * plvs_tsdf_get_meshes = reading ChunkManager::GetAllMeshes() (what ChiselServer::GetPointCloud walks, ChiselServer.cpp:872-975), in
+ * (x,y,z) chunk-key order: keys[3*i], counts[i] = vertices of mesh i, then 3 floats per vertex for positions, normals and colours
+ * (r,g,b in [0,1]; zeros when the map has no colour), concatenated in mesh order; vertex order inside a mesh is the reference's.
+ * Any output may be NULL; vertex arrays may be device pointers (on_device != 0).  kfids are not carried. */
+int plvs_tsdf_update_meshes(plvs_tsdf* h, int* n_meshes, long long* n_verts);
+int plvs_tsdf_get_meshes(plvs_tsdf* h, int32_t* keys, int32_t* counts, int cap_meshes, float* verts, float* normals, float* colors,
+                         long long cap_verts, int on_device);
 
 /* read-out for tests/merge: chunk ids (x,y,z), per-voxel sdf / weight (4096 each, voxel index
  * (z*16+y)*16+x as Chunk.h:90-93) and rgba (r,g,b,colour-weight).  Any output may be NULL. */

@@ -102,6 +102,29 @@ class ChiselServer:
         _lib.check(self._lib.plvs_tsdf_last_stats(self._h, C.byref(s)), "plvs_tsdf_last_stats")
         return {f: getattr(s, f) for f, _ in s._fields_}
 
+    def UpdateMesh(self):
+        """ChiselServer::UpdateMesh (Chisel::UpdateMeshes): marching cubes + colours + gradient normals for every chunk, left on the device.
+        -> (number of non-empty chunk meshes, number of vertices)"""
+        nm, nv = C.c_int(), C.c_longlong()
+        _lib.check(self._lib.plvs_tsdf_update_meshes(self._h, C.byref(nm), C.byref(nv)), "plvs_tsdf_update_meshes")
+        self._mesh_sizes = (nm.value, nv.value)
+        return self._mesh_sizes
+
+    def GetMeshes(self):
+        """ChunkManager::GetAllMeshes of the last UpdateMesh, chunk-key order -> keys[m,3], counts[m], vertices[v,3], normals[v,3], colours[v,3]"""
+        nm, nv = getattr(self, "_mesh_sizes", None) or self.UpdateMesh()
+        keys = np.zeros((nm, 3), np.int32); counts = np.zeros(nm, np.int32)
+        V = np.zeros((nv, 3), np.float32); N = np.zeros((nv, 3), np.float32); Cc = np.zeros((nv, 3), np.float32)
+        _lib.check(self._lib.plvs_tsdf_get_meshes(self._h, keys.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), nm, V.ctypes.data_as(C.c_void_p),
+                                                  N.ctypes.data_as(C.c_void_p), Cc.ctypes.data_as(C.c_void_p), nv, 0), "plvs_tsdf_get_meshes")
+        return keys, counts, V, N, Cc
+
+    def GetPointCloud(self):
+        """ChiselServer::GetPointCloud (ChiselServer.cpp:872-1075) for a coloured map: one point per mesh vertex, r/g/b = colour * 255 truncated
+        to a byte, plus the normals.  Chunk order is (x,y,z) key order (the reference walks an unordered_map)."""
+        _, _, V, N, Cc = self.GetMeshes()
+        return V, (Cc * np.float32(255)).astype(np.uint8), N
+
     def download(self):
         """-> keys[n,3] (sorted lexicographically), sdf[n,4096], weight[n,4096], rgba[n,4096,4]"""
         n = C.c_int()

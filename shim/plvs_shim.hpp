@@ -13,6 +13,7 @@
 // those members works.
 #pragma once
 #include <cmath>
+#include <type_traits>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -47,6 +48,13 @@ template <class Sim3T> inline auto se3_of_sim3(const Sim3T& Scw) { return standi
 template <class P> auto point_rgb_impl(const P& pt, float k, float* out, int) -> decltype((void)pt.r, true) { out[0] = pt.r * k; out[1] = pt.g * k; out[2] = pt.b * k; return true; }
 template <class P> bool point_rgb_impl(const P&, float, float*, long) { return false; }
 template <class P> bool point_rgb(const P& pt, float k, float* out) { return point_rgb_impl(pt, k, out, 0); }
+// normals / alpha of an output point, when the point type has them (the reference selects GetPointCloud overloads on these fields)
+template <class P> auto point_set_normal_impl(P& pt, const float* n, int) -> decltype((void)pt.normal_x, void()) { pt.normal_x = n[0]; pt.normal_y = n[1]; pt.normal_z = n[2]; }
+template <class P> void point_set_normal_impl(P&, const float*, long) {}
+template <class P> void point_set_normal(P& pt, const float* n) { point_set_normal_impl(pt, n, 0); }
+template <class P> auto point_set_alpha_impl(P& pt, int) -> decltype((void)pt.a, void()) { pt.a = 255; }
+template <class P> void point_set_alpha_impl(P&, long) {}
+template <class P> void point_set_alpha(P& pt) { point_set_alpha_impl(pt, 0); }
 inline void check(int rc, const char* what)
 {
     if (rc != PLVS_OK) throw std::runtime_error(std::string(what) + ": " + plvs_last_error());
@@ -682,6 +690,40 @@ public:
     ~ChiselServer() { plvs_tsdf_destroy(h_); }
     ChiselServer(const ChiselServer&) = delete;
 
+    // ChiselServer::UpdateMesh (ChiselServer.cpp:707-710): marching cubes, colours and gradient normals of every chunk, on the device
+    void UpdateMesh() { plvs_shim::check(plvs_tsdf_update_meshes(h_, &nMeshes_, &nMeshVerts_), "plvs_tsdf_update_meshes"); }
+    // ChiselServer::GetPointCloud (ChiselServer.cpp:872-1075): one point per mesh vertex; colour * 255 when the map has colour,
+    // otherwise the reference's two-light Lambert shading of the normal (lightDir normalised, lightDir1 left as written, :907-911).
+    // Chunks come in (x,y,z) key order (the reference walks an unordered_map).  CloudT: pcl::PointCloud<PointT>-like (clear, push_back).
+    template <class CloudT>
+    void GetPointCloud(CloudT& output_cloud)
+    {
+        output_cloud.clear();
+        if (nMeshVerts_ <= 0) return;
+        const size_t n = (size_t)nMeshVerts_;
+        meshV_.resize(3 * n); meshN_.resize(3 * n); meshC_.resize(3 * n);
+        plvs_shim::check(plvs_tsdf_get_meshes(h_, nullptr, nullptr, 0, meshV_.data(), meshN_.data(), meshC_.data(), nMeshVerts_, 0), "plvs_tsdf_get_meshes");
+        const float l0[3] = {0.8f, -0.2f, 0.7f};
+        const float l0n = std::sqrt(l0[0] * l0[0] + (l0[1] * l0[1] + l0[2] * l0[2]));
+        const float lightDir[3] = {l0[0] / l0n, l0[1] / l0n, l0[2] / l0n}, lightDir1[3] = {-0.5f, 0.2f, 0.2f};
+        typedef typename std::decay<decltype(output_cloud.points[0])>::type PointT;
+        for (size_t i = 0; i < n; ++i) {
+            PointT point;
+            point.x = meshV_[3 * i]; point.y = meshV_[3 * i + 1]; point.z = meshV_[3 * i + 2];
+            const float* nrm = &meshN_[3 * i];
+            if (useColor) {
+                point.r = meshC_[3 * i] * 255; point.g = meshC_[3 * i + 1] * 255; point.b = meshC_[3 * i + 2] * 255;
+                plvs_shim::point_set_normal(point, nrm);
+            } else {
+                const float d0 = std::fmax(nrm[0] * lightDir[0] + (nrm[1] * lightDir[1] + nrm[2] * lightDir[2]), 0.0f);
+                const float d1 = std::fmax(nrm[0] * lightDir1[0] + (nrm[1] * lightDir1[1] + nrm[2] * lightDir1[2]), 0.0f);
+                const float lambert = (d0 * 0.5f + d1 * 0.5f) + 0.2f;
+                point.r = std::fmin(lambert, 1.0) * 255; point.g = point.r; point.b = point.r;
+                plvs_shim::point_set_alpha(point);
+            }
+            output_cloud.push_back(point);
+        }
+    }
     void Reset() { plvs_shim::check(plvs_tsdf_reset(h_), "plvs_tsdf_reset"); }
     void SetDepthCameraInfo(const double fx, const double fy, const double cx, const double cy, const int width, const int height)
     {
@@ -758,6 +800,7 @@ protected:
     float Twc_[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     float* depth_ = nullptr; int dw_ = 0, dh_ = 0;
     const uint16_t* depth16_ = nullptr; int dstep16_ = 0; float dfactor_ = 1.0f;
+    int nMeshes_ = 0; long long nMeshVerts_ = 0; std::vector<float> meshV_, meshN_, meshC_;
     unsigned char* color_ = nullptr; int cw_ = 0, ch_ = 0, cstep_ = 0, cn_ = 0;
     plvs_tsdf* h_ = nullptr;
 };

@@ -98,6 +98,9 @@ extern "C" int shim_instantiate(int run)
     cs.IntegrateLastDepthImage(false);
     std::vector<uint16_t> d16(640 * 480, 5000); cs.SetRawDepthImageMemorySharing(d16.data(), 640, 480, 640 * 2, 1.0f / 5000.0f, 0);
     cs.IntegrateLastDepthImage(false);
+    struct PointOut { float x, y, z, normal_x, normal_y, normal_z; unsigned char r, g, b, a; };
+    struct CloudOut { std::vector<PointOut> points; void clear() { points.clear(); } void push_back(const PointOut& q) { points.push_back(q); } } out;
+    cs.UpdateMesh(); cs.GetPointCloud(out);
     // a26: SetPointCloud + IntegrateLastPointCloud with a coloured and a colourless PCL-like cloud
     struct PointXYZRGBA { float x, y, z; unsigned char b, g, r, a; };
     struct PointXYZ { float x, y, z; };

@@ -128,3 +128,41 @@ def test_search_for_initialization(gpu):
     e = scenario.make_frame(f2.keys[:0], f2.desc[:0], synth.depth_frame(11), K, tab.scale)
     n, a, p = ORBmatcher(0.9, True).SearchForInitialization(f1, e, prev, 100)
     assert n == 0 and (a == -1).all() and np.array_equal(p, prev)
+
+
+def test_mesh_read_out(gpu):
+    """§8f rank 3: ChunkManager::RecomputeMesh for every chunk on the device (marching cubes in the reference's vertex order, colours through
+    InterpolateColor as written, gradient normals) == the oracle, which is pinned bit-exactly to the compiled open_chisel
+    (tests/test_oracle_vs_reference_mesh.py).  The voxel arrays of the two maps are identical in these sequences, so the meshes must be too."""
+    from plvs_b200 import tsdf as T
+    from oracle import tsdf as OT
+
+    def pair(w, h, **kw):
+        K = synth.intrinsics(w, h)
+        p = T.default_params(**kw)
+        g = T.ChiselServer(p); g.SetDepthCameraInfo(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
+        o = OT.Map(p, threads=8); o.set_camera(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
+        return g, o
+
+    def same(g, o):
+        nm, nv = g.UpdateMesh()
+        gk, gc, gV, gN, gC = g.GetMeshes()
+        ok, oc, oV, oN, oC = o.extract_mesh()
+        assert nm == len(ok) and nv == len(oV)
+        assert np.array_equal(gk, ok) and np.array_equal(gc, oc)
+        for a, b in ((gV, oV), (gN, oN), (gC, oC)):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        return nv
+
+    for color, res in ((1, 0.04), (0, 0.04), (1, 0.5)):            # 0.5 m voxels: InterpolateColor's trilinear branch is live
+        g, o = pair(160, 120, voxel_resolution=res, use_carving=1, near_plane=0.1, far_plane=4.0 if res < 0.1 else 6.0, max_blocks=8192, use_color=color)
+        for f in (0, 1, 2, 6):
+            d = synth.depth_frame(f, 160, 120); c = synth.bgr_frame(f, 160, 120) if color else None
+            g.integrate(d, synth.pose(f), c); o.integrate(d, synth.pose(f), c)
+            assert np.array_equal(g.download()[1].view(np.uint32), o.download()[1].view(np.uint32))
+            nv = same(g, o)
+        assert nv > (10000 if res < 0.1 else 100)
+    xyz, rgb, nrm = g.GetPointCloud()
+    assert len(xyz) == nv and rgb.dtype == np.uint8 and rgb.max() > 50
+    g.Reset()
+    assert g.UpdateMesh() == (0, 0) and len(g.GetMeshes()[2]) == 0
