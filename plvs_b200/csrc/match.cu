@@ -19,103 +19,7 @@ using namespace plvs;
 
 namespace {
 
-constexpr int GRID_COLS = 64, GRID_ROWS = 48, GRID_CELLS = GRID_COLS * GRID_ROWS;
-constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO = 12;
-
-struct GridParams { float min_x, min_y, max_x, max_y, inv_w, inv_h; };
-
-// candidate packing: idx:16 | dist:9 | level:5
-__device__ __forceinline__ uint32_t pack_cand(int idx, int dist, int level) { return (uint32_t)idx | ((uint32_t)dist << 16) | ((uint32_t)level << 25); }
-__device__ __forceinline__ int cand_idx(uint32_t c) { return c & 0xffff; }
-__device__ __forceinline__ int cand_dist(uint32_t c) { return (c >> 16) & 0x1ff; }
-__device__ __forceinline__ int cand_level(uint32_t c) { return c >> 25; }
-
-__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint8_t* __restrict__ b)
-{
-    const uint4 b0 = *reinterpret_cast<const uint4*>(b), b1 = *reinterpret_cast<const uint4*>(b + 16);
-    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
-           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Frame::AssignFeaturesToGrid (src/Frame.cc:716-746): 64x48 cells, cell = round((p-min)*inv),
-// indices appended in keypoint order.  One CTA: histogram, scan, unordered scatter, per-cell insertion sort
-// (cells hold a handful of keypoints), so every cell list is ascending == the reference's push_back order.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_build_grid(const plvs_keypoint* __restrict__ keys, int n, GridParams gp, int* __restrict__ cell_start /*GRID_CELLS+1*/,
-             int* __restrict__ sorted /*n*/, int* __restrict__ kp_cell /*n*/)
-{
-    __shared__ int s_cnt[GRID_CELLS + 1];
-    __shared__ int s_part[32];
-    const int tid = threadIdx.x;
-    for (int i = tid; i <= GRID_CELLS; i += 1024) s_cnt[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += 1024) {
-        const int px = (int)roundf((keys[i].x - gp.min_x) * gp.inv_w);
-        const int py = (int)roundf((keys[i].y - gp.min_y) * gp.inv_h);
-        int c = -1;
-        if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) { c = px * GRID_ROWS + py; atomicAdd(&s_cnt[c], 1); }
-        kp_cell[i] = c;
-    }
-    __syncthreads();
-    // exclusive scan of 3072 counts: 3 per thread
-    int v[3], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { v[k] = s_cnt[tid * 3 + k]; sum += v[k]; }
-    int x = sum;
-    const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) s_part[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-        int p = s_part[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, p, o); if (lane >= o) p += y; }
-        s_part[lane] = p;
-    }
-    __syncthreads();
-    int base = (wid ? s_part[wid - 1] : 0) + x - sum;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { s_cnt[tid * 3 + k] = base; base += v[k]; }
-    if (tid == 1023) s_cnt[GRID_CELLS] = base;
-    __syncthreads();
-    for (int i = tid; i <= GRID_CELLS; i += 1024) cell_start[i] = s_cnt[i];
-    __syncthreads();
-    // scatter in arbitrary order (s_cnt doubles as the per-cell cursor), then every cell list -- they hold
-    // 0-3 entries in practice -- is put back into ascending index order (== push_back order) by one thread
-    for (int i = tid; i < n; i += 1024) { const int c = kp_cell[i]; if (c >= 0) sorted[atomicAdd(&s_cnt[c], 1)] = i; }
-    __syncthreads();
-    for (int c = tid; c < GRID_CELLS; c += 1024) {
-        const int b0 = cell_start[c], b1 = cell_start[c + 1];
-        for (int i = b0 + 1; i < b1; ++i) {
-            const int v = sorted[i];
-            int j = i - 1;
-            while (j >= b0 && sorted[j] > v) { sorted[j + 1] = sorted[j]; --j; }
-            sorted[j + 1] = v;
-        }
-    }
-}
-
-// Frame::GetFeaturesInArea cell window (src/Frame.cc:1239-1261); returns false if empty
-__device__ __forceinline__ bool cell_window(const GridParams& gp, float x, float y, float r, int& c0, int& c1, int& r0, int& r1)
-{
-    c0 = max(0, (int)floorf((x - gp.min_x - r) * gp.inv_w));
-    if (c0 >= GRID_COLS) return false;
-    c1 = min(GRID_COLS - 1, (int)ceilf((x - gp.min_x + r) * gp.inv_w));
-    if (c1 < 0) return false;
-    r0 = max(0, (int)floorf((y - gp.min_y - r) * gp.inv_h));
-    if (r0 >= GRID_ROWS) return false;
-    r1 = min(GRID_ROWS - 1, (int)ceilf((y - gp.min_y + r) * gp.inv_h));
-    if (r1 < 0) return false;
-    return true;
-}
-
-struct ViewDev {
-    const plvs_keypoint* keys; const uint8_t* desc; const float* uright; int n;
-    GridParams gp; float bf; float scale[PLVS_MAX_LEVELS]; float sigma2[PLVS_MAX_LEVELS];
-};
+#include "match_common.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Phase A (both projection searches): one warp per query walks the window column by column
@@ -668,216 +572,9 @@ k_distinctive(const uint8_t* __restrict__ desc, const int32_t* __restrict__ off,
     if (lane == 0) best[pt] = (int)(key & 0xffffu);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Frame::isInFrustum (src/Frame.cc:955-1017) + Pinhole::project (Pinhole.cpp:61-67) + MapPoint::PredictScale (MapPoint.cc:598-613), one thread
-// per map point.  fp32 in the reference's operation order (Eigen's e0 + (e1 + e2), IEEE sqrt and divisions, no contraction).  PredictScale's
-// ceil(logf(ratio) / logf(scaleFactor)) is evaluated as a count of host-computed thresholds (see plvs_match_in_frustum), so no device logarithm
-// has to match glibc's.
-// ---------------------------------------------------------------------------------------------
-struct FrustumDev { plvs_frustum f; float T[PLVS_MAX_LEVELS]; };
+#include "match_frustum.cuh"
 
-__global__ void __launch_bounds__(256)
-k_in_frustum(FrustumDev D, const plvs_map_point* __restrict__ pts, int n, plvs_mp_query* __restrict__ q, uint8_t* __restrict__ in_view, int* __restrict__ count)
-{
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const plvs_frustum& fr = D.f;
-    const plvs_map_point p = pts[i];
-    plvs_mp_query o;
-    o.proj_x = -1.f; o.proj_y = -1.f; o.proj_xr = 0.f; o.track_depth = 0.f; o.view_cos = 0.f; o.level = 0; o.flags = p.flags;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) o.desc[k] = p.desc[k];
-    bool in = false;
-    const float X = p.xw[0], Y = p.xw[1], Z = p.xw[2];
-    const float pcx = (fr.Rcw[0] * X + (fr.Rcw[1] * Y + fr.Rcw[2] * Z)) + fr.tcw[0];
-    const float pcy = (fr.Rcw[3] * X + (fr.Rcw[4] * Y + fr.Rcw[5] * Z)) + fr.tcw[1];
-    const float pcz = (fr.Rcw[6] * X + (fr.Rcw[7] * Y + fr.Rcw[8] * Z)) + fr.tcw[2];
-    if (!(pcz < 0.0f)) {
-        const float u = fr.fx * pcx / pcz + fr.cx, v = fr.fy * pcy / pcz + fr.cy;
-        if (!(u < fr.min_x || u > fr.max_x) && !(v < fr.min_y || v > fr.max_y)) {
-            o.proj_x = u; o.proj_y = v;
-            const float maxDistance = 1.2f * p.max_dist, minDistance = 0.8f * p.min_dist;
-            const float pox = X - fr.Ow[0], poy = Y - fr.Ow[1], poz = Z - fr.Ow[2];
-            const float dist = sqrtf(pox * pox + (poy * poy + poz * poz));
-            if (!(dist < minDistance || dist > maxDistance)) {
-                const float viewCos = (pox * p.normal[0] + (poy * p.normal[1] + poz * p.normal[2])) / dist;
-                if (!(viewCos < fr.viewing_cos_limit)) {
-                    const float ratio = p.max_dist / dist;
-                    int lvl = 0;
-                    for (int k = 0; k + 1 < fr.nlevels; ++k) lvl += ratio >= D.T[k];
-                    o.level = lvl;
-                    o.proj_xr = u - fr.bf * (1.0f / pcz);
-                    o.track_depth = sqrtf(pcx * pcx + (pcy * pcy + pcz * pcz));
-                    o.view_cos = viewCos;
-                    in = true;
-                }
-            }
-        }
-    }
-    q[i] = o;
-    in_view[i] = in ? 1 : 0;
-    if (in) atomicAdd(count, 1);
-}
-
-// stable compaction of the in-view queries (the order SearchByProjection walks vpMapPoints in): one CTA, block-wide scan in chunks of 1024
-__global__ void __launch_bounds__(1024)
-k_compact_queries(const plvs_mp_query* __restrict__ q, const uint8_t* __restrict__ in_view, int n, plvs_mp_query* __restrict__ out, int32_t* __restrict__ src_index)
-{
-    __shared__ int s_warp[32];
-    __shared__ int s_base;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_base = 0;
-    __syncthreads();
-    for (int c0 = 0; c0 < n; c0 += 1024) {
-        const int i = c0 + tid;
-        const int f = (i < n && in_view[i]) ? 1 : 0;
-        int x = f;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) s_warp[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            int w = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-            s_warp[lane] = w;
-        }
-        __syncthreads();
-        const int pos = s_base + (wid ? s_warp[wid - 1] : 0) + x - f;
-        if (f) { out[pos] = q[i]; src_index[pos] = i; }
-        __syncthreads();
-        if (tid == 1023) s_base += s_warp[31];
-        __syncthreads();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:732-852), monocular start-up.
-// k_init_candidates: one warp per level-0 keypoint of F1 lists the level-0 keypoints of F2 inside the square window around its
-// previously matched position, in GetFeaturesInArea order, with their Hamming distances (all of it independent of the other queries).
-// k_init_resolve: what is left IS sequential -- a candidate is skipped when an earlier accepted match on it was at least as good
-// (vMatchedDistance), and a winner takes a feature away from an earlier query (vnMatches21) -- so one warp walks the queries in
-// order with the matched distances in shared memory: lanes over the candidates, best = first position of the smallest distance,
-// second = second smallest of the multiset (what the if / else-if pair computes).  Mono initialisation handles ~10^3 level-0
-// keypoints a few times per session; the sequential pass is a few hundred microseconds.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_init_candidates(ViewDev F1, ViewDev F2, const int* __restrict__ cell_start, const int* __restrict__ sorted, const float2* __restrict__ prev,
-                  float window, uint32_t* __restrict__ cand, int* __restrict__ cand_n, int cap)
-{
-    const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (q >= F1.n) return;
-    const int level1 = F1.keys[q].octave;
-    int count = 0, c0, c1, r0, r1;
-    const float2 pm = prev[q];
-    if (level1 <= 0 && cell_window(F2.gp, pm.x, pm.y, window, c0, c1, r0, r1)) {
-        const bool check = (level1 > 0) || (level1 >= 0);               // GetFeaturesInArea(x, y, r, level1, level1)
-        const uint8_t* qd = F1.desc + (size_t)q * 32;
-        const uint4 a0 = *reinterpret_cast<const uint4*>(qd), a1 = *reinterpret_cast<const uint4*>(qd + 16);
-        uint32_t* out = cand + (size_t)q * cap;
-        for (int ix = c0; ix <= c1; ++ix) {
-            const int pbeg = cell_start[ix * GRID_ROWS + r0], pend = cell_start[ix * GRID_ROWS + r1 + 1];
-            for (int p = pbeg + lane; p < ((pend - pbeg + 31) / 32) * 32 + pbeg; p += 32) {
-                bool ok = p < pend;
-                int idx = 0, oct = 0, dist = 0;
-                if (ok) {
-                    idx = sorted[p];
-                    const plvs_keypoint kp = F2.keys[idx];
-                    oct = kp.octave;
-                    if (check && (oct < level1 || oct > level1)) ok = false;
-                    if (ok && !(fabsf(kp.x - pm.x) < window && fabsf(kp.y - pm.y) < window)) ok = false;
-                    if (ok) dist = hamming256(a0, a1, F2.desc + (size_t)idx * 32);
-                }
-                const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                if (ok) { const int pos = count + __popc(m & ((1u << lane) - 1)); if (pos < cap) out[pos] = pack_cand(idx, dist, oct & 31); }
-                count += __popc(m);
-            }
-        }
-    }
-    if (lane == 0) cand_n[q] = count;
-}
-
-__global__ void __launch_bounds__(32)
-k_init_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int cap, const plvs_keypoint* __restrict__ k1,
-               const plvs_keypoint* __restrict__ k2, int n1, int n2, float ratio, int check_ori, int32_t* __restrict__ m12, int32_t* __restrict__ m21,
-               int* __restrict__ bin_of, float2* __restrict__ prev, int32_t* __restrict__ m12_out, float2* __restrict__ prev_out, int* __restrict__ result)
-{
-    extern __shared__ uint16_t s_md[];                  // vMatchedDistance: 0xffff = INT_MAX, else a Hamming distance
-    __shared__ int s_hist[HISTO], s_keep[HISTO];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < n2; i += 32) { s_md[i] = 0xffff; m21[i] = -1; }
-    for (int i = lane; i < n1; i += 32) { m12[i] = -1; bin_of[i] = -1; }
-    if (lane < HISTO) { s_hist[lane] = 0; s_keep[lane] = 1; }
-    __syncwarp();
-    int nmatches = 0;                                   // lane 0's copy is the one that counts
-    for (int q = 0; q < n1; ++q) {
-        const int cn = min(cand_n[q], cap);
-        if (cn == 0) continue;
-        int best = INT_MAX, bpos = INT_MAX, bidx = -1, second = INT_MAX;
-        const uint32_t* list = cand + (size_t)q * cap;
-        for (int p = lane; p < cn; p += 32) {
-            const uint32_t c = list[p];
-            const int i2 = cand_idx(c), d = cand_dist(c);
-            if ((int)s_md[i2] <= d) continue;           // an earlier query holds this feature with a distance at least as small
-            if (d < best) { second = best; best = d; bpos = p; bidx = i2; }
-            else if (d < second) second = d;
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            const int ob = __shfl_xor_sync(0xffffffffu, best, o), op = __shfl_xor_sync(0xffffffffu, bpos, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bidx, o), os = __shfl_xor_sync(0xffffffffu, second, o);
-            const int ns = min(min(second, os), max(best, ob));
-            if (ob < best || (ob == best && op < bpos)) { best = ob; bpos = op; bidx = oi; }
-            second = ns;
-        }
-        if (best <= TH_LOW && (float)best < (float)second * ratio) {
-            if (lane == 0) {
-                const int before = m21[bidx];
-                if (before >= 0) { m12[before] = -1; --nmatches; }
-                m12[q] = bidx; m21[bidx] = q; s_md[bidx] = (uint16_t)best; ++nmatches;
-                if (check_ori) {
-                    float rot = k1[q].angle - k2[bidx].angle;
-                    if (rot < 0.0f) rot += 360.0f;
-                    int bin = (int)roundf(rot * (HISTO / 360.0f));
-                    if (bin == HISTO) bin = 0;
-                    bin_of[q] = bin; ++s_hist[bin];      // stays in the histogram even if the match is stolen later
-                }
-            }
-            __syncwarp();
-        }
-    }
-    __syncwarp();
-    int dropped = 0;
-    if (check_ori) {
-        if (lane == 0) {
-            int m1 = 0, m2 = 0, m3 = 0, i1 = -1, i2 = -1, i3 = -1;
-            for (int i = 0; i < HISTO; ++i) {
-                const int s = s_hist[i];
-                if (s > m1) { m3 = m2; m2 = m1; m1 = s; i3 = i2; i2 = i1; i1 = i; }
-                else if (s > m2) { m3 = m2; m2 = s; i3 = i2; i2 = i; }
-                else if (s > m3) { m3 = s; i3 = i; }
-            }
-            if ((float)m2 < 0.1f * (float)m1) { i2 = -1; i3 = -1; }
-            else if ((float)m3 < 0.1f * (float)m1) { i3 = -1; }
-            for (int i = 0; i < HISTO; ++i) s_keep[i] = (i == i1 || i == i2 || i == i3);
-        }
-        __syncwarp();
-        for (int i = lane; i < n1; i += 32) {
-            const int b = bin_of[i];
-            if (b >= 0 && !s_keep[b] && m12[i] >= 0) { m12[i] = -1; ++dropped; }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) dropped += __shfl_xor_sync(0xffffffffu, dropped, o);
-    for (int i = lane; i < n1; i += 32) {
-        const int j = m12[i];
-        float2 pm = prev[i];
-        if (j >= 0) pm = make_float2(k2[j].x, k2[j].y);                 // "update prev matched" (:847-849)
-        m12_out[i] = j; prev_out[i] = pm;
-    }
-    if (lane == 0) result[0] = nmatches - dropped;
-}
+#include "match_init.cuh"
 
 __global__ void k_fill_i32(int32_t* p, int n, int32_t v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 

@@ -1,0 +1,205 @@
+// TEST INFRASTRUCTURE ONLY -- a small CPU execution model for CUDA device code, so that kernels which have not met a GPU yet can be
+// run in this container: tests/native/emu_kernels.cpp includes the product's device-only headers (plvs_b200/csrc/*.cuh) after this
+// file and drives them through emu::launch.  Nothing here is linked into libplvs_b200.so, and nothing in the product falls back to it.
+//
+// Model: one CTA at a time; every CUDA thread is a ucontext fiber on the calling OS thread (so "atomics" are plain operations and
+// __shared__ variables are function-level statics), scheduled round-robin.  __syncthreads / __syncwarp / __shfl_*_sync / __ballot_sync
+// are rendezvous points: a fiber that reaches one yields until every live thread of the CTA (or every live lane named by the mask) has
+// arrived.  A rendezvous that can never complete (divergent barrier, a shuffle some lane skips) is reported as a deadlock instead of
+// hanging.  Floating point: x86-64 SSE arithmetic is IEEE like the device's with --fmad=false; compile with -ffp-contract=off.
+// Not modelled: clusters, TMA / mbarrier, tensor cores, memory ordering weaker than sequential consistency, scheduling races.
+#pragma once
+#define PLVS_CUDA_EMU 1
+#include <ucontext.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+struct dim3 { unsigned x, y, z; dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {} };
+struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+struct int2 { int x, y; };
+struct float2 { float x, y; };
+struct float3 { float x, y, z; };
+struct float4 { float x, y, z, w; };
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline float3 make_float3(float x, float y, float z) { return float3{x, y, z}; }
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
+
+namespace emu {
+
+struct Fiber {
+    ucontext_t ctx;
+    std::unique_ptr<char[]> stack;
+    dim3 tid;
+    int linear = 0;
+    bool done = false;
+};
+
+struct Warp { uint64_t vals[32]; uint32_t preds = 0; int arrived = 0; unsigned gen = 0; uint32_t alive = 0; };
+
+struct State {
+    std::vector<Fiber> fibers;
+    std::vector<Warp> warps;
+    Fiber* cur = nullptr;
+    ucontext_t sched;
+    dim3 bid, bdim, gdim;
+    int alive = 0, bar_arrived = 0;
+    unsigned bar_gen = 0;
+    long idle = 0;                 // consecutive yields without progress: deadlock detector
+    std::function<void()>* body = nullptr;
+    std::vector<char> dyn;
+    char* dyn_smem = nullptr;
+    const char* failure = nullptr;
+};
+inline State& st() { static State s; return s; }
+
+inline void yield()
+{
+    State& g = st();
+    if (++g.idle > 64L * (long)g.fibers.size() + 4096) { g.failure = "deadlock: a barrier / warp rendezvous can never complete"; }
+    swapcontext(&g.cur->ctx, &g.sched);
+}
+
+inline void trampoline()
+{
+    State& g = st();
+    (*g.body)();
+    Fiber* f = g.cur;
+    f->done = true; g.idle = 0;
+    --g.alive;
+    g.warps[f->linear >> 5].alive &= ~(1u << (f->linear & 31));
+    swapcontext(&f->ctx, &g.sched);
+}
+
+template <class F>
+void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call)
+{
+    State& g = st();
+    std::function<void()> body = kernel_call;
+    g.body = &body; g.bdim = block; g.gdim = grid;
+    const int nthreads = (int)(block.x * block.y * block.z);
+    const size_t stack_bytes = 256 * 1024;
+    g.dyn.assign(smem_bytes + 16, 0); g.dyn_smem = g.dyn.data();
+    for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; ++bx) {
+        g.bid = dim3(bx, by, bz);
+        g.fibers.clear(); g.fibers.resize(nthreads);
+        g.warps.assign((nthreads + 31) / 32, Warp());
+        g.alive = nthreads; g.bar_arrived = 0; g.idle = 0; g.failure = nullptr;
+        for (int t = 0; t < nthreads; ++t) {
+            Fiber& f = g.fibers[t];
+            f.linear = t; f.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y)); f.done = false;
+            f.stack.reset(new char[stack_bytes]);
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack.get(); f.ctx.uc_stack.ss_size = stack_bytes; f.ctx.uc_link = nullptr;
+            makecontext(&f.ctx, (void (*)())trampoline, 0);
+            g.warps[t >> 5].alive |= 1u << (t & 31);
+        }
+        while (g.alive > 0) {
+            for (int t = 0; t < nthreads && g.alive > 0; ++t) {
+                Fiber& f = g.fibers[t];
+                if (f.done) continue;
+                g.cur = &f;
+                swapcontext(&g.sched, &f.ctx);
+                if (g.failure) { const char* why = g.failure; g.failure = nullptr; g.fibers.clear(); throw std::runtime_error(why); }
+            }
+        }
+        g.fibers.clear();
+    }
+}
+
+inline void cta_barrier()
+{
+    State& g = st();
+    const unsigned my = g.bar_gen;
+    ++g.bar_arrived;
+    while (g.bar_gen == my) {
+        if (g.bar_arrived >= g.alive) { g.bar_arrived = 0; ++g.bar_gen; g.idle = 0; break; }
+        yield();
+    }
+}
+
+inline Warp& my_warp() { State& g = st(); return g.warps[g.cur->linear >> 5]; }
+inline int lane_id() { return st().cur->linear & 31; }
+
+inline void warp_barrier(uint32_t mask)
+{
+    Warp& w = my_warp();
+    const unsigned my = w.gen;
+    ++w.arrived;
+    while (w.gen == my) {
+        if (w.arrived >= __builtin_popcount(mask & w.alive)) { w.arrived = 0; ++w.gen; st().idle = 0; break; }
+        yield();
+    }
+}
+
+template <class T> inline uint64_t to_bits(T v) { uint64_t b = 0; static_assert(sizeof(T) <= 8, "shuffle payload"); std::memcpy(&b, &v, sizeof(T)); return b; }
+template <class T> inline T from_bits(uint64_t b) { T v; std::memcpy(&v, &b, sizeof(T)); return v; }
+
+template <class T> inline T shfl(uint32_t mask, T v, int src)
+{
+    Warp& w = my_warp();
+    w.vals[lane_id()] = to_bits(v);
+    warp_barrier(mask);
+    const T r = (src >= 0 && src < 32 && ((w.alive >> src) & 1u)) ? from_bits<T>(w.vals[src]) : v;
+    warp_barrier(mask);
+    return r;
+}
+
+}  // namespace emu
+
+// ---- the CUDA surface the device-only headers use -------------------------------------------------------------------------------
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __constant__ static
+#define __align__(n) alignas(n)
+#define PLVS_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::st().dyn_smem)
+#define threadIdx (emu::st().cur->tid)
+#define blockIdx (emu::st().bid)
+#define blockDim (emu::st().bdim)
+#define gridDim (emu::st().gdim)
+
+using std::max;
+using std::min;
+
+inline void __syncthreads() { emu::cta_barrier(); }
+inline void __syncwarp(uint32_t mask = 0xffffffffu) { emu::warp_barrier(mask); }
+inline void __threadfence() {}
+template <class T> inline T __shfl_sync(uint32_t m, T v, int src) { return emu::shfl(m, v, src); }
+template <class T> inline T __shfl_xor_sync(uint32_t m, T v, int x) { return emu::shfl(m, v, emu::lane_id() ^ x); }
+template <class T> inline T __shfl_up_sync(uint32_t m, T v, unsigned d) { const int l = emu::lane_id(); return emu::shfl(m, v, l >= (int)d ? l - (int)d : l); }
+template <class T> inline T __shfl_down_sync(uint32_t m, T v, unsigned d) { const int l = emu::lane_id(); return emu::shfl(m, v, l + (int)d < 32 ? l + (int)d : l); }
+inline uint32_t __ballot_sync(uint32_t mask, bool pred)
+{
+    emu::Warp& w = emu::my_warp();
+    emu::warp_barrier(mask);                      // the previous ballot's readers are done
+    if (pred) w.preds |= 1u << emu::lane_id(); else w.preds &= ~(1u << emu::lane_id());
+    emu::warp_barrier(mask);
+    const uint32_t r = w.preds & mask & w.alive;
+    emu::warp_barrier(mask);
+    return r;
+}
+inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+template <class T> inline T atomicAdd(T* p, T v) { const T o = *p; *p = o + v; return o; }
+template <class T> inline T atomicSub(T* p, T v) { const T o = *p; *p = o - v; return o; }
+template <class T> inline T atomicExch(T* p, T v) { const T o = *p; *p = v; return o; }
+template <class T> inline T atomicCAS(T* p, T cmp, T v) { const T o = *p; if (o == cmp) *p = v; return o; }
+template <class T> inline T atomicMax(T* p, T v) { const T o = *p; if (v > o) *p = v; return o; }
+template <class T> inline T atomicMin(T* p, T v) { const T o = *p; if (v < o) *p = v; return o; }

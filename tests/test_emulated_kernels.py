@@ -1,0 +1,151 @@
+"""CPU: the product's own kernel source (plvs_b200/csrc/*.cuh, device-only headers) executed on the small CPU model of CUDA in
+tests/native/cuda_emu.hpp -- every CUDA thread a fiber, barriers / shuffles / ballots as rendezvous points -- and compared with the oracle.
+It exists for the kernels written after the round's GPU budget was spent (tests/test_zz_gpu_unverified.py holds their GPU tests): index
+arithmetic, warp-level reductions, prefix sums, barrier placement and float operation order are exercised here with the real text; what a CPU
+model cannot show (memory-ordering races, launch configuration limits, nvcc code generation) stays for the GPU run.  k_build_grid and
+k_in_frustum already passed on a B200 and double as a check of the model itself."""
+import ctypes as C
+import numpy as np
+import pytest
+
+from plvs_b200 import synth, scenario, tsdf as T, _lib as ABI
+from plvs_b200.matcher import Frame
+from plvs_b200.orb import KP_DTYPE
+from oracle import match as OM, orb as O, tsdf as OT
+from tests.native_build import build_emulated_kernels
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return C.CDLL(build_emulated_kernels())
+
+
+@pytest.fixture(scope="module")
+def frames():
+    K = synth.intrinsics(640, 480)
+    tab = O.Tables(3000)
+    out = []
+    for f in (10, 11, 14):
+        kp, desc, _, _ = O.extract_port(synth.gray_frame(f), 3000)
+        out.append(scenario.make_frame(kp, desc, synth.depth_frame(f), K, tab.scale))
+    return K, tab, out
+
+
+def test_model_on_a_verified_kernel_build_grid(emu, frames):
+    """k_build_grid (1024 threads: shared-memory histogram, two-level shuffle scan, atomics, per-cell insertion sort) passed on the B200;
+    here it has to reproduce Frame::AssignFeaturesToGrid's cell lists on the CPU model"""
+    _, _, fr = frames
+    f = fr[0]
+    v = f.view()
+    cs = np.zeros(64 * 48 + 1, np.int32); srt = np.zeros(f.n, np.int32)
+    assert emu.emu_build_grid(C.byref(v), cs.ctypes.data_as(C.c_void_p), srt.ctypes.data_as(C.c_void_p)) == 0
+    def c_round(v):                                            # C round(): halves away from zero (numpy rounds them to even)
+        v = v.astype(np.float64)
+        return np.where(v >= 0, np.floor(v + 0.5), np.ceil(v - 0.5)).astype(int)
+    px = c_round((f.keys["x"] - np.float32(f.min_x)) * np.float32(f.grid_inv_w))
+    py = c_round((f.keys["y"] - np.float32(f.min_y)) * np.float32(f.grid_inv_h))
+    ok = (px >= 0) & (px < 64) & (py >= 0) & (py < 48)
+    cell = px * 48 + py
+    want = [np.nonzero(ok & (cell == c))[0] for c in range(64 * 48)]
+    assert cs[-1] == ok.sum()
+    for c in range(64 * 48):
+        assert np.array_equal(srt[cs[c]:cs[c + 1]], want[c])
+
+
+@pytest.mark.parametrize("window,ratio,check,cap", [(100, 0.9, True, 128), (100, 0.9, False, 128), (30, 0.7, True, 128), (400, 1.0, True, 16), (10, 0.9, True, 4)])
+def test_search_for_initialization_kernels(emu, frames, window, ratio, check, cap):
+    """k_init_candidates + k_init_resolve == the oracle (pinned to the reference's compiled SearchForInitialization): matches, count, updated
+    vbPrevMatched; small initial caps force the redo-with-room loop of the entry point"""
+    _, _, fr = frames
+    f1, f2, f3 = fr
+    prev = np.stack([f1.keys["x"], f1.keys["y"]], 1).astype(np.float32)
+    emu.emu_match_initialization.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    for other in (f2, f3):
+        v1, v2 = f1.view(), other.view()
+        p = prev.copy(); m = np.full(f1.n, -1, np.int32); nm = C.c_int()
+        assert emu.emu_match_initialization(C.byref(v1), C.byref(v2), p.ctypes.data_as(C.c_void_p), window, ratio, int(check), m.ctypes.data_as(C.c_void_p),
+                                            C.byref(nm), cap) == 0
+        on, om, op = OM.search_for_initialization(f1, other, prev, window, ratio, check)
+        assert nm.value == on and np.array_equal(m, om) and np.array_equal(p.view(np.uint32), op.view(np.uint32))
+        if window >= 30:
+            assert on > 50
+        prev = op
+
+
+def test_in_frustum_and_compaction_kernels(emu, frames):
+    """k_in_frustum (already green on the B200) and k_compact_queries (not yet): the in-view queries, in order, with their source indices;
+    n is not a multiple of 1024 and spans several chunks of the block-wide scan"""
+    K, tab, fr = frames
+    last, cur = fr[0], fr[1]
+    Tl, Tc = synth.pose(10), synth.pose(11)
+    ok = last.depth_at_kp > 0
+    Pw = scenario.backproject(last.keys[ok], last.depth_at_kp[ok], K, Tl)
+    Pw = np.concatenate([Pw, Pw + np.float32(0.01), Pw[::-1] * np.float32(1.5)])           # ~ 3 x 1500 points, some out of view
+    n = len(Pw)
+    rng = np.random.default_rng(2)
+    pts = np.zeros(n, OM.MAP_POINT)
+    pts["xw"] = Pw
+    Ow = np.asarray(Tl, np.float64).reshape(3, 4)[:, 3]
+    v = Pw.astype(np.float64) - Ow; d = np.linalg.norm(v, axis=1)
+    pts["normal"] = (v / d[:, None]).astype(np.float32)
+    pts["max_dist"] = (d * rng.uniform(0.8, 2.0, n)).astype(np.float32); pts["min_dist"] = (pts["max_dist"] / tab.scale[7]).astype(np.float32)
+    pts["flags"] = (rng.random(n) < 0.9).astype(np.uint32); pts["desc"] = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    frm = OM.make_frustum(Tc, K, (0.0, 0.0, 640.0, 480.0), K["bf"], 0.5, 1.2, 8)
+    Tt = np.zeros(16, np.float32); Tt[:7] = OM.scale_thresholds(1.2, 8)
+    q = np.zeros(n, OM.MP_QUERY); iv = np.zeros(n, np.uint8); cq = np.zeros(n, OM.MP_QUERY); src = np.full(n, -1, np.int32); cnt = C.c_int()
+    assert emu.emu_in_frustum(C.byref(frm), Tt.ctypes.data_as(C.c_void_p), pts.ctypes.data_as(C.c_void_p), n, q.ctypes.data_as(C.c_void_p),
+                              iv.ctypes.data_as(C.c_void_p), C.byref(cnt), cq.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p)) == 0
+    on, oq, oiv = OM.in_frustum(frm, pts)
+    assert cnt.value == on and np.array_equal(iv, oiv) and np.array_equal(q.tobytes(), oq.tobytes())
+    assert 1000 < on < n - 100 and n > 3 * 1024
+    idx = np.nonzero(oiv)[0]
+    assert np.array_equal(src[:on], idx) and np.array_equal(cq[:on].tobytes(), oq[idx].tobytes())
+
+
+def test_undistort_kernel(emu, frames):
+    cv2 = pytest.importorskip("cv2")
+    _, _, fr = frames
+    kp = fr[0].keys
+    xy = np.stack([kp["x"], kp["y"]], 1).astype(np.float32)
+    emu.emu_undistort.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    for K4, dist in (((517.306408, 516.469215, 318.643040, 255.313989), (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)),
+                     ((458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)),
+                     ((500.0, 500.0, 320.0, 240.0), (0.1, -0.2, 0.001, -0.002, 0.05, 0.01, -0.02, 0.003))):
+        K4f = [float(np.float32(v)) for v in K4]                       # the camera matrix and the coefficients are CV_32F in PLVS (src/Frame.cc:1521-1527)
+        k14 = np.zeros(14, np.float64); k14[:len(dist)] = np.array(dist, np.float32)
+        out = np.zeros(len(kp), KP_DTYPE)
+        assert emu.emu_undistort(kp.ctypes.data_as(C.c_void_p), len(kp), *K4f, k14.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)) == 0
+        want = O.undistort_points(xy, K4, np.array(dist, np.float32))
+        Km = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], np.float32)
+        cvw = cv2.undistortPoints(xy.reshape(-1, 1, 2), Km, np.array(dist, np.float32), None, Km).reshape(-1, 2)
+        assert np.array_equal(want.view(np.uint32), cvw.view(np.uint32))
+        assert np.array_equal(out["x"].view(np.uint32), want[:, 0].view(np.uint32)) and np.array_equal(out["y"].view(np.uint32), want[:, 1].view(np.uint32))
+        for f in ("size", "angle", "response", "octave", "class_id"):
+            assert np.array_equal(out[f], kp[f])
+
+
+@pytest.mark.parametrize("color,res,far", [(1, 0.04, 4.0), (0, 0.04, 4.0), (1, 0.5, 6.0)])
+def test_mesh_kernels(emu, color, res, far):
+    """k_mesh_count / k_mesh_emit / k_mesh_shade over the oracle's voxel blocks (handed over in a shuffled pool order) == the oracle's meshes, which
+    are pinned bit-exactly to the compiled open_chisel: chunk order, vertex order, positions, normals, colours"""
+    K = synth.intrinsics(160, 120)
+    p = T.default_params(voxel_resolution=res, use_carving=1, near_plane=0.1, far_plane=far, max_blocks=8192, use_color=color)
+    o = OT.Map(p, threads=8); o.set_camera(K["fx"], K["fy"], K["cx"], K["cy"], 160, 120)
+    for f in (0, 1, 2, 6):
+        o.integrate(synth.depth_frame(f, 160, 120), synth.pose(f), synth.bgr_frame(f, 160, 120) if color else None)
+    keys, sdf, w, rgba = o.download()
+    perm = np.random.default_rng(0).permutation(len(keys))
+    keys, sdf, w, rgba = (np.ascontiguousarray(a[perm]) for a in (keys, sdf, w, rgba))
+    emu.emu_update_meshes.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_longlong, C.c_void_p]
+    ok, oc, oV, oN, oC = o.extract_mesh()
+    nb = len(keys)
+    mk = np.zeros((nb, 3), np.int32); mc = np.zeros(nb, np.int32); nv = C.c_longlong()
+    V = np.zeros((len(oV) + 8, 3), np.float32); N = np.zeros_like(V); Cc = np.zeros_like(V)
+    nm = emu.emu_update_meshes(nb, keys.ctypes.data_as(C.c_void_p), sdf.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), rgba.ctypes.data_as(C.c_void_p),
+                               res, color, mk.ctypes.data_as(C.c_void_p), mc.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p), N.ctypes.data_as(C.c_void_p),
+                               Cc.ctypes.data_as(C.c_void_p), len(V), C.byref(nv))
+    assert nm == len(ok) and nv.value == len(oV) and nm > 3
+    assert np.array_equal(mk[:nm], ok) and np.array_equal(mc[:nm], oc)
+    for a, b in ((V, oV), (N, oN), (Cc, oC)):
+        assert np.array_equal(a[:len(oV)].view(np.uint32), b.view(np.uint32))

@@ -1,6 +1,7 @@
-"""-m gpu: features written after the round's GPU budget was spent.  The kernels compile for sm_100a and their oracles are pinned on the CPU, but
-these comparisons have not run on a GPU yet -- hence the non-strict xfail (a pass shows as XPASS, a failure does not fail the suite) and the
-file name that sorts behind every other GPU test."""
+"""-m gpu: features written after the round's GPU budget was spent.  The kernels compile for sm_100a, their oracles are pinned on the CPU, and
+their source text runs oracle-identical on the CPU execution model of tests/native/cuda_emu.hpp (tests/test_emulated_kernels.py) -- but these
+comparisons have not run on a GPU yet, hence the non-strict xfail (a pass shows as XPASS, a failure does not fail the suite) and the file
+name that sorts behind every other GPU test."""
 import cv2
 import numpy as np
 import pytest
