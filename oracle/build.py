@@ -8,13 +8,13 @@ The reference's own sources for the path are compiled separately by oracle/ref_b
 import os, subprocess, sys, pathlib
 
 HERE = pathlib.Path(__file__).resolve().parent
-SRCS = ["orb_oracle.cpp", "match_oracle.cpp", "tsdf_oracle.cpp"]
+SRCS = ["orb_oracle.cpp", "match_oracle.cpp", "tsdf_oracle.cpp", "bow_oracle.cpp"]
 OUT = HERE / "liboracle.so"
 
 
 def build(force=False):
     srcs = [HERE / s for s in SRCS if (HERE / s).exists()]
-    deps = srcs + [HERE.parent / "plvs_b200" / "csrc" / "orb_pattern.inc"]
+    deps = srcs + [HERE.parent / "plvs_b200" / "csrc" / "orb_pattern.inc", HERE.parent / "plvs_b200" / "csrc" / "mc_tables.inc"]
     if OUT.exists() and not force and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return str(OUT)
     cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared",

@@ -20,11 +20,15 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <cstdio>
+#include <cstdlib>
+#include <sstream>
 #include <vector>
 
 typedef unsigned char uchar;
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5      // named by DBoW2's FORB::toMat32F (never called here; this Mat holds bytes)
 #define CV_PI 3.1415926535897932384626433832795
 
 extern "C" {
@@ -225,6 +229,34 @@ struct KeyPointsFilter {       // only referenced by ComputeKeyPointsOld, which 
         }
     }
 };
+
+// cv::FileStorage / cv::FileNode: DBoW2's TemplatedVocabulary.h names them in its YAML save/load members.  The oracle builds read vocabularies
+// with loadFromTextFile and never call those members; the stubs exist so that the header parses and links, and abort if reached.
+[[noreturn]] inline void filestorage_unavailable() { std::fprintf(stderr, "cv stand-in: cv::FileStorage is not available\n"); std::abort(); }
+class FileNode {
+public:
+    enum { NONE = 0, SEQ = 4, MAP = 5 };
+    FileNode operator[](const char*) const { filestorage_unavailable(); }
+    FileNode operator[](const std::string&) const { filestorage_unavailable(); }
+    FileNode operator[](int) const { filestorage_unavailable(); }
+    int type() const { filestorage_unavailable(); }
+    size_t size() const { filestorage_unavailable(); }
+    operator int() const { filestorage_unavailable(); }
+    operator float() const { filestorage_unavailable(); }
+    operator double() const { filestorage_unavailable(); }
+    operator std::string() const { filestorage_unavailable(); }
+};
+class FileStorage {
+public:
+    enum { READ = 0, WRITE = 1 };
+    FileStorage() {}
+    FileStorage(const std::string&, int) {}
+    bool isOpened() const { return false; }
+    void release() {}
+    FileNode operator[](const char*) const { filestorage_unavailable(); }
+    FileNode operator[](const std::string&) const { filestorage_unavailable(); }
+};
+template <class T> FileStorage& operator<<(FileStorage&, const T&) { filestorage_unavailable(); }
 
 }  // namespace cv
 #endif

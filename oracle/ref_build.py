@@ -205,3 +205,24 @@ if __name__ == "__main__":
     print(build_match(force="-f" in sys.argv))
     print(build_stereo(force="-f" in sys.argv))
     print(build_frustum(force="-f" in sys.argv))
+
+
+BOW_OUT = OUTDIR / "libbow_ref.so"
+
+
+def build_bow(force=False):
+    """Thirdparty/DBoW2 (TemplatedVocabulary.h, FORB.cpp, BowVector.cpp, FeatureVector.cpp, ScoringObject.cpp, DUtils) + oracle/ref_bow_harness.cpp
+    -> oracle/_ref/libbow_ref.so, against the OpenCV stand-in (cv::Mat of bytes; cv::FileStorage only as aborting stubs: vocabularies are
+    read with the reference's loadFromTextFile)."""
+    ref = pathlib.Path("/root/reference/Thirdparty/DBoW2")
+    if not (ref / "DBoW2" / "TemplatedVocabulary.h").exists():
+        return str(BOW_OUT) if BOW_OUT.exists() else None
+    srcs = [HERE / "ref_bow_harness.cpp"] + [ref / "DBoW2" / n for n in ("BowVector.cpp", "FeatureVector.cpp", "FORB.cpp", "ScoringObject.cpp")] + \
+        [ref / "DUtils" / n for n in ("Random.cpp", "Timestamp.cpp")]
+    deps = srcs + [ref / "DBoW2" / "TemplatedVocabulary.h", HERE / "cv_standin" / "opencv2" / "opencv.hpp"]
+    if BOW_OUT.exists() and not force and all(BOW_OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return str(BOW_OUT)
+    OUTDIR.mkdir(parents=True, exist_ok=True)
+    flags = ["-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w", "-I", str(HERE / "cv_standin"), "-I", str(ref / "DBoW2"), "-I", str(ref)]
+    subprocess.check_call(["g++"] + flags + ["-shared", "-o", str(BOW_OUT)] + [str(x) for x in srcs] + ["-lm"])
+    return str(BOW_OUT)
