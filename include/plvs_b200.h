@@ -251,6 +251,29 @@ typedef struct {
     const int32_t* features;      /* offsets[n_nodes] */
 } plvs_featvec;
 
+/* ---------------------------------------------------------------------------------------------------------------------------------
+ * Bag of words: ORBVocabulary (include/ORBVocabulary.h = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>) as
+ * Frame::ComputeBoW / KeyFrame::ComputeBoW use it (src/Frame.cc:1498-1505): transform(vCurrentDesc, mBowVec, mFeatVec, 4).
+ * plvs_voc_load_text = TemplatedVocabulary::loadFromTextFile (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1351-1436, the ORBvoc.txt format;
+ * empty lines are ignored).  plvs_voc_create takes the same tree as flat arrays: node 0 is the root, parent[i] < i, word_id[i] >= 0 for
+ * leaves (-1 otherwise), 32 descriptor bytes and a weight per node; scoring / weighting are DBoW2's enums (BowVector.h:39-56).
+ * plvs_voc_transform = transform(features, BowVector&, FeatureVector&, levelsup) (:1140-1207): per feature the word, its weight and the node
+ * `levelsup` levels above the leaves (any of the three may be NULL); the BowVector as ascending word ids + values (n entries at most); the
+ * FeatureVector flattened as in plvs_featvec -- fv_nodes and fv_features hold n entries at most, fv_offsets n + 1.  fv_device, if not NULL, receives the
+ * same FeatureVector as device pointers -- valid until the next transform on this handle -- for the matcher entry points that take
+ * device-resident frames.  desc may be a device pointer (desc_on_device != 0: the extractor's descriptor buffer). */
+typedef struct plvs_voc plvs_voc;
+int plvs_voc_create(int device, int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent, const int32_t* word_id,
+                    const uint8_t* desc, const double* weight, plvs_voc** out);
+int plvs_voc_load_text(const char* path, int device, plvs_voc** out);
+void plvs_voc_destroy(plvs_voc* h);
+int plvs_voc_size(const plvs_voc* h);
+int plvs_voc_transform(plvs_voc* h, const uint8_t* desc, int n, int desc_on_device, int levelsup, uint32_t* word, double* weight, uint32_t* node,
+                       uint32_t* bow_ids, double* bow_vals, int* n_bow, uint32_t* fv_nodes, int32_t* fv_offsets, int32_t* fv_features,
+                       int* n_fv_nodes, plvs_featvec* fv_device);
+/* the BowVector step of the transform on its own (host arithmetic, no device involved): bow_ids / bow_vals sized for n entries */
+int plvs_bow_vector(int scoring, int weighting, const uint32_t* word, const double* weight, int n, uint32_t* bow_ids, double* bow_vals, int* n_bow);
+
 /* ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:999-1242), monocular-camera branch
  * (mpCamera2 == NULL).  has_mp*[i]!=0 <=> KeyFrame::GetMapPoint(i) != NULL.  F12 = the matrix
  * Pinhole::epipolarConstrain builds (src/CameraModels/Pinhole.cpp:125-131), row-major; ep = epipole

@@ -131,6 +131,13 @@ def load():
     lib.plvs_tsdf_integrate_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
     lib.plvs_tsdf_integrate_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.plvs_tsdf_last_stats.argtypes = [C.c_void_p, C.POINTER(TsdfStats)]
+    lib.plvs_voc_create.argtypes = [C.c_int] * 6 + [C.c_void_p] * 5
+    lib.plvs_voc_load_text.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+    lib.plvs_voc_destroy.argtypes = [C.c_void_p]; lib.plvs_voc_destroy.restype = None
+    lib.plvs_voc_size.argtypes = [C.c_void_p]
+    lib.plvs_voc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(C.c_int)] + [C.c_void_p] * 3 + \
+        [C.POINTER(C.c_int), C.c_void_p]
+    lib.plvs_bow_vector.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     lib.plvs_tsdf_update_meshes.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
     lib.plvs_tsdf_get_meshes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]
     lib.plvs_tsdf_download_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]

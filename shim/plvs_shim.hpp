@@ -655,6 +655,46 @@ protected:
     plvs_match* h_ = nullptr;
 };
 
+// ------------------------------------------------------------------------------------------------------
+// ORBVocabulary (include/ORBVocabulary.h: DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>) for the calls PLVS makes on the path:
+// loadFromTextFile (src/System.cc) and transform(features, BowVector&, FeatureVector&, levelsup) from Frame::ComputeBoW / KeyFrame::ComputeBoW
+// (src/Frame.cc:1498-1505).  BowVectorT / FeatureVectorT are DBoW2's own map types (std::map<WordId, WordValue>, std::map<NodeId,
+// std::vector<unsigned>>): the device returns them flattened in ascending key order, so they are rebuilt with hinted insertions.
+class ORBVocabulary {
+public:
+    explicit ORBVocabulary(int device = 0) : device_(device) {}
+    ~ORBVocabulary() { if (h_) plvs_voc_destroy(h_); }
+    ORBVocabulary(const ORBVocabulary&) = delete;
+    bool loadFromTextFile(const std::string& filename)
+    {
+        if (h_) { plvs_voc_destroy(h_); h_ = nullptr; }
+        return plvs_voc_load_text(filename.c_str(), device_, &h_) == PLVS_OK;
+    }
+    bool empty() const { return h_ == nullptr; }
+    unsigned int size() const { return (unsigned int)plvs_voc_size(h_); }
+    template <class BowVectorT, class FeatureVectorT>
+    void transform(const std::vector<cv::Mat>& features, BowVectorT& v, FeatureVectorT& fv, int levelsup)
+    {
+        v.clear(); fv.clear();
+        if (!h_) return;                                                        // empty(): "safe for subclasses" (TemplatedVocabulary.h:1147-1150)
+        const int n = (int)features.size();
+        desc_.resize((size_t)n * 32);
+        for (int i = 0; i < n; ++i) std::memcpy(&desc_[(size_t)i * 32], features[i].data, 32);
+        bowIds_.resize(n + 1); bowVals_.resize(n + 1); fvNodes_.resize(n + 1); fvOff_.resize(n + 2); fvFeat_.resize(n + 1);
+        int nb = 0, nn = 0;
+        plvs_shim::check(plvs_voc_transform(h_, desc_.data(), n, 0, levelsup, nullptr, nullptr, nullptr, bowIds_.data(), bowVals_.data(), &nb, fvNodes_.data(),
+                                            fvOff_.data(), fvFeat_.data(), &nn, nullptr), "plvs_voc_transform");
+        for (int i = 0; i < nb; ++i) v.insert(v.end(), typename BowVectorT::value_type(bowIds_[i], bowVals_[i]));
+        for (int i = 0; i < nn; ++i) {
+            auto it = fv.insert(fv.end(), typename FeatureVectorT::value_type(fvNodes_[i], typename FeatureVectorT::mapped_type()));
+            it->second.assign(fvFeat_.begin() + fvOff_[i], fvFeat_.begin() + fvOff_[i + 1]);
+        }
+    }
+private:
+    plvs_voc* h_ = nullptr; int device_ = 0;
+    std::vector<uint8_t> desc_; std::vector<uint32_t> bowIds_, fvNodes_; std::vector<double> bowVals_; std::vector<int32_t> fvOff_, fvFeat_;
+};
+
 }  // namespace PLVS2
 
 // ------------------------------------------------------------------------------------------------------

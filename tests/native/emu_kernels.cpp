@@ -12,6 +12,7 @@ namespace {
 #include "../../plvs_b200/csrc/orb_undistort.cuh"
 #include "../../plvs_b200/csrc/tsdf_hash.cuh"
 #include "../../plvs_b200/csrc/mesh_kernels.cuh"
+#include "../../plvs_b200/csrc/bow_kernels.cuh"
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
@@ -144,6 +145,25 @@ int emu_update_meshes(int nb, const int32_t* block_key, const float* sdf_pool, c
         emu::launch(dim3((unsigned)((nv + 255) / 256)), dim3(256), 0, [&] {
             k_mesh_shade(nv, tab.data(), mask, block_key, sdf_pool, w_pool, rgba_pool, M, verts, normals, colors); });
         return nm;
+    } catch (const std::exception& e) { std::fprintf(stderr, "emu: %s\n", e.what()); return -1; }
+}
+
+// plvs_voc_transform's kernels (bow.cu): k_bow_descend -> k_bow_rank -> k_bow_offsets over a vocabulary given in the sibling-contiguous layout
+int emu_bow_transform(const int32_t* child_off, const int32_t* child_id, const uint8_t* child_desc, const int32_t* word_id, const double* node_weight, int L,
+                      const uint8_t* desc, int n, int levelsup, uint32_t* word, double* weight, uint32_t* node, uint32_t* fv_nodes, int32_t* fv_offsets,
+                      int32_t* fv_features, int* n_fv_nodes)
+{
+    try {
+        *n_fv_nodes = 0; fv_offsets[0] = 0;
+        if (n == 0) return 0;
+        const VocDev V{child_off, child_id, child_desc, word_id, node_weight, L};
+        std::vector<uint32_t> sorted_node(n);
+        int cnt[4] = {0, 0, 0, 0};
+        emu::launch(dim3(div_up(n, 8)), dim3(256), 0, [&] { k_bow_descend(V, desc, n, levelsup, word, weight, node); });
+        emu::launch(dim3(div_up(n, 256)), dim3(256), 0, [&] { k_bow_rank(node, weight, n, fv_features, sorted_node.data(), &cnt[0]); });
+        emu::launch(dim3(1), dim3(1024), 0, [&] { k_bow_offsets(sorted_node.data(), &cnt[0], fv_nodes, fv_offsets, &cnt[1]); });
+        *n_fv_nodes = cnt[1];
+        return cnt[0];
     } catch (const std::exception& e) { std::fprintf(stderr, "emu: %s\n", e.what()); return -1; }
 }
 

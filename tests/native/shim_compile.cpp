@@ -91,6 +91,9 @@ extern "C" int shim_instantiate(int run)
     struct P2f { float x, y; };
     std::vector<P2f> prevMatched(F.mvKeysUn.size()); std::vector<int> m12;
     c += m.SearchForInitialization(F, L, prevMatched, m12, 100);
+    PLVS2::ORBVocabulary voc; voc.loadFromTextFile("ORBvoc.txt");
+    std::map<unsigned, double> bowVec; std::map<unsigned, std::vector<unsigned>> featVec; std::vector<cv::Mat> vDesc(1, cv::Mat(1, 32, CV_8U));
+    voc.transform(vDesc, bowVec, featVec, 4); c += (int)voc.size();
     chisel_server::ChiselServerParams p; chisel_server::ChiselServer cs(p);
     cs.SetDepthCameraInfo(500, 500, 320, 240, 640, 480);
     Eigen::Affine3f T; cs.SetDepthPose(T);

@@ -19,7 +19,7 @@ def build_emulated_kernels():
     out = HERE / "native" / "libemu_kernels.so"
     csrc = HERE.parent / "plvs_b200" / "csrc"
     deps = [src, HERE / "native" / "cuda_emu.hpp", HERE.parent / "include" / "plvs_b200.h"] + \
-        [csrc / n for n in ("match_common.cuh", "match_frustum.cuh", "match_init.cuh", "orb_undistort.cuh", "tsdf_hash.cuh", "mesh_kernels.cuh", "mc_tables.inc")]
+        [csrc / n for n in ("match_common.cuh", "match_frustum.cuh", "match_init.cuh", "orb_undistort.cuh", "tsdf_hash.cuh", "mesh_kernels.cuh", "mc_tables.inc", "bow_kernels.cuh")]
     if not out.exists() or any(out.stat().st_mtime < d.stat().st_mtime for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", str(src), "-o", str(out), "-lm"])
     return str(out)

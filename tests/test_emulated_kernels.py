@@ -149,3 +149,42 @@ def test_mesh_kernels(emu, color, res, far):
     assert np.array_equal(mk[:nm], ok) and np.array_equal(mc[:nm], oc)
     for a, b in ((V, oV), (N, oN), (Cc, oC)):
         assert np.array_equal(a[:len(oV)].view(np.uint32), b.view(np.uint32))
+
+
+def _sibling_layout(parent, desc):
+    """what plvs_voc_create builds on the host: children in id order, their descriptors contiguous"""
+    n = len(parent)
+    off = np.zeros(n + 1, np.int32)
+    for i in range(1, n):
+        off[parent[i] + 1] += 1
+    off = np.cumsum(off).astype(np.int32)
+    cur = off[:-1].copy()
+    cid = np.zeros(max(n - 1, 1), np.int32); cdesc = np.zeros((max(n - 1, 1), 32), np.uint8)
+    for i in range(1, n):
+        s = cur[parent[i]]; cur[parent[i]] += 1
+        cid[s] = i; cdesc[s] = desc[i]
+    return off, cid, cdesc
+
+
+@pytest.mark.parametrize("k,L,levelsup,zero", [(10, 3, 2, 0.0), (6, 4, 4, 0.3), (4, 5, 1, 0.1)])
+def test_bow_kernels(emu, frames, tmp_path, k, L, levelsup, zero):
+    """k_bow_descend / k_bow_rank / k_bow_offsets == the oracle (pinned to the compiled DBoW2): word, weight and node per feature, FeatureVector"""
+    from oracle import bow as OB
+    _, _, fr = frames
+    desc = np.ascontiguousarray(np.concatenate([fr[0].desc, fr[1].desc[:700]]))
+    path = tmp_path / "voc.txt"
+    OB.write_vocabulary(path, k, L, seed=7 * k + L, zero_weight_fraction=zero)
+    voc = OB.Vocabulary(path)
+    (kk, LL, _, _), parent, wid, ndesc, w = voc.export()
+    off, cid, cdesc = _sibling_layout(parent, ndesc)
+    n = len(desc)
+    word = np.zeros(n, np.uint32); weight = np.zeros(n, np.float64); node = np.zeros(n, np.uint32)
+    fvn = np.zeros(n, np.uint32); fvo = np.zeros(n + 1, np.int32); fvf = np.zeros(n, np.int32); nn = C.c_int()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    emu.emu_bow_transform.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.POINTER(C.c_int)]
+    kept = emu.emu_bow_transform(p(off), p(cid), p(cdesc), p(wid), p(w), LL, p(desc), n, levelsup, p(word), p(weight), p(node), p(fvn), p(fvo), p(fvf), C.byref(nn))
+    o = voc.transform(desc, levelsup)
+    assert kept == (o["weight"] > 0).sum() and nn.value == len(o["fv_nodes"]) >= 1 and (levelsup >= L or nn.value > 3)
+    assert np.array_equal(word, o["word"]) and np.array_equal(weight.view(np.uint64), o["weight"].view(np.uint64)) and np.array_equal(node, o["node"])
+    m = nn.value
+    assert np.array_equal(fvn[:m], o["fv_nodes"]) and np.array_equal(fvo[:m + 1], o["fv_offsets"]) and np.array_equal(fvf[:kept], o["fv_features"])

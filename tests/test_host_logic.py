@@ -120,3 +120,21 @@ def test_hamming_host_helper():
         assert lib.plvs_hamming256(a[i].ctypes.data_as(C.c_void_p), b[i].ctypes.data_as(C.c_void_p)) == int(np.unpackbits(a[i] ^ b[i]).sum())
     z = np.zeros(32, np.uint8); o = np.full(32, 255, np.uint8)
     assert lib.plvs_hamming256(z.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p)) == 256
+
+
+def test_bow_vector_host_step_matches_the_oracle(tmp_path):
+    """plvs_bow_vector (the host half of plvs_voc_transform: BowVector accumulation and normalisation in the reference's order) against the oracle's
+    BowVector, which is pinned to the compiled DBoW2 -- for every weighting and scoring type, with stopped words"""
+    from oracle import bow as OB, orb as O
+    from plvs_b200 import synth
+    from plvs_b200.bow import bow_vector
+    desc = O.extract_port(synth.gray_frame(3), 1500)[1]
+    for scoring in range(6):
+        for weighting in range(4):
+            path = tmp_path / ("v%d%d.txt" % (scoring, weighting))
+            OB.write_vocabulary(path, 6, 3, seed=scoring * 4 + weighting, scoring=scoring, weighting=weighting, zero_weight_fraction=0.2)
+            o = OB.Vocabulary(path).transform(desc, 2)
+            ids, vals = bow_vector(scoring, weighting, o["word"], o["weight"])
+            assert np.array_equal(ids, o["bow_ids"]) and np.array_equal(vals.view(np.uint64), o["bow_vals"].view(np.uint64)), (scoring, weighting)
+    ids, vals = bow_vector(0, 0, np.zeros(0, np.uint32), np.zeros(0, np.float64))
+    assert len(ids) == 0

@@ -167,3 +167,43 @@ def test_mesh_read_out(gpu):
     assert len(xyz) == nv and rgb.dtype == np.uint8 and rgb.max() > 50
     g.Reset()
     assert g.UpdateMesh() == (0, 0) and len(g.GetMeshes()[2]) == 0
+
+
+def test_bow_transform(gpu, tmp_path):
+    """§8f rank 4: ORBVocabulary::transform (Frame::ComputeBoW) on the device == the oracle (pinned to the compiled DBoW2): words, weights, nodes,
+    BowVector bit for bit, FeatureVector; then SearchByBoW fed with the device-resident FeatureVectors gives the same matches as with host ones"""
+    from oracle import bow as OB, match as OM
+    from plvs_b200.bow import ORBVocabulary
+    from plvs_b200 import scenario
+    from plvs_b200.matcher import ORBmatcher
+    K = synth.intrinsics(640, 480)
+    tab = O.Tables(2000)
+    fr = []
+    for f in (10, 11):
+        kp, desc, _, _ = O.extract_port(synth.gray_frame(f), 2000)
+        fr.append(scenario.make_frame(kp, desc, synth.depth_frame(f), K, tab.scale))
+    for k, L, levelsup, zero in ((10, 4, 2, 0.0), (10, 3, 1, 0.2), (6, 4, 4, 0.1)):
+        path = tmp_path / ("voc%d%d.txt" % (k, L))
+        OB.write_vocabulary(path, k, L, seed=k + L, zero_weight_fraction=zero)
+        ov = OB.Vocabulary(path)
+        gv = ORBVocabulary()
+        assert gv.loadFromTextFile(path) and gv.size() == ov.size() == k ** L
+        outs = []
+        for f in fr:
+            g, o = gv.transform(f.desc, levelsup), ov.transform(f.desc, levelsup)
+            for name in o:
+                a, b = g[name], o[name]
+                assert np.array_equal(a.view(np.uint64), b.view(np.uint64)) if a.dtype == np.float64 else np.array_equal(a, b), name
+            outs.append(o)
+    # the matcher consumes what the transform produced (node ids two levels above the leaves of the last vocabulary: root -> one node; use the first)
+    path = tmp_path / "voc_match.txt"
+    OB.write_vocabulary(path, 10, 3, seed=5)
+    gv = ORBVocabulary(); assert gv.loadFromTextFile(path)
+    ov = OB.Vocabulary(path)
+    fk, ff = (ov.transform(f.desc, 1) for f in fr)
+    fvK = (fk["fv_nodes"], fk["fv_offsets"], fk["fv_features"]); fvF = (ff["fv_nodes"], ff["fv_offsets"], ff["fv_features"])
+    has = np.ones(fr[0].n, np.uint8)
+    m = ORBmatcher(0.7, True)
+    n1, m1 = m.SearchByBoW(fr[0], fr[1], fvK, fvF, has)
+    n2, m2 = OM.search_by_bow(fr[0], fr[1], fvK, fvF, has, 0.7, True)
+    assert n1 == n2 and np.array_equal(m1, m2) and n1 > 50
