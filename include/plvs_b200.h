@@ -487,6 +487,10 @@ int plvs_tsdf_update_meshes(plvs_tsdf* h, int* n_meshes, long long* n_verts);
 int plvs_tsdf_get_meshes(plvs_tsdf* h, int32_t* keys, int32_t* counts, int cap_meshes, float* verts, float* normals, float* colors,
                          long long cap_verts, int on_device);
 
+/* ChiselServer::SaveMesh -> Chisel::SaveAllMeshesToPLY (Thirdparty/open_chisel/src/Chisel.cpp:79-118, src/io/PLY.cpp:29-86): the vertices (and colours,
+ * or NULL for a map without colour) that plvs_tsdf_get_meshes returned, as the reference's ASCII PLY.  Host I/O only. */
+int plvs_mesh_save_ply(const char* path, const float* verts, const float* colors, long long n_verts);
+
 /* read-out for tests/merge: chunk ids (x,y,z), per-voxel sdf / weight (4096 each, voxel index
  * (z*16+y)*16+x as Chunk.h:90-93) and rgba (r,g,b,colour-weight).  Any output may be NULL. */
 int plvs_tsdf_download_blocks(plvs_tsdf* h, int32_t* keys, float* sdf, float* weight, uint8_t* rgba,

@@ -21,6 +21,10 @@
 #include <open_chisel/pointcloud/PointCloud.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <csignal>
+#include <sys/wait.h>
+#include <unistd.h>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -208,6 +212,19 @@ int ref_tsdf_mesh_download(void* h, int32_t* keys, int32_t* counts, int cap_mesh
     }
     if (total_verts) *total_verts = nv;
     return nm;
+}
+
+// Chisel::SaveAllMeshesToPLY (src/Chisel.cpp:79-118).  SaveMeshPLYASCII (src/io/PLY.cpp:29-86) flows off its end without a return statement, which
+// g++ turns into a trap instruction: the file is complete by then (every line ends with std::endl), so the call runs in a forked child whose
+// death by SIGILL is expected.  Returns the child's wait status.
+int ref_tsdf_save_ply(void* h, const char* path)
+{
+    std::fflush(nullptr);
+    const pid_t pid = fork();
+    if (pid == 0) { signal(SIGILL, SIG_DFL); ((Ref*)h)->map->SaveAllMeshesToPLY(path); _exit(0); }
+    int status = 0;
+    waitpid(pid, &status, 0);
+    return status;
 }
 
 }  // extern "C"

@@ -142,3 +142,8 @@ class RefMap(Map):
     def extract_mesh(self):
         self.update_meshes(True)
         return self.meshes()
+
+    def save_ply(self, path):
+        """Chisel::SaveAllMeshesToPLY of the current meshes"""
+        RefMap._lib.ref_tsdf_save_ply.argtypes = [C.c_void_p, C.c_char_p]
+        RefMap._lib.ref_tsdf_save_ply(self._h, str(path).encode())

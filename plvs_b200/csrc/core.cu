@@ -1,5 +1,6 @@
 // Library-wide helpers: error string, version, device count, pinned host memory.
 #include <cstdarg>
+#include <fstream>
 #include "common.cuh"
 
 namespace plvs {
@@ -39,6 +40,36 @@ int plvs_host_free(void* p)
 {
     if (p && cudaFreeHost(p) != cudaSuccess) return PLVS_ENODEV;
     return PLVS_OK;
+}
+
+// Chisel::SaveAllMeshesToPLY + SaveMeshPLYASCII (Thirdparty/open_chisel/src/Chisel.cpp:79-118, src/io/PLY.cpp:29-86): one ASCII PLY of all mesh
+// vertices (default ostream float formatting, colours as static_cast<int>(c * 255.0f)), faces = consecutive vertex triples.  Host I/O only.
+int plvs_mesh_save_ply(const char* path, const float* verts, const float* colors, long long n_verts)
+{
+    if (!path || n_verts < 0 || (n_verts && !verts)) { plvs::set_error("bad argument"); return PLVS_EINVAL; }
+    std::ofstream stream(path);
+    if (!stream) { plvs::set_error("cannot open %s", path); return PLVS_EINVAL; }
+    stream << "ply" << std::endl;
+    stream << "format ascii 1.0" << std::endl;
+    stream << "element vertex " << (size_t)n_verts << std::endl;
+    stream << "property float x" << std::endl;
+    stream << "property float y" << std::endl;
+    stream << "property float z" << std::endl;
+    if (colors) {
+        stream << "property uchar red" << std::endl;
+        stream << "property uchar green" << std::endl;
+        stream << "property uchar blue" << std::endl;
+    }
+    stream << "element face " << (size_t)n_verts / 3 << std::endl;
+    stream << "property list uchar int vertex_index" << std::endl;
+    stream << "end_header" << std::endl;
+    for (long long i = 0; i < n_verts; ++i) {
+        stream << verts[3 * i] << " " << verts[3 * i + 1] << " " << verts[3 * i + 2];
+        if (colors) stream << " " << static_cast<int>(colors[3 * i] * 255.0f) << " " << static_cast<int>(colors[3 * i + 1] * 255.0f) << " " << static_cast<int>(colors[3 * i + 2] * 255.0f);
+        stream << std::endl;
+    }
+    for (long long i = 0; i + 2 < n_verts; i += 3) stream << "3 " << (size_t)i << " " << (size_t)(i + 1) << " " << (size_t)(i + 2) << " " << std::endl;
+    return stream ? PLVS_OK : PLVS_EINVAL;
 }
 
 }  // extern "C"

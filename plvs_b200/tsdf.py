@@ -125,6 +125,11 @@ class ChiselServer:
         _, _, V, N, Cc = self.GetMeshes()
         return V, (Cc * np.float32(255)).astype(np.uint8), N
 
+    def SaveMesh(self, filename):
+        """ChiselServer::SaveMesh -> Chisel::SaveAllMeshesToPLY: the meshes of the last UpdateMesh as the reference's ASCII PLY (chunks in key order)"""
+        _, _, V, _, Cc = self.GetMeshes()
+        return save_ply(filename, V, Cc if self.params.use_color else None)
+
     def download(self):
         """-> keys[n,3] (sorted lexicographically), sdf[n,4096], weight[n,4096], rgba[n,4096,4]"""
         n = C.c_int()
@@ -139,3 +144,12 @@ class ChiselServer:
                        "plvs_tsdf_download_blocks")
         order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))
         return keys[order], sdf[order], w[order], rgba[order]
+
+
+def save_ply(filename, verts, colors=None):
+    """SaveMeshPLYASCII (Thirdparty/open_chisel/src/io/PLY.cpp:29-86) for concatenated mesh vertices; host I/O through the C ABI"""
+    V = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+    Cc = None if colors is None else np.ascontiguousarray(colors, np.float32).reshape(-1, 3)
+    rc = _lib.load().plvs_mesh_save_ply(str(filename).encode(), V.ctypes.data_as(C.c_void_p), Cc.ctypes.data_as(C.c_void_p) if Cc is not None else None, len(V))
+    _lib.check(rc, "plvs_mesh_save_ply")
+    return True

@@ -764,6 +764,14 @@ public:
             output_cloud.push_back(point);
         }
     }
+    // ChiselServer::SaveMesh (ChiselServer.cpp) -> Chisel::SaveAllMeshesToPLY: the meshes of the last UpdateMesh, chunks in key order
+    bool SaveMesh(const std::string& filename)
+    {
+        const size_t n = (size_t)std::max<long long>(nMeshVerts_, 0);
+        meshV_.resize(3 * n); meshC_.resize(3 * n);
+        if (n) plvs_shim::check(plvs_tsdf_get_meshes(h_, nullptr, nullptr, 0, meshV_.data(), nullptr, meshC_.data(), nMeshVerts_, 0), "plvs_tsdf_get_meshes");
+        return plvs_mesh_save_ply(filename.c_str(), meshV_.data(), useColor ? meshC_.data() : nullptr, nMeshVerts_) == PLVS_OK;
+    }
     void Reset() { plvs_shim::check(plvs_tsdf_reset(h_), "plvs_tsdf_reset"); }
     void SetDepthCameraInfo(const double fx, const double fy, const double cx, const double cy, const int width, const int height)
     {

@@ -98,3 +98,28 @@ def test_mesh_with_coarse_voxels_takes_the_trilinear_colour_branch():
     v0 = np.floor(V / np.float32(0.5)).astype(int)
     live = sum(all(tuple(np.floor((v + np.array(dv)) / 8.0).astype(int)) in blocks for dv in np.ndindex(2, 2, 2)) for v in v0)
     assert len(V) > 100 and live > 20
+
+
+def _ply_parts(path):
+    lines = open(path).read().split("\n")
+    e = lines.index("end_header")
+    nv = int([l for l in lines[:e] if l.startswith("element vertex")][0].split()[-1])
+    return lines[:e + 1], lines[e + 1:e + 1 + nv], lines[e + 1 + nv:]
+
+
+@pytest.mark.parametrize("color", [0, 1])
+def test_ply_writer_against_the_reference_file(tmp_path, color):
+    """plvs_mesh_save_ply (host I/O behind the C ABI) fed with the oracle's meshes == Chisel::SaveAllMeshesToPLY of the compiled reference: same header,
+    same face list, the same vertex lines per chunk (the reference walks an unordered_map, so chunks come in another order: compared as sorted triangles)"""
+    o, r = _pair(160, 120, voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=8192, use_color=color)
+    for f in (0, 1):
+        d = synth.depth_frame(f, 160, 120); c = synth.bgr_frame(f, 160, 120) if color else None
+        o.integrate(d, synth.pose(f), c); r.integrate(d, synth.pose(f), c)
+    r.update_meshes()
+    r.save_ply(tmp_path / "ref.ply")
+    _, _, V, _, Cc = o.extract_mesh()
+    T.save_ply(tmp_path / "own.ply", V, Cc if color else None)
+    rh, rv, rf = _ply_parts(tmp_path / "ref.ply"); oh, ov, of = _ply_parts(tmp_path / "own.ply")
+    assert oh == rh and of == rf and len(ov) == len(V) > 3000
+    tri = lambda v: sorted(tuple(v[i:i + 3]) for i in range(0, len(v), 3))
+    assert tri(ov) == tri(rv)
