@@ -216,12 +216,12 @@ int ref_tsdf_mesh_download(void* h, int32_t* keys, int32_t* counts, int cap_mesh
 
 // Chisel::SaveAllMeshesToPLY (src/Chisel.cpp:79-118).  SaveMeshPLYASCII (src/io/PLY.cpp:29-86) flows off its end without a return statement, which
 // g++ turns into a trap instruction: the file is complete by then (every line ends with std::endl), so the call runs in a forked child whose
-// death by SIGILL is expected.  Returns the child's wait status.
+// death by a signal is expected.  Returns the child's wait status.
 int ref_tsdf_save_ply(void* h, const char* path)
 {
     std::fflush(nullptr);
     const pid_t pid = fork();
-    if (pid == 0) { signal(SIGILL, SIG_DFL); ((Ref*)h)->map->SaveAllMeshesToPLY(path); _exit(0); }
+    if (pid == 0) { for (int sg : {SIGILL, SIGABRT, SIGSEGV, SIGBUS, SIGFPE}) signal(sg, SIG_DFL); ((Ref*)h)->map->SaveAllMeshesToPLY(path); _exit(0); }
     int status = 0;
     waitpid(pid, &status, 0);
     return status;
