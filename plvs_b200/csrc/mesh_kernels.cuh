@@ -8,11 +8,11 @@
 // InterpolateColor (:715-806), ComputeNormalsFromGradients (:838-856).  The reference appends triangles voxel by voxel in a fixed order
 // (inside voxels z,y,x; then the max-X, max-Y, max-Z planes, whose cubes reach into the +x/+y/+z neighbour blocks): `rank` below is
 // a voxel's position in that order, so counting per voxel + a prefix sum reproduces the vertex order exactly.
-//   k_mesh_count : CTA per block, thread = 16 consecutive ranks -> triangles per block
+//   k_mesh_count : CTA per block (17^3 corner lattice staged in shared memory), thread = 16 consecutive ranks -> triangles per block
 //   k_mesh_emit  : same walk, in-block prefix sum, writes positions + face normals at the block's base offset
 //   k_mesh_shade : thread per vertex -> colour (InterpolateColor as written, including its look-ups by voxel index) and the
 //                  normal from the SDF gradient (kept in double where the reference is)
-// HBM-bound: 8 B per voxel read (through L1/L2 for the 8-corner reuse) + 36 B per vertex written.
+// HBM-bound: 8 B per voxel read (coalesced rows into shared memory; the 8-corner reuse is on chip) + 36 B per vertex written.
 // ---------------------------------------------------------------------------------------------
 __device__ const uint64_t d_tri_table[256] = {
 #include "mc_tables.inc"
@@ -29,23 +29,39 @@ __device__ __forceinline__ void mesh_rank_to_voxel(int r, int& x, int& y, int& z
     else { r -= 3840; z = 15; x = r % 16; y = r / 16; }
 }
 
-// corner SDFs of the cube at voxel (ix,iy,iz) of block b; returns the configuration, 0 when a corner is unobserved / its block is missing.
-// nb[k]: pool index of the neighbour block at offset (k&1, k>>1&1, k>>2&1), -1 if absent; nb[0] = b.
-__device__ __forceinline__ int mesh_cube(const float* __restrict__ sdf_pool, const float* __restrict__ w_pool, const int* nb, int ix, int iy, int iz, float* sdf)
+// The 17^3 corner lattice of a block -- its own 16^3 voxels plus the first layer of the +x/+y/+z neighbours -- staged in shared memory: the block's
+// own voxels arrive as coalesced rows, every cube then reads its 8 corners on chip.  s_ok = 0 marks a corner that is unobserved (weight <= 1e-15,
+// ChunkManager.cpp:336,366) or whose block does not exist; nb[k] = pool index of the neighbour at offset (k&1, k>>1&1, k>>2&1), -1 if absent.
+constexpr int kLat = 17, kLatN = kLat * kLat * kLat;
+
+__device__ __forceinline__ void mesh_stage_lattice(const float* __restrict__ sdf_pool, const float* __restrict__ w_pool, const int* nb, float* s_sdf, uint8_t* s_ok)
+{
+    for (int i = threadIdx.x; i < kLatN; i += blockDim.x) {
+        int x = i % kLat, y = (i / kLat) % kLat, z = i / (kLat * kLat), k = 0;
+        if (x == 16) { k |= 1; x = 0; }
+        if (y == 16) { k |= 2; y = 0; }
+        if (z == 16) { k |= 4; z = 0; }
+        const int blk = nb[k];
+        float s = 0.f; uint8_t ok = 0;
+        if (blk >= 0) {
+            const size_t id = (size_t)blk * kBlockVox + ((z * 16 + y) * 16 + x);
+            ok = !((double)w_pool[id] <= 1e-15);
+            s = sdf_pool[id];
+        }
+        s_sdf[i] = s; s_ok[i] = ok;
+    }
+}
+
+// corner SDFs of the cube at voxel (ix,iy,iz); returns the configuration, 0 when a corner is unobserved / its block is missing
+__device__ __forceinline__ int mesh_cube(const float* s_sdf, const uint8_t* s_ok, int ix, int iy, int iz, float* sdf)
 {
     int cfg = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int ox = (i == 1 || i == 2 || i == 5 || i == 6), oy = (i == 2 || i == 3 || i == 6 || i == 7), oz = i >> 2;     // cubeIndexOffsets (:84-86)
-        int x = ix + ox, y = iy + oy, z = iz + oz, k = 0;
-        if (x >= 16) { k |= 1; x = 0; }
-        if (y >= 16) { k |= 2; y = 0; }
-        if (z >= 16) { k |= 4; z = 0; }
-        const int blk = nb[k];
-        if (blk < 0) return 0;
-        const size_t id = (size_t)blk * kBlockVox + ((z * 16 + y) * 16 + x);
-        if ((double)w_pool[id] <= 1e-15) return 0;
-        const float s = sdf_pool[id];
+        const int id = ((iz + oz) * kLat + (iy + oy)) * kLat + (ix + ox);
+        if (!s_ok[id]) return 0;
+        const float s = s_sdf[id];
         sdf[i] = s;
         if (s < 0) cfg |= 1 << i;
     }
@@ -58,17 +74,21 @@ k_mesh_count(const int* __restrict__ list, const int* __restrict__ block_key, co
 {
     __shared__ int s_nb[8];
     __shared__ int s_sum[8];
+    __shared__ float s_sdf[kLatN];
+    __shared__ uint8_t s_ok[kLatN];
     const int b = list[blockIdx.x];
     if (threadIdx.x < 8) {
         const int k = threadIdx.x;
         s_nb[k] = k == 0 ? b : hash_find(tab, mask, block_key[3 * b] + (k & 1), block_key[3 * b + 1] + ((k >> 1) & 1), block_key[3 * b + 2] + (k >> 2));
     }
     __syncthreads();
+    mesh_stage_lattice(sdf_pool, w_pool, s_nb, s_sdf, s_ok);
+    __syncthreads();
     int n = 0;
     for (int j = 0; j < 16; ++j) {
         int x, y, z; float sdf[8];
         mesh_rank_to_voxel(threadIdx.x * 16 + j, x, y, z);
-        const int cfg = mesh_cube(sdf_pool, w_pool, s_nb, x, y, z, sdf);
+        const int cfg = mesh_cube(s_sdf, s_ok, x, y, z, sdf);
         n += (int)(d_tri_table[cfg] >> 60);
     }
 #pragma unroll
@@ -85,18 +105,22 @@ k_mesh_emit(const int* __restrict__ list, const int* __restrict__ block_key, con
 {
     __shared__ int s_nb[8];
     __shared__ int s_warp[8];
+    __shared__ float s_sdf[kLatN];
+    __shared__ uint8_t s_ok[kLatN];
     const int b = list[blockIdx.x];
     if (threadIdx.x < 8) {
         const int k = threadIdx.x;
         s_nb[k] = k == 0 ? b : hash_find(tab, mask, block_key[3 * b] + (k & 1), block_key[3 * b + 1] + ((k >> 1) & 1), block_key[3 * b + 2] + (k >> 2));
     }
     __syncthreads();
+    mesh_stage_lattice(sdf_pool, w_pool, s_nb, s_sdf, s_ok);
+    __syncthreads();
     // pass 1: triangles of this thread's 16 voxels, exclusive prefix over the CTA (thread order == rank order)
     int n = 0;
     for (int j = 0; j < 16; ++j) {
         int x, y, z; float sdf[8];
         mesh_rank_to_voxel(threadIdx.x * 16 + j, x, y, z);
-        n += (int)(d_tri_table[mesh_cube(sdf_pool, w_pool, s_nb, x, y, z, sdf)] >> 60);
+        n += (int)(d_tri_table[mesh_cube(s_sdf, s_ok, x, y, z, sdf)] >> 60);
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int incl = n;
@@ -113,7 +137,7 @@ k_mesh_emit(const int* __restrict__ list, const int* __restrict__ block_key, con
     for (int j = 0; j < 16; ++j) {
         int x, y, z; float sdf[8];
         mesh_rank_to_voxel(threadIdx.x * 16 + j, x, y, z);
-        const int cfg = mesh_cube(sdf_pool, w_pool, s_nb, x, y, z, sdf);
+        const int cfg = mesh_cube(s_sdf, s_ok, x, y, z, sdf);
         const uint64_t row = d_tri_table[cfg];
         const int ntri = (int)(row >> 60);
         if (ntri == 0) continue;
