@@ -61,8 +61,8 @@ int plvs_voc_create(int device, int k, int L, int scoring, int weighting, int n_
     h->device = device; h->k = k; h->L = L; h->scoring = scoring; h->weighting = weighting; h->n_nodes = n_nodes; h->n_words = words;
     auto fail = [&](int rc) { delete h; return rc; };
     if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return fail(PLVS_ENODEV); }
+    if (create_handle_stream(&h->stream, 1) != cudaSuccess) { set_error("stream creation failed"); return fail(PLVS_ENODEV); }
     int rc;
-    if ((rc = create_handle_stream(&h->stream, 1))) return fail(rc);
     if ((rc = h->d_child_off.alloc(n_nodes + 1)) || (rc = h->d_child_id.alloc(id.size())) || (rc = h->d_child_desc.alloc(cdesc.size())) ||
         (rc = h->d_word_id.alloc(n_nodes)) || (rc = h->d_weight.alloc(n_nodes)) || (rc = h->d_cnt.alloc(4)) || (rc = h->p_cnt.alloc(4))) return fail(rc);
     if (cudaMemcpy(h->d_child_off.p, off.data(), (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice) != cudaSuccess ||

@@ -23,3 +23,48 @@ def build_emulated_kernels():
     if not out.exists() or any(out.stat().st_mtime < d.stat().st_mtime for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", str(src), "-o", str(out), "-lm"])
     return str(out)
+
+
+def build_emulated_library(units=("core.cu", "bow.cu")):
+    """Whole translation units of the product on the CPU: `kernel<<<grid, block, smem, stream>>>(args);` is rewritten to emu::launch, the CUDA runtime
+    calls resolve to tests/native/fake_cuda/cuda_runtime.h (host memory), device code runs on cuda_emu.hpp.  Only units without inline PTX qualify.
+    -> tests/native/libemu_units.so exporting the same C ABI as the real library for those units."""
+    import re
+    csrc = HERE.parent / "plvs_b200" / "csrc"
+    gen = HERE / "native" / "_gen"
+    out = HERE / "native" / "libemu_units.so"
+    deps = [csrc / u for u in units] + [csrc / "common.cuh", csrc / "bow_kernels.cuh", HERE / "native" / "cuda_emu.hpp", HERE / "native" / "fake_cuda" / "cuda_runtime.h",
+                                        HERE.parent / "include" / "plvs_b200.h", pathlib.Path(__file__)]
+    if out.exists() and all(out.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return str(out)
+    gen.mkdir(parents=True, exist_ok=True)
+    launch = re.compile(r"(\b[A-Za-z_][\w:]*(?:<[^<>;]*>)?)\s*<<<(.*?)>>>\s*\(", re.S)
+    srcs = []
+    for u in units:
+        text = (csrc / u).read_text()
+        res, pos = [], 0
+        for m in launch.finditer(text):
+            cfg, depth0, cur = [], 0, ""
+            for ch in m.group(2):             # split the launch configuration at its top-level commas
+                if ch == "," and depth0 == 0:
+                    cfg.append(cur.strip()); cur = ""
+                else:
+                    depth0 += {"(": 1, ")": -1}.get(ch, 0); cur += ch
+            cfg.append(cur.strip())
+            assert len(cfg) >= 2, (u, m.group(0))
+            depth, j = 1, m.end()
+            while depth:                      # the matching parenthesis of the argument list
+                depth += {"(": 1, ")": -1}.get(text[j], 0); j += 1
+            args = text[m.end():j - 1]
+            assert text[j:].lstrip().startswith(";"), (u, text[m.start():j + 20])
+            grid, block, smem = cfg[0], cfg[1], cfg[2] if len(cfg) > 2 else "0"
+            res.append(text[pos:m.start()] + "emu::launch(dim3(%s), dim3(%s), (size_t)(%s), [&] { %s(%s); })" % (grid, block, smem, m.group(1), args))
+            pos = j
+        res.append(text[pos:])
+        body = "".join(res).replace('#include "', '#include "%s/' % csrc)
+        dst = gen / (u.replace(".cu", "_emu.cpp"))
+        dst.write_text('#include "%s"\n' % (HERE / "native" / "cuda_emu.hpp") + body)
+        srcs.append(str(dst))
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", "-I", str(HERE / "native" / "fake_cuda")] + srcs +
+                          ["-o", str(out), "-lm", "-pthread"])
+    return str(out)

@@ -188,3 +188,62 @@ def test_bow_kernels(emu, frames, tmp_path, k, L, levelsup, zero):
     assert np.array_equal(word, o["word"]) and np.array_equal(weight.view(np.uint64), o["weight"].view(np.uint64)) and np.array_equal(node, o["node"])
     m = nn.value
     assert np.array_equal(fvn[:m], o["fv_nodes"]) and np.array_equal(fvo[:m + 1], o["fv_offsets"]) and np.array_equal(fvf[:kept], o["fv_features"])
+
+
+def test_bow_entry_points_whole_unit(tmp_path, frames):
+    """plvs_b200/csrc/bow.cu as a whole -- text loader, tree flattening, kernel sequence, read-back, BowVector -- built for the CPU (launches rewritten to
+    emu::launch, CUDA runtime calls on host memory: tests/native_build.py) and driven through its own C ABI: plvs_voc_load_text + plvs_voc_transform ==
+    the oracle, for a vocabulary file with and without a trailing newline; plvs_voc_create from flat arrays gives the same handle behaviour"""
+    from oracle import bow as OB
+    from tests.native_build import build_emulated_library
+    lib = C.CDLL(build_emulated_library())
+    _, _, fr = frames
+    desc = np.ascontiguousarray(fr[0].desc)
+    n = len(desc)
+    lib.plvs_voc_load_text.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+    lib.plvs_voc_destroy.argtypes = [C.c_void_p]; lib.plvs_voc_destroy.restype = None
+    lib.plvs_voc_size.argtypes = [C.c_void_p]
+    lib.plvs_voc_create.argtypes = [C.c_int] * 6 + [C.c_void_p] * 5
+    lib.plvs_voc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(C.c_int)] + [C.c_void_p] * 3 + [C.POINTER(C.c_int), C.c_void_p]
+    lib.plvs_last_error.restype = C.c_char_p
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def run(h, levelsup):
+        word = np.zeros(n, np.uint32); weight = np.zeros(n, np.float64); node = np.zeros(n, np.uint32)
+        bi = np.zeros(n, np.uint32); bv = np.zeros(n, np.float64); nb = C.c_int()
+        fvn = np.zeros(n, np.uint32); off = np.zeros(n + 1, np.int32); feat = np.zeros(n, np.int32); nn = C.c_int()
+        rc = lib.plvs_voc_transform(h, p(desc), n, 0, levelsup, p(word), p(weight), p(node), p(bi), p(bv), C.byref(nb), p(fvn), p(off), p(feat), C.byref(nn), None)
+        assert rc == 0, lib.plvs_last_error()
+        k = nn.value
+        return dict(word=word, weight=weight, node=node, bow_ids=bi[:nb.value], bow_vals=bv[:nb.value], fv_nodes=fvn[:k], fv_offsets=off[:k + 1], fv_features=feat[:off[k]])
+
+    def same(a, b):
+        for name in b:
+            x, y = a[name], b[name]
+            assert np.array_equal(x.view(np.uint64), y.view(np.uint64)) if x.dtype == np.float64 else np.array_equal(x, y), name
+
+    for k, L, levelsup, zero, scoring, weighting in ((10, 3, 2, 0.2, 0, 0), (5, 4, 4, 0.0, 1, 1), (7, 3, 1, 0.1, 5, 3)):
+        path = tmp_path / ("voc%d.txt" % k)
+        OB.write_vocabulary(path, k, L, seed=k, scoring=scoring, weighting=weighting, zero_weight_fraction=zero)
+        ov = OB.Vocabulary(path)
+        want = ov.transform(desc, levelsup)
+        h = C.c_void_p()
+        assert lib.plvs_voc_load_text(str(path).encode(), 0, C.byref(h)) == 0, lib.plvs_last_error()
+        assert lib.plvs_voc_size(h) == ov.size() == k ** L
+        same(run(h, levelsup), want)
+        lib.plvs_voc_destroy(h)
+        with open(path, "a") as f:
+            f.write("\n")                                  # the file as saveToTextFile leaves it: the trailing empty line is ignored
+        h = C.c_void_p()
+        assert lib.plvs_voc_load_text(str(path).encode(), 0, C.byref(h)) == 0
+        same(run(h, levelsup), want)
+        lib.plvs_voc_destroy(h)
+        (kk, LL, sc, wt), parent, wid, ndesc, w = ov.export()
+        h = C.c_void_p()
+        assert lib.plvs_voc_create(0, kk, LL, sc, wt, len(parent), p(parent), p(wid), p(ndesc), p(w), C.byref(h)) == 0, lib.plvs_last_error()
+        same(run(h, levelsup), want)
+        lib.plvs_voc_destroy(h)
+    h = C.c_void_p()
+    assert lib.plvs_voc_load_text(str(tmp_path / "missing.txt").encode(), 0, C.byref(h)) != 0
+    bad = tmp_path / "bad.txt"; bad.write_text("hello world\n")
+    assert lib.plvs_voc_load_text(str(bad).encode(), 0, C.byref(h)) != 0
