@@ -1,7 +1,12 @@
 """-m gpu: features written after the round's GPU budget was spent.  The kernels compile for sm_100a, their oracles are pinned on the CPU, and
 their source text runs oracle-identical on the CPU execution model of tests/native/cuda_emu.hpp (tests/test_emulated_kernels.py) -- but these
 comparisons have not run on a GPU yet, hence the non-strict xfail (a pass shows as XPASS, a failure does not fail the suite) and the file
-name that sorts behind every other GPU test."""
+name that sorts behind every other GPU test.  Each body runs in a child interpreter with a time limit: a kernel that hangs or host code that
+crashes ends that child (and is reported as this test's failure), not the test session."""
+import os
+import pathlib
+import subprocess
+import sys
 import cv2
 import numpy as np
 import pytest
@@ -13,7 +18,7 @@ from oracle import orb as O
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first GPU run still pending", strict=False)]
 
 
-def test_undistort_keypoints_on_device(gpu):
+def _impl_undistort_keypoints_on_device():
     """Frame::UndistortKeyPoints (§8f rank 2): device == oracle == the real cv2.undistortPoints, bit for bit, TUM1 / EuRoC / rational models"""
     ex = ORBextractor(2000, 1.2, 8, 20, 7)
     mono, kp, desc = ex(synth.gray_frame(3))
@@ -34,7 +39,7 @@ def test_undistort_keypoints_on_device(gpu):
     assert np.array_equal(un, kp)
 
 
-def test_search_local_points_resident(gpu):
+def _impl_search_local_points_resident():
     """Tracking::SearchLocalPoints without a host round trip: plvs_match_in_frustum leaves the in-view queries on the device (compacted in order)
     and plvs_match_projection_map_resident searches with them; result == oracle isInFrustum -> host compaction -> oracle SearchByProjection"""
     from plvs_b200 import scenario
@@ -77,7 +82,7 @@ def test_search_local_points_resident(gpu):
     assert nm2 == onm and np.array_equal(assign2, oassign)
 
 
-def test_tsdf_from_raw_u16_depth(gpu):
+def _impl_tsdf_from_raw_u16_depth():
     """§8f rank 2: `mImDepth.convertTo(CV_32F, mDepthMapFactor)` (src/Tracking.cc:1812-1813) on the device: the map built from the raw 16-bit
     image (TUM factor 5000, row padding) is the map built from the host-converted float image, bit for bit, with and without colour"""
     from plvs_b200 import tsdf as T
@@ -102,7 +107,7 @@ def test_tsdf_from_raw_u16_depth(gpu):
         assert np.array_equal(sa.view(np.uint32), sb.view(np.uint32)) and np.array_equal(wa.view(np.uint32), wb.view(np.uint32)) and np.array_equal(ca, cb)
 
 
-def test_search_for_initialization(gpu):
+def _impl_search_for_initialization():
     """ORBmatcher::SearchForInitialization (§8f rank 1, the last overload): device == oracle (itself pinned to the reference's compiled function) for
     the matches, the count and the updated vbPrevMatched, two calls in a row as Tracking::MonocularInitialization makes them; the mono
     initialisation extractor asks for 5x the features, so ~2000 level-0 keypoints compete"""
@@ -131,7 +136,7 @@ def test_search_for_initialization(gpu):
     assert n == 0 and (a == -1).all() and np.array_equal(p, prev)
 
 
-def test_mesh_read_out(gpu):
+def _impl_mesh_read_out():
     """§8f rank 3: ChunkManager::RecomputeMesh for every chunk on the device (marching cubes in the reference's vertex order, colours through
     InterpolateColor as written, gradient normals) == the oracle, which is pinned bit-exactly to the compiled open_chisel
     (tests/test_oracle_vs_reference_mesh.py).  The voxel arrays of the two maps are identical in these sequences, so the meshes must be too."""
@@ -169,7 +174,7 @@ def test_mesh_read_out(gpu):
     assert g.UpdateMesh() == (0, 0) and len(g.GetMeshes()[2]) == 0
 
 
-def test_bow_transform(gpu, tmp_path):
+def _impl_bow_transform(tmp_path):
     """§8f rank 4: ORBVocabulary::transform (Frame::ComputeBoW) on the device == the oracle (pinned to the compiled DBoW2): words, weights, nodes,
     BowVector bit for bit, FeatureVector; then SearchByBoW fed with the device-resident FeatureVectors gives the same matches as with host ones"""
     from oracle import bow as OB, match as OM
@@ -207,3 +212,43 @@ def test_bow_transform(gpu, tmp_path):
     n1, m1 = m.SearchByBoW(fr[0], fr[1], fvK, fvF, has)
     n2, m2 = OM.search_by_bow(fr[0], fr[1], fvK, fvF, has, 0.7, True)
     assert n1 == n2 and np.array_equal(m1, m2) and n1 > 50
+
+
+# ---- the tests proper: one isolated child per body -----------------------------------------------------------------------------------
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+CHILD_TIMEOUT_S = 240
+
+
+def _isolated(name, *args):
+    code = "import sys; sys.path.insert(0, %r); import pathlib; from tests import test_zz_gpu_unverified as t; t.%s(%s)" % (
+        str(ROOT), name, ", ".join("pathlib.Path(%r)" % str(a) for a in args))
+    try:
+        r = subprocess.run([sys.executable, "-c", code], cwd=str(ROOT), capture_output=True, text=True, timeout=CHILD_TIMEOUT_S,
+                           env=dict(os.environ, PYTHONFAULTHANDLER="1"))
+    except subprocess.TimeoutExpired:
+        pytest.fail("%s did not finish within %d s (child killed)" % (name, CHILD_TIMEOUT_S))
+    assert r.returncode == 0, "%s: exit %d\n%s\n%s" % (name, r.returncode, r.stdout[-2000:], r.stderr[-4000:])
+
+
+def test_undistort_keypoints_on_device(gpu):
+    _isolated("_impl_undistort_keypoints_on_device")
+
+
+def test_search_local_points_resident(gpu):
+    _isolated("_impl_search_local_points_resident")
+
+
+def test_tsdf_from_raw_u16_depth(gpu):
+    _isolated("_impl_tsdf_from_raw_u16_depth")
+
+
+def test_search_for_initialization(gpu):
+    _isolated("_impl_search_for_initialization")
+
+
+def test_mesh_read_out(gpu):
+    _isolated("_impl_mesh_read_out")
+
+
+def test_bow_transform(gpu, tmp_path):
+    _isolated("_impl_bow_transform", tmp_path)
