@@ -79,7 +79,12 @@ def load():
     if not LIB_PATH.exists():
         raise PlvsError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(the product has no CPU fallback)")
-    lib = C.CDLL(str(LIB_PATH))
+    _lib = declare(C.CDLL(str(LIB_PATH)))
+    return _lib
+
+
+def declare(lib):
+    """argument / result types of the C ABI (include/plvs_b200.h) on a loaded library object"""
     lib.plvs_version.restype = C.c_char_p
     lib.plvs_last_error.restype = C.c_char_p
     lib.plvs_orb_destroy.restype = None
@@ -148,7 +153,6 @@ def load():
         if hasattr(lib, name):
             getattr(lib, name).restype = None
             getattr(lib, name).argtypes = [C.c_void_p]
-    _lib = lib
     return lib
 
 

@@ -22,6 +22,11 @@ void set_error(const char* fmt, ...);
         }                                                                                     \
     } while (0)
 
+// dynamic shared memory of a kernel (the CPU execution model of tests/native/cuda_emu.hpp defines its own before this header is seen)
+#ifndef PLVS_DYN_SMEM
+#define PLVS_DYN_SMEM(T, name) extern __shared__ T name[]
+#endif
+
 #ifdef __CUDACC__
 // 1-D bulk asynchronous copies (the TMA engine; SASS UBLKCP) completed through an mbarrier.  Addresses and sizes must be
 // multiples of 16 bytes.

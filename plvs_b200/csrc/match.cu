@@ -171,6 +171,10 @@ k_fuse(ViewDev K, FuseSigma sg, const int* __restrict__ cell_start, const int* _
 // ---------------------------------------------------------------------------------------------
 constexpr int kResolveCtas = 8;
 
+#ifdef PLVS_CUDA_EMU        // tests/native/cuda_emu.hpp: the CTAs of the cluster are resident together on the CPU model
+__device__ __forceinline__ uint32_t cluster_cta_rank() { return emu::cluster_rank(); }
+__device__ __forceinline__ void cluster_sync_all() { emu::cluster_barrier(); }
+#else
 __device__ __forceinline__ uint32_t cluster_cta_rank()
 {
     uint32_t r;
@@ -181,6 +185,7 @@ __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n" "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
+#endif
 
 // SMEM == true: the candidate lists of the range are cached in shared memory (row stride cap|1: conflict-free column
 // walks); SMEM == false reads them from L2 (any size).
@@ -195,7 +200,7 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
     int tr_n = 0;
     auto stamp = [&]() { if (trace && threadIdx.x == 0 && tr_n < 32) trace[cluster_cta_rank() * 32 + tr_n++] = clock64(); };
     stamp();
-    extern __shared__ uint32_t s_dyn[];
+    PLVS_DYN_SMEM(uint32_t, s_dyn);
     __shared__ int s_count, s_hist[HISTO], s_keep[HISTO];
     const int tid = threadIdx.x;
     const int crank = (int)cluster_cta_rank();
@@ -540,7 +545,7 @@ k_bow(ViewDev K, ViewDev F, FvDev fK, FvDev fF, const uint8_t* __restrict__ has_
 __global__ void __launch_bounds__(32)
 k_distinctive(const uint8_t* __restrict__ desc, const int32_t* __restrict__ off, int32_t* __restrict__ best)
 {
-    extern __shared__ uint16_t s_d[];
+    PLVS_DYN_SMEM(uint16_t, s_d);
     const int pt = blockIdx.x, lane = threadIdx.x;
     const int o = off[pt], n = off[pt + 1] - o;
     if (n <= 0) { if (lane == 0) best[pt] = -1; return; }

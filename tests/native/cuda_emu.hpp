@@ -7,7 +7,8 @@
 // are rendezvous points: a fiber that reaches one yields until every live thread of the CTA (or every live lane named by the mask) has
 // arrived.  A rendezvous that can never complete (divergent barrier, a shuffle some lane skips) is reported as a deadlock instead of
 // hanging.  Floating point: x86-64 SSE arithmetic is IEEE like the device's with --fmad=false; compile with -ffp-contract=off.
-// Not modelled: clusters, TMA / mbarrier, tensor cores, memory ordering weaker than sequential consistency, scheduling races.
+// Clusters: the CTAs of one cluster are resident together (launch_cluster) and meet at emu::cluster_barrier.
+// Not modelled: distributed shared memory, TMA / mbarrier, tensor cores, memory ordering weaker than sequential consistency, scheduling races.
 #pragma once
 #define PLVS_CUDA_EMU 1
 #include <ucontext.h>
@@ -42,7 +43,9 @@ struct Fiber {
     ucontext_t ctx;
     std::unique_ptr<char[]> stack;
     dim3 tid;
-    int linear = 0;
+    dim3 bid;
+    int linear = 0;                // thread index inside its CTA
+    int cta = 0;                   // CTA index inside the resident group (0 unless a cluster is being run)
     bool done = false;
 };
 
@@ -53,9 +56,14 @@ struct State {
     std::vector<Warp> warps;
     Fiber* cur = nullptr;
     ucontext_t sched;
-    dim3 bid, bdim, gdim;
-    int alive = 0, bar_arrived = 0;
-    unsigned bar_gen = 0;
+    dim3 bdim, gdim;
+    int alive = 0;                                  // live fibers of the resident group
+    std::vector<int> cta_alive, bar_arrived;        // per resident CTA
+    std::vector<unsigned> bar_gen;
+    int cluster = 1, cl_arrived = 0;                // CTAs resident together; cluster barrier state
+    unsigned cl_gen = 0;
+    int warps_per_cta = 0;
+    size_t dyn_stride = 0;
     long idle = 0;                 // consecutive yields without progress: deadlock detector
     std::function<void()>* body = nullptr;
     std::vector<char> dyn;
@@ -77,36 +85,45 @@ inline void trampoline()
     (*g.body)();
     Fiber* f = g.cur;
     f->done = true; g.idle = 0;
-    --g.alive;
-    g.warps[f->linear >> 5].alive &= ~(1u << (f->linear & 31));
+    --g.alive; --g.cta_alive[f->cta];
+    g.warps[f->cta * g.warps_per_cta + (f->linear >> 5)].alive &= ~(1u << (f->linear & 31));
     swapcontext(&f->ctx, &g.sched);
 }
 
+// `cluster` CTAs (consecutive in x) are resident together and may meet at cluster_barrier(); 1 = ordinary launch.  Limits of the cluster mode:
+// function-level __shared__ variables are one copy per launch (a cluster kernel must keep per-CTA state in dynamic shared memory, or touch its
+// static shared variables from one CTA only), and distributed shared memory is not modelled.
 template <class F>
-void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call)
+void launch_cluster(int cluster, dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call)
 {
     State& g = st();
     std::function<void()> body = kernel_call;
-    g.body = &body; g.bdim = block; g.gdim = grid;
+    g.body = &body; g.bdim = block; g.gdim = grid; g.cluster = cluster;
     const int nthreads = (int)(block.x * block.y * block.z);
-    const size_t stack_bytes = 256 * 1024;
-    g.dyn.assign(smem_bytes + 16, 0); g.dyn_smem = g.dyn.data();
-    for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; ++bx) {
-        g.bid = dim3(bx, by, bz);
-        g.fibers.clear(); g.fibers.resize(nthreads);
-        g.warps.assign((nthreads + 31) / 32, Warp());
-        g.alive = nthreads; g.bar_arrived = 0; g.idle = 0; g.failure = nullptr;
-        for (int t = 0; t < nthreads; ++t) {
-            Fiber& f = g.fibers[t];
+    const size_t stack_bytes = 128 * 1024;
+    g.warps_per_cta = (nthreads + 31) / 32;
+    g.dyn_stride = (smem_bytes + 16 + 127) / 128 * 128;
+    g.dyn.assign(g.dyn_stride * cluster, 0); g.dyn_smem = g.dyn.data();
+    if (grid.x % cluster) throw std::runtime_error("grid.x is not a multiple of the cluster size");
+    for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; bx += cluster) {
+        const int total = nthreads * cluster;
+        g.fibers.clear(); g.fibers.resize(total);
+        g.warps.assign((size_t)g.warps_per_cta * cluster, Warp());
+        g.alive = total; g.idle = 0; g.failure = nullptr; g.cl_arrived = 0;
+        g.cta_alive.assign(cluster, nthreads); g.bar_arrived.assign(cluster, 0); g.bar_gen.assign(cluster, 0u);
+        for (int i = 0; i < total; ++i) {
+            Fiber& f = g.fibers[i];
+            const int t = i % nthreads;
+            f.cta = i / nthreads; f.bid = dim3(bx + f.cta, by, bz);
             f.linear = t; f.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y)); f.done = false;
             f.stack.reset(new char[stack_bytes]);
             getcontext(&f.ctx);
             f.ctx.uc_stack.ss_sp = f.stack.get(); f.ctx.uc_stack.ss_size = stack_bytes; f.ctx.uc_link = nullptr;
             makecontext(&f.ctx, (void (*)())trampoline, 0);
-            g.warps[t >> 5].alive |= 1u << (t & 31);
+            g.warps[f.cta * g.warps_per_cta + (t >> 5)].alive |= 1u << (t & 31);
         }
         while (g.alive > 0) {
-            for (int t = 0; t < nthreads && g.alive > 0; ++t) {
+            for (int t = 0; t < total && g.alive > 0; ++t) {
                 Fiber& f = g.fibers[t];
                 if (f.done) continue;
                 g.cur = &f;
@@ -116,20 +133,52 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call)
         }
         g.fibers.clear();
     }
+    g.cluster = 1;
 }
+
+template <class F>
+void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call) { launch_cluster(1, grid, block, smem_bytes, kernel_call); }
 
 inline void cta_barrier()
 {
     State& g = st();
-    const unsigned my = g.bar_gen;
-    ++g.bar_arrived;
-    while (g.bar_gen == my) {
-        if (g.bar_arrived >= g.alive) { g.bar_arrived = 0; ++g.bar_gen; g.idle = 0; break; }
+    const int c = g.cur->cta;
+    const unsigned my = g.bar_gen[c];
+    ++g.bar_arrived[c];
+    while (g.bar_gen[c] == my) {
+        if (g.bar_arrived[c] >= g.cta_alive[c]) { g.bar_arrived[c] = 0; ++g.bar_gen[c]; g.idle = 0; break; }
         yield();
     }
 }
 
-inline Warp& my_warp() { State& g = st(); return g.warps[g.cur->linear >> 5]; }
+// barrier.cluster.arrive + wait over every live thread of the resident CTAs
+inline void cluster_barrier()
+{
+    State& g = st();
+    const unsigned my = g.cl_gen;
+    ++g.cl_arrived;
+    while (g.cl_gen == my) {
+        if (g.cl_arrived >= g.alive) { g.cl_arrived = 0; ++g.cl_gen; g.idle = 0; break; }
+        yield();
+    }
+}
+inline unsigned cluster_rank() { return (unsigned)st().cur->cta; }
+
+// __syncthreads_or: the barrier plus an OR over the CTA
+inline int cta_barrier_or(int pred)
+{
+    static int acc[64];
+    const int c = st().cur->cta;
+    if (pred) acc[c] = 1;
+    cta_barrier();                 // every contribution is in
+    const int r = acc[c];
+    cta_barrier();                 // every thread has read it
+    acc[c] = 0;
+    cta_barrier();                 // cleared before anybody can contribute to the next one
+    return r;
+}
+
+inline Warp& my_warp() { State& g = st(); return g.warps[g.cur->cta * g.warps_per_cta + (g.cur->linear >> 5)]; }
 inline int lane_id() { return st().cur->linear & 31; }
 
 inline void warp_barrier(uint32_t mask)
@@ -167,9 +216,10 @@ template <class T> inline T shfl(uint32_t mask, T v, int src)
 #define __shared__ static
 #define __constant__ static
 #define __align__(n) alignas(n)
-#define PLVS_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::st().dyn_smem)
+#define __cluster_dims__(...)
+#define PLVS_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::st().dyn_smem + emu::st().dyn_stride * emu::st().cur->cta)
 #define threadIdx (emu::st().cur->tid)
-#define blockIdx (emu::st().bid)
+#define blockIdx (emu::st().cur->bid)
 #define blockDim (emu::st().bdim)
 #define gridDim (emu::st().gdim)
 
@@ -177,6 +227,10 @@ using std::max;
 using std::min;
 
 inline void __syncthreads() { emu::cta_barrier(); }
+inline int __syncthreads_or(int pred) { return emu::cta_barrier_or(pred); }
+inline long long clock64() { static long long t = 0; return ++t; }
+template <class T> inline T __ldcg(const T* p) { return *p; }
+template <class T> inline T __ldg(const T* p) { return *p; }
 inline void __syncwarp(uint32_t mask = 0xffffffffu) { emu::warp_barrier(mask); }
 inline void __threadfence() {}
 template <class T> inline T __shfl_sync(uint32_t m, T v, int src) { return emu::shfl(m, v, src); }
@@ -193,6 +247,24 @@ inline uint32_t __ballot_sync(uint32_t mask, bool pred)
     emu::warp_barrier(mask);
     return r;
 }
+template <class T> inline T __reduce_min_sync(uint32_t mask, T v)
+{
+    T r = v;
+    for (int o = 16; o; o >>= 1) { const T w = emu::shfl(mask, r, emu::lane_id() ^ o); if (w < r) r = w; }
+    return r;
+}
+template <class T> inline T __reduce_max_sync(uint32_t mask, T v)
+{
+    T r = v;
+    for (int o = 16; o; o >>= 1) { const T w = emu::shfl(mask, r, emu::lane_id() ^ o); if (w > r) r = w; }
+    return r;
+}
+template <class T> inline T __reduce_add_sync(uint32_t mask, T v)
+{
+    T r = v;
+    for (int o = 16; o; o >>= 1) r += emu::shfl(mask, r, emu::lane_id() ^ o);
+    return r;
+}
 inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
@@ -202,4 +274,6 @@ template <class T> inline T atomicSub(T* p, T v) { const T o = *p; *p = o - v; r
 template <class T> inline T atomicExch(T* p, T v) { const T o = *p; *p = v; return o; }
 template <class T> inline T atomicCAS(T* p, T cmp, T v) { const T o = *p; if (o == cmp) *p = v; return o; }
 template <class T> inline T atomicMax(T* p, T v) { const T o = *p; if (v > o) *p = v; return o; }
+template <class T> inline T atomicOr(T* p, T v) { const T o = *p; *p = o | v; return o; }
+template <class T> inline T atomicAnd(T* p, T v) { const T o = *p; *p = o & v; return o; }
 template <class T> inline T atomicMin(T* p, T v) { const T o = *p; if (v < o) *p = v; return o; }

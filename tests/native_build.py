@@ -25,7 +25,10 @@ def build_emulated_kernels():
     return str(out)
 
 
-def build_emulated_library(units=("core.cu", "bow.cu")):
+CLUSTER_KERNELS = {"k_resolve": 8}          # __cluster_dims__ of the kernels that need their CTAs resident together
+
+
+def build_emulated_library(units=("core.cu", "bow.cu", "match.cu")):
     """Whole translation units of the product on the CPU: `kernel<<<grid, block, smem, stream>>>(args);` is rewritten to emu::launch, the CUDA runtime
     calls resolve to tests/native/fake_cuda/cuda_runtime.h (host memory), device code runs on cuda_emu.hpp.  Only units without inline PTX qualify.
     -> tests/native/libemu_units.so exporting the same C ABI as the real library for those units."""
@@ -33,7 +36,7 @@ def build_emulated_library(units=("core.cu", "bow.cu")):
     csrc = HERE.parent / "plvs_b200" / "csrc"
     gen = HERE / "native" / "_gen"
     out = HERE / "native" / "libemu_units.so"
-    deps = [csrc / u for u in units] + [csrc / "common.cuh", csrc / "bow_kernels.cuh", HERE / "native" / "cuda_emu.hpp", HERE / "native" / "fake_cuda" / "cuda_runtime.h",
+    deps = [csrc / u for u in units] + list(csrc.glob("*.cuh")) + [ HERE / "native" / "cuda_emu.hpp", HERE / "native" / "fake_cuda" / "cuda_runtime.h",
                                         HERE.parent / "include" / "plvs_b200.h", pathlib.Path(__file__)]
     if out.exists() and all(out.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return str(out)
@@ -58,7 +61,8 @@ def build_emulated_library(units=("core.cu", "bow.cu")):
             args = text[m.end():j - 1]
             assert text[j:].lstrip().startswith(";"), (u, text[m.start():j + 20])
             grid, block, smem = cfg[0], cfg[1], cfg[2] if len(cfg) > 2 else "0"
-            res.append(text[pos:m.start()] + "emu::launch(dim3(%s), dim3(%s), (size_t)(%s), [&] { %s(%s); })" % (grid, block, smem, m.group(1), args))
+            cl = CLUSTER_KERNELS.get(m.group(1).split("<")[0].strip(), 1)
+            res.append(text[pos:m.start()] + "emu::launch_cluster(%d, dim3(%s), dim3(%s), (size_t)(%s), [&] { %s(%s); })" % (cl, grid, block, smem, m.group(1), args))
             pos = j
         res.append(text[pos:])
         body = "".join(res).replace('#include "', '#include "%s/' % csrc)

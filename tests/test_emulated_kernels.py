@@ -247,3 +247,143 @@ def test_bow_entry_points_whole_unit(tmp_path, frames):
     assert lib.plvs_voc_load_text(str(tmp_path / "missing.txt").encode(), 0, C.byref(h)) != 0
     bad = tmp_path / "bad.txt"; bad.write_text("hello world\n")
     assert lib.plvs_voc_load_text(str(bad).encode(), 0, C.byref(h)) != 0
+
+
+# ---- the matcher translation unit as a whole (plvs_b200/csrc/match.cu) on the CPU model, through the product's own Python mirror ------------------
+class _Missing:
+    """stands for the entry points of the other translation units while the signatures are declared"""
+    def __setattr__(self, k, v):
+        pass
+
+
+class _Partial:
+    def __init__(self, lib):
+        object.__setattr__(self, "_lib", lib)
+
+    def __getattr__(self, name):
+        try:
+            return getattr(object.__getattribute__(self, "_lib"), name)
+        except AttributeError:
+            return _Missing()
+
+
+@pytest.fixture(scope="module")
+def emu_matcher():
+    from tests.native_build import build_emulated_library
+    from plvs_b200.matcher import ORBmatcher
+    lib = ABI.declare(_Partial(C.CDLL(build_emulated_library())))
+
+    def make(nnratio, check):
+        m = object.__new__(ORBmatcher)                      # the product class, bound to the emulated unit instead of libplvs_b200.so
+        m._lib = lib; m.mfNNratio, m.mbCheckOrientation = nnratio, check
+        m._h = C.c_void_p()
+        assert lib.plvs_match_create(0, C.byref(m._h)) == 0
+        return m
+    return make
+
+
+def test_matcher_unit_projection_searches(emu_matcher, frames):
+    """k_build_grid + k_candidates + the 8-CTA cluster kernel k_resolve (cluster barrier, claim tables, Jacobi rounds) through
+    plvs_match_projection_map / _last: the sequential claim semantics of the reference, reproduced on the CPU model"""
+    K, tab, fr = frames
+    (last, Tl), (cur, Tc) = (fr[0], synth.pose(10)), (fr[1], synth.pose(11))
+    q, _ = scenario.map_queries(last, cur, K, Tl, Tc)
+    q = q[:900]
+    rng = np.random.default_rng(3)
+    claimed = (rng.random(cur.n) < 0.15).astype(np.uint8)
+    m = emu_matcher(0.8, True)
+    for th in (3.0, 15.0):
+        n, a = m.SearchByProjectionMap(cur, q, th, claimed=claimed)
+        on, oa = OM.search_by_projection_map(cur, q, th, 0.8, claimed=claimed)
+        assert n == on and np.array_equal(a, oa) and n > 100
+    ql, _ = scenario.last_queries(last, cur, K, Tl, Tc)
+    ql = ql[:900]
+    m2 = emu_matcher(0.9, True)
+    n, a = m2.SearchByProjectionLast(cur, ql, 15.0, False, False)
+    on, oa = OM.search_by_projection_last(cur, ql, 15.0, False, False, True)
+    assert n == on and np.array_equal(a, oa) and n > 100
+
+
+def test_matcher_unit_search_local_points_and_initialization(emu_matcher, frames):
+    """the two entry points that have not met a GPU, host code included: plvs_match_in_frustum -> plvs_match_projection_map_resident (compaction on
+    first use, device-resident queries, source indices) and plvs_match_initialization"""
+    K, tab, fr = frames
+    last, cur = fr[0], fr[1]
+    Tl, Tc = synth.pose(10), synth.pose(11)
+    ok = last.depth_at_kp > 0
+    Pw = scenario.backproject(last.keys[ok], last.depth_at_kp[ok], K, Tl)[:1200]
+    n = len(Pw)
+    pts = np.zeros(n, OM.MAP_POINT)
+    pts["xw"] = Pw
+    Ow = np.asarray(Tl, np.float64).reshape(3, 4)[:, 3]
+    v = Pw.astype(np.float64) - Ow; d = np.linalg.norm(v, axis=1)
+    pts["normal"] = (v / d[:, None]).astype(np.float32)
+    lvl = last.keys["octave"][ok][:n]
+    pts["max_dist"] = (d * tab.scale[lvl]).astype(np.float32); pts["min_dist"] = (pts["max_dist"] / tab.scale[7]).astype(np.float32)
+    rng = np.random.default_rng(1)
+    pts["flags"] = (rng.random(n) < 0.9).astype(np.uint32); pts["desc"] = last.desc[ok][:n]
+    frm = OM.make_frustum(Tc, K, (0.0, 0.0, 640.0, 480.0), K["bf"], 0.5, 1.2, 8)
+    claimed = (rng.random(cur.n) < 0.2).astype(np.uint8)
+    m = emu_matcher(0.8, True)
+    nin, q, iv = m.InFrustum(frm, pts)
+    nm, assign = m.SearchByProjectionMapResident(cur, 3.0, claimed=claimed)
+    on, oq, oiv = OM.in_frustum(frm, pts)
+    assert nin == on and np.array_equal(iv, oiv) and nin > 300
+    src = np.nonzero(oiv)[0]
+    onm, oassign = OM.search_by_projection_map(cur, oq[src], 3.0, 0.8, claimed=claimed)
+    want = np.where(oassign >= 0, src[np.maximum(oassign, 0)], -1)
+    assert nm == onm and np.array_equal(assign, want) and nm > 100
+    mi = emu_matcher(0.9, True)
+    prev = np.stack([last.keys["x"], last.keys["y"]], 1)
+    n1, a1, p1 = mi.SearchForInitialization(last, cur, prev, 100)
+    o1, oa1, op1 = OM.search_for_initialization(last, cur, prev, 100, 0.9, True)
+    assert n1 == o1 and np.array_equal(a1, oa1) and np.array_equal(p1.view(np.uint32), op1.view(np.uint32)) and n1 > 50
+
+
+# ---- the GPU matcher tests themselves, replayed on the CPU model -----------------------------------------------------------------------------
+def _gpu_matcher_cases():
+    import tests.test_gpu_match as G
+    cases = [(G.test_hamming_helper, None, {})]
+    cases += [(G.test_projection_map, "f", dict(th=t)) for t in (1.0, 15.0)]
+    cases += [(G.test_projection_map_claims_and_far, "f", {}), (G.test_projection_last_competition, "f", {}), (G.test_match_empty_inputs, "f", {})]
+    cases += [(G.test_projection_last, "f", dict(th=t, fwd=a, bwd=b)) for t, a, b in ((15.0, False, False), (15.0, True, False), (15.0, False, True))]
+    cases += [(G.test_triangulation, "f", dict(coarse=c, only_stereo=s)) for c, s in ((False, False), (True, False), (False, True))]
+    cases += [(G.test_fuse, "f", dict(with_uright=u, dup=d, th=t)) for u, d, t in ((True, True, 4.0), (False, False, 3.0))]
+    cases += [(G.test_search_by_bow, "f", dict(nodes=n)) for n in (16, 1024)]
+    cases += [(G.test_projection_reloc, "f", dict(th=10.0, orb_dist=100)), (G.test_fuse_sim3, "f", dict(dup=True, th=3.0)),
+              (G.test_projection_sim3, "f", dict(th=8, ratio=1.5)), (G.test_search_by_sim3, "f", {})]
+    cases += [(G.test_search_by_bow_kf, "f", dict(nodes=n)) for n in (16, 1024)]
+    cases += [(G.test_distinctive_descriptors, None, {})]
+    return cases
+
+
+@pytest.fixture(scope="module")
+def gpu_test_frames():
+    """what tests/test_gpu_match.py's `frames` fixture holds, with the (bit-identical) oracle extractor in place of the device one"""
+    K = synth.intrinsics(640, 480)
+    tab = O.Tables(2000)
+    out = []
+    for f in (10, 11, 15):
+        kp, desc, _, _ = O.extract_port(synth.gray_frame(f), 2000)
+        fr = scenario.make_frame(kp, desc, synth.depth_frame(f), K, tab.scale)
+        fr.level_sigma2 = tab.sigma2
+        out.append((fr, synth.pose(f)))
+    return K, out
+
+
+@pytest.fixture
+def product_bound_to_emulated_units(monkeypatch):
+    """plvs_b200._lib.load() hands out the emulated translation units for the duration of one test: every product class then runs on the CPU model"""
+    from tests.native_build import build_emulated_library
+    monkeypatch.setattr(ABI, "_lib", ABI.declare(_Partial(C.CDLL(build_emulated_library()))))
+
+
+@pytest.mark.parametrize("fn,needs,kw", _gpu_matcher_cases(), ids=lambda v: getattr(v, "__name__", None) or (",".join("%s=%s" % i for i in v.items()) if isinstance(v, dict) else "x"))
+def test_gpu_matcher_tests_replayed_on_the_cpu_model(product_bound_to_emulated_units, gpu_test_frames, fn, needs, kw):
+    """tests/test_gpu_match.py's own test functions (those that need no extractor), run against plvs_b200/csrc/match.cu compiled for the CPU model:
+    the whole matcher -- grid, candidate walks, the cluster kernel's claim resolution, triangulation, Fuse, BoW searches, Sim3 searches,
+    distinctive descriptors -- is exercised from its real source in the CPU suite, not only on the GPU box"""
+    if needs == "f":
+        fn(gpu_test_frames, **kw)
+    else:
+        fn(True, **kw)
