@@ -25,6 +25,7 @@ void set_error(const char* fmt, ...);
 // dynamic shared memory of a kernel (the CPU execution model of tests/native/cuda_emu.hpp defines its own before this header is seen)
 #ifndef PLVS_DYN_SMEM
 #define PLVS_DYN_SMEM(T, name) extern __shared__ T name[]
+#define PLVS_DYN_SMEM_ALIGNED(T, name, a) extern __shared__ __align__(a) T name[]
 #endif
 
 #ifdef __CUDACC__

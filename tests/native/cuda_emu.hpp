@@ -35,6 +35,7 @@ struct float4 { float x, y, z, w; };
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline float3 make_float3(float x, float y, float z) { return float3{x, y, z}; }
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 inline int2 make_int2(int x, int y) { return int2{x, y}; }
 
 namespace emu {
@@ -103,7 +104,8 @@ void launch_cluster(int cluster, dim3 grid, dim3 block, size_t smem_bytes, F&& k
     const size_t stack_bytes = 128 * 1024;
     g.warps_per_cta = (nthreads + 31) / 32;
     g.dyn_stride = (smem_bytes + 16 + 127) / 128 * 128;
-    g.dyn.assign(g.dyn_stride * cluster, 0); g.dyn_smem = g.dyn.data();
+    g.dyn.assign(g.dyn_stride * cluster + 256, 0);
+    g.dyn_smem = g.dyn.data() + (256 - (reinterpret_cast<uintptr_t>(g.dyn.data()) & 255)) % 256;          // 256-byte aligned like the device's window
     if (grid.x % cluster) throw std::runtime_error("grid.x is not a multiple of the cluster size");
     for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; bx += cluster) {
         const int total = nthreads * cluster;
@@ -164,6 +166,20 @@ inline void cluster_barrier()
 }
 inline unsigned cluster_rank() { return (unsigned)st().cur->cta; }
 
+// 32-bit "shared-memory addresses" (what __cvta_generic_to_shared yields on the device) for code that does address arithmetic on them:
+// region id in the top byte, byte offset below; a region is a 16 MiB window starting at the first pointer seen in it
+inline std::vector<const char*>& smem_regions() { static std::vector<const char*> r; return r; }
+inline uint32_t smem_handle(const void* p)
+{
+    auto& r = smem_regions();
+    const char* c = (const char*)p;
+    for (size_t i = 0; i < r.size(); ++i) if (c >= r[i] && c < r[i] + (1u << 24)) return (uint32_t)((i + 1) << 24) | (uint32_t)(c - r[i]);
+    if (r.size() >= 254) r.clear();
+    r.push_back(c);
+    return (uint32_t)(r.size() << 24);
+}
+inline void* smem_pointer(uint32_t h) { return (void*)(smem_regions()[(h >> 24) - 1] + (h & 0xffffffu)); }
+
 // __syncthreads_or: the barrier plus an OR over the CTA
 inline int cta_barrier_or(int pred)
 {
@@ -215,9 +231,10 @@ template <class T> inline T shfl(uint32_t mask, T v, int src)
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __constant__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __cluster_dims__(...)
 #define PLVS_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::st().dyn_smem + emu::st().dyn_stride * emu::st().cur->cta)
+#define PLVS_DYN_SMEM_ALIGNED(T, name, a) PLVS_DYN_SMEM(T, name)
 #define threadIdx (emu::st().cur->tid)
 #define blockIdx (emu::st().cur->bid)
 #define blockDim (emu::st().bdim)
@@ -225,12 +242,30 @@ template <class T> inline T shfl(uint32_t mask, T v, int src)
 
 using std::max;
 using std::min;
+using std::isnan;
+using std::isinf;
 
 inline void __syncthreads() { emu::cta_barrier(); }
 inline int __syncthreads_or(int pred) { return emu::cta_barrier_or(pred); }
 inline long long clock64() { static long long t = 0; return ++t; }
 template <class T> inline T __ldcg(const T* p) { return *p; }
 template <class T> inline T __ldg(const T* p) { return *p; }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __frcp_rn(float a) { return 1.0f / a; }
+inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+inline int __float2int_rd(float a) { return (int)std::floor(a); }
+inline int __float2int_rn(float a) { return (int)std::nearbyint(a); }
+inline int __float2int_rz(float a) { return (int)a; }
+inline float __int2float_rn(int a) { return (float)a; }
+inline uint32_t __float_as_uint(float a) { uint32_t u; std::memcpy(&u, &a, 4); return u; }
+inline float __uint_as_float(uint32_t u) { float a; std::memcpy(&a, &u, 4); return a; }
+inline int __float_as_int(float a) { int u; std::memcpy(&u, &a, 4); return u; }
+inline float __int_as_float(int u) { float a; std::memcpy(&a, &u, 4); return a; }
+inline float __saturatef(float a) { return a < 0.f ? 0.f : a > 1.f ? 1.f : a; }
 inline void __syncwarp(uint32_t mask = 0xffffffffu) { emu::warp_barrier(mask); }
 inline void __threadfence() {}
 template <class T> inline T __shfl_sync(uint32_t m, T v, int src) { return emu::shfl(m, v, src); }
@@ -263,6 +298,20 @@ template <class T> inline T __reduce_add_sync(uint32_t mask, T v)
 {
     T r = v;
     for (int o = 16; o; o >>= 1) r += emu::shfl(mask, r, emu::lane_id() ^ o);
+    return r;
+}
+inline int __any_sync(uint32_t mask, int pred) { return __ballot_sync(mask, pred != 0) != 0; }
+inline int __all_sync(uint32_t mask, int pred) { emu::Warp& w = emu::my_warp(); const uint32_t b = __ballot_sync(mask, pred != 0); return b == (mask & w.alive); }
+template <class T> inline T __reduce_or_sync(uint32_t mask, T v)
+{
+    T r = v;
+    for (int o = 16; o; o >>= 1) r |= emu::shfl(mask, r, emu::lane_id() ^ o);
+    return r;
+}
+template <class T> inline T __reduce_and_sync(uint32_t mask, T v)
+{
+    T r = v;
+    for (int o = 16; o; o >>= 1) r &= emu::shfl(mask, r, emu::lane_id() ^ o);
     return r;
 }
 inline int __popc(uint32_t v) { return __builtin_popcount(v); }

@@ -267,79 +267,6 @@ class _Partial:
             return _Missing()
 
 
-@pytest.fixture(scope="module")
-def emu_matcher():
-    from tests.native_build import build_emulated_library
-    from plvs_b200.matcher import ORBmatcher
-    lib = ABI.declare(_Partial(C.CDLL(build_emulated_library())))
-
-    def make(nnratio, check):
-        m = object.__new__(ORBmatcher)                      # the product class, bound to the emulated unit instead of libplvs_b200.so
-        m._lib = lib; m.mfNNratio, m.mbCheckOrientation = nnratio, check
-        m._h = C.c_void_p()
-        assert lib.plvs_match_create(0, C.byref(m._h)) == 0
-        return m
-    return make
-
-
-def test_matcher_unit_projection_searches(emu_matcher, frames):
-    """k_build_grid + k_candidates + the 8-CTA cluster kernel k_resolve (cluster barrier, claim tables, Jacobi rounds) through
-    plvs_match_projection_map / _last: the sequential claim semantics of the reference, reproduced on the CPU model"""
-    K, tab, fr = frames
-    (last, Tl), (cur, Tc) = (fr[0], synth.pose(10)), (fr[1], synth.pose(11))
-    q, _ = scenario.map_queries(last, cur, K, Tl, Tc)
-    q = q[:900]
-    rng = np.random.default_rng(3)
-    claimed = (rng.random(cur.n) < 0.15).astype(np.uint8)
-    m = emu_matcher(0.8, True)
-    for th in (3.0, 15.0):
-        n, a = m.SearchByProjectionMap(cur, q, th, claimed=claimed)
-        on, oa = OM.search_by_projection_map(cur, q, th, 0.8, claimed=claimed)
-        assert n == on and np.array_equal(a, oa) and n > 100
-    ql, _ = scenario.last_queries(last, cur, K, Tl, Tc)
-    ql = ql[:900]
-    m2 = emu_matcher(0.9, True)
-    n, a = m2.SearchByProjectionLast(cur, ql, 15.0, False, False)
-    on, oa = OM.search_by_projection_last(cur, ql, 15.0, False, False, True)
-    assert n == on and np.array_equal(a, oa) and n > 100
-
-
-def test_matcher_unit_search_local_points_and_initialization(emu_matcher, frames):
-    """the two entry points that have not met a GPU, host code included: plvs_match_in_frustum -> plvs_match_projection_map_resident (compaction on
-    first use, device-resident queries, source indices) and plvs_match_initialization"""
-    K, tab, fr = frames
-    last, cur = fr[0], fr[1]
-    Tl, Tc = synth.pose(10), synth.pose(11)
-    ok = last.depth_at_kp > 0
-    Pw = scenario.backproject(last.keys[ok], last.depth_at_kp[ok], K, Tl)[:1200]
-    n = len(Pw)
-    pts = np.zeros(n, OM.MAP_POINT)
-    pts["xw"] = Pw
-    Ow = np.asarray(Tl, np.float64).reshape(3, 4)[:, 3]
-    v = Pw.astype(np.float64) - Ow; d = np.linalg.norm(v, axis=1)
-    pts["normal"] = (v / d[:, None]).astype(np.float32)
-    lvl = last.keys["octave"][ok][:n]
-    pts["max_dist"] = (d * tab.scale[lvl]).astype(np.float32); pts["min_dist"] = (pts["max_dist"] / tab.scale[7]).astype(np.float32)
-    rng = np.random.default_rng(1)
-    pts["flags"] = (rng.random(n) < 0.9).astype(np.uint32); pts["desc"] = last.desc[ok][:n]
-    frm = OM.make_frustum(Tc, K, (0.0, 0.0, 640.0, 480.0), K["bf"], 0.5, 1.2, 8)
-    claimed = (rng.random(cur.n) < 0.2).astype(np.uint8)
-    m = emu_matcher(0.8, True)
-    nin, q, iv = m.InFrustum(frm, pts)
-    nm, assign = m.SearchByProjectionMapResident(cur, 3.0, claimed=claimed)
-    on, oq, oiv = OM.in_frustum(frm, pts)
-    assert nin == on and np.array_equal(iv, oiv) and nin > 300
-    src = np.nonzero(oiv)[0]
-    onm, oassign = OM.search_by_projection_map(cur, oq[src], 3.0, 0.8, claimed=claimed)
-    want = np.where(oassign >= 0, src[np.maximum(oassign, 0)], -1)
-    assert nm == onm and np.array_equal(assign, want) and nm > 100
-    mi = emu_matcher(0.9, True)
-    prev = np.stack([last.keys["x"], last.keys["y"]], 1)
-    n1, a1, p1 = mi.SearchForInitialization(last, cur, prev, 100)
-    o1, oa1, op1 = OM.search_for_initialization(last, cur, prev, 100, 0.9, True)
-    assert n1 == o1 and np.array_equal(a1, oa1) and np.array_equal(p1.view(np.uint32), op1.view(np.uint32)) and n1 > 50
-
-
 # ---- the GPU matcher tests themselves, replayed on the CPU model -----------------------------------------------------------------------------
 def _gpu_matcher_cases():
     import tests.test_gpu_match as G
@@ -387,3 +314,34 @@ def test_gpu_matcher_tests_replayed_on_the_cpu_model(product_bound_to_emulated_u
         fn(gpu_test_frames, **kw)
     else:
         fn(True, **kw)
+
+
+# ---- tsdf.cu as a whole on the CPU model: the GPU TSDF tests and the GPU tests of the not-yet-verified rows --------------------------------------
+def _gpu_tsdf_cases():
+    import os
+    import tests.test_gpu_tsdf as G
+    cases = [(G.test_scan_sequence, dict(carve=1)), (G.test_scan_color_sequence, {}), (G.test_carving_moves_surface, {}), (G.test_nan_zero_and_rotated_pose, {}),
+             (G.test_reset_and_errors, {})]
+    if os.environ.get("PLVS_EMU_SLOW"):        # minutes each on the CPU model: the cloud route (ray casting, hit lists) and the 20-scan sequence
+        cases += [(G.test_scan_sequence, dict(carve=0)), (G.test_cloud_sequence, dict(color=True, carve=1)), (G.test_cloud_edge_cases, {}),
+                  (G.test_many_scans_carvable_mask_stays_exact, {})]
+    return cases
+
+
+@pytest.mark.parametrize("fn,kw", _gpu_tsdf_cases(), ids=lambda v: getattr(v, "__name__", None) or ",".join("%s=%s" % i for i in v.items()) or "-")
+def test_gpu_tsdf_tests_replayed_on_the_cpu_model(product_bound_to_emulated_units, fn, kw):
+    """tests/test_gpu_tsdf.py's own test functions against plvs_b200/csrc/tsdf.cu compiled for the CPU model: depth-tile pass, chunk classification, commit,
+    and the persistent k_integrate with its bulk-copy ring (copies complete at issue on the model) -- chunk sets, sdf / weight / colour as on the B200.
+    PLVS_EMU_SLOW=1 adds the point-cloud route and the long sequences."""
+    fn(True, **kw)
+
+
+@pytest.mark.parametrize("name", ["_impl_tsdf_from_raw_u16_depth", "_impl_mesh_read_out", "_impl_search_for_initialization", "_impl_search_local_points_resident",
+                                  "_impl_bow_transform"])
+def test_unverified_gpu_tests_replayed_on_the_cpu_model(product_bound_to_emulated_units, tmp_path, name):
+    """the bodies of tests/test_zz_gpu_unverified.py (the rows that have not met a GPU), unchanged, against the emulated translation units: entry points,
+    host sequencing and kernels of the 16-bit depth path, the mesh read-out, SearchForInitialization, the resident SearchLocalPoints and the BoW
+    transform all give the oracle's results (UndistortKeyPoints needs the extractor unit, which is not emulated: its kernel is covered above)"""
+    import tests.test_zz_gpu_unverified as Z
+    fn = getattr(Z, name)
+    fn(tmp_path) if name == "_impl_bow_transform" else fn()
