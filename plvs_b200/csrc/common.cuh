@@ -28,7 +28,13 @@ void set_error(const char* fmt, ...);
 #define PLVS_DYN_SMEM_ALIGNED(T, name, a) extern __shared__ __align__(a) T name[]
 #endif
 
-#ifdef __CUDACC__
+#ifdef PLVS_CUDA_EMU        // tests/native/cuda_emu.hpp: bulk copies complete at issue on the CPU model
+inline uint32_t tma_smem_u32(const void* p) { return emu::smem_handle(p); }
+inline void tma_mbar_init(uint32_t, uint32_t) {}
+inline void tma_mbar_expect_tx(uint32_t, uint32_t) {}
+inline void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t) { std::memcpy(emu::smem_pointer(dst), src, bytes); }
+inline void tma_mbar_wait(uint32_t, uint32_t) {}
+#elif defined(__CUDACC__)
 // 1-D bulk asynchronous copies (the TMA engine; SASS UBLKCP) completed through an mbarrier.  Addresses and sizes must be
 // multiples of 16 bytes.
 __device__ __forceinline__ uint32_t tma_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -231,7 +231,7 @@ struct DistArgs {
 __global__ void __launch_bounds__(kDistThreads)
 k_distribute(DistArgs A)
 {
-    extern __shared__ unsigned long long s_sort[];       // max quota + 8 elements for the std::sort emulation
+    PLVS_DYN_SMEM(unsigned long long, s_sort);           // max quota + 8 elements for the std::sort emulation
     __shared__ int s_i32[32];
     __shared__ unsigned long long s_u64[32];
     __shared__ int s_nc, s_nk, s_ne, s_live, s_flag;

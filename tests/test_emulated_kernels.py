@@ -337,11 +337,37 @@ def test_gpu_tsdf_tests_replayed_on_the_cpu_model(product_bound_to_emulated_unit
 
 
 @pytest.mark.parametrize("name", ["_impl_tsdf_from_raw_u16_depth", "_impl_mesh_read_out", "_impl_search_for_initialization", "_impl_search_local_points_resident",
-                                  "_impl_bow_transform"])
+                                  "_impl_bow_transform", "_impl_undistort_keypoints_on_device"])
 def test_unverified_gpu_tests_replayed_on_the_cpu_model(product_bound_to_emulated_units, tmp_path, name):
     """the bodies of tests/test_zz_gpu_unverified.py (the rows that have not met a GPU), unchanged, against the emulated translation units: entry points,
-    host sequencing and kernels of the 16-bit depth path, the mesh read-out, SearchForInitialization, the resident SearchLocalPoints and the BoW
-    transform all give the oracle's results (UndistortKeyPoints needs the extractor unit, which is not emulated: its kernel is covered above)"""
+    host sequencing and kernels of the 16-bit depth path, the mesh read-out, SearchForInitialization, the resident SearchLocalPoints, the BoW
+    transform and UndistortKeyPoints (on keypoints left "on the device" by the emulated extractor) all give the oracle's results"""
     import tests.test_zz_gpu_unverified as Z
     fn = getattr(Z, name)
     fn(tmp_path) if name == "_impl_bow_transform" else fn()
+
+
+
+# ---- orb.cu as a whole on the CPU model ------------------------------------------------------------------------------------------------------
+def _gpu_orb_cases():
+    import os
+    import tests.test_gpu_orb as G
+    cases = [G.test_orb_vga_2000, G.test_orb_low_texture_fallback, G.test_orb_flat_and_empty]
+    if os.environ.get("PLVS_EMU_SLOW"):
+        cases += [G.test_orb_lapping_area, G.test_orb_odd_sizes, G.test_orb_batch_matches_single, G.test_color_input_and_stereo_from_rgbd]
+    return cases
+
+
+@pytest.mark.parametrize("fn", _gpu_orb_cases(), ids=lambda f: f.__name__)
+def test_gpu_orb_tests_replayed_on_the_cpu_model(product_bound_to_emulated_units, fn):
+    """tests/test_gpu_orb.py's own test functions against plvs_b200/csrc/orb.cu compiled for the CPU model: pyramid, per-cell FAST with fallback, the
+    device quadtree distributor with its std::sort emulation, the bulk-copy-staged Gaussian, orientation and steered BRIEF -- keypoints and
+    descriptors bit-identical to the oracle, as on the B200"""
+    fn(True)
+
+
+def test_smoke_replayed_on_the_cpu_model(product_bound_to_emulated_units):
+    """__graft_entry__.smoke() -- one small frame through extract -> match -> TSDF, each stage against the oracle (and the compiled reference when it is
+    there) -- with every translation unit of the library on the CPU model"""
+    import __graft_entry__ as g
+    g.smoke()
