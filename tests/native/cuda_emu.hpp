@@ -2,7 +2,7 @@
 // run in this container: tests/native/emu_kernels.cpp includes the product's device-only headers (plvs_b200/csrc/*.cuh) after this
 // file and drives them through emu::launch.  Nothing here is linked into libplvs_b200.so, and nothing in the product falls back to it.
 //
-// Model: one CTA at a time; every CUDA thread is a ucontext fiber on the calling OS thread (so "atomics" are plain operations and
+// Model: one CTA at a time; every CUDA thread is a fiber (own stack, hand-written switch) on the calling OS thread (so "atomics" are plain operations and
 // __shared__ variables are function-level statics), scheduled round-robin.  __syncthreads / __syncwarp / __shfl_*_sync / __ballot_sync
 // are rendezvous points: a fiber that reaches one yields until every live thread of the CTA (or every live lane named by the mask) has
 // arrived.  A rendezvous that can never complete (divergent barrier, a shuffle some lane skips) is reported as a deadlock instead of
@@ -11,7 +11,6 @@
 // Not modelled: distributed shared memory, TMA / mbarrier, tensor cores, memory ordering weaker than sequential consistency, scheduling races.
 #pragma once
 #define PLVS_CUDA_EMU 1
-#include <ucontext.h>
 
 #include <algorithm>
 #include <climits>
@@ -40,9 +39,20 @@ inline int2 make_int2(int x, int y) { return int2{x, y}; }
 
 namespace emu {
 
+// Context switch: callee-saved registers pushed on the old stack, stack pointers exchanged (glibc's swapcontext would add two signal-mask system
+// calls per switch, which dominated the run time).  x86-64 System V only; the symbol is weak because every emulated unit carries a copy.
+#if !defined(__x86_64__)
+#error "tests/native/cuda_emu.hpp: the fiber switch is written for x86-64"
+#endif
+extern "C" void plvs_emu_switch(void** save_sp, void* load_sp);
+asm(".text\n.weak plvs_emu_switch\n.type plvs_emu_switch,@function\nplvs_emu_switch:\n"
+    "pushq %rbp\npushq %rbx\npushq %r12\npushq %r13\npushq %r14\npushq %r15\n"
+    "movq %rsp, (%rdi)\nmovq %rsi, %rsp\n"
+    "popq %r15\npopq %r14\npopq %r13\npopq %r12\npopq %rbx\npopq %rbp\nret\n");
+
 struct Fiber {
-    ucontext_t ctx;
-    std::unique_ptr<char[]> stack;
+    void* sp = nullptr;            // saved stack pointer while the fiber is switched out
+    char* stack = nullptr;         // borrowed from the pool below: allocating and releasing 128 KiB per thread and launch dominated the run time
     dim3 tid;
     dim3 bid;
     int linear = 0;                // thread index inside its CTA
@@ -56,7 +66,7 @@ struct State {
     std::vector<Fiber> fibers;
     std::vector<Warp> warps;
     Fiber* cur = nullptr;
-    ucontext_t sched;
+    void* sched_sp = nullptr;
     dim3 bdim, gdim;
     int alive = 0;                                  // live fibers of the resident group
     std::vector<int> cta_alive, bar_arrived;        // per resident CTA
@@ -72,12 +82,19 @@ struct State {
     const char* failure = nullptr;
 };
 inline State& st() { static State s; return s; }
+inline char* pooled_stack(size_t index, size_t bytes)
+{
+    static std::vector<std::unique_ptr<char[]>> pool;
+    if (pool.size() <= index) pool.resize(index + 1);
+    if (!pool[index]) pool[index].reset(new char[bytes]);
+    return pool[index].get();
+}
 
 inline void yield()
 {
     State& g = st();
     if (++g.idle > 64L * (long)g.fibers.size() + 4096) { g.failure = "deadlock: a barrier / warp rendezvous can never complete"; }
-    swapcontext(&g.cur->ctx, &g.sched);
+    plvs_emu_switch(&g.cur->sp, g.sched_sp);
 }
 
 inline void trampoline()
@@ -88,7 +105,8 @@ inline void trampoline()
     f->done = true; g.idle = 0;
     --g.alive; --g.cta_alive[f->cta];
     g.warps[f->cta * g.warps_per_cta + (f->linear >> 5)].alive &= ~(1u << (f->linear & 31));
-    swapcontext(&f->ctx, &g.sched);
+    plvs_emu_switch(&f->sp, g.sched_sp);
+    std::abort();                  // a finished fiber is never resumed
 }
 
 // `cluster` CTAs (consecutive in x) are resident together and may meet at cluster_barrier(); 1 = ordinary launch.  Limits of the cluster mode:
@@ -118,10 +136,14 @@ void launch_cluster(int cluster, dim3 grid, dim3 block, size_t smem_bytes, F&& k
             const int t = i % nthreads;
             f.cta = i / nthreads; f.bid = dim3(bx + f.cta, by, bz);
             f.linear = t; f.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y)); f.done = false;
-            f.stack.reset(new char[stack_bytes]);
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = f.stack.get(); f.ctx.uc_stack.ss_size = stack_bytes; f.ctx.uc_link = nullptr;
-            makecontext(&f.ctx, (void (*)())trampoline, 0);
+            f.stack = pooled_stack((size_t)i, stack_bytes);
+            // first switch-in: six zeroed callee-saved registers, then `ret` into trampoline with the stack as a call would leave it (rsp = 8 mod 16)
+            uintptr_t top = (reinterpret_cast<uintptr_t>(f.stack) + stack_bytes) & ~(uintptr_t)15;
+            void** sp = reinterpret_cast<void**>(top - 64);
+            for (int k = 0; k < 6; ++k) sp[k] = nullptr;
+            sp[6] = reinterpret_cast<void*>(&trampoline);
+            sp[7] = nullptr;
+            f.sp = sp;
             g.warps[f.cta * g.warps_per_cta + (t >> 5)].alive |= 1u << (t & 31);
         }
         while (g.alive > 0) {
@@ -129,7 +151,7 @@ void launch_cluster(int cluster, dim3 grid, dim3 block, size_t smem_bytes, F&& k
                 Fiber& f = g.fibers[t];
                 if (f.done) continue;
                 g.cur = &f;
-                swapcontext(&g.sched, &f.ctx);
+                plvs_emu_switch(&g.sched_sp, f.sp);
                 if (g.failure) { const char* why = g.failure; g.failure = nullptr; g.fibers.clear(); throw std::runtime_error(why); }
             }
         }
