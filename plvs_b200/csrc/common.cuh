@@ -79,6 +79,9 @@ inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 // slack: 25 % on top of the request, at least 1.5x the old size.  Buffers above 64 MiB are allocated exactly.
 inline size_t grow_capacity(size_t count, size_t old_n, size_t elem)
 {
+#ifdef PLVS_CUDA_EMU
+    if (std::getenv("PLVS_EMU_GUARD")) return count;       // guard-page runs of the CPU model: no slack that would hide an overrun
+#endif
     if (count * elem > ((size_t)64 << 20)) return count;
     size_t c = count + count / 4 + 64;
     if (c < old_n + old_n / 2) c = old_n + old_n / 2;

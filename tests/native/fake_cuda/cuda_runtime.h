@@ -4,6 +4,36 @@
 #pragma once
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <sys/mman.h>
+#include <unistd.h>
+
+// PLVS_EMU_GUARD=1: every "device" / pinned allocation ends flush against an inaccessible page and starts behind one, so a kernel or a copy that runs
+// past the end of a buffer (or before its start, for 4 KiB-multiple sizes) faults at the offending access -- the CPU model's stand-in for
+// compute-sanitizer's memcheck.  Sizes are rounded up to 16 bytes (vector loads), so overruns inside that slack go unseen.
+namespace fake_cuda {
+inline bool guard_mode() { static const bool on = std::getenv("PLVS_EMU_GUARD") != nullptr; return on; }
+inline std::map<void*, std::pair<void*, size_t>>& guarded() { static std::map<void*, std::pair<void*, size_t>> m; return m; }
+inline void* guarded_alloc(size_t bytes)
+{
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    const size_t body = (bytes + 15) / 16 * 16;
+    const size_t span = (body + page - 1) / page * page;
+    char* base = (char*)mmap(nullptr, span + 2 * page, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == (char*)MAP_FAILED) return nullptr;
+    mprotect(base + page, span, PROT_READ | PROT_WRITE);
+    char* p = base + page + (span - body);
+    guarded()[p] = std::make_pair((void*)base, span + 2 * page);
+    return p;
+}
+inline void guarded_free(void* p)
+{
+    auto it = guarded().find(p);
+    if (it == guarded().end()) return;
+    munmap(it->second.first, it->second.second);
+    guarded().erase(it);
+}
+}  // namespace fake_cuda
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
@@ -17,11 +47,15 @@ inline const char* cudaGetErrorString(cudaError_t) { return "fake runtime error"
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-inline cudaError_t cudaMalloc(void** p, size_t bytes) { *p = std::aligned_alloc(256, (bytes + 255) / 256 * 256 + 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMalloc(void** p, size_t bytes)
+{
+    *p = fake_cuda::guard_mode() ? fake_cuda::guarded_alloc(bytes) : std::aligned_alloc(256, (bytes + 255) / 256 * 256 + 256);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+inline cudaError_t cudaFree(void* p) { if (fake_cuda::guard_mode()) fake_cuda::guarded_free(p); else std::free(p); return cudaSuccess; }
 inline cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { return cudaMalloc(p, bytes); }
 inline cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return cudaSuccess; }
-inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(d, s, n, k); }
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) std::memset(d, v, n); return cudaSuccess; }

@@ -5,6 +5,7 @@ arithmetic, warp-level reductions, prefix sums, barrier placement and float oper
 model cannot show (memory-ordering races, launch configuration limits, nvcc code generation) stays for the GPU run.  k_build_grid and
 k_in_frustum already passed on a B200 and double as a check of the model itself."""
 import ctypes as C
+import pathlib
 import numpy as np
 import pytest
 
@@ -13,6 +14,9 @@ from plvs_b200.matcher import Frame
 from plvs_b200.orb import KP_DTYPE
 from oracle import match as OM, orb as O, tsdf as OT
 from tests.native_build import build_emulated_kernels
+
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
 
 
 @pytest.fixture(scope="module")
@@ -356,3 +360,24 @@ def test_smoke_replayed_on_the_cpu_model(product_bound_to_emulated_units):
     there) -- with every translation unit of the library on the CPU model"""
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_memcheck_on_the_cpu_model(tmp_path):
+    """PLVS_EMU_GUARD=1: every "device" allocation of the emulated library sits between inaccessible pages and buffers are sized exactly, so an
+    out-of-bounds access by a kernel or a copy faults (the model's stand-in for compute-sanitizer memcheck).  In a child interpreter: first that an
+    overrun really faults, then smoke() and the six not-yet-verified GPU test bodies run clean."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PLVS_EMU_GUARD="1")
+    pre = ("import sys, ctypes as C, pathlib; sys.path.insert(0, %r); from plvs_b200 import _lib as ABI; from tests.native_build import build_emulated_library; "
+           "from tests.test_emulated_kernels import _Partial; lib = C.CDLL(build_emulated_library()); ABI._lib = ABI.declare(_Partial(lib)); " % str(ROOT))
+    bad = subprocess.run([sys.executable, "-c", pre + "p = C.c_void_p(); lib.plvs_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]; "
+                          "assert lib.plvs_host_alloc(C.byref(p), 1000) == 0; b = (C.c_ubyte * 2000).from_address(p.value); b[999] = 1; print('in bounds', flush=True); b[1008] = 1; print('missed')"],
+                         capture_output=True, text=True, env=env, cwd=str(ROOT))
+    assert bad.returncode != 0 and "in bounds" in bad.stdout and "missed" not in bad.stdout
+    body = ("import __graft_entry__ as g, tests.test_zz_gpu_unverified as Z; g.smoke(); "
+            "[getattr(Z, n)() for n in ('_impl_tsdf_from_raw_u16_depth', '_impl_mesh_read_out', '_impl_search_for_initialization', '_impl_search_local_points_resident', "
+            "'_impl_undistort_keypoints_on_device')]; Z._impl_bow_transform(pathlib.Path(%r)); print('clean')" % str(tmp_path))
+    ok = subprocess.run([sys.executable, "-c", pre + body], capture_output=True, text=True, env=env, cwd=str(ROOT), timeout=1200)
+    assert ok.returncode == 0 and "clean" in ok.stdout, ok.stderr[-3000:]
