@@ -853,7 +853,9 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
             while (lpq < 32 && per_cta * lpq * 2 <= 1024) lpq *= 2;
             const size_t smem = ((size_t)2 * n + (size_t)per_cta * (h->cap | 1)) * sizeof(uint32_t);
             const size_t smem_small = (size_t)2 * n * sizeof(uint32_t);
-            if (per_cta <= 1024 && smem <= 200 * 1024) {
+            // PLVS_MATCH_RESOLVE_SMEM=0 (experiment knob): candidate lists stay in L2, the CTA needs 8n bytes of shared memory only
+            static const bool lists_in_smem = [] { const char* e = std::getenv("PLVS_MATCH_RESOLVE_SMEM"); return !(e && e[0] == '0'); }();
+            if (per_cta <= 1024 && smem <= 200 * 1024 && lists_in_smem) {
                 static thread_local bool attr_set[2] = {false, false};
                 if (!attr_set[MODE]) {
                     PLVS_CUDA(cudaFuncSetAttribute(k_resolve<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

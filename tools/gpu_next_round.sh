@@ -6,3 +6,8 @@ timeout 600 python -m pytest tests/test_zz_gpu_unverified.py -q -rA --runxfail -
 timeout 300 python tools/bench_extras.py > gpurun_out/bench_extras.jsonl 2> gpurun_out/bench_extras.err; echo "extras exit $?"; cat gpurun_out/bench_extras.jsonl
 timeout 300 ncu --set full --clock-control none -k "regex:k_mesh_|k_bow_|k_init_|k_compact_queries|k_undistort|k_depth_u16" -c 24 -f -o /tmp/extras python tools/bench_extras.py > gpurun_out/extras_ncu.log 2>&1; echo "ncu exit $?"
 ncu -i /tmp/extras.ncu-rep --page raw --csv > gpurun_out/extras_raw.csv 2>/dev/null; ls -la gpurun_out/extras_raw.csv
+# A/B of the SM-sharing knobs: same bench, one JSON line each
+for cfg in "" "PLVS_TSDF_CTAS_PER_SM=1 PLVS_MATCH_RESOLVE_SMEM=0" "PLVS_MATCH_RESOLVE_SMEM=0" "PLVS_TSDF_SM_RESERVE=16" "PLVS_TSDF_SM_RESERVE=32"; do
+  tag=$(echo "${cfg:-default}" | tr ' =' '__')
+  env $cfg timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ab_${tag}.json 2> gpurun_out/bench_ab_${tag}.err; echo "bench [$cfg] exit $?"; cut -c1-260 gpurun_out/bench_ab_${tag}.json
+done
