@@ -280,15 +280,22 @@ _REPLAY_SKIP = {"test_vga_1cm_single_scan": "oracle brute force over a VGA / 1 c
                 "test_orb_1080p": "1080p extraction on the CPU model", "test_orb_vga_1000_frames": "many VGA frames on the CPU model"}
 
 
+# the heaviest replays (10-20 s each on the model) run with PLVS_EMU_FULL=1; the default set keeps the CPU suite within a few minutes
+_REPLAY_FULL_ONLY = {"test_orb_batch_matches_single", "test_color_input_and_stereo_from_rgbd", "test_many_scans_carvable_mask_stays_exact", "test_cloud_sequence",
+                     "test_device_distributor_equals_host_distributor", "test_orb_odd_sizes", "test_orb_lapping_area"}
+
+
 def _replay_cases():
     import importlib
     import itertools
+    import os
+    full = bool(os.environ.get("PLVS_EMU_FULL"))
     cases = []
     for modname in _REPLAY_MODULES:
         mod = importlib.import_module(modname)
         for name in sorted(n for n in vars(mod) if n.startswith("test_")):
             fn = getattr(mod, name)
-            if name in _REPLAY_SKIP:
+            if name in _REPLAY_SKIP or (name in _REPLAY_FULL_ONLY and not full):
                 continue
             axes = []
             for mark in getattr(fn, "pytestmark", []):
