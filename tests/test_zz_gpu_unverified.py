@@ -252,3 +252,29 @@ def test_mesh_read_out(gpu):
 
 def test_bow_transform(gpu, tmp_path):
     _isolated("_impl_bow_transform", tmp_path)
+
+
+def _impl_reference_goldens(tmp_path):
+    """the three widened rows against vectors recorded from the reference's own code (tests/golden/extras_ref.npz): no oracle in between"""
+    import tests.test_extras_golden as G
+    from plvs_b200 import tsdf as T
+    from plvs_b200.bow import ORBVocabulary
+    from plvs_b200.matcher import ORBmatcher
+
+    def search(f1, f2, prev, window, ratio, check):
+        return ORBmatcher(ratio, check).SearchForInitialization(f1, f2, prev, window)
+
+    def meshes(g):
+        g.UpdateMesh()
+        return g.GetMeshes()
+
+    def vocabulary(path):
+        v = ORBVocabulary(); assert v.loadFromTextFile(path)
+        return v
+    G.check_initialization(search)
+    G.check_meshes(lambda kw, frames, color: G.X.mesh_map(T.ChiselServer, kw, frames, color), meshes)
+    G.check_bow(vocabulary, tmp_path)
+
+
+def test_reference_goldens(gpu, tmp_path):
+    _isolated("_impl_reference_goldens", tmp_path)
