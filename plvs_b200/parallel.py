@@ -40,11 +40,13 @@ def exchange_blocks(keys, wsdf, w, group=None):
     return rk, rs, rw
 
 
-def merge_maps(server, group=None):
+def merge_maps(server, group=None, device=None):
     """Global voxel-block merge of the per-rank TSDF maps (plvs_b200.tsdf.ChiselServer).  Afterwards each rank
-    holds exactly the blocks it owns, fused over all ranks.  Returns (#blocks sent, #blocks received)."""
+    holds exactly the blocks it owns, fused over all ranks.  Returns (#blocks sent, #blocks received).
+    `device`: where the exchange buffers live -- the current CUDA device by default (NCCL); the CPU tests run the library on the
+    CPU execution model of tests/native/cuda_emu.hpp, whose "device" memory is host memory, over gloo."""
     lib, h = server._lib, server._h
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
     n = C.c_int()
     rc = lib.plvs_tsdf_export_packed(h, None, None, None, 0, C.byref(n))
     assert rc == 0
@@ -57,7 +59,8 @@ def merge_maps(server, group=None):
         rc = lib.plvs_tsdf_export_packed(h, C.c_void_p(keys.data_ptr()), C.c_void_p(wsdf.data_ptr()), C.c_void_p(w.data_ptr()), n, C.byref(m))
         assert rc == 0 and m.value == n
     rk, rs, rw = exchange_blocks(keys, wsdf, w, group)
-    torch.cuda.synchronize(dev)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
     server.Reset()
     if len(rk):
         rc = lib.plvs_tsdf_merge_packed(h, C.c_void_p(rk.data_ptr()), C.c_void_p(rs.data_ptr()), C.c_void_p(rw.data_ptr()), len(rk))

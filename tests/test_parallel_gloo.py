@@ -60,3 +60,57 @@ def test_owner_hash_is_stable():
     assert o8.tolist() == [0, ((1 * 73856093) ^ (2 * 19349663) ^ (3 * 83492791)) % 8,
                            (((-1 * 73856093) ^ (-2 * 19349663) ^ (-3 * 83492791)) & 0xFFFFFFFF) % 8,
                            (((100 * 73856093) ^ (-7 * 19349663) ^ (42 * 83492791)) & 0xFFFFFFFF) % 8]
+
+
+
+def _merge_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ctypes as C
+    from plvs_b200 import _lib as ABI, parallel, synth, tsdf as T
+    from oracle import tsdf as OT
+    from tests.native_build import build_emulated_library
+    from tests.test_emulated_kernels import _Partial
+    from tests.merge_expect import fold, compare
+    ABI._lib = ABI.declare(_Partial(C.CDLL(build_emulated_library())))          # this process runs the library on the CPU model
+    w, h = 160, 120
+    K = synth.intrinsics(w, h)
+    p = T.default_params(voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=4096, use_color=0)
+    frames = ((0, 1, 2), (2, 5, 9))                                              # the two ranks see the same world from different poses
+    g = T.ChiselServer(p); g.SetDepthCameraInfo(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
+    for f in frames[rank]:
+        g.integrate(synth.depth_frame(f, w, h), synth.pose(f))
+    sent, received = parallel.merge_maps(g, device=torch.device("cpu"))
+    ck, cs, cw, _ = g.download()
+    # expectation: both ranks' maps from the oracle, folded in rank order, restricted to the blocks this rank owns
+    host = []
+    for fr in frames:
+        o = OT.Map(p, threads=4); o.set_camera(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
+        for f in fr:
+            o.integrate(synth.depth_frame(f, w, h), synth.pose(f))
+        ok, osdf, ow, _ = o.download()
+        host.append((ok, osdf, ow))
+    exp = fold(host)
+    mine = {k: v for k, v in exp.items() if int(parallel.owner_of(torch.tensor([k], dtype=torch.int32), world)[0]) == rank}
+    shared = set(map(tuple, host[0][0])) & set(map(tuple, host[1][0]))
+    ret[rank] = dict(bad=compare(mine, ck, cs, cw), n=len(ck), expected=len(mine), sent=sent, received=received, shared=len(shared))
+    dist.destroy_process_group()
+
+
+def test_merge_maps_world2_with_the_library_on_the_cpu_model():
+    """plvs_b200.parallel.merge_maps end to end in two processes over gloo: export kernel -> owner routing -> all-to-all -> merge kernels, with the library's
+    translation units on the CPU execution model (tests/native/cuda_emu.hpp); every rank ends up with exactly the blocks it owns, fused as the
+    host-side fold of the two oracle maps says"""
+    from tests.native_build import build_emulated_library
+    build_emulated_library()                                                   # once, before the workers race for it
+    world, port = 2, _free_port()
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    mp.spawn(_merge_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    total = 0
+    for r in range(world):
+        assert ret[r]["bad"] == 0 and ret[r]["n"] == ret[r]["expected"] > 10, ret[r]
+        assert ret[r]["shared"] > 10
+        total += ret[r]["n"]
+    assert sum(ret[r]["sent"] for r in range(world)) == sum(ret[r]["received"] for r in range(world)) >= total
