@@ -216,16 +216,20 @@ def _impl_bow_transform(tmp_path):
 
 # ---- the tests proper: one isolated child per body -----------------------------------------------------------------------------------
 ROOT = pathlib.Path(__file__).resolve().parent.parent
-CHILD_TIMEOUT_S = 240
+CHILD_TIMEOUT_S = 120
+_timed_out = []              # once a child had to be killed, the remaining bodies are not started: the whole file then costs one time limit, not seven
 
 
 def _isolated(name, *args):
+    if _timed_out:
+        pytest.fail("not started: %s did not finish within its time limit" % _timed_out[0])
     code = "import sys; sys.path.insert(0, %r); import pathlib; from tests import test_zz_gpu_unverified as t; t.%s(%s)" % (
         str(ROOT), name, ", ".join("pathlib.Path(%r)" % str(a) for a in args))
     try:
         r = subprocess.run([sys.executable, "-c", code], cwd=str(ROOT), capture_output=True, text=True, timeout=CHILD_TIMEOUT_S,
                            env=dict(os.environ, PYTHONFAULTHANDLER="1"))
     except subprocess.TimeoutExpired:
+        _timed_out.append(name)
         pytest.fail("%s did not finish within %d s (child killed)" % (name, CHILD_TIMEOUT_S))
     assert r.returncode == 0, "%s: exit %d\n%s\n%s" % (name, r.returncode, r.stdout[-2000:], r.stderr[-4000:])
 
