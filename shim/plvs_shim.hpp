@@ -127,8 +127,27 @@ public:
         pyramidFresh_ = true;
     }
 
+    // void PrecomputeGaussianPyramid(const cv::Mat& image)  (include/ORBextractor.h:116, src/ORBextractor.cc:1401-1427): the line-feature front end
+    // calls it to get mvImagePyramid and mvImagePyramidFiltered (each level cloned and blurred 7x7, sigma 2) before operator().  Both pyramids
+    // are by-products of the device extraction, so this runs one extraction (keypoints discarded) and mirrors them; the following operator() on the
+    // same image repeats the device work (about the cost the reference saves by its flag) and returns identical results.
+    void PrecomputeGaussianPyramid(const cv::Mat& image)
+    {
+        if (image.empty()) return;
+        const int cap = 2 * nfeatures + 64 * nlevels;
+        std::vector<cv::KeyPoint> kps(cap);
+        cv::Mat desc(cap, 32, CV_8U);
+        int n = 0, mono = 0;
+        plvs_shim::check(plvs_orb_extract(h_, image.data, image.cols, image.rows, (int)image.step, 0, 0, 0, reinterpret_cast<plvs_keypoint*>(kps.data()), desc.data, cap,
+                                          &n, &mono), "plvs_orb_extract");
+        SyncImagePyramid(false);
+        SyncImagePyramid(true);
+        mbPrecomputedGaussianPyramid = true;
+    }
+
     std::vector<cv::Mat> mvImagePyramid;
     std::vector<cv::Mat> mvImagePyramidFiltered;
+    bool mbPrecomputedGaussianPyramid = false;
     plvs_orb* handle() { return h_; }
 
 protected:

@@ -71,6 +71,7 @@ extern "C" int shim_instantiate(int run)
     cv::Mat img(480, 640, CV_8U), desc; std::vector<cv::KeyPoint> kps; std::vector<int> lap{0, 0};
     int mono = ex(img, cv::Mat(), kps, desc, lap);
     ex.SyncImagePyramid();
+    ex.PrecomputeGaussianPyramid(img);
     PLVS2::ORBmatcher m(0.8f, true);
     Frame F, L; std::vector<MapPointPtr> mps;
     int a = m.SearchByProjection(F, mps, 3.f, false, 50.f);
