@@ -388,3 +388,22 @@ def test_memcheck_on_the_cpu_model(tmp_path):
             "'_impl_undistort_keypoints_on_device')]; Z._impl_bow_transform(pathlib.Path(%r)); print('clean')" % str(tmp_path))
     ok = subprocess.run([sys.executable, "-c", pre + body], capture_output=True, text=True, env=env, cwd=str(ROOT), timeout=1200)
     assert ok.returncode == 0 and "clean" in ok.stdout, ok.stderr[-3000:]
+
+
+def test_image_pyramids_of_the_extractor_on_the_cpu_model(product_bound_to_emulated_units):
+    """mvImagePyramid / mvImagePyramidFiltered as ORBextractor::PrecomputeGaussianPyramid leaves them (src/ORBextractor.cc:1401-1427): every level of the
+    device pyramid == cv2.resize chain, every filtered level == the 7x7 sigma-2 blur of that level's clone (the oracle's gauss7, pinned to cv2)"""
+    from plvs_b200.orb import ORBextractor
+    img = synth.gray_frame(2, 480, 360)
+    ex = ORBextractor(800, 1.2, 8, 20, 7)
+    ex(img)
+    tab = O.Tables(800)
+    pyr = O.pyramid_cv2(img, tab)
+    for l in range(8):
+        h, w = pyr[l].shape
+        got = ex.pyramid_level(l, blurred=0)
+        flt = ex.pyramid_level(l, blurred=1)
+        assert got.shape == flt.shape
+        oy, ox = (got.shape[0] - h) // 2, (got.shape[1] - w) // 2            # the device levels may carry their border
+        assert np.array_equal(got[oy:oy + h, ox:ox + w], pyr[l]), l
+        assert np.array_equal(flt[oy:oy + h, ox:ox + w], O.gauss7(pyr[l])), l
