@@ -123,6 +123,19 @@ int ref_tsdf_integrate(void* h, const float* depth, int w, int ht, const uint8_t
     return 0;
 }
 
+static const uint32_t* g_kfids = nullptr;
+static uint32_t g_kfid_all = 0;
+
+int ref_tsdf_integrate_cloud(void* h, const float* xyz, const float* rgb, int n, const float* depth, int w, int ht, const float* Twc);
+// the same with the cloud's keyframe ids (PointCloud::GetKfids): kfids[n], or NULL for one id for every point
+int ref_tsdf_integrate_cloud_kf(void* h, const float* xyz, const float* rgb, const uint32_t* kfids, uint32_t kfid_all, int n, const float* depth, int w, int ht, const float* Twc)
+{
+    g_kfids = kfids; g_kfid_all = kfid_all;
+    const int rc = ref_tsdf_integrate_cloud(h, xyz, rgb, n, depth, w, ht, Twc);
+    g_kfids = nullptr; g_kfid_all = 0;
+    return rc;
+}
+
 int ref_tsdf_integrate_cloud(void* h, const float* xyz, const float* rgb, int n, const float* depth, int w, int ht, const float* Twc)
 {
     Ref* r = (Ref*)h;
@@ -130,7 +143,7 @@ int ref_tsdf_integrate_cloud(void* h, const float* xyz, const float* rgb, int n,
     for (int i = 0; i < n; ++i) {
         cloud.AddPoint(chisel::Vec3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
         cloud.AddColor(rgb ? chisel::Vec3(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]) : chisel::Vec3(0.f, 0.f, 0.f));
-        cloud.GetMutableKfids().push_back(0u);
+        cloud.GetMutableKfids().push_back(g_kfids ? g_kfids[i] : g_kfid_all);
     }
     std::shared_ptr<chisel::DepthImage<float>> d;
     if (depth) { d.reset(new chisel::DepthImage<float>(w, ht)); std::memcpy(d->GetMutableData(), depth, sizeof(float) * (size_t)w * ht); }
@@ -225,6 +238,33 @@ int ref_tsdf_save_ply(void* h, const char* path)
     int status = 0;
     waitpid(pid, &status, 0);
     return status;
+}
+
+// DistVoxel::GetKfid of every voxel, chunks in the order of ref_tsdf_download
+int ref_tsdf_download_kfid(void* h, uint32_t* kfid, int cap)
+{
+    Ref* r = (Ref*)h;
+    std::map<std::tuple<int, int, int>, chisel::ChunkPtr> ord;
+    for (auto& kv : r->map->GetChunkManager().GetChunks()) ord[{kv.first(0), kv.first(1), kv.first(2)}] = kv.second;
+    int n = 0;
+    for (auto& kv : ord) {
+        if (n >= cap) break;
+        for (int i = 0; i < 4096; ++i) kfid[(size_t)n * 4096 + i] = kv.second->GetDistVoxel(i).GetKfid();
+        ++n;
+    }
+    return (int)ord.size();
+}
+
+// Mesh::kfids of the non-empty meshes, concatenated in the order of ref_tsdf_mesh_download
+int ref_tsdf_extract_mesh_kfids(void* h, uint32_t* kfids, long cap_verts)
+{
+    Ref* r = (Ref*)h;
+    std::map<std::tuple<int, int, int>, chisel::MeshPtr> ord;
+    for (auto& kv : r->map->GetChunkManager().GetAllMeshes())
+        if (kv.second && !kv.second->vertices.empty()) ord[{kv.first(0), kv.first(1), kv.first(2)}] = kv.second;
+    long nv = 0;
+    for (auto& kv : ord) for (size_t i = 0; i < kv.second->vertices.size(); ++i) { if (nv < cap_verts) kfids[nv] = kv.second->kfids[i]; ++nv; }
+    return (int)ord.size();
 }
 
 }  // extern "C"

@@ -95,6 +95,42 @@ def _mesh_call(fn, h):
     return keys, counts, V, N, Cc
 
 
+def _integrate_cloud_kf(self, xyz, rgb, Twc, depth=None, kfids=None, kfid=0):
+    """Chisel::IntegratePointCloudWidthDepth with the cloud's keyframe ids: kfids [n] uint32, or one id for every point"""
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    T = np.ascontiguousarray(Twc, np.float32).reshape(12)
+    rgb = None if rgb is None else np.ascontiguousarray(rgb, np.float32)
+    d = None if depth is None else np.ascontiguousarray(depth, np.float32)
+    kf = None if kfids is None else np.ascontiguousarray(kfids, np.uint32)
+    fn = self._l.orc_tsdf_integrate_cloud_kf
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    rc = fn(self._h, p(xyz), p(rgb), p(kf), int(kfid), len(xyz), p(d), d.shape[1] if d is not None else 0, d.shape[0] if d is not None else 0, p(T))
+    assert rc == 0
+
+
+def _download_kfid(self):
+    n = self._l.orc_tsdf_download(self._h, None, None, None, None, 0)
+    out = np.zeros((n, 4096), np.uint32)
+    self._l.orc_tsdf_download_kfid.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    if n:
+        self._l.orc_tsdf_download_kfid(self._h, out.ctypes.data_as(C.c_void_p), n)
+    return out
+
+
+def _mesh_kfids(self, n_verts):
+    """Mesh::kfids of the meshes extract_mesh() / meshes() return, per vertex"""
+    out = np.zeros(max(n_verts, 1), np.uint32)
+    self._l.orc_tsdf_extract_mesh_kfids.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+    self._l.orc_tsdf_extract_mesh_kfids(self._h, out.ctypes.data_as(C.c_void_p), n_verts)
+    return out[:n_verts]
+
+
+Map.integrate_cloud_kf = _integrate_cloud_kf
+Map.download_kfid = _download_kfid
+Map.mesh_kfids = _mesh_kfids
+
+
 def _extract_mesh(self):
     """ChunkManager::RecomputeMesh for every chunk of the current map (GenerateMesh + ColorizeMesh + ComputeNormalsFromGradients)."""
     return _mesh_call(self._l.orc_tsdf_extract_mesh, self._h)

@@ -63,7 +63,8 @@ struct KeyHash { size_t operator()(const Key& k) const { return ((size_t)k.x * 7
 struct Block {
     std::vector<float> sdf, w;
     std::vector<uint8_t> rgba;    // r,g,b,colour weight
-    Block() : sdf(4096, 99999.f), w(4096, 0.f), rgba(4096 * 4, 0) {}
+    std::vector<uint32_t> kfid;   // DistVoxel::kfid (DistVoxel.h:64-86,107-117): written by the point-cloud route, zeroed by Reset()
+    Block() : sdf(4096, 99999.f), w(4096, 0.f), rgba(4096 * 4, 0), kfid(4096, 0u) {}
 };
 
 struct Map {
@@ -243,7 +244,7 @@ int orc_tsdf_integrate(void* h, const float* depth, int w, int ht, const uint8_t
                         upd = true;
                     } else if (P.use_carving && s > trunc + P.carving_dist) {
                         if (B.w[i] > 0 && B.sdf[i] < 1e-5) {
-                            if (mode == 1) { B.sdf[i] = 99999.f; B.w[i] = 0.f; }         // Reset()
+                            if (mode == 1) { B.sdf[i] = 99999.f; B.w[i] = 0.f; B.kfid[i] = 0u; }         // Reset()
                             else { const float ow = B.w[i], os = B.sdf[i]; B.sdf[i] = (ow * os + 1.5f * 0.0f) / (1.5f + ow); B.w[i] = ow + 1.5f; }   // Carve()
                             upd = true;
                         }
@@ -283,6 +284,17 @@ int orc_tsdf_download(void* h, int32_t* keys, float* sdf, float* weight, uint8_t
     return (int)ord.size();
 }
 
+// DistVoxel::GetKfid of every voxel, blocks in the order of orc_tsdf_download
+int orc_tsdf_download_kfid(void* h, uint32_t* kfid, int cap)
+{
+    Map* m = (Map*)h;
+    std::map<std::tuple<int, int, int>, Block*> ord;
+    for (auto& kv : m->blocks) ord[{kv.first.x, kv.first.y, kv.first.z}] = kv.second.get();
+    int n = 0;
+    for (auto& kv : ord) { if (n >= cap) break; std::memcpy(kfid + (size_t)n * 4096, kv.second->kfid.data(), 4096 * 4); ++n; }
+    return (int)ord.size();
+}
+
 // ---------------------------------------------------------------------------------------------
 // a26: Chisel::IntegratePointCloudWidthDepth (Thirdparty/open_chisel/src/Chisel.cpp:382-585) -- PLVS's default
 // Chisel route (src/PointCloudMapping.cc:641-642): (i) ProjectionIntegrator::CarveWithDepth over the existing chunks
@@ -301,6 +313,19 @@ static float intbound(float s, int ds)
     if (ds < 0) return intbound(-s, -ds);
     s = mod1(s, 1.f);
     return (1 - s) / ds;
+}
+
+static const uint32_t* g_cloud_kfids = nullptr;      // per-point keyframe ids of the cloud being integrated (cloud.GetKfids(), src/Chisel.cpp:470)
+static uint32_t g_cloud_kfid_all = 0;
+
+int orc_tsdf_integrate_cloud(void* h, const float* xyz, const float* rgb, int n, const float* depth, int w, int ht, const float* Twc);
+// the same with keyframe ids: kfids[n], or NULL for one id for the whole cloud
+int orc_tsdf_integrate_cloud_kf(void* h, const float* xyz, const float* rgb, const uint32_t* kfids, uint32_t kfid_all, int n, const float* depth, int w, int ht, const float* Twc)
+{
+    g_cloud_kfids = kfids; g_cloud_kfid_all = kfid_all;
+    const int rc = orc_tsdf_integrate_cloud(h, xyz, rgb, n, depth, w, ht, Twc);
+    g_cloud_kfids = nullptr; g_cloud_kfid_all = 0;
+    return rc;
 }
 
 int orc_tsdf_integrate_cloud(void* h, const float* xyz, const float* rgb, int n, const float* depth, int w, int ht, const float* Twc)
@@ -341,7 +366,7 @@ int orc_tsdf_integrate_cloud(void* h, const float* xyz, const float* rgb, int n,
                 if (std::isnan(d)) continue;
                 const float trunc = std::max((P.trunc_quad * d * d + P.trunc_linear * d + P.trunc_const) * P.trunc_scale, diagD);
                 const float s = d - pc.z;
-                if (s > trunc + P.carving_dist && B.sdf[i] < 1e-5) { B.sdf[i] = 99999.f; B.w[i] = 0.f; upd = true; }
+                if (s > trunc + P.carving_dist && B.sdf[i] < 1e-5) { B.sdf[i] = 99999.f; B.w[i] = 0.f; B.kfid[i] = 0u; upd = true; }
             }
             n_carved += upd;
         }
@@ -416,6 +441,7 @@ int orc_tsdf_integrate_cloud(void* h, const float* xyz, const float* rgb, int n,
                 const float ow = B.w[id], os = B.sdf[id];
                 B.sdf[id] = (ow * os + weight * u) / (weight + ow);
                 B.w[id] = ow + weight;
+                B.kfid[id] = g_cloud_kfids ? g_cloud_kfids[i] : g_cloud_kfid_all;         // distVoxel.SetKfid(kfid) (src/Chisel.cpp:534)
                 if (rgb) {
                     uint8_t* cv = &B.rgba[(size_t)id * 4];
                     if (!(cv[3] >= 255 - 1)) {
@@ -560,13 +586,15 @@ struct MeshCtx {
     }
 };
 
-void mesh_voxel(const MeshCtx& c, const Key& key, const Block* blk, int ix, int iy, int iz, bool border, std::vector<V3>& verts, std::vector<V3>& normals)
+void mesh_voxel(const MeshCtx& c, const Key& key, const Block* blk, int ix, int iy, int iz, bool border, std::vector<V3>& verts, std::vector<V3>& normals,
+                std::vector<uint32_t>& kfids)
 {
     const float res = c.res;
     const V3 halfVoxel = V3{res, res, res} * 0.5f;
     const V3 centroid = V3{(float)ix, (float)iy, (float)iz} * res + halfVoxel;
     const V3 coords = centroid + MeshCtx::origin(key, res);
     V3 cc[8]; float sdf[8];
+    uint32_t corner_kfid = 0;            // USE_KFID_VERTICES == 0: the cube takes the keyframe id of its first corner (ChunkManager.cpp:464-468)
     for (int i = 0; i < 8; ++i) {
         int x = ix + kCubeOff[i][0], y = iy + kCubeOff[i][1], z = iz + kCubeOff[i][2];
         const Block* b = blk;
@@ -582,6 +610,7 @@ void mesh_voxel(const MeshCtx& c, const Key& key, const Block* blk, int ix, int 
         if (b->w[id] <= 1e-15) return;
         cc[i] = coords + V3{(float)kCubeOff[i][0] * res, (float)kCubeOff[i][1] * res, (float)kCubeOff[i][2] * res};
         sdf[i] = b->sdf[id];
+        if (i == 0) corner_kfid = b->kfid[id];
     }
     int cfg = 0;
     for (int i = 0; i < 8; ++i) if (sdf[i] < 0) cfg |= 1 << i;
@@ -604,6 +633,7 @@ void mesh_voxel(const MeshCtx& c, const Key& key, const Block* blk, int ix, int 
         if (sq > 0.f) { const float s = std::sqrt(sq); n = V3{n.x / s, n.y / s, n.z / s}; }
         verts.push_back(p0); verts.push_back(p1); verts.push_back(p2);
         normals.push_back(n); normals.push_back(n); normals.push_back(n);
+        kfids.push_back(corner_kfid); kfids.push_back(corner_kfid); kfids.push_back(corner_kfid);
     }
 }
 
@@ -614,6 +644,19 @@ extern "C" {
 // meshes of all chunks in (x,y,z) key order; chunks without triangles are left out like ChunkManager::RecomputeMesh does (:165-167).
 // keys[3*i], counts[i] = vertices of mesh i; verts / normals / colors = 3 floats per vertex, concatenated.  Returns the number of
 // meshes, *total_verts the number of vertices; arrays may be null (counting pass) and are filled up to the caps.
+static uint32_t* g_mesh_kfids = nullptr;          // optional per-vertex keyframe ids of the next orc_tsdf_extract_mesh (Mesh::kfids)
+
+int orc_tsdf_extract_mesh(void* h, int32_t* keys, int32_t* counts, int cap_meshes, float* verts, float* normals, float* colors, long cap_verts, long* total_verts);
+int orc_tsdf_extract_mesh_kfids(void* h, uint32_t* kfids, long cap_verts)
+{
+    g_mesh_kfids = kfids;
+    long total = 0;
+    std::vector<float> dummy;
+    const int nm = orc_tsdf_extract_mesh(h, nullptr, nullptr, 0, nullptr, nullptr, nullptr, cap_verts, &total);
+    g_mesh_kfids = nullptr;
+    return nm;
+}
+
 int orc_tsdf_extract_mesh(void* h, int32_t* keys, int32_t* counts, int cap_meshes, float* verts, float* normals, float* colors, long cap_verts, long* total_verts)
 {
     Map* m = (Map*)h;
@@ -622,14 +665,15 @@ int orc_tsdf_extract_mesh(void* h, int32_t* keys, int32_t* counts, int cap_meshe
     for (auto& kv : m->blocks) ord[{kv.first.x, kv.first.y, kv.first.z}] = kv.second.get();
     int nm = 0; long nv = 0;
     std::vector<V3> V, N;
+    std::vector<uint32_t> Kf;
     for (auto& kv : ord) {
         const Key key{std::get<0>(kv.first), std::get<1>(kv.first), std::get<2>(kv.first)};
         const Block* b = kv.second;
-        V.clear(); N.clear();
-        for (int z = 0; z < 15; ++z) for (int y = 0; y < 15; ++y) for (int x = 0; x < 15; ++x) mesh_voxel(c, key, b, x, y, z, false, V, N);
-        for (int z = 0; z < 15; ++z) for (int y = 0; y < 16; ++y) mesh_voxel(c, key, b, 15, y, z, true, V, N);
-        for (int z = 0; z < 15; ++z) for (int x = 0; x < 15; ++x) mesh_voxel(c, key, b, x, 15, z, true, V, N);
-        for (int y = 0; y < 16; ++y) for (int x = 0; x < 16; ++x) mesh_voxel(c, key, b, x, y, 15, true, V, N);
+        V.clear(); N.clear(); Kf.clear();
+        for (int z = 0; z < 15; ++z) for (int y = 0; y < 15; ++y) for (int x = 0; x < 15; ++x) mesh_voxel(c, key, b, x, y, z, false, V, N, Kf);
+        for (int z = 0; z < 15; ++z) for (int y = 0; y < 16; ++y) mesh_voxel(c, key, b, 15, y, z, true, V, N, Kf);
+        for (int z = 0; z < 15; ++z) for (int x = 0; x < 15; ++x) mesh_voxel(c, key, b, x, 15, z, true, V, N, Kf);
+        for (int y = 0; y < 16; ++y) for (int x = 0; x < 16; ++x) mesh_voxel(c, key, b, x, y, 15, true, V, N, Kf);
         if (V.empty()) continue;
         if (nm < cap_meshes) {
             if (keys) { keys[3 * nm] = key.x; keys[3 * nm + 1] = key.y; keys[3 * nm + 2] = key.z; }
@@ -641,6 +685,7 @@ int orc_tsdf_extract_mesh(void* h, int32_t* keys, int32_t* counts, int cap_meshe
             V3 n = N[i];
             c.gradient_normal(V[i], &n);
             if (nv < cap_verts) {
+                if (g_mesh_kfids) g_mesh_kfids[nv] = Kf[i];
                 if (verts) { verts[3 * nv] = V[i].x; verts[3 * nv + 1] = V[i].y; verts[3 * nv + 2] = V[i].z; }
                 if (normals) { normals[3 * nv] = n.x; normals[3 * nv + 1] = n.y; normals[3 * nv + 2] = n.z; }
                 if (colors) { colors[3 * nv] = col.x; colors[3 * nv + 1] = col.y; colors[3 * nv + 2] = col.z; }

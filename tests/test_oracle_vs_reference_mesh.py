@@ -123,3 +123,30 @@ def test_ply_writer_against_the_reference_file(tmp_path, color):
     assert oh == rh and of == rf and len(ov) == len(V) > 3000
     tri = lambda v: sorted(tuple(v[i:i + 3]) for i in range(0, len(v), 3))
     assert tri(ov) == tri(rv)
+
+
+def test_keyframe_ids_of_voxels_and_mesh_vertices():
+    """DistVoxel::kfid (set by the point-cloud route per integrated point, zeroed by Reset) and Mesh::kfids (the cube's first corner): oracle == compiled
+    reference, with one id per cloud and with per-point ids"""
+    from plvs_b200 import scenario
+    w, h = 160, 120
+    K = synth.intrinsics(w, h)
+    o, r = _pair(w, h, voxel_resolution=0.04, use_carving=1, carving_dist=0.05, near_plane=0.1, far_plane=4.0, max_blocks=8192, use_color=1)
+    rng = np.random.default_rng(7)
+    for step, f in enumerate((0, 1, 3, 6)):
+        d = synth.depth_frame(f, w, h) + np.float32(0.15 * step)         # the surface retreats: carving resets voxels (kfid back to 0)
+        c = synth.bgr_frame(f, w, h)
+        xyz, rgb = scenario.cloud_from_depth(d, c, K, step=2)
+        kfids = None if step % 2 == 0 else rng.integers(1, 50, len(xyz)).astype(np.uint32)
+        for m in (o, r):
+            m.integrate_cloud_kf(xyz, rgb, synth.pose(f), d, kfids=kfids, kfid=100 + f)
+        ko, kr = o.download_kfid(), r.download_kfid()
+        assert np.array_equal(o.download()[0], r.download()[0]) and np.array_equal(ko, kr)
+        assert (ko > 0).sum() > 1000
+        r.update_meshes()
+        mo, mr = o.extract_mesh(), r.meshes()
+        _same(mo, mr)
+        assert np.array_equal(o.mesh_kfids(len(mo[2])), r.mesh_kfids(len(mr[2])))
+    wts = o.download()[2]
+    assert ((ko > 0) <= (wts > 0)).all()                                 # a keyframe id only on observed voxels: Reset clears both
+    assert len(np.unique(ko)) > 10
