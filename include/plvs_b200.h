@@ -487,6 +487,17 @@ int plvs_tsdf_update_meshes(plvs_tsdf* h, int* n_meshes, long long* n_verts);
 int plvs_tsdf_get_meshes(plvs_tsdf* h, int32_t* keys, int32_t* counts, int cap_meshes, float* verts, float* normals, float* colors,
                          long long cap_verts, int on_device);
 
+/* Keyframe ids (DistVoxel::kfid, Thirdparty/open_chisel/include/open_chisel/DistVoxel.h:64-86; Mesh::kfids): the point-cloud route stamps every voxel it
+ * integrates with the id of the point's keyframe (src/Chisel.cpp:470,534), Reset() clears it, and every mesh vertex carries the id of its cube's first
+ * corner (ChunkManager.cpp:464-468) -- what ChunkManager::Deform keys on.  plvs_tsdf_integrate_cloud_kf = plvs_tsdf_integrate_cloud with
+ * cloud.GetKfids(): kfids[n], or NULL for kfid_all on every point.  plvs_tsdf_download_kfid: per-voxel ids in the block order of
+ * plvs_tsdf_download_blocks (kfid may be NULL to size).  plvs_tsdf_get_mesh_kfids: one id per vertex of the last plvs_tsdf_update_meshes.
+ * The depth-scan route never writes ids; a voxel that route resets and re-integrates keeps the id of its last cloud here (0 in the reference). */
+int plvs_tsdf_integrate_cloud_kf(plvs_tsdf* h, const float* xyz, const float* rgb, const uint32_t* kfids, uint32_t kfid_all, int n,
+                                 const float* depth, int w, int h_, const float Twc[12]);
+int plvs_tsdf_download_kfid(plvs_tsdf* h, uint32_t* kfid, int cap, int* n_out);
+int plvs_tsdf_get_mesh_kfids(plvs_tsdf* h, uint32_t* kfids, long long cap_verts, int on_device);
+
 /* ChiselServer::SaveMesh -> Chisel::SaveAllMeshesToPLY (Thirdparty/open_chisel/src/Chisel.cpp:79-118, src/io/PLY.cpp:29-86): the vertices (and colours,
  * or NULL for a map without colour) that plvs_tsdf_get_meshes returned, as the reference's ASCII PLY.  Host I/O only. */
 int plvs_mesh_save_ply(const char* path, const float* verts, const float* colors, long long n_verts);

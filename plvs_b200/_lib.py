@@ -143,6 +143,9 @@ def declare(lib):
     lib.plvs_voc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(C.c_int)] + [C.c_void_p] * 3 + \
         [C.POINTER(C.c_int), C.c_void_p]
     lib.plvs_bow_vector.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    lib.plvs_tsdf_integrate_cloud_kf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.plvs_tsdf_download_kfid.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.plvs_tsdf_get_mesh_kfids.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]
     lib.plvs_mesh_save_ply.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_longlong]
     lib.plvs_tsdf_update_meshes.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
     lib.plvs_tsdf_get_meshes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]

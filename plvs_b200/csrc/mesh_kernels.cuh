@@ -101,7 +101,7 @@ k_mesh_count(const int* __restrict__ list, const int* __restrict__ block_key, co
 __global__ void __launch_bounds__(256)
 k_mesh_emit(const int* __restrict__ list, const int* __restrict__ block_key, const HashEntry* __restrict__ tab, uint32_t mask,
             const float* __restrict__ sdf_pool, const float* __restrict__ w_pool, const long long* __restrict__ vert_base, MeshParams M,
-            float* __restrict__ verts, float* __restrict__ normals)
+            float* __restrict__ verts, float* __restrict__ normals, const uint32_t* __restrict__ kfid_pool, uint32_t* __restrict__ vert_kfid)
 {
     __shared__ int s_nb[8];
     __shared__ int s_warp[8];
@@ -156,6 +156,8 @@ k_mesh_emit(const int* __restrict__ list, const int* __restrict__ block_key, con
                 else { const float t = sa / diff; ex[e] = ax + (bx - ax) * t; ey[e] = ay + (by - ay) * t; ez[e] = az + (bz - az) * t; }
             }
         }
+        // Mesh::kfids: every vertex of the cube carries the keyframe id of the cube's first corner, i.e. of this voxel (ChunkManager.cpp:464-468)
+        const uint32_t cube_kfid = (vert_kfid && kfid_pool) ? kfid_pool[(size_t)b * kBlockVox + ((z * 16 + y) * 16 + x)] : 0u;
         for (int t = 0; t < ntri; ++t) {
             const int e0 = (int)(row >> (4 * (3 * t + 2))) & 15, e1 = (int)(row >> (4 * (3 * t + 1))) & 15, e2 = (int)(row >> (4 * (3 * t))) & 15;
             const float p0x = ex[e0], p0y = ey[e0], p0z = ez[e0], p1x = ex[e1], p1y = ey[e1], p1z = ez[e1], p2x = ex[e2], p2y = ey[e2], p2z = ez[e2];
@@ -166,6 +168,7 @@ k_mesh_emit(const int* __restrict__ list, const int* __restrict__ block_key, con
             float* V = verts + 3 * v; float* N = normals + 3 * v;
             V[0] = p0x; V[1] = p0y; V[2] = p0z; V[3] = p1x; V[4] = p1y; V[5] = p1z; V[6] = p2x; V[7] = p2y; V[8] = p2z;
             N[0] = nx; N[1] = ny; N[2] = nz; N[3] = nx; N[4] = ny; N[5] = nz; N[6] = nx; N[7] = ny; N[8] = nz;
+            if (vert_kfid) { vert_kfid[v] = cube_kfid; vert_kfid[v + 1] = cube_kfid; vert_kfid[v + 2] = cube_kfid; }
             v += 3;
         }
     }

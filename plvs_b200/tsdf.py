@@ -97,6 +97,36 @@ class ChiselServer:
                                                  d.shape[1] if d is not None else 0, d.shape[0] if d is not None else 0, T.ctypes.data_as(C.c_void_p))
         _lib.check(rc, "plvs_tsdf_integrate_cloud")
 
+    def integrate_cloud_kf(self, xyz, rgb, Twc, depth=None, kfids=None, kfid=0):
+        """integrate_cloud with the cloud's keyframe ids (PointCloud::GetKfids): kfids [n] uint32, or one id for every point"""
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        T = np.ascontiguousarray(Twc, np.float32).reshape(12)
+        rgb = None if rgb is None else np.ascontiguousarray(rgb, np.float32)
+        d = None if depth is None else np.ascontiguousarray(depth, np.float32)
+        kf = None if kfids is None else np.ascontiguousarray(kfids, np.uint32)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        rc = self._lib.plvs_tsdf_integrate_cloud_kf(self._h, p(xyz), p(rgb), p(kf), int(kfid), len(xyz), p(d), d.shape[1] if d is not None else 0,
+                                                    d.shape[0] if d is not None else 0, p(T))
+        _lib.check(rc, "plvs_tsdf_integrate_cloud_kf")
+
+    def download_kfid(self):
+        """DistVoxel::GetKfid of every voxel, blocks sorted like download()"""
+        n = C.c_int()
+        _lib.check(self._lib.plvs_tsdf_download_kfid(self._h, None, 0, C.byref(n)), "plvs_tsdf_download_kfid")
+        n = n.value
+        keys = np.zeros((n, 3), np.int32); out = np.zeros((n, 4096), np.uint32); m = C.c_int()
+        if n:
+            _lib.check(self._lib.plvs_tsdf_download_blocks(self._h, keys.ctypes.data_as(C.c_void_p), None, None, None, n, C.byref(m)), "plvs_tsdf_download_blocks")
+            _lib.check(self._lib.plvs_tsdf_download_kfid(self._h, out.ctypes.data_as(C.c_void_p), n, C.byref(m)), "plvs_tsdf_download_kfid")
+        return out[np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))]
+
+    def mesh_kfids(self):
+        """Mesh::kfids of the meshes GetMeshes() returns, per vertex"""
+        nm, nv = getattr(self, "_mesh_sizes", None) or self.UpdateMesh()
+        out = np.zeros(max(nv, 1), np.uint32)
+        _lib.check(self._lib.plvs_tsdf_get_mesh_kfids(self._h, out.ctypes.data_as(C.c_void_p), nv, 0), "plvs_tsdf_get_mesh_kfids")
+        return out[:nv]
+
     def stats(self):
         s = _lib.TsdfStats()
         _lib.check(self._lib.plvs_tsdf_last_stats(self._h, C.byref(s)), "plvs_tsdf_last_stats")

@@ -48,6 +48,10 @@ template <class Sim3T> inline auto se3_of_sim3(const Sim3T& Scw) { return standi
 template <class P> auto point_rgb_impl(const P& pt, float k, float* out, int) -> decltype((void)pt.r, true) { out[0] = pt.r * k; out[1] = pt.g * k; out[2] = pt.b * k; return true; }
 template <class P> bool point_rgb_impl(const P&, float, float*, long) { return false; }
 template <class P> bool point_rgb(const P& pt, float k, float* out) { return point_rgb_impl(pt, k, out, 0); }
+// keyframe id of a cloud point, when the point type has one (PclPointCloudToChisel fills PointCloud::kfids from it, Conversions.h)
+template <class P> auto point_kfid_impl(const P& pt, uint32_t* out, int) -> decltype((void)pt.kfid, true) { *out = (uint32_t)pt.kfid; return true; }
+template <class P> bool point_kfid_impl(const P&, uint32_t*, long) { return false; }
+template <class P> bool point_kfid(const P& pt, uint32_t* out) { return point_kfid_impl(pt, out, 0); }
 // normals / alpha of an output point, when the point type has them (the reference selects GetPointCloud overloads on these fields)
 template <class P> auto point_set_normal_impl(P& pt, const float* n, int) -> decltype((void)pt.normal_x, void()) { pt.normal_x = n[0]; pt.normal_y = n[1]; pt.normal_z = n[2]; }
 template <class P> void point_set_normal_impl(P&, const float*, long) {}
@@ -838,14 +842,17 @@ public:
         const size_t n = cloud_camera.points.size();
         cloudXyz_.resize(3 * n);
         cloudRgb_.resize(useColor && useColorCloud_ ? 3 * n : 0);
+        cloudKfid_.assign(n, 0u); bool hasKfid = n > 0;
         const float byteToFloat = 1.0f / 255.0f;
         size_t i = 0;
         for (const auto& pt : cloud_camera.points) {
             cloudXyz_[3 * i] = pt.x; cloudXyz_[3 * i + 1] = pt.y; cloudXyz_[3 * i + 2] = pt.z;
             if (!cloudRgb_.empty() && !plvs_shim::point_rgb(pt, byteToFloat, &cloudRgb_[3 * i])) { cloudRgb_.clear(); useColorCloud_ = false; }
+            if (hasKfid && !plvs_shim::point_kfid(pt, &cloudKfid_[i])) hasKfid = false;
             ++i;
         }
         for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) cloudTwc_[4 * r + c] = Twc.linear()(r, c); cloudTwc_[4 * r + 3] = Twc.translation()(r); }
+        if (!hasKfid) cloudKfid_.clear();
         gotCloudPose = true;
     }
     // ChiselServer::IntegrateLastPointCloud (ChiselServer.cpp:664-705) -> Chisel::IntegratePointCloudWidthDepth: the carve pass
@@ -854,6 +861,11 @@ public:
     {
         if (!gotCloudPose) { std::fprintf(stderr, "ChiselServer - PROBLEM in integrating point cloud!!! ************\n"); return; }
         const bool with_depth = gotInfo && depth_;
+        if (!cloudKfid_.empty())         // the cloud's points carry keyframe ids: they are stamped on the voxels like PointCloud::kfids (src/Chisel.cpp:470,534)
+            plvs_shim::check(plvs_tsdf_integrate_cloud_kf(h_, cloudXyz_.data(), cloudRgb_.empty() ? nullptr : cloudRgb_.data(), cloudKfid_.data(), 0u,
+                                                          (int)(cloudXyz_.size() / 3), with_depth ? depth_ : nullptr, with_depth ? dw_ : 0, with_depth ? dh_ : 0, cloudTwc_),
+                             "plvs_tsdf_integrate_cloud_kf");
+        else
         plvs_shim::check(plvs_tsdf_integrate_cloud(h_, cloudXyz_.data(), cloudRgb_.empty() ? nullptr : cloudRgb_.data(), (int)(cloudXyz_.size() / 3),
                                                    with_depth ? depth_ : nullptr, with_depth ? dw_ : 0, with_depth ? dh_ : 0, cloudTwc_), "plvs_tsdf_integrate_cloud");
     }
@@ -868,6 +880,7 @@ protected:
     float* depth_ = nullptr; int dw_ = 0, dh_ = 0;
     const uint16_t* depth16_ = nullptr; int dstep16_ = 0; float dfactor_ = 1.0f;
     int nMeshes_ = 0; long long nMeshVerts_ = 0; std::vector<float> meshV_, meshN_, meshC_;
+    std::vector<uint32_t> cloudKfid_;
     unsigned char* color_ = nullptr; int cw_ = 0, ch_ = 0, cstep_ = 0, cn_ = 0;
     plvs_tsdf* h_ = nullptr;
 };

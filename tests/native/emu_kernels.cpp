@@ -141,7 +141,7 @@ int emu_update_meshes(int nb, const int32_t* block_key, const float* sdf_pool, c
         if (!verts || nv == 0) return nm;
         if (cap_verts < nv) return -2;
         const MeshParams M{res, 1.f / res, 0.5f * res, 1.0f / ((float)16 * res), use_color};
-        emu::launch(dim3(nb), dim3(256), 0, [&] { k_mesh_emit(list.data(), block_key, tab.data(), mask, sdf_pool, w_pool, base.data(), M, verts, normals); });
+        emu::launch(dim3(nb), dim3(256), 0, [&] { k_mesh_emit(list.data(), block_key, tab.data(), mask, sdf_pool, w_pool, base.data(), M, verts, normals, nullptr, nullptr); });
         emu::launch(dim3((unsigned)((nv + 255) / 256)), dim3(256), 0, [&] {
             k_mesh_shade(nv, tab.data(), mask, block_key, sdf_pool, w_pool, rgba_pool, M, verts, normals, colors); });
         return nm;

@@ -108,6 +108,9 @@ extern "C" int shim_instantiate(int run)
     // a26: SetPointCloud + IntegrateLastPointCloud with a coloured and a colourless PCL-like cloud
     struct PointXYZRGBA { float x, y, z; unsigned char b, g, r, a; };
     struct PointXYZ { float x, y, z; };
+    struct PointKf { float x, y, z; unsigned char b, g, r, a; unsigned kfid; };
+    struct CloudK { std::vector<PointKf> points; } ck; ck.points.push_back({0.1f, 0.2f, 1.f, 1, 2, 3, 255, 7u});
+    cs.SetPointCloud(ck, T); cs.IntegrateLastPointCloud(false);
     struct CloudC { std::vector<PointXYZRGBA> points; } cc; cc.points.push_back({0.1f, 0.2f, 1.f, 1, 2, 3, 255});
     struct CloudP { std::vector<PointXYZ> points; } cp; cp.points.push_back({0.1f, 0.2f, 1.f});
     cs.SetPointCloud(cc, T); cs.IntegrateLastPointCloud(false);

@@ -352,7 +352,7 @@ def test_gpu_tests_replayed_on_the_cpu_model(product_bound_to_emulated_units, mo
 
 
 @pytest.mark.parametrize("name", ["_impl_tsdf_from_raw_u16_depth", "_impl_mesh_read_out", "_impl_search_for_initialization", "_impl_search_local_points_resident",
-                                  "_impl_bow_transform", "_impl_undistort_keypoints_on_device", "_impl_reference_goldens"])
+                                  "_impl_bow_transform", "_impl_undistort_keypoints_on_device", "_impl_reference_goldens", "_impl_keyframe_ids"])
 def test_unverified_gpu_tests_replayed_on_the_cpu_model(product_bound_to_emulated_units, tmp_path, name):
     """the bodies of tests/test_zz_gpu_unverified.py (the rows that have not met a GPU), unchanged, against the emulated translation units: entry points,
     host sequencing and kernels of the 16-bit depth path, the mesh read-out, SearchForInitialization, the resident SearchLocalPoints, the BoW
@@ -385,7 +385,7 @@ def test_memcheck_on_the_cpu_model(tmp_path):
     assert bad.returncode != 0 and "in bounds" in bad.stdout and "missed" not in bad.stdout
     body = ("import __graft_entry__ as g, tests.test_zz_gpu_unverified as Z; g.smoke(); "
             "[getattr(Z, n)() for n in ('_impl_tsdf_from_raw_u16_depth', '_impl_mesh_read_out', '_impl_search_for_initialization', '_impl_search_local_points_resident', "
-            "'_impl_undistort_keypoints_on_device')]; Z._impl_bow_transform(pathlib.Path(%r)); print('clean')" % str(tmp_path))
+            "'_impl_undistort_keypoints_on_device', '_impl_keyframe_ids')]; Z._impl_bow_transform(pathlib.Path(%r)); print('clean')" % str(tmp_path))
     ok = subprocess.run([sys.executable, "-c", pre + body], capture_output=True, text=True, env=env, cwd=str(ROOT), timeout=1200)
     assert ok.returncode == 0 and "clean" in ok.stdout, ok.stderr[-3000:]
 

@@ -282,3 +282,34 @@ def _impl_reference_goldens(tmp_path):
 
 def test_reference_goldens(gpu, tmp_path):
     _isolated("_impl_reference_goldens", tmp_path)
+
+
+def _impl_keyframe_ids():
+    """DistVoxel::kfid / Mesh::kfids through the point-cloud route: product == oracle (pinned to the compiled open_chisel), with one id per cloud and
+    with per-point ids, carving resets included; the voxel arrays stay what plvs_tsdf_integrate_cloud gives"""
+    from plvs_b200 import scenario, tsdf as T
+    from oracle import tsdf as OT
+    w, h = 160, 120
+    K = synth.intrinsics(w, h)
+    p = T.default_params(voxel_resolution=0.04, use_carving=1, carving_dist=0.05, near_plane=0.1, far_plane=4.0, max_blocks=8192, use_color=1)
+    g = T.ChiselServer(p); g.SetDepthCameraInfo(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
+    o = OT.Map(p, threads=8); o.set_camera(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
+    rng = np.random.default_rng(7)
+    for step, f in enumerate((0, 1, 3, 6)):
+        d = synth.depth_frame(f, w, h) + np.float32(0.15 * step)
+        c = synth.bgr_frame(f, w, h)
+        xyz, rgb = scenario.cloud_from_depth(d, c, K, step=2)
+        kfids = None if step % 2 == 0 else rng.integers(1, 50, len(xyz)).astype(np.uint32)
+        g.integrate_cloud_kf(xyz, rgb, synth.pose(f), d, kfids=kfids, kfid=100 + f); o.integrate_cloud_kf(xyz, rgb, synth.pose(f), d, kfids=kfids, kfid=100 + f)
+        gk, gs, gw, gc = g.download(); ok, os_, ow, oc = o.download()
+        assert np.array_equal(gk, ok) and np.array_equal(gs.view(np.uint32), os_.view(np.uint32)) and np.array_equal(gw.view(np.uint32), ow.view(np.uint32))
+        assert np.array_equal(g.download_kfid(), o.download_kfid())
+        nm, nv = g.UpdateMesh()
+        assert nv == len(o.extract_mesh()[2]) and np.array_equal(g.mesh_kfids(), o.mesh_kfids(nv))
+    assert (o.download_kfid() > 0).sum() > 1000
+    g.Reset()
+    assert g.download_kfid().size == 0
+
+
+def test_keyframe_ids(gpu):
+    _isolated("_impl_keyframe_ids")
