@@ -8,6 +8,7 @@
 // arrived.  A rendezvous that can never complete (divergent barrier, a shuffle some lane skips) is reported as a deadlock instead of
 // hanging.  Floating point: x86-64 SSE arithmetic is IEEE like the device's with --fmad=false; compile with -ffp-contract=off.
 // Clusters: the CTAs of one cluster are resident together (launch_cluster) and meet at emu::cluster_barrier.
+// Scheduling: round-robin by default; PLVS_EMU_SCHED_SEED=n randomises the order in which thread segments run (a race detector of sorts).
 // Not modelled: distributed shared memory, TMA / mbarrier, tensor cores, memory ordering weaker than sequential consistency, scheduling races.
 #pragma once
 #define PLVS_CUDA_EMU 1
@@ -146,10 +147,19 @@ void launch_cluster(int cluster, dim3 grid, dim3 block, size_t smem_bytes, F&& k
             f.sp = sp;
             g.warps[f.cta * g.warps_per_cta + (t >> 5)].alive |= 1u << (t & 31);
         }
+        // PLVS_EMU_SCHED_SEED=n: instead of round-robin, every sweep visits the live threads in a fresh pseudo-random order and leaves a random
+        // quarter of them out -- between two rendezvous points any interleaving of whole thread segments can then occur, so a missing barrier
+        // (a shared-memory producer / consumer pair that only works in thread order) shows up as a wrong result under some seed
+        static const char* seed_env = std::getenv("PLVS_EMU_SCHED_SEED");
+        uint64_t rng = seed_env ? 0x9E3779B97F4A7C15ull * (uint64_t)(std::atoll(seed_env) + 1) : 0;
+        std::vector<int> order(total);
+        for (int t = 0; t < total; ++t) order[t] = t;
         while (g.alive > 0) {
-            for (int t = 0; t < total && g.alive > 0; ++t) {
-                Fiber& f = g.fibers[t];
+            if (seed_env) for (int t = total - 1; t > 0; --t) { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; std::swap(order[t], order[(size_t)(rng % (uint64_t)(t + 1))]); }
+            for (int k = 0; k < total && g.alive > 0; ++k) {
+                Fiber& f = g.fibers[order[k]];
                 if (f.done) continue;
+                if (seed_env) { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; if ((rng & 3u) == 0) continue; }
                 g.cur = &f;
                 plvs_emu_switch(&g.sched_sp, f.sp);
                 if (g.failure) { const char* why = g.failure; g.failure = nullptr; g.fibers.clear(); throw std::runtime_error(why); }

@@ -16,6 +16,13 @@ namespace {
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
+// a deliberately broken kernel for the model's own test: thread 0 publishes a value, everybody reads it, and the __syncthreads between is missing
+__global__ void k_missing_barrier_demo(int* flag, int* out)
+{
+    if (threadIdx.x == 0) *flag = 42;
+    out[threadIdx.x] = *flag;
+}
+
 ViewDev view_dev(const plvs_frame_view* v)
 {
     ViewDev o;
@@ -164,6 +171,18 @@ int emu_bow_transform(const int32_t* child_off, const int32_t* child_id, const u
         emu::launch(dim3(1), dim3(1024), 0, [&] { k_bow_offsets(sorted_node.data(), &cnt[0], fv_nodes, fv_offsets, &cnt[1]); });
         *n_fv_nodes = cnt[1];
         return cnt[0];
+    } catch (const std::exception& e) { std::fprintf(stderr, "emu: %s\n", e.what()); return -1; }
+}
+
+// the model's own test: how many of 256 threads saw the value thread 0 publishes without a barrier
+int emu_missing_barrier_demo(void)
+{
+    try {
+        int flag = 0; std::vector<int> out(256, -1);
+        emu::launch(dim3(1), dim3(256), 0, [&] { k_missing_barrier_demo(&flag, out.data()); });
+        int seen = 0;
+        for (int v : out) seen += v == 42;
+        return seen;
     } catch (const std::exception& e) { std::fprintf(stderr, "emu: %s\n", e.what()); return -1; }
 }
 

@@ -407,3 +407,23 @@ def test_image_pyramids_of_the_extractor_on_the_cpu_model(product_bound_to_emula
         oy, ox = (got.shape[0] - h) // 2, (got.shape[1] - w) // 2            # the device levels may carry their border
         assert np.array_equal(got[oy:oy + h, ox:ox + w], pyr[l]), l
         assert np.array_equal(flt[oy:oy + h, ox:ox + w], O.gauss7(pyr[l])), l
+
+
+
+def test_randomised_scheduling_exposes_a_missing_barrier():
+    """PLVS_EMU_SCHED_SEED: with round-robin scheduling a kernel whose threads read what thread 0 wrote WITHOUT a barrier looks fine (thread 0 always runs first);
+    with a randomised order of thread segments some threads read too early.  The product's kernels give the oracle's results under such schedules too
+    (run by hand over the whole file with seeds 1 and 2; profiles/r01_cpu_model_runs.md)."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys, ctypes as C; sys.path.insert(0, %r); from tests.native_build import build_emulated_kernels; "
+            "print(C.CDLL(build_emulated_kernels()).emu_missing_barrier_demo())" % str(ROOT))
+    plain = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT), env={k: v for k, v in os.environ.items() if k != "PLVS_EMU_SCHED_SEED"})
+    assert plain.returncode == 0 and int(plain.stdout.split()[-1]) == 256
+    seen = []
+    for seed in ("1", "2", "3"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT), env=dict(os.environ, PLVS_EMU_SCHED_SEED=seed))
+        assert r.returncode == 0
+        seen.append(int(r.stdout.split()[-1]))
+    assert all(0 < s < 256 for s in seen), seen
