@@ -427,3 +427,37 @@ def test_randomised_scheduling_exposes_a_missing_barrier():
         assert r.returncode == 0
         seen.append(int(r.stdout.split()[-1]))
     assert all(0 < s < 256 for s in seen), seen
+
+
+def test_bench_step_dataflow_on_the_cpu_model(product_bound_to_emulated_units):
+    """bench.py's unit of work -- plvs_b200.pipeline.HotPath.step: batch extraction, the two tracking searches on the device-resident frame, the
+    triangulation search, the colour depth-scan integration -- run sequentially on the CPU model over a short synthetic stream and compared with the
+    oracle stage by stage: the bench measures the path the parity tests pin, with nothing skipped"""
+    from plvs_b200.pipeline import StreamData, HotPath
+    d = StreamData(4, 320, 240, stream=0, pinned=False)
+    hp = HotPath(d, nfeatures=500, voxel=0.04, far=4.0, max_blocks=4096, batch=2)
+    hp.prepare()
+    got = {}
+    for f0 in (0, 2):
+        for k, v in hp.step(f0, 2, resident=False, concurrent=False).items():
+            got[k] = got.get(k, 0) + v
+    want_matches, want_kp = 0, 0
+    p = T.default_params(voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=4096, use_color=1)
+    o = OT.Map(p, threads=8); o.set_camera(d.K["fx"], d.K["fy"], d.K["cx"], d.K["cy"], d.w, d.h)
+    for f in range(d.n):
+        kp, desc, _, _ = O.extract_port(d.gray[f], 500)
+        assert np.array_equal(kp, hp.frames[f].keys) and np.array_equal(desc, hp.frames[f].desc)
+        want_kp += len(kp)
+        o.integrate(d.depth[f], d.poses[f], d.bgr[f])
+        q = hp.prepared[f]
+        if q is None:
+            continue
+        cur, last = hp.frames[f], hp.frames[f - 1]
+        n1, a1 = OM.search_by_projection_last(cur, q["ql"], 15.0, False, False, True)
+        n2, _ = OM.search_by_projection_map(cur, q["qm"], 3.0, 0.8, claimed=(a1 >= 0).astype(np.uint8))
+        n3, _ = OM.search_for_triangulation(cur, last, q["fv1"], q["fv2"], q["has1"], q["has2"], q["F12"], q["ep"], False, False, False)
+        want_matches += n1 + n2 + n3
+    assert got["keypoints"] == want_kp and got["matches"] == want_matches > 100
+    gk, gs, gw, gc = hp.tsdf.download(); ok, os_, ow, oc = o.download()
+    assert np.array_equal(gk, ok) and np.array_equal(gw.view(np.uint32), ow.view(np.uint32)) and np.array_equal(gs.view(np.uint32), os_.view(np.uint32)) and np.array_equal(gc, oc)
+    assert len(gk) > 20
