@@ -11,3 +11,5 @@ for cfg in "" "PLVS_TSDF_CTAS_PER_SM=1 PLVS_MATCH_RESOLVE_SMEM=0" "PLVS_MATCH_RE
   tag=$(echo "${cfg:-default}" | tr ' =' '__')
   env $cfg timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ab_${tag}.json 2> gpurun_out/bench_ab_${tag}.err; echo "bench [$cfg] exit $?"; cut -c1-260 gpurun_out/bench_ab_${tag}.json
 done
+# the open FAST min/max-tree issue: score-map mismatches of the tree path on the device, with the ring values of the first few
+PLVS_FAST_TREE=1 PLVS_ORB_DEBUG=1 timeout 120 python tools/fast_tree_probe.py > gpurun_out/fast_tree_probe.log 2>&1; echo "fast tree probe exit $?"; tail -12 gpurun_out/fast_tree_probe.log
