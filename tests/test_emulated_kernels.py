@@ -461,3 +461,47 @@ def test_bench_step_dataflow_on_the_cpu_model(product_bound_to_emulated_units):
     gk, gs, gw, gc = hp.tsdf.download(); ok, os_, ow, oc = o.download()
     assert np.array_equal(gk, ok) and np.array_equal(gw.view(np.uint32), ow.view(np.uint32)) and np.array_equal(gs.view(np.uint32), os_.view(np.uint32)) and np.array_equal(gc, oc)
     assert len(gk) > 20
+
+
+def test_error_paths_of_the_new_entry_points(product_bound_to_emulated_units, tmp_path):
+    """argument validation and capacity errors of the entry points written last return codes (PLVS_EINVAL / PLVS_ECAP / PLVS_ESTATE) with a message --
+    nothing aborts, nothing is written out of bounds (the reference quick_exit()s in places like these)"""
+    from plvs_b200.matcher import ORBmatcher
+    from plvs_b200.bow import ORBVocabulary
+    from oracle import bow as OB
+    lib = ABI.load()
+    K = synth.intrinsics(160, 120)
+    g = T.ChiselServer(T.default_params(voxel_resolution=0.04, max_blocks=1024, use_color=1))
+    d16 = np.full((120, 160), 5000, np.uint16); pose = np.ascontiguousarray(synth.pose(0), np.float32).reshape(12)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert lib.plvs_tsdf_integrate_depth_u16(g._h, p(d16), 160, 120, 320, 0.0002, None, 0, 0, p(pose), T.SCAN) != 0            # no camera yet
+    g.SetDepthCameraInfo(K["fx"], K["fy"], K["cx"], K["cy"], 160, 120)
+    assert lib.plvs_tsdf_integrate_depth_u16(g._h, p(d16), 160, 120, 100, 0.0002, None, 0, 0, p(pose), T.SCAN) != 0            # row stride shorter than a row
+    assert lib.plvs_tsdf_integrate_depth_u16(g._h, p(d16), 160, 120, 320, 0.0002, None, 0, 3, p(pose), T.SCAN_COLOR) != 0      # colour mode without an image
+    assert b"colour" in lib.plvs_last_error() or b"color" in lib.plvs_last_error()
+    g.integrate_u16(d16, 0.0002, synth.pose(0), synth.bgr_frame(0, 160, 120))
+    nm, nv = g.UpdateMesh()
+    assert nv > 0
+    small = np.zeros(3, np.float32)
+    assert lib.plvs_tsdf_get_meshes(g._h, None, None, 0, p(small), None, None, 1, 0) == -4                                    # PLVS_ECAP
+    k1 = np.zeros(1, np.uint32)
+    assert lib.plvs_tsdf_get_mesh_kfids(g._h, p(k1), 1, 0) == -4
+    n = C.c_int()
+    assert lib.plvs_tsdf_download_kfid(g._h, p(k1), 0, C.byref(n)) == -4 and n.value > 0
+    assert (g.download_kfid() == 0).all()                                                                                   # no cloud with ids yet
+    m = ORBmatcher(0.9, True)
+    kp = np.zeros(0, KP_DTYPE); de = np.zeros((0, 32), np.uint8)
+    e = Frame(kp, de, 640, 480, O.Tables(1000).scale)
+    n0, a0, p0 = m.SearchForInitialization(e, e, np.zeros((0, 2), np.float32), 100)
+    assert n0 == 0 and len(a0) == 0
+    v = e.view(); nmatch = C.c_int(); out = np.zeros(1, np.int32)
+    assert lib.plvs_match_initialization(m._h, C.byref(v), C.byref(v), None, -5, 0.9, 1, p(out), C.byref(nmatch)) != 0        # negative window
+    voc = ORBVocabulary()
+    assert not voc.loadFromTextFile(tmp_path / "nope.txt")
+    path = tmp_path / "v.txt"; OB.write_vocabulary(path, 4, 2, seed=1)
+    assert voc.loadFromTextFile(path)
+    r = voc.transform(np.zeros((0, 32), np.uint8), 1)
+    assert len(r["word"]) == 0 and len(r["bow_ids"]) == 0 and len(r["fv_nodes"]) == 0
+    h = C.c_void_p()
+    par = np.array([0, 5, 0], np.int32); wid = np.array([-1, 0, 1], np.int32); dsc = np.zeros((3, 32), np.uint8); wgt = np.ones(3)
+    assert lib.plvs_voc_create(0, 2, 1, 0, 0, 3, p(par), p(wid), p(dsc), p(wgt), C.byref(h)) != 0                             # a parent that does not precede its child
