@@ -56,6 +56,9 @@ template <class P> bool point_kfid(const P& pt, uint32_t* out) { return point_kf
 template <class P> auto point_set_normal_impl(P& pt, const float* n, int) -> decltype((void)pt.normal_x, void()) { pt.normal_x = n[0]; pt.normal_y = n[1]; pt.normal_z = n[2]; }
 template <class P> void point_set_normal_impl(P&, const float*, long) {}
 template <class P> void point_set_normal(P& pt, const float* n) { point_set_normal_impl(pt, n, 0); }
+template <class P> auto point_set_kfid_impl(P& pt, uint32_t k, int) -> decltype((void)pt.kfid, true) { pt.kfid = k; return true; }
+template <class P> bool point_set_kfid_impl(P&, uint32_t, long) { return false; }
+template <class P> bool point_set_kfid(P& pt, uint32_t k) { return point_set_kfid_impl(pt, k, 0); }
 template <class P> auto point_set_alpha_impl(P& pt, int) -> decltype((void)pt.a, void()) { pt.a = 255; }
 template <class P> void point_set_alpha_impl(P&, long) {}
 template <class P> void point_set_alpha(P& pt) { point_set_alpha_impl(pt, 0); }
@@ -770,8 +773,12 @@ public:
         const float l0n = std::sqrt(l0[0] * l0[0] + (l0[1] * l0[1] + l0[2] * l0[2]));
         const float lightDir[3] = {l0[0] / l0n, l0[1] / l0n, l0[2] / l0n}, lightDir1[3] = {-0.5f, 0.2f, 0.2f};
         typedef typename std::decay<decltype(output_cloud.points[0])>::type PointT;
+        { PointT probe; if (plvs_shim::point_set_kfid(probe, 0u)) {            // the overload for point types with a kfid field (ChiselServer.cpp:1077-1180)
+            meshK_.resize(n);
+            plvs_shim::check(plvs_tsdf_get_mesh_kfids(h_, meshK_.data(), nMeshVerts_, 0), "plvs_tsdf_get_mesh_kfids"); } else meshK_.clear(); }
         for (size_t i = 0; i < n; ++i) {
             PointT point;
+            if (!meshK_.empty()) plvs_shim::point_set_kfid(point, meshK_[i]);
             point.x = meshV_[3 * i]; point.y = meshV_[3 * i + 1]; point.z = meshV_[3 * i + 2];
             const float* nrm = &meshN_[3 * i];
             if (useColor) {
@@ -880,7 +887,7 @@ protected:
     float* depth_ = nullptr; int dw_ = 0, dh_ = 0;
     const uint16_t* depth16_ = nullptr; int dstep16_ = 0; float dfactor_ = 1.0f;
     int nMeshes_ = 0; long long nMeshVerts_ = 0; std::vector<float> meshV_, meshN_, meshC_;
-    std::vector<uint32_t> cloudKfid_;
+    std::vector<uint32_t> cloudKfid_, meshK_;
     unsigned char* color_ = nullptr; int cw_ = 0, ch_ = 0, cstep_ = 0, cn_ = 0;
     plvs_tsdf* h_ = nullptr;
 };

@@ -105,6 +105,9 @@ extern "C" int shim_instantiate(int run)
     struct PointOut { float x, y, z, normal_x, normal_y, normal_z; unsigned char r, g, b, a; };
     struct CloudOut { std::vector<PointOut> points; void clear() { points.clear(); } void push_back(const PointOut& q) { points.push_back(q); } } out;
     cs.UpdateMesh(); cs.GetPointCloud(out);
+    struct PointOutK { float x, y, z, normal_x, normal_y, normal_z; unsigned char r, g, b, a; unsigned kfid; };
+    struct CloudOutK { std::vector<PointOutK> points; void clear() { points.clear(); } void push_back(const PointOutK& q) { points.push_back(q); } } outk;
+    cs.GetPointCloud(outk);
     // a26: SetPointCloud + IntegrateLastPointCloud with a coloured and a colourless PCL-like cloud
     struct PointXYZRGBA { float x, y, z; unsigned char b, g, r, a; };
     struct PointXYZ { float x, y, z; };
