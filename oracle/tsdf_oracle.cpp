@@ -192,16 +192,21 @@ int orc_tsdf_integrate(void* h, const float* depth, int w, int ht, const uint8_t
     const float fx = m->fx, fy = m->fy, cx = m->cx, cy = m->cy;
     const int width = m->width, height = m->height;
 
-    // create missing chunks first (sequential map mutation), then evaluate chunks in parallel
+    // The reference creates every missing chunk of the range first, evaluates all of them and garbage-collects the new ones that
+    // stayed untouched (Chisel.h:86-129).  Same result with bounded memory: a missing chunk is evaluated in a scratch block that
+    // only enters the map if a voxel changed (at 5 mm / 5 m the range holds ~400 k chunks = 25 GB if all were kept alive at once).
     std::vector<Block*> blk(list.size());
+    std::vector<std::unique_ptr<Block>> fresh(list.size());
     std::vector<char> is_new(list.size(), 0), updated(list.size(), 0);
     for (size_t i = 0; i < list.size(); ++i) {
         auto it = m->blocks.find(list[i]);
-        if (it == m->blocks.end()) { is_new[i] = 1; it = m->blocks.emplace(list[i], std::make_unique<Block>()).first; }
-        blk[i] = it->second.get();
+        if (it == m->blocks.end()) { is_new[i] = 1; blk[i] = nullptr; }
+        else blk[i] = it->second.get();
     }
 #pragma omp parallel for schedule(dynamic, 16) num_threads(m->threads)
     for (long ci = 0; ci < (long)list.size(); ++ci) {
+        std::unique_ptr<Block> scratch;
+        if (!blk[ci]) { scratch = std::make_unique<Block>(); blk[ci] = scratch.get(); }
         Block& B = *blk[ci];
         const Key k = list[ci];
         const V3 origin{(float)(16 * k.x) * res, (float)(16 * k.y) * res, (float)(16 * k.z) * res};
@@ -251,11 +256,12 @@ int orc_tsdf_integrate(void* h, const float* depth, int w, int ht, const uint8_t
                     }
                 }
         updated[ci] = upd;
+        if (scratch && upd) fresh[ci] = std::move(scratch);
     }
     m->n_updated = m->n_new = m->n_collected = 0;
     for (size_t i = 0; i < list.size(); ++i) {
-        if (updated[i]) { ++m->n_updated; if (is_new[i]) ++m->n_new; }
-        else if (is_new[i]) { m->blocks.erase(list[i]); ++m->n_collected; }
+        if (updated[i]) { ++m->n_updated; if (is_new[i]) { ++m->n_new; m->blocks.emplace(list[i], std::move(fresh[i])); } }
+        else if (is_new[i]) ++m->n_collected;
     }
     return 0;
 }

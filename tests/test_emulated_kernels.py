@@ -1,6 +1,6 @@
 """CPU: the product's own kernel source (plvs_b200/csrc/*.cuh, device-only headers) executed on the small CPU model of CUDA in
 tests/native/cuda_emu.hpp -- every CUDA thread a fiber, barriers / shuffles / ballots as rendezvous points -- and compared with the oracle.
-It exists for the kernels written after the round's GPU budget was spent (tests/test_zz_gpu_unverified.py holds their GPU tests): index
+It exists for the kernels written after the round's GPU budget was spent (tests/test_gpu_widened.py holds their GPU tests): index
 arithmetic, warp-level reductions, prefix sums, barrier placement and float operation order are exercised here with the real text; what a CPU
 model cannot show (memory-ordering races, launch configuration limits, nvcc code generation) stays for the GPU run.  k_build_grid and
 k_in_frustum already passed on a B200 and double as a check of the model itself."""
@@ -354,10 +354,10 @@ def test_gpu_tests_replayed_on_the_cpu_model(product_bound_to_emulated_units, mo
 @pytest.mark.parametrize("name", ["_impl_tsdf_from_raw_u16_depth", "_impl_mesh_read_out", "_impl_search_for_initialization", "_impl_search_local_points_resident",
                                   "_impl_bow_transform", "_impl_undistort_keypoints_on_device", "_impl_reference_goldens", "_impl_keyframe_ids"])
 def test_unverified_gpu_tests_replayed_on_the_cpu_model(product_bound_to_emulated_units, tmp_path, name):
-    """the bodies of tests/test_zz_gpu_unverified.py (the rows that have not met a GPU), unchanged, against the emulated translation units: entry points,
+    """the bodies of tests/test_gpu_widened.py (the rows that have not met a GPU), unchanged, against the emulated translation units: entry points,
     host sequencing and kernels of the 16-bit depth path, the mesh read-out, SearchForInitialization, the resident SearchLocalPoints, the BoW
     transform and UndistortKeyPoints (on keypoints left "on the device" by the emulated extractor) all give the oracle's results"""
-    import tests.test_zz_gpu_unverified as Z
+    import tests.test_gpu_widened as Z
     fn = getattr(Z, name)
     fn(tmp_path) if name in ("_impl_bow_transform", "_impl_reference_goldens") else fn()
 
@@ -383,7 +383,7 @@ def test_memcheck_on_the_cpu_model(tmp_path):
                           "assert lib.plvs_host_alloc(C.byref(p), 1000) == 0; b = (C.c_ubyte * 2000).from_address(p.value); b[999] = 1; print('in bounds', flush=True); b[1008] = 1; print('missed')"],
                          capture_output=True, text=True, env=env, cwd=str(ROOT))
     assert bad.returncode != 0 and "in bounds" in bad.stdout and "missed" not in bad.stdout
-    body = ("import __graft_entry__ as g, tests.test_zz_gpu_unverified as Z; g.smoke(); "
+    body = ("import __graft_entry__ as g, tests.test_gpu_widened as Z; g.smoke(); "
             "[getattr(Z, n)() for n in ('_impl_tsdf_from_raw_u16_depth', '_impl_mesh_read_out', '_impl_search_for_initialization', '_impl_search_local_points_resident', "
             "'_impl_undistort_keypoints_on_device', '_impl_keyframe_ids')]; Z._impl_bow_transform(pathlib.Path(%r)); print('clean')" % str(tmp_path))
     ok = subprocess.run([sys.executable, "-c", pre + body], capture_output=True, text=True, env=env, cwd=str(ROOT), timeout=1200)
@@ -430,37 +430,21 @@ def test_randomised_scheduling_exposes_a_missing_barrier():
 
 
 def test_bench_step_dataflow_on_the_cpu_model(product_bound_to_emulated_units):
-    """bench.py's unit of work -- plvs_b200.pipeline.HotPath.step: batch extraction, the two tracking searches on the device-resident frame, the
-    triangulation search, the colour depth-scan integration -- run sequentially on the CPU model over a short synthetic stream and compared with the
-    oracle stage by stage: the bench measures the path the parity tests pin, with nothing skipped"""
-    from plvs_b200.pipeline import StreamData, HotPath
-    d = StreamData(4, 320, 240, stream=0, pinned=False)
-    hp = HotPath(d, nfeatures=500, voxel=0.04, far=4.0, max_blocks=4096, batch=2)
-    hp.prepare()
-    got = {}
-    for f0 in (0, 2):
-        for k, v in hp.step(f0, 2, resident=False, concurrent=False).items():
-            got[k] = got.get(k, 0) + v
-    want_matches, want_kp = 0, 0
-    p = T.default_params(voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=4096, use_color=1)
-    o = OT.Map(p, threads=8); o.set_camera(d.K["fx"], d.K["fy"], d.K["cx"], d.K["cy"], d.w, d.h)
-    for f in range(d.n):
-        kp, desc, _, _ = O.extract_port(d.gray[f], 500)
-        assert np.array_equal(kp, hp.frames[f].keys) and np.array_equal(desc, hp.frames[f].desc)
-        want_kp += len(kp)
-        o.integrate(d.depth[f], d.poses[f], d.bgr[f])
-        q = hp.prepared[f]
-        if q is None:
-            continue
-        cur, last = hp.frames[f], hp.frames[f - 1]
-        n1, a1 = OM.search_by_projection_last(cur, q["ql"], 15.0, False, False, True)
-        n2, _ = OM.search_by_projection_map(cur, q["qm"], 3.0, 0.8, claimed=(a1 >= 0).astype(np.uint8))
-        n3, _ = OM.search_for_triangulation(cur, last, q["fv1"], q["fv2"], q["has1"], q["has2"], q["F12"], q["ep"], False, False, False)
-        want_matches += n1 + n2 + n3
-    assert got["keypoints"] == want_kp and got["matches"] == want_matches > 100
-    gk, gs, gw, gc = hp.tsdf.download(); ok, os_, ow, oc = o.download()
-    assert np.array_equal(gk, ok) and np.array_equal(gw.view(np.uint32), ow.view(np.uint32)) and np.array_equal(gs.view(np.uint32), os_.view(np.uint32)) and np.array_equal(gc, oc)
-    assert len(gk) > 20
+    """bench.py's unit of work -- plvs_b200.pipeline.HotPath.step and the threaded HotPath.run_stream: batch extraction, the two tracking searches
+    on the device-resident frame, the triangulation search, the colour depth-scan integration -- on the CPU model over a short synthetic stream,
+    compared with the oracle stage by stage (the body of tests/test_gpu_bench_config.py::test_hot_path_step_at_bench_config, reduced): the bench
+    measures the path the parity tests pin, with nothing skipped"""
+    import tests.test_gpu_bench_config as B
+    nblk, nm = B._impl_hot_path(320, 240, 500, 0.04, 4.0, 2, 2, 4096, threaded=False)     # the model runs one host thread at a time
+    assert nblk > 20 and nm > 100
+
+
+def test_bench_geometry_scan_sequence_on_the_cpu_model(product_bound_to_emulated_units):
+    """the body of tests/test_gpu_bench_config.py::test_c2_bench_geometry_ten_scans at 160x120 / 4 cm: consecutive colour scans with carving on one
+    map, planes 0.1-5 m, compared after every scan"""
+    import tests.test_gpu_bench_config as B
+    n, s, exact = B._impl_depth_scan_sequence(160, 120, 0.04, 5.0, 5, 8192)
+    assert n > 50 and exact
 
 
 def test_error_paths_of_the_new_entry_points(product_bound_to_emulated_units, tmp_path):

@@ -1,6 +1,6 @@
 """Golden vectors recorded from the REFERENCE's own code (tests/golden/extras_ref.npz, made by tests/golden/make_extras_golden.py from oracle/_ref) for the
 rows widened last: SearchForInitialization, mesh read-out, bag-of-words transform.  They hold where /root/reference is absent: the oracle is checked
-against them here (CPU), the product in tests/test_zz_gpu_unverified.py's GPU run and on the CPU model."""
+against them here (CPU), the product in tests/test_gpu_widened.py's GPU run and on the CPU model."""
 import hashlib
 import pathlib
 

@@ -1,8 +1,7 @@
-"""-m gpu: features written after the round's GPU budget was spent.  The kernels compile for sm_100a, their oracles are pinned on the CPU, and
-their source text runs oracle-identical on the CPU execution model of tests/native/cuda_emu.hpp (tests/test_emulated_kernels.py) -- but these
-comparisons have not run on a GPU yet, hence the non-strict xfail (a pass shows as XPASS, a failure does not fail the suite) and the file
-name that sorts behind every other GPU test.  Each body runs in a child interpreter with a time limit: a kernel that hangs or host code that
-crashes ends that child (and is reported as this test's failure), not the test session."""
+"""-m gpu: the widened rows: UndistortKeyPoints, the resident SearchLocalPoints chain, 16-bit depth in front of the
+TSDF, SearchForInitialization, mesh read-out, the DBoW2 transform, keyframe ids and the goldens recorded from the reference's own code.
+They first ran on a B200 at the end of round 1 (all passed); they are ordinary strict tests now.  Each body still runs in a child interpreter
+with a time limit: a kernel that hangs or host code that crashes ends that child (and is reported as this test's failure), not the session."""
 import os
 import pathlib
 import subprocess
@@ -15,7 +14,7 @@ from plvs_b200 import synth
 from plvs_b200.orb import ORBextractor
 from oracle import orb as O
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first GPU run still pending", strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 def _impl_undistort_keypoints_on_device():
@@ -223,7 +222,7 @@ _timed_out = []              # once a child had to be killed, the remaining bodi
 def _isolated(name, *args):
     if _timed_out:
         pytest.fail("not started: %s did not finish within its time limit" % _timed_out[0])
-    code = "import sys; sys.path.insert(0, %r); import pathlib; from tests import test_zz_gpu_unverified as t; t.%s(%s)" % (
+    code = "import sys; sys.path.insert(0, %r); import pathlib; from tests import test_gpu_widened as t; t.%s(%s)" % (
         str(ROOT), name, ", ".join("pathlib.Path(%r)" % str(a) for a in args))
     try:
         r = subprocess.run([sys.executable, "-c", code], cwd=str(ROOT), capture_output=True, text=True, timeout=CHILD_TIMEOUT_S,

@@ -2,7 +2,7 @@
 # first GPU call of the next round: the tests that never met a GPU (shown as real passes / failures), then the timings of the widened rows, then
 # ncu over the new kernels.  Usage: gpurun --timeout 900 -- 'bash tools/gpu_next_round.sh'
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_zz_gpu_unverified.py -q -rA --runxfail -p no:cacheprovider > gpurun_out/unverified_tests.log 2>&1; echo "unverified tests exit $?"; tail -15 gpurun_out/unverified_tests.log
+timeout 600 python -m pytest tests/test_gpu_widened.py -q -rA --runxfail -p no:cacheprovider > gpurun_out/unverified_tests.log 2>&1; echo "unverified tests exit $?"; tail -15 gpurun_out/unverified_tests.log
 timeout 300 python tools/bench_extras.py > gpurun_out/bench_extras.jsonl 2> gpurun_out/bench_extras.err; echo "extras exit $?"; cat gpurun_out/bench_extras.jsonl
 timeout 300 ncu --set full --clock-control none -k "regex:k_mesh_|k_bow_|k_init_|k_compact_queries|k_undistort|k_depth_u16" -c 24 -f -o /tmp/extras python tools/bench_extras.py > gpurun_out/extras_ncu.log 2>&1; echo "ncu exit $?"
 ncu -i /tmp/extras.ncu-rep --page raw --csv > gpurun_out/extras_raw.csv 2>/dev/null; ls -la gpurun_out/extras_raw.csv
