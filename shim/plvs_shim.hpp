@@ -827,18 +827,21 @@ public:
     {
         depth16_ = img; dw_ = width; dh_ = height; dstep16_ = step_bytes; dfactor_ = depthMapFactor; depth_ = nullptr;
     }
-    void IntegrateLastDepthImage(bool /*updateMesh*/ = true)
+    // ChiselServer::IntegrateLastDepthImage(bool updateMesh = true) (ChiselServer.cpp:623-662): integrates, then chiselMap->UpdateMeshes() when asked
+    void IntegrateLastDepthImage(bool updateMesh = true)
     {
         if (gotInfo && gotPose && depth16_ && !depth_) {
             const bool color16 = useColor && color_;
             plvs_shim::check(plvs_tsdf_integrate_depth_u16(h_, depth16_, dw_, dh_, dstep16_, dfactor_, color16 ? color_ : nullptr, cstep_, cn_, Twc_,
                                                            color16 ? PLVS_TSDF_SCAN_COLOR : PLVS_TSDF_SCAN), "plvs_tsdf_integrate_depth_u16");
+            if (updateMesh) UpdateMesh();
             return;
         }
         if (!gotInfo || !gotPose || !depth_) { std::fprintf(stderr, "ChiselServer - PROBLEM in integrating depth scan!!! ************\n"); return; }
         const bool color = useColor && color_;
         plvs_shim::check(plvs_tsdf_integrate_depth(h_, depth_, dw_, dh_, color ? color_ : nullptr, cstep_, cn_, Twc_,
                                                    color ? PLVS_TSDF_SCAN_COLOR : PLVS_TSDF_SCAN, 0), "plvs_tsdf_integrate_depth");
+        if (updateMesh) UpdateMesh();
     }
     // ChiselServer::SetPointCloud (ChiselServer.cpp:560-583): camera-frame cloud + its pose; colours become floats with
     // byteToFloat = 1.0f / 255.0f exactly as PclPointCloudToChisel does (Conversions.h:69-94).  CloudT is any
@@ -864,7 +867,7 @@ public:
     }
     // ChiselServer::IntegrateLastPointCloud (ChiselServer.cpp:664-705) -> Chisel::IntegratePointCloudWidthDepth: the carve pass
     // uses the depth image registered with SetDepthImage[MemorySharing] when the depth camera info is known
-    void IntegrateLastPointCloud(bool /*updateMesh*/ = true)
+    void IntegrateLastPointCloud(bool updateMesh = true)
     {
         if (!gotCloudPose) { std::fprintf(stderr, "ChiselServer - PROBLEM in integrating point cloud!!! ************\n"); return; }
         const bool with_depth = gotInfo && depth_;
@@ -875,6 +878,7 @@ public:
         else
         plvs_shim::check(plvs_tsdf_integrate_cloud(h_, cloudXyz_.data(), cloudRgb_.empty() ? nullptr : cloudRgb_.data(), (int)(cloudXyz_.size() / 3),
                                                    with_depth ? depth_ : nullptr, with_depth ? dw_ : 0, with_depth ? dh_ : 0, cloudTwc_), "plvs_tsdf_integrate_cloud");
+        if (updateMesh) UpdateMesh();
     }
     plvs_tsdf* handle() { return h_; }
 
