@@ -513,6 +513,12 @@ int plvs_tsdf_download_blocks(plvs_tsdf* h, int32_t* keys, float* sdf, float* we
  * by the caller (plvs_b200/parallel.py uses torch.distributed). */
 int plvs_tsdf_export_packed(plvs_tsdf* h, int32_t* d_keys, float* d_wsdf, float* d_w, int cap, int* n_out);
 int plvs_tsdf_merge_packed(plvs_tsdf* h, const int32_t* d_keys, const float* d_wsdf, const float* d_w, int n);
+/* The same with the colour state: d_rgba[n][4096] = every voxel's ColorVoxel (r, g, b, colour weight; Thirdparty/open_chisel/include/open_chisel/
+ * ColorVoxel.h:34-127) as stored.  The merge folds an incoming ColorVoxel in as ColorVoxel::Integrate would fold `weight` observations of that colour
+ * (weighted mean truncated to a byte, weight saturating at 255), items of one block in list order.  d_rgba may be NULL (= the calls above);
+ * any number of items per call. */
+int plvs_tsdf_export_packed_rgba(plvs_tsdf* h, int32_t* d_keys, float* d_wsdf, float* d_w, uint32_t* d_rgba, int cap, int* n_out);
+int plvs_tsdf_merge_packed_rgba(plvs_tsdf* h, const int32_t* d_keys, const float* d_wsdf, const float* d_w, const uint32_t* d_rgba, int n);
 
 #ifdef __cplusplus
 }

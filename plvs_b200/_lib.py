@@ -152,6 +152,8 @@ def declare(lib):
     lib.plvs_tsdf_download_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.plvs_tsdf_export_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.plvs_tsdf_merge_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.plvs_tsdf_export_packed_rgba.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.plvs_tsdf_merge_packed_rgba.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     for name in ("plvs_match_destroy", "plvs_tsdf_destroy"):
         if hasattr(lib, name):
             getattr(lib, name).restype = None

@@ -24,7 +24,8 @@ def _worker(rank, world, port, ret):
     keys = torch.from_numpy(np.concatenate([shared, private]).astype(np.int32))
     w = torch.from_numpy(rng.random((len(keys), 4096)).astype(np.float32))
     wsdf = w * 0.01 * (rank + 1)
-    rk, rs, rw = parallel.exchange_blocks(keys, wsdf, w)
+    rk, rp = parallel.exchange_blocks(keys, torch.cat([wsdf, w], 1))
+    rs, rw = rp[:, :4096], rp[:, 4096:]
     own = parallel.owner_of(rk, world)
     ok_owner = bool((own == rank).all())
     tot_sent = torch.tensor([float(w.double().sum()), float(len(keys))], dtype=torch.float64)
@@ -75,25 +76,39 @@ def _merge_worker(rank, world, port, ret):
     ABI._lib = ABI.declare(_Partial(C.CDLL(build_emulated_library())))          # this process runs the library on the CPU model
     w, h = 160, 120
     K = synth.intrinsics(w, h)
-    p = T.default_params(voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=4096, use_color=0)
+    p = T.default_params(voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=4096, use_color=1)
     frames = ((0, 1, 2), (2, 5, 9))                                              # the two ranks see the same world from different poses
     g = T.ChiselServer(p); g.SetDepthCameraInfo(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
     for f in frames[rank]:
-        g.integrate(synth.depth_frame(f, w, h), synth.pose(f))
-    sent, received = parallel.merge_maps(g, device=torch.device("cpu"))
-    ck, cs, cw, _ = g.download()
+        g.integrate(synth.depth_frame(f, w, h), synth.pose(f), synth.bgr_frame(f, w, h))
+    # a pool too small for the blocks this rank will own: refused BEFORE the map is touched
+    tiny = T.ChiselServer(T.default_params(voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=4096, use_color=1))
+    before = g.download()
+    g.params.max_blocks, keep = 4, g.params.max_blocks
+    try:
+        parallel.merge_maps(g, device=torch.device("cpu"))
+        refused = False
+    except RuntimeError:
+        refused = True
+    g.params.max_blocks = keep
+    after = g.download()
+    untouched = refused and all(np.array_equal(a, b) for a, b in zip(before, after))
+    del tiny
+    rep = {}
+    sent, received = parallel.merge_maps(g, device=torch.device("cpu"), report=rep)
+    ck, cs, cw, cc = g.download()
     # expectation: both ranks' maps from the oracle, folded in rank order, restricted to the blocks this rank owns
     host = []
     for fr in frames:
         o = OT.Map(p, threads=4); o.set_camera(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
         for f in fr:
-            o.integrate(synth.depth_frame(f, w, h), synth.pose(f))
-        ok, osdf, ow, _ = o.download()
-        host.append((ok, osdf, ow))
+            o.integrate(synth.depth_frame(f, w, h), synth.pose(f), synth.bgr_frame(f, w, h))
+        host.append(o.download())
     exp = fold(host)
     mine = {k: v for k, v in exp.items() if int(parallel.owner_of(torch.tensor([k], dtype=torch.int32), world)[0]) == rank}
     shared = set(map(tuple, host[0][0])) & set(map(tuple, host[1][0]))
-    ret[rank] = dict(bad=compare(mine, ck, cs, cw), n=len(ck), expected=len(mine), sent=sent, received=received, shared=len(shared))
+    ret[rank] = dict(bad=compare(mine, ck, cs, cw, cc), n=len(ck), expected=len(mine), sent=sent, received=received, shared=len(shared), untouched=untouched,
+                     bytes_ok=rep["sent_bytes"] == sent * (12 + 3 * 4096 * 4) and rep["exchange_s"] > 0, coloured=int((cc[..., 3] > 0).sum()))
     dist.destroy_process_group()
 
 
@@ -111,6 +126,7 @@ def test_merge_maps_world2_with_the_library_on_the_cpu_model():
     total = 0
     for r in range(world):
         assert ret[r]["bad"] == 0 and ret[r]["n"] == ret[r]["expected"] > 10, ret[r]
+        assert ret[r]["untouched"] and ret[r]["bytes_ok"] and ret[r]["coloured"] > 1000, ret[r]
         assert ret[r]["shared"] > 10
         total += ret[r]["n"]
     assert sum(ret[r]["sent"] for r in range(world)) == sum(ret[r]["received"] for r in range(world)) >= total
