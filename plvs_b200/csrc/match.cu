@@ -32,9 +32,15 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restrict__ sorted,
              const void* __restrict__ queries, int nq, float th, int far_points, float th_far, int forward, int backward,
-             uint32_t* __restrict__ cand, int* __restrict__ cand_n, int cap)
+             uint32_t* __restrict__ cand, int* __restrict__ cand_n, int cap, int* __restrict__ max_count)
 {
-    const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    // The window of GetFeaturesInArea is a run of grid columns; the cells r0..r1 of one column are contiguous in the cell-column-major
+    // CSR, so the reference's visiting order is the concatenation of one [pbeg, pend) range per column.  The lanes fetch the ranges of up
+    // to 32 columns at once, a warp scan turns them into one flat index space, and the warp then walks 32 flat positions per step: the
+    // dependent-load chain is cell_start -> sorted -> {keypoint, descriptor} per 32 candidates instead of per column.
+    __shared__ int s_beg[8][32], s_excl[8][33];
+    const int w = threadIdx.x >> 5;
+    const int q = blockIdx.x * 8 + w;
     const int lane = threadIdx.x & 31;
     if (q >= nq) return;
     float px, py, radius, xr_ref, xr_tol;
@@ -69,13 +75,27 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
         const uint32_t* qw = reinterpret_cast<const uint32_t*>(qd);
         const uint4 a0 = make_uint4(qw[0], qw[1], qw[2], qw[3]), a1 = make_uint4(qw[4], qw[5], qw[6], qw[7]);
         uint32_t* out = cand + (size_t)q * cap;
-        for (int ix = c0; ix <= c1; ++ix) {
-            const int pbeg = cell_start[ix * GRID_ROWS + r0], pend = cell_start[ix * GRID_ROWS + r1 + 1];
-            for (int p = pbeg + lane; p < ((pend - pbeg + 31) / 32) * 32 + pbeg; p += 32) {
-                bool ok = p < pend;
+        for (int cb = c0; cb <= c1; cb += 32) {            // at most two chunks: the grid has 64 columns
+            const int ix = cb + lane;
+            int pbeg = 0, cnt = 0;
+            if (ix <= c1) { pbeg = cell_start[ix * GRID_ROWS + r0]; cnt = cell_start[ix * GRID_ROWS + r1 + 1] - pbeg; }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            s_beg[w][lane] = pbeg; s_excl[w][lane] = incl - cnt;
+            if (lane == 31) s_excl[w][32] = total;
+            __syncwarp();
+            for (int base = 0; base < total; base += 32) {
+                const int f = base + lane;
+                bool ok = f < total;
                 int idx = 0, oct = 0, dist = 0;
                 if (ok) {
-                    idx = sorted[p];
+                    int lo = 0;                                   // the column whose range holds flat position f: last j with excl[j] <= f
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) if (s_excl[w][lo + step] <= f) lo += step;
+                    idx = sorted[s_beg[w][lo] + (f - s_excl[w][lo])];
                     const plvs_keypoint kp = F.keys[idx];
                     oct = kp.octave;
                     if (check && (oct < minL || oct > maxL)) ok = false;     // the maxLevel test applies even for -1 (src/Frame.cc:1283-1286)
@@ -87,9 +107,10 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
                 if (ok) { const int pos = count + __popc(m & ((1u << lane) - 1)); if (pos < cap) out[pos] = pack_cand(idx, dist, oct); }
                 count += __popc(m);
             }
+            __syncwarp();
         }
     }
-    if (lane == 0) cand_n[q] = count;
+    if (lane == 0) { cand_n[q] = count; if (max_count && count > cap) atomicMax(max_count, count); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -366,6 +387,183 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Phase B on ONE CTA (the default): the same Jacobi fixed point as k_resolve with everything in shared memory -- the candidate lists
+// compacted to a CSR, the two claim tables, the targets -- so a round is a list walk and two CTA barriers: no cluster barrier, no L2
+// round trip, and no need to find eight free SMs at once next to the persistent TSDF kernel.  lpq lanes share a query (strided walk,
+// shuffle merge); a table entry is -1 for a pre-claimed keypoint (blocks everybody), else the lowest query (with Observations() > 0)
+// that targeted the keypoint in the previous round.  Lists that do not fit the shared memory the launch was given are read from L2.
+// result: [0] matches, [1] rounds, [2] list words (sizes the next launch), [3] largest raw candidate count if it exceeded `cap`.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(1024)
+k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int cap, const void* __restrict__ queries, int nq,
+              const plvs_keypoint* __restrict__ keys, int n, const uint8_t* __restrict__ claimed_in, float nn_ratio, int check_ori, int th_high,
+              int32_t* __restrict__ assign_out /*n, mapped host*/, int* __restrict__ result, int* __restrict__ max_count, int lpq_shift,
+              int list_budget /*words of dynamic shared memory left for the lists*/)
+{
+    PLVS_DYN_SMEM(uint32_t, s_dyn);
+    __shared__ int s_count, s_hist[HISTO], s_keep[HISTO], s_part[32], s_total;
+    const int tid = threadIdx.x, lane32 = tid & 31, wid = tid >> 5;
+    const int INF = 0x7fffffff;
+    int* tab0 = reinterpret_cast<int*>(s_dyn);      // n
+    int* tab1 = tab0 + n;                           // n
+    int* s_target = tab1 + n;                       // nq
+    int* s_off = s_target + nq;                     // nq + 1
+    int* s_meta = s_off + nq + 1;                   // nq: list length << 1 | Observations() > 0
+    uint32_t* s_list = s_dyn + 2 * n + 3 * nq + 1;
+    // list lengths, their exclusive scan (consecutive queries per thread), table initialisation
+    const int ipt = (nq + 1023) >> 10;
+    int sum = 0;
+    for (int k = 0; k < ipt; ++k) {
+        const int q = tid * ipt + k;
+        if (q < nq) {
+            const int m = min(cand_n[q], cap);
+            const uint32_t fl = MODE == 0 ? reinterpret_cast<const plvs_mp_query*>(queries)[q].flags : reinterpret_cast<const plvs_last_query*>(queries)[q].flags;
+            s_meta[q] = (m << 1) | ((fl & PLVS_Q_OBS_POSITIVE) ? 1 : 0);
+            s_target[q] = -2;
+            sum += m;
+        }
+    }
+    int x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane32 >= o) x += y; }
+    if (lane32 == 31) s_part[wid] = x;
+    for (int i = tid; i < n; i += 1024) { const int v = (claimed_in && claimed_in[i]) ? -1 : INF; tab0[i] = v; tab1[i] = v; }
+    __syncthreads();
+    if (wid == 0) {
+        int p = s_part[lane32];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, p, o); if (lane32 >= o) p += y; }
+        s_part[lane32] = p;
+        if (lane32 == 31) s_total = p;
+    }
+    __syncthreads();
+    {
+        int base = (wid ? s_part[wid - 1] : 0) + x - sum;
+        for (int k = 0; k < ipt; ++k) { const int q = tid * ipt + k; if (q < nq) { s_off[q] = base; base += s_meta[q] >> 1; } }
+        if (tid == 1023) s_off[nq] = s_total;
+    }
+    __syncthreads();
+    const bool staged = s_total <= list_budget;
+    if (staged)
+        for (int q = wid; q < nq; q += 32) {             // a warp copies one list: coalesced reads of the row's head
+            const int m = s_meta[q] >> 1, o = s_off[q];
+            for (int k = lane32; k < m; k += 32) s_list[o + k] = cand[(size_t)q * cap + k];
+        }
+    __syncthreads();
+
+    const int lpq = 1 << lpq_shift;
+    const int slots = nq << lpq_shift;
+    int* cur = tab0; int* nxt = tab1;
+    int rounds = 0;
+    for (;;) {
+        bool changed = false;
+        for (int base = 0; base < slots; base += 1024) {
+            const int slot = base + tid;
+            const int q = slot >> lpq_shift, lane = slot & (lpq - 1);
+            const bool mine = q < nq;
+            // The reference's running best / second best (strict `<` in list order, the old best demoted to second) are the two smallest
+            // (distance, position) keys of the unblocked candidates: each lane keeps the two smallest of its strided share, shuffles merge.
+            uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+            int m = 0, off = 0;
+            if (mine) {
+                m = s_meta[q] >> 1; off = s_off[q];
+                for (int k = lane; k < m; k += lpq) {
+                    const uint32_t e = staged ? s_list[off + k] : cand[(size_t)q * cap + k];
+                    const bool blocked = cur[cand_idx(e)] < q;
+                    const uint32_t key = blocked ? 0xffffffffu : (((uint32_t)cand_dist(e) << 16) | (uint32_t)k);
+                    const uint32_t lo = min(k1, key), hi = max(k1, key);
+                    k2 = min(k2, hi); k1 = lo;
+                }
+            }
+            for (int o = 1; o < lpq; o <<= 1) {
+                const uint32_t a1 = __shfl_xor_sync(0xffffffffu, k1, o), a2 = __shfl_xor_sync(0xffffffffu, k2, o);
+                const uint32_t lo = min(k1, a1), hi = max(k1, a1);
+                k2 = min(hi, min(k2, a2));
+                k1 = lo;
+            }
+            if (mine && lane == 0) {
+                int t = -1;
+                const int bestDist = k1 == 0xffffffffu ? 256 : (int)(k1 >> 16);
+                if (bestDist <= th_high) {
+                    const uint32_t e1 = staged ? s_list[off + (k1 & 0xffffu)] : cand[(size_t)q * cap + (k1 & 0xffffu)];
+                    if (MODE == 0) {
+                        int bestDist2 = 256, bestLevel2 = -1;
+                        if (k2 != 0xffffffffu) {
+                            const uint32_t e2 = staged ? s_list[off + (k2 & 0xffffu)] : cand[(size_t)q * cap + (k2 & 0xffffu)];
+                            bestDist2 = (int)(k2 >> 16); bestLevel2 = cand_level(e2);
+                        }
+                        const int bestLevel = cand_level(e1);
+                        if (!(bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) &&
+                            (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2)) t = cand_idx(e1);
+                    } else t = cand_idx(e1);
+                }
+                if (t != s_target[q]) { s_target[q] = t; changed = true; }
+                if (t >= 0 && (s_meta[q] & 1)) atomicMin(&nxt[t], q);
+            }
+        }
+        ++rounds;
+        if (!__syncthreads_or(changed ? 1 : 0)) break;
+        { int* t = cur; cur = nxt; nxt = t; }
+        for (int i = tid; i < n; i += 1024) nxt[i] = cur[i] < 0 ? -1 : INF;
+        __syncthreads();
+    }
+    // final holders: the last (highest) query that wrote each keypoint
+    int* assign = tab0;
+    for (int i = tid; i < n; i += 1024) assign[i] = -1;
+    if (tid == 0) s_count = 0;
+    if (tid < HISTO) { s_hist[tid] = 0; s_keep[tid] = 1; }
+    __syncthreads();
+    int local = 0;
+    for (int q = tid; q < nq; q += 1024) {
+        const int t = s_target[q];
+        if (t < 0) continue;
+        ++local;
+        atomicMax(&assign[t], q);
+        if (MODE == 1 && check_ori) {
+            const float factor = HISTO / 360.0f;
+            float rot = reinterpret_cast<const plvs_last_query*>(queries)[q].angle - keys[t].angle;
+            if (rot < 0.0f) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == HISTO) bin = 0;
+            atomicAdd(&s_hist[bin], 1);
+        }
+    }
+    atomicAdd(&s_count, local);
+    __syncthreads();
+    if (MODE == 1 && check_ori) {
+        if (tid == 0) {     // ComputeThreeMaxima (src/ORBmatcher.cc:2123-2164)
+            int m1 = 0, m2 = 0, m3 = 0, i1 = -1, i2 = -1, i3 = -1;
+            for (int i = 0; i < HISTO; ++i) {
+                const int sh = s_hist[i];
+                if (sh > m1) { m3 = m2; m2 = m1; m1 = sh; i3 = i2; i2 = i1; i1 = i; }
+                else if (sh > m2) { m3 = m2; m2 = sh; i3 = i2; i2 = i; }
+                else if (sh > m3) { m3 = sh; i3 = i; }
+            }
+            if ((float)m2 < 0.1f * (float)m1) { i2 = -1; i3 = -1; }
+            else if ((float)m3 < 0.1f * (float)m1) { i3 = -1; }
+            for (int i = 0; i < HISTO; ++i) s_keep[i] = (i == i1 || i == i2 || i == i3);
+        }
+        __syncthreads();
+        int dropped = 0;
+        for (int q = tid; q < nq; q += 1024) {
+            const int t = s_target[q];
+            if (t < 0) continue;
+            const float factor = HISTO / 360.0f;
+            float rot = reinterpret_cast<const plvs_last_query*>(queries)[q].angle - keys[t].angle;
+            if (rot < 0.0f) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == HISTO) bin = 0;
+            if (!s_keep[bin]) { assign[t] = -1; ++dropped; }       // the reference nulls the slot whoever holds it now
+        }
+        atomicSub(&s_count, dropped);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) assign_out[i] = assign[i];
+    if (tid == 0) { result[0] = s_count; result[1] = rounds; result[2] = s_total; result[3] = *max_count; *max_count = 0; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // SearchForTriangulation (src/ORBmatcher.cc:1059-1208): one warp per feature of KF1 (entries of its feature
 // vector, flattened); lanes sweep the KF2 features of the same vocabulary node.  Winner = smallest
 // distance <= TH_LOW among the gated candidates, LAST one on ties (the `dist>bestDist` skip).
@@ -581,6 +779,7 @@ k_distinctive(const uint8_t* __restrict__ desc, const int32_t* __restrict__ off,
 
 #include "match_init.cuh"
 
+__global__ void k_take_max(int* max_count, int* result) { result[3] = *max_count; *max_count = 0; }
 __global__ void k_fill_i32(int32_t* p, int n, int32_t v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 }  // namespace
@@ -751,6 +950,9 @@ struct plvs_match {
     PinBuf<int32_t> p_assign;
     PinBuf<int> p_result, p_cand_n;
     int cap = 128;
+    DevBuf<uint8_t> d_stage; PinBuf<uint8_t> p_stage;     // one packed H2D per projection search
+    bool state_zeroed = false;
+    int list_words_hint = 16384;                          // shared-memory words the last search's candidate lists needed
     int last_rounds = 0, last_launches = 0;
     uint64_t grid_key = 0; int grid_n = -1;
     KernelTimer timer;
@@ -794,6 +996,9 @@ int stage_view(plvs_match* h, int slot, const plvs_frame_view* v, ViewDev* out)
     return PLVS_OK;
 }
 
+// the dynamic shared memory the one-CTA resolve may use (the opt-in limit of sm_100a is 227 KiB; 200 KiB leaves the static part and some air)
+constexpr size_t kResolveSmemMax = 200 * 1024;
+
 template <int MODE>
 int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_t qsize, int nq, float th, float nn_ratio,
                    int far_points, float th_far, int forward, int backward, int check_ori,
@@ -803,30 +1008,44 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
     std::unique_lock<std::mutex> lock(h->mu, std::defer_lock);
     if (!q_on_device) lock.lock();            // the resident entry point already holds the handle's mutex
     PLVS_CUDA(cudaSetDevice(h->device));
-    ViewDev V;
-    int rc = stage_view(h, 0, F, &V);
-    if (rc) return rc;
     const int n = F->n;
+    cudaStream_t st = h->stream;
+    int rc;
+    // Everything the caller holds on the host for this search -- the query records, the pre-claim flags and (when the keypoints stayed
+    // on the device after extraction) mvuRight -- travels in ONE copy: packed into the handle's pinned slab (the caller's containers are
+    // pageable std::vectors in PLVS), then a single asynchronous H2D.
+    plvs_frame_view Fv = *F;
+    if (n < 0 || n > 65535 || (n && (!F->keys || !F->desc))) { set_error("bad frame view"); return PLVS_EINVAL; }
+    const bool frame_host = !F->on_device && n > 0;
+    const bool ur_host = n > 0 && F->uright && (!F->on_device || (F->on_device & PLVS_VIEW_URIGHT_ON_HOST));
+    struct Part { const void* src; size_t bytes, off; } parts[5] = {
+        {q_on_device ? nullptr : q, q_on_device ? 0 : qsize * (size_t)nq, 0}, {frame_host ? F->keys : nullptr, frame_host ? (size_t)n * sizeof(plvs_keypoint) : 0, 0},
+        {frame_host ? F->desc : nullptr, frame_host ? (size_t)n * 32 : 0, 0}, {ur_host ? F->uright : nullptr, ur_host ? (size_t)n * 4 : 0, 0},
+        {claimed_in, claimed_in ? (size_t)n : 0, 0}};
+    size_t stage_bytes = 0;
+    for (Part& pt : parts) { pt.off = stage_bytes; stage_bytes = align_up(stage_bytes + pt.bytes, 16); }
+    const void* dq = q;                        // device-resident queries (plvs_match_in_frustum) are used where they are
+    const uint8_t* d_claimed = nullptr;
+    if (stage_bytes && n > 0 && nq > 0) {
+        if ((rc = h->p_stage.alloc(stage_bytes)) || (rc = h->d_stage.alloc(stage_bytes))) return rc;
+        for (const Part& pt : parts) if (pt.bytes) std::memcpy(h->p_stage.h + pt.off, pt.src, pt.bytes);
+        PLVS_CUDA(cudaMemcpyAsync(h->d_stage.p, h->p_stage.h, stage_bytes, cudaMemcpyHostToDevice, st));
+        if (parts[0].bytes) dq = h->d_stage.p + parts[0].off;
+        if (frame_host) { Fv.keys = reinterpret_cast<const plvs_keypoint*>(h->d_stage.p + parts[1].off); Fv.desc = h->d_stage.p + parts[2].off; Fv.on_device = 1; Fv.cache_key = 0; }
+        if (ur_host) { Fv.uright = reinterpret_cast<const float*>(h->d_stage.p + parts[3].off); Fv.on_device = 1; }
+        else if (frame_host) Fv.uright = nullptr;
+        if (parts[4].bytes) d_claimed = h->d_stage.p + parts[4].off;
+    }
+    ViewDev V;
+    rc = stage_view(h, 0, &Fv, &V);
+    if (rc) return rc;
     *nmatches = 0;
     for (int i = 0; i < n; ++i) assign[i] = -1;
     if (n == 0 || nq == 0) return PLVS_OK;
-    cudaStream_t st = h->stream;
-    const void* dq = q;                        // device-resident queries (plvs_match_in_frustum) are used where they are
-    if (!q_on_device) {
-        if ((rc = h->d_query.alloc(qsize * nq))) return rc;
-        PLVS_CUDA(cudaMemcpyAsync(h->d_query.p, q, qsize * nq, cudaMemcpyHostToDevice, st));
-        dq = h->d_query.p;
-    }
-    const uint8_t* d_claimed = nullptr;
-    if (claimed_in) {
-        if ((rc = h->d_claimed.alloc(n))) return rc;
-        PLVS_CUDA(cudaMemcpyAsync(h->d_claimed.p, claimed_in, n, cudaMemcpyHostToDevice, st));
-        d_claimed = h->d_claimed.p;
-    }
     if ((rc = h->d_cell_start.alloc(GRID_CELLS + 1)) || (rc = h->d_sorted.alloc(n)) || (rc = h->d_kp_cell.alloc(n)) ||
-        (rc = h->d_cand_n.alloc(nq)) || (rc = h->d_state.alloc(16)) || (rc = h->d_claim_a.alloc((size_t)3 * n)) || (rc = h->d_target.alloc(nq)) ||
-        (rc = h->d_assign.alloc(n)) || (rc = h->p_assign.alloc(n)) || (rc = h->p_result.alloc(4)) || (rc = h->p_cand_n.alloc(nq)))
+        (rc = h->d_cand_n.alloc(nq)) || (rc = h->d_state.alloc(16)) || (rc = h->p_assign.alloc(n)) || (rc = h->p_result.alloc(8)))
         return rc;
+    if (!h->state_zeroed) { PLVS_CUDA(cudaMemsetAsync(h->d_state.p, 0, 16 * sizeof(int), st)); h->state_zeroed = true; }
     int launches = 0;
     if (!(F->cache_key != 0 && F->cache_key == h->grid_key && n == h->grid_n)) {
         h->timer.begin(PLVS_MATCH_K_GRID, st);
@@ -835,55 +1054,55 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         ++launches;
         h->grid_key = F->cache_key; h->grid_n = n;
     }
+    // one CTA holds the claim tables, the targets and (if they fit) the compacted lists; past that the 8-CTA cluster kernel takes over
+    const size_t fixed_words = (size_t)2 * n + (size_t)3 * nq + 1;
+    // development / test knobs, read per call: PLVS_MATCH_RESOLVE=cluster forces the cluster kernel, PLVS_MATCH_RESOLVE_LPQ=log2(lanes per query),
+    // PLVS_MATCH_LIST_WORDS=n caps the shared-memory words for the lists (0: always read them from L2)
+    const char* e_res = std::getenv("PLVS_MATCH_RESOLVE"); const char* e_lpq = std::getenv("PLVS_MATCH_RESOLVE_LPQ"); const char* e_lw = std::getenv("PLVS_MATCH_LIST_WORDS");
+    const bool force_cluster = e_res && std::strcmp(e_res, "cluster") == 0;
+    const int lpq_shift = e_lpq ? std::max(0, std::min(5, std::atoi(e_lpq))) : 2;
+    const bool one_cta = !force_cluster && fixed_words * 4 + 16 * 1024 <= kResolveSmemMax;
     for (;;) {
         if ((rc = h->d_cand.alloc((size_t)nq * h->cap))) return rc;
         h->timer.begin(PLVS_MATCH_K_CANDIDATES, st);
         k_candidates<MODE><<<div_up(nq, 8), 256, 0, st>>>(V, h->d_cell_start.p, h->d_sorted.p, dq, nq, th, far_points, th_far, forward, backward,
-                                                           h->d_cand.p, h->d_cand_n.p, h->cap);
+                                                           h->d_cand.p, h->d_cand_n.p, h->cap, h->d_state.p + 8);
         h->timer.end(st);
         ++launches;
-        PLVS_CUDA(cudaMemcpyAsync(h->p_cand_n.h, h->d_cand_n.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
         h->timer.begin(PLVS_MATCH_K_RESOLVE, st);
-        PLVS_CUDA(cudaMemsetAsync(h->d_state.p, 0, 16 * sizeof(int), st));
-        static const bool trace_on = std::getenv("PLVS_RESOLVE_TRACE") != nullptr;
-        if (trace_on) { if ((rc = h->d_trace.alloc(kResolveCtas * 32))) return rc; PLVS_CUDA(cudaMemsetAsync(h->d_trace.p, 0, kResolveCtas * 32 * 8, st)); }
-        {
+        if (one_cta) {
+            // the lists get what the previous search on this handle needed plus a quarter (the kernel reads them from L2 when they do not fit)
+            size_t want = (size_t)h->list_words_hint + h->list_words_hint / 4 + 1024;
+            want = std::min(want, (size_t)nq * h->cap);
+            if (e_lw) want = (size_t)std::max(0, std::atoi(e_lw));
+            const size_t budget = std::min(want, kResolveSmemMax / 4 - fixed_words);
+            k_resolve_cta<MODE><<<1, 1024, (fixed_words + budget) * 4, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, dq, nq, V.keys, n, d_claimed, nn_ratio, check_ori, th_high,
+                                                                            h->p_assign.d, h->p_result.d, h->d_state.p + 8, lpq_shift, (int)budget);
+        } else {
+            if ((rc = h->d_claim_a.alloc((size_t)3 * n)) || (rc = h->d_target.alloc(nq)) || (rc = h->d_assign.alloc(n))) return rc;
+            PLVS_CUDA(cudaMemsetAsync(h->d_state.p, 0, 8 * sizeof(int), st));
             const int per_cta = div_up(nq, kResolveCtas);
             int lpq = 1;
             while (lpq < 32 && per_cta * lpq * 2 <= 1024) lpq *= 2;
             const size_t smem = ((size_t)2 * n + (size_t)per_cta * (h->cap | 1)) * sizeof(uint32_t);
             const size_t smem_small = (size_t)2 * n * sizeof(uint32_t);
-            // PLVS_MATCH_RESOLVE_SMEM=0 (experiment knob): candidate lists stay in L2, the CTA needs 8n bytes of shared memory only
-            static const bool lists_in_smem = [] { const char* e = std::getenv("PLVS_MATCH_RESOLVE_SMEM"); return !(e && e[0] == '0'); }();
-            if (per_cta <= 1024 && smem <= 200 * 1024 && lists_in_smem) {
-                static thread_local bool attr_set[2] = {false, false};
-                if (!attr_set[MODE]) {
-                    PLVS_CUDA(cudaFuncSetAttribute(k_resolve<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    attr_set[MODE] = true;
-                }
+            if (per_cta > 1024) { set_error("more than %d queries per search are not supported", kResolveCtas * 1024); return PLVS_EINVAL; }
+            if (smem_small > kResolveSmemMax) { set_error("frames of more than %d keypoints are not supported by the claim resolution", (int)(kResolveSmemMax / 8)); return PLVS_EINVAL; }
+            if (smem <= kResolveSmemMax)
                 k_resolve<MODE, true><<<kResolveCtas, 1024, smem, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, dq, nq, V.keys, n, d_claimed, nn_ratio, check_ori, th_high,
-                                                                        h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta, lpq, h->d_trace.p);
-            } else if (per_cta <= 1024) {
+                                                                        h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta, lpq, nullptr);
+            else
                 k_resolve<MODE, false><<<kResolveCtas, 1024, smem_small, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, dq, nq, V.keys, n, d_claimed, nn_ratio, check_ori, th_high,
-                                                                      h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta, lpq, h->d_trace.p);
-            } else { set_error("more than %d queries per search are not supported", kResolveCtas * 1024); return PLVS_EINVAL; }
+                                                                               h->d_claim_a.p, h->d_target.p, h->d_state.p, h->d_assign.p, h->p_assign.d, h->p_result.d, per_cta, lpq, nullptr);
+            k_take_max<<<1, 1, 0, st>>>(h->d_state.p + 8, h->p_result.d);
         }
         h->timer.end(st);
         ++launches;
         PLVS_CUDA(cudaGetLastError());
         PLVS_CUDA(cudaStreamSynchronize(st));
         h->timer.collect();
-        if (trace_on) {
-            long long tr[kResolveCtas * 32];
-            cudaMemcpy(tr, h->d_trace.p, sizeof(tr), cudaMemcpyDeviceToHost);
-            for (int c = 0; c < kResolveCtas; c += kResolveCtas - 1) {
-                std::fprintf(stderr, "resolve<%d> nq=%d cta%d cycles:", MODE, nq, c);
-                for (int i = 1; i < 32 && tr[c * 32 + i]; ++i) std::fprintf(stderr, " %lld", tr[c * 32 + i] - tr[c * 32 + i - 1]);
-                std::fprintf(stderr, "\n");
-            }
-        }
-        int mx = 0;
-        for (int i = 0; i < nq; ++i) mx = std::max(mx, h->p_cand_n.h[i]);
+        if (one_cta) h->list_words_hint = h->p_result.h[2];
+        const int mx = h->p_result.h[3];
         if (mx <= h->cap) break;
         while (h->cap < mx) h->cap *= 2;       // a window held more candidates than reserved: redo with room (exactness first)
     }
@@ -932,6 +1151,13 @@ int plvs_match_create(int device, plvs_match** out)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: libplvs_b200 has no CPU fallback"); return PLVS_ENODEV; }
     if (device < 0 || device >= ndev) { set_error("device %d out of range", device); return PLVS_EINVAL; }
     PLVS_CUDA(cudaSetDevice(device));
+    // opt-in shared memory limits are per device: raised here, once per handle, for every kernel that can ask for more than 48 KiB
+    PLVS_CUDA(cudaFuncSetAttribute(k_resolve_cta<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmemMax));
+    PLVS_CUDA(cudaFuncSetAttribute(k_resolve_cta<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmemMax));
+    PLVS_CUDA(cudaFuncSetAttribute(k_resolve<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmemMax));
+    PLVS_CUDA(cudaFuncSetAttribute(k_resolve<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmemMax));
+    PLVS_CUDA(cudaFuncSetAttribute(k_resolve<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmemMax));
+    PLVS_CUDA(cudaFuncSetAttribute(k_resolve<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmemMax));
     plvs_match* h = new plvs_match();
     h->device = device; h->timer.component = 2;
     { cudaError_t e = create_handle_stream(&h->stream, 2);
