@@ -1,16 +1,17 @@
 #!/usr/bin/env python3
 """bench.py -- frames/s of the PLVS per-frame hot path (ORB extract + Hamming match + Chisel TSDF) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c3]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One step = one batch of `--batch` consecutive 640x480 RGB-D frames of a synthetic stream (BASELINE.json
-configs[1]: ORB nFeatures=2000 + Chisel TSDF 1 cm voxels); every frame is extracted, matched against the
-previous frame (SearchByProjection Cur<-Last), against its local map points (SearchByProjection F<-map),
-triangulation-searched against the previous frame and integrated into the TSDF.  One camera stream per
-rank (weak scaling, no collective on the data path).  Prints ONE JSON line (rank 0).
+One step = one batch of `frames_per_step` consecutive RGB-D frames of a synthetic stream (default: BASELINE.json configs[1], 640x480, ORB
+nFeatures=2000 + Chisel TSDF 1 cm voxels; `--config c3` = configs[2], 1920x1080, nFeatures=4000, 5 mm); every frame is extracted, matched
+against the previous frame (SearchByProjection Cur<-Last), against its local map points (SearchByProjection F<-map), triangulation-searched
+against the previous frame and integrated into the TSDF.  One camera stream per rank (weak scaling, no collective on the data path).
+Prints ONE JSON line (rank 0).
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -24,7 +25,11 @@ sys.path.insert(0, str(ROOT))
 
 import numpy as np
 
-METRIC = "frames/sec (extract+match+TSDF) 640x480 RGB-D"
+CONFIGS = {
+    # BASELINE.json configs[1] / configs[2] (the ORB part; line features are outside SURVEY.md §8's scope table)
+    "c2": dict(width=640, height=480, nfeatures=2000, voxel=0.01, far=5.0, batch=8, max_blocks=49152),
+    "c3": dict(width=1920, height=1080, nfeatures=4000, voxel=0.005, far=5.0, batch=4, max_blocks=400000),
+}
 
 
 def parse():
@@ -33,21 +38,30 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--width", type=int, default=640)
-    ap.add_argument("--height", type=int, default=480)
-    ap.add_argument("--nfeatures", type=int, default=2000)
-    ap.add_argument("--voxel", type=float, default=0.01)
-    ap.add_argument("--far", type=float, default=5.0)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    for k, t in (("batch", int), ("width", int), ("height", int), ("nfeatures", int), ("voxel", float), ("far", float), ("max_blocks", int)):
+        ap.add_argument("--" + k.replace("_", "-"), type=t, default=None)
+    ap.add_argument("--repeats", type=int, default=5, help="timed passes per arm; the median is reported")
+    ap.add_argument("--driver", default="native", choices=["native", "python"], help="stage threads in C++ (plvs_pipeline_run) or in Python")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=2)
-    return ap.parse_args()
+    a = ap.parse_args()
+    for k, v in CONFIGS[a.config].items():
+        if getattr(a, k) is None:
+            setattr(a, k, v)
+    return a
+
+
+def metric_name(a):
+    return f"frames/sec (extract+match+TSDF) {a.width}x{a.height} RGB-D"
 
 
 def workload_config(a, extra=None):
     c = {"workload": f"synthetic {a.width}x{a.height} RGB-D stream, ORB nFeatures={a.nfeatures} (8 levels, 1.2, FAST 20/7) + "
                      f"SearchByProjection(Cur,Last) th=15 + SearchByProjection(F,map) th=3 + SearchForTriangulation + "
                      f"Chisel TSDF {a.voxel * 100:g} cm voxels (colour depth-scan, carving on, planes 0.1-{a.far:g} m), every frame integrated",
+         "baseline_config": {"c2": "BASELINE.json configs[1]", "c3": "BASELINE.json configs[2] (ORB part)"}[a.config],
          "frames_per_step": a.batch, "streams_per_gpu": 1, "parallelism": f"1 camera stream per GPU x{a.gpus}"}
     if extra:
         c.update(extra)
@@ -55,72 +69,8 @@ def workload_config(a, extra=None):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (restatement of the reference's CPU path) timed on this box's host cores
+# CPU arm.  Nothing in this section touches libplvs_b200.so: parameters come from the oracle side, the frame / query helpers are numpy.
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(a, frames, threads, generous, tsdf_ref_frames=0):
-    """times the CPU path on frames [1, frames] of stream 0; returns (frames/s, per-stage seconds per frame).
-    Extract = cv2 primitives + C++ restatement, match = C++ restatement.  TSDF = the restatement (OpenMP over chunks when
-    `generous`), and additionally -- for the first `tsdf_ref_frames` timed frames, when oracle/_ref/libchisel_ref.so
-    exists -- the REFERENCE's own open_chisel code (single-threaded, as Chisel.h:91 is), whose mean seconds/frame then
-    replaces the restatement's in the total ("tsdf_s"; the restatement's time stays in "tsdf_port_s")."""
-    import cv2
-    from oracle import orb as O, match as OM, tsdf as OT
-    from plvs_b200 import synth, scenario, tsdf as T
-    from plvs_b200.matcher import featvec
-    cv2.setNumThreads(threads if generous else 1)
-    K = synth.intrinsics(a.width, a.height)
-    tab = O.Tables(a.nfeatures)
-    p = T.default_params(voxel_resolution=a.voxel, use_carving=1, near_plane=0.1, far_plane=a.far, max_blocks=1 << 20, use_color=1)
-    omap = OT.Map(p, threads=threads if generous else 1)
-    omap.set_camera(K["fx"], K["fy"], K["cx"], K["cy"], a.width, a.height)
-    rmap = None
-    if tsdf_ref_frames > 0 and OT.ref_available():
-        rmap = OT.RefMap(p)
-        rmap.set_camera(K["fx"], K["fy"], K["cx"], K["cy"], a.width, a.height)
-    t_ext = t_match = t_tsdf = t_ref = 0.0
-    n_ref = 0
-    prev = None
-    for f in range(frames + 1):
-        img = synth.gray_frame(f, a.width, a.height); depth = synth.depth_frame(f, a.width, a.height); bgr = synth.bgr_frame(f, a.width, a.height)
-        t0 = time.perf_counter()
-        kp, desc, mono, _ = O.extract_cv2(img, a.nfeatures, angle_impl="c")
-        t1 = time.perf_counter()
-        cur = scenario.make_frame(kp, desc, depth, K, tab.scale); cur.level_sigma2 = tab.sigma2
-        if prev is not None:
-            ql, _ = scenario.last_queries(prev, cur, K, synth.pose(f - 1), synth.pose(f))
-            qm, _ = scenario.map_queries(prev, cur, K, synth.pose(f - 1), synth.pose(f), seed=f)
-            fv1, fv2 = featvec(scenario.node_ids(cur.desc)), featvec(scenario.node_ids(prev.desc))
-            F12, ep = scenario.fundamental(K, synth.pose(f), synth.pose(f - 1))
-            t2 = time.perf_counter()
-            n1, a1 = OM.search_by_projection_last(cur, ql, 15.0)
-            OM.search_by_projection_map(cur, qm, 3.0, 0.8, claimed=(a1 >= 0).astype(np.uint8))
-            OM.search_for_triangulation(cur, prev, fv1, fv2, np.zeros(cur.n, np.uint8), np.zeros(prev.n, np.uint8), F12, ep, check_ori=False)
-            t3 = time.perf_counter()
-            omap.integrate(depth, synth.pose(f), bgr)
-            t4 = time.perf_counter()
-            t_ext += t1 - t0; t_match += t3 - t2; t_tsdf += t4 - t3
-            if rmap is not None and n_ref < tsdf_ref_frames:
-                with _quiet_stdout():
-                    rmap.integrate(depth, synth.pose(f), bgr)
-                t_ref += time.perf_counter() - t4; n_ref += 1
-        else:
-            omap.integrate(depth, synth.pose(f), bgr)        # map initialisation, untimed
-            if rmap is not None:
-                with _quiet_stdout():
-                    rmap.integrate(depth, synth.pose(f), bgr)
-        prev = cur
-    stages = dict(extract_s=t_ext / frames, match_s=t_match / frames, tsdf_s=t_tsdf / frames)
-    if n_ref:
-        stages["tsdf_port_s"] = stages["tsdf_s"]
-        stages["tsdf_s"] = t_ref / n_ref
-        stages["tsdf_ref_frames"] = n_ref
-    tot = stages["extract_s"] + stages["match_s"] + stages["tsdf_s"]
-    return 1.0 / tot, stages
-
-
-import contextlib
-
-
 @contextlib.contextmanager
 def _quiet_stdout():
     """the reference's open_chisel prints per scan; bench.py must print exactly one JSON line"""
@@ -135,37 +85,139 @@ def _quiet_stdout():
         os.dup2(saved, 1); os.close(null); os.close(saved)
 
 
+class CpuPath:
+    """The reference's CPU path on one stream.  With oracle/_ref present: extraction = the reference's own src/ORBextractor.cc (liborb_ref.so),
+    the three searches = its own src/ORBmatcher.cc (libmatch_ref.so), TSDF = its own open_chisel (libchisel_ref.so, single-threaded like
+    Chisel.h:91) or the restated TSDF over `threads` OpenMP threads.  Without oracle/_ref everything is the restatement (kind "port")."""
+
+    def __init__(self, a, threads):
+        from oracle import orb as O, match as OM, tsdf as OT
+        from plvs_b200 import synth
+        self.a, self.O, self.OM, self.OT, self.synth = a, O, OM, OT, synth
+        self.K = synth.intrinsics(a.width, a.height)
+        self.tab = O.Tables(a.nfeatures)
+        self.have_ref = O.ref_available() and OM.ref_available() and OT.ref_available()
+        self.ex = O.RefExtractor(a.nfeatures) if self.have_ref else None
+        p = OT.default_params(voxel_resolution=a.voxel, use_carving=1, near_plane=0.1, far_plane=a.far, max_blocks=1 << 20, use_color=1)
+        self.port_map = OT.Map(p, threads=threads); self.port_map.set_camera(self.K["fx"], self.K["fy"], self.K["cx"], self.K["cy"], a.width, a.height)
+        self.ref_map = None
+        if self.have_ref:
+            self.ref_map = OT.RefMap(p); self.ref_map.set_camera(self.K["fx"], self.K["fy"], self.K["cx"], self.K["cy"], a.width, a.height)
+        self.prev = None
+        self.t = dict(extract_s=0.0, match_s=0.0, tsdf_ref_s=0.0, tsdf_port_s=0.0)
+        self.n = dict(frames=0, tsdf_ref=0, tsdf_port=0)
+
+    def frame(self, f, tsdf="port", timed=True):
+        """one frame through extract + the three searches + one TSDF integration (`tsdf`: "ref", "port" or "both")"""
+        from plvs_b200 import scenario
+        from plvs_b200.matcher import featvec
+        a, O, OM, synth = self.a, self.O, self.OM, self.synth
+        img = synth.gray_frame(f, a.width, a.height); depth = synth.depth_frame(f, a.width, a.height); bgr = synth.bgr_frame(f, a.width, a.height)
+        t0 = time.perf_counter()
+        if self.ex is not None:
+            kp, desc, mono = self.ex(img)
+        else:
+            kp, desc, mono, _ = O.extract_port(img, a.nfeatures)
+        t1 = time.perf_counter()
+        cur = scenario.make_frame(kp, desc, depth, self.K, self.tab.scale); cur.level_sigma2 = self.tab.sigma2
+        t_match = 0.0
+        if self.prev is not None:
+            prev = self.prev
+            ql, _ = scenario.last_queries(prev, cur, self.K, synth.pose(f - 1), synth.pose(f))
+            qm, _ = scenario.map_queries(prev, cur, self.K, synth.pose(f - 1), synth.pose(f), seed=f)
+            fv1, fv2 = featvec(scenario.node_ids(cur.desc)), featvec(scenario.node_ids(prev.desc))
+            F12, ep = scenario.fundamental(self.K, synth.pose(f), synth.pose(f - 1))
+            z0, z1 = np.zeros(cur.n, np.uint8), np.zeros(prev.n, np.uint8)
+            if self.have_ref:
+                qc, z = OM.canonical_last_queries(ql)
+                t2 = time.perf_counter()
+                n1, a1 = OM.ref_search_by_projection_last(cur, qc, z, 15.0)
+                OM.ref_search_by_projection_map(cur, qm, 3.0, 0.8, claimed=(a1 >= 0).astype(np.uint8))
+                OM.ref_search_for_triangulation(cur, prev, fv1, fv2, z0, z1, F12, ep, check_ori=False)
+            else:
+                t2 = time.perf_counter()
+                n1, a1 = OM.search_by_projection_last(cur, ql, 15.0)
+                OM.search_by_projection_map(cur, qm, 3.0, 0.8, claimed=(a1 >= 0).astype(np.uint8))
+                OM.search_for_triangulation(cur, prev, fv1, fv2, z0, z1, F12, ep, check_ori=False)
+            t_match = time.perf_counter() - t2
+        self.prev = cur
+        t3 = time.perf_counter()
+        t_ref = t_port = None
+        if tsdf in ("port", "both"):
+            self.port_map.integrate(depth, synth.pose(f), bgr)
+            t_port = time.perf_counter() - t3
+        if tsdf in ("ref", "both") and self.ref_map is not None:
+            t4 = time.perf_counter()
+            with _quiet_stdout():
+                self.ref_map.integrate(depth, synth.pose(f), bgr)
+            t_ref = time.perf_counter() - t4
+        if timed:
+            self.t["extract_s"] += t1 - t0; self.t["match_s"] += t_match; self.n["frames"] += 1
+            if t_port is not None:
+                self.t["tsdf_port_s"] += t_port; self.n["tsdf_port"] += 1
+            if t_ref is not None:
+                self.t["tsdf_ref_s"] += t_ref; self.n["tsdf_ref"] += 1
+        return t_ref, t_port
+
+    def per_frame(self):
+        n = max(self.n["frames"], 1)
+        out = dict(extract_s=self.t["extract_s"] / n, match_s=self.t["match_s"] / n)
+        if self.n["tsdf_port"]:
+            out["tsdf_port_s"] = self.t["tsdf_port_s"] / self.n["tsdf_port"]
+        if self.n["tsdf_ref"]:
+            out["tsdf_ref_s"] = self.t["tsdf_ref_s"] / self.n["tsdf_ref"]
+        return out
+
+
 def run_reference_arm(a):
+    """The reference's own CPU implementation of the path on this box's host cores, K steps of `frames_per_step` frames like the b200 arm.
+    Every frame of a step goes through extraction and the three searches; the TSDF -- 5-6 s per scan in the reference's brute-force
+    open_chisel at C2 -- runs through the reference's own code for ONE frame of each step (the bounded sample) and through the restated TSDF
+    spread over all host threads (OpenMP) for the other frames.  The step time is the measured wall time of exactly that work, so the line
+    UNDERSTATES the reference's cost (value = frames_per_step / step time); cpu_baseline.sample spells the per-stage seconds out."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import tsdf as OT
+    import cv2
     threads = os.cpu_count() or 1
-    have_ref = OT.ref_available()
-    # each step = one frame of the same workload (a bounded sample: the CPU TSDF alone takes seconds per frame).  The
-    # warm-up frames run the multi-threaded restatement only; the timed frames run extract/match through the restatement with
-    # all host threads and the TSDF through the reference's own open_chisel code (oracle/_ref) for the first REF_FRAMES frames.
-    REF_FRAMES = 2
-    w = max(0, min(a.warmup, 1))
-    if w:
-        cpu_reference_run(a, w, threads, True)
-    t0 = time.perf_counter()
-    fps, stages = cpu_reference_run(a, a.steps, threads, True, tsdf_ref_frames=REF_FRAMES if have_ref else 0)
-    wall = time.perf_counter() - t0
-    port_fps = 1.0 / (stages["extract_s"] + stages["match_s"] + stages.get("tsdf_port_s", stages["tsdf_s"]))
-    kind = "reference" if have_ref else "port"
-    note = ("extract = cv2 primitives + C++ restatement (cv2.setNumThreads(n)), match = C++ restatement, TSDF = the reference's own open_chisel "
-            "sources compiled into oracle/_ref (single-threaded: Chisel.h:91 has its parallel_for commented out); 'port_value' = same run with "
-            "the restated TSDF spread over all host threads with OpenMP; rank 0 only") if have_ref else \
-           "CPU oracle (cv2 primitives + C++ restatement of the reference), all host threads: cv2.setNumThreads(n), TSDF chunks over OpenMP; rank 0 only"
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32+f32",
-            "data": "synthetic", "config": workload_config(a, {"frames_per_step": 1, "note": note}),
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "port_value": port_fps,
-                             "sample": f"{a.steps} frames of the same stream (TSDF through oracle/_ref on the first {stages.get('tsdf_ref_frames', 0)}), "
-                                       f"stage seconds/frame {json.dumps({k: round(v, 4) for k, v in stages.items()})}"},
+    cv2.setNumThreads(threads)
+    cp = CpuPath(a, threads)
+    B = a.batch
+    cp.frame(0, tsdf="both", timed=False)                  # map seed, untimed (both maps)
+    f = 1
+    for s in range(min(a.warmup, 1)):                      # bounded warm-up: one step, restated TSDF only
+        for b in range(B):
+            cp.frame(f, tsdf="port", timed=False); f += 1
+    step_s = []
+    for s in range(a.steps):
+        t0 = time.perf_counter()
+        twice = 0.0
+        for b in range(B):
+            t_ref, t_port = cp.frame(f, tsdf="both" if (b == 0 and cp.have_ref) else "port"); f += 1
+            if t_ref is not None and t_port is not None:
+                twice += t_port        # this frame ran BOTH TSDFs (the restated map has to see every frame): only the reference's counts towards the step
+        step_s.append(time.perf_counter() - t0 - twice)
+    pf = cp.per_frame()
+    mean_step = float(np.mean(step_s))
+    fps = B / mean_step
+    front_end = pf["extract_s"] + pf["match_s"]
+    kind = "reference" if cp.have_ref else "port"
+    note = ("every frame: extraction = the reference's own src/ORBextractor.cc (oracle/_ref/liborb_ref.so, OpenCV primitives restated in C and pinned to cv2), the three "
+            "searches = its own src/ORBmatcher.cc (libmatch_ref.so); TSDF = its own open_chisel (libchisel_ref.so, single-threaded: Chisel.h:91 has its parallel_for "
+            "commented out) on the first frame of each step, the restated TSDF over all host threads (OpenMP) on the other frames; rank 0 only") if cp.have_ref else \
+           "CPU oracle (C restatement of the reference), TSDF chunks over OpenMP with all host threads; rank 0 only"
+    all_ref_step = B * (front_end + pf.get("tsdf_ref_s", pf.get("tsdf_port_s", 0.0)))
+    line = {"impl": "reference", "metric": metric_name(a), "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1000.0 * mean_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32+f32",
+            "data": "synthetic", "config": workload_config(a, {"note": note}),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                             "sample": f"{a.steps} steps x {B} frames of the same stream; seconds/frame {json.dumps({k: round(v, 4) for k, v in pf.items()})}; "
+                                       f"reference TSDF on 1 of {B} frames per step, restated TSDF ({threads} threads) on the rest",
+                             "front_end_frames_per_s": 1.0 / front_end,
+                             "all_frames_through_reference_tsdf_frames_per_s": B / all_ref_step,
+                             "all_frames_through_restated_tsdf_frames_per_s": 1.0 / (front_end + pf.get("tsdf_port_s", pf.get("tsdf_ref_s", 0.0)))},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
-            "wall_s": wall}
+            "wall_s": float(np.sum(step_s))}
     print(json.dumps(line), flush=True)
 
 
@@ -236,70 +288,8 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def run_b200_arm(a):
-    import torch
-    sys.setswitchinterval(1e-4)          # 4 stage threads: hand the GIL over quickly when a library call returns
-    import torch.distributed as dist
-    from plvs_b200 import _lib
-    from plvs_b200.pipeline import StreamData, HotPath
-
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        # NCCL writes its version banner (NCCL_DEBUG=VERSION/INFO) to stdout by default; stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    lib = _lib.load()
-    B, K, W = a.batch, a.steps, a.warmup
-    nframes = 1 + (W + K) * B            # frame 0 only seeds the map / the "last frame"
-    data = StreamData(nframes, a.width, a.height, stream=rank, pinned=True)
-    hp = HotPath(data, a.nfeatures, a.voxel, a.far, max_blocks=49152, device=local, batch=B)
-    hp.prepare()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    sampler = ClockSampler(local); sampler.start()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def run(resident, timed_profile=0):
-        hp.tsdf.Reset()
-        hp.tsdf.integrate(data.depth[0], data.poses[0], data.bgr[0])           # seed (untimed)
-        hp.run_stream(1, W, resident)                                          # warm-up steps (untimed)
-        lib.plvs_set_profiling(timed_profile)
-        lib.plvs_tsdf_kernel_times(hp.tsdf._h, None, None, 1)
-        for ex in (hp.ex, hp.ex2):
-            if ex is not None:
-                lib.plvs_orb_kernel_times(ex._h, None, None, 1)
-        for m in (hp.m_track, hp.m_map, hp.m_tri):
-            lib.plvs_match_kernel_times(m._h, None, None, 1)
-        barrier()
-        mark = sampler.mark()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        t0 = time.perf_counter()
-        # K steps through the 4-stage pipeline (extract | projection searches | triangulation | TSDF); returns when drained
-        agg = hp.run_stream(1 + W * B, K, resident, per_step=lambda s: flush.fill_(s & 0xff))   # L2 flush once per step
-        e1.record()
-        barrier()
-        wall = time.perf_counter() - t0
-        clocks = sampler.window(mark)
-        t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        lib.plvs_set_profiling(0)
-        return float(t_ms.item()), wall, clocks, agg
-
+def kernel_table(lib, hp):
     import ctypes as C
-    # ---- value arm: inputs resident in HBM ----------------------------------------------------------------
-    hp.upload_inputs()
-    # timed run: only the roofline kernel (k_integrate) carries events (2 per frame); the per-kernel table comes from a
-    # second, untimed pass with all events on
-    # order: the per-kernel profile pass runs first (its result is not a bench value; it also settles every data-dependent
-    # buffer size and the clocks), then the timed passes
-    run(resident=True, timed_profile=7)
     ktimes = {}
     ms = np.zeros(12, np.float32); cnt = np.zeros(12, np.int32)
     lib.plvs_tsdf_kernel_times(hp.tsdf._h, ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 0)
@@ -318,17 +308,134 @@ def run_b200_arm(a):
         mm += ms; mc += cnt
     for i, nme in enumerate(("match.grid", "match.candidates", "match.resolve", "match.triangulate")):
         ktimes[nme] = (float(mm[i]), int(mc[i]))
-    t_ms, wall, clocks, agg = run(resident=True, timed_profile=4 | 8)
+    return ktimes
+
+
+def latency_block(hp, data, f_first, n):
+    """per-call latency of the single-frame surfaces (include/ORBextractor.h:86, ORBmatcher.h:68-97, ChiselServer.h:190-286), one call at a
+    time with nothing else on the GPU: what a sequential tracker sees per frame.  Host buffers in, host results out; median over n frames."""
+    from plvs_b200.matcher import Frame
+    d = data
+    sf, s2 = hp.ex.mvScaleFactor, hp.ex.mvLevelSigma2
+    t = {k: [] for k in ("extract_1_frame", "search_by_projection_last", "search_by_projection_map", "search_for_triangulation", "tsdf_scan")}
+    hp.tsdf.stats()
+    for f in range(f_first, f_first + n):
+        p = hp.prepared[f]
+        t0 = time.perf_counter()
+        mono, kp, desc = hp.ex(d.gray[f])
+        t1 = time.perf_counter()
+        dv = hp.ex.device_result(0)
+        cur = Frame(None, None, d.w, d.h, sf, s2, uright=hp.frames[f].uright, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key))
+        t2 = time.perf_counter()
+        n1, a1 = hp.m_track.SearchByProjectionLast(cur, p["ql"], 15.0)
+        t3 = time.perf_counter()
+        claimed = (a1 >= 0).astype(np.uint8)
+        t4 = time.perf_counter()
+        hp.m_track.SearchByProjectionMap(cur, p["qm"], 3.0, claimed=claimed, nnratio=0.8)
+        t5 = time.perf_counter()
+        k1 = Frame(kp, desc, d.w, d.h, sf, s2, uright=hp.frames[f].uright, bf=d.K["bf"])
+        t6 = time.perf_counter()
+        hp.m_tri.SearchForTriangulation(k1, hp.frames[f - 1], p["fv1"], p["fv2"], p["has1"], p["has2"], p["F12"], p["ep"], False, False)
+        t7 = time.perf_counter()
+        hp.tsdf.integrate(d.depth[f], d.poses[f], d.bgr[f]); hp.tsdf.stats()            # stats() waits for the scan
+        t8 = time.perf_counter()
+        for k, v in zip(t, (t1 - t0, t3 - t2, t5 - t4, t7 - t6, t8 - t7)):
+            t[k].append(v * 1e3)
+    out = {k + "_ms": round(float(np.median(v)), 4) for k, v in t.items()}
+    out["frame_ms"] = round(float(np.median(np.sum([t[k] for k in t], 0))), 4)
+    out["note"] = (f"median over {n} consecutive frames, one synchronous call at a time through the Python mirror of the single-frame surfaces "
+                   "(host image in, host keypoints / assignments out); the pipeline value above overlaps these calls across stages and batches frames in the extractor")
+    return out
+
+
+def run_b200_arm(a):
+    import torch
+    sys.setswitchinterval(1e-4)          # python driver: 4 stage threads hand the GIL over quickly when a library call returns
+    import torch.distributed as dist
+    import ctypes as C
+    from plvs_b200 import _lib
+    from plvs_b200.pipeline import StreamData, HotPath
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION/INFO) to stdout by default; stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    B, K, W, R = a.batch, a.steps, a.warmup, max(1, a.repeats)
+    n_lat = 0 if a.no_latency else 16
+    nframes = 1 + (W + K) * B + n_lat            # frame 0 only seeds the map / the "last frame"
+    data = StreamData(nframes, a.width, a.height, stream=rank, pinned=True)
+    hp = HotPath(data, a.nfeatures, a.voxel, a.far, max_blocks=a.max_blocks, device=local, batch=B)
+    hp.prepare()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    sampler = ClockSampler(local); sampler.start()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def stream(f0, nsteps, resident, timed):
+        if a.driver == "native":
+            return hp.run_stream_native(f0, nsteps, resident, flush=(flush.data_ptr(), flush.numel()) if timed else None)
+        return hp.run_stream(f0, nsteps, resident, per_step=(lambda s: flush.fill_(s & 0xff)) if timed else None)
+
+    def run(resident, timed_profile=0):
+        hp.tsdf.Reset()
+        hp.tsdf.integrate(data.depth[0], data.poses[0], data.bgr[0])           # seed (untimed)
+        stream(1, W, resident, False)                                          # warm-up steps (untimed)
+        lib.plvs_set_profiling(timed_profile)
+        barrier()
+        lib.plvs_io_bytes(None, None, 1)
+        mark = sampler.mark()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        # K steps through the 4-stage pipeline (extract | projection searches | triangulation | TSDF); returns when drained
+        agg = stream(1 + W * B, K, resident, True)                             # L2 flush once per step, inside the timed region
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        h2d, d2h = C.c_longlong(), C.c_longlong()
+        lib.plvs_io_bytes(C.byref(h2d), C.byref(d2h), 0)
+        clocks = sampler.window(mark)
+        t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        lib.plvs_set_profiling(0)
+        return dict(ms=float(t_ms.item()), wall=wall, clocks=clocks, agg=agg, h2d=h2d.value, d2h=d2h.value)
+
+    def reset_timers():
+        lib.plvs_tsdf_kernel_times(hp.tsdf._h, None, None, 1)
+        for ex in (hp.ex, hp.ex2):
+            if ex is not None:
+                lib.plvs_orb_kernel_times(ex._h, None, None, 1)
+        for m in (hp.m_track, hp.m_map, hp.m_tri):
+            lib.plvs_match_kernel_times(m._h, None, None, 1)
+
+    # ---- value arm: inputs resident in HBM ----------------------------------------------------------------
+    hp.upload_inputs()
+    # order: the per-kernel profile pass runs first (every kernel carries events; its result is not a bench value, it also settles every
+    # data-dependent buffer size and the clocks), then the timed passes in which only the roofline kernel (k_integrate) carries events
+    reset_timers()
+    run(resident=True, timed_profile=7)
+    ktimes = kernel_table(lib, hp)
+    reset_timers()
+    val = [run(resident=True, timed_profile=4 | 8) for _ in range(R)]
     ms = np.zeros(12, np.float32); cnt = np.zeros(12, np.int32)
     lib.plvs_tsdf_kernel_times(hp.tsdf._h, ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 0)
-    integ_live = (float(ms[2]), int(cnt[2]))
+    integ_ms, integ_n = float(ms[2]), int(cnt[2])              # k_integrate over all R timed passes (and their warm-ups)
     frames = K * B
-    value = world * frames / (t_ms / 1000.0)
+    vals = sorted(world * frames / (r["ms"] / 1000.0) for r in val)
+    med = sorted(val, key=lambda r: r["ms"])[len(val) // 2]
+    value, t_ms = world * frames / (med["ms"] / 1000.0), med["ms"]
     launches_per_step = hp.launches_per_frame() * B
 
     # roofline of the dominant kernel: TSDF voxel update.  Algorithmic bytes per launch (SURVEY.md §8d):
     # depth 4*W*H + colour 3*W*H + n_updated_blocks * 4096 voxels * 12 B (sdf f32 + weight f32 + rgba) * 2 (read+write)
-    integ_ms, integ_n = integ_live
     tst = hp.tsdf.stats()          # running totals since the Reset at the start of the last pass (seed + warm-up + timed scans)
     upd_per_launch = tst["total_updated"] / max(tst["total_integrations"], 1)
     vis_per_launch = tst["total_candidates"] / max(tst["total_integrations"], 1)
@@ -339,24 +446,32 @@ def run_b200_arm(a):
         achieved = alg_bytes / (integ_ms / integ_n / 1000.0) / 1e9
         # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (not measurable live)
         traffic, traffic_src = None, None
-        tp = ROOT / "profiles" / "r01_k_integrate_traffic.json"
-        if tp.exists():
-            try:
-                tj = json.loads(tp.read_text())
-                traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj.get("source")
-            except Exception:
-                pass
+        for name in (f"r02_k_integrate_traffic_{a.config}.json", "r01_k_integrate_traffic.json" if a.config == "c2" else ""):
+            tp = ROOT / "profiles" / name
+            if name and tp.exists():
+                try:
+                    tj = json.loads(tp.read_text())
+                    traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj.get("source")
+                    break
+                except Exception:
+                    pass
         roof = {"kernel": "k_integrate (TSDF voxel update)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": integ_ms / integ_n,
-                "updated_blocks_per_launch": upd_per_launch}
+                "launches_timed": integ_n, "updated_blocks_per_launch": upd_per_launch}
     gpu_time_ms = sum(v[0] for v in ktimes.values())
 
-    # ---- e2e arm: host (pinned) buffers through the public classes, copies inside the timed region ---------
-    t2_ms, wall2, clocks2, agg2 = run(resident=False)
-    e2e_value = world * frames / (t2_ms / 1000.0)
-    # every host->device byte of a step: the images (gray u8 + depth f32 + bgr u8x3) and what the searches stage per frame
-    h2d = B * data.input_bytes_per_frame() + int(sum(hp.search_h2d_bytes(f) for f in range(1 + W * B, 1 + (W + K) * B)) / K)
-    d2h = int(B * (agg2.get("keypoints", 0) / max(frames, 1)) * 60 + B * 3 * a.nfeatures * 4)
+    # ---- e2e arm: host (pinned) buffers through the C ABI, copies inside the timed region -------------------
+    e2e = [run(resident=False) for _ in range(R)]
+    e2e_vals = sorted(world * frames / (r["ms"] / 1000.0) for r in e2e)
+    emed = sorted(e2e, key=lambda r: r["ms"])[len(e2e) // 2]
+    e2e_value = world * frames / (emed["ms"] / 1000.0)
+
+    # ---- per-call latency of the single-frame surfaces (untimed region, rank-local) -------------------------
+    latency = None
+    if n_lat:
+        hp.tsdf.Reset(); hp.tsdf.integrate(data.depth[0], data.poses[0], data.bgr[0])
+        latency_block(hp, data, 1, min(4, n_lat))                       # warm the single-frame shapes
+        latency = latency_block(hp, data, 1 + (W + K) * B, n_lat)
 
     sampler.stop()
     if world > 1:
@@ -364,34 +479,52 @@ def run_b200_arm(a):
         dist.destroy_process_group()      # every rank leaves the group here; rank 0 still has the (CPU-only) baseline to time
     if rank != 0:
         return
-    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K,
+    agg = med["agg"]
+    line = {"metric": metric_name(a), "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32+f32", "data": "synthetic",
-            "config": workload_config(a, {"l2": "256 MiB device buffer rewritten between steps (inside the timed region); every step reads new frames",
-                                          "timing": "torch.cuda.Event pair around K steps, barrier+synchronize both sides, max over ranks; "
-                                                    "library calls synchronise their own streams before returning",
+            "config": workload_config(a, {"l2": "256 MiB device buffer rewritten at the start of every step (inside the timed region); every step reads new frames",
+                                          "timing": f"torch.cuda.Event pair around K steps, barrier+synchronize both sides, max over ranks; median of {R} timed passes "
+                                                    "(each: map reset, seed scan, W warm-up steps, K timed steps); library calls synchronise their own streams before returning",
                                           "threads": "4 host threads = the reference's thread roles, each with its own library handle/CUDA stream: frame construction (ORB extraction, "
-                                                     "batches of 8 frames), Tracking (2x SearchByProjection per frame), LocalMapping (SearchForTriangulation per frame), "
-                                                     "PointCloudMapping (TSDF per frame); consecutive steps overlap as a software pipeline, the timed region ends when all "
-                                                     "stages have drained"}),
-            "roofline": roof, "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t2_ms / K},
-            "gpu_launches": int(round(launches_per_step * K)), "clocks": clocks,
+                                                     f"batches of {B} frames: a throughput construct -- the reference's operator() takes one frame, see `latency`), Tracking (2x "
+                                                     "SearchByProjection per frame), LocalMapping (SearchForTriangulation per frame), PointCloudMapping (TSDF per frame); consecutive "
+                                                     "steps overlap as a software pipeline, the timed region ends when all stages have drained; the searches' queries are prepared "
+                                                     "before the timed region (caller-side work, SURVEY.md §8d), which a live tracker would do between the calls",
+                                          "driver": "plvs_pipeline_run (C++ stage threads over the C ABI)" if a.driver == "native" else "Python stage threads over the ctypes mirror"}),
+            "value_passes": [round(v, 1) for v in vals],
+            "roofline": roof,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(emed["h2d"] / K), "d2h_bytes_per_step": int(emed["d2h"] / K),
+                    "ms_per_step": emed["ms"] / K, "passes": [round(v, 1) for v in e2e_vals],
+                    "bytes": "counted by the library at every copy it issues and every result written into mapped host memory (plvs_io_bytes)"},
+            "gpu_launches": int(round(launches_per_step * K)), "clocks": med["clocks"],
             "kernel_ms_per_step": {k: round(v[0] / K, 4) for k, v in ktimes.items()}, "gpu_busy_frac": gpu_time_ms / t_ms,
             "per_step": {"keypoints": agg.get("keypoints", 0) / K, "matches": agg.get("matches", 0) / K,
                          "tsdf_blocks_visited_per_scan": vis_per_launch, "tsdf_blocks_updated_per_scan": upd_per_launch,
                          "match_rounds_last_call": hp.match_rounds()},
-            "stage_busy_ms_per_step": {k[5:-2]: round(v / K * 1e3, 3) for k, v in agg.items() if k.startswith("busy_")}, "wall_s": [wall, wall2]}
-    if not a.no_cpu_baseline:
-        from oracle import tsdf as OT
-        have_ref = OT.ref_available()
-        fps, stages = cpu_reference_run(a, a.cpu_frames, 1, False, tsdf_ref_frames=1 if have_ref else 0)
-        port_fps = 1.0 / (stages["extract_s"] + stages["match_s"] + stages.get("tsdf_port_s", stages["tsdf_s"]))
-        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference" if have_ref else "port", "port_value": port_fps,
-                                "sample": f"{a.cpu_frames} frames of stream 0 (after a 1-frame map seed), faithful mode: 1 thread "
-                                          f"(cv2.setNumThreads(1), single-threaded chunk loop like Chisel.h:91); extract = real OpenCV primitives + "
-                                          f"restated octree/descriptor code, match = restatement, TSDF = "
-                                          + ("the reference's own open_chisel sources (oracle/_ref, 1 frame; 'port_value'/'tsdf_port_s' = the restated TSDF)"
-                                             if have_ref else "restatement") +
-                                          f"; seconds/frame {json.dumps({k: round(v, 4) for k, v in stages.items()})}; host has {os.cpu_count()} cpus"}
+            "stage_busy_ms_per_step": {k[5:-2]: round(v / K * 1e3, 3) for k, v in agg.items() if k.startswith("busy_")},
+            "wall_s": [round(med["wall"], 4), round(emed["wall"], 4)]}
+    if latency:
+        line["latency"] = latency
+    if not a.no_cpu_baseline and world == 1:
+        import cv2
+        cv2.setNumThreads(1)
+        cp = CpuPath(a, 1)
+        cp.frame(0, tsdf="both", timed=False)
+        for f in range(1, a.cpu_frames + 1):
+            cp.frame(f, tsdf="both" if f == 1 else "port")
+        pf = cp.per_frame()
+        tsdf_s = pf.get("tsdf_ref_s", pf["tsdf_port_s"])
+        fps = 1.0 / (pf["extract_s"] + pf["match_s"] + tsdf_s)
+        front = 1.0 / (pf["extract_s"] + pf["match_s"])
+        port = 1.0 / (pf["extract_s"] + pf["match_s"] + pf["tsdf_port_s"])
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference" if cp.have_ref else "port",
+                                "front_end_frames_per_s": front, "port_value": port,
+                                "sample": f"{a.cpu_frames} frames of stream 0 (after a 1-frame map seed), faithful mode: 1 thread; extract + match = "
+                                          + ("the reference's own ORBextractor.cc / ORBmatcher.cc (oracle/_ref), TSDF = its own open_chisel on 1 frame "
+                                             "('port_value' / tsdf_port_s = the restated TSDF)" if cp.have_ref else "the C restatement") +
+                                          f"; seconds/frame {json.dumps({k: round(v, 4) for k, v in pf.items()})}; host has {os.cpu_count()} cpus"}
+        line["speedup_vs_cpu_baseline"] = {"e2e_vs_whole_path": e2e_value / fps, "e2e_vs_front_end_only": e2e_value / front, "e2e_vs_restated_tsdf_path": e2e_value / port,
+                                           "note": "same run, same box; the front-end figure is what north_star's >=30x target is about"}
     print(json.dumps(line), flush=True)
 
 

@@ -64,6 +64,9 @@ int plvs_set_profiling(int mask);
 #define PLVS_TSDF_K_COMMIT 3
 #define PLVS_TSDF_K_MESH 4
 #define PLVS_K_SLOTS 12
+/* bytes the library has moved over the bus since the last reset (process-wide): host->device and device->host, counted at every copy the
+ * library issues and at every result a kernel writes straight into mapped host memory */
+int plvs_io_bytes(long long* h2d, long long* d2h, int reset);
 /* pinned host memory for the e2e path (cudaHostAlloc / cudaFreeHost) */
 int plvs_host_alloc(void** p, size_t bytes);
 int plvs_host_free(void* p);
@@ -519,6 +522,50 @@ int plvs_tsdf_merge_packed(plvs_tsdf* h, const int32_t* d_keys, const float* d_w
  * any number of items per call. */
 int plvs_tsdf_export_packed_rgba(plvs_tsdf* h, int32_t* d_keys, float* d_wsdf, float* d_w, uint32_t* d_rgba, int cap, int* n_out);
 int plvs_tsdf_merge_packed_rgba(plvs_tsdf* h, const int32_t* d_keys, const float* d_wsdf, const float* d_w, const uint32_t* d_rgba, int n);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Stream driver (host code only; plvs_b200/csrc/pipeline.cu)                                   */
+/* ------------------------------------------------------------------------------------------ */
+/* The reference's thread roles around the entry points above, as native threads: frame construction (plvs_orb_extract_batch on batches of
+ * `batch` frames), Tracking (plvs_match_projection_last + plvs_match_projection_map per frame on the device-resident keypoints), LocalMapping
+ * (plvs_match_triangulation against the previous frame) and PointCloudMapping (plvs_tsdf_integrate_depth per frame), src/System.cc:317-398.
+ * It calls nothing but those public entry points; every call is synchronous for its stage, consecutive steps overlap as a pipeline.  The
+ * caller-side inputs of the searches (SURVEY.md §8d "Matcher queries": projected map points, feature vectors, F12) are prepared per frame by the
+ * caller, as Tracking / LocalMapping would.  bench.py times this function. */
+typedef struct {
+    int32_t valid;                    /* 0 = no searches for this frame (the first frame of a stream) */
+    int32_t n_ql, n_qm;
+    const plvs_last_query* ql;        /* SearchByProjection(Cur, Last): the last frame's map points, projected */
+    const plvs_mp_query* qm;          /* SearchByProjection(F, vpMapPoints): the local map points in view */
+    const float* uright;              /* mvuRight of this frame (host, one per keypoint) or NULL */
+    plvs_featvec fv_cur, fv_last;     /* DBoW2 feature vectors of this frame and the previous one (host) */
+    const uint8_t* has_cur;           /* per keypoint: already has a map point (this frame / the previous one) */
+    const uint8_t* has_last;
+    float F12[9], ep[2];              /* fundamental matrix and epipole of (this frame, previous frame) */
+    plvs_frame_view last;             /* the previous frame (host view): KeyFrame 2 of SearchForTriangulation */
+} plvs_pipeline_frame;
+
+typedef struct {
+    int32_t device, width, height, batch, n_steps, first_frame, cap;   /* cap: keypoint capacity per frame of the extractor outputs */
+    int32_t inputs_on_device;         /* gray / depth / bgr are device pointers (inputs resident in HBM) */
+    const uint8_t* gray;              /* frame f at gray + f*w*h */
+    const float* depth;               /* depth + f*w*h (metres) */
+    const uint8_t* bgr;               /* bgr + f*w*h*3, or NULL for a map without colour */
+    const float* poses;               /* Twc of frame f at poses + 12*f */
+    const plvs_pipeline_frame* frames;    /* indexed by absolute frame number */
+    plvs_frame_view view_template;    /* bounds, grid cell sizes, scale factors, level sigmas, bf shared by the stream's frames */
+    float th_last, th_map, nnratio_map;   /* 15, 3, 0.8 in Tracking */
+    void* flush_buf; size_t flush_bytes;  /* optional device buffer rewritten at the start of every step (evicts L2 between steps) */
+} plvs_pipeline_job;
+
+typedef struct {
+    int64_t keypoints, matches;
+    double wall_s, busy_extract_s, busy_track_s, busy_tri_s, busy_map_s;
+} plvs_pipeline_stats;
+
+/* steps first_frame + s*batch .. for s in [0, n_steps); ex[s & 1] extracts step s.  Returns when every stage has drained. */
+int plvs_pipeline_run(plvs_orb* const ex[2], plvs_match* m_track, plvs_match* m_tri, plvs_tsdf* tsdf, const plvs_pipeline_job* job,
+                      plvs_pipeline_stats* out);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,19 @@ from .orb import lib
 from plvs_b200 import _lib as _abi
 
 
+def default_params(**kw):
+    """ChiselServerParams() defaults (Thirdparty/chisel_server/src/ChiselServer.cpp:44-69) in the flat parameter record, overridden by keywords --
+    built here, on the oracle side, so the CPU arm of bench.py needs nothing from libplvs_b200.so (the product's copy: plvs_tsdf_default_params)"""
+    p = _abi.TsdfParams()
+    p.voxel_resolution = 0.015
+    p.trunc_quad, p.trunc_linear, p.trunc_const, p.trunc_scale = 0.0019, -0.00152, 0.001504, 6.0
+    p.weight, p.use_carving, p.carving_dist, p.use_color = 1.0, 1, 0.05, 1
+    p.near_plane, p.far_plane, p.max_blocks = 0.05, 5.0, 65536
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
 class _Prefixed:
     """view of a ctypes library that prepends a prefix to every symbol (orc_ = restatement, ref_ = compiled reference)"""
     def __init__(self, l, prefix):

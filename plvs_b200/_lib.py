@@ -68,6 +68,25 @@ class TsdfStats(C.Structure):
                 ("total_updated", C.c_int64), ("total_candidates", C.c_int64), ("total_integrations", C.c_int64)]
 
 
+class PipelineFrame(C.Structure):
+    _fields_ = [("valid", C.c_int32), ("n_ql", C.c_int32), ("n_qm", C.c_int32), ("ql", C.c_void_p), ("qm", C.c_void_p), ("uright", C.c_void_p),
+                ("fv_cur", FeatVec), ("fv_last", FeatVec), ("has_cur", C.c_void_p), ("has_last", C.c_void_p),
+                ("F12", C.c_float * 9), ("ep", C.c_float * 2), ("last", FrameView)]
+
+
+class PipelineJob(C.Structure):
+    _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("batch", C.c_int32), ("n_steps", C.c_int32),
+                ("first_frame", C.c_int32), ("cap", C.c_int32), ("inputs_on_device", C.c_int32),
+                ("gray", C.c_void_p), ("depth", C.c_void_p), ("bgr", C.c_void_p), ("poses", C.c_void_p), ("frames", C.c_void_p),
+                ("view_template", FrameView), ("th_last", C.c_float), ("th_map", C.c_float), ("nnratio_map", C.c_float),
+                ("flush_buf", C.c_void_p), ("flush_bytes", C.c_size_t)]
+
+
+class PipelineStats(C.Structure):
+    _fields_ = [("keypoints", C.c_int64), ("matches", C.c_int64), ("wall_s", C.c_double), ("busy_extract_s", C.c_double),
+                ("busy_track_s", C.c_double), ("busy_tri_s", C.c_double), ("busy_map_s", C.c_double)]
+
+
 _lib = None
 
 
@@ -154,6 +173,8 @@ def declare(lib):
     lib.plvs_tsdf_merge_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.plvs_tsdf_export_packed_rgba.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.plvs_tsdf_merge_packed_rgba.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.plvs_io_bytes.argtypes = [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]
+    lib.plvs_pipeline_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     for name in ("plvs_match_destroy", "plvs_tsdf_destroy"):
         if hasattr(lib, name):
             getattr(lib, name).restype = None

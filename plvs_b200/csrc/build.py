@@ -3,7 +3,7 @@ import os, pathlib, subprocess, sys
 
 HERE = pathlib.Path(__file__).resolve().parent
 OUT = HERE.parent / "libplvs_b200.so"
-SRCS = ["core.cu", "orb.cu", "match.cu", "tsdf.cu", "bow.cu"]
+SRCS = ["core.cu", "orb.cu", "match.cu", "tsdf.cu", "bow.cu", "pipeline.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "--fmad=false",                      # bit-exact fp32 paths: contraction is opted into per kernel, never implicit

@@ -9,9 +9,23 @@
 #include <vector>
 #include "../../include/plvs_b200.h"
 
+#include <atomic>
+
 namespace plvs {
 
 void set_error(const char* fmt, ...);
+
+// Bytes that crossed the bus, counted where they are copied (bench.py's e2e block reports them): every cudaMemcpyAsync of the library goes
+// through counted_memcpy_async (the macro below), kernels that write results straight into mapped host memory add theirs with count_d2h.
+extern std::atomic<long long> g_io_bytes[2];       // [0] host->device, [1] device->host
+inline void count_h2d(size_t n) { g_io_bytes[0].fetch_add((long long)n, std::memory_order_relaxed); }
+inline void count_d2h(size_t n) { g_io_bytes[1].fetch_add((long long)n, std::memory_order_relaxed); }
+inline cudaError_t counted_memcpy_async(void* dst, const void* src, size_t n, cudaMemcpyKind kind, cudaStream_t st = 0)
+{
+    if (kind == cudaMemcpyHostToDevice) count_h2d(n); else if (kind == cudaMemcpyDeviceToHost) count_d2h(n);
+    return cudaMemcpyAsync(dst, src, n, kind, st);
+}
+#define cudaMemcpyAsync(...) ::plvs::counted_memcpy_async(__VA_ARGS__)
 
 #define PLVS_CUDA(expr)                                                                       \
     do {                                                                                      \

@@ -5,6 +5,7 @@
 
 namespace plvs {
 int g_profiling = 0;
+std::atomic<long long> g_io_bytes[2];
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...)
 {
@@ -21,6 +22,14 @@ const char* plvs_version(void) { return "plvs_b200 0.1 (sm_100a)"; }
 const char* plvs_last_error(void) { return plvs::g_err; }
 
 int plvs_set_profiling(int mask) { plvs::g_profiling = mask; return PLVS_OK; }
+
+int plvs_io_bytes(long long* h2d, long long* d2h, int reset)
+{
+    if (h2d) *h2d = plvs::g_io_bytes[0].load();
+    if (d2h) *d2h = plvs::g_io_bytes[1].load();
+    if (reset) { plvs::g_io_bytes[0] = 0; plvs::g_io_bytes[1] = 0; }
+    return PLVS_OK;
+}
 
 int plvs_device_count(void)
 {

@@ -1107,6 +1107,7 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         while (h->cap < mx) h->cap *= 2;       // a window held more candidates than reserved: redo with room (exactness first)
     }
     std::memcpy(assign, h->p_assign.h, (size_t)n * 4);
+    count_d2h((size_t)n * 4 + 16);               // the kernel wrote assign[n] and the result record into mapped host memory
     *nmatches = h->p_result.h[0];
     h->last_rounds = h->p_result.h[1];
     h->last_launches = launches;
@@ -1384,6 +1385,7 @@ int plvs_match_triangulation(plvs_match* h, const plvs_frame_view* kf1, const pl
     PLVS_CUDA(cudaStreamSynchronize(st));
     h->timer.collect();
     std::memcpy(match12, h->p_assign.h, (size_t)n1 * 4);
+    count_d2h((size_t)n1 * 4 + 16);
     *nmatches = h->p_result.h[0];
     h->last_launches = 3;
     return PLVS_OK;
@@ -1465,6 +1467,7 @@ int plvs_match_bow_kf(plvs_match* h, const plvs_frame_view* kf1, const plvs_fram
     PLVS_CUDA(cudaStreamSynchronize(st));
     h->timer.collect();
     std::memcpy(match12, h->p_assign.h, (size_t)n1 * 4);
+    count_d2h((size_t)n1 * 4 + 16);
     *nmatches = h->p_result.h[0];
     h->last_launches = 3;
     return PLVS_OK;

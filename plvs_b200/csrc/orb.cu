@@ -517,6 +517,7 @@ static int extract_impl(plvs_orb* o, int batch, const uint8_t* gray, int w, int 
     o->stats.pyramid_pixels = 0;
     for (int l = 0; l < nl; ++l) o->stats.pyramid_pixels += (int64_t)o->lv[l].w * o->lv[l].h;
     o->stats.candidates = ncand; o->stats.keypoints = nkp; o->stats.kernel_launches = launches;
+    count_d2h((size_t)nkp * (sizeof(plvs_keypoint) + 32) + (size_t)batch * (nl + 1) * 4);     // keypoints + descriptors + counters written into mapped host memory by the kernels
     {
         const auto tp4 = std::chrono::steady_clock::now();
         auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<float, std::milli>(b - a).count(); };

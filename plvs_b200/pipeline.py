@@ -7,12 +7,13 @@ ORBmatcher, ChiselServer) over a synthetic RGB-D stream the way PLVS's threads d
 Caller-side work that is NOT part of the hot path (building map-point / last-frame queries from poses and
 depth) is precomputed once by `prepare()` so the timed region contains only the hot path."""
 import ctypes as C
+import os
 import threading
 import time
 import numpy as np
 
 from . import _lib, synth, scenario, tsdf as T
-from .matcher import ORBmatcher, Frame, featvec
+from .matcher import ORBmatcher, Frame, featvec, featvec_struct
 from .orb import ORBextractor, KP_DTYPE
 
 
@@ -37,7 +38,7 @@ class PinnedArray:
 class StreamData:
     """Synthetic inputs of one camera stream: gray u8, depth f32, bgr u8 and poses for `n` frames."""
 
-    def __init__(self, n, w, h, stream=0, pinned=True):
+    def __init__(self, n, w, h, stream=0, pinned=True, workers=None):
         self.n, self.w, self.h, self.stream = n, w, h, stream
         self.K = synth.intrinsics(w, h)
         mk = (lambda s, d: PinnedArray(s, d)) if pinned else None
@@ -50,8 +51,14 @@ class StreamData:
         self.depth = alloc((n, h, w), np.float32)
         self.bgr = alloc((n, h, w, 3), np.uint8)
         self.poses = np.zeros((n, 3, 4), np.float32)
+        # rendering a frame is pure numpy (about 0.2 s at VGA, 1.7 s at 1080p): long or large streams are rendered by worker processes
+        grays = None
+        if workers is None:
+            workers = min(32, os.cpu_count() or 1) if n * w * h >= 64 * 640 * 480 else 0
+        if workers > 1:
+            grays = synth.render_gray_parallel(n, w, h, stream, min(workers, n))       # None if the worker processes could not be used
         for f in range(n):
-            self.gray[f] = synth.gray_frame(f, w, h, stream)
+            self.gray[f] = grays[f] if grays is not None else synth.gray_frame(f, w, h, stream)
             self.depth[f] = synth.depth_frame(f, w, h, stream)
             self.bgr[f] = np.stack([self.gray[f], np.roll(self.gray[f], 3, 1), 255 - self.gray[f]], -1)
             self.poses[f] = synth.pose(f)
@@ -315,6 +322,68 @@ class HotPath:
         if err:
             raise err[0]
         return out
+
+    # ---- timed: the same pipeline on native threads (plvs_b200/csrc/pipeline.cu) -----------------------------------------------
+    def _native_job(self):
+        """flat per-frame records for plvs_pipeline_run: pointers into the arrays prepare() built (kept alive by self)"""
+        if getattr(self, "_job_frames", None) is not None:
+            return self._job_frames
+        d = self.d
+        recs = (_lib.PipelineFrame * d.n)()
+        keep = []
+        for f in range(d.n):
+            p = self.prepared[f]
+            r = recs[f]
+            if p is None:
+                r.valid = 0
+                continue
+            cur, last = self.frames[f], self.frames[f - 1]
+            r.valid = 1
+            r.n_ql, r.n_qm = len(p["ql"]), len(p["qm"])
+            r.ql, r.qm = p["ql"].ctypes.data, p["qm"].ctypes.data
+            r.uright = cur.uright.ctypes.data
+            r.fv_cur, r.fv_last = featvec_struct(p["fv1"]), featvec_struct(p["fv2"])
+            r.has_cur, r.has_last = p["has1"].ctypes.data, p["has2"].ctypes.data
+            F12 = np.ascontiguousarray(p["F12"], np.float32).reshape(9); ep = np.ascontiguousarray(p["ep"], np.float32)
+            for i in range(9):
+                r.F12[i] = float(F12[i])
+            r.ep[0], r.ep[1] = float(ep[0]), float(ep[1])
+            r.last = last.view()
+            keep.append((cur, last, p))
+        self._job_keep, self._job_frames = keep, recs
+        return recs
+
+    def run_stream_native(self, f0, nsteps, resident=False, flush=None):
+        """HotPath.run_stream with the four stage threads in C++ (plvs_pipeline_run): the same calls in the same order per stage, without the
+        interpreter between them.  `flush` = (device pointer, bytes) of a buffer rewritten at the start of every step, or None."""
+        d = self.d
+        if self.ex2 is None:
+            self.ex2 = ORBextractor(self.ex.nfeatures, 1.2, 8, 20, 7, device=self.device)
+        recs = self._native_job()
+        job = _lib.PipelineJob()
+        job.device, job.width, job.height, job.batch, job.n_steps, job.first_frame = self.device, d.w, d.h, self.batch, nsteps, f0
+        job.cap = self.ex._cap
+        job.inputs_on_device = int(resident)
+        if resident:
+            job.gray, job.depth = self.dev["gray"].data_ptr(), self.dev["depth"].data_ptr()
+            job.bgr = self.dev["bgr"].data_ptr() if self.use_color else None
+        else:
+            job.gray, job.depth = d.gray.ctypes.data, d.depth.ctypes.data
+            job.bgr = d.bgr.ctypes.data if self.use_color else None
+        poses = np.ascontiguousarray(d.poses, np.float32)
+        job.poses = poses.ctypes.data
+        job.frames = C.addressof(recs)
+        sf, s2 = self.ex.mvScaleFactor, self.ex.mvLevelSigma2
+        job.view_template = Frame(np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8), d.w, d.h, sf, s2, bf=d.K["bf"]).view()
+        job.th_last, job.th_map, job.nnratio_map = 15.0, 3.0, 0.8
+        if flush is not None:
+            job.flush_buf, job.flush_bytes = flush
+        exs = (C.c_void_p * 2)(self.ex._h.value, self.ex2._h.value)
+        st = _lib.PipelineStats()
+        rc = self.ex._lib.plvs_pipeline_run(exs, self.m_track._h, self.m_tri._h, self.tsdf._h, C.byref(job), C.byref(st))
+        _lib.check(rc, "plvs_pipeline_run")
+        return dict(keypoints=st.keypoints, matches=st.matches, busy_extract_s=st.busy_extract_s, busy_track_s=st.busy_track_s,
+                    busy_tri_s=st.busy_tri_s, busy_map_s=st.busy_map_s, wall_s=st.wall_s)
 
     def match_rounds(self):
         lib = self.ex._lib

@@ -120,6 +120,28 @@ def gray_frame(frame, w=640, h=480, stream=0, eye=0.0):
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
 
 
+def render_gray_parallel(n, w, h, stream, workers):
+    """gray_frame(f, w, h, stream) for f in range(n), rendered by `workers` child interpreters (each takes every workers-th frame and leaves its
+    slice as a .npy file in a temporary directory).  Returns the list of frames, or None if that did not work (the caller then renders here)."""
+    import os, subprocess, sys, tempfile, pathlib
+    root = str(pathlib.Path(__file__).resolve().parent.parent)
+    try:
+        with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+            code = ("import sys, numpy as np; sys.path.insert(0, %r); from plvs_b200 import synth; k = int(sys.argv[1]); "
+                    "np.save(%r + '/g%%d.npy' %% k, np.stack([synth.gray_frame(f, %d, %d, %d) for f in range(k, %d, %d)]))" % (root, tmp, w, h, stream, n, workers))
+            procs = [subprocess.Popen([sys.executable, "-c", code, str(k)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for k in range(workers)]
+            if any(pr.wait() != 0 for pr in procs):
+                return None
+            out = [None] * n
+            for k in range(workers):
+                part = np.load(os.path.join(tmp, "g%d.npy" % k))
+                for j, f in enumerate(range(k, n, workers)):
+                    out[f] = part[j]
+            return out
+    except Exception:
+        return None
+
+
 def depth_frame(frame, w=640, h=480, stream=0, noise=True):
     """float32 depth (metres) of the analytic scene seen from pose(frame): Kinect-style noise, 2 % invalid (0) pixels."""
     z = _raycast(frame, w, h)[0].copy()

@@ -28,7 +28,7 @@ def build_emulated_kernels():
 CLUSTER_KERNELS = {"k_resolve": 8}          # __cluster_dims__ of the kernels that need their CTAs resident together
 
 
-def build_emulated_library(units=("core.cu", "bow.cu", "match.cu", "tsdf.cu", "orb.cu")):
+def build_emulated_library(units=("core.cu", "bow.cu", "match.cu", "tsdf.cu", "orb.cu", "pipeline.cu")):
     """Whole translation units of the product on the CPU: `kernel<<<grid, block, smem, stream>>>(args);` is rewritten to emu::launch, the CUDA runtime
     calls resolve to tests/native/fake_cuda/cuda_runtime.h (host memory), device code runs on cuda_emu.hpp.  Only units without inline PTX qualify.
     -> tests/native/libemu_units.so exporting the same C ABI as the real library for those units."""

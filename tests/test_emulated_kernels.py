@@ -429,13 +429,14 @@ def test_randomised_scheduling_exposes_a_missing_barrier():
     assert all(0 < s < 256 for s in seen), seen
 
 
-def test_bench_step_dataflow_on_the_cpu_model(product_bound_to_emulated_units):
+def test_bench_step_dataflow_on_the_cpu_model(product_bound_to_emulated_units, monkeypatch):
     """bench.py's unit of work -- plvs_b200.pipeline.HotPath.step and the threaded HotPath.run_stream: batch extraction, the two tracking searches
     on the device-resident frame, the triangulation search, the colour depth-scan integration -- on the CPU model over a short synthetic stream,
     compared with the oracle stage by stage (the body of tests/test_gpu_bench_config.py::test_hot_path_step_at_bench_config, reduced): the bench
     measures the path the parity tests pin, with nothing skipped"""
     import tests.test_gpu_bench_config as B
-    nblk, nm = B._impl_hot_path(320, 240, 500, 0.04, 4.0, 2, 2, 4096, threaded=False)     # the model runs one host thread at a time
+    monkeypatch.setenv("PLVS_PIPELINE_SERIAL", "1")      # the model runs one host thread at a time: the driver's stages in sequence
+    nblk, nm = B._impl_hot_path(320, 240, 500, 0.04, 4.0, 2, 2, 4096, threaded=False, native="host")
     assert nblk > 20 and nm > 100
 
 

@@ -52,11 +52,12 @@ def _impl_depth_scan_sequence(w, h, voxel, far, nscans, max_blocks, clip=None, d
     return n, s, exact
 
 
-def _impl_hot_path(w, h, nfeatures, voxel, far, batch, nsteps, max_blocks, threaded):
+def _impl_hot_path(w, h, nfeatures, voxel, far, batch, nsteps, max_blocks, threaded, native=True):
     """bench.py's step: batch extraction -> SearchByProjection(Cur,Last) + SearchByProjection(F,map) on the device-resident frame ->
     SearchForTriangulation -> colour depth-scan integration, compared with the oracle stage by stage (keypoints + descriptors per frame, the
     assignment arrays of every search, the TSDF map at the end of every step).  `threaded` additionally runs the same frames through the 4-thread
-    pipeline bench.py times (HotPath.run_stream, host buffers and device-resident inputs) and compares its totals and final map (`threaded="host"`: host buffers only -- the CPU model has no device tensors)."""
+    pipeline (HotPath.run_stream, host buffers and device-resident inputs) and compares its totals and final map; `native` does the same through
+    plvs_pipeline_run, the C++ stream driver bench.py times (`threaded="host"`: host buffers only -- the CPU model has no device tensors)."""
     from plvs_b200.pipeline import StreamData, HotPath
     from plvs_b200.matcher import Frame
     n = 1 + batch * nsteps
@@ -109,6 +110,15 @@ def _impl_hot_path(w, h, nfeatures, voxel, far, batch, nsteps, max_blocks, threa
             got[k] = got.get(k, 0) + v
     assert got["keypoints"] == want_kp - len(hp.frames[0].keys) and got["matches"] == want_matches, (got, want_kp, want_matches)
     nblk, _ = _tsdf_equal(hp.tsdf, o, "HotPath.step", stats=False)
+    # the native stream driver (plvs_pipeline_run: the stage threads in C++; PLVS_PIPELINE_SERIAL=1 runs its stages on one thread)
+    if native:
+        for resident in ((False,) if native == "host" else (False, True)):
+            if resident:
+                hp.upload_inputs()
+            hp.tsdf.Reset(); hp.tsdf.integrate(d.depth[0], d.poses[0], d.bgr[0])
+            agg = hp.run_stream_native(1, nsteps, resident)
+            assert agg["keypoints"] == got["keypoints"] and agg["matches"] == want_matches, ("native", resident, agg, got)
+            _tsdf_equal(hp.tsdf, o, f"plvs_pipeline_run resident={resident}", stats=False)
     if threaded:
         for resident in ((False,) if threaded == "host" else (False, True)):
             if resident:
@@ -124,7 +134,7 @@ def _impl_hot_path(w, h, nfeatures, voxel, far, batch, nsteps, max_blocks, threa
 def test_c2_bench_geometry_ten_scans(gpu):
     """BASELINE configs[1] exactly as bench.py integrates it: 640x480, 1 cm voxels, planes 0.1-5 m, colour + carving, 10 consecutive scans"""
     n, s, exact = _impl_depth_scan_sequence(640, 480, 0.01, 5.0, 10, 49152)
-    assert n > 3000 and s["n_range"] > 40000 and s["n_updated"] > 2000, s
+    assert n > 1500 and s["n_range"] > 40000 and s["n_updated"] > 1000 and s["n_candidates"] < 0.2 * s["n_range"], s
     assert exact, "within 1e-4 but not bit-identical (expected: the kernels follow the oracle's operation order)"
 
 
@@ -157,14 +167,14 @@ def test_hot_path_step_at_bench_config(gpu):
     """bench.py's configuration (VGA, 2000 features, batch 8, 1 cm, 0.1-5 m): two steps = 17 frames, every stage against the oracle, then the
     threaded pipeline with host buffers and with device-resident inputs"""
     nblk, nm = _impl_hot_path(640, 480, 2000, 0.01, 5.0, 8, 2, 49152, threaded=True)
-    assert nblk > 3000 and nm > 10000
+    assert nblk > 1500 and nm > 10000
 
 
 @pytest.mark.gpu
 def test_c3_full_range_two_scans(gpu):
     """BASELINE configs[2] geometry: 1920x1080, 5 mm voxels, planes 0.1-5 m (no depth clipping), two consecutive colour scans with carving"""
     n, s, exact = _impl_depth_scan_sequence(1920, 1080, 0.005, 5.0, 2, 200000)
-    assert n > 15000 and s["n_range"] > 300000, s
+    assert n > 5000 and s["n_range"] > 300000, s
     assert exact
 
 
