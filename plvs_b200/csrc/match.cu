@@ -394,6 +394,8 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
 // that targeted the keypoint in the previous round.  Lists that do not fit the shared memory the launch was given are read from L2.
 // result: [0] matches, [1] rounds, [2] list words (sizes the next launch), [3] largest raw candidate count if it exceeded `cap`.
 // ---------------------------------------------------------------------------------------------
+constexpr int kLenBins = 128;        // list lengths >= 127 share the first bin
+
 template <int MODE>
 __global__ void __launch_bounds__(1024)
 k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int cap, const void* __restrict__ queries, int nq,
@@ -410,14 +412,19 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
     int* s_target = tab1 + n;                       // nq
     int* s_off = s_target + nq;                     // nq + 1
     int* s_meta = s_off + nq + 1;                   // nq: list length << 1 | Observations() > 0
-    uint32_t* s_list = s_dyn + 2 * n + 3 * nq + 1;
+    int* s_perm = s_meta + nq;                      // nq: queries ordered by list length, longest first (processing order only)
+    uint32_t* s_list = s_dyn + 2 * n + 4 * nq + 1;
+    __shared__ int s_bin[kLenBins + 1];
     // list lengths, their exclusive scan (consecutive queries per thread), table initialisation
     const int ipt = (nq + 1023) >> 10;
     int sum = 0;
+    for (int i = tid; i <= kLenBins; i += 1024) s_bin[i] = 0;
+    __syncthreads();
     for (int k = 0; k < ipt; ++k) {
         const int q = tid * ipt + k;
         if (q < nq) {
             const int m = min(cand_n[q], cap);
+            atomicAdd(&s_bin[kLenBins - 1 - min(m, kLenBins - 1)], 1);        // bin 0 = the longest lists
             const uint32_t fl = MODE == 0 ? reinterpret_cast<const plvs_mp_query*>(queries)[q].flags : reinterpret_cast<const plvs_last_query*>(queries)[q].flags;
             s_meta[q] = (m << 1) | ((fl & PLVS_Q_OBS_POSITIVE) ? 1 : 0);
             s_target[q] = -2;
@@ -444,6 +451,25 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
         if (tid == 1023) s_off[nq] = s_total;
     }
     __syncthreads();
+    // Processing order: queries sorted by list length (counting sort, longest first), so the lanes of a warp walk lists of about the same
+    // length.  The order inside a bin is whatever the atomics give -- it only decides which thread evaluates which query, never the result:
+    // a round reads the previous round's table and writes the next one with atomicMin.
+    if (wid == 0) {
+        int run = 0;
+        for (int b0 = 0; b0 < kLenBins; b0 += 32) {
+            const int c = s_bin[b0 + lane32];
+            int xx = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, xx, o); if (lane32 >= o) xx += y; }
+            s_bin[b0 + lane32] = run + xx - c;
+            run += __shfl_sync(0xffffffffu, xx, 31);
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < ipt; ++k) {
+        const int q = tid * ipt + k;
+        if (q < nq) s_perm[atomicAdd(&s_bin[kLenBins - 1 - min(s_meta[q] >> 1, kLenBins - 1)], 1)] = q;
+    }
     const bool staged = s_total <= list_budget;
     if (staged)
         for (int q = wid; q < nq; q += 32) {             // a warp copies one list: coalesced reads of the row's head
@@ -460,8 +486,9 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
         bool changed = false;
         for (int base = 0; base < slots; base += 1024) {
             const int slot = base + tid;
-            const int q = slot >> lpq_shift, lane = slot & (lpq - 1);
-            const bool mine = q < nq;
+            const int lane = slot & (lpq - 1);
+            const bool mine = (slot >> lpq_shift) < nq;
+            const int q = mine ? s_perm[slot >> lpq_shift] : 0;
             // The reference's running best / second best (strict `<` in list order, the old best demoted to second) are the two smallest
             // (distance, position) keys of the unblocked candidates: each lane keeps the two smallest of its strided share, shuffles merge.
             uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
@@ -1055,12 +1082,12 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         h->grid_key = F->cache_key; h->grid_n = n;
     }
     // one CTA holds the claim tables, the targets and (if they fit) the compacted lists; past that the 8-CTA cluster kernel takes over
-    const size_t fixed_words = (size_t)2 * n + (size_t)3 * nq + 1;
+    const size_t fixed_words = (size_t)2 * n + (size_t)4 * nq + 1;
     // development / test knobs, read per call: PLVS_MATCH_RESOLVE=cluster forces the cluster kernel, PLVS_MATCH_RESOLVE_LPQ=log2(lanes per query),
     // PLVS_MATCH_LIST_WORDS=n caps the shared-memory words for the lists (0: always read them from L2)
     const char* e_res = std::getenv("PLVS_MATCH_RESOLVE"); const char* e_lpq = std::getenv("PLVS_MATCH_RESOLVE_LPQ"); const char* e_lw = std::getenv("PLVS_MATCH_LIST_WORDS");
     const bool force_cluster = e_res && std::strcmp(e_res, "cluster") == 0;
-    const int lpq_shift = e_lpq ? std::max(0, std::min(5, std::atoi(e_lpq))) : 2;
+    const int lpq_shift = e_lpq ? std::max(0, std::min(5, std::atoi(e_lpq))) : 1;
     const bool one_cta = !force_cluster && fixed_words * 4 + 16 * 1024 <= kResolveSmemMax;
     for (;;) {
         if ((rc = h->d_cand.alloc((size_t)nq * h->cap))) return rc;

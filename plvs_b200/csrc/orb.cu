@@ -52,7 +52,7 @@ struct plvs_orb {
     DevBuf<uint32_t> d_dist_stage;
     DevBuf<DistLevel> d_dist_levels;
     PinBuf<int> p_nkp, p_err;
-    bool host_distribute = false, fast_tree = false;
+    bool host_distribute = false; int fast_tree = 0;
     int dist_smem = 0;
     DevBuf<int> d_cell_count, d_cand_count;
     DevBuf<plvs_keypoint> d_kp;
@@ -280,7 +280,7 @@ int plvs_orb_create(const plvs_orb_params* p, int device, plvs_orb** out)
     o->prm = *p; o->device = device; o->timer.component = 1;
     { static std::atomic<uint64_t> counter{1}; o->serial = counter.fetch_add(1); }
     { const char* e = getenv("PLVS_ORB_DEBUG"); o->debug = e && e[0] == '1'; }
-    { const char* e = getenv("PLVS_FAST_TREE"); o->fast_tree = e && e[0] == '1'; }     // experiment: min/max-tree corner score (DESIGN.md open issue)
+    { const char* e = getenv("PLVS_FAST_TREE"); o->fast_tree = e ? std::atoi(e) : 0; }     // experiment: min/max-tree corner score (DESIGN.md open issue)
     { const char* e = getenv("PLVS_ORB_HOST_DISTRIBUTE"); o->host_distribute = e && e[0] == '1'; }   // A/B aid: run DistributeOctTree on host threads
     build_tables(o);
     cudaError_t e1 = create_handle_stream(&o->stream, 1);
@@ -380,7 +380,7 @@ static int extract_impl(plvs_orb* o, int batch, const uint8_t* gray, int w, int 
     o->timer.begin(PLVS_ORB_K_FAST, st);
     k_fast_cells<<<dim3((unsigned)o->cells.size(), batch), 256, 0, st>>>(o->d_pyr.p, o->frame_stride, o->d_lv.p, o->d_cells.p, o->d_slots.p,
                                                                           o->slots_per_frame, o->d_cell_count.p, (int)o->cells.size(),
-                                                                          o->prm.ini_th_fast, o->prm.min_th_fast, o->fast_tree ? 1 : 0, o->debug ? o->d_dbg_score.p : nullptr);
+                                                                          o->prm.ini_th_fast, o->prm.min_th_fast, o->fast_tree, o->debug ? o->d_dbg_score.p : nullptr);
     o->timer.end(st);
     o->timer.begin(PLVS_ORB_K_COMPACT, st);
     k_compact<<<dim3(nl, batch), 256, 0, st>>>(o->d_slots.p, o->slots_per_frame, o->d_cell_count.p, (int)o->cells.size(), o->d_lv.p, o->d_cells.p, nl,

@@ -220,7 +220,7 @@ __device__ __forceinline__ int fast_corner_score(const uint8_t* p, int stride, i
     // (An unrolled min/max-tree formulation returned max(d)-1 inside this kernel on the B200 although
     // the same tree passes standalone -- tools/vimnmx_probe.cu -- and on the host; until that is
     // understood the score uses compares and bit logic only.  DESIGN.md "open issues".)
-    if (use_tree) {
+    if (use_tree == 1) {
         // max over the 16 arcs of (min d) / (min -d), minus 1: doubling windows 2 -> 4 -> 8 (+1)
         int lo2[16], hi2[16], lo4[16], hi4[16];
 #pragma unroll
@@ -235,6 +235,29 @@ __device__ __forceinline__ int fast_corner_score(const uint8_t* p, int stride, i
             best = max(best, max(lo9, -hi9));
         }
         return best - 1;
+    }
+    if (use_tree == 2) {
+        // cv::cornerScore<16> as written (modules/features2d/src/fast_score.cpp), without its early `continue`s (they only skip work):
+        // arcs start at even k; a = min over the 8 ring values k+1..k+8 serves the two arcs {k..k+8} and {k+1..k+9}
+        int a0 = min_th;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+            int a = min(d[(k + 1) & 15], d[(k + 2) & 15]);
+            a = min(a, d[(k + 3) & 15]); a = min(a, d[(k + 4) & 15]); a = min(a, d[(k + 5) & 15]);
+            a = min(a, d[(k + 6) & 15]); a = min(a, d[(k + 7) & 15]); a = min(a, d[(k + 8) & 15]);
+            a0 = max(a0, min(a, d[k]));
+            a0 = max(a0, min(a, d[(k + 9) & 15]));
+        }
+        int b0 = -a0;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+            int b = max(d[(k + 1) & 15], d[(k + 2) & 15]);
+            b = max(b, d[(k + 3) & 15]); b = max(b, d[(k + 4) & 15]); b = max(b, d[(k + 5) & 15]);
+            b = max(b, d[(k + 6) & 15]); b = max(b, d[(k + 7) & 15]); b = max(b, d[(k + 8) & 15]);
+            b0 = min(b0, max(b, d[k]));
+            b0 = min(b0, max(b, d[(k + 9) & 15]));
+        }
+        return -b0 - 1;
     }
     int lo = min_th, hi = 255;
 #pragma unroll 1
