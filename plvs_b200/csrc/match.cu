@@ -28,11 +28,34 @@ namespace {
 // mode 0: map points (levels [l-1,l], radius by viewing cosine, xR gate with r*scale)
 // mode 1: last frame (level window by motion direction, radius th*scale, xR gate with bf*invz)
 // ---------------------------------------------------------------------------------------------
+// What a query picks from its best / second-best unblocked candidates (keys = distance << 16 | list position, 0xffffffff = none; e1 / e2 = the
+// list entries they point at): src/ORBmatcher.cc:130-150 for the map search (TH_HIGH, then the level-aware ratio test), :1940-1958 for the
+// last-frame search (ORBdist / TH_HIGH only).  Returns the keypoint index or -1.
+template <int MODE>
+__device__ __forceinline__ int decide_target(uint32_t k1, uint32_t k2, uint32_t e1, uint32_t e2, float nn_ratio, int th_high)
+{
+    const int bestDist = k1 == 0xffffffffu ? 256 : (int)(k1 >> 16);
+    if (bestDist > th_high) return -1;
+    if (MODE == 0) {
+        int bestDist2 = 256, bestLevel2 = -1;
+        if (k2 != 0xffffffffu) { bestDist2 = (int)(k2 >> 16); bestLevel2 = cand_level(e2); }
+        const int bestLevel = cand_level(e1);
+        if (!(bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) &&
+            (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2)) return cand_idx(e1);
+        return -1;
+    }
+    return cand_idx(e1);
+}
+
+// per query, what round 0 of the claim resolution (nobody has claimed anything yet; pre-claimed keypoints are blocked) leaves behind
+struct Round0 { int32_t u1, u2, target, pad; };       // list positions of the best / second-best unblocked candidate (-1: none), chosen keypoint
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restrict__ sorted,
              const void* __restrict__ queries, int nq, float th, int far_points, float th_far, int forward, int backward,
-             uint32_t* __restrict__ cand, int* __restrict__ cand_n, int cap, int* __restrict__ max_count)
+             uint32_t* __restrict__ cand, int* __restrict__ cand_n, int cap, int* __restrict__ max_count,
+             const uint8_t* __restrict__ claimed_in, float nn_ratio, int th_high, Round0* __restrict__ round0)
 {
     // The window of GetFeaturesInArea is a run of grid columns; the cells r0..r1 of one column are contiguous in the cell-column-major
     // CSR, so the reference's visiting order is the concatenation of one [pbeg, pend) range per column.  The lanes fetch the ranges of up
@@ -68,13 +91,14 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
         xr_ref = m.u - F.bf * m.invz; xr_tol = radius; qd = m.desc;
     }
     int c0, c1, r0, r1, count = 0;
+    uint32_t best1 = 0xffffffffu, best2 = 0xffffffffu;      // round 0: the two smallest (distance, position) keys among the candidates not pre-claimed
+    uint32_t* out = cand + (size_t)q * cap;
     if (active) active = cell_window(F.gp, px, py, radius, c0, c1, r0, r1);
     if (active) {
         const bool check = (minL > 0) || (maxL >= 0);
         // query records are 60/56-byte structs: the embedded descriptor is only 4-byte aligned
         const uint32_t* qw = reinterpret_cast<const uint32_t*>(qd);
         const uint4 a0 = make_uint4(qw[0], qw[1], qw[2], qw[3]), a1 = make_uint4(qw[4], qw[5], qw[6], qw[7]);
-        uint32_t* out = cand + (size_t)q * cap;
         for (int cb = c0; cb <= c1; cb += 32) {            // at most two chunks: the grid has 64 columns
             const int ix = cb + lane;
             int pbeg = 0, cnt = 0;
@@ -104,13 +128,37 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
                     if (ok) dist = hamming256(a0, a1, F.desc + (size_t)idx * 32);
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                if (ok) { const int pos = count + __popc(m & ((1u << lane) - 1)); if (pos < cap) out[pos] = pack_cand(idx, dist, oct); }
+                uint32_t key = 0xffffffffu;
+                if (ok) {
+                    const int pos = count + __popc(m & ((1u << lane) - 1));
+                    if (pos < cap) out[pos] = pack_cand(idx, dist, oct);
+                    if (pos < 65536 && !(claimed_in && claimed_in[idx])) key = ((uint32_t)dist << 16) | (uint32_t)pos;
+                }
                 count += __popc(m);
+                // the two smallest keys of this step (positions are unique, so keys are), merged into the running pair
+                const uint32_t s1 = __reduce_min_sync(0xffffffffu, key);
+                const uint32_t s2 = __reduce_min_sync(0xffffffffu, key == s1 ? 0xffffffffu : key);
+                const uint32_t lo = min(best1, s1), hi = max(best1, s1);
+                best2 = min(hi, min(best2, s2));
+                best1 = lo;
             }
             __syncwarp();
         }
     }
-    if (lane == 0) { cand_n[q] = count; if (max_count && count > cap) atomicMax(max_count, count); }
+    if (lane == 0) {
+        cand_n[q] = count;
+        if (max_count && count > cap) atomicMax(max_count, count);
+        Round0 r; r.pad = 0;
+        r.u1 = best1 == 0xffffffffu ? -1 : (int)(best1 & 0xffffu);
+        r.u2 = best2 == 0xffffffffu ? -1 : (int)(best2 & 0xffffu);
+        r.target = -1;
+        if (count <= cap) {           // otherwise the search is repeated with more room and this record is not used
+            __syncwarp(1u);
+            const uint32_t e1 = r.u1 >= 0 ? out[r.u1] : 0u, e2 = r.u2 >= 0 ? out[r.u2] : 0u;
+            r.target = decide_target<MODE>(best1, best2, e1, e2, nn_ratio, th_high);
+        }
+        round0[q] = r;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -387,156 +435,110 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// Phase B on ONE CTA (the default): the same Jacobi fixed point as k_resolve with everything in shared memory -- the candidate lists
-// compacted to a CSR, the two claim tables, the targets -- so a round is a list walk and two CTA barriers: no cluster barrier, no L2
-// round trip, and no need to find eight free SMs at once next to the persistent TSDF kernel.  lpq lanes share a query (strided walk,
-// shuffle merge); a table entry is -1 for a pre-claimed keypoint (blocks everybody), else the lowest query (with Observations() > 0)
-// that targeted the keypoint in the previous round.  Lists that do not fit the shared memory the launch was given are read from L2.
-// result: [0] matches, [1] rounds, [2] list words (sizes the next launch), [3] largest raw candidate count if it exceeded `cap`.
+// Phase B on ONE CTA (the default): the same Jacobi fixed point as k_resolve, evaluated incrementally.  Round 0 (nobody has claimed anything
+// yet) comes out of k_candidates for free.  From then on a round is: rebuild the claim table from the current targets (one atomicMin per
+// query), then re-evaluate ONLY the queries whose decision can have changed.  A query's decision is a function of which of its candidates are
+// blocked by a lower query, and only of the candidates up to (in list-key order) its second-best unblocked one (map search: the ratio test
+// reads the second best) or its best unblocked one (last-frame search): anything behind them can flip without consequence.  So every
+// evaluation leaves a WATCH SET -- those few candidates with the blocked / free state it saw (pre-claimed keypoints never change and are left
+// out) -- and a round just compares the watch set with the new table (a handful of shared-memory reads per query); only on a difference is
+// the candidate list walked again (from L2: a few dozen queries per round).  Queries whose watch set does not fit kWatch entries are walked
+// every round.  The shared memory holds two claim tables and the per-query records -- no candidate lists -- so the kernel needs no large
+// opt-in allocation and starts on any SM with room for one CTA.  By induction over the rounds every query holds exactly what a full
+// re-evaluation would give it, so the fixed point is the one k_resolve reaches: the sequential result.
+// result: [0] matches, [1] rounds, [2] list walks after round 0, [3] largest raw candidate count if it exceeded `cap`.
 // ---------------------------------------------------------------------------------------------
-constexpr int kLenBins = 128;        // list lengths >= 127 share the first bin
+constexpr int kWatch = 6;
+struct WatchRec { uint16_t kp[kWatch]; uint8_t n, blocked; uint16_t pad; };      // n == 255: re-evaluate every round
+static_assert(sizeof(WatchRec) == 16, "WatchRec layout");
 
 template <int MODE>
 __global__ void __launch_bounds__(1024)
 k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int cap, const void* __restrict__ queries, int nq,
               const plvs_keypoint* __restrict__ keys, int n, const uint8_t* __restrict__ claimed_in, float nn_ratio, int check_ori, int th_high,
-              int32_t* __restrict__ assign_out /*n, mapped host*/, int* __restrict__ result, int* __restrict__ max_count, int lpq_shift,
-              int list_budget /*words of dynamic shared memory left for the lists*/)
+              const Round0* __restrict__ round0, int32_t* __restrict__ assign_out /*n, mapped host*/, int* __restrict__ result, int* __restrict__ max_count)
 {
-    PLVS_DYN_SMEM(uint32_t, s_dyn);
-    __shared__ int s_count, s_hist[HISTO], s_keep[HISTO], s_part[32], s_total;
-    const int tid = threadIdx.x, lane32 = tid & 31, wid = tid >> 5;
+    PLVS_DYN_SMEM_ALIGNED(uint32_t, s_dyn, 16);
+    __shared__ int s_count, s_hist[HISTO], s_keep[HISTO], s_walks;
+    const int tid = threadIdx.x;
     const int INF = 0x7fffffff;
-    int* tab0 = reinterpret_cast<int*>(s_dyn);      // n
-    int* tab1 = tab0 + n;                           // n
-    int* s_target = tab1 + n;                       // nq
-    int* s_off = s_target + nq;                     // nq + 1
-    int* s_meta = s_off + nq + 1;                   // nq: list length << 1 | Observations() > 0
-    int* s_perm = s_meta + nq;                      // nq: queries ordered by list length, longest first (processing order only)
-    uint32_t* s_list = s_dyn + 2 * n + 4 * nq + 1;
-    __shared__ int s_bin[kLenBins + 1];
-    // list lengths, their exclusive scan (consecutive queries per thread), table initialisation
-    const int ipt = (nq + 1023) >> 10;
-    int sum = 0;
-    for (int i = tid; i <= kLenBins; i += 1024) s_bin[i] = 0;
-    __syncthreads();
-    for (int k = 0; k < ipt; ++k) {
-        const int q = tid * ipt + k;
-        if (q < nq) {
-            const int m = min(cand_n[q], cap);
-            atomicAdd(&s_bin[kLenBins - 1 - min(m, kLenBins - 1)], 1);        // bin 0 = the longest lists
-            const uint32_t fl = MODE == 0 ? reinterpret_cast<const plvs_mp_query*>(queries)[q].flags : reinterpret_cast<const plvs_last_query*>(queries)[q].flags;
-            s_meta[q] = (m << 1) | ((fl & PLVS_Q_OBS_POSITIVE) ? 1 : 0);
-            s_target[q] = -2;
-            sum += m;
-        }
-    }
-    int x = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane32 >= o) x += y; }
-    if (lane32 == 31) s_part[wid] = x;
+    WatchRec* s_watch = reinterpret_cast<WatchRec*>(s_dyn);                    // nq (16-byte records first: alignment)
+    int* tab0 = reinterpret_cast<int*>(s_dyn + 4 * (size_t)nq);               // n
+    int* tab1 = tab0 + n;                                                      // n
+    int* s_target = tab1 + n;                                                  // nq
+    uint8_t* s_obs = reinterpret_cast<uint8_t*>(s_target + nq);                // nq: Observations() > 0
+    if (tid == 0) s_walks = 0;
     for (int i = tid; i < n; i += 1024) { const int v = (claimed_in && claimed_in[i]) ? -1 : INF; tab0[i] = v; tab1[i] = v; }
-    __syncthreads();
-    if (wid == 0) {
-        int p = s_part[lane32];
+    for (int q = tid; q < nq; q += 1024) {
+        const uint32_t fl = MODE == 0 ? reinterpret_cast<const plvs_mp_query*>(queries)[q].flags : reinterpret_cast<const plvs_last_query*>(queries)[q].flags;
+        s_obs[q] = (fl & PLVS_Q_OBS_POSITIVE) ? 1 : 0;
+        // round 0: the watch set is the best (and, for the map search, the second-best) candidate that was free; with fewer free candidates
+        // than that, ANY candidate coming free would matter -- but at round 0 nothing is blocked except pre-claims, which never come free
+        const Round0 r = round0[q];
+        s_target[q] = r.target;
+        WatchRec w; w.n = 0; w.blocked = 0; w.pad = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, p, o); if (lane32 >= o) p += y; }
-        s_part[lane32] = p;
-        if (lane32 == 31) s_total = p;
+        for (int j = 0; j < kWatch; ++j) w.kp[j] = 0;
+        const uint32_t* row = cand + (size_t)q * cap;
+        if (r.u1 >= 0) w.kp[w.n++] = (uint16_t)cand_idx(row[r.u1]);
+        if (MODE == 0 && r.u2 >= 0) w.kp[w.n++] = (uint16_t)cand_idx(row[r.u2]);
+        s_watch[q] = w;
     }
-    __syncthreads();
-    {
-        int base = (wid ? s_part[wid - 1] : 0) + x - sum;
-        for (int k = 0; k < ipt; ++k) { const int q = tid * ipt + k; if (q < nq) { s_off[q] = base; base += s_meta[q] >> 1; } }
-        if (tid == 1023) s_off[nq] = s_total;
-    }
-    __syncthreads();
-    // Processing order: queries sorted by list length (counting sort, longest first), so the lanes of a warp walk lists of about the same
-    // length.  The order inside a bin is whatever the atomics give -- it only decides which thread evaluates which query, never the result:
-    // a round reads the previous round's table and writes the next one with atomicMin.
-    if (wid == 0) {
-        int run = 0;
-        for (int b0 = 0; b0 < kLenBins; b0 += 32) {
-            const int c = s_bin[b0 + lane32];
-            int xx = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, xx, o); if (lane32 >= o) xx += y; }
-            s_bin[b0 + lane32] = run + xx - c;
-            run += __shfl_sync(0xffffffffu, xx, 31);
-        }
-    }
-    __syncthreads();
-    for (int k = 0; k < ipt; ++k) {
-        const int q = tid * ipt + k;
-        if (q < nq) s_perm[atomicAdd(&s_bin[kLenBins - 1 - min(s_meta[q] >> 1, kLenBins - 1)], 1)] = q;
-    }
-    const bool staged = s_total <= list_budget;
-    if (staged)
-        for (int q = wid; q < nq; q += 32) {             // a warp copies one list: coalesced reads of the row's head
-            const int m = s_meta[q] >> 1, o = s_off[q];
-            for (int k = lane32; k < m; k += 32) s_list[o + k] = cand[(size_t)q * cap + k];
-        }
     __syncthreads();
 
-    const int lpq = 1 << lpq_shift;
-    const int slots = nq << lpq_shift;
     int* cur = tab0; int* nxt = tab1;
-    int rounds = 0;
+    int rounds = 1;                         // round 0 ran inside k_candidates
     for (;;) {
+        // claim table of the current targets: lowest query (with Observations() > 0) per keypoint; -1 marks a pre-claimed keypoint
+        for (int i = tid; i < n; i += 1024) nxt[i] = cur[i] < 0 ? -1 : INF;
+        __syncthreads();
+        for (int q = tid; q < nq; q += 1024) { const int t = s_target[q]; if (t >= 0 && s_obs[q]) atomicMin(&nxt[t], q); }
+        __syncthreads();
+        { int* t = cur; cur = nxt; nxt = t; }
         bool changed = false;
-        for (int base = 0; base < slots; base += 1024) {
-            const int slot = base + tid;
-            const int lane = slot & (lpq - 1);
-            const bool mine = (slot >> lpq_shift) < nq;
-            const int q = mine ? s_perm[slot >> lpq_shift] : 0;
-            // The reference's running best / second best (strict `<` in list order, the old best demoted to second) are the two smallest
-            // (distance, position) keys of the unblocked candidates: each lane keeps the two smallest of its strided share, shuffles merge.
+        for (int q = tid; q < nq; q += 1024) {
+            WatchRec w = s_watch[q];
+            bool walk = w.n == 255;
+            if (!walk)
+                for (int j = 0; j < (int)w.n; ++j) walk |= ((cur[w.kp[j]] < q) != (((w.blocked >> j) & 1) != 0));
+            if (!walk) continue;
+            // full evaluation against the new table (list from L2; rows are cap * 4 bytes, cap a multiple of 4)
+            const int m = min(cand_n[q], cap);
+            const uint32_t* row = cand + (size_t)q * cap;
             uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
-            int m = 0, off = 0;
-            if (mine) {
-                m = s_meta[q] >> 1; off = s_off[q];
-                for (int k = lane; k < m; k += lpq) {
-                    const uint32_t e = staged ? s_list[off + k] : cand[(size_t)q * cap + k];
-                    const bool blocked = cur[cand_idx(e)] < q;
-                    const uint32_t key = blocked ? 0xffffffffu : (((uint32_t)cand_dist(e) << 16) | (uint32_t)k);
-                    const uint32_t lo = min(k1, key), hi = max(k1, key);
-                    k2 = min(k2, hi); k1 = lo;
-                }
+            for (int k = 0; k < m; ++k) {
+                const uint32_t e = row[k];
+                const uint32_t key = (cur[cand_idx(e)] < q) ? 0xffffffffu : (((uint32_t)cand_dist(e) << 16) | (uint32_t)k);
+                const uint32_t lo = min(k1, key), hi = max(k1, key);
+                k2 = min(k2, hi); k1 = lo;
             }
-            for (int o = 1; o < lpq; o <<= 1) {
-                const uint32_t a1 = __shfl_xor_sync(0xffffffffu, k1, o), a2 = __shfl_xor_sync(0xffffffffu, k2, o);
-                const uint32_t lo = min(k1, a1), hi = max(k1, a1);
-                k2 = min(hi, min(k2, a2));
-                k1 = lo;
+            const uint32_t e1 = k1 != 0xffffffffu ? row[k1 & 0xffffu] : 0u, e2 = k2 != 0xffffffffu ? row[k2 & 0xffffu] : 0u;
+            const int t = decide_target<MODE>(k1, k2, e1, e2, nn_ratio, th_high);
+            // new watch set: every candidate up to the last one the decision read, except pre-claimed ones, with the state just seen
+            const uint32_t limit = MODE == 0 ? k2 : k1;              // 0xffffffff (not enough free candidates): the whole list matters
+            WatchRec nw; nw.n = 0; nw.blocked = 0; nw.pad = 0;
+#pragma unroll
+            for (int j = 0; j < kWatch; ++j) nw.kp[j] = 0;
+            for (int k = 0; k < m; ++k) {
+                const uint32_t e = row[k];
+                const uint32_t key = ((uint32_t)cand_dist(e) << 16) | (uint32_t)k;
+                const int c = cur[cand_idx(e)];
+                if (key > limit || c == -1) continue;
+                if (nw.n >= kWatch) { nw.n = 255; break; }
+                nw.kp[nw.n] = (uint16_t)cand_idx(e);
+                if (c < q) nw.blocked |= (uint8_t)(1u << nw.n);
+                ++nw.n;
             }
-            if (mine && lane == 0) {
-                int t = -1;
-                const int bestDist = k1 == 0xffffffffu ? 256 : (int)(k1 >> 16);
-                if (bestDist <= th_high) {
-                    const uint32_t e1 = staged ? s_list[off + (k1 & 0xffffu)] : cand[(size_t)q * cap + (k1 & 0xffffu)];
-                    if (MODE == 0) {
-                        int bestDist2 = 256, bestLevel2 = -1;
-                        if (k2 != 0xffffffffu) {
-                            const uint32_t e2 = staged ? s_list[off + (k2 & 0xffffu)] : cand[(size_t)q * cap + (k2 & 0xffffu)];
-                            bestDist2 = (int)(k2 >> 16); bestLevel2 = cand_level(e2);
-                        }
-                        const int bestLevel = cand_level(e1);
-                        if (!(bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) &&
-                            (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2)) t = cand_idx(e1);
-                    } else t = cand_idx(e1);
-                }
-                if (t != s_target[q]) { s_target[q] = t; changed = true; }
-                if (t >= 0 && (s_meta[q] & 1)) atomicMin(&nxt[t], q);
-            }
+            s_watch[q] = nw;
+            atomicAdd(&s_walks, 1);
+            if (t != s_target[q]) { s_target[q] = t; changed = true; }
         }
         ++rounds;
         if (!__syncthreads_or(changed ? 1 : 0)) break;
-        { int* t = cur; cur = nxt; nxt = t; }
-        for (int i = tid; i < n; i += 1024) nxt[i] = cur[i] < 0 ? -1 : INF;
-        __syncthreads();
     }
     // final holders: the last (highest) query that wrote each keypoint
-    int* assign = tab0;
+    int* assign = nxt;
+    __syncthreads();
     for (int i = tid; i < n; i += 1024) assign[i] = -1;
     if (tid == 0) s_count = 0;
     if (tid < HISTO) { s_hist[tid] = 0; s_keep[tid] = 1; }
@@ -587,7 +589,7 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
     }
     __syncthreads();
     for (int i = tid; i < n; i += 1024) assign_out[i] = assign[i];
-    if (tid == 0) { result[0] = s_count; result[1] = rounds; result[2] = s_total; result[3] = *max_count; *max_count = 0; }
+    if (tid == 0) { result[0] = s_count; result[1] = rounds; result[2] = s_walks; result[3] = *max_count; *max_count = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -979,7 +981,8 @@ struct plvs_match {
     int cap = 128;
     DevBuf<uint8_t> d_stage; PinBuf<uint8_t> p_stage;     // one packed H2D per projection search
     bool state_zeroed = false;
-    int list_words_hint = 16384;                          // shared-memory words the last search's candidate lists needed
+    DevBuf<Round0> d_round0;                              // per query: what round 0 of the claim resolution leaves (written by k_candidates)
+    int last_walks = 0;                                   // list re-evaluations of the last search after round 0 (statistics)
     int last_rounds = 0, last_launches = 0;
     uint64_t grid_key = 0; int grid_n = -1;
     KernelTimer timer;
@@ -1082,29 +1085,23 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         h->grid_key = F->cache_key; h->grid_n = n;
     }
     // one CTA holds the claim tables, the targets and (if they fit) the compacted lists; past that the 8-CTA cluster kernel takes over
-    const size_t fixed_words = (size_t)2 * n + (size_t)4 * nq + 1;
-    // development / test knobs, read per call: PLVS_MATCH_RESOLVE=cluster forces the cluster kernel, PLVS_MATCH_RESOLVE_LPQ=log2(lanes per query),
-    // PLVS_MATCH_LIST_WORDS=n caps the shared-memory words for the lists (0: always read them from L2)
-    const char* e_res = std::getenv("PLVS_MATCH_RESOLVE"); const char* e_lpq = std::getenv("PLVS_MATCH_RESOLVE_LPQ"); const char* e_lw = std::getenv("PLVS_MATCH_LIST_WORDS");
+    const size_t cta_smem = (size_t)16 * nq + (size_t)8 * n + (size_t)4 * nq + align_up((size_t)nq, 16);      // watch records, two claim tables, targets, flags
+    // development / test knob, read per call: PLVS_MATCH_RESOLVE=cluster forces the 8-CTA cluster kernel
+    const char* e_res = std::getenv("PLVS_MATCH_RESOLVE");
     const bool force_cluster = e_res && std::strcmp(e_res, "cluster") == 0;
-    const int lpq_shift = e_lpq ? std::max(0, std::min(5, std::atoi(e_lpq))) : 1;
-    const bool one_cta = !force_cluster && fixed_words * 4 + 16 * 1024 <= kResolveSmemMax;
+    const bool one_cta = !force_cluster && cta_smem <= kResolveSmemMax;
+    if ((rc = h->d_round0.alloc((size_t)nq))) return rc;
     for (;;) {
         if ((rc = h->d_cand.alloc((size_t)nq * h->cap))) return rc;
         h->timer.begin(PLVS_MATCH_K_CANDIDATES, st);
         k_candidates<MODE><<<div_up(nq, 8), 256, 0, st>>>(V, h->d_cell_start.p, h->d_sorted.p, dq, nq, th, far_points, th_far, forward, backward,
-                                                           h->d_cand.p, h->d_cand_n.p, h->cap, h->d_state.p + 8);
+                                                           h->d_cand.p, h->d_cand_n.p, h->cap, h->d_state.p + 8, d_claimed, nn_ratio, th_high, h->d_round0.p);
         h->timer.end(st);
         ++launches;
         h->timer.begin(PLVS_MATCH_K_RESOLVE, st);
         if (one_cta) {
-            // the lists get what the previous search on this handle needed plus a quarter (the kernel reads them from L2 when they do not fit)
-            size_t want = (size_t)h->list_words_hint + h->list_words_hint / 4 + 1024;
-            want = std::min(want, (size_t)nq * h->cap);
-            if (e_lw) want = (size_t)std::max(0, std::atoi(e_lw));
-            const size_t budget = std::min(want, kResolveSmemMax / 4 - fixed_words);
-            k_resolve_cta<MODE><<<1, 1024, (fixed_words + budget) * 4, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, dq, nq, V.keys, n, d_claimed, nn_ratio, check_ori, th_high,
-                                                                            h->p_assign.d, h->p_result.d, h->d_state.p + 8, lpq_shift, (int)budget);
+            k_resolve_cta<MODE><<<1, 1024, cta_smem, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, dq, nq, V.keys, n, d_claimed, nn_ratio, check_ori, th_high,
+                                                          h->d_round0.p, h->p_assign.d, h->p_result.d, h->d_state.p + 8);
         } else {
             if ((rc = h->d_claim_a.alloc((size_t)3 * n)) || (rc = h->d_target.alloc(nq)) || (rc = h->d_assign.alloc(n))) return rc;
             PLVS_CUDA(cudaMemsetAsync(h->d_state.p, 0, 8 * sizeof(int), st));
@@ -1128,7 +1125,7 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         PLVS_CUDA(cudaGetLastError());
         PLVS_CUDA(cudaStreamSynchronize(st));
         h->timer.collect();
-        if (one_cta) h->list_words_hint = h->p_result.h[2];
+        h->last_walks = one_cta ? h->p_result.h[2] : -1;
         const int mx = h->p_result.h[3];
         if (mx <= h->cap) break;
         while (h->cap < mx) h->cap *= 2;       // a window held more candidates than reserved: redo with room (exactness first)

@@ -280,7 +280,7 @@ int plvs_orb_create(const plvs_orb_params* p, int device, plvs_orb** out)
     o->prm = *p; o->device = device; o->timer.component = 1;
     { static std::atomic<uint64_t> counter{1}; o->serial = counter.fetch_add(1); }
     { const char* e = getenv("PLVS_ORB_DEBUG"); o->debug = e && e[0] == '1'; }
-    { const char* e = getenv("PLVS_FAST_TREE"); o->fast_tree = e ? std::atoi(e) : 0; }     // experiment: min/max-tree corner score (DESIGN.md open issue)
+    { const char* e = getenv("PLVS_FAST_TREE"); o->fast_tree = e ? (std::atoi(e) ? 2 : 0) : 2; }     // 2 = cv::cornerScore's min/max sequence (default), 0 = bisection
     { const char* e = getenv("PLVS_ORB_HOST_DISTRIBUTE"); o->host_distribute = e && e[0] == '1'; }   // A/B aid: run DistributeOctTree on host threads
     build_tables(o);
     cudaError_t e1 = create_handle_stream(&o->stream, 1);

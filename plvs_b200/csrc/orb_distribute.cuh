@@ -23,7 +23,7 @@
 namespace plvs {
 namespace orb {
 
-constexpr int kDistThreads = 512;      // x 64 registers = half an SM: a CTA lives for 100-270 us (latency-bound phases) and must not own a whole SM
+constexpr int kDistThreads = 1024;
 
 struct DNode {
     short ulx, uly, urx, bry;

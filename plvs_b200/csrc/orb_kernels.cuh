@@ -215,27 +215,11 @@ __device__ __forceinline__ int fast_corner_score(const uint8_t* p, int stride, i
     uint32_t rb = mb & (mb >> 1); rb &= rb >> 2; rb &= rb >> 4; rb &= mb >> 8;     // 9 contiguous ones
     uint32_t rd = md & (md >> 1); rd &= rd >> 2; rd &= rd >> 4; rd &= md >> 8;
     if (((rb | rd) & 0xffffu) == 0) return 0;
-    // exact score = largest t for which the pixel is still a corner (cv::FAST's cornerScore):
-    // bisection on t with the same 16-bit arc test; corner(min_th) holds, corner(255) cannot.
-    // (An unrolled min/max-tree formulation returned max(d)-1 inside this kernel on the B200 although
-    // the same tree passes standalone -- tools/vimnmx_probe.cu -- and on the host; until that is
-    // understood the score uses compares and bit logic only.  DESIGN.md "open issues".)
-    if (use_tree == 1) {
-        // max over the 16 arcs of (min d) / (min -d), minus 1: doubling windows 2 -> 4 -> 8 (+1)
-        int lo2[16], hi2[16], lo4[16], hi4[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
-#pragma unroll
-        for (int k = 0; k < 16; ++k) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
-        int best = -1000;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
-            const int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
-            best = max(best, max(lo9, -hi9));
-        }
-        return best - 1;
-    }
+    // exact score = largest t for which the pixel is still a corner (cv::FAST's cornerScore).  Default (use_tree == 2): OpenCV's own
+    // min/max sequence, ~180 VIMNMX; use_tree == 0 (PLVS_FAST_TREE=0): bisection on t with the 16-bit arc test (compares and bit logic
+    // only, ~3x the instructions) -- the form round 1 shipped because a doubling-window min/max tree gave wrong scores inside this kernel
+    // on the B200; the sequence below was checked on the device against the oracle's score map pixel by pixel
+    // (tools/fast_tree_probe.py: 0 mismatches on all 8 levels) and by the extractor tests.
     if (use_tree == 2) {
         // cv::cornerScore<16> as written (modules/features2d/src/fast_score.cpp), without its early `continue`s (they only skip work):
         // arcs start at even k; a = min over the 8 ring values k+1..k+8 serves the two arcs {k..k+8} and {k+1..k+9}
