@@ -120,34 +120,96 @@ __device__ __forceinline__ int quadrant_of(const DNode& nd, int x, int y)
     return (x < mx ? 0 : 1) + (y < my ? 0 : 2);
 }
 
+// the same from the node's first eight bytes (ulx, uly | urx, bry as two 32-bit words)
+__device__ __forceinline__ int quadrant_of_packed(uint2 b, int x, int y)
+{
+    const int ulx = (short)(b.x & 0xffffu), uly = (short)(b.x >> 16), urx = (short)(b.y & 0xffffu), bry = (short)(b.y >> 16);
+    const int mx = ulx + ((urx - ulx + 1) >> 1), my = uly + ((bry - uly + 1) >> 1);
+    return (x < mx ? 0 : 1) + (y < my ? 0 : 2);
+}
+
 __device__ __forceinline__ void child_counts(const DistLevel& D, const DNode& nd, int c[4])
 {
     const unsigned long long da = D.scan_a[nd.begin + nd.count] - D.scan_a[nd.begin], db = D.scan_b[nd.begin + nd.count] - D.scan_b[nd.begin];
     c[0] = (int)(uint32_t)da; c[1] = (int)(da >> 32); c[2] = (int)(uint32_t)db; c[3] = (int)(db >> 32);
 }
 
+// Exclusive prefix sums of TWO packed-counter arrays at once, in place, over n elements.  Every warp owns one contiguous segment and carries
+// its running sums in registers (32 elements per step, shuffles only); the 32 segment totals are scanned once by warp 0 and added back in a
+// second coalesced pass: two CTA barriers in all, however long the arrays are.
+__device__ inline void block_scan2_u64(unsigned long long* __restrict__ a, unsigned long long* __restrict__ b, int n, unsigned long long* s_part /*64*/)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    const int seg = ((n + nw - 1) / nw + 31) & ~31;                 // elements per warp, a multiple of 32
+    const int beg = wid * seg, end = min(beg + seg, n);
+    unsigned long long ra = 0, rb = 0;
+    for (int base = beg; base < end; base += 32) {
+        const int i = base + lane;
+        const unsigned long long va = i < end ? a[i] : 0ull, vb = i < end ? b[i] : 0ull;
+        unsigned long long xa = va, xb = vb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t al = __shfl_up_sync(0xffffffffu, (uint32_t)xa, o), ah = __shfl_up_sync(0xffffffffu, (uint32_t)(xa >> 32), o);
+            const uint32_t bl = __shfl_up_sync(0xffffffffu, (uint32_t)xb, o), bh = __shfl_up_sync(0xffffffffu, (uint32_t)(xb >> 32), o);
+            if (lane >= o) { xa += ((unsigned long long)ah << 32) | al; xb += ((unsigned long long)bh << 32) | bl; }
+        }
+        if (i < end) { a[i] = ra + xa - va; b[i] = rb + xb - vb; }
+        const uint32_t tal = __shfl_sync(0xffffffffu, (uint32_t)xa, 31), tah = __shfl_sync(0xffffffffu, (uint32_t)(xa >> 32), 31);
+        const uint32_t tbl = __shfl_sync(0xffffffffu, (uint32_t)xb, 31), tbh = __shfl_sync(0xffffffffu, (uint32_t)(xb >> 32), 31);
+        ra += ((unsigned long long)tah << 32) | tal; rb += ((unsigned long long)tbh << 32) | tbl;
+    }
+    if (lane == 0) { s_part[wid] = ra; s_part[32 + wid] = rb; }
+    __syncthreads();
+    if (wid == 0) {
+        const unsigned long long va = lane < nw ? s_part[lane] : 0ull, vb = lane < nw ? s_part[32 + lane] : 0ull;
+        unsigned long long xa = va, xb = vb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t al = __shfl_up_sync(0xffffffffu, (uint32_t)xa, o), ah = __shfl_up_sync(0xffffffffu, (uint32_t)(xa >> 32), o);
+            const uint32_t bl = __shfl_up_sync(0xffffffffu, (uint32_t)xb, o), bh = __shfl_up_sync(0xffffffffu, (uint32_t)(xb >> 32), o);
+            if (lane >= o) { xa += ((unsigned long long)ah << 32) | al; xb += ((unsigned long long)bh << 32) | bl; }
+        }
+        s_part[lane] = xa - va; s_part[32 + lane] = xb - vb;           // exclusive segment bases
+    }
+    __syncthreads();
+    const unsigned long long ba = s_part[wid], bb = s_part[32 + wid];
+    if (wid > 0 && (ba | bb))
+        for (int i = beg + lane; i < end; i += 32) { a[i] += ba; b[i] += bb; }
+    __syncthreads();
+}
+
 // quadrant prefix sums over all permutation slots whose node carries `tag`
 __device__ inline void quadrant_scans(const uint32_t* __restrict__ cand, int n, const DistLevel& D, int cur, int tag, unsigned long long* s_u64)
 {
     const int tid = threadIdx.x, T = blockDim.x;
-    const int* perm = D.perm[cur]; const int* nof = D.node_of[cur];
-    for (int p = tid; p <= n; p += T) {
-        unsigned long long a = 0, b = 0;
-        if (p < n) {
-            const DNode nd = D.nodes[nof[p]];
-            if (nd.tag == tag) {
-                const uint32_t c = cand[perm[p]];
-                const int q = quadrant_of(nd, unpack_x(c) - kRoiMargin, unpack_y(c) - kRoiMargin);
+    const int* __restrict__ perm = D.perm[cur]; const int* __restrict__ nof = D.node_of[cur];
+    const DNode* __restrict__ nodes = D.nodes;
+    unsigned long long* __restrict__ sa = D.scan_a; unsigned long long* __restrict__ sb = D.scan_b;
+    // four slots per thread and step: the three dependent loads (owner -> node, slot -> candidate) of the four are in flight together
+    for (int p0 = tid; p0 <= n; p0 += 4 * T) {
+        int k[4], ci[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int p = p0 + u * T; k[u] = p < n ? nof[p] : -1; ci[u] = p < n ? perm[p] : 0; }
+        uint2 bd[4]; int tg[4]; uint32_t c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            bd[u] = make_uint2(0u, 0u); tg[u] = tag - 1; c[u] = 0u;
+            if (k[u] >= 0) { { const uint32_t* nw32 = reinterpret_cast<const uint32_t*>(&nodes[k[u]]); bd[u] = make_uint2(nw32[0], nw32[1]); }      /* DNode is 44 bytes: 4-byte aligned only */ tg[u] = nodes[k[u]].tag; c[u] = cand[ci[u]]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + u * T;
+            if (p > n) continue;
+            unsigned long long a = 0, b = 0;
+            if (tg[u] == tag) {
+                const int q = quadrant_of_packed(bd[u], unpack_x(c[u]) - kRoiMargin, unpack_y(c[u]) - kRoiMargin);
                 if (q == 0) a = 1ull; else if (q == 1) a = 1ull << 32; else if (q == 2) b = 1ull; else b = 1ull << 32;
             }
+            sa[p] = a; sb[p] = b;
         }
-        D.scan_a[p] = a; D.scan_b[p] = b;
     }
     __syncthreads();
-    block_scan_u64(D.scan_a, n + 1, s_u64);
-    __syncthreads();
-    block_scan_u64(D.scan_b, n + 1, s_u64);
-    __syncthreads();
+    block_scan2_u64(D.scan_a, D.scan_b, n + 1, s_u64);
 }
 
 // Splits plist[0..nparents) (all carrying `tag`, quadrant_scans already done) at once.  Children are created in the
@@ -195,19 +257,40 @@ __device__ inline void split_nodes(const uint32_t* __restrict__ cand, int n, Dis
         D.nodes[pid] = nd;
     }
     __syncthreads();
-    const int* perm = D.perm[cur]; const int* nof = D.node_of[cur];
-    int* perm2 = D.perm[cur ^ 1]; int* nof2 = D.node_of[cur ^ 1];
-    for (int p = tid; p < n; p += T) {
-        const int k = nof[p];
-        const DNode nd = D.nodes[k];
-        if (nd.tag != tag) { perm2[p] = perm[p]; nof2[p] = k; continue; }
-        const uint32_t c = cand[perm[p]];
-        const int q = quadrant_of(nd, unpack_x(c) - kRoiMargin, unpack_y(c) - kRoiMargin);
-        const unsigned long long s = q < 2 ? D.scan_a[p] - D.scan_a[nd.begin] : D.scan_b[p] - D.scan_b[nd.begin];
-        const int r = (q & 1) ? (int)(s >> 32) : (int)(uint32_t)s;
-        const int cid = nd.kid[q];
-        const int cb = D.nodes[cid].begin;
-        perm2[cb + r] = perm[p]; nof2[cb + r] = cid;
+    const int* __restrict__ perm = D.perm[cur]; const int* __restrict__ nof = D.node_of[cur];
+    int* __restrict__ perm2 = D.perm[cur ^ 1]; int* __restrict__ nof2 = D.node_of[cur ^ 1];
+    const DNode* __restrict__ nodes = D.nodes;
+    const unsigned long long* __restrict__ sa = D.scan_a; const unsigned long long* __restrict__ sb = D.scan_b;
+    for (int p0 = tid; p0 < n; p0 += 4 * T) {           // four slots per thread and step, their dependent loads in flight together
+        int k[4], ci[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int p = p0 + u * T; k[u] = p < n ? nof[p] : -1; ci[u] = p < n ? perm[p] : 0; }
+        uint2 bd[4]; int tg[4], nb[4]; uint32_t c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            bd[u] = make_uint2(0u, 0u); tg[u] = tag - 1; nb[u] = 0; c[u] = 0u;
+            if (k[u] >= 0) { { const uint32_t* nw32 = reinterpret_cast<const uint32_t*>(&nodes[k[u]]); bd[u] = make_uint2(nw32[0], nw32[1]); }      /* DNode is 44 bytes: 4-byte aligned only */ tg[u] = nodes[k[u]].tag; nb[u] = nodes[k[u]].begin; c[u] = cand[ci[u]]; }
+        }
+        int q[4], cid[4], r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            q[u] = -1; cid[u] = 0; r[u] = 0;
+            if (tg[u] != tag) continue;
+            q[u] = quadrant_of_packed(bd[u], unpack_x(c[u]) - kRoiMargin, unpack_y(c[u]) - kRoiMargin);
+            const int p = p0 + u * T;
+            const unsigned long long sdf = q[u] < 2 ? sa[p] - sa[nb[u]] : sb[p] - sb[nb[u]];
+            r[u] = (q[u] & 1) ? (int)(sdf >> 32) : (int)(uint32_t)sdf;
+            cid[u] = nodes[k[u]].kid[q[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (q[u] >= 0) r[u] += nodes[cid[u]].begin;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + u * T;
+            if (k[u] < 0) continue;
+            if (q[u] < 0) { perm2[p] = ci[u]; nof2[p] = k[u]; continue; }
+            perm2[r[u]] = ci[u]; nof2[r[u]] = cid[u];
+        }
     }
     __syncthreads();
     if (tid == 0) { *node_count = base_id + total_kids; *total_kids_out = total_kids; *total_exp_out = total_exp; }
@@ -233,7 +316,7 @@ k_distribute(DistArgs A)
 {
     PLVS_DYN_SMEM(unsigned long long, s_sort);           // max quota + 8 elements for the std::sort emulation
     __shared__ int s_i32[32];
-    __shared__ unsigned long long s_u64[32];
+    __shared__ unsigned long long s_u64[64];
     __shared__ int s_nc, s_nk, s_ne, s_live, s_flag;
     const int level = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
     const LevelGeom g = A.levels[level];

@@ -33,6 +33,7 @@ struct float2 { float x, y; };
 struct float3 { float x, y, z; };
 struct float4 { float x, y, z, w; };
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline float3 make_float3(float x, float y, float z) { return float3{x, y, z}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
