@@ -267,4 +267,46 @@ int ref_tsdf_extract_mesh_kfids(void* h, uint32_t* kfids, long cap_verts)
     return (int)ord.size();
 }
 
+// The chunk map's iteration order (std::unordered_map<ChunkID, ChunkPtr, ChunkHasher>): what ChunkManager::Deform walks.  keys may be NULL.
+int ref_tsdf_chunk_order(void* h, int32_t* keys, int cap)
+{
+    Ref* r = (Ref*)h;
+    int n = 0;
+    for (auto& kv : r->map->GetChunkManager().GetChunks()) {
+        if (keys && n < cap) { keys[3 * n] = kv.first(0); keys[3 * n + 1] = kv.first(1); keys[3 * n + 2] = kv.first(2); }
+        ++n;
+    }
+    return n;
+}
+
+// ChiselServer::Deform (ChiselServer.cpp:616-620) -> Chisel::Deform -> ChunkManager::Deform.  Rt: n x 12 (R row-major, t in the 4th column).
+int ref_tsdf_deform(void* h, const uint32_t* kfids, const float* Rt, int n)
+{
+    Ref* r = (Ref*)h;
+    chisel::MapKfidRt map;
+    for (int i = 0; i < n; ++i) {
+        chisel::TransformRt T;
+        for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) T.R(a, b) = Rt[12 * i + 4 * a + b]; T.t(a) = Rt[12 * i + 4 * a + 3]; }
+        map[kfids[i]] = T;
+    }
+    r->map->Deform(map);
+    return 0;
+}
+
+// ChiselServer::IntegrateWorldPointCloud (ChiselServer.cpp:588-614) -> Chisel::IntegrateWorldPointCloudWithNormals
+int ref_tsdf_integrate_world_cloud(void* h, const float* xyz, const float* rgb, const float* normals, const uint32_t* kfids, uint32_t kfid_all, int n, const float* Twc)
+{
+    Ref* r = (Ref*)h;
+    chisel::PointCloud cloud;
+    for (int i = 0; i < n; ++i) {
+        cloud.AddPoint(chisel::Vec3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+        cloud.AddColor(rgb ? chisel::Vec3(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]) : chisel::Vec3(0.f, 0.f, 0.f));
+        cloud.GetMutableNormals().push_back(chisel::Vec3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]));
+        cloud.GetMutableKfids().push_back(kfids ? kfids[i] : kfid_all);
+    }
+    const chisel::Transform T = to_transform(Twc);
+    r->map->IntegrateWorldPointCloudWithNormals(r->integrator, cloud, T, r->p.far_plane);
+    return 0;
+}
+
 }  // extern "C"

@@ -139,6 +139,56 @@ def _mesh_kfids(self, n_verts):
     return out[:n_verts]
 
 
+def _deform(self, kfids, Rt, order=None):
+    """ChunkManager::Deform: kfids [n] uint32, Rt [n,3,4] float32 (R | t).  `order`: chunk keys [m,3] in the visiting order (the restatement
+    only; the compiled reference walks its own unordered_map)"""
+    kf = np.ascontiguousarray(kfids, np.uint32); T = np.ascontiguousarray(Rt, np.float32).reshape(len(kf), 12)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    if isinstance(self, RefMap):
+        fn = self._l.orc_tsdf_deform
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        with _quiet():
+            rc = fn(self._h, p(kf), p(T), len(kf))
+    else:
+        o = None if order is None else np.ascontiguousarray(order, np.int32).reshape(-1, 3)
+        fn = self._l.orc_tsdf_deform
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        rc = fn(self._h, p(kf), p(T), len(kf), p(o), 0 if o is None else len(o))
+    assert rc == 0
+
+
+def _integrate_world_cloud(self, xyz, rgb, normals, Twc, kfids=None, kfid=0):
+    """Chisel::IntegrateWorldPointCloudWithNormals: points (cloud frame), colours in [0,1] or None, normals, Twc; per-point keyframe ids or one id"""
+    xyz = np.ascontiguousarray(xyz, np.float32); nrm = np.ascontiguousarray(normals, np.float32)
+    rgb = None if rgb is None else np.ascontiguousarray(rgb, np.float32)
+    kf = None if kfids is None else np.ascontiguousarray(kfids, np.uint32)
+    T = np.ascontiguousarray(Twc, np.float32).reshape(12)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    fn = self._l.orc_tsdf_integrate_world_cloud
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+    with _quiet():
+        rc = fn(self._h, p(xyz), p(rgb), p(nrm), p(kf), int(kfid), len(xyz), p(T))
+    assert rc == 0
+
+
+import contextlib, os, sys
+
+
+@contextlib.contextmanager
+def _quiet():
+    """the reference prints progress lines to stdout"""
+    sys.stdout.flush()
+    saved = os.dup(1); null = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(null, 1)
+    try:
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1); os.close(null); os.close(saved)
+
+
+Map.deform = _deform
+Map.integrate_world_cloud = _integrate_world_cloud
 Map.integrate_cloud_kf = _integrate_cloud_kf
 Map.download_kfid = _download_kfid
 Map.mesh_kfids = _mesh_kfids
@@ -178,6 +228,16 @@ class RefMap(Map):
                 raise RuntimeError("oracle/_ref/libchisel_ref.so missing and /root/reference not present")
             RefMap._lib = C.CDLL(so)
         return _Prefixed(RefMap._lib, "ref_")
+
+    def chunk_order(self):
+        """keys [n,3] of the chunk map in its own iteration order (what ChunkManager::Deform walks)"""
+        fn = RefMap._lib.ref_tsdf_chunk_order
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        n = fn(self._h, None, 0)
+        keys = np.zeros((n, 3), np.int32)
+        if n:
+            fn(self._h, keys.ctypes.data_as(C.c_void_p), n)
+        return keys
 
     def update_meshes(self, all_chunks=False):
         """Chisel::UpdateMeshes (the chunks flagged since the last call), or every chunk"""

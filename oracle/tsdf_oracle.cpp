@@ -472,6 +472,167 @@ int orc_tsdf_integrate_cloud(void* h, const float* xyz, const float* rgb, int n,
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// §8f rank 3: ChunkManager::Deform (Thirdparty/open_chisel/src/ChunkManager.cpp:920-1062; ChiselServer::Deform, PointCloudMapChisel.cc:406-489).
+// Every known voxel (weight > 1e-15) whose keyframe id has an entry in the deformation map moves to R * pos + t; the first voxel that lands
+// in a new cell is copied (distance, weight, kfid, colour), later ones are folded in with DistVoxel::Integrate(sdf, weight) + SetKfid and
+// ColorVoxel::Integrate(r, g, b, 1) (division form, saturated), in the order the reference visits them: its chunk map's iteration order, then
+// voxel id.  That map is a std::unordered_map -- its order is a property of libstdc++ and of the whole insert/erase history -- so the order
+// is an INPUT here (`order` = m chunk keys; chunks not listed follow in (x,y,z) key order; NULL = key order, what the product uses);
+// tests/test_oracle_vs_reference_deform.py passes the compiled reference's own order and gets its result bit for bit.
+// The two float roundings that pick the new chunk (floor(pos * 1/(16 res))) and the new voxel (floor(pos * 1/res) - 16 * chunk) can disagree
+// at a chunk face; the reference then indexes outside the chunk (undefined behaviour): such voxels are dropped here.
+// ---------------------------------------------------------------------------------------------
+int orc_tsdf_deform(void* h, const uint32_t* kfids, const float* Rt /* n x 12: R row-major, then t in the 4th column */, int n, const int32_t* order, int m_order)
+{
+    Map* m = (Map*)h;
+    const float res = m->p.voxel_resolution;
+    const float half = res * 0.5f, inv_res = 1.f / res, rf = 1.0f / (16 * res);
+    std::unordered_map<uint32_t, int> which;
+    for (int i = 0; i < n; ++i) which[kfids[i]] = i;          // later entries of the same id win, like repeated operator[] assignments
+    std::vector<Key> visit;
+    std::unordered_map<Key, bool, KeyHash> listed;
+    for (int i = 0; i < m_order; ++i) { const Key k{order[3 * i], order[3 * i + 1], order[3 * i + 2]}; if (m->blocks.count(k) && !listed[k]) { visit.push_back(k); listed[k] = true; } }
+    {
+        std::map<std::tuple<int, int, int>, Key> rest;
+        for (auto& kv : m->blocks) if (!listed.count(kv.first)) rest[{kv.first.x, kv.first.y, kv.first.z}] = kv.first;
+        for (auto& kv : rest) visit.push_back(kv.second);
+    }
+    std::unordered_map<Key, std::unique_ptr<Block>, KeyHash> fresh;
+    int dropped = 0;
+    for (const Key& k : visit) {
+        const Block& B = *m->blocks[k];
+        const V3 origin{(float)(16 * k.x) * res, (float)(16 * k.y) * res, (float)(16 * k.z) * res};
+        int id = 0;
+        for (int z = 0; z < 16; ++z) for (int y = 0; y < 16; ++y) for (int x = 0; x < 16; ++x, ++id) {
+            if (B.w[id] <= 1e-15) continue;
+            auto it = which.find(B.kfid[id]);
+            if (it == which.end()) { ++dropped; continue; }
+            const float* T = Rt + 12 * (size_t)it->second;
+            const V3 pos = V3{(float)x * res + half, (float)y * res + half, (float)z * res + half} + origin;
+            const V3 np{T[0] * pos.x + (T[1] * pos.y + T[2] * pos.z) + T[3], T[4] * pos.x + (T[5] * pos.y + T[6] * pos.z) + T[7],
+                        T[8] * pos.x + (T[9] * pos.y + T[10] * pos.z) + T[11]};
+            const Key nk{(int)std::floor(np.x * rf), (int)std::floor(np.y * rf), (int)std::floor(np.z * rf)};
+            const int lx = (int)std::floor(np.x * inv_res) - 16 * nk.x, ly = (int)std::floor(np.y * inv_res) - 16 * nk.y, lz = (int)std::floor(np.z * inv_res) - 16 * nk.z;
+            if (lx < 0 || lx > 15 || ly < 0 || ly > 15 || lz < 0 || lz > 15) { ++dropped; continue; }
+            auto fit = fresh.find(nk);
+            if (fit == fresh.end()) fit = fresh.emplace(nk, std::make_unique<Block>()).first;
+            Block& N = *fit->second;
+            const int nid = (lz * 16 + ly) * 16 + lx;
+            if (N.w[nid] <= 1e-15) {
+                N.sdf[nid] = B.sdf[id]; N.w[nid] = B.w[id]; N.kfid[nid] = B.kfid[id];
+                std::memcpy(&N.rgba[(size_t)nid * 4], &B.rgba[(size_t)id * 4], 4);
+            } else {
+                const float ow = N.w[nid], os = N.sdf[nid];
+                N.sdf[nid] = (ow * os + B.w[id] * B.sdf[id]) / (B.w[id] + ow);
+                N.w[nid] = ow + B.w[id];
+                N.kfid[nid] = B.kfid[id];
+                if (m->p.use_color) {
+                    uint8_t* cv = &N.rgba[(size_t)nid * 4];
+                    const uint8_t* sc = &B.rgba[(size_t)id * 4];
+                    if (!(cv[3] >= 255 - 1)) {             // ColorVoxel::Integrate(r, g, b, 1) (ColorVoxel.h:68-89)
+                        const float wsum = (float)(1 + cv[3]);
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const float upd = std::min(std::max((float)(cv[3] * (float)cv[ch] + 1 * sc[ch]) / wsum, 0.0f), 255.0f);
+                            cv[ch] = (uint8_t)upd;
+                        }
+                        cv[3] = (uint8_t)(cv[3] + 1);
+                    }
+                }
+            }
+        }
+    }
+    m->blocks.swap(fresh);
+    m->n_collected = dropped;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// §8f rank 3 ("PLY load"): PointCloudMapChisel::LoadMap (src/PointCloudMapChisel.cc:527-549) reads the saved cloud with PCL (host I/O) and
+// hands it to ChiselServer::IntegrateWorldPointCloud -> Chisel::IntegrateWorldPointCloudWithNormals (Thirdparty/open_chisel/src/Chisel.cpp:
+// 238-379): per point a ray of +-4 voxels along its NORMAL, u = (centre - point) . dir, |u| < 4 res -> DistVoxel::Integrate(u, weight / (8 res)),
+// SetKfid, ColorVoxel::Integrate(r, g, b, 1); no carving; new chunks that stayed untouched are collected.
+// ---------------------------------------------------------------------------------------------
+int orc_tsdf_integrate_world_cloud(void* h, const float* xyz, const float* rgb, const float* normals, const uint32_t* kfids, uint32_t kfid_all, int n, const float* Twc)
+{
+    Map* m = (Map*)h;
+    const Params& P = m->p;
+    const float res = P.voxel_resolution;
+    const float r00 = Twc[0], r01 = Twc[1], r02 = Twc[2], r10 = Twc[4], r11 = Twc[5], r12 = Twc[6], r20 = Twc[8], r21 = Twc[9], r22 = Twc[10];
+    const V3 t{Twc[3], Twc[7], Twc[11]};
+    const float roundToVoxel = 1.0f / res, half = 0.5f * res, rf = 1.0f / (16 * res);
+    const float truncation = 4 * res;
+    std::unordered_map<Key, bool, KeyHash> updated, created;
+    m->n_updated = m->n_new = m->n_collected = 0;
+    std::vector<Key> walk;
+    for (int i = 0; i < n; ++i) {
+        const V3 p{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        const V3 wp{r00 * p.x + (r01 * p.y + r02 * p.z) + t.x, r10 * p.x + (r11 * p.y + r12 * p.z) + t.y, r20 * p.x + (r21 * p.y + r22 * p.z) + t.z};
+        V3 dir{normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]};
+        const float nn = dir.x * dir.x + (dir.y * dir.y + dir.z * dir.z);
+        if (nn > 0) { const float sq = std::sqrt(nn); dir = V3{dir.x / sq, dir.y / sq, dir.z / sq}; }
+        const V3 swp = wp * roundToVoxel;
+        const V3 sdt = (dir * truncation) * roundToVoxel;
+        const V3 start = swp - sdt, end = swp + sdt;
+        walk.clear();
+        {
+            int x = (int)std::floor(start.x), y = (int)std::floor(start.y), z = (int)std::floor(start.z);
+            const int endX = (int)std::floor(end.x), endY = (int)std::floor(end.y), endZ = (int)std::floor(end.z);
+            const V3 direction = end - start;
+            const float maxDist = direction.x * direction.x + (direction.y * direction.y + direction.z * direction.z);
+            const float dx = (float)(endX - x), dy = (float)(endY - y), dz = (float)(endZ - z);
+            const int stepX = (int)sgn_f((int)dx), stepY = (int)sgn_f((int)dy), stepZ = (int)sgn_f((int)dz);
+            float tMaxX = intbound(start.x, (int)dx), tMaxY = intbound(start.y, (int)dy), tMaxZ = intbound(start.z, (int)dz);
+            const float tDeltaX = ((float)stepX) / dx, tDeltaY = ((float)stepY) / dy, tDeltaZ = ((float)stepZ) / dz;
+            if (!(stepX == 0 && stepY == 0 && stepZ == 0)) {
+                for (;;) {
+                    walk.push_back(Key{x, y, z});
+                    const V3 d3{(float)x - start.x, (float)y - start.y, (float)z - start.z};
+                    const float dist = d3.x * d3.x + (d3.y * d3.y + d3.z * d3.z);
+                    if (dist > maxDist) break;
+                    if (x == endX && y == endY && z == endZ) break;
+                    if (tMaxX < tMaxY) { if (tMaxX < tMaxZ) { x += stepX; tMaxX += tDeltaX; } else { z += stepZ; tMaxZ += tDeltaZ; } }
+                    else { if (tMaxY < tMaxZ) { y += stepY; tMaxY += tDeltaY; } else { z += stepZ; tMaxZ += tDeltaZ; } }
+                }
+            }
+        }
+        for (const Key& vc : walk) {
+            const V3 center{(float)vc.x * res + half, (float)vc.y * res + half, (float)vc.z * res + half};
+            const Key cid{(int)std::floor(center.x * rf), (int)std::floor(center.y * rf), (int)std::floor(center.z * rf)};
+            auto it = m->blocks.find(cid);
+            if (it == m->blocks.end()) { it = m->blocks.emplace(cid, std::make_unique<Block>()).first; created[cid] = true; updated[cid] = false; }
+            const int lx = vc.x - cid.x * 16, ly = vc.y - cid.y * 16, lz = vc.z - cid.z * 16;
+            const int id = (lz * 16 + ly) * 16 + lx;
+            if (!(id >= 0 && id < 4096)) continue;
+            Block& B = *it->second;
+            const V3 dcp = center - wp;
+            const float u = dcp.x * dir.x + (dcp.y * dir.y + dcp.z * dir.z);
+            const float weight = P.weight / (2.0f * truncation);
+            if (std::fabs(u) < truncation) {
+                const float ow = B.w[id], os = B.sdf[id];
+                B.sdf[id] = (ow * os + weight * u) / (weight + ow);
+                B.w[id] = ow + weight;
+                B.kfid[id] = kfids ? kfids[i] : kfid_all;
+                uint8_t* cv = &B.rgba[(size_t)id * 4];
+                if (P.use_color && !(cv[3] >= 255 - 1)) {
+                    const uint8_t nc[3] = {(uint8_t)((rgb ? rgb[3 * i] : 0.f) * 255.0f), (uint8_t)((rgb ? rgb[3 * i + 1] : 0.f) * 255.0f), (uint8_t)((rgb ? rgb[3 * i + 2] : 0.f) * 255.0f)};
+                    const float wsum = (float)(1 + cv[3]);
+                    for (int ch = 0; ch < 3; ++ch) cv[ch] = (uint8_t)std::min(std::max((float)(cv[3] * (float)cv[ch] + 1 * nc[ch]) / wsum, 0.0f), 255.0f);
+                    cv[3] = (uint8_t)(cv[3] + 1);
+                }
+                updated[cid] = true;
+            }
+        }
+    }
+    for (auto& kv : updated) if (kv.second) ++m->n_updated;
+    for (auto& kv : created) {
+        if (!updated[kv.first]) { m->blocks.erase(kv.first); ++m->n_collected; }
+        else ++m->n_new;
+    }
+    return 0;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
