@@ -245,6 +245,8 @@ int plvs_match_projection_last(plvs_match* h, const plvs_frame_view* cur, const 
 int plvs_match_kernel_times(plvs_match* h, float* ms, int32_t* launches, int reset);
 /* rounds of the claim fixed point and kernels launched by the last projection search */
 int plvs_match_last_stats(const plvs_match* h, int* rounds, int* kernel_launches);
+/* candidate-list re-evaluations of the last projection search after round 0 (-1: the cluster kernel ran, which re-walks every list every round) */
+int plvs_match_last_walks(const plvs_match* h);
 
 /* DBoW2::FeatureVector flattened: sorted node ids, CSR offsets, feature indices (ascending per node) */
 typedef struct {

@@ -459,14 +459,15 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
               const Round0* __restrict__ round0, int32_t* __restrict__ assign_out /*n, mapped host*/, int* __restrict__ result, int* __restrict__ max_count)
 {
     PLVS_DYN_SMEM_ALIGNED(uint32_t, s_dyn, 16);
-    __shared__ int s_count, s_hist[HISTO], s_keep[HISTO], s_walks;
-    const int tid = threadIdx.x;
+    __shared__ int s_count, s_hist[HISTO], s_keep[HISTO], s_walks, s_nwalk;
+    const int tid = threadIdx.x, lane32 = tid & 31, wid = tid >> 5;
     const int INF = 0x7fffffff;
     WatchRec* s_watch = reinterpret_cast<WatchRec*>(s_dyn);                    // nq (16-byte records first: alignment)
     int* tab0 = reinterpret_cast<int*>(s_dyn + 4 * (size_t)nq);               // n
     int* tab1 = tab0 + n;                                                      // n
     int* s_target = tab1 + n;                                                  // nq
-    uint8_t* s_obs = reinterpret_cast<uint8_t*>(s_target + nq);                // nq: Observations() > 0
+    int* s_wlist = s_target + nq;                                              // nq: queries queued for a re-evaluation this round
+    uint8_t* s_obs = reinterpret_cast<uint8_t*>(s_wlist + nq);                 // nq: Observations() > 0
     if (tid == 0) s_walks = 0;
     for (int i = tid; i < n; i += 1024) { const int v = (claimed_in && claimed_in[i]) ? -1 : INF; tab0[i] = v; tab1[i] = v; }
     for (int q = tid; q < nq; q += 1024) {
@@ -496,21 +497,34 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
         __syncthreads();
         { int* t = cur; cur = nxt; nxt = t; }
         bool changed = false;
+        // (1) which queries saw something change among the candidates they depend on?  They queue up for a re-evaluation.
+        if (tid == 0) s_nwalk = 0;
+        __syncthreads();
         for (int q = tid; q < nq; q += 1024) {
-            WatchRec w = s_watch[q];
+            const WatchRec w = s_watch[q];
             bool walk = w.n == 255;
             if (!walk)
                 for (int j = 0; j < (int)w.n; ++j) walk |= ((cur[w.kp[j]] < q) != (((w.blocked >> j) & 1) != 0));
-            if (!walk) continue;
-            // full evaluation against the new table (list from L2; rows are cap * 4 bytes, cap a multiple of 4)
+            if (walk) s_wlist[atomicAdd(&s_nwalk, 1)] = q;          // order irrelevant: an evaluation reads `cur` and writes its own records only
+        }
+        __syncthreads();
+        // (2) one warp per queued query: the lanes take the list entries (rows are read from L2, coalesced), warp reductions give the best and
+        // second-best free candidate, a ballot the new watch set
+        const int nwalk = s_nwalk;
+        for (int i = wid; i < nwalk; i += 32) {
+            const int q = s_wlist[i];
             const int m = min(cand_n[q], cap);
             const uint32_t* row = cand + (size_t)q * cap;
             uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
-            for (int k = 0; k < m; ++k) {
-                const uint32_t e = row[k];
-                const uint32_t key = (cur[cand_idx(e)] < q) ? 0xffffffffu : (((uint32_t)cand_dist(e) << 16) | (uint32_t)k);
-                const uint32_t lo = min(k1, key), hi = max(k1, key);
-                k2 = min(k2, hi); k1 = lo;
+            for (int k0 = 0; k0 < m; k0 += 32) {
+                const int k = k0 + lane32;
+                uint32_t key = 0xffffffffu;
+                if (k < m) { const uint32_t e = row[k]; if (!(cur[cand_idx(e)] < q)) key = ((uint32_t)cand_dist(e) << 16) | (uint32_t)k; }
+                const uint32_t s1 = __reduce_min_sync(0xffffffffu, key);
+                const uint32_t s2 = __reduce_min_sync(0xffffffffu, key == s1 ? 0xffffffffu : key);
+                const uint32_t lo = min(k1, s1), hi = max(k1, s1);
+                k2 = min(hi, min(k2, s2));
+                k1 = lo;
             }
             const uint32_t e1 = k1 != 0xffffffffu ? row[k1 & 0xffffu] : 0u, e2 = k2 != 0xffffffffu ? row[k2 & 0xffffu] : 0u;
             const int t = decide_target<MODE>(k1, k2, e1, e2, nn_ratio, th_high);
@@ -519,20 +533,33 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
             WatchRec nw; nw.n = 0; nw.blocked = 0; nw.pad = 0;
 #pragma unroll
             for (int j = 0; j < kWatch; ++j) nw.kp[j] = 0;
-            for (int k = 0; k < m; ++k) {
-                const uint32_t e = row[k];
-                const uint32_t key = ((uint32_t)cand_dist(e) << 16) | (uint32_t)k;
-                const int c = cur[cand_idx(e)];
-                if (key > limit || c == -1) continue;
-                if (nw.n >= kWatch) { nw.n = 255; break; }
-                nw.kp[nw.n] = (uint16_t)cand_idx(e);
-                if (c < q) nw.blocked |= (uint8_t)(1u << nw.n);
-                ++nw.n;
+            int cnt = 0;
+            for (int k0 = 0; k0 < m && cnt <= kWatch; k0 += 32) {
+                const int k = k0 + lane32;
+                bool rel = false; int c = 0; uint32_t e = 0;
+                if (k < m) { e = row[k]; c = cur[cand_idx(e)]; rel = ((((uint32_t)cand_dist(e) << 16) | (uint32_t)k) <= limit) && c != -1; }
+                const uint32_t mask = __ballot_sync(0xffffffffu, rel);
+                const int pos = cnt + __popc(mask & ((1u << lane32) - 1));
+                // the lanes hand their entry to lane 0, which assembles the record (at most kWatch entries matter)
+#pragma unroll
+                for (int j = 0; j < kWatch; ++j) {
+                    const uint32_t src = __ballot_sync(0xffffffffu, rel && pos == j);
+                    if (src) {
+                        const int l = __ffs(src) - 1;
+                        const uint32_t ee = __shfl_sync(0xffffffffu, e, l); const int cc = __shfl_sync(0xffffffffu, c, l);
+                        nw.kp[j] = (uint16_t)cand_idx(ee);
+                        if (cc < q) nw.blocked |= (uint8_t)(1u << j);
+                    }
+                }
+                cnt += __popc(mask);
             }
-            s_watch[q] = nw;
-            atomicAdd(&s_walks, 1);
-            if (t != s_target[q]) { s_target[q] = t; changed = true; }
+            nw.n = cnt > kWatch ? 255 : (uint8_t)cnt;
+            if (lane32 == 0) {
+                s_watch[q] = nw;
+                if (t != s_target[q]) { s_target[q] = t; changed = true; }
+            }
         }
+        if (tid == 0) s_walks += nwalk;
         ++rounds;
         if (!__syncthreads_or(changed ? 1 : 0)) break;
     }
@@ -1085,7 +1112,7 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         h->grid_key = F->cache_key; h->grid_n = n;
     }
     // one CTA holds the claim tables, the targets and (if they fit) the compacted lists; past that the 8-CTA cluster kernel takes over
-    const size_t cta_smem = (size_t)16 * nq + (size_t)8 * n + (size_t)4 * nq + align_up((size_t)nq, 16);      // watch records, two claim tables, targets, flags
+    const size_t cta_smem = (size_t)16 * nq + (size_t)8 * n + (size_t)8 * nq + align_up((size_t)nq, 16);      // watch records, two claim tables, targets, walk queue, flags
     // development / test knob, read per call: PLVS_MATCH_RESOLVE=cluster forces the 8-CTA cluster kernel
     const char* e_res = std::getenv("PLVS_MATCH_RESOLVE");
     const bool force_cluster = e_res && std::strcmp(e_res, "cluster") == 0;
@@ -1207,6 +1234,8 @@ int plvs_match_kernel_times(plvs_match* h, float* ms, int32_t* launches, int res
     if (reset) h->timer.reset();
     return PLVS_OK;
 }
+
+int plvs_match_last_walks(const plvs_match* h) { return h ? h->last_walks : -1; }
 
 int plvs_match_last_stats(const plvs_match* h, int* rounds, int* kernel_launches)
 {
