@@ -503,6 +503,22 @@ int plvs_tsdf_integrate_cloud_kf(plvs_tsdf* h, const float* xyz, const float* rg
 int plvs_tsdf_download_kfid(plvs_tsdf* h, uint32_t* kfid, int cap, int* n_out);
 int plvs_tsdf_get_mesh_kfids(plvs_tsdf* h, uint32_t* kfids, long long cap_verts, int on_device);
 
+/* ChiselServer::Deform(MapKfidRt&) -> ChunkManager::Deform (Thirdparty/open_chisel/src/ChunkManager.cpp:920-1062), the loop-closure correction of
+ * PointCloudMapChisel (src/PointCloudMapChisel.cc:406-489): every known voxel whose keyframe id (plvs_tsdf_integrate_cloud_kf) is one of kfids[n] moves to
+ * R * pos + t with Rt[12 * i] = (R row-major | t) of kfids[i]; voxels of other keyframes are dropped; voxels that land in one cell are folded in visiting
+ * order (first: copy; later: DistVoxel::Integrate, SetKfid, ColorVoxel::Integrate(r,g,b,1)).  The reference visits its chunks in std::unordered_map order,
+ * which no caller can know: chunk_order[3 * i] lists chunk ids to visit first (tests pass the compiled reference's own order), the remaining chunks follow
+ * in (x,y,z) order -- n_order = 0 gives a deterministic result.  The meshes of the last plvs_tsdf_update_meshes move with their vertices.  The pool must
+ * hold the old and the new map at once; otherwise PLVS_ENOMEM is returned and the map is left unchanged. */
+int plvs_tsdf_deform(plvs_tsdf* h, const uint32_t* kfids, const float* Rt, int n, const int32_t* chunk_order, int n_order);
+
+/* ChiselServer::IntegrateWorldPointCloud -> Chisel::IntegrateWorldPointCloudWithNormals (Thirdparty/open_chisel/src/Chisel.cpp:238-379), what
+ * PointCloudMapChisel::LoadMap does with a saved map (src/PointCloudMapChisel.cc:527-549, after PCL has read the PLY file): every point updates the voxels
+ * within 4 voxel sizes along its normal (u = (centre - point) . n, weight = w / (8 res)), stamps them with its keyframe id and colour.  xyz / normals: n
+ * triples in the frame of Twc; rgb in [0,1] or NULL; kfids[n] or NULL for kfid_all. */
+int plvs_tsdf_integrate_world_cloud(plvs_tsdf* h, const float* xyz, const float* rgb, const float* normals, const uint32_t* kfids, uint32_t kfid_all, int n,
+                                    const float Twc[12]);
+
 /* ChiselServer::SaveMesh -> Chisel::SaveAllMeshesToPLY (Thirdparty/open_chisel/src/Chisel.cpp:79-118, src/io/PLY.cpp:29-86): the vertices (and colours,
  * or NULL for a map without colour) that plvs_tsdf_get_meshes returned, as the reference's ASCII PLY.  Host I/O only. */
 int plvs_mesh_save_ply(const char* path, const float* verts, const float* colors, long long n_verts);

@@ -109,6 +109,26 @@ class ChiselServer:
                                                     d.shape[0] if d is not None else 0, p(T))
         _lib.check(rc, "plvs_tsdf_integrate_cloud_kf")
 
+    def Deform(self, kfids, Rt, chunk_order=None):
+        """ChiselServer::Deform(MapKfidRt&): kfids [n] uint32 -> Rt [n,3,4] (R | t).  chunk_order: optional chunk ids [m,3] to visit first (the
+        reference walks a std::unordered_map; the default, key order, is deterministic)"""
+        kf = np.ascontiguousarray(kfids, np.uint32); T = np.ascontiguousarray(Rt, np.float32).reshape(len(kf), 12)
+        o = None if chunk_order is None else np.ascontiguousarray(chunk_order, np.int32).reshape(-1, 3)
+        rc = self._lib.plvs_tsdf_deform(self._h, kf.ctypes.data_as(C.c_void_p), T.ctypes.data_as(C.c_void_p), len(kf),
+                                        o.ctypes.data_as(C.c_void_p) if o is not None else None, 0 if o is None else len(o))
+        _lib.check(rc, "plvs_tsdf_deform")
+
+    def IntegrateWorldPointCloud(self, xyz, rgb, normals, Twc, kfids=None, kfid=0):
+        """ChiselServer::IntegrateWorldPointCloud (what PointCloudMapChisel::LoadMap feeds a saved map into): points + normals in the frame of Twc,
+        colours in [0,1] or None, per-point keyframe ids or one id"""
+        xyz = np.ascontiguousarray(xyz, np.float32); nrm = np.ascontiguousarray(normals, np.float32)
+        rgb = None if rgb is None else np.ascontiguousarray(rgb, np.float32)
+        kf = None if kfids is None else np.ascontiguousarray(kfids, np.uint32)
+        T = np.ascontiguousarray(Twc, np.float32).reshape(12)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        rc = self._lib.plvs_tsdf_integrate_world_cloud(self._h, p(xyz), p(rgb), p(nrm), p(kf), int(kfid), len(xyz), p(T))
+        _lib.check(rc, "plvs_tsdf_integrate_world_cloud")
+
     def download_kfid(self):
         """DistVoxel::GetKfid of every voxel, blocks sorted like download()"""
         n = C.c_int()

@@ -880,6 +880,42 @@ public:
                                                    with_depth ? depth_ : nullptr, with_depth ? dw_ : 0, with_depth ? dh_ : 0, cloudTwc_), "plvs_tsdf_integrate_cloud");
         if (updateMesh) UpdateMesh();
     }
+    // void ChiselServer::Deform(chisel::MapKfidRt& deformationMap) (ChiselServer.h:202, src/PointCloudMapChisel.cc:489): MapT is any map
+    // kfid -> {R (3x3, operator()(r,c)), t (operator()(r))} such as chisel::MapKfidRt.  Chunks are visited in (x,y,z) key order (the reference
+    // walks a std::unordered_map: see plvs_tsdf_deform).
+    template <class MapT>
+    void Deform(MapT& deformationMap)
+    {
+        std::vector<uint32_t> ids; std::vector<float> Rt;
+        ids.reserve(deformationMap.size()); Rt.reserve(12 * deformationMap.size());
+        for (const auto& kv : deformationMap) {
+            ids.push_back((uint32_t)kv.first);
+            for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) Rt.push_back(kv.second.R(r, c)); Rt.push_back(kv.second.t(r)); }
+        }
+        plvs_shim::check(plvs_tsdf_deform(h_, ids.data(), Rt.data(), (int)ids.size(), nullptr, 0), "plvs_tsdf_deform");
+    }
+    // template<PointType> void ChiselServer::IntegrateWorldPointCloud(const pcl::PointCloud<PointType>& cloud, chisel::Transform& Twc)
+    // (ChiselServer.h:199, PointCloudMapChisel::LoadMap): points with x, y, z, normal_x/y/z, r/g/b (and kfid when the type has it)
+    template <class CloudT>
+    void IntegrateWorldPointCloud(const CloudT& cloud, const Eigen::Affine3f& Twc)
+    {
+        const size_t n = cloud.points.size();
+        std::vector<float> xyz(3 * n), nrm(3 * n), rgb(useColor ? 3 * n : 0);
+        std::vector<uint32_t> kf(n, 0u); bool hasKfid = n > 0;
+        const float byteToFloat = 1.0f / 255.0f;
+        size_t i = 0;
+        for (const auto& pt : cloud.points) {
+            xyz[3 * i] = pt.x; xyz[3 * i + 1] = pt.y; xyz[3 * i + 2] = pt.z;
+            nrm[3 * i] = pt.normal_x; nrm[3 * i + 1] = pt.normal_y; nrm[3 * i + 2] = pt.normal_z;
+            if (!rgb.empty() && !plvs_shim::point_rgb(pt, byteToFloat, &rgb[3 * i])) rgb.clear();
+            if (hasKfid && !plvs_shim::point_kfid(pt, &kf[i])) hasKfid = false;
+            ++i;
+        }
+        float T[12];
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T[4 * r + c] = Twc.linear()(r, c); T[4 * r + 3] = Twc.translation()(r); }
+        plvs_shim::check(plvs_tsdf_integrate_world_cloud(h_, xyz.data(), rgb.empty() ? nullptr : rgb.data(), nrm.data(), hasKfid ? kf.data() : nullptr, 0u, (int)n, T),
+                         "plvs_tsdf_integrate_world_cloud");
+    }
     plvs_tsdf* handle() { return h_; }
 
 protected:

@@ -118,5 +118,14 @@ extern "C" int shim_instantiate(int run)
     struct CloudP { std::vector<PointXYZ> points; } cp; cp.points.push_back({0.1f, 0.2f, 1.f});
     cs.SetPointCloud(cc, T); cs.IntegrateLastPointCloud(false);
     cs.SetPointCloud(cp, T); cs.IntegrateLastPointCloud(false);
+    // Deform + the map-loading route
+    struct M3 { float m[3][3]; float operator()(int r, int c2) const { return m[r][c2]; } };
+    struct Vt { float v[3]; float operator()(int r) const { return v[r]; } };
+    struct Rt { M3 R; Vt t; };
+    std::map<unsigned, Rt> deformation; deformation[7u] = Rt{{{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}}, {{0.f, 0.f, 0.f}}};
+    cs.Deform(deformation);
+    struct PointN { float x, y, z, normal_x, normal_y, normal_z; unsigned char b, g, r, a; unsigned kfid; };
+    struct CloudN { std::vector<PointN> points; } cn; cn.points.push_back({0.1f, 0.2f, 1.f, 0.f, 0.f, -1.f, 1, 2, 3, 255, 7u});
+    cs.IntegrateWorldPointCloud(cn, T);
     return mono + a + b + c;
 }

@@ -312,3 +312,105 @@ def _impl_keyframe_ids():
 
 def test_keyframe_ids(gpu):
     _isolated("_impl_keyframe_ids")
+
+
+def _rt(rng, scale):
+    a = rng.normal(size=3); a /= np.linalg.norm(a)
+    th = scale * rng.uniform(0.2, 1.0)
+    Kx = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+    return np.concatenate([R, (scale * rng.normal(size=3))[:, None]], 1).astype(np.float32)
+
+
+def _impl_deform():
+    """ChunkManager::Deform (§8f rank 3): product == oracle (pinned bit-exactly to the compiled open_chisel with the reference's own chunk order,
+    tests/test_oracle_vs_reference_deform.py) for the default key order and for an explicit visiting order; voxels of unlisted keyframes vanish;
+    collisions fold in order; the meshes of the last UpdateMesh move along; the map keeps working afterwards; a pool too small leaves it untouched"""
+    from plvs_b200 import scenario, tsdf as T
+    from oracle import tsdf as OT
+    w, h = 160, 120
+    K = synth.intrinsics(w, h)
+    rng = np.random.default_rng(3)
+    for color, scale, explicit in ((1, 0.02, False), (1, 0.3, True), (0, 0.1, False)):
+        p = T.default_params(voxel_resolution=0.04, use_carving=1, carving_dist=0.05, near_plane=0.1, far_plane=4.0, max_blocks=8192, use_color=color)
+        g = T.ChiselServer(p); g.SetDepthCameraInfo(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
+        o = OT.Map(p, threads=8); o.set_camera(K["fx"], K["fy"], K["cx"], K["cy"], w, h)
+        for i, f in enumerate((0, 2, 5, 9)):
+            d = synth.depth_frame(f, w, h)
+            xyz, rgb = scenario.cloud_from_depth(d, synth.bgr_frame(f, w, h) if color else None, K, step=2)
+            g.integrate_cloud_kf(xyz, rgb, synth.pose(f), d, kfid=101 + i); o.integrate_cloud_kf(xyz, rgb, synth.pose(f), d, kfid=101 + i)
+        nm, nv = g.UpdateMesh()
+        mk, mc, V0, N0, C0 = g.GetMeshes(); vk = g.mesh_kfids()
+        kf = np.array([101, 102, 104], np.uint32)
+        Rt = np.stack([_rt(rng, scale) for _ in kf])
+        order = o.download()[0][::-1].copy() if explicit else None
+        g.Deform(kf, Rt, order); o.deform(kf, Rt, order=order)
+        gk, gs, gw, gc = g.download(); ok, os_, ow, oc = o.download()
+        assert np.array_equal(gk, ok) and len(gk) > 30
+        assert np.array_equal(gw.view(np.uint32), ow.view(np.uint32)) and np.array_equal(gs.view(np.uint32), os_.view(np.uint32)) and np.array_equal(gc, oc)
+        assert np.array_equal(g.download_kfid(), o.download_kfid())
+        assert g.stats()["n_blocks"] == len(gk)
+        # the stored meshes moved with their keyframes (vertices of keyframe 103 stay)
+        _, _, V1, N1, _ = g.GetMeshes()
+        for j, k in enumerate(kf):
+            sel = vk == k
+            R, t = Rt[j][:, :3], Rt[j][:, 3]
+            want = np.stack([R[a, 0] * V0[sel, 0] + (R[a, 1] * V0[sel, 1] + R[a, 2] * V0[sel, 2]) + t[a] for a in range(3)], 1).astype(np.float32)
+            assert np.array_equal(V1[sel].view(np.uint32), want.view(np.uint32)) and sel.sum() > 10
+        assert np.array_equal(V1[vk == 103], V0[vk == 103])
+        # the deformed map keeps working
+        d = synth.depth_frame(11, w, h)
+        xyz, rgb = scenario.cloud_from_depth(d, synth.bgr_frame(11, w, h) if color else None, K, step=3)
+        g.integrate_cloud_kf(xyz, rgb, synth.pose(11), d, kfid=105); o.integrate_cloud_kf(xyz, rgb, synth.pose(11), d, kfid=105)
+        gk, gs, gw, gc = g.download(); ok, os_, ow, oc = o.download()
+        assert np.array_equal(gk, ok) and np.array_equal(gw.view(np.uint32), ow.view(np.uint32)) and np.array_equal(gs.view(np.uint32), os_.view(np.uint32))
+    # a pool that cannot hold both maps: refused, map unchanged
+    p = T.default_params(voxel_resolution=0.04, use_carving=0, near_plane=0.1, far_plane=4.0, max_blocks=0, use_color=1)
+    d = synth.depth_frame(0, w, h)
+    xyz, rgb = scenario.cloud_from_depth(d, synth.bgr_frame(0, w, h), K, step=2)
+    probe = T.ChiselServer(T.default_params(voxel_resolution=0.04, use_carving=0, near_plane=0.1, far_plane=4.0, max_blocks=4096, use_color=1))
+    probe.integrate_cloud_kf(xyz, rgb, synth.pose(0), None, kfid=1)
+    nblk = probe.stats()["n_blocks"]
+    p.max_blocks = nblk + 8
+    small = T.ChiselServer(p)
+    small.integrate_cloud_kf(xyz, rgb, synth.pose(0), None, kfid=1)
+    before = small.download()
+    with pytest.raises(Exception):
+        small.Deform(np.array([1], np.uint32), _rt(rng, 0.5)[None])
+    after = small.download()
+    assert all(np.array_equal(a, b) for a, b in zip(before, after)) and small.stats()["n_blocks"] == nblk
+
+
+def test_deform(gpu):
+    _isolated("_impl_deform")
+
+
+def _impl_world_cloud():
+    """Chisel::IntegrateWorldPointCloudWithNormals (§8f rank 3, the map-loading route): product == oracle (pinned bit-exactly to the compiled open_chisel)"""
+    from plvs_b200 import scenario, tsdf as T
+    from oracle import tsdf as OT
+    w, h = 160, 120
+    K = synth.intrinsics(w, h)
+    rng = np.random.default_rng(9)
+    for color in (1, 0):
+        p = T.default_params(voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=8192, use_color=color)
+        g = T.ChiselServer(p); o = OT.Map(p, threads=8)
+        for f in (0, 4):
+            d = synth.depth_frame(f, w, h)
+            xyz, rgb = scenario.cloud_from_depth(d, synth.bgr_frame(f, w, h), K, step=2)
+            Pw = (xyz @ synth.pose(f)[:, :3].T + synth.pose(f)[:, 3]).astype(np.float32)
+            nrm = rng.normal(size=Pw.shape).astype(np.float32) * np.float32(0.2) + np.array([0, 0, -1], np.float32)
+            nrm[::97] = 0
+            kf = rng.integers(1, 9, len(Pw)).astype(np.uint32)
+            Twc = np.eye(4, dtype=np.float32)[:3] if f == 0 else synth.pose(1)
+            g.IntegrateWorldPointCloud(Pw, rgb if color else None, nrm, Twc, kfids=kf); o.integrate_world_cloud(Pw, rgb if color else None, nrm, Twc, kfids=kf)
+            gk, gs, gw, gc = g.download(); ok, os_, ow, oc = o.download()
+            assert np.array_equal(gk, ok) and len(gk) > 30
+            assert np.array_equal(gw.view(np.uint32), ow.view(np.uint32)) and np.array_equal(gs.view(np.uint32), os_.view(np.uint32)) and np.array_equal(gc, oc)
+            assert np.array_equal(g.download_kfid(), o.download_kfid())
+        g.IntegrateWorldPointCloud(np.zeros((0, 3), np.float32), None, np.zeros((0, 3), np.float32), np.eye(4, dtype=np.float32)[:3])      # empty cloud: nothing happens
+        assert g.stats()["n_blocks"] == len(gk)
+
+
+def test_world_cloud(gpu):
+    _isolated("_impl_world_cloud")
