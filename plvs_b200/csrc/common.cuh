@@ -1,6 +1,9 @@
 // Shared host/device helpers for libplvs_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#ifndef PLVS_CUDA_EMU
+#include <cuda.h>            // CUtensorMap + the cuTensorMapEncodeTiled prototype (the function is fetched with cudaGetDriverEntryPoint: no libcuda link)
+#endif
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>

@@ -501,10 +501,15 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
         if (tid == 0) s_nwalk = 0;
         __syncthreads();
         for (int q = tid; q < nq; q += 1024) {
-            const WatchRec w = s_watch[q];
-            bool walk = w.n == 255;
-            if (!walk)
-                for (int j = 0; j < (int)w.n; ++j) walk |= ((cur[w.kp[j]] < q) != (((w.blocked >> j) & 1) != 0));
+            const uint4 raw = reinterpret_cast<const uint4*>(s_watch)[q];                 // kp[0..5] | n, blocked, pad
+            const uint32_t wn = raw.w & 0xffu, wb = (raw.w >> 8) & 0xffu;
+            bool walk = wn == 255u;
+            if (!walk) {
+                const uint32_t kp[kWatch] = {raw.x & 0xffffu, raw.x >> 16, raw.y & 0xffffu, raw.y >> 16, raw.z & 0xffffu, raw.z >> 16};
+#pragma unroll
+                for (int j = 0; j < kWatch; ++j)
+                    if ((uint32_t)j < wn) walk |= ((cur[kp[j]] < q) != (((wb >> j) & 1u) != 0u));
+            }
             if (walk) s_wlist[atomicAdd(&s_nwalk, 1)] = q;          // order irrelevant: an evaluation reads `cur` and writes its own records only
         }
         __syncthreads();
@@ -515,11 +520,11 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
             const int q = s_wlist[i];
             const int m = min(cand_n[q], cap);
             const uint32_t* row = cand + (size_t)q * cap;
-            uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+            uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu, e_first = 0u;
             for (int k0 = 0; k0 < m; k0 += 32) {
                 const int k = k0 + lane32;
                 uint32_t key = 0xffffffffu;
-                if (k < m) { const uint32_t e = row[k]; if (!(cur[cand_idx(e)] < q)) key = ((uint32_t)cand_dist(e) << 16) | (uint32_t)k; }
+                if (k < m) { const uint32_t e = row[k]; if (k0 == 0) e_first = e; if (!(cur[cand_idx(e)] < q)) key = ((uint32_t)cand_dist(e) << 16) | (uint32_t)k; }
                 const uint32_t s1 = __reduce_min_sync(0xffffffffu, key);
                 const uint32_t s2 = __reduce_min_sync(0xffffffffu, key == s1 ? 0xffffffffu : key);
                 const uint32_t lo = min(k1, s1), hi = max(k1, s1);
@@ -528,34 +533,29 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
             }
             const uint32_t e1 = k1 != 0xffffffffu ? row[k1 & 0xffffu] : 0u, e2 = k2 != 0xffffffffu ? row[k2 & 0xffffu] : 0u;
             const int t = decide_target<MODE>(k1, k2, e1, e2, nn_ratio, th_high);
-            // new watch set: every candidate up to the last one the decision read, except pre-claimed ones, with the state just seen
+            // new watch set: every candidate up to the last one the decision read, except pre-claimed ones, with the state just seen.  The
+            // lanes write their keypoint straight into the shared-memory record at their rank; lane 0 derives the blocked bits from two ballots.
             const uint32_t limit = MODE == 0 ? k2 : k1;              // 0xffffffff (not enough free candidates): the whole list matters
-            WatchRec nw; nw.n = 0; nw.blocked = 0; nw.pad = 0;
-#pragma unroll
-            for (int j = 0; j < kWatch; ++j) nw.kp[j] = 0;
-            int cnt = 0;
+            uint16_t* wkp = reinterpret_cast<uint16_t*>(&s_watch[q]);
+            int cnt = 0; uint32_t bits = 0;
             for (int k0 = 0; k0 < m && cnt <= kWatch; k0 += 32) {
                 const int k = k0 + lane32;
-                bool rel = false; int c = 0; uint32_t e = 0;
-                if (k < m) { e = row[k]; c = cur[cand_idx(e)]; rel = ((((uint32_t)cand_dist(e) << 16) | (uint32_t)k) <= limit) && c != -1; }
-                const uint32_t mask = __ballot_sync(0xffffffffu, rel);
-                const int pos = cnt + __popc(mask & ((1u << lane32) - 1));
-                // the lanes hand their entry to lane 0, which assembles the record (at most kWatch entries matter)
-#pragma unroll
-                for (int j = 0; j < kWatch; ++j) {
-                    const uint32_t src = __ballot_sync(0xffffffffu, rel && pos == j);
-                    if (src) {
-                        const int l = __ffs(src) - 1;
-                        const uint32_t ee = __shfl_sync(0xffffffffu, e, l); const int cc = __shfl_sync(0xffffffffu, c, l);
-                        nw.kp[j] = (uint16_t)cand_idx(ee);
-                        if (cc < q) nw.blocked |= (uint8_t)(1u << j);
-                    }
+                bool rel = false, blk = false; uint32_t e = 0;
+                if (k < m) {
+                    e = (m <= 32) ? e_first : row[k];
+                    const int c = cur[cand_idx(e)];
+                    rel = ((((uint32_t)cand_dist(e) << 16) | (uint32_t)k) <= limit) && c != -1;
+                    blk = c < q;
                 }
-                cnt += __popc(mask);
+                const uint32_t relmask = __ballot_sync(0xffffffffu, rel), blkmask = __ballot_sync(0xffffffffu, rel && blk);
+                const int pos = cnt + __popc(relmask & ((1u << lane32) - 1));
+                if (rel && pos < kWatch) wkp[pos] = (uint16_t)cand_idx(e);
+                uint32_t rm = relmask;
+                for (int j = cnt; j < kWatch && rm; ++j) { const int l = __ffs(rm) - 1; if ((blkmask >> l) & 1u) bits |= 1u << j; rm &= rm - 1; }
+                cnt += __popc(relmask);
             }
-            nw.n = cnt > kWatch ? 255 : (uint8_t)cnt;
             if (lane32 == 0) {
-                s_watch[q] = nw;
+                reinterpret_cast<uint32_t*>(&s_watch[q])[3] = (cnt > kWatch ? 255u : (uint32_t)cnt) | (bits << 8);
                 if (t != s_target[q]) { s_target[q] = t; changed = true; }
             }
         }

@@ -36,6 +36,8 @@ struct plvs_orb {
     long long slots_per_frame = 0;
     int sel_cap = 0;                 // keypoint capacity per frame
     DevBuf<uint8_t> d_pyr, d_blur, d_dbg_score, d_color;
+    PyramidMaps maps{};              // TMA tensor maps of the pyramid levels (k_fast_cells); valid when use_tma
+    bool use_tma = false;
     DevBuf<float> d_uright, d_kdepth, d_depth_img, d_keys_un_x;
     DevBuf<plvs_keypoint> d_kp_un;       // mvKeysUn of the last batch (plvs_orb_undistort)
     PinBuf<plvs_keypoint> p_kp_un;
@@ -194,6 +196,28 @@ int setup_geometry(plvs_orb* o, int w, int h, int batch)
         if ((rc = o->d_dbg_score.alloc((size_t)o->frame_stride * B))) return rc;
         PLVS_CUDA(cudaMemsetAsync(o->d_dbg_score.p, 0, (size_t)o->frame_stride * B, o->stream));
     }
+    o->use_tma = false;
+#ifndef PLVS_CUDA_EMU
+    {
+        // one tensor map per level over (x, y, frame); PLVS_ORB_TMA=0 keeps the plain-load staging
+        const char* e = getenv("PLVS_ORB_TMA");
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+        if (!(e && e[0] == '0') && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn && qres == cudaDriverEntryPointSuccess) {
+            bool ok = true;
+            for (int l = 0; l < nl && ok; ++l) {
+                const LevelGeom& g = o->lv[l];
+                const cuuint64_t dims[3] = {(cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)B};
+                const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)o->frame_stride};
+                const cuuint32_t box[3] = {(cuuint32_t)kMaxCell, (cuuint32_t)kMaxCell, 1u}, estr[3] = {1u, 1u, 1u};
+                ok = ((EncodeFn)fn)(&o->maps.level[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, o->d_pyr.p + g.off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            }
+            o->use_tma = ok;
+        }
+    }
+#endif
     if ((rc = o->d_lv.alloc(nl))) return rc;
     if ((rc = o->d_cells.alloc(o->cells.size()))) return rc;
     if ((rc = o->d_tiles.alloc(o->blur_tiles.size()))) return rc;
@@ -378,7 +402,7 @@ static int extract_impl(plvs_orb* o, int batch, const uint8_t* gray, int w, int 
     }
     o->timer.end(st);
     o->timer.begin(PLVS_ORB_K_FAST, st);
-    k_fast_cells<<<dim3((unsigned)o->cells.size(), batch), 256, 0, st>>>(o->d_pyr.p, o->frame_stride, o->d_lv.p, o->d_cells.p, o->d_slots.p,
+    k_fast_cells<<<dim3((unsigned)o->cells.size(), batch), 256, 0, st>>>(o->maps, o->use_tma ? 1 : 0, o->d_pyr.p, o->frame_stride, o->d_lv.p, o->d_cells.p, o->d_slots.p,
                                                                           o->slots_per_frame, o->d_cell_count.p, (int)o->cells.size(),
                                                                           o->prm.ini_th_fast, o->prm.min_th_fast, o->fast_tree, o->debug ? o->d_dbg_score.p : nullptr);
     o->timer.end(st);

@@ -258,16 +258,37 @@ __device__ __forceinline__ int fast_corner_score(const uint8_t* p, int stride, i
     return lo;      // <= 254
 }
 
+// One tensor map per pyramid level: a 3-D view (x, y, frame) of the level inside the batch's pyramid buffer, box = kMaxCell x kMaxCell x 1
+// bytes.  The TMA engine then stages a whole FAST cell (wherever it starts: cells begin at arbitrary x) with ONE instruction issued by one
+// thread -- cp.async.bulk.tensor, SASS UTMALDG -- into a dense kMaxCell-pitch tile, which is exactly the layout the score pass indexes;
+// out-of-image parts of the box arrive as zeros and are never read.  (The CPU execution model has no tensor maps: plain loads there.)
+struct PyramidMaps {
+#ifndef PLVS_CUDA_EMU
+    CUtensorMap level[PLVS_MAX_LEVELS];
+#else
+    int unused;
+#endif
+};
+
+#if !defined(PLVS_CUDA_EMU) && defined(__CUDACC__)
+__device__ __forceinline__ void tma_tile3d_g2s(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+#endif
+
 __global__ void __launch_bounds__(256)
-k_fast_cells(const uint8_t* __restrict__ pyr, long long frame_stride,
+k_fast_cells(const __grid_constant__ PyramidMaps maps, int use_tma, const uint8_t* __restrict__ pyr, long long frame_stride,
              const LevelGeom* __restrict__ levels, const CellDesc* __restrict__ cells,
              uint32_t* __restrict__ slots, long long slots_per_frame,
              int* __restrict__ cell_count, int cells_per_frame, int ini_th, int min_th, int use_tree,
              uint8_t* __restrict__ dbg_score /* optional: score map in pyramid layout (inspection) */)
 {
-    __shared__ uint8_t s_img[kMaxCell * kMaxCell];
+    __shared__ __align__(128) uint8_t s_img[kMaxCell * kMaxCell];
     __shared__ uint8_t s_sc[kMaxCell * kMaxCell];
     __shared__ int s_cnt[2][8];
+    __shared__ __align__(8) unsigned long long s_bar;
     const CellDesc c = cells[blockIdx.x];
     const LevelGeom g = levels[c.level];
     const uint8_t* src = pyr + (long long)blockIdx.y * frame_stride + g.off;
@@ -276,10 +297,25 @@ k_fast_cells(const uint8_t* __restrict__ pyr, long long frame_stride,
     const int iw = w - 6, ih = h - 6;
     uint32_t* out = slots + (long long)blockIdx.y * slots_per_frame + c.slot_off;
     if (iw <= 0 || ih <= 0) { if (tid == 0) cell_count[blockIdx.y * cells_per_frame + blockIdx.x] = 0; return; }
-    for (int i = tid; i < w * h; i += 256) {
-        const int r = i / w, cc = i - r * w;
-        s_img[r * kMaxCell + cc] = src[(long long)(c.y0 + r) * g.pitch + c.x0 + cc];
-        s_sc[r * kMaxCell + cc] = 0;
+#if !defined(PLVS_CUDA_EMU)
+    if (use_tma) {
+        const uint32_t bar = tma_smem_u32(&s_bar);
+        if (tid == 0) tma_mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            tma_mbar_expect_tx(bar, kMaxCell * kMaxCell);            // the whole box is delivered, zeros where it leaves the image
+            tma_tile3d_g2s(tma_smem_u32(s_img), &maps.level[c.level], c.x0, c.y0, (int)blockIdx.y, bar);
+        }
+        for (int i = tid; i < kMaxCell * kMaxCell / 4; i += 256) reinterpret_cast<uint32_t*>(s_sc)[i] = 0u;
+        tma_mbar_wait(bar, 0);
+    } else
+#endif
+    {
+        for (int i = tid; i < w * h; i += 256) {
+            const int r = i / w, cc = i - r * w;
+            s_img[r * kMaxCell + cc] = src[(long long)(c.y0 + r) * g.pitch + c.x0 + cc];
+            s_sc[r * kMaxCell + cc] = 0;
+        }
     }
     __syncthreads();
     const int n = iw * ih;

@@ -257,6 +257,7 @@ template <class T> inline T shfl(uint32_t mask, T v, int src)
 }  // namespace emu
 
 // ---- the CUDA surface the device-only headers use -------------------------------------------------------------------------------
+#define __grid_constant__
 #define __global__
 #define __device__
 #define __host__
