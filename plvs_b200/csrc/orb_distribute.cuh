@@ -3,12 +3,14 @@
 //
 // The reference is a sequential std::list algorithm whose iteration order is observable (it is the order of the
 // returned keypoints).  What it computes, restated so that it parallelises:
-//   * A node = (UL.x, UL.y, UR.x, BR.y) + a contiguous range of a permutation of the candidates; a split is a STABLE
-//     4-way partition of that range (so "first maximum response wins" sees the reference's order inside a node).
+//   * A node = (UL.x, UL.y, UR.x, BR.y) + the set of candidates inside it.  The reference keeps every node's keys in a vector whose order is
+//     preserved by every split (stable), so inside a node the keys are always in candidate-index order and "first maximum response wins"
+//     (:842-862) is simply max over (response, lowest index).  Nothing else reads that order: the candidates need not be moved at all -- each
+//     one only carries the id of the node it is in (node_of[p]); a split counts its candidates per quadrant and relabels them.
 //   * Full sweeps: every node with >1 point splits; children are pushed to the list FRONT, the parent is erased.
 //     With the list stored back-to-front a sweep is  new_list = kept-leaves (old order) ++ children (creation order).
-//     All splits of a sweep are ONE segmented stable partition: two 64-bit prefix scans over the permutation
-//     (quadrant counters packed 2 x 32 bit) + a scatter; child slots come from prefix scans over the node list.
+//     All splits of a sweep are two passes over the candidates: count per (parent, quadrant) -- in shared memory while the sweep has few
+//     parents, where all candidates hit a handful of counters -- and relabel; child slots come from prefix scans over the node list.
 //   * Partial phase (entered when another full sweep would overshoot the quota): the expandable nodes of the last
 //     sweep are sorted by (size, UL.x) with std::sort -- the comparator is not a total order, so ties land wherever
 //     libstdc++'s introsort puts them: one thread runs an exact emulation (stdsort_emul.cuh) -- and split largest
@@ -32,6 +34,7 @@ struct DNode {
     int leaf;          // bNoMore
     int dead;          // erased from the list
     int tag;           // == current split tag while this node is being split
+    int slot;          // index in plist while tagged: its quadrant counters are qcnt[4 * slot .. 4 * slot + 3]
 };
 
 struct DistLevel {                 // per (frame, level) scratch, all device pointers
@@ -51,40 +54,6 @@ struct DistLevel {                 // per (frame, level) scratch, all device poi
 };
 
 // ---- block-wide exclusive scans, in place over global arrays (n may exceed the block size) -------------------
-__device__ inline unsigned long long block_scan_u64(unsigned long long* a, int n, unsigned long long* s_part /*32*/)
-{
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    unsigned long long running = 0;
-    for (int base = 0; base < n; base += blockDim.x) {
-        const int i = base + tid;
-        const unsigned long long v = i < n ? a[i] : 0ull;
-        unsigned long long x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)x, o), hi = __shfl_up_sync(0xffffffffu, (uint32_t)(x >> 32), o);
-            if (lane >= o) x += ((unsigned long long)hi << 32) | lo;
-        }
-        if (lane == 31) s_part[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            unsigned long long p = lane < nw ? s_part[lane] : 0ull;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)p, o), hi = __shfl_up_sync(0xffffffffu, (uint32_t)(p >> 32), o);
-                if (lane >= o) p += ((unsigned long long)hi << 32) | lo;
-            }
-            s_part[lane] = p;
-        }
-        __syncthreads();
-        const unsigned long long wbase = wid ? s_part[wid - 1] : 0ull;
-        if (i < n) a[i] = running + wbase + x - v;
-        const unsigned long long chunk = s_part[nw - 1];
-        __syncthreads();
-        running += chunk;
-    }
-    return running;
-}
-
 __device__ inline int block_scan_i32(int* a, int n, int* s_part /*32*/)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
@@ -128,100 +97,55 @@ __device__ __forceinline__ int quadrant_of_packed(uint2 b, int x, int y)
     return (x < mx ? 0 : 1) + (y < my ? 0 : 2);
 }
 
-__device__ __forceinline__ void child_counts(const DistLevel& D, const DNode& nd, int c[4])
+constexpr int kQcntShared = 1024;          // parents whose quadrant counters live in shared memory (4 ints each)
+
+__device__ __forceinline__ int* qcnt_of(const DistLevel& D) { return reinterpret_cast<int*>(D.scan_a); }     // 4 ints per parent: 2 (n + 1) ints are there, parents hold >= 2 candidates
+
+__device__ __forceinline__ void child_counts(const DistLevel& D, int slot, int c[4])
 {
-    const unsigned long long da = D.scan_a[nd.begin + nd.count] - D.scan_a[nd.begin], db = D.scan_b[nd.begin + nd.count] - D.scan_b[nd.begin];
-    c[0] = (int)(uint32_t)da; c[1] = (int)(da >> 32); c[2] = (int)(uint32_t)db; c[3] = (int)(db >> 32);
+    const int* q = qcnt_of(D) + 4 * slot;
+    c[0] = q[0]; c[1] = q[1]; c[2] = q[2]; c[3] = q[3];
 }
 
-// Exclusive prefix sums of TWO packed-counter arrays at once, in place, over n elements.  Every warp owns one contiguous segment and carries
-// its running sums in registers (32 elements per step, shuffles only); the 32 segment totals are scanned once by warp 0 and added back in a
-// second coalesced pass: two CTA barriers in all, however long the arrays are.
-__device__ inline void block_scan2_u64(unsigned long long* __restrict__ a, unsigned long long* __restrict__ b, int n, unsigned long long* s_part /*64*/)
-{
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    const int seg = ((n + nw - 1) / nw + 31) & ~31;                 // elements per warp, a multiple of 32
-    const int beg = wid * seg, end = min(beg + seg, n);
-    unsigned long long ra = 0, rb = 0;
-    for (int base = beg; base < end; base += 32) {
-        const int i = base + lane;
-        const unsigned long long va = i < end ? a[i] : 0ull, vb = i < end ? b[i] : 0ull;
-        unsigned long long xa = va, xb = vb;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t al = __shfl_up_sync(0xffffffffu, (uint32_t)xa, o), ah = __shfl_up_sync(0xffffffffu, (uint32_t)(xa >> 32), o);
-            const uint32_t bl = __shfl_up_sync(0xffffffffu, (uint32_t)xb, o), bh = __shfl_up_sync(0xffffffffu, (uint32_t)(xb >> 32), o);
-            if (lane >= o) { xa += ((unsigned long long)ah << 32) | al; xb += ((unsigned long long)bh << 32) | bl; }
-        }
-        if (i < end) { a[i] = ra + xa - va; b[i] = rb + xb - vb; }
-        const uint32_t tal = __shfl_sync(0xffffffffu, (uint32_t)xa, 31), tah = __shfl_sync(0xffffffffu, (uint32_t)(xa >> 32), 31);
-        const uint32_t tbl = __shfl_sync(0xffffffffu, (uint32_t)xb, 31), tbh = __shfl_sync(0xffffffffu, (uint32_t)(xb >> 32), 31);
-        ra += ((unsigned long long)tah << 32) | tal; rb += ((unsigned long long)tbh << 32) | tbl;
-    }
-    if (lane == 0) { s_part[wid] = ra; s_part[32 + wid] = rb; }
-    __syncthreads();
-    if (wid == 0) {
-        const unsigned long long va = lane < nw ? s_part[lane] : 0ull, vb = lane < nw ? s_part[32 + lane] : 0ull;
-        unsigned long long xa = va, xb = vb;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t al = __shfl_up_sync(0xffffffffu, (uint32_t)xa, o), ah = __shfl_up_sync(0xffffffffu, (uint32_t)(xa >> 32), o);
-            const uint32_t bl = __shfl_up_sync(0xffffffffu, (uint32_t)xb, o), bh = __shfl_up_sync(0xffffffffu, (uint32_t)(xb >> 32), o);
-            if (lane >= o) { xa += ((unsigned long long)ah << 32) | al; xb += ((unsigned long long)bh << 32) | bl; }
-        }
-        s_part[lane] = xa - va; s_part[32 + lane] = xb - vb;           // exclusive segment bases
-    }
-    __syncthreads();
-    const unsigned long long ba = s_part[wid], bb = s_part[32 + wid];
-    if (wid > 0 && (ba | bb))
-        for (int i = beg + lane; i < end; i += 32) { a[i] += ba; b[i] += bb; }
-    __syncthreads();
-}
-
-// quadrant prefix sums over all permutation slots whose node carries `tag`
-__device__ inline void quadrant_scans(const uint32_t* __restrict__ cand, int n, const DistLevel& D, int cur, int tag, unsigned long long* s_u64)
+// candidates per quadrant of every node that carries `tag` (slots 0..nparents-1) -> qcnt
+__device__ inline void quadrant_counts(const uint32_t* __restrict__ cand, int n, const DistLevel& D, int tag, int nparents, int* s_q /*4 * kQcntShared*/)
 {
     const int tid = threadIdx.x, T = blockDim.x;
-    const int* __restrict__ perm = D.perm[cur]; const int* __restrict__ nof = D.node_of[cur];
+    int* qc = qcnt_of(D);
+    const bool in_smem = nparents <= kQcntShared;
+    int* cnt = in_smem ? s_q : qc;
+    for (int i = tid; i < 4 * nparents; i += T) cnt[i] = 0;
+    __syncthreads();
+    const int* __restrict__ nof = D.node_of[0];
     const DNode* __restrict__ nodes = D.nodes;
-    unsigned long long* __restrict__ sa = D.scan_a; unsigned long long* __restrict__ sb = D.scan_b;
-    // four slots per thread and step: the three dependent loads (owner -> node, slot -> candidate) of the four are in flight together
-    for (int p0 = tid; p0 <= n; p0 += 4 * T) {
-        int k[4], ci[4];
+    for (int p0 = tid; p0 < n; p0 += 4 * T) {            // four candidates per thread and step: their dependent loads are in flight together
+        int k[4]; uint32_t c[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int p = p0 + u * T; k[u] = p < n ? nof[p] : -1; ci[u] = p < n ? perm[p] : 0; }
-        uint2 bd[4]; int tg[4]; uint32_t c[4];
+        for (int u = 0; u < 4; ++u) { const int p = p0 + u * T; k[u] = p < n ? nof[p] : -1; c[u] = p < n ? cand[p] : 0u; }
+        uint2 bd[4]; int tg[4], sl[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            bd[u] = make_uint2(0u, 0u); tg[u] = tag - 1; c[u] = 0u;
-            if (k[u] >= 0) { { const uint32_t* nw32 = reinterpret_cast<const uint32_t*>(&nodes[k[u]]); bd[u] = make_uint2(nw32[0], nw32[1]); }      /* DNode is 44 bytes: 4-byte aligned only */ tg[u] = nodes[k[u]].tag; c[u] = cand[ci[u]]; }
+            bd[u] = make_uint2(0u, 0u); tg[u] = tag - 1; sl[u] = 0;
+            if (k[u] >= 0) { const uint32_t* nw32 = reinterpret_cast<const uint32_t*>(&nodes[k[u]]); bd[u] = make_uint2(nw32[0], nw32[1]); tg[u] = nodes[k[u]].tag; sl[u] = nodes[k[u]].slot; }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int p = p0 + u * T;
-            if (p > n) continue;
-            unsigned long long a = 0, b = 0;
-            if (tg[u] == tag) {
-                const int q = quadrant_of_packed(bd[u], unpack_x(c[u]) - kRoiMargin, unpack_y(c[u]) - kRoiMargin);
-                if (q == 0) a = 1ull; else if (q == 1) a = 1ull << 32; else if (q == 2) b = 1ull; else b = 1ull << 32;
-            }
-            sa[p] = a; sb[p] = b;
-        }
+        for (int u = 0; u < 4; ++u)
+            if (tg[u] == tag) atomicAdd(&cnt[4 * sl[u] + quadrant_of_packed(bd[u], unpack_x(c[u]) - kRoiMargin, unpack_y(c[u]) - kRoiMargin)], 1);
     }
     __syncthreads();
-    block_scan2_u64(D.scan_a, D.scan_b, n + 1, s_u64);
+    if (in_smem) { for (int i = tid; i < 4 * nparents; i += T) qc[i] = s_q[i]; __syncthreads(); }
 }
 
-// Splits plist[0..nparents) (all carrying `tag`, quadrant_scans already done) at once.  Children are created in the
+// Splits plist[0..nparents) (all carrying `tag`, quadrant_counts already done) at once.  Children are created in the
 // order of plist x quadrant (n1,n2,n3,n4), ids from *node_count; their ids go to child_order[], the ones with more
-// than one point to expand_out[] (same order).  perm/node_of are rewritten into the other buffer for ALL slots.
-__device__ inline void split_nodes(const uint32_t* __restrict__ cand, int n, DistLevel& D, int cur, int tag, int nparents, int* node_count,
+// than one point to expand_out[] (same order).  The candidates of the split nodes are relabelled with their child.
+__device__ inline void split_nodes(const uint32_t* __restrict__ cand, int n, DistLevel& D, int tag, int nparents, int* node_count,
                                    int* s_i32, int* total_kids_out, int* total_exp_out, unsigned long long* expand_out, int* child_order)
 {
     const int tid = threadIdx.x, T = blockDim.x;
     for (int j = tid; j < nparents; j += T) {
         int c[4];
-        child_counts(D, D.nodes[D.plist[j]], c);
+        child_counts(D, j, c);
         D.nkids[j] = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
         D.nexp[j] = (c[0] > 1) + (c[1] > 1) + (c[2] > 1) + (c[3] > 1);
     }
@@ -235,62 +159,43 @@ __device__ inline void split_nodes(const uint32_t* __restrict__ cand, int n, Dis
         const int pid = D.plist[j];
         DNode nd = D.nodes[pid];
         int c[4];
-        child_counts(D, nd, c);
+        child_counts(D, j, c);
         const int mx = nd.ulx + ((nd.urx - nd.ulx + 1) >> 1), my = nd.uly + ((nd.bry - nd.uly + 1) >> 1);
-        int k = D.nkids[j], e = D.nexp[j], b = nd.begin;
+        int k = D.nkids[j], e = D.nexp[j];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (c[q] == 0) { nd.kid[q] = -1; continue; }
             DNode ch;
             ch.ulx = (short)((q & 1) ? mx : nd.ulx); ch.urx = (short)((q & 1) ? nd.urx : mx);
             ch.uly = (short)((q & 2) ? my : nd.uly); ch.bry = (short)((q & 2) ? nd.bry : my);
-            ch.begin = b; ch.count = c[q]; ch.leaf = c[q] == 1; ch.dead = 0; ch.tag = 0;
+            ch.begin = 0; ch.count = c[q]; ch.leaf = c[q] == 1; ch.dead = 0; ch.tag = 0; ch.slot = 0;
             ch.kid[0] = ch.kid[1] = ch.kid[2] = ch.kid[3] = -1;
             const int id = base_id + k;
             D.nodes[id] = ch;
             nd.kid[q] = id;
             child_order[k] = id;
             if (c[q] > 1) { expand_out[e] = ((unsigned long long)(((unsigned)min(c[q], (1 << 20) - 1) << 12) | (unsigned)ch.ulx) << 32) | (unsigned)id; ++e; }
-            ++k; b += c[q];
+            ++k;
         }
         nd.dead = 1;
         D.nodes[pid] = nd;
     }
     __syncthreads();
-    const int* __restrict__ perm = D.perm[cur]; const int* __restrict__ nof = D.node_of[cur];
-    int* __restrict__ perm2 = D.perm[cur ^ 1]; int* __restrict__ nof2 = D.node_of[cur ^ 1];
+    int* __restrict__ nof = D.node_of[0];
     const DNode* __restrict__ nodes = D.nodes;
-    const unsigned long long* __restrict__ sa = D.scan_a; const unsigned long long* __restrict__ sb = D.scan_b;
-    for (int p0 = tid; p0 < n; p0 += 4 * T) {           // four slots per thread and step, their dependent loads in flight together
-        int k[4], ci[4];
+    for (int p0 = tid; p0 < n; p0 += 4 * T) {
+        int k[4]; uint32_t c[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int p = p0 + u * T; k[u] = p < n ? nof[p] : -1; ci[u] = p < n ? perm[p] : 0; }
-        uint2 bd[4]; int tg[4], nb[4]; uint32_t c[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            bd[u] = make_uint2(0u, 0u); tg[u] = tag - 1; nb[u] = 0; c[u] = 0u;
-            if (k[u] >= 0) { { const uint32_t* nw32 = reinterpret_cast<const uint32_t*>(&nodes[k[u]]); bd[u] = make_uint2(nw32[0], nw32[1]); }      /* DNode is 44 bytes: 4-byte aligned only */ tg[u] = nodes[k[u]].tag; nb[u] = nodes[k[u]].begin; c[u] = cand[ci[u]]; }
-        }
-        int q[4], cid[4], r[4];
+        for (int u = 0; u < 4; ++u) { const int p = p0 + u * T; k[u] = p < n ? nof[p] : -1; c[u] = p < n ? cand[p] : 0u; }
+        uint2 bd[4]; int tg[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            q[u] = -1; cid[u] = 0; r[u] = 0;
-            if (tg[u] != tag) continue;
-            q[u] = quadrant_of_packed(bd[u], unpack_x(c[u]) - kRoiMargin, unpack_y(c[u]) - kRoiMargin);
-            const int p = p0 + u * T;
-            const unsigned long long sdf = q[u] < 2 ? sa[p] - sa[nb[u]] : sb[p] - sb[nb[u]];
-            r[u] = (q[u] & 1) ? (int)(sdf >> 32) : (int)(uint32_t)sdf;
-            cid[u] = nodes[k[u]].kid[q[u]];
+            bd[u] = make_uint2(0u, 0u); tg[u] = tag - 1;
+            if (k[u] >= 0) { const uint32_t* nw32 = reinterpret_cast<const uint32_t*>(&nodes[k[u]]); bd[u] = make_uint2(nw32[0], nw32[1]); tg[u] = nodes[k[u]].tag; }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) if (q[u] >= 0) r[u] += nodes[cid[u]].begin;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int p = p0 + u * T;
-            if (k[u] < 0) continue;
-            if (q[u] < 0) { perm2[p] = ci[u]; nof2[p] = k[u]; continue; }
-            perm2[r[u]] = ci[u]; nof2[r[u]] = cid[u];
-        }
+        for (int u = 0; u < 4; ++u)
+            if (tg[u] == tag) nof[p0 + u * T] = nodes[k[u]].kid[quadrant_of_packed(bd[u], unpack_x(c[u]) - kRoiMargin, unpack_y(c[u]) - kRoiMargin)];
     }
     __syncthreads();
     if (tid == 0) { *node_count = base_id + total_kids; *total_kids_out = total_kids; *total_exp_out = total_exp; }
@@ -316,8 +221,8 @@ k_distribute(DistArgs A)
 {
     PLVS_DYN_SMEM(unsigned long long, s_sort);           // max quota + 8 elements for the std::sort emulation
     __shared__ int s_i32[32];
-    __shared__ unsigned long long s_u64[64];
     __shared__ int s_nc, s_nk, s_ne, s_live, s_flag;
+    __shared__ int s_q[4 * kQcntShared];
     const int level = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
     const LevelGeom g = A.levels[level];
     const int n = A.cand_count[frame * A.nlevels + level];
@@ -330,30 +235,24 @@ k_distribute(DistArgs A)
     if (n == 0 || nIni == 0 || nIni > D.ncap) { if (tid == 0) *out_count = 0; return; }
     const float hX = (float)(maxX - minX) / (float)nIni;
 
-    // ---- roots (src/ORBextractor.cc:626-664): stable bucketing by root index, one scan per root (nIni is 1-3)
-    int cur = 0;
+    // ---- roots (src/ORBextractor.cc:626-664): every candidate goes to the root its x falls in (nIni is 1-3)
     for (int r = tid; r < nIni; r += T) {
         DNode nd;
         nd.ulx = (short)(int)(hX * (float)r); nd.uly = 0; nd.urx = (short)(int)(hX * (float)(r + 1)); nd.bry = (short)(maxY - minY);
-        nd.begin = 0; nd.count = 0; nd.leaf = 0; nd.dead = 0; nd.tag = 0; nd.kid[0] = nd.kid[1] = nd.kid[2] = nd.kid[3] = -1;
+        nd.begin = 0; nd.count = 0; nd.leaf = 0; nd.dead = 0; nd.tag = 0; nd.slot = 0; nd.kid[0] = nd.kid[1] = nd.kid[2] = nd.kid[3] = -1;
         D.nodes[r] = nd;
     }
+    for (int i = tid; i < nIni; i += T) s_q[i] = 0;
     __syncthreads();
-    {
-        int placed = 0;
-        for (int r = 0; r < nIni; ++r) {
-            for (int p = tid; p <= n; p += T)
-                D.scan_a[p] = (p < n && (int)((float)(unpack_x(cand[p]) - kRoiMargin) / hX) == r) ? 1ull : 0ull;
-            __syncthreads();
-            const int cnt = (int)block_scan_u64(D.scan_a, n + 1, s_u64);
-            __syncthreads();
-            for (int p = tid; p < n; p += T)
-                if ((int)((float)(unpack_x(cand[p]) - kRoiMargin) / hX) == r) { const int pos = placed + (int)D.scan_a[p]; D.perm[cur][pos] = p; D.node_of[cur][pos] = r; }
-            if (tid == 0) { D.nodes[r].begin = placed; D.nodes[r].count = cnt; D.nodes[r].leaf = cnt == 1; }
-            placed += cnt;
-            __syncthreads();
-        }
+    for (int p = tid; p < n; p += T) {
+        const int r = (int)((float)(unpack_x(cand[p]) - kRoiMargin) / hX);
+        const bool in = r >= 0 && r < nIni;
+        D.node_of[0][p] = in ? r : -1;
+        if (in) atomicAdd(&s_q[r], 1);
     }
+    __syncthreads();
+    for (int r = tid; r < nIni; r += T) { D.nodes[r].count = s_q[r]; D.nodes[r].leaf = s_q[r] == 1; }
+    __syncthreads();
     if (tid == 0) {      // list = roots 0..nIni-1 front to back, empty ones erased; stored back-to-front
         int L = 0;
         for (int r = nIni - 1; r >= 0; --r) if (D.nodes[r].count > 0) D.order[0][L++] = r;
@@ -378,12 +277,12 @@ k_distribute(DistArgs A)
         for (int i = tid; i < live; i += T) {
             const int id = ord[i];
             if (D.nodes[id].leaf) ord2[D.flag[i]] = id;                       // kept leaves, old relative order
-            else { D.plist[nparents - 1 - (i - D.flag[i])] = id; D.nodes[id].tag = tag; }   // traversal = storage back -> front
+            else { const int j = nparents - 1 - (i - D.flag[i]); D.plist[j] = id; D.nodes[id].tag = tag; D.nodes[id].slot = j; }   // traversal = storage back -> front
         }
         __syncthreads();
-        quadrant_scans(cand, n, D, cur, tag, s_u64);
-        split_nodes(cand, n, D, cur, tag, nparents, &s_nc, s_i32, &s_nk, &s_ne, D.expand[ecur], ord2 + n_leaves);
-        cur ^= 1; ocur ^= 1;
+        quadrant_counts(cand, n, D, tag, nparents, s_q);
+        split_nodes(cand, n, D, tag, nparents, &s_nc, s_i32, &s_nk, &s_ne, D.expand[ecur], ord2 + n_leaves);
+        ocur ^= 1;
         const int nToExpand = s_ne;
         live = n_leaves + s_nk;
         __syncthreads();
@@ -400,13 +299,13 @@ k_distribute(DistArgs A)
             if (tid == 0) stdsort::sort(s_sort, nexp);
             __syncthreads();
             ++tag;
-            for (int j = tid; j < nexp; j += T) { const int id = (int)(uint32_t)s_sort[nexp - 1 - j]; D.plist[j] = id; D.nodes[id].tag = tag; }   // largest first
+            for (int j = tid; j < nexp; j += T) { const int id = (int)(uint32_t)s_sort[nexp - 1 - j]; D.plist[j] = id; D.nodes[id].tag = tag; D.nodes[id].slot = j; }   // largest first
             __syncthreads();
-            quadrant_scans(cand, n, D, cur, tag, s_u64);
+            quadrant_counts(cand, n, D, tag, nexp, s_q);
             // a split adds (#non-empty children - 1) nodes; the loop stops right after the split that reaches the quota
             for (int j = tid; j < nexp; j += T) {
                 int c[4];
-                child_counts(D, D.nodes[D.plist[j]], c);
+                child_counts(D, j, c);
                 D.flag[j] = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0) - 1;
             }
             __syncthreads();
@@ -422,8 +321,8 @@ k_distribute(DistArgs A)
             __syncthreads();
             if (s_nc + 4 * nproc > D.ncap || live + 4 * nproc > D.ncap) { if (tid == 0) atomicExch(A.error, 1); done = true; break; }
             // children are pushed to the list front == appended to the storage, in processing order
-            split_nodes(cand, n, D, cur, tag, nproc, &s_nc, s_i32, &s_nk, &s_ne, D.expand[ecur ^ 1], ord + live);
-            cur ^= 1; ecur ^= 1;
+            split_nodes(cand, n, D, tag, nproc, &s_nc, s_i32, &s_nk, &s_ne, D.expand[ecur ^ 1], ord + live);
+            ecur ^= 1;
             const int stored = live + s_nk;
             // drop the erased parents so the list stays dense
             int* ord2b = D.order[ocur ^ 1];
@@ -441,18 +340,22 @@ k_distribute(DistArgs A)
         if (done) break;
     }
     __syncthreads();
-    // ---- per surviving node, in list order (storage back -> front), the first maximum response (:842-862)
+    // ---- per surviving node, in list order (storage back -> front), the first maximum response (:842-862): inside a node the reference's keys
+    // are in candidate-index order, so "first maximum" is the largest (response, lowest index) -- one atomicMax per candidate
     {
         const int* ord = D.order[ocur];
-        const int* perm = D.perm[cur];
+        unsigned long long* best = D.expand[0];                 // free by now; indexed by node id
         const int m = min(live, D.ncap);
-        for (int i = tid; i < m; i += T) {
-            const DNode nd = D.nodes[ord[live - 1 - i]];
-            int best = perm[nd.begin];
-            int br = unpack_s(cand[best]);
-            for (int k = 1; k < nd.count; ++k) { const int c = perm[nd.begin + k]; const int r = unpack_s(cand[c]); if (r > br) { best = c; br = r; } }
-            D.stage[i] = cand[best];
+        const int nc = s_nc;
+        for (int i = tid; i < nc; i += T) best[i] = 0ull;
+        __syncthreads();
+        const int* __restrict__ nof = D.node_of[0];
+        for (int p = tid; p < n; p += T) {
+            const int k = nof[p];
+            if (k >= 0) atomicMax(&best[k], ((unsigned long long)(uint32_t)unpack_s(cand[p]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)p));
         }
+        __syncthreads();
+        for (int i = tid; i < m; i += T) D.stage[i] = cand[0xffffffffu - (uint32_t)best[ord[live - 1 - i]]];
         if (tid == 0) *out_count = m;
     }
 }
