@@ -408,7 +408,7 @@ static int extract_impl(plvs_orb* o, int batch, const uint8_t* gray, int w, int 
     o->timer.end(st);
     o->timer.begin(PLVS_ORB_K_COMPACT, st);
     k_compact<<<dim3(nl, batch), 256, 0, st>>>(o->d_slots.p, o->slots_per_frame, o->d_cell_count.p, (int)o->cells.size(), o->d_lv.p, o->d_cells.p, nl,
-                                                o->d_cand.p, o->p_cand.d, o->d_cand_count.p, o->p_cand_count.d);
+                                                o->d_cand.p, o->host_distribute ? o->p_cand.d : nullptr, o->d_cand_count.p, o->p_cand_count.d);      // the host copy of the candidates (22 k x 4 B over PCIe per VGA frame) only feeds the host distributor
     o->timer.end(st);
     launches += 2;
     int64_t ncand = 0, nkp = 0;
@@ -681,6 +681,12 @@ int plvs_orb_candidates(const plvs_orb* o, int frame, int level, int32_t* x, int
     *n_out = n;
     if (n > cap) { set_error("candidate capacity too small"); return PLVS_ECAP; }
     const uint32_t* c = o->p_cand.h + (size_t)frame * o->slots_per_frame + o->lv[level].slot_begin;
+    if (!o->host_distribute && n > 0) {       // inspection call: the candidates stayed on the device, fetch this level now
+        cudaSetDevice(o->device);
+        if (cudaMemcpy(const_cast<uint32_t*>(c), o->d_cand.p + (size_t)frame * o->slots_per_frame + o->lv[level].slot_begin, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("candidate download failed"); return PLVS_ENODEV;
+        }
+    }
     for (int i = 0; i < n; ++i) {
         if (x) x[i] = unpack_x(c[i]);
         if (y) y[i] = unpack_y(c[i]);

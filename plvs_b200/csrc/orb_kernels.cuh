@@ -424,7 +424,7 @@ k_compact(const uint32_t* __restrict__ slots, long long slots_per_frame,
     for (int ci = wid; ci < g.cell_count; ci += 8) {
         const CellDesc c = cells[g.cell_begin + ci];
         const int m = cnt[ci], o = s_off[ci];
-        for (int k = lane; k < m; k += 32) { const uint32_t v = in[c.slot_off + k]; od[o + k] = v; oh[o + k] = v; }
+        for (int k = lane; k < m; k += 32) { const uint32_t v = in[c.slot_off + k]; od[o + k] = v; if (cand_host) oh[o + k] = v; }
     }
 }
 
