@@ -73,18 +73,24 @@ __device__ __forceinline__ void tma_mbar_wait(uint32_t bar, uint32_t parity)
 #endif
 
 // Stream of a handle.  The three kinds of handle run concurrently in a SLAM process (tracking thread, local mapping, dense mapping) and
-// share the SMs.  The matcher's kernels are short and latency-critical (a thread is blocked on every search), the TSDF update is a long
-// persistent kernel that nobody waits for: `rank` 2 = matcher, 1 = extractor, 0 = TSDF maps to CUDA stream priorities (highest for the
-// matcher) unless PLVS_STREAM_PRIORITIES=0.
+// share the SMs.  The matcher's kernels are short and latency-critical (a thread is blocked on every search): highest priority.  The TSDF
+// scan is the longest serial kernel chain of a frame and the extractor's wide grids (thousands of CTAs) are what delays it most, so the TSDF
+// streams come second and the extractor last (`rank` 2 = matcher, 1 = extractor, 0 = TSDF; PLVS_STREAM_ORDER=orb puts the extractor before the
+// TSDF as in round 1, PLVS_STREAM_PRIORITIES=0 gives every stream the same priority).
 inline cudaError_t create_handle_stream(cudaStream_t* st, int rank)
 {
     const char* e = std::getenv("PLVS_STREAM_PRIORITIES");
     if (e && e[0] == '0') return cudaStreamCreateWithFlags(st, cudaStreamNonBlocking);
     int least = 0, greatest = 0;
     if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return cudaStreamCreateWithFlags(st, cudaStreamNonBlocking);
+    const char* o = std::getenv("PLVS_STREAM_ORDER");
+    const bool orb_first = o && o[0] == 'o';
     // numerically lower = higher priority; spread the three ranks over the available range
-    int prio = least;
-    if (rank == 2) prio = greatest; else if (rank == 1) prio = (least + greatest) / 2;
+    const int mid = (least + greatest) / 2;
+    int prio;
+    if (rank == 2) prio = greatest;
+    else if (rank == 1) prio = orb_first ? mid : least;
+    else prio = orb_first ? least : mid;
     return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio);
 }
 
