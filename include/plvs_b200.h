@@ -67,6 +67,10 @@ int plvs_set_profiling(int mask);
 /* bytes the library has moved over the bus since the last reset (process-wide): host->device and device->host, counted at every copy the
  * library issues and at every result a kernel writes straight into mapped host memory */
 int plvs_io_bytes(long long* h2d, long long* d2h, int reset);
+/* Kernels of `device` may read the memory of `peer` over NVLink (cudaDeviceEnablePeerAccess): the two-GPU eye split of a stereo frame
+ * (src/Frame.cc:314-329 extracts the two eyes in two threads) keeps the right eye's pyramid and keypoints on the second GPU and
+ * lets plvs_stereo_match on the first one read them in place. */
+int plvs_enable_peer_access(int device, int peer);
 /* pinned host memory for the e2e path (cudaHostAlloc / cudaFreeHost) */
 int plvs_host_alloc(void** p, size_t bytes);
 int plvs_host_free(void* p);

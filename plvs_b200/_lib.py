@@ -175,6 +175,7 @@ def declare(lib):
     lib.plvs_tsdf_merge_packed_rgba.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.plvs_tsdf_deform.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.plvs_tsdf_integrate_world_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+    lib.plvs_enable_peer_access.argtypes = [C.c_int, C.c_int]
     lib.plvs_io_bytes.argtypes = [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]
     lib.plvs_pipeline_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     for name in ("plvs_match_destroy", "plvs_tsdf_destroy"):

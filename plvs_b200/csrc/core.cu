@@ -38,6 +38,21 @@ int plvs_device_count(void)
     return n;
 }
 
+int plvs_enable_peer_access(int device, int peer)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || peer < 0 || device >= n || peer >= n || device == peer) { plvs::set_error("bad device pair %d -> %d", device, peer); return PLVS_EINVAL; }
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, device, peer) != cudaSuccess || !can) { plvs::set_error("device %d cannot map the memory of device %d", device, peer); return PLVS_ENODEV; }
+    int prev = 0; cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { plvs::set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", device, peer, cudaGetErrorString(e)); return PLVS_ENODEV; }
+    cudaGetLastError();
+    return PLVS_OK;
+}
+
 int plvs_host_alloc(void** p, size_t bytes)
 {
     if (!p) return PLVS_EINVAL;
