@@ -43,7 +43,6 @@ __global__ void __launch_bounds__(256) k_probe(const __grid_constant__ Maps maps
 
 int main(int argc, char** argv)
 {
-    const int only = argc > 1 ? atoi(argv[1]) : -1;
     const int w = 640, h = 480, pitch = 640, B = 3, box = 80;
     const long long fstride = (long long)pitch * h + 256;
     std::vector<uint8_t> img((size_t)fstride * B);
@@ -65,17 +64,13 @@ int main(int argc, char** argv)
     }
     CUtensorMap* gm; cudaMalloc(&gm, sizeof(maps)); cudaMemcpy(gm, &maps, sizeof(maps), cudaMemcpyHostToDevice);
     int* dm; cudaMalloc(&dm, 4);
-    for (int mode = 0; mode < 2; ++mode)
-        for (int t = 0; t < 3; ++t) {
-            if (only >= 0 && mode != only) continue;
-            const int x0 = 16 + 37 * t, y0 = 19 + 41 * t, z = t, level = 5 * t;
-            cudaMemset(dm, 0, 4);
-            if (mode == 0) k_probe<0><<<1, 256>>>(maps, gm, level, d, pitch, fstride, x0, y0, z, box, dm);
-            else k_probe<1><<<1, 256>>>(maps, gm, level, d, pitch, fstride, x0, y0, z, box, dm);
-            cudaError_t s = cudaDeviceSynchronize();
-            int bad = -1; cudaMemcpy(&bad, dm, 4, cudaMemcpyDeviceToHost);
-            printf("mode %d (%s) level %d at (%d,%d,%d): %s, mismatches %d\n", mode, mode ? "global descriptor" : "param descriptor", level, x0, y0, z, cudaGetErrorString(s), bad);
-            if (s != cudaSuccess) { printf("context lost\n"); return 1; }
-        }
+    // one configuration per process (a faulting launch takes the context with it): tma_probe.bin mode x0 y0 z level
+    const int mode = argc > 1 ? atoi(argv[1]) : 1, x0 = argc > 2 ? atoi(argv[2]) : 16, y0 = argc > 3 ? atoi(argv[3]) : 19, z = argc > 4 ? atoi(argv[4]) : 0, level = argc > 5 ? atoi(argv[5]) : 0;
+    cudaMemset(dm, 0, 4);
+    if (mode == 0) k_probe<0><<<1, 256>>>(maps, gm, level, d, pitch, fstride, x0, y0, z, box, dm);
+    else k_probe<1><<<1, 256>>>(maps, gm, level, d, pitch, fstride, x0, y0, z, box, dm);
+    cudaError_t st = cudaDeviceSynchronize();
+    int bad = -1; cudaMemcpy(&bad, dm, 4, cudaMemcpyDeviceToHost);
+    printf("mode %d (%s) level %d at (%d,%d,%d): %s, mismatches %d\n", mode, mode ? "global descriptor" : "param descriptor", level, x0, y0, z, cudaGetErrorString(st), bad);
     return 0;
 }
