@@ -210,7 +210,7 @@ int setup_geometry(plvs_orb* o, int w, int h, int batch)
                 const LevelGeom& g = o->lv[l];
                 const cuuint64_t dims[3] = {(cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)B};
                 const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)o->frame_stride};
-                const cuuint32_t box[3] = {(cuuint32_t)kMaxCell, (cuuint32_t)kMaxCell, 1u}, estr[3] = {1u, 1u, 1u};
+                const cuuint32_t box[3] = {(cuuint32_t)kCellPitch, (cuuint32_t)kMaxCell, 1u}, estr[3] = {1u, 1u, 1u};
                 ok = ((EncodeFn)fn)(&o->maps.level[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, o->d_pyr.p + g.off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
             }
@@ -407,7 +407,7 @@ static int extract_impl(plvs_orb* o, int batch, const uint8_t* gray, int w, int 
                                                                           o->prm.ini_th_fast, o->prm.min_th_fast, o->fast_tree, o->debug ? o->d_dbg_score.p : nullptr);
     o->timer.end(st);
     o->timer.begin(PLVS_ORB_K_COMPACT, st);
-    k_compact<<<dim3(nl, batch), 256, 0, st>>>(o->d_slots.p, o->slots_per_frame, o->d_cell_count.p, (int)o->cells.size(), o->d_lv.p, o->d_cells.p, nl,
+    k_compact<<<dim3(nl, batch), 1024, 0, st>>>(o->d_slots.p, o->slots_per_frame, o->d_cell_count.p, (int)o->cells.size(), o->d_lv.p, o->d_cells.p, nl,
                                                 o->d_cand.p, o->host_distribute ? o->p_cand.d : nullptr, o->d_cand_count.p, o->p_cand_count.d);      // the host copy of the candidates (22 k x 4 B over PCIe per VGA frame) only feeds the host distributor
     o->timer.end(st);
     launches += 2;

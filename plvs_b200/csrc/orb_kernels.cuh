@@ -11,6 +11,7 @@ constexpr int kEdge = 19;           // EDGE_THRESHOLD (src/ORBextractor.cc:106)
 constexpr int kHalfPatch = 15;      // HALF_PATCH_SIZE
 constexpr int kRoiMargin = kEdge - 3;
 constexpr int kMaxCell = 80;        // cell image side is < 70 + 6 (W=35 => wCell < 70)
+constexpr int kCellPitch = 96;      // shared-memory pitch of the cell image: kMaxCell + 15 rounded up to 16 (the TMA box starts at a 16-byte aligned x)
 
 // ---- geometry tables (built once per image size on the host, resident in HBM) ---------------
 struct LevelGeom {
@@ -258,10 +259,12 @@ __device__ __forceinline__ int fast_corner_score(const uint8_t* p, int stride, i
     return lo;      // <= 254
 }
 
-// One tensor map per pyramid level: a 3-D view (x, y, frame) of the level inside the batch's pyramid buffer, box = kMaxCell x kMaxCell x 1
-// bytes.  The TMA engine then stages a whole FAST cell (wherever it starts: cells begin at arbitrary x) with ONE instruction issued by one
-// thread -- cp.async.bulk.tensor, SASS UTMALDG -- into a dense kMaxCell-pitch tile, which is exactly the layout the score pass indexes;
-// out-of-image parts of the box arrive as zeros and are never read.  (The CPU execution model has no tensor maps: plain loads there.)
+// One tensor map per pyramid level: a 3-D view (x, y, frame) of the level inside the batch's pyramid buffer, box = kCellPitch x kMaxCell x 1
+// bytes.  The TMA engine then stages a whole FAST cell with ONE instruction issued by one thread -- cp.async.bulk.tensor, SASS UTMALDG --
+// into a dense kCellPitch-pitch tile.  The innermost start coordinate of a tiled u8 load has to be a multiple of 16 bytes on the B200 (measured
+// with tools/tma_probe.cu: x = 16, 32, 48, 64 load correctly, x = 53 raises "illegal instruction"), and cells begin at arbitrary x: the box
+// starts at x0 & ~15 and the kernel reads the tile `x0 & 15` bytes in.  Out-of-image parts of the box arrive as zeros and are never read.
+// (The CPU execution model has no tensor maps: plain loads there.)
 struct PyramidMaps {
 #ifndef PLVS_CUDA_EMU
     CUtensorMap level[PLVS_MAX_LEVELS];
@@ -285,7 +288,7 @@ k_fast_cells(const __grid_constant__ PyramidMaps maps, int use_tma, const uint8_
              int* __restrict__ cell_count, int cells_per_frame, int ini_th, int min_th, int use_tree,
              uint8_t* __restrict__ dbg_score /* optional: score map in pyramid layout (inspection) */)
 {
-    __shared__ __align__(128) uint8_t s_img[kMaxCell * kMaxCell];
+    __shared__ __align__(128) uint8_t s_img_raw[kCellPitch * kMaxCell];
     __shared__ uint8_t s_sc[kMaxCell * kMaxCell];
     __shared__ int s_cnt[2][8];
     __shared__ __align__(8) unsigned long long s_bar;
@@ -297,15 +300,17 @@ k_fast_cells(const __grid_constant__ PyramidMaps maps, int use_tma, const uint8_
     const int iw = w - 6, ih = h - 6;
     uint32_t* out = slots + (long long)blockIdx.y * slots_per_frame + c.slot_off;
     if (iw <= 0 || ih <= 0) { if (tid == 0) cell_count[blockIdx.y * cells_per_frame + blockIdx.x] = 0; return; }
+    uint8_t* s_img = s_img_raw;          // cell pixel (r, cc) at s_img[r * kCellPitch + cc]
 #if !defined(PLVS_CUDA_EMU)
     if (use_tma) {
         const uint32_t bar = tma_smem_u32(&s_bar);
         if (tid == 0) tma_mbar_init(bar, 1);
         __syncthreads();
         if (tid == 0) {
-            tma_mbar_expect_tx(bar, kMaxCell * kMaxCell);            // the whole box is delivered, zeros where it leaves the image
-            tma_tile3d_g2s(tma_smem_u32(s_img), &maps.level[c.level], c.x0, c.y0, (int)blockIdx.y, bar);
+            tma_mbar_expect_tx(bar, kCellPitch * kMaxCell);          // the whole box is delivered, zeros where it leaves the image
+            tma_tile3d_g2s(tma_smem_u32(s_img_raw), &maps.level[c.level], c.x0 & ~15, c.y0, (int)blockIdx.y, bar);
         }
+        s_img = s_img_raw + (c.x0 & 15);
         for (int i = tid; i < kMaxCell * kMaxCell / 4; i += 256) reinterpret_cast<uint32_t*>(s_sc)[i] = 0u;
         tma_mbar_wait(bar, 0);
     } else
@@ -313,7 +318,7 @@ k_fast_cells(const __grid_constant__ PyramidMaps maps, int use_tma, const uint8_
     {
         for (int i = tid; i < w * h; i += 256) {
             const int r = i / w, cc = i - r * w;
-            s_img[r * kMaxCell + cc] = src[(long long)(c.y0 + r) * g.pitch + c.x0 + cc];
+            s_img[r * kCellPitch + cc] = src[(long long)(c.y0 + r) * g.pitch + c.x0 + cc];
             s_sc[r * kMaxCell + cc] = 0;
         }
     }
@@ -321,7 +326,7 @@ k_fast_cells(const __grid_constant__ PyramidMaps maps, int use_tma, const uint8_
     const int n = iw * ih;
     for (int i = tid; i < n; i += 256) {
         const int r = i / iw + 3, cc = i - (r - 3) * iw + 3;
-        s_sc[r * kMaxCell + cc] = (uint8_t)fast_corner_score(&s_img[r * kMaxCell + cc], kMaxCell, min_th, use_tree);
+        s_sc[r * kMaxCell + cc] = (uint8_t)fast_corner_score(&s_img[r * kCellPitch + cc], kCellPitch, min_th, use_tree);
     }
     __syncthreads();
     if (dbg_score) {
@@ -345,7 +350,7 @@ k_fast_cells(const __grid_constant__ PyramidMaps maps, int use_tma, const uint8_
                 s > p[kMaxCell - 1] && s > p[kMaxCell] && s > p[kMaxCell + 1])
                 flag = s >= ini_th ? 2 : 1;
             // reuse the (now dead) image tile as the flag plane
-            s_img[r * kMaxCell + cc] = (uint8_t)flag;
+            s_img[r * kCellPitch + cc] = (uint8_t)flag;
         }
         cnt_lo += __popc(__ballot_sync(0xffffffffu, flag != 0));
         cnt_hi += __popc(__ballot_sync(0xffffffffu, flag == 2));
@@ -363,7 +368,7 @@ k_fast_cells(const __grid_constant__ PyramidMaps maps, int use_tma, const uint8_
         int keep = 0, r = 0, cc = 0;
         if (i < end) {
             r = i / iw + 3; cc = i - (r - 3) * iw + 3;
-            const int flag = s_img[r * kMaxCell + cc];
+            const int flag = s_img[r * kCellPitch + cc];
             keep = sel ? (flag == 2) : (flag != 0);
         }
         const uint32_t m = __ballot_sync(0xffffffffu, keep);
@@ -381,7 +386,7 @@ k_fast_cells(const __grid_constant__ PyramidMaps maps, int use_tma, const uint8_
 // copy of the candidates (cell-row-major, raster inside the cell == vToDistributeKeys order)
 // into a dense array in HBM and, mirrored, into mapped pinned host memory for the distributor.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_compact(const uint32_t* __restrict__ slots, long long slots_per_frame,
           const int* __restrict__ cell_count, int cells_per_frame,
           const LevelGeom* __restrict__ levels, const CellDesc* __restrict__ cells, int nlevels,
@@ -389,13 +394,13 @@ k_compact(const uint32_t* __restrict__ slots, long long slots_per_frame,
           int* __restrict__ cand_count_host)
 {
     __shared__ int s_off[4096 + 1];
-    __shared__ int s_warp[8];
+    __shared__ int s_warp[32];
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom g = levels[level];
     const int* cnt = cell_count + frame * cells_per_frame + g.cell_begin;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, T = blockDim.x, nw = T >> 5;
     int running = 0;
-    for (int base = 0; base < g.cell_count; base += 256) {
+    for (int base = 0; base < g.cell_count; base += T) {
         const int i = base + tid;
         const int v = i < g.cell_count ? cnt[i] : 0;
         int x = v;
@@ -403,12 +408,8 @@ k_compact(const uint32_t* __restrict__ slots, long long slots_per_frame,
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
         if (lane == 31) s_warp[wid] = x;
         __syncthreads();
-        int wbase = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (k < wid) wbase += s_warp[k];
-        int chunk_total = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) chunk_total += s_warp[k];
+        int wbase = 0, chunk_total = 0;
+        for (int k = 0; k < nw; ++k) { const int sv = s_warp[k]; if (k < wid) wbase += sv; chunk_total += sv; }
         if (i < g.cell_count && i < 4096) s_off[i] = running + wbase + x - v;
         running += chunk_total;
         __syncthreads();
@@ -420,8 +421,8 @@ k_compact(const uint32_t* __restrict__ slots, long long slots_per_frame,
     const uint32_t* in = slots + (long long)frame * slots_per_frame;
     uint32_t* od = cand_dev + (long long)frame * slots_per_frame + g.slot_begin;
     uint32_t* oh = cand_host + (long long)frame * slots_per_frame + g.slot_begin;
-    // one warp per cell, lanes over the cell's candidates
-    for (int ci = wid; ci < g.cell_count; ci += 8) {
+    // one warp per cell, lanes over the cell's candidates (32 warps: the level-0 copy is a chain of small dependent loads per cell)
+    for (int ci = wid; ci < g.cell_count; ci += nw) {
         const CellDesc c = cells[g.cell_begin + ci];
         const int m = cnt[ci], o = s_off[ci];
         for (int k = lane; k < m; k += 32) { const uint32_t v = in[c.slot_off + k]; od[o + k] = v; if (cand_host) oh[o + k] = v; }

@@ -36,7 +36,7 @@ inline void guarded_free(void* p)
 }  // namespace fake_cuda
 
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorPeerAccessAlreadyEnabled = 704 };
 typedef struct fake_stream* cudaStream_t;
 typedef struct fake_event* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
@@ -47,6 +47,9 @@ inline const char* cudaGetErrorString(cudaError_t) { return "fake runtime error"
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaErrorInvalidValue; }
 inline cudaError_t cudaMalloc(void** p, size_t bytes)
 {
     *p = fake_cuda::guard_mode() ? fake_cuda::guarded_alloc(bytes) : std::aligned_alloc(256, (bytes + 255) / 256 * 256 + 256);
