@@ -199,12 +199,13 @@ int setup_geometry(plvs_orb* o, int w, int h, int batch)
     o->use_tma = false;
 #ifndef PLVS_CUDA_EMU
     {
-        // one tensor map per level over (x, y, frame); PLVS_ORB_TMA=1 turns the tensor-map staging on (default: plain loads)
+        // one tensor map per level over (x, y, frame): k_fast_cells stages its cells with cp.async.bulk.tensor (profiles/r02_tma_fast.md);
+        // PLVS_ORB_TMA=0 goes back to plain loads
         const char* e = getenv("PLVS_ORB_TMA");
         typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
         void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
-        if (e && e[0] == '1' && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn && qres == cudaDriverEntryPointSuccess) {
+        if (!(e && e[0] == '0') && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn && qres == cudaDriverEntryPointSuccess) {
             bool ok = true;
             for (int l = 0; l < nl && ok; ++l) {
                 const LevelGeom& g = o->lv[l];
