@@ -300,7 +300,7 @@ def kernel_table(lib, hp):
         if ex is not None:
             lib.plvs_orb_kernel_times(ex._h, ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 0)
             om += ms; oc += cnt
-    for i, nme in enumerate(("orb.pyramid", "orb.fast_cells", "orb.compact", "orb.blur", "orb.orient_describe", "orb.distribute")):
+    for i, nme in enumerate(("orb.pyramid", "orb.fast_cells", "orb.compact", "orb.blur", "orb.orient_describe", "orb.distribute", "orb.frame_grid")):
         ktimes[nme] = (float(om[i]), int(oc[i]))
     mm = np.zeros(12, np.float32); mc = np.zeros(12, np.int32)
     for m in (hp.m_track, hp.m_map, hp.m_tri):
@@ -325,7 +325,8 @@ def latency_block(hp, data, f_first, n):
         mono, kp, desc = hp.ex(d.gray[f])
         t1 = time.perf_counter()
         dv = hp.ex.device_result(0)
-        cur = Frame(None, None, d.w, d.h, sf, s2, uright=hp.frames[f].uright, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key))
+        cur = Frame(None, None, d.w, d.h, sf, s2, uright=hp.frames[f].uright, bf=d.K["bf"],
+                    device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key, dv.grid_cell_start, dv.grid_sorted))
         t2 = time.perf_counter()
         n1, a1 = hp.m_track.SearchByProjectionLast(cur, p["ql"], 15.0)
         t3 = time.perf_counter()

@@ -51,6 +51,7 @@ int plvs_set_profiling(int mask);
 #define PLVS_ORB_K_BLUR 3
 #define PLVS_ORB_K_DESCRIBE 4
 #define PLVS_ORB_K_DISTRIBUTE 5
+#define PLVS_ORB_K_GRID 6
 #define PLVS_MATCH_K_GRID 0
 #define PLVS_MATCH_K_CANDIDATES 1
 #define PLVS_MATCH_K_RESOLVE 2
@@ -63,6 +64,7 @@ int plvs_set_profiling(int mask);
 #define PLVS_TSDF_K_INTEGRATE 2
 #define PLVS_TSDF_K_COMMIT 3
 #define PLVS_TSDF_K_MESH 4
+#define PLVS_TSDF_K_BIND 5
 #define PLVS_K_SLOTS 12
 /* bytes the library has moved over the bus since the last reset (process-wide): host->device and device->host, counted at every copy the
  * library issues and at every result a kernel writes straight into mapped host memory */
@@ -151,7 +153,16 @@ typedef struct {
     const plvs_keypoint* keys;   /* device */
     const uint8_t* desc;         /* device, n x 32 */
     uint64_t cache_key;          /* unique per (handle, extract call, frame): pass it on in plvs_frame_view.cache_key */
+    const int32_t* grid_cell_start;   /* device; the frame's feature grid when plvs_orb_set_frame_grid is in effect, else NULL: */
+    const int32_t* grid_sorted;       /* pass both on in plvs_frame_view.grid_cell_start / grid_sorted */
 } plvs_orb_device_view;
+
+/* Frame::AssignFeaturesToGrid (src/Frame.cc:716-746) as the last step of frame construction, where the reference has it (Frame constructor,
+ * src/Frame.cc:598): with bounds set, every extraction also bins the device-resident keypoints of each frame into the 64 x 48 grid
+ * (mnMinX, mnMinY, mnMaxX, mnMaxY, mfGridElementWidthInv, mfGridElementHeightInv: the static members of Frame, src/Frame.cc:444-449,1749-1778)
+ * and plvs_orb_device_result hands the grid out.  Valid when mvKeysUn == mvKeys (no distortion: RGB-D / rectified input); a matcher given
+ * the grid skips its own build.  bounds == NULL turns it off again. */
+int plvs_orb_set_frame_grid(plvs_orb* h, const float bounds[6]);
 int plvs_orb_device_result(const plvs_orb* h, int frame, plvs_orb_device_view* out);
 
 /* Inspection: FAST candidates of (frame, level) of the last batch in the order they enter
@@ -203,6 +214,8 @@ typedef struct {
     uint64_t cache_key;                   /* 0 = none.  Same non-zero key on consecutive searches of one handle = same keypoints:
                                              the feature grid built for the previous search is reused (the reference builds it once
                                              per Frame, src/Frame.cc:598) */
+    const int32_t* grid_cell_start;       /* optional, device (with on_device): the frame's grid as plvs_orb_device_result returned it */
+    const int32_t* grid_sorted;           /* (built at frame construction); both NULL = the matcher builds the grid itself */
 } plvs_frame_view;
 
 #define PLVS_Q_OBS_POSITIVE 1u   /* MapPoint::Observations() > 0 */

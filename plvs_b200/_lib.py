@@ -32,7 +32,8 @@ class OrbStats(C.Structure):
 
 
 class OrbDeviceView(C.Structure):
-    _fields_ = [("n", C.c_int32), ("keys", C.c_void_p), ("desc", C.c_void_p), ("cache_key", C.c_uint64)]
+    _fields_ = [("n", C.c_int32), ("keys", C.c_void_p), ("desc", C.c_void_p), ("cache_key", C.c_uint64),
+                ("grid_cell_start", C.c_void_p), ("grid_sorted", C.c_void_p)]
 
 
 MAX_LEVELS = 16
@@ -43,7 +44,8 @@ class FrameView(C.Structure):
                 ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
                 ("grid_inv_w", C.c_float), ("grid_inv_h", C.c_float),
                 ("scale_factors", C.c_float * MAX_LEVELS), ("level_sigma2", C.c_float * MAX_LEVELS),
-                ("nlevels", C.c_int32), ("bf", C.c_float), ("on_device", C.c_int32), ("cache_key", C.c_uint64)]
+                ("nlevels", C.c_int32), ("bf", C.c_float), ("on_device", C.c_int32), ("cache_key", C.c_uint64),
+                ("grid_cell_start", C.c_void_p), ("grid_sorted", C.c_void_p)]
 
 
 class PyramidView(C.Structure):
@@ -118,6 +120,7 @@ def declare(lib):
                                            C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.plvs_orb_download_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     lib.plvs_orb_device_result.argtypes = [C.c_void_p, C.c_int, C.POINTER(OrbDeviceView)]
+    lib.plvs_orb_set_frame_grid.argtypes = [C.c_void_p, C.c_void_p]
     lib.plvs_orb_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.plvs_orb_last_stats.argtypes = [C.c_void_p, C.POINTER(OrbStats)]
     lib.plvs_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]

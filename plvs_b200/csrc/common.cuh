@@ -156,6 +156,17 @@ struct PinBuf {
     ~PinBuf() { release(); }
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may become resident while its
+// predecessor in the stream still runs; it must not read the predecessor's output before PLVS_GRID_DEP_WAIT().  The predecessor lets it in
+// early with PLVS_GRID_DEP_LAUNCH().  Both are no-ops for a plain launch and on the CPU execution model.
+#if defined(PLVS_CUDA_EMU)
+#define PLVS_GRID_DEP_WAIT() ((void)0)
+#define PLVS_GRID_DEP_LAUNCH() ((void)0)
+#else
+#define PLVS_GRID_DEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define PLVS_GRID_DEP_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#endif
+
 // Optional per-kernel timing with CUDA events on the handle's own stream (bench.py's roofline leg).
 // Off by default: when off, begin()/end() are a load and a branch.
 extern int g_profiling;

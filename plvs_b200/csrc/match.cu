@@ -48,7 +48,9 @@ __device__ __forceinline__ int decide_target(uint32_t k1, uint32_t k2, uint32_t 
 }
 
 // per query, what round 0 of the claim resolution (nobody has claimed anything yet; pre-claimed keypoints are blocked) leaves behind
-struct Round0 { int32_t u1, u2, target, pad; };       // list positions of the best / second-best unblocked candidate (-1: none), chosen keypoint
+struct Round0 { int32_t target; uint16_t w1, w2, nwatch, m; int32_t pad; };   // chosen keypoint (-1: none); the keypoints of the best / second-best unblocked
+                                                                             // candidate (the first watch set, nwatch of them valid); list length min(count, cap)
+static_assert(sizeof(Round0) == 16, "Round0 layout");
 
 template <int MODE>
 __global__ void __launch_bounds__(256)
@@ -62,6 +64,7 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
     // to 32 columns at once, a warp scan turns them into one flat index space, and the warp then walks 32 flat positions per step: the
     // dependent-load chain is cell_start -> sorted -> {keypoint, descriptor} per 32 candidates instead of per column.
     __shared__ int s_beg[8][32], s_excl[8][33];
+    PLVS_GRID_DEP_LAUNCH();                 // the resolve CTA may become resident (and set its tables up) while the windows are walked
     const int w = threadIdx.x >> 5;
     const int q = blockIdx.x * 8 + w;
     const int lane = threadIdx.x & 31;
@@ -148,14 +151,15 @@ k_candidates(ViewDev F, const int* __restrict__ cell_start, const int* __restric
     if (lane == 0) {
         cand_n[q] = count;
         if (max_count && count > cap) atomicMax(max_count, count);
-        Round0 r; r.pad = 0;
-        r.u1 = best1 == 0xffffffffu ? -1 : (int)(best1 & 0xffffu);
-        r.u2 = best2 == 0xffffffffu ? -1 : (int)(best2 & 0xffffu);
+        Round0 r; r.pad = 0; r.w1 = r.w2 = 0; r.nwatch = 0;
+        r.m = (uint16_t)min(count, min(cap, 65535));
         r.target = -1;
         if (count <= cap) {           // otherwise the search is repeated with more room and this record is not used
             __syncwarp(1u);
-            const uint32_t e1 = r.u1 >= 0 ? out[r.u1] : 0u, e2 = r.u2 >= 0 ? out[r.u2] : 0u;
+            const uint32_t e1 = best1 != 0xffffffffu ? out[best1 & 0xffffu] : 0u, e2 = best2 != 0xffffffffu ? out[best2 & 0xffffu] : 0u;
             r.target = decide_target<MODE>(best1, best2, e1, e2, nn_ratio, th_high);
+            if (best1 != 0xffffffffu) { r.w1 = (uint16_t)cand_idx(e1); r.nwatch = 1; }
+            if (MODE == 0 && best2 != 0xffffffffu) { r.w2 = (uint16_t)cand_idx(e2); r.nwatch = 2; }
         }
         round0[q] = r;
     }
@@ -449,7 +453,8 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
 // result: [0] matches, [1] rounds, [2] list walks after round 0, [3] largest raw candidate count if it exceeded `cap`.
 // ---------------------------------------------------------------------------------------------
 constexpr int kWatch = 6;
-struct WatchRec { uint16_t kp[kWatch]; uint8_t n, blocked; uint16_t pad; };      // n == 255: re-evaluate every round
+struct WatchRec { uint16_t kp[kWatch]; uint8_t n, blocked; uint16_t m; };        // n == 255: re-evaluate every round; m: length of the candidate list
+constexpr int kWalkBatch = 4;
 static_assert(sizeof(WatchRec) == 16, "WatchRec layout");
 
 template <int MODE>
@@ -460,7 +465,7 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
 {
     PLVS_DYN_SMEM_ALIGNED(uint32_t, s_dyn, 16);
     __shared__ int s_count, s_hist[HISTO], s_keep[HISTO], s_walks, s_nwalk;
-    const int tid = threadIdx.x, lane32 = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane32 = tid & 31, wid = tid >> 5, nthr = blockDim.x;
     const int INF = 0x7fffffff;
     WatchRec* s_watch = reinterpret_cast<WatchRec*>(s_dyn);                    // nq (16-byte records first: alignment)
     int* tab0 = reinterpret_cast<int*>(s_dyn + 4 * (size_t)nq);               // n
@@ -469,39 +474,38 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
     int* s_wlist = s_target + nq;                                              // nq: queries queued for a re-evaluation this round
     uint8_t* s_obs = reinterpret_cast<uint8_t*>(s_wlist + nq);                 // nq: Observations() > 0
     if (tid == 0) s_walks = 0;
-    for (int i = tid; i < n; i += 1024) { const int v = (claimed_in && claimed_in[i]) ? -1 : INF; tab0[i] = v; tab1[i] = v; }
-    for (int q = tid; q < nq; q += 1024) {
+    for (int i = tid; i < n; i += nthr) { const int v = (claimed_in && claimed_in[i]) ? -1 : INF; tab0[i] = v; tab1[i] = v; }
+    for (int q = tid; q < nq; q += nthr) {
         const uint32_t fl = MODE == 0 ? reinterpret_cast<const plvs_mp_query*>(queries)[q].flags : reinterpret_cast<const plvs_last_query*>(queries)[q].flags;
         s_obs[q] = (fl & PLVS_Q_OBS_POSITIVE) ? 1 : 0;
+    }
+    PLVS_GRID_DEP_WAIT();                   // everything above read the caller's inputs only; from here on: what k_candidates wrote
+    for (int q = tid; q < nq; q += nthr) {
         // round 0: the watch set is the best (and, for the map search, the second-best) candidate that was free; with fewer free candidates
         // than that, ANY candidate coming free would matter -- but at round 0 nothing is blocked except pre-claims, which never come free
         const Round0 r = round0[q];
         s_target[q] = r.target;
-        WatchRec w; w.n = 0; w.blocked = 0; w.pad = 0;
+        WatchRec w; w.blocked = 0; w.n = (uint8_t)r.nwatch; w.m = r.m;
 #pragma unroll
         for (int j = 0; j < kWatch; ++j) w.kp[j] = 0;
-        const uint32_t* row = cand + (size_t)q * cap;
-        if (r.u1 >= 0) w.kp[w.n++] = (uint16_t)cand_idx(row[r.u1]);
-        if (MODE == 0 && r.u2 >= 0) w.kp[w.n++] = (uint16_t)cand_idx(row[r.u2]);
+        w.kp[0] = r.w1; w.kp[1] = r.w2;
         s_watch[q] = w;
     }
     __syncthreads();
 
-    int* cur = tab0; int* nxt = tab1;
+    // A round: (B) claim table of the current targets -- lowest query with Observations() > 0 per keypoint, -1 marks a pre-claimed keypoint --
+    // into the clean table; (C) every query compares its watch set with it and queues up if something it depends on changed, while the table of
+    // the previous round is wiped for the next one; (D) the queued queries are evaluated again.  Three CTA barriers per round.
+    int* cur = tab0; int* nxt = tab1;       // both clean (pre-claims only) here
     int rounds = 1;                         // round 0 ran inside k_candidates
     for (;;) {
-        // claim table of the current targets: lowest query (with Observations() > 0) per keypoint; -1 marks a pre-claimed keypoint
-        for (int i = tid; i < n; i += 1024) nxt[i] = cur[i] < 0 ? -1 : INF;
-        __syncthreads();
-        for (int q = tid; q < nq; q += 1024) { const int t = s_target[q]; if (t >= 0 && s_obs[q]) atomicMin(&nxt[t], q); }
+        for (int q = tid; q < nq; q += nthr) { const int t = s_target[q]; if (t >= 0 && s_obs[q]) atomicMin(&nxt[t], q); }
+        if (tid == 0) s_nwalk = 0;
         __syncthreads();
         { int* t = cur; cur = nxt; nxt = t; }
         bool changed = false;
-        // (1) which queries saw something change among the candidates they depend on?  They queue up for a re-evaluation.
-        if (tid == 0) s_nwalk = 0;
-        __syncthreads();
-        for (int q = tid; q < nq; q += 1024) {
-            const uint4 raw = reinterpret_cast<const uint4*>(s_watch)[q];                 // kp[0..5] | n, blocked, pad
+        for (int q = tid; q < nq; q += nthr) {
+            const uint4 raw = reinterpret_cast<const uint4*>(s_watch)[q];                 // kp[0..5] | n, blocked, m
             const uint32_t wn = raw.w & 0xffu, wb = (raw.w >> 8) & 0xffu;
             bool walk = wn == 255u;
             if (!walk) {
@@ -512,51 +516,68 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
             }
             if (walk) s_wlist[atomicAdd(&s_nwalk, 1)] = q;          // order irrelevant: an evaluation reads `cur` and writes its own records only
         }
+        for (int i = tid; i < n; i += nthr) nxt[i] = nxt[i] < 0 ? -1 : INF;
         __syncthreads();
-        // (2) one warp per queued query: the lanes take the list entries (rows are read from L2, coalesced), warp reductions give the best and
-        // second-best free candidate, a ballot the new watch set
+        // (D) one warp per queued query: the lanes take the list entries (rows are read from L2, coalesced; the first 32 entries of up to four
+        // queries are requested before the first one is evaluated, so a warp pays the L2 round trip once per four queries), warp reductions
+        // give the best and second-best free candidate, ballots the new watch set
         const int nwalk = s_nwalk;
-        for (int i = wid; i < nwalk; i += 32) {
-            const int q = s_wlist[i];
-            const int m = min(cand_n[q], cap);
-            const uint32_t* row = cand + (size_t)q * cap;
-            uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu, e_first = 0u;
-            for (int k0 = 0; k0 < m; k0 += 32) {
-                const int k = k0 + lane32;
-                uint32_t key = 0xffffffffu;
-                if (k < m) { const uint32_t e = row[k]; if (k0 == 0) e_first = e; if (!(cur[cand_idx(e)] < q)) key = ((uint32_t)cand_dist(e) << 16) | (uint32_t)k; }
-                const uint32_t s1 = __reduce_min_sync(0xffffffffu, key);
-                const uint32_t s2 = __reduce_min_sync(0xffffffffu, key == s1 ? 0xffffffffu : key);
-                const uint32_t lo = min(k1, s1), hi = max(k1, s1);
-                k2 = min(hi, min(k2, s2));
-                k1 = lo;
+        for (int i0 = wid; i0 < nwalk; i0 += (nthr >> 5) * kWalkBatch) {
+            int qv[kWalkBatch], mv[kWalkBatch]; uint32_t ev[kWalkBatch];
+#pragma unroll
+            for (int u = 0; u < kWalkBatch; ++u) {
+                const int i = i0 + u * (nthr >> 5);
+                qv[u] = i < nwalk ? s_wlist[i] : -1;
+                mv[u] = qv[u] >= 0 ? (int)s_watch[qv[u]].m : 0;
+                ev[u] = lane32 < mv[u] ? cand[(size_t)qv[u] * cap + lane32] : 0u;
             }
-            const uint32_t e1 = k1 != 0xffffffffu ? row[k1 & 0xffffu] : 0u, e2 = k2 != 0xffffffffu ? row[k2 & 0xffffu] : 0u;
-            const int t = decide_target<MODE>(k1, k2, e1, e2, nn_ratio, th_high);
-            // new watch set: every candidate up to the last one the decision read, except pre-claimed ones, with the state just seen.  The
-            // lanes write their keypoint straight into the shared-memory record at their rank; lane 0 derives the blocked bits from two ballots.
-            const uint32_t limit = MODE == 0 ? k2 : k1;              // 0xffffffff (not enough free candidates): the whole list matters
-            uint16_t* wkp = reinterpret_cast<uint16_t*>(&s_watch[q]);
-            int cnt = 0; uint32_t bits = 0;
-            for (int k0 = 0; k0 < m && cnt <= kWatch; k0 += 32) {
-                const int k = k0 + lane32;
-                bool rel = false, blk = false; uint32_t e = 0;
-                if (k < m) {
-                    e = (m <= 32) ? e_first : row[k];
-                    const int c = cur[cand_idx(e)];
-                    rel = ((((uint32_t)cand_dist(e) << 16) | (uint32_t)k) <= limit) && c != -1;
-                    blk = c < q;
+#pragma unroll
+            for (int u = 0; u < kWalkBatch; ++u) {
+                const int q = qv[u], m = mv[u];
+                if (q < 0) break;                      // warp-uniform
+                const uint32_t e_first = ev[u];
+                const uint32_t* row = cand + (size_t)q * cap;
+                uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+                for (int k0 = 0; k0 < m; k0 += 32) {
+                    const int k = k0 + lane32;
+                    uint32_t key = 0xffffffffu;
+                    if (k < m) { const uint32_t e = k0 == 0 ? e_first : row[k]; if (!(cur[cand_idx(e)] < q)) key = ((uint32_t)cand_dist(e) << 16) | (uint32_t)k; }
+                    const uint32_t s1 = __reduce_min_sync(0xffffffffu, key);
+                    const uint32_t s2 = __reduce_min_sync(0xffffffffu, key == s1 ? 0xffffffffu : key);
+                    const uint32_t lo = min(k1, s1), hi = max(k1, s1);
+                    k2 = min(hi, min(k2, s2));
+                    k1 = lo;
                 }
-                const uint32_t relmask = __ballot_sync(0xffffffffu, rel), blkmask = __ballot_sync(0xffffffffu, rel && blk);
-                const int pos = cnt + __popc(relmask & ((1u << lane32) - 1));
-                if (rel && pos < kWatch) wkp[pos] = (uint16_t)cand_idx(e);
-                uint32_t rm = relmask;
-                for (int j = cnt; j < kWatch && rm; ++j) { const int l = __ffs(rm) - 1; if ((blkmask >> l) & 1u) bits |= 1u << j; rm &= rm - 1; }
-                cnt += __popc(relmask);
-            }
-            if (lane32 == 0) {
-                reinterpret_cast<uint32_t*>(&s_watch[q])[3] = (cnt > kWatch ? 255u : (uint32_t)cnt) | (bits << 8);
-                if (t != s_target[q]) { s_target[q] = t; changed = true; }
+                // the two winners' records: out of a lane's register when they sit in the first 32 entries (warp-uniform positions)
+                const uint32_t p1 = k1 & 0xffffu, p2 = k2 & 0xffffu;
+                const uint32_t f1 = __shfl_sync(0xffffffffu, e_first, (int)(p1 & 31u)), f2 = __shfl_sync(0xffffffffu, e_first, (int)(p2 & 31u));
+                const uint32_t e1 = k1 != 0xffffffffu ? (p1 < 32u ? f1 : row[p1]) : 0u, e2 = k2 != 0xffffffffu ? (p2 < 32u ? f2 : row[p2]) : 0u;
+                const int t = decide_target<MODE>(k1, k2, e1, e2, nn_ratio, th_high);
+                // new watch set: every candidate up to the last one the decision read, except pre-claimed ones, with the state just seen.  The
+                // lanes write their keypoint straight into the shared-memory record at their rank; lane 0 derives the blocked bits from two ballots.
+                const uint32_t limit = MODE == 0 ? k2 : k1;              // 0xffffffff (not enough free candidates): the whole list matters
+                uint16_t* wkp = reinterpret_cast<uint16_t*>(&s_watch[q]);
+                int cnt = 0; uint32_t bits = 0;
+                for (int k0 = 0; k0 < m && cnt <= kWatch; k0 += 32) {
+                    const int k = k0 + lane32;
+                    bool rel = false, blk = false; uint32_t e = 0;
+                    if (k < m) {
+                        e = k0 == 0 ? e_first : row[k];
+                        const int c = cur[cand_idx(e)];
+                        rel = ((((uint32_t)cand_dist(e) << 16) | (uint32_t)k) <= limit) && c != -1;
+                        blk = c < q;
+                    }
+                    const uint32_t relmask = __ballot_sync(0xffffffffu, rel), blkmask = __ballot_sync(0xffffffffu, rel && blk);
+                    const int pos = cnt + __popc(relmask & ((1u << lane32) - 1));
+                    if (rel && pos < kWatch) wkp[pos] = (uint16_t)cand_idx(e);
+                    uint32_t rm = relmask;
+                    for (int j = cnt; j < kWatch && rm; ++j) { const int l = __ffs(rm) - 1; if ((blkmask >> l) & 1u) bits |= 1u << j; rm &= rm - 1; }
+                    cnt += __popc(relmask);
+                }
+                if (lane32 == 0) {
+                    reinterpret_cast<uint32_t*>(&s_watch[q])[3] = (cnt > kWatch ? 255u : (uint32_t)cnt) | (bits << 8) | ((uint32_t)m << 16);
+                    if (t != s_target[q]) { s_target[q] = t; changed = true; }
+                }
             }
         }
         if (tid == 0) s_walks += nwalk;
@@ -566,12 +587,12 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
     // final holders: the last (highest) query that wrote each keypoint
     int* assign = nxt;
     __syncthreads();
-    for (int i = tid; i < n; i += 1024) assign[i] = -1;
+    for (int i = tid; i < n; i += nthr) assign[i] = -1;
     if (tid == 0) s_count = 0;
     if (tid < HISTO) { s_hist[tid] = 0; s_keep[tid] = 1; }
     __syncthreads();
     int local = 0;
-    for (int q = tid; q < nq; q += 1024) {
+    for (int q = tid; q < nq; q += nthr) {
         const int t = s_target[q];
         if (t < 0) continue;
         ++local;
@@ -602,7 +623,7 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
         }
         __syncthreads();
         int dropped = 0;
-        for (int q = tid; q < nq; q += 1024) {
+        for (int q = tid; q < nq; q += nthr) {
             const int t = s_target[q];
             if (t < 0) continue;
             const float factor = HISTO / 360.0f;
@@ -615,7 +636,7 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
         atomicSub(&s_count, dropped);
     }
     __syncthreads();
-    for (int i = tid; i < n; i += 1024) assign_out[i] = assign[i];
+    for (int i = tid; i < n; i += nthr) assign_out[i] = assign[i];
     if (tid == 0) { result[0] = s_count; result[1] = rounds; result[2] = s_walks; result[3] = *max_count; *max_count = 0; }
 }
 
@@ -1008,6 +1029,8 @@ struct plvs_match {
     int cap = 128;
     DevBuf<uint8_t> d_stage; PinBuf<uint8_t> p_stage;     // one packed H2D per projection search
     bool state_zeroed = false;
+    bool use_pdl = true;                                 // k_resolve_cta as a programmatic dependent launch behind k_candidates (PLVS_MATCH_PDL=0: plain)
+    int resolve_threads = 512;                           // CTA size of k_resolve_cta (PLVS_MATCH_RESOLVE_THREADS: 256 / 512 / 1024)
     DevBuf<Round0> d_round0;                              // per query: what round 0 of the claim resolution leaves (written by k_candidates)
     int last_walks = 0;                                   // list re-evaluations of the last search after round 0 (statistics)
     int last_rounds = 0, last_launches = 0;
@@ -1104,7 +1127,10 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         return rc;
     if (!h->state_zeroed) { PLVS_CUDA(cudaMemsetAsync(h->d_state.p, 0, 16 * sizeof(int), st)); h->state_zeroed = true; }
     int launches = 0;
-    if (!(F->cache_key != 0 && F->cache_key == h->grid_key && n == h->grid_n)) {
+    // the frame's grid: handed in with the view (built at frame construction, plvs_orb_set_frame_grid), else built here once per cache_key
+    const int* g_start = h->d_cell_start.p; const int* g_sorted = h->d_sorted.p;
+    if (F->on_device && F->grid_cell_start && F->grid_sorted) { g_start = F->grid_cell_start; g_sorted = F->grid_sorted; }
+    else if (!(F->cache_key != 0 && F->cache_key == h->grid_key && n == h->grid_n)) {
         h->timer.begin(PLVS_MATCH_K_GRID, st);
         k_build_grid<<<1, 1024, 0, st>>>(V.keys, n, V.gp, h->d_cell_start.p, h->d_sorted.p, h->d_kp_cell.p);
         h->timer.end(st);
@@ -1121,13 +1147,23 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
     for (;;) {
         if ((rc = h->d_cand.alloc((size_t)nq * h->cap))) return rc;
         h->timer.begin(PLVS_MATCH_K_CANDIDATES, st);
-        k_candidates<MODE><<<div_up(nq, 8), 256, 0, st>>>(V, h->d_cell_start.p, h->d_sorted.p, dq, nq, th, far_points, th_far, forward, backward,
+        k_candidates<MODE><<<div_up(nq, 8), 256, 0, st>>>(V, g_start, g_sorted, dq, nq, th, far_points, th_far, forward, backward,
                                                            h->d_cand.p, h->d_cand_n.p, h->cap, h->d_state.p + 8, d_claimed, nn_ratio, th_high, h->d_round0.p);
         h->timer.end(st);
         ++launches;
         h->timer.begin(PLVS_MATCH_K_RESOLVE, st);
         if (one_cta) {
-            k_resolve_cta<MODE><<<1, 1024, cta_smem, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, dq, nq, V.keys, n, d_claimed, nn_ratio, check_ori, th_high,
+#ifndef PLVS_CUDA_EMU
+            if (h->use_pdl && !h->timer.on(PLVS_MATCH_K_RESOLVE)) {
+                // programmatic dependent launch: the CTA is scheduled while k_candidates still runs and waits at PLVS_GRID_DEP_WAIT()
+                cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(1); cfg.blockDim = dim3((unsigned)h->resolve_threads); cfg.dynamicSmemBytes = cta_smem; cfg.stream = st;
+                cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                PLVS_CUDA(cudaLaunchKernelEx(&cfg, k_resolve_cta<MODE>, (const uint32_t*)h->d_cand.p, (const int*)h->d_cand_n.p, h->cap, (const void*)dq, nq, (const plvs_keypoint*)V.keys, n,
+                                             (const uint8_t*)d_claimed, nn_ratio, check_ori, th_high, (const Round0*)h->d_round0.p, (int32_t*)h->p_assign.d, (int*)h->p_result.d, (int*)(h->d_state.p + 8)));
+            } else
+#endif
+            k_resolve_cta<MODE><<<1, h->resolve_threads, cta_smem, st>>>(h->d_cand.p, h->d_cand_n.p, h->cap, dq, nq, V.keys, n, d_claimed, nn_ratio, check_ori, th_high,
                                                           h->d_round0.p, h->p_assign.d, h->p_result.d, h->d_state.p + 8);
         } else {
             if ((rc = h->d_claim_a.alloc((size_t)3 * n)) || (rc = h->d_target.alloc(nq)) || (rc = h->d_assign.alloc(n))) return rc;
@@ -1212,6 +1248,8 @@ int plvs_match_create(int device, plvs_match** out)
     PLVS_CUDA(cudaFuncSetAttribute(k_resolve<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmemMax));
     plvs_match* h = new plvs_match();
     h->device = device; h->timer.component = 2;
+    if (const char* e = std::getenv("PLVS_MATCH_PDL")) h->use_pdl = e[0] != '0';
+    if (const char* e = std::getenv("PLVS_MATCH_RESOLVE_THREADS")) { const int v = std::atoi(e); if (v == 256 || v == 512 || v == 1024) h->resolve_threads = v; }
     { cudaError_t e = create_handle_stream(&h->stream, 2);
       if (e != cudaSuccess) { delete h; set_error("stream creation failed: %s", cudaGetErrorString(e)); return PLVS_ENODEV; } }
     *out = h;

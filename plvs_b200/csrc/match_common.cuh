@@ -27,9 +27,8 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
 // indices appended in keypoint order.  One CTA: histogram, scan, unordered scatter, per-cell insertion sort
 // (cells hold a handful of keypoints), so every cell list is ascending == the reference's push_back order.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_build_grid(const plvs_keypoint* __restrict__ keys, int n, GridParams gp, int* __restrict__ cell_start /*GRID_CELLS+1*/,
-             int* __restrict__ sorted /*n*/, int* __restrict__ kp_cell /*n*/)
+__device__ __forceinline__ void build_grid_cta(const plvs_keypoint* __restrict__ keys, int n, GridParams gp, int* __restrict__ cell_start /*GRID_CELLS+1*/,
+                                               int* __restrict__ sorted /*n*/, int* __restrict__ kp_cell /*n*/)
 {
     __shared__ int s_cnt[GRID_CELLS + 1];
     __shared__ int s_part[32];
@@ -81,6 +80,23 @@ k_build_grid(const plvs_keypoint* __restrict__ keys, int n, GridParams gp, int* 
             sorted[j + 1] = v;
         }
     }
+}
+
+__global__ void __launch_bounds__(1024)
+k_build_grid(const plvs_keypoint* __restrict__ keys, int n, GridParams gp, int* __restrict__ cell_start, int* __restrict__ sorted, int* __restrict__ kp_cell)
+{
+    build_grid_cta(keys, n, gp, cell_start, sorted, kp_cell);
+}
+
+// The same at frame construction (the reference calls AssignFeaturesToGrid at the end of the Frame constructor, src/Frame.cc:598): one CTA per
+// frame of an extractor batch, over the keypoints the extractor left in HBM.  count_of[b * count_stride] = number of keypoints of frame b.
+__global__ void __launch_bounds__(1024)
+k_build_grid_batch(const plvs_keypoint* __restrict__ keys, int key_stride, const int* __restrict__ count_of, int count_stride, GridParams gp,
+                   int* __restrict__ cell_start /*B x (GRID_CELLS+1)*/, int* __restrict__ sorted /*B x key_stride*/, int* __restrict__ kp_cell /*B x key_stride*/)
+{
+    const int b = blockIdx.x;
+    build_grid_cta(keys + (size_t)b * key_stride, min(count_of[(size_t)b * count_stride], key_stride), gp, cell_start + (size_t)b * (GRID_CELLS + 1),
+                   sorted + (size_t)b * key_stride, kp_cell + (size_t)b * key_stride);
 }
 
 // Frame::GetFeaturesInArea cell window (src/Frame.cc:1239-1261); returns false if empty

@@ -10,6 +10,9 @@
 #include "orb_distribute.hpp"
 #include "orb_kernels.cuh"
 #include "orb_distribute.cuh"
+namespace framegrid {
+#include "match_common.cuh"
+}
 
 using namespace plvs;
 using namespace plvs::orb;
@@ -59,6 +62,9 @@ struct plvs_orb {
     DevBuf<int> d_cell_count, d_cand_count;
     DevBuf<plvs_keypoint> d_kp;
     DevBuf<uint8_t> d_desc;
+    bool grid_on = false;            // plvs_orb_set_frame_grid: AssignFeaturesToGrid at frame construction
+    framegrid::GridParams grid_gp{};
+    DevBuf<int> d_grid_start, d_grid_sorted, d_grid_cell;
     PinBuf<uint32_t> p_cand;         // compacted candidates (device writes, host reads)
     PinBuf<int> p_cand_count;
     PinBuf<uint32_t> p_sel;          // selected keypoints (host writes, device reads)
@@ -434,6 +440,14 @@ static int extract_impl(plvs_orb* o, int batch, const uint8_t* gray, int w, int 
                                                                               o->sel_cap, o->d_kp.p, o->d_desc.p, o->p_kp.d, o->p_desc.d);
         o->timer.end(st);
         launches += 4;
+        if (o->grid_on) {
+            if ((rc = o->d_grid_start.alloc((size_t)(framegrid::GRID_CELLS + 1) * o->batch_cap)) || (rc = o->d_grid_sorted.alloc((size_t)o->sel_cap * o->batch_cap)) ||
+                (rc = o->d_grid_cell.alloc((size_t)o->sel_cap * o->batch_cap))) return rc;
+            o->timer.begin(PLVS_ORB_K_GRID, st);
+            framegrid::k_build_grid_batch<<<batch, 1024, 0, st>>>(o->d_kp.p, o->sel_cap, o->d_sel_off.p + nl, nl + 1, o->grid_gp, o->d_grid_start.p, o->d_grid_sorted.p, o->d_grid_cell.p);
+            o->timer.end(st);
+            ++launches;
+        }
         PLVS_CUDA(cudaGetLastError());
         tp0 = tp1 = tp2 = std::chrono::steady_clock::now();
         PLVS_CUDA(cudaStreamSynchronize(st));
@@ -671,6 +685,19 @@ int plvs_orb_device_result(const plvs_orb* o, int frame, plvs_orb_device_view* o
     out->keys = o->d_kp.p + (size_t)frame * o->sel_cap;
     out->desc = o->d_desc.p + (size_t)frame * o->sel_cap * 32;
     out->cache_key = (o->serial << 44) | ((o->epoch & 0xfffffffffull) << 8) | (uint64_t)(frame & 0xff);
+    const bool grid = o->grid_on && !o->host_distribute && o->d_grid_start.p;
+    out->grid_cell_start = grid ? o->d_grid_start.p + (size_t)frame * (framegrid::GRID_CELLS + 1) : nullptr;
+    out->grid_sorted = grid ? o->d_grid_sorted.p + (size_t)frame * o->sel_cap : nullptr;
+    return PLVS_OK;
+}
+
+int plvs_orb_set_frame_grid(plvs_orb* o, const float bounds[6])
+{
+    if (!o) { set_error("null handle"); return PLVS_EINVAL; }
+    if (!bounds) { o->grid_on = false; return PLVS_OK; }
+    if (!(bounds[2] > bounds[0]) || !(bounds[3] > bounds[1]) || !(bounds[4] > 0.f) || !(bounds[5] > 0.f)) { set_error("bad grid bounds"); return PLVS_EINVAL; }
+    o->grid_gp = framegrid::GridParams{bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5]};
+    o->grid_on = true;
     return PLVS_OK;
 }
 

@@ -93,6 +93,7 @@ extern "C" int plvs_pipeline_run(plvs_orb* const ex[2], plvs_match* m_track, plv
             if (rc) { fail(rc, "plvs_orb_device_result"); break; }
             plvs_frame_view cur = job->view_template;      // bounds, grid, scale factors, bf of the stream's frames
             cur.n = dv.n; cur.keys = dv.keys; cur.desc = dv.desc; cur.cache_key = dv.cache_key;
+            cur.grid_cell_start = dv.grid_cell_start; cur.grid_sorted = dv.grid_sorted;      // built at frame construction when the caller turned it on
             cur.uright = fr.uright; cur.on_device = fr.uright ? (PLVS_VIEW_ON_DEVICE | PLVS_VIEW_URIGHT_ON_HOST) : PLVS_VIEW_ON_DEVICE;
             a1.assign((size_t)std::max(dv.n, 1), -1); a2.assign((size_t)std::max(dv.n, 1), -1); claimed.assign((size_t)std::max(dv.n, 1), 0);
             int n1 = 0, n2 = 0;

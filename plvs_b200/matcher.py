@@ -27,7 +27,7 @@ class Frame:
         self.desc = np.ascontiguousarray(desc, np.uint8) if desc is not None else None
         self.uright = None if uright is None else np.ascontiguousarray(uright, np.float32)
         self.n = len(self.keys) if device_ptrs is None else device_ptrs[0]
-        self.device_ptrs = device_ptrs          # (n, keys_ptr, desc_ptr, uright_ptr|0[, cache_key])
+        self.device_ptrs = device_ptrs          # (n, keys_ptr, desc_ptr, uright_ptr|0[, cache_key[, grid_cell_start, grid_sorted]])
         self.scale_factors = np.asarray(scale_factors, np.float32)
         self.level_sigma2 = np.asarray(level_sigma2 if level_sigma2 is not None else self.scale_factors ** 2, np.float32)
         # Frame::ComputeImageBounds without distortion (src/Frame.cc:1770-1776)
@@ -46,6 +46,8 @@ class Frame:
                 v.uright = self.uright.ctypes.data
                 v.on_device = 1 | 2
             v.cache_key = self.device_ptrs[4] if len(self.device_ptrs) > 4 else 0
+            if len(self.device_ptrs) > 6 and self.device_ptrs[5] and self.device_ptrs[6]:      # grid built at frame construction
+                v.grid_cell_start, v.grid_sorted = self.device_ptrs[5], self.device_ptrs[6]
         else:
             v.keys = self.keys.ctypes.data
             v.desc = self.desc.ctypes.data
@@ -96,6 +98,12 @@ class ORBmatcher:
             self._h = None
 
     __del__ = close
+
+    def last_stats(self):
+        """(rounds of the claim resolution, kernel launches) of the last projection search on this handle"""
+        r, k = C.c_int(), C.c_int()
+        _lib.check(self._lib.plvs_match_last_stats(self._h, C.byref(r), C.byref(k)), "plvs_match_last_stats")
+        return r.value, k.value
 
     @staticmethod
     def DescriptorDistance(a, b):

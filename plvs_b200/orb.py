@@ -139,6 +139,18 @@ class ORBextractor:
         _lib.check(self._lib.plvs_orb_pyramid_view(self._h, frame, int(blurred), C.byref(v)), "plvs_orb_pyramid_view")
         return v
 
+    def set_frame_grid(self, width=None, height=None, bounds=None):
+        """Frame::AssignFeaturesToGrid at frame construction (src/Frame.cc:598,716): from now on every extraction also bins the keypoints of
+        each frame into the 64 x 48 grid over `bounds` = (mnMinX, mnMinY, mnMaxX, mnMaxY) (default: the image, i.e. no distortion), and
+        device_result() carries the grid.  set_frame_grid() without arguments turns it off."""
+        if width is None and bounds is None:
+            _lib.check(self._lib.plvs_orb_set_frame_grid(self._h, None), "plvs_orb_set_frame_grid")
+            return
+        x0, y0, x1, y1 = bounds or (0.0, 0.0, float(width), float(height))
+        b = np.array([x0, y0, x1, y1, np.float32(64) / np.float32(np.float32(x1) - np.float32(x0)),
+                      np.float32(48) / np.float32(np.float32(y1) - np.float32(y0))], np.float32)
+        _lib.check(self._lib.plvs_orb_set_frame_grid(self._h, b.ctypes.data_as(C.c_void_p)), "plvs_orb_set_frame_grid")
+
     def device_result(self, frame=0):
         v = _lib.OrbDeviceView()
         _lib.check(self._lib.plvs_orb_device_result(self._h, frame, C.byref(v)), "plvs_orb_device_result")

@@ -73,6 +73,7 @@ class HotPath:
     def __init__(self, data, nfeatures=2000, voxel=0.01, far=5.0, max_blocks=32768, device=0, batch=8, use_color=True):
         self.d, self.batch, self.device = data, batch, device
         self.ex = ORBextractor(nfeatures, 1.2, 8, 20, 7, device=device)
+        self.ex.set_frame_grid(data.w, data.h)      # frame construction ends with AssignFeaturesToGrid (src/Frame.cc:598)
         self.ex2 = None           # second extractor workspace, created by run_stream (batch k+1 extracts while batch k is matched)
         self.m_track = ORBmatcher(0.9, True, device=device)      # TrackWithMotionModel (src/Tracking.cc:3593)
         self.m_map = ORBmatcher(0.8, True, device=device)        # SearchLocalPoints (src/Tracking.cc:4477)
@@ -152,7 +153,7 @@ class HotPath:
             # descriptors/keypoints of the current frame stay on the device for the searches
             dv = self.ex.device_result(b)
             cur_ref = self.frames[f]
-            cur = Frame(None, None, d.w, d.h, sf, s2, uright=self.frames[f].uright, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key))
+            cur = Frame(None, None, d.w, d.h, sf, s2, uright=self.frames[f].uright, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key, dv.grid_cell_start, dv.grid_sorted))
             n1, a1 = self.m_track.SearchByProjectionLast(cur, p["ql"], 15.0)
             claimed = (a1 >= 0).astype(np.uint8)
             # same tracking-thread workspace => the feature grid of the frame is built once for both searches
@@ -218,6 +219,7 @@ class HotPath:
         d, nb = self.d, self.batch
         if self.ex2 is None:
             self.ex2 = ORBextractor(self.ex.nfeatures, 1.2, 8, 20, 7, device=self.device)
+            self.ex2.set_frame_grid(self.d.w, self.d.h)
         exs = (self.ex, self.ex2)
         free = [threading.Semaphore(1), threading.Semaphore(1)]      # extractor workspace i may be overwritten
         q_track, q_tri = queue.Queue(), queue.Queue()
@@ -275,7 +277,7 @@ class HotPath:
                     if p is None:
                         continue
                     dv = exs[i].device_result(b)
-                    cur = Frame(None, None, d.w, d.h, sf, s2, uright=self.frames[f].uright, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key))
+                    cur = Frame(None, None, d.w, d.h, sf, s2, uright=self.frames[f].uright, bf=d.K["bf"], device_ptrs=(dv.n, dv.keys, dv.desc, 0, dv.cache_key, dv.grid_cell_start, dv.grid_sorted))
                     n1, a1 = self.m_track.SearchByProjectionLast(cur, p["ql"], 15.0)
                     claimed = (a1 >= 0).astype(np.uint8)
                     n2, a2 = self.m_track.SearchByProjectionMap(cur, p["qm"], 3.0, claimed=claimed, nnratio=0.8)
@@ -359,6 +361,7 @@ class HotPath:
         d = self.d
         if self.ex2 is None:
             self.ex2 = ORBextractor(self.ex.nfeatures, 1.2, 8, 20, 7, device=self.device)
+            self.ex2.set_frame_grid(self.d.w, self.d.h)
         recs = self._native_job()
         job = _lib.PipelineJob()
         job.device, job.width, job.height, job.batch, job.n_steps, job.first_frame = self.device, d.w, d.h, self.batch, nsteps, f0

@@ -94,6 +94,14 @@ def _impl_hot_path(w, h, nfeatures, voxel, far, batch, nsteps, max_blocks, threa
             n2, a2 = hp.m_track.SearchByProjectionMap(cur, q["qm"], 3.0, claimed=claimed, nnratio=0.8)
             on2, oa2 = OM.search_by_projection_map(cur_ref, q["qm"], 3.0, 0.8, claimed=claimed)
             assert n2 == on2 and np.array_equal(a2, oa2), f"frame {f}: SearchByProjection(F,map) differs"
+            # the same two searches on the grid the extractor built at frame construction (what HotPath.step / plvs_pipeline_run hand over)
+            assert dv.grid_cell_start and dv.grid_sorted
+            curg = Frame(None, None, d.w, d.h, sf, s2, uright=cur_ref.uright, bf=d.K["bf"],
+                         device_ptrs=(dv.n, dv.keys, dv.desc, 0, 0, dv.grid_cell_start, dv.grid_sorted))
+            g1, ga1 = hp.m_map.SearchByProjectionLast(curg, q["ql"], 15.0)
+            g2, ga2 = hp.m_map.SearchByProjectionMap(curg, q["qm"], 3.0, claimed=claimed, nnratio=0.8)
+            assert (g1, g2) == (on1, on2) and np.array_equal(ga1, oa1) and np.array_equal(ga2, oa2), f"frame {f}: searches on the frame-construction grid differ"
+            assert hp.m_map.last_stats()[1] == 2, "a search handed a grid must not build one"
             n3, m12 = hp.m_tri.SearchForTriangulation(Frame(kps[b], descs[b], d.w, d.h, sf, s2, uright=cur_ref.uright, bf=d.K["bf"]), last,
                                                       q["fv1"], q["fv2"], q["has1"], q["has2"], q["F12"], q["ep"], False, False)
             on3, om12 = OM.search_for_triangulation(cur_ref, last, q["fv1"], q["fv2"], q["has1"], q["has2"], q["F12"], q["ep"], False, False, False)
