@@ -455,6 +455,74 @@ k_resolve(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n, int
 constexpr int kWatch = 6;
 struct WatchRec { uint16_t kp[kWatch]; uint8_t n, blocked; uint16_t m; };        // n == 255: re-evaluate every round; m: length of the candidate list
 constexpr int kWalkBatch = 4;
+
+// One evaluation of query q against the claim table `cur` by one warp: best / second-best free candidate -> target, and the new watch set
+// (every candidate up to the last one the decision read, except pre-claimed ones, with the state just seen).  Lists of up to 32 entries -- the
+// common case -- are handled without loops: the lanes hold the entries (e_first), two REDUX give the two smallest keys, shuffles their
+// records, one ballot the watch set, one REDUX.OR its blocked bits.  Returns (lane 0) whether the target changed.
+template <int MODE>
+__device__ __forceinline__ bool reevaluate(int q, int m, uint32_t e_first, const uint32_t* __restrict__ row, const int* __restrict__ cur,
+                                           WatchRec* __restrict__ s_watch, int* __restrict__ s_target, float nn_ratio, int th_high, int lane32)
+{
+    uint16_t* wkp = reinterpret_cast<uint16_t*>(&s_watch[q]);
+    int t, cnt; uint32_t bits;
+    if (m <= 32) {
+        const bool valid = lane32 < m;
+        const int idx = cand_idx(e_first);
+        const int c = valid ? cur[idx] : -1;
+        const uint32_t kk = ((uint32_t)cand_dist(e_first) << 16) | (uint32_t)lane32;
+        const uint32_t key = (valid && !(c < q)) ? kk : 0xffffffffu;
+        const uint32_t k1 = __reduce_min_sync(0xffffffffu, key);
+        const uint32_t k2 = __reduce_min_sync(0xffffffffu, key == k1 ? 0xffffffffu : key);
+        const uint32_t e1 = __shfl_sync(0xffffffffu, e_first, (int)(k1 & 31u)), e2 = __shfl_sync(0xffffffffu, e_first, (int)(k2 & 31u));
+        t = decide_target<MODE>(k1, k2, k1 != 0xffffffffu ? e1 : 0u, k2 != 0xffffffffu ? e2 : 0u, nn_ratio, th_high);
+        const uint32_t limit = MODE == 0 ? k2 : k1;              // 0xffffffff (not enough free candidates): the whole list matters
+        const bool rel = valid && kk <= limit && c != -1;
+        const uint32_t relmask = __ballot_sync(0xffffffffu, rel);
+        const int pos = __popc(relmask & ((1u << lane32) - 1));
+        cnt = __popc(relmask);
+        if (rel && pos < kWatch) wkp[pos] = (uint16_t)idx;
+        bits = __reduce_or_sync(0xffffffffu, (rel && pos < kWatch && c < q) ? (1u << pos) : 0u);
+    } else {
+        uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+        for (int k0 = 0; k0 < m; k0 += 32) {
+            const int k = k0 + lane32;
+            uint32_t key = 0xffffffffu;
+            if (k < m) { const uint32_t e = k0 == 0 ? e_first : row[k]; if (!(cur[cand_idx(e)] < q)) key = ((uint32_t)cand_dist(e) << 16) | (uint32_t)k; }
+            const uint32_t s1 = __reduce_min_sync(0xffffffffu, key);
+            const uint32_t s2 = __reduce_min_sync(0xffffffffu, key == s1 ? 0xffffffffu : key);
+            const uint32_t lo = min(k1, s1), hi = max(k1, s1);
+            k2 = min(hi, min(k2, s2));
+            k1 = lo;
+        }
+        const uint32_t e1 = k1 != 0xffffffffu ? row[k1 & 0xffffu] : 0u, e2 = k2 != 0xffffffffu ? row[k2 & 0xffffu] : 0u;
+        t = decide_target<MODE>(k1, k2, e1, e2, nn_ratio, th_high);
+        const uint32_t limit = MODE == 0 ? k2 : k1;
+        cnt = 0; bits = 0;
+        for (int k0 = 0; k0 < m && cnt <= kWatch; k0 += 32) {
+            const int k = k0 + lane32;
+            bool rel = false, blk = false; uint32_t e = 0;
+            if (k < m) {
+                e = k0 == 0 ? e_first : row[k];
+                const int c = cur[cand_idx(e)];
+                rel = ((((uint32_t)cand_dist(e) << 16) | (uint32_t)k) <= limit) && c != -1;
+                blk = c < q;
+            }
+            const uint32_t relmask = __ballot_sync(0xffffffffu, rel);
+            const int pos = cnt + __popc(relmask & ((1u << lane32) - 1));
+            if (rel && pos < kWatch) wkp[pos] = (uint16_t)cand_idx(e);
+            bits |= __reduce_or_sync(0xffffffffu, (rel && pos < kWatch && blk) ? (1u << pos) : 0u);
+            cnt += __popc(relmask);
+        }
+    }
+    bool changed = false;
+    if (lane32 == 0) {
+        reinterpret_cast<uint32_t*>(&s_watch[q])[3] = (cnt > kWatch ? 255u : (uint32_t)cnt) | (bits << 8) | ((uint32_t)m << 16);
+        if (t != s_target[q]) { s_target[q] = t; changed = true; }
+    }
+    return changed;
+}
+
 static_assert(sizeof(WatchRec) == 16, "WatchRec layout");
 
 template <int MODE>
@@ -531,53 +599,13 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
                 mv[u] = qv[u] >= 0 ? (int)s_watch[qv[u]].m : 0;
                 ev[u] = lane32 < mv[u] ? cand[(size_t)qv[u] * cap + lane32] : 0u;
             }
-#pragma unroll
-            for (int u = 0; u < kWalkBatch; ++u) {
-                const int q = qv[u], m = mv[u];
+#pragma unroll 1
+            for (int u = 0; u < kWalkBatch; ++u) {        // one copy of the evaluation in the code; the batch only exists to have the loads in flight together
+                const int q = u == 0 ? qv[0] : u == 1 ? qv[1] : u == 2 ? qv[2] : qv[3];
                 if (q < 0) break;                      // warp-uniform
-                const uint32_t e_first = ev[u];
-                const uint32_t* row = cand + (size_t)q * cap;
-                uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
-                for (int k0 = 0; k0 < m; k0 += 32) {
-                    const int k = k0 + lane32;
-                    uint32_t key = 0xffffffffu;
-                    if (k < m) { const uint32_t e = k0 == 0 ? e_first : row[k]; if (!(cur[cand_idx(e)] < q)) key = ((uint32_t)cand_dist(e) << 16) | (uint32_t)k; }
-                    const uint32_t s1 = __reduce_min_sync(0xffffffffu, key);
-                    const uint32_t s2 = __reduce_min_sync(0xffffffffu, key == s1 ? 0xffffffffu : key);
-                    const uint32_t lo = min(k1, s1), hi = max(k1, s1);
-                    k2 = min(hi, min(k2, s2));
-                    k1 = lo;
-                }
-                // the two winners' records: out of a lane's register when they sit in the first 32 entries (warp-uniform positions)
-                const uint32_t p1 = k1 & 0xffffu, p2 = k2 & 0xffffu;
-                const uint32_t f1 = __shfl_sync(0xffffffffu, e_first, (int)(p1 & 31u)), f2 = __shfl_sync(0xffffffffu, e_first, (int)(p2 & 31u));
-                const uint32_t e1 = k1 != 0xffffffffu ? (p1 < 32u ? f1 : row[p1]) : 0u, e2 = k2 != 0xffffffffu ? (p2 < 32u ? f2 : row[p2]) : 0u;
-                const int t = decide_target<MODE>(k1, k2, e1, e2, nn_ratio, th_high);
-                // new watch set: every candidate up to the last one the decision read, except pre-claimed ones, with the state just seen.  The
-                // lanes write their keypoint straight into the shared-memory record at their rank; lane 0 derives the blocked bits from two ballots.
-                const uint32_t limit = MODE == 0 ? k2 : k1;              // 0xffffffff (not enough free candidates): the whole list matters
-                uint16_t* wkp = reinterpret_cast<uint16_t*>(&s_watch[q]);
-                int cnt = 0; uint32_t bits = 0;
-                for (int k0 = 0; k0 < m && cnt <= kWatch; k0 += 32) {
-                    const int k = k0 + lane32;
-                    bool rel = false, blk = false; uint32_t e = 0;
-                    if (k < m) {
-                        e = k0 == 0 ? e_first : row[k];
-                        const int c = cur[cand_idx(e)];
-                        rel = ((((uint32_t)cand_dist(e) << 16) | (uint32_t)k) <= limit) && c != -1;
-                        blk = c < q;
-                    }
-                    const uint32_t relmask = __ballot_sync(0xffffffffu, rel), blkmask = __ballot_sync(0xffffffffu, rel && blk);
-                    const int pos = cnt + __popc(relmask & ((1u << lane32) - 1));
-                    if (rel && pos < kWatch) wkp[pos] = (uint16_t)cand_idx(e);
-                    uint32_t rm = relmask;
-                    for (int j = cnt; j < kWatch && rm; ++j) { const int l = __ffs(rm) - 1; if ((blkmask >> l) & 1u) bits |= 1u << j; rm &= rm - 1; }
-                    cnt += __popc(relmask);
-                }
-                if (lane32 == 0) {
-                    reinterpret_cast<uint32_t*>(&s_watch[q])[3] = (cnt > kWatch ? 255u : (uint32_t)cnt) | (bits << 8) | ((uint32_t)m << 16);
-                    if (t != s_target[q]) { s_target[q] = t; changed = true; }
-                }
+                const int m = u == 0 ? mv[0] : u == 1 ? mv[1] : u == 2 ? mv[2] : mv[3];
+                const uint32_t e_first = u == 0 ? ev[0] : u == 1 ? ev[1] : u == 2 ? ev[2] : ev[3];
+                if (reevaluate<MODE>(q, m, e_first, cand + (size_t)q * cap, cur, s_watch, s_target, nn_ratio, th_high, lane32)) changed = true;
             }
         }
         if (tid == 0) s_walks += nwalk;
@@ -1030,7 +1058,7 @@ struct plvs_match {
     DevBuf<uint8_t> d_stage; PinBuf<uint8_t> p_stage;     // one packed H2D per projection search
     bool state_zeroed = false;
     bool use_pdl = true;                                 // k_resolve_cta as a programmatic dependent launch behind k_candidates (PLVS_MATCH_PDL=0: plain)
-    int resolve_threads = 512;                           // CTA size of k_resolve_cta (PLVS_MATCH_RESOLVE_THREADS: 256 / 512 / 1024)
+    int resolve_threads = 1024;                          // CTA size of k_resolve_cta (PLVS_MATCH_RESOLVE_THREADS: 256 / 512 / 1024)
     DevBuf<Round0> d_round0;                              // per query: what round 0 of the claim resolution leaves (written by k_candidates)
     int last_walks = 0;                                   // list re-evaluations of the last search after round 0 (statistics)
     int last_rounds = 0, last_launches = 0;

@@ -50,7 +50,7 @@ struct plvs_orb {
     DevBuf<CellDesc> d_cells;
     DevBuf<TileDesc> d_tiles;
     DevBuf<BilinearTap> d_taps;
-    DevBuf<uint32_t> d_slots, d_cand, d_sel;
+    DevBuf<uint32_t> d_slots, d_cand, d_sel, d_pattern;
     DevBuf<int> d_sel_off, d_sel_count, d_quota, d_dist_i32;
     DevBuf<unsigned long long> d_dist_u64;
     DevBuf<DNode> d_dist_nodes;
@@ -287,7 +287,16 @@ int setup_geometry(plvs_orb* o, int w, int h, int batch)
     PLVS_CUDA(cudaMemcpyAsync(o->d_cells.p, o->cells.data(), o->cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice, o->stream));
     PLVS_CUDA(cudaMemcpyAsync(o->d_tiles.p, o->blur_tiles.data(), o->blur_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, o->stream));
     PLVS_CUDA(cudaMemcpyAsync(o->d_taps.p, taps.data(), taps.size() * sizeof(BilinearTap), cudaMemcpyHostToDevice, o->stream));
-    PLVS_CUDA(cudaMemcpyToSymbolAsync(c_pattern, h_pattern, sizeof(h_pattern), 0, cudaMemcpyHostToDevice, o->stream));
+    {
+        std::vector<uint32_t> packed(256);
+        for (int lane = 0; lane < 32; ++lane)
+            for (int t = 0; t < 8; ++t) {
+                const int* q = h_pattern + lane * 32 + 4 * t;
+                packed[(size_t)t * 32 + lane] = (uint32_t)(uint8_t)(int8_t)q[0] | ((uint32_t)(uint8_t)(int8_t)q[1] << 8) | ((uint32_t)(uint8_t)(int8_t)q[2] << 16) | ((uint32_t)(uint8_t)(int8_t)q[3] << 24);
+            }
+        if ((rc = o->d_pattern.alloc(256))) return rc;
+        PLVS_CUDA(cudaMemcpy(o->d_pattern.p, packed.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     PLVS_CUDA(cudaMemcpyToSymbolAsync(c_umax, o->umax, sizeof(o->umax), 0, cudaMemcpyHostToDevice, o->stream));
     PLVS_CUDA(cudaStreamSynchronize(o->stream));
     return PLVS_OK;
@@ -437,7 +446,7 @@ static int extract_impl(plvs_orb* o, int batch, const uint8_t* gray, int w, int 
         o->timer.end(st);
         o->timer.begin(PLVS_ORB_K_DESCRIBE, st);
         k_orient_describe<<<dim3(div_up(o->sel_cap, 8), batch), 256, 0, st>>>(o->d_pyr.p, o->d_blur.p, o->frame_stride, o->d_lv.p, nl, o->d_sel.p, o->d_sel_off.p,
-                                                                              o->sel_cap, o->d_kp.p, o->d_desc.p, o->p_kp.d, o->p_desc.d);
+                                                                              o->sel_cap, o->d_kp.p, o->d_desc.p, o->p_kp.d, o->p_desc.d, o->d_pattern.p);
         o->timer.end(st);
         launches += 4;
         if (o->grid_on) {
@@ -517,7 +526,7 @@ static int extract_impl(plvs_orb* o, int batch, const uint8_t* gray, int w, int 
         PLVS_CUDA(cudaMemcpyAsync(o->d_sel_off.p, o->p_sel_off.h, (size_t)(nl + 1) * batch * sizeof(int), cudaMemcpyHostToDevice, st));
         o->timer.begin(PLVS_ORB_K_DESCRIBE, st);
         k_orient_describe<<<dim3(div_up(max_k, 8), batch), 256, 0, st>>>(o->d_pyr.p, o->d_blur.p, o->frame_stride, o->d_lv.p, nl, o->d_sel.p, o->d_sel_off.p,
-                                                                          o->sel_cap, o->d_kp.p, o->d_desc.p, o->p_kp.d, o->p_desc.d);
+                                                                          o->sel_cap, o->d_kp.p, o->d_desc.p, o->p_kp.d, o->p_desc.d, o->d_pattern.p);
         o->timer.end(st);
         ++launches;
     }

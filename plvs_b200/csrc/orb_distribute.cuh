@@ -365,20 +365,25 @@ __global__ void __launch_bounds__(256)
 k_pack_selected(DistArgs A, int* __restrict__ sel_level_off /* (nlevels+1) per frame */, int* __restrict__ n_kp_host /* mapped host, per frame */)
 {
     const int frame = blockIdx.x, tid = threadIdx.x;
-    __shared__ int s_off[PLVS_MAX_LEVELS + 1];
+    __shared__ int s_off[PLVS_MAX_LEVELS + 1], s_cnt[PLVS_MAX_LEVELS];
+    __shared__ const uint32_t* s_stage[PLVS_MAX_LEVELS];
+    // the per-level records are fetched by one thread each (one trip to L2 for all levels), then a short serial prefix
+    if (tid < A.nlevels) { s_cnt[tid] = A.sel_count[frame * A.nlevels + tid]; s_stage[tid] = A.scratch[frame * A.nlevels + tid].stage; }
+    __syncthreads();
     if (tid == 0) {
         int k = 0;
-        for (int l = 0; l < A.nlevels; ++l) { s_off[l] = k; k += A.sel_count[frame * A.nlevels + l]; }
+        for (int l = 0; l < A.nlevels; ++l) { s_off[l] = k; k += s_cnt[l]; }
         s_off[A.nlevels] = k;
         if (k > A.sel_cap) atomicExch(A.error, 2);
-        for (int l = 0; l <= A.nlevels; ++l) sel_level_off[frame * (A.nlevels + 1) + l] = min(s_off[l], A.sel_cap);
         n_kp_host[frame] = min(k, A.sel_cap);
     }
     __syncthreads();
-    for (int l = 0; l < A.nlevels; ++l) {
-        const uint32_t* stage = A.scratch[frame * A.nlevels + l].stage;
-        const int cnt = A.sel_count[frame * A.nlevels + l], base = s_off[l];
-        for (int i = tid; i < cnt; i += 256) if (base + i < A.sel_cap) A.sel[(long long)frame * A.sel_cap + base + i] = stage[i];
+    if (tid <= A.nlevels) sel_level_off[frame * (A.nlevels + 1) + tid] = min(s_off[tid], A.sel_cap);
+    // one warp per level (round-robin when there are more levels than warps): the levels are copied side by side
+    for (int l = tid >> 5; l < A.nlevels; l += 8) {
+        const uint32_t* stage = s_stage[l];
+        const int cnt = s_cnt[l], base = s_off[l];
+        for (int i = tid & 31; i < cnt; i += 32) if (base + i < A.sel_cap) A.sel[(long long)frame * A.sel_cap + base + i] = stage[i];
     }
 }
 

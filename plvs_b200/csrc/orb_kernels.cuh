@@ -393,16 +393,18 @@ k_compact(const uint32_t* __restrict__ slots, long long slots_per_frame,
           uint32_t* __restrict__ cand_dev, uint32_t* __restrict__ cand_host, int* __restrict__ cand_count_dev,
           int* __restrict__ cand_count_host)
 {
-    __shared__ int s_off[4096 + 1];
+    __shared__ int s_off[4096 + 1], s_slot[4096];
     __shared__ int s_warp[32];
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom g = levels[level];
     const int* cnt = cell_count + frame * cells_per_frame + g.cell_begin;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, T = blockDim.x, nw = T >> 5;
+    const int ncell = min(g.cell_count, 4096);
     int running = 0;
-    for (int base = 0; base < g.cell_count; base += T) {
+    for (int base = 0; base < ncell; base += T) {
         const int i = base + tid;
-        const int v = i < g.cell_count ? cnt[i] : 0;
+        const int v = i < ncell ? cnt[i] : 0;
+        if (i < ncell) s_slot[i] = cells[g.cell_begin + i].slot_off;
         int x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -410,22 +412,27 @@ k_compact(const uint32_t* __restrict__ slots, long long slots_per_frame,
         __syncthreads();
         int wbase = 0, chunk_total = 0;
         for (int k = 0; k < nw; ++k) { const int sv = s_warp[k]; if (k < wid) wbase += sv; chunk_total += sv; }
-        if (i < g.cell_count && i < 4096) s_off[i] = running + wbase + x - v;
+        if (i < ncell) s_off[i] = running + wbase + x - v;
         running += chunk_total;
         __syncthreads();
     }
     if (tid == 0) {
+        s_off[ncell] = running;
         cand_count_dev[frame * nlevels + level] = running;
         cand_count_host[frame * nlevels + level] = running;
     }
+    __syncthreads();
     const uint32_t* in = slots + (long long)frame * slots_per_frame;
     uint32_t* od = cand_dev + (long long)frame * slots_per_frame + g.slot_begin;
     uint32_t* oh = cand_host + (long long)frame * slots_per_frame + g.slot_begin;
-    // one warp per cell, lanes over the cell's candidates (32 warps: the level-0 copy is a chain of small dependent loads per cell)
-    for (int ci = wid; ci < g.cell_count; ci += nw) {
-        const CellDesc c = cells[g.cell_begin + ci];
-        const int m = cnt[ci], o = s_off[ci];
-        for (int k = lane; k < m; k += 32) { const uint32_t v = in[c.slot_off + k]; od[o + k] = v; if (cand_host) oh[o + k] = v; }
+    // flat copy: thread <-> output position; its cell is the last one whose offset is <= the position (empty cells share an offset with the next
+    // non-empty one, which is the last of the run).  Every load is independent: one trip to L2 per thread instead of one per cell and warp.
+    for (int j = tid; j < running; j += T) {
+        int lo = 0, hi = ncell;                      // s_off[lo] <= j < s_off[hi]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= j) lo = mid; else hi = mid; }
+        const uint32_t v = in[s_slot[lo] + (j - s_off[lo])];
+        od[j] = v;
+        if (cand_host) oh[j] = v;
     }
 }
 
@@ -435,7 +442,6 @@ k_compact(const uint32_t* __restrict__ slots, long long slots_per_frame,
 // blurred level (glibc-exact cosf/sinf, non-fused x*b+y*a, cvRound; :141-180), keypoint fix-up
 // (+border is already in the coordinates, octave, size; :1036-1046) and scaling to level 0 (:1363).
 // ---------------------------------------------------------------------------------------------
-__constant__ int c_pattern[1024];
 __constant__ int c_umax[16];
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x)
@@ -464,7 +470,8 @@ k_orient_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ b
                   const uint32_t* __restrict__ sel, const int* __restrict__ sel_level_off /* (nlevels+1) per frame */,
                   int sel_cap,
                   plvs_keypoint* __restrict__ kp_dev, uint8_t* __restrict__ desc_dev,
-                  plvs_keypoint* __restrict__ kp_host, uint8_t* __restrict__ desc_host)
+                  plvs_keypoint* __restrict__ kp_host, uint8_t* __restrict__ desc_host,
+                  const uint32_t* __restrict__ pattern /* [8][32] words: x0 | y0 << 8 | x1 << 16 | y1 << 24 (int8) of test pair 8*lane + t at [t][lane] */)
 {
     const int frame = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -497,11 +504,16 @@ k_orient_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ b
     float a, b;
     libm_sincosf(__fmul_rn(angle, factorPI), &a, &b);
     const uint8_t* c = blur + fo + (long long)y * g.pitch + x;
-    const int* pat = c_pattern + lane * 32;
+    // the 256 test pairs: lane <-> byte, 8 pairs per lane.  Packed four int8 per word and laid out [pair][lane], a warp fetches the eight words
+    // of its lanes with eight coalesced loads (a lane-strided table in constant memory costs one serialised fetch per lane and coordinate)
+    uint32_t pw[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) pw[t] = __ldg(pattern + t * 32 + lane);
     int val = 0;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-        const float x0 = (float)pat[4 * t], y0 = (float)pat[4 * t + 1], x1 = (float)pat[4 * t + 2], y1 = (float)pat[4 * t + 3];
+        const float x0 = (float)(int)(int8_t)(pw[t] & 0xffu), y0 = (float)(int)(int8_t)((pw[t] >> 8) & 0xffu);
+        const float x1 = (float)(int)(int8_t)((pw[t] >> 16) & 0xffu), y1 = (float)(int)(int8_t)(pw[t] >> 24);
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
         const int q0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, a), -__fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
