@@ -58,7 +58,7 @@ struct plvs_orb {
     DevBuf<DistLevel> d_dist_levels;
     PinBuf<int> p_nkp, p_err;
     bool host_distribute = false; int fast_tree = 0;
-    int dist_smem = 0;
+    int dist_smem = 0, dist_arena = 0;
     DevBuf<int> d_cell_count, d_cand_count;
     DevBuf<plvs_keypoint> d_kp;
     DevBuf<uint8_t> d_desc;
@@ -278,7 +278,15 @@ int setup_geometry(plvs_orb* o, int w, int h, int batch)
         PLVS_CUDA(cudaMemcpyAsync(o->d_quota.p, o->quota, nl * sizeof(int), cudaMemcpyHostToDevice, o->stream));
         PLVS_CUDA(cudaStreamSynchronize(o->stream));          // tab is a local
         o->dist_smem = (max_quota + 8) * (int)sizeof(unsigned long long);
-        if (o->dist_smem > 48 * 1024) PLVS_CUDA(cudaFuncSetAttribute(k_distribute, cudaFuncAttributeMaxDynamicSharedMemorySize, o->dist_smem));
+        // single-frame calls keep the distributor's node-level state in shared memory (orb_distribute.cuh): an arena for the largest level that fits
+        {
+            const size_t per_node = sizeof(DNode) + 2 * 8 + 6 * 4, limit = (size_t)190 * 1024 - (size_t)o->dist_smem;
+            size_t arena = 0;
+            for (int l = 0; l < nl; ++l) { const size_t need = (size_t)std::min(ncap[l], 4 * o->quota[l] + 128) * per_node; if (need <= limit) arena = std::max(arena, need); }
+            const char* e = getenv("PLVS_ORB_DIST_SMEM");
+            o->dist_arena = (e && e[0] == '0') ? 0 : (int)arena;
+        }
+        if (o->dist_smem + o->dist_arena > 48 * 1024) PLVS_CUDA(cudaFuncSetAttribute(k_distribute, cudaFuncAttributeMaxDynamicSharedMemorySize, o->dist_smem + o->dist_arena));
     }
     if ((rc = o->p_sel_off.alloc((size_t)(nl + 1) * B))) return rc;
     if ((rc = o->p_kp.alloc((size_t)o->sel_cap * B))) return rc;
@@ -438,7 +446,10 @@ static int extract_impl(plvs_orb* o, int batch, const uint8_t* gray, int w, int 
         da.error = o->p_err.d;
         o->p_err.h[0] = 0;
         o->timer.begin(PLVS_ORB_K_DISTRIBUTE, st);
-        k_distribute<<<dim3(nl, batch), kDistThreads, o->dist_smem, st>>>(da);
+        da.sort_bytes = o->dist_smem;
+        { const char* e = getenv("PLVS_ORB_DIST_ARENA_NODES"); da.arena_nodes = e ? std::max(0, atoi(e)) : 0; }      // test hook
+        da.arena_bytes = batch == 1 ? o->dist_arena : 0;          // batches are throughput-bound and share the SMs' shared memory with the other stages
+        k_distribute<<<dim3(nl, batch), kDistThreads, o->dist_smem + da.arena_bytes, st>>>(da);
         k_pack_selected<<<batch, 256, 0, st>>>(da, o->d_sel_off.p, o->p_nkp.d);
         o->timer.end(st);
         o->timer.begin(PLVS_ORB_K_BLUR, st);

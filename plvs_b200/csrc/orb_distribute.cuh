@@ -214,6 +214,9 @@ struct DistArgs {
     int* sel_count;                // out: [frame][level]
     int sel_cap;
     int* error;                    // != 0 on node-pool / keypoint-capacity overflow
+    int sort_bytes;                // dynamic shared memory: the std::sort area first ...
+    int arena_bytes;               // ... then (single-frame calls) room for the node-level state; 0 = node-level state in global memory
+    int arena_nodes;               // test hook: > 0 caps the nodes the arena is carved for (forces the start-over path)
 };
 
 __global__ void __launch_bounds__(kDistThreads)
@@ -234,6 +237,31 @@ k_distribute(DistArgs A)
     const int nIni = (int)roundf((float)(maxX - minX) / (float)(maxY - minY));
     if (n == 0 || nIni == 0 || nIni > D.ncap) { if (tid == 0) *out_count = 0; return; }
     const float hX = (float)(maxX - minX) / (float)nIni;
+    // Latency mode (single-frame calls; the host passes an arena): the node-level state -- node pool, the list, the per-parent scratch, the
+    // expandable-node lists -- lives in shared memory instead of L2, which is where the ~15 dependent phases of a sweep spent their time.  The
+    // pointers of D are simply redirected; the code below is the same.  The arena holds 4 x quota + 128 nodes, plenty in practice (a sweep
+    // stops at the quota); should a level ever need more, the kernel starts that level over with the state in global memory.
+    bool in_smem = false;
+    {
+        const int scap = A.arena_nodes > 0 ? min(D.ncap, A.arena_nodes) : min(D.ncap, 4 * N + 128);
+        if (A.arena_bytes > 0 && (long long)scap * (long long)(sizeof(DNode) + 2 * 8 + 6 * 4) <= (long long)A.arena_bytes && nIni <= scap) {
+            char* base = reinterpret_cast<char*>(s_sort) + A.sort_bytes;
+            D.expand[0] = reinterpret_cast<unsigned long long*>(base); base += 8 * (size_t)scap;
+            D.expand[1] = reinterpret_cast<unsigned long long*>(base); base += 8 * (size_t)scap;
+            D.nodes = reinterpret_cast<DNode*>(base); base += sizeof(DNode) * (size_t)scap;
+            D.order[0] = reinterpret_cast<int*>(base); base += 4 * (size_t)scap;
+            D.order[1] = reinterpret_cast<int*>(base); base += 4 * (size_t)scap;
+            D.plist = reinterpret_cast<int*>(base); base += 4 * (size_t)scap;
+            D.nkids = reinterpret_cast<int*>(base); base += 4 * (size_t)scap;
+            D.nexp = reinterpret_cast<int*>(base); base += 4 * (size_t)scap;
+            D.flag = reinterpret_cast<int*>(base);
+            D.ncap = scap;
+            in_smem = true;
+        }
+    }
+    bool retry;
+restart:
+    retry = false;
 
     // ---- roots (src/ORBextractor.cc:626-664): every candidate goes to the root its x falls in (nIni is 1-3)
     for (int r = tid; r < nIni; r += T) {
@@ -272,7 +300,7 @@ k_distribute(DistArgs A)
         __syncthreads();
         const int nparents = live - n_leaves;
         if (nparents == 0) break;
-        if (s_nc + 4 * nparents > D.ncap) { if (tid == 0) atomicExch(A.error, 1); break; }
+        if (s_nc + 4 * nparents > D.ncap) { if (in_smem) retry = true; else if (tid == 0) atomicExch(A.error, 1); break; }
         ++tag;
         for (int i = tid; i < live; i += T) {
             const int id = ord[i];
@@ -319,7 +347,7 @@ k_distribute(DistArgs A)
             const int nproc = s_flag;
             for (int j = nproc + tid; j < nexp; j += T) D.nodes[D.plist[j]].tag = 0;          // not reached: stay as they are
             __syncthreads();
-            if (s_nc + 4 * nproc > D.ncap || live + 4 * nproc > D.ncap) { if (tid == 0) atomicExch(A.error, 1); done = true; break; }
+            if (s_nc + 4 * nproc > D.ncap || live + 4 * nproc > D.ncap) { if (in_smem) retry = true; else if (tid == 0) atomicExch(A.error, 1); done = true; break; }
             // children are pushed to the list front == appended to the storage, in processing order
             split_nodes(cand, n, D, tag, nproc, &s_nc, s_i32, &s_nk, &s_ne, D.expand[ecur ^ 1], ord + live);
             ecur ^= 1;
@@ -340,6 +368,11 @@ k_distribute(DistArgs A)
         if (done) break;
     }
     __syncthreads();
+    if (retry) {            // uniform: the arena was too small for this level -- once more with the node-level state in global memory
+        D = A.scratch[frame * A.nlevels + level];
+        in_smem = false;
+        goto restart;
+    }
     // ---- per surviving node, in list order (storage back -> front), the first maximum response (:842-862): inside a node the reference's keys
     // are in candidate-index order, so "first maximum" is the largest (response, lowest index) -- one atomicMax per candidate
     {

@@ -123,6 +123,22 @@ def test_device_distributor_equals_host_distributor(gpu, monkeypatch, nfeat):
         assert np.array_equal(k1, k2) and np.array_equal(d1, d2)
 
 
+@pytest.mark.parametrize("arena_nodes", [0, 24, 200])
+def test_distributor_state_in_shared_memory_and_in_global_memory(gpu, monkeypatch, arena_nodes):
+    """single-frame calls keep the distributor's node-level state in shared memory; a level that outgrows the arena starts over with the state
+    in global memory (forced here with a tiny arena: 24 nodes overflow on every level, 200 on the lower ones); batches use global memory.  All the same keypoints."""
+    imgs = [synth.gray_frame(3), synth.gray_frame(0, 333, 257)]
+    want = [ORBextractor(2000, 1.2, 8, 20, 7).extract_batch(np.stack([im, im]))[1][0] for im in imgs]      # batch of two: global-memory state
+    if arena_nodes:
+        monkeypatch.setenv("PLVS_ORB_DIST_ARENA_NODES", str(arena_nodes))
+    for im, w in zip(imgs, want):
+        ex = ORBextractor(2000, 1.2, 8, 20, 7)
+        mono, kp, desc = ex(im)
+        assert np.array_equal(kp, w)
+        okp = O.extract_port(im, 2000)[0]
+        assert np.array_equal(kp, okp)
+
+
 def test_cuda_vs_compiled_reference_live(gpu):
     """the CUDA extractor against the REFERENCE's own ORBextractor.cc (oracle/_ref/liborb_ref.so, prebuilt in the build
     container by oracle/ref_build.py; it travels to the GPU box with the snapshot)"""
