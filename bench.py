@@ -296,7 +296,7 @@ def kernel_table(lib, hp):
     for i, nme in enumerate(("tsdf.depth_tiles", "tsdf.classify", "tsdf.integrate", "tsdf.commit")):
         ktimes[nme] = (float(ms[i]), int(cnt[i]))
     om = np.zeros(12, np.float32); oc = np.zeros(12, np.int32)
-    for ex in (hp.ex, hp.ex2):
+    for ex in [hp.ex, hp.ex2] + list(getattr(hp, "ex_more", [])):
         if ex is not None:
             lib.plvs_orb_kernel_times(ex._h, ms.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 0)
             om += ms; oc += cnt
@@ -411,7 +411,7 @@ def run_b200_arm(a):
 
     def reset_timers():
         lib.plvs_tsdf_kernel_times(hp.tsdf._h, None, None, 1)
-        for ex in (hp.ex, hp.ex2):
+        for ex in [hp.ex, hp.ex2] + list(getattr(hp, "ex_more", [])):
             if ex is not None:
                 lib.plvs_orb_kernel_times(ex._h, None, None, 1)
         for m in (hp.m_track, hp.m_map, hp.m_tri):

@@ -264,6 +264,9 @@ int plvs_match_kernel_times(plvs_match* h, float* ms, int32_t* launches, int res
 int plvs_match_last_stats(const plvs_match* h, int* rounds, int* kernel_launches);
 /* candidate-list re-evaluations of the last projection search after round 0 (-1: the cluster kernel ran, which re-walks every list every round) */
 int plvs_match_last_walks(const plvs_match* h);
+/* inspection: SM cycles thread 0 of the last one-CTA claim resolution spent in [0] building the claim tables, [1] comparing watch sets, [2] re-evaluating
+ * queries, and [3] from the first round to the end of the kernel (rounds + wrap-up) */
+int plvs_match_last_phase_cycles(const plvs_match* h, int32_t out[4]);
 
 /* DBoW2::FeatureVector flattened: sorted node ids, CSR offsets, feature indices (ascending per node) */
 typedef struct {
@@ -598,8 +601,9 @@ typedef struct {
     double wall_s, busy_extract_s, busy_track_s, busy_tri_s, busy_map_s;
 } plvs_pipeline_stats;
 
-/* steps first_frame + s*batch .. for s in [0, n_steps); ex[s & 1] extracts step s.  Returns when every stage has drained. */
-int plvs_pipeline_run(plvs_orb* const ex[2], plvs_match* m_track, plvs_match* m_tri, plvs_tsdf* tsdf, const plvs_pipeline_job* job,
+/* steps first_frame + s*batch .. for s in [0, n_steps); ex[s % n_ex] extracts step s (n_ex even, 2..8: n_ex / 2 frame-construction threads take
+ * alternate steps, so with n_ex = 4 two batches are in extraction while Tracking / LocalMapping read a third).  Returns when every stage has drained. */
+int plvs_pipeline_run(plvs_orb* const* ex, int n_ex, plvs_match* m_track, plvs_match* m_tri, plvs_tsdf* tsdf, const plvs_pipeline_job* job,
                       plvs_pipeline_stats* out);
 
 #ifdef __cplusplus

@@ -121,6 +121,7 @@ def declare(lib):
     lib.plvs_orb_download_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     lib.plvs_orb_device_result.argtypes = [C.c_void_p, C.c_int, C.POINTER(OrbDeviceView)]
     lib.plvs_orb_set_frame_grid.argtypes = [C.c_void_p, C.c_void_p]
+    lib.plvs_match_last_phase_cycles.argtypes = [C.c_void_p, C.c_void_p]
     lib.plvs_orb_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.plvs_orb_last_stats.argtypes = [C.c_void_p, C.POINTER(OrbStats)]
     lib.plvs_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
@@ -180,7 +181,7 @@ def declare(lib):
     lib.plvs_tsdf_integrate_world_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
     lib.plvs_enable_peer_access.argtypes = [C.c_int, C.c_int]
     lib.plvs_io_bytes.argtypes = [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]
-    lib.plvs_pipeline_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.plvs_pipeline_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     for name in ("plvs_match_destroy", "plvs_tsdf_destroy"):
         if hasattr(lib, name):
             getattr(lib, name).restype = None

@@ -566,10 +566,13 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
     // the previous round is wiped for the next one; (D) the queued queries are evaluated again.  Three CTA barriers per round.
     int* cur = tab0; int* nxt = tab1;       // both clean (pre-claims only) here
     int rounds = 1;                         // round 0 ran inside k_candidates
+    long long t_mark = clock64(), t_b = 0, t_c = 0, t_d = 0;      // thread 0: cycles per phase (inspection: plvs_match_last_phase_cycles)
+    const long long t_start = t_mark;
     for (;;) {
         for (int q = tid; q < nq; q += nthr) { const int t = s_target[q]; if (t >= 0 && s_obs[q]) atomicMin(&nxt[t], q); }
         if (tid == 0) s_nwalk = 0;
         __syncthreads();
+        { const long long t = clock64(); t_b += t - t_mark; t_mark = t; }
         { int* t = cur; cur = nxt; nxt = t; }
         bool changed = false;
         for (int q = tid; q < nq; q += nthr) {
@@ -586,6 +589,7 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
         }
         for (int i = tid; i < n; i += nthr) nxt[i] = nxt[i] < 0 ? -1 : INF;
         __syncthreads();
+        { const long long t = clock64(); t_c += t - t_mark; t_mark = t; }
         // (D) one warp per queued query: the lanes take the list entries (rows are read from L2, coalesced; the first 32 entries of up to four
         // queries are requested before the first one is evaluated, so a warp pays the L2 round trip once per four queries), warp reductions
         // give the best and second-best free candidate, ballots the new watch set
@@ -610,7 +614,9 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
         }
         if (tid == 0) s_walks += nwalk;
         ++rounds;
-        if (!__syncthreads_or(changed ? 1 : 0)) break;
+        const int go_on = __syncthreads_or(changed ? 1 : 0);
+        { const long long t = clock64(); t_d += t - t_mark; t_mark = t; }
+        if (!go_on) break;
     }
     // final holders: the last (highest) query that wrote each keypoint
     int* assign = nxt;
@@ -665,7 +671,10 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
     }
     __syncthreads();
     for (int i = tid; i < n; i += nthr) assign_out[i] = assign[i];
-    if (tid == 0) { result[0] = s_count; result[1] = rounds; result[2] = s_walks; result[3] = *max_count; *max_count = 0; }
+    if (tid == 0) {
+        result[0] = s_count; result[1] = rounds; result[2] = s_walks; result[3] = *max_count; *max_count = 0;
+        result[4] = (int)t_b; result[5] = (int)t_c; result[6] = (int)t_d; result[7] = (int)(clock64() - t_start);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1057,6 +1066,7 @@ struct plvs_match {
     int cap = 128;
     DevBuf<uint8_t> d_stage; PinBuf<uint8_t> p_stage;     // one packed H2D per projection search
     bool state_zeroed = false;
+    int last_phase[4] = {0, 0, 0, 0};                    // SM cycles of the last one-CTA resolve: claim table, watch-set compare, re-evaluations, rounds + wrap-up
     bool use_pdl = true;                                 // k_resolve_cta as a programmatic dependent launch behind k_candidates (PLVS_MATCH_PDL=0: plain)
     int resolve_threads = 1024;                          // CTA size of k_resolve_cta (PLVS_MATCH_RESOLVE_THREADS: 256 / 512 / 1024)
     DevBuf<Round0> d_round0;                              // per query: what round 0 of the claim resolution leaves (written by k_candidates)
@@ -1217,6 +1227,7 @@ int run_projection(plvs_match* h, const plvs_frame_view* F, const void* q, size_
         PLVS_CUDA(cudaStreamSynchronize(st));
         h->timer.collect();
         h->last_walks = one_cta ? h->p_result.h[2] : -1;
+        for (int i = 0; i < 4; ++i) h->last_phase[i] = one_cta ? h->p_result.h[4 + i] : 0;
         const int mx = h->p_result.h[3];
         if (mx <= h->cap) break;
         while (h->cap < mx) h->cap *= 2;       // a window held more candidates than reserved: redo with room (exactness first)
@@ -1302,6 +1313,13 @@ int plvs_match_kernel_times(plvs_match* h, float* ms, int32_t* launches, int res
 }
 
 int plvs_match_last_walks(const plvs_match* h) { return h ? h->last_walks : -1; }
+
+int plvs_match_last_phase_cycles(const plvs_match* h, int32_t out[4])
+{
+    if (!h || !out) return PLVS_EINVAL;
+    for (int i = 0; i < 4; ++i) out[i] = h->last_phase[i];
+    return PLVS_OK;
+}
 
 int plvs_match_last_stats(const plvs_match* h, int* rounds, int* kernel_launches)
 {

@@ -58,7 +58,7 @@ struct plvs_orb {
     DevBuf<DistLevel> d_dist_levels;
     PinBuf<int> p_nkp, p_err;
     bool host_distribute = false; int fast_tree = 0;
-    int dist_smem = 0, dist_arena = 0;
+    int dist_smem = 0, dist_arena = 0, dist_sort_elems = 0;
     DevBuf<int> d_cell_count, d_cand_count;
     DevBuf<plvs_keypoint> d_kp;
     DevBuf<uint8_t> d_desc;
@@ -277,7 +277,8 @@ int setup_geometry(plvs_orb* o, int w, int h, int batch)
         PLVS_CUDA(cudaMemcpyAsync(o->d_dist_levels.p, tab.data(), tab.size() * sizeof(DistLevel), cudaMemcpyHostToDevice, o->stream));
         PLVS_CUDA(cudaMemcpyAsync(o->d_quota.p, o->quota, nl * sizeof(int), cudaMemcpyHostToDevice, o->stream));
         PLVS_CUDA(cudaStreamSynchronize(o->stream));          // tab is a local
-        o->dist_smem = (max_quota + 8) * (int)sizeof(unsigned long long);
+        o->dist_sort_elems = max_quota + 8;
+        o->dist_smem = (int)align_up((size_t)o->dist_sort_elems * sizeof(unsigned long long) + (size_t)stdsort::sort_cta_scratch_ints(o->dist_sort_elems) * sizeof(int), 16);
         // single-frame calls keep the distributor's node-level state in shared memory (orb_distribute.cuh): an arena for the largest level that fits
         {
             const size_t per_node = sizeof(DNode) + 2 * 8 + 6 * 4, limit = (size_t)190 * 1024 - (size_t)o->dist_smem;
@@ -446,7 +447,7 @@ static int extract_impl(plvs_orb* o, int batch, const uint8_t* gray, int w, int 
         da.error = o->p_err.d;
         o->p_err.h[0] = 0;
         o->timer.begin(PLVS_ORB_K_DISTRIBUTE, st);
-        da.sort_bytes = o->dist_smem;
+        da.sort_bytes = o->dist_smem; da.sort_elems = o->dist_sort_elems;
         { const char* e = getenv("PLVS_ORB_DIST_ARENA_NODES"); da.arena_nodes = e ? std::max(0, atoi(e)) : 0; }      // test hook
         da.arena_bytes = batch == 1 ? o->dist_arena : 0;          // batches are throughput-bound and share the SMs' shared memory with the other stages
         k_distribute<<<dim3(nl, batch), kDistThreads, o->dist_smem + da.arena_bytes, st>>>(da);

@@ -214,7 +214,8 @@ struct DistArgs {
     int* sel_count;                // out: [frame][level]
     int sel_cap;
     int* error;                    // != 0 on node-pool / keypoint-capacity overflow
-    int sort_bytes;                // dynamic shared memory: the std::sort area first ...
+    int sort_elems;                // dynamic shared memory: the std::sort area first (sort_elems 64-bit elements + the scratch of stdsort::sort_cta) ...
+    int sort_bytes;                // ... sort_bytes in all
     int arena_bytes;               // ... then (single-frame calls) room for the node-level state; 0 = node-level state in global memory
     int arena_nodes;               // test hook: > 0 caps the nodes the arena is carved for (forces the start-over path)
 };
@@ -222,7 +223,7 @@ struct DistArgs {
 __global__ void __launch_bounds__(kDistThreads)
 k_distribute(DistArgs A)
 {
-    PLVS_DYN_SMEM(unsigned long long, s_sort);           // max quota + 8 elements for the std::sort emulation
+    PLVS_DYN_SMEM(unsigned long long, s_sort);           // max quota + 8 elements for the std::sort emulation, then its scratch, then the arena
     __shared__ int s_i32[32];
     __shared__ int s_nc, s_nk, s_ne, s_live, s_flag;
     __shared__ int s_q[4 * kQcntShared];
@@ -324,8 +325,7 @@ restart:
             ord = D.order[ocur];
             for (int i = tid; i < nexp; i += T) s_sort[i] = D.expand[ecur][i];
             __syncthreads();
-            if (tid == 0) stdsort::sort(s_sort, nexp);
-            __syncthreads();
+            stdsort::sort_cta(s_sort, nexp, reinterpret_cast<int*>(s_sort + A.sort_elems));      // std::sort, range by range (stdsort_emul.cuh)
             ++tag;
             for (int j = tid; j < nexp; j += T) { const int id = (int)(uint32_t)s_sort[nexp - 1 - j]; D.plist[j] = id; D.nodes[id].tag = tag; D.nodes[id].slot = j; }   // largest first
             __syncthreads();

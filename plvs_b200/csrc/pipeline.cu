@@ -1,7 +1,7 @@
 // Stream driver: the reference's thread structure around the three replaced surfaces, in its own host language.
 // PLVS runs frame construction + Tracking in the caller's thread, LocalMapping and PointCloudMapping in threads of their own
 // (src/System.cc:317-398); here the four roles are four std::threads connected by queues, each with its own library handle (= CUDA stream):
-//   frame construction : ORBextractor::operator() on batches of frames        (src/Frame.cc:292-330 -> src/ORBextractor.cc:1245)
+//   frame construction : ORBextractor::operator() on batches of frames        (src/Frame.cc:292-330 -> src/ORBextractor.cc:1245); n_ex / 2 threads, alternate batches
 //   Tracking           : SearchByProjection(Cur, Last) + SearchByProjection(F, local map points) per frame   (src/Tracking.cc:3593, 4477)
 //   LocalMapping       : SearchForTriangulation against the previous frame    (src/LocalMapping.cc:537)
 //   PointCloudMapping  : ChiselServer::IntegrateLastDepthImage per frame       (src/PointCloudMapChisel.cc:100-131)
@@ -28,48 +28,53 @@ struct Channel {
     T get() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return !q.empty(); }); T v = q.front(); q.pop_front(); return v; }
 };
 
-struct Semaphore {
-    std::mutex mu; std::condition_variable cv; int count;
-    explicit Semaphore(int c) : count(c) {}
-    void acquire() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return count > 0; }); --count; }
-    void release() { { std::lock_guard<std::mutex> l(mu); ++count; } cv.notify_one(); }
-};
-
 struct Workspace {           // what one extractor call hands to the next stages (the caller's vectors in the reference)
     std::vector<plvs_keypoint> kps; std::vector<uint8_t> desc; std::vector<int> n, mono;
 };
+
+constexpr int kMaxExtractors = 8;
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 }  // namespace
 
-extern "C" int plvs_pipeline_run(plvs_orb* const ex[2], plvs_match* m_track, plvs_match* m_tri, plvs_tsdf* tsdf, const plvs_pipeline_job* job,
+extern "C" int plvs_pipeline_run(plvs_orb* const* ex, int n_ex, plvs_match* m_track, plvs_match* m_tri, plvs_tsdf* tsdf, const plvs_pipeline_job* job,
                                  plvs_pipeline_stats* out)
 {
-    if (!ex || !ex[0] || !ex[1] || !m_track || !m_tri || !tsdf || !job || !out) { set_error("null argument"); return PLVS_EINVAL; }
+    if (!ex || n_ex < 2 || n_ex > kMaxExtractors || (n_ex & 1) || !m_track || !m_tri || !tsdf || !job || !out) { set_error("null / bad argument"); return PLVS_EINVAL; }
+    for (int i = 0; i < n_ex; ++i) if (!ex[i]) { set_error("null extractor handle"); return PLVS_EINVAL; }
     if (job->batch < 1 || job->n_steps < 0 || job->cap < 1 || !job->frames || !job->gray || !job->depth || !job->poses) { set_error("bad pipeline job"); return PLVS_EINVAL; }
     const int B = job->batch, W = job->width, H = job->height, cap = job->cap;
     const size_t px = (size_t)W * H;
-    Workspace ws[2];
+    // Extractor handle / workspace i serves the steps s with s % n_ex == i.  n_ex / 2 frame-construction threads take alternate steps, so two
+    // batches can be in extraction at once (a batch is a chain of fourteen mostly narrow kernels) while Tracking and LocalMapping read a third one.
+    const int NX = n_ex, n_ex_threads = n_ex / 2;
+    std::vector<Workspace> ws(NX);
     for (Workspace& w : ws) { w.kps.resize((size_t)B * cap); w.desc.resize((size_t)B * cap * 32); w.n.assign(B, 0); w.mono.assign(B, 0); }
-    Semaphore free_ws[2] = {Semaphore(1), Semaphore(1)};       // workspace i may be overwritten by the extractor
-    std::atomic<int> users[2];                                 // consumers (Tracking, LocalMapping) still reading workspace i
-    users[0] = 0; users[1] = 0;
-    Channel<int> q_track, q_tri;           // step index, -1 = end of stream
+    std::mutex sync_mu; std::condition_variable sync_cv;       // guards free_slot[], extracted[]: who may write a workspace, which steps are ready
+    std::vector<char> free_slot(NX, 1);                        // workspace i may be overwritten by the extractor
+    std::vector<char> extracted((size_t)std::max(job->n_steps, 1), 0);
+    std::atomic<int> users[kMaxExtractors];                    // consumers (Tracking, LocalMapping) still reading workspace i
+    for (int i = 0; i < kMaxExtractors; ++i) users[i] = 0;
+    Channel<int> q_tri;                    // step index, -1 = end of stream
     std::atomic<int> failed{0};
     std::mutex err_mu; std::string err_msg;
     std::atomic<long long> keypoints{0}, matches{0};
     double busy[4] = {0, 0, 0, 0};
     auto fail = [&](int rc, const char* what) {
         if (!failed.exchange(rc ? rc : PLVS_EINVAL)) { std::lock_guard<std::mutex> l(err_mu); err_msg = std::string(what) + ": " + plvs_last_error(); }
+        { std::lock_guard<std::mutex> l(sync_mu); }
+        sync_cv.notify_all();
     };
+    auto release_slot = [&](int i) { { std::lock_guard<std::mutex> l(sync_mu); free_slot[i] = 1; } sync_cv.notify_all(); };
     cudaStream_t flush_stream = nullptr;
+    if (job->flush_buf && job->flush_bytes) { cudaSetDevice(job->device); cudaStreamCreateWithFlags(&flush_stream, cudaStreamNonBlocking); }
 
     // ---- one step of each stage ------------------------------------------------------------------------------------------------
     auto extract_step = [&](int s) -> bool {
-        const int i = s & 1;
-        if (job->flush_buf && job->flush_bytes) {            // evict the previous step's working set from L2 (inside the timed region)
-            if (!flush_stream) { cudaSetDevice(job->device); cudaStreamCreateWithFlags(&flush_stream, cudaStreamNonBlocking); }
+        const int i = s % NX;
+        if (flush_stream) {                                   // evict the previous step's working set from L2 (inside the timed region)
+            cudaSetDevice(job->device);
             cudaMemsetAsync(job->flush_buf, s & 0xff, job->flush_bytes, flush_stream);
         }
         const size_t f0 = (size_t)job->first_frame + (size_t)s * B;
@@ -83,7 +88,7 @@ extern "C" int plvs_pipeline_run(plvs_orb* const ex[2], plvs_match* m_track, plv
     };
     std::vector<int32_t> a1, a2, m12; std::vector<uint8_t> claimed;       // a1/a2/claimed: Tracking's thread only; m12: LocalMapping's only
     auto track_step = [&](int s) {
-        const int i = s & 1;
+        const int i = s % NX;
         long long nm = 0;
         for (int b = 0; b < B && !failed; ++b) {
             const plvs_pipeline_frame& fr = job->frames[(size_t)job->first_frame + (size_t)s * B + b];
@@ -107,7 +112,7 @@ extern "C" int plvs_pipeline_run(plvs_orb* const ex[2], plvs_match* m_track, plv
         matches += nm;
     };
     auto tri_step = [&](int s) {
-        const int i = s & 1;
+        const int i = s % NX;
         long long nm = 0;
         for (int b = 0; b < B && !failed; ++b) {
             const plvs_pipeline_frame& fr = job->frames[(size_t)job->first_frame + (size_t)s * B + b];
@@ -151,26 +156,28 @@ extern "C" int plvs_pipeline_run(plvs_orb* const ex[2], plvs_match* m_track, plv
         map_finish();
     } else {
         // ---- the stage threads ------------------------------------------------------------------------------------------------------
-        auto extract_stage = [&] {
-            for (int s = 0; s < job->n_steps && !failed; ++s) {
-                const int i = s & 1;
-                free_ws[i].acquire();
+        double busy_ex[kMaxExtractors] = {0};
+        auto extract_stage = [&](int j) {
+            for (int s = j; s < job->n_steps && !failed; s += n_ex_threads) {
+                const int i = s % NX;
+                { std::unique_lock<std::mutex> l(sync_mu); sync_cv.wait(l, [&] { return free_slot[i] || failed; }); free_slot[i] = 0; }
+                if (failed) break;
                 const double t0 = now_s();
-                if (!extract_step(s)) { free_ws[i].release(); break; }
-                busy[0] += now_s() - t0;
+                if (!extract_step(s)) { release_slot(i); break; }
+                busy_ex[j] += now_s() - t0;
                 users[i] = 2;
-                q_track.put(s);
+                { std::lock_guard<std::mutex> l(sync_mu); extracted[s] = 1; }
+                sync_cv.notify_all();
             }
-            q_track.put(-1);
         };
         auto track_stage = [&] {
-            for (;;) {
-                const int s = q_track.get();
-                if (s < 0) break;
+            for (int s = 0; s < job->n_steps; ++s) {          // Tracking takes the frames in order
+                { std::unique_lock<std::mutex> l(sync_mu); sync_cv.wait(l, [&] { return extracted[s] || failed; }); }
+                if (failed) break;
                 q_tri.put(s);
                 const double t0 = now_s();
                 track_step(s);
-                if (--users[s & 1] == 0) free_ws[s & 1].release();
+                if (--users[s % NX] == 0) release_slot(s % NX);
                 busy[1] += now_s() - t0;
             }
             q_tri.put(-1);
@@ -181,7 +188,7 @@ extern "C" int plvs_pipeline_run(plvs_orb* const ex[2], plvs_match* m_track, plv
                 if (s < 0) break;
                 const double t0 = now_s();
                 tri_step(s);
-                if (--users[s & 1] == 0) free_ws[s & 1].release();
+                if (--users[s % NX] == 0) release_slot(s % NX);
                 busy[2] += now_s() - t0;
             }
         };
@@ -191,8 +198,11 @@ extern "C" int plvs_pipeline_run(plvs_orb* const ex[2], plvs_match* m_track, plv
             map_finish();
             busy[3] = now_s() - t0;
         };
-        std::thread th[4] = {std::thread(extract_stage), std::thread(track_stage), std::thread(tri_stage), std::thread(map_stage)};
+        std::vector<std::thread> th;
+        for (int j = 0; j < n_ex_threads; ++j) th.emplace_back(extract_stage, j);
+        th.emplace_back(track_stage); th.emplace_back(tri_stage); th.emplace_back(map_stage);
         for (std::thread& x : th) x.join();
+        for (int j = 0; j < n_ex_threads; ++j) busy[0] += busy_ex[j];          // summed over the frame-construction threads
     }
     if (flush_stream) { cudaStreamSynchronize(flush_stream); cudaStreamDestroy(flush_stream); }
     out->wall_s = now_s() - t_begin;

@@ -140,5 +140,76 @@ PLVS_SORT_HD void sort(elem_t* base, int n)
     } else insertion_sort(base, 0, n);
 }
 
+// ---- the same result, computed range by range ----------------------------------------------------------------------------------------------
+// __introsort_loop recurses into [cut, last) and loops on [first, cut): two DISJOINT ranges, so the two sub-sorts commute and the recursion
+// tree can be processed level by level, every range of a level by a different thread.  __final_insertion_sort then only ever moves an element
+// inside the leaf range it ended up in (<= 16 elements, or a heap-sorted range): after a Hoare partition everything left of the cut is <= pivot
+// <= everything right of it, so `less(val, *prev)` fails at the first element of the previous leaf -- and the guarded variant used for the
+// first 16 positions moves to the front exactly when a linear insert would get there too (the prefix is sorted).  Hence: leaf-wise guarded
+// linear insertion, one thread per leaf.  tests/test_host_logic.py checks this formulation against std::sort as well.
+PLVS_SORT_HD int introsort_step(elem_t* base, int first, int last, int depth)        // one iteration of the loop on a range of > 16 elements
+{
+    if (depth == 0) { heap_sort(base + first, last - first); return -1; }          // sorted: no children
+    const int mid = first + (last - first) / 2;
+    move_median_to_first(&base[first], &base[first + 1], &base[mid], &base[last - 1]);
+    return unguarded_partition(base, first + 1, last, first);                       // children [first, cut) and [cut, last), depth - 1
+}
+
+PLVS_SORT_HD void leaf_insertion(elem_t* base, int a, int b)
+{
+    for (int i = a + 1; i < b; ++i) {
+        const elem_t val = base[i];
+        int k = i;
+        while (k > a && less_key(val, base[k - 1])) { base[k] = base[k - 1]; --k; }
+        base[k] = val;
+    }
+}
+
+PLVS_SORT_HD int depth_limit(int n) { int lg = 0; for (int t = n; t > 1; t >>= 1) ++lg; return 2 * lg; }
+
+#if defined(__CUDACC__) || defined(PLVS_CUDA_EMU)
+// std::sort on base[0..n) by a whole CTA (every thread calls it).  scratch: 2 * n ints for the leaves, 6 * (n / 16 + 2) ints for the two range
+// lists, 4 counters -- see sort_cta_scratch_ints().
+__host__ __device__ inline int sort_cta_scratch_ints(int n) { return 2 * (n + 1) + 6 * (n / 16 + 2) + 4; }
+__device__ inline void sort_cta(elem_t* base, int n, int* scratch)
+{
+    if (n <= 1) return;
+    const int tid = threadIdx.x, R = n / 16 + 2;
+    int* leaf_a = scratch; int* leaf_b = leaf_a + (n + 1);
+    int* rng[2] = {leaf_b + (n + 1), leaf_b + (n + 1) + 3 * R};
+    int* cnt = rng[1] + 3 * R;                       // [0] ranges of the current level, [1] of the next, [2] leaves
+    if (tid == 0) {
+        cnt[0] = cnt[1] = cnt[2] = 0;
+        if (n > 16) { rng[0][0] = 0; rng[0][1] = n; rng[0][2] = depth_limit(n); cnt[0] = 1; }
+        else { leaf_a[0] = 0; leaf_b[0] = n; cnt[2] = 1; }
+    }
+    __syncthreads();
+    int cur = 0;
+    for (;;) {
+        const int ncur = cnt[0];
+        if (ncur == 0) break;
+        __syncthreads();                              // everyone has read cnt[0]
+        for (int r = tid; r < ncur; r += blockDim.x) {
+            const int first = rng[cur][3 * r], last = rng[cur][3 * r + 1], depth = rng[cur][3 * r + 2];
+            const int cut = introsort_step(base, first, last, depth);
+            if (cut < 0) { const int l = atomicAdd(&cnt[2], 1); leaf_a[l] = first; leaf_b[l] = last; continue; }
+            const int lo[2] = {first, cut}, hi[2] = {cut, last};
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (hi[c] - lo[c] > 16) { const int k = atomicAdd(&cnt[1], 1); rng[cur ^ 1][3 * k] = lo[c]; rng[cur ^ 1][3 * k + 1] = hi[c]; rng[cur ^ 1][3 * k + 2] = depth - 1; }
+                else if (hi[c] - lo[c] > 1) { const int l = atomicAdd(&cnt[2], 1); leaf_a[l] = lo[c]; leaf_b[l] = hi[c]; }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { cnt[0] = cnt[1]; cnt[1] = 0; }
+        cur ^= 1;
+        __syncthreads();
+    }
+    const int nleaf = cnt[2];
+    for (int l = tid; l < nleaf; l += blockDim.x) leaf_insertion(base, leaf_a[l], leaf_b[l]);
+    __syncthreads();
+}
+#endif
+
 }  // namespace stdsort
 }  // namespace plvs

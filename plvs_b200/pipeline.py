@@ -75,6 +75,7 @@ class HotPath:
         self.ex = ORBextractor(nfeatures, 1.2, 8, 20, 7, device=device)
         self.ex.set_frame_grid(data.w, data.h)      # frame construction ends with AssignFeaturesToGrid (src/Frame.cc:598)
         self.ex2 = None           # second extractor workspace, created by run_stream (batch k+1 extracts while batch k is matched)
+        self.ex_more = []         # further extractor handles of the native driver (two frame-construction threads)
         self.m_track = ORBmatcher(0.9, True, device=device)      # TrackWithMotionModel (src/Tracking.cc:3593)
         self.m_map = ORBmatcher(0.8, True, device=device)        # SearchLocalPoints (src/Tracking.cc:4477)
         self.m_tri = ORBmatcher(0.6, False, device=device)       # CreateNewMapFeatures (src/LocalMapping.cc:537)
@@ -381,9 +382,15 @@ class HotPath:
         job.th_last, job.th_map, job.nnratio_map = 15.0, 3.0, 0.8
         if flush is not None:
             job.flush_buf, job.flush_bytes = flush
-        exs = (C.c_void_p * 2)(self.ex._h.value, self.ex2._h.value)
+        # extractor handles: 2 = one frame-construction thread (batch k+1 extracts while batch k is matched); 4 (default) = two threads on alternate batches
+        n_ex = max(2, int(os.environ.get("PLVS_PIPELINE_EXTRACTORS", "4")) & ~1)
+        while len(self.ex_more) < n_ex - 2:
+            e = ORBextractor(self.ex.nfeatures, 1.2, 8, 20, 7, device=self.device)
+            e.set_frame_grid(self.d.w, self.d.h)
+            self.ex_more.append(e)
+        exs = (C.c_void_p * n_ex)(self.ex._h.value, self.ex2._h.value, *[e._h.value for e in self.ex_more[:n_ex - 2]])
         st = _lib.PipelineStats()
-        rc = self.ex._lib.plvs_pipeline_run(exs, self.m_track._h, self.m_tri._h, self.tsdf._h, C.byref(job), C.byref(st))
+        rc = self.ex._lib.plvs_pipeline_run(exs, n_ex, self.m_track._h, self.m_tri._h, self.tsdf._h, C.byref(job), C.byref(st))
         _lib.check(rc, "plvs_pipeline_run")
         return dict(keypoints=st.keypoints, matches=st.matches, busy_extract_s=st.busy_extract_s, busy_track_s=st.busy_track_s,
                     busy_tri_s=st.busy_tri_s, busy_map_s=st.busy_map_s, wall_s=st.wall_s)

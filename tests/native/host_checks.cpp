@@ -34,6 +34,37 @@ int chk_stdsort(int n, const uint32_t* keys, int* order_out)
     return bad;
 }
 
+// the range-by-range formulation the device runs (stdsort_emul.cuh: introsort_step per range, level by level, then leaf-wise insertion) vs std::sort
+int chk_stdsort_ranges(int n, const uint32_t* keys)
+{
+    using namespace plvs::stdsort;
+    std::vector<std::pair<uint32_t, int>> ref(n);
+    std::vector<elem_t> em(n);
+    for (int i = 0; i < n; ++i) { ref[i] = std::make_pair(keys[i], i); em[i] = ((elem_t)keys[i] << 32) | (uint32_t)i; }
+    std::sort(ref.begin(), ref.end(), [](const std::pair<uint32_t, int>& a, const std::pair<uint32_t, int>& b) { return a.first < b.first; });
+    struct R { int first, last, depth; };
+    std::vector<R> cur, next; std::vector<std::pair<int, int>> leaves;
+    if (n > 16) cur.push_back(R{0, n, depth_limit(n)}); else if (n > 1) leaves.push_back(std::make_pair(0, n));
+    while (!cur.empty()) {
+        next.clear();
+        for (size_t r = cur.size(); r-- > 0;) {                 // any order inside a level: here back to front
+            const R g = cur[r];
+            const int cut = introsort_step(em.data(), g.first, g.last, g.depth);
+            if (cut < 0) { leaves.push_back(std::make_pair(g.first, g.last)); continue; }
+            const int lo[2] = {g.first, cut}, hi[2] = {cut, g.last};
+            for (int c = 0; c < 2; ++c) {
+                if (hi[c] - lo[c] > 16) next.push_back(R{lo[c], hi[c], g.depth - 1});
+                else if (hi[c] - lo[c] > 1) leaves.push_back(std::make_pair(lo[c], hi[c]));
+            }
+        }
+        cur.swap(next);
+    }
+    for (size_t l = leaves.size(); l-- > 0;) leaf_insertion(em.data(), leaves[l].first, leaves[l].second);
+    int bad = 0;
+    for (int i = 0; i < n; ++i) if ((int)(uint32_t)em[i] != ref[i].second) ++bad;
+    return bad;
+}
+
 // sweep floats in [lo_bits, hi_bits] with the given stride; returns the number of (cos,sin) mismatches vs libm
 long chk_sincosf_sweep(uint32_t lo_bits, uint32_t hi_bits, uint32_t stride, float* first_bad)
 {

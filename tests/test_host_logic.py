@@ -72,10 +72,12 @@ def test_stdsort_emulation_matches_libstdcxx_on_ties(host):
             keys = (rng.integers(2, 30, n) << 16) | rng.integers(0, 600, n)   # (size, UL.x) like the real use
         keys = np.ascontiguousarray(keys, np.uint32)
         assert host.chk_stdsort(n, keys.ctypes.data_as(C.c_void_p), None) == 0, (trial, n)
+        assert host.chk_stdsort_ranges(n, keys.ctypes.data_as(C.c_void_p)) == 0, ("range by range", trial, n)
     # adversarial for median-of-3 quicksort: organ-pipe and many-duplicates inputs big enough to hit the heapsort fallback
     for n in (5000, 20000):
         pipe = np.concatenate([np.arange(n // 2), np.arange(n // 2)[::-1]]).astype(np.uint32)
         assert host.chk_stdsort(len(pipe), pipe.ctypes.data_as(C.c_void_p), None) == 0
+        assert host.chk_stdsort_ranges(len(pipe), pipe.ctypes.data_as(C.c_void_p)) == 0
 
 
 def test_sincosf_port_equals_libm_exhaustively(host):
