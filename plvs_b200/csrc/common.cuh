@@ -87,8 +87,10 @@ inline cudaError_t create_handle_stream(cudaStream_t* st, int rank)
     const bool orb_first = o && o[0] == 'o';
     // numerically lower = higher priority; spread the three ranks over the available range
     const int mid = (least + greatest) / 2;
+    const bool tsdf_first = o && o[0] == 't';          // PLVS_STREAM_ORDER=tsdf: TSDF > matcher > extractor (A/B aid)
     int prio;
-    if (rank == 2) prio = greatest;
+    if (tsdf_first) prio = rank == 0 ? greatest : rank == 2 ? mid : least;
+    else if (rank == 2) prio = greatest;
     else if (rank == 1) prio = orb_first ? mid : least;
     else prio = orb_first ? least : mid;
     return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio);

@@ -575,17 +575,23 @@ k_resolve_cta(const uint32_t* __restrict__ cand, const int* __restrict__ cand_n,
         { const long long t = clock64(); t_b += t - t_mark; t_mark = t; }
         { int* t = cur; cur = nxt; nxt = t; }
         bool changed = false;
-        for (int q = tid; q < nq; q += nthr) {
-            const uint4 raw = reinterpret_cast<const uint4*>(s_watch)[q];                 // kp[0..5] | n, blocked, m
+        for (int q0 = 0; q0 < nq; q0 += nthr) {
+            const int q = q0 + tid;
+            const uint4 raw = q < nq ? reinterpret_cast<const uint4*>(s_watch)[q] : make_uint4(0u, 0u, 0u, 0u);                 // kp[0..5] | n, blocked, m
             const uint32_t wn = raw.w & 0xffu, wb = (raw.w >> 8) & 0xffu;
             bool walk = wn == 255u;
-            if (!walk) {
+            if (!walk && q < nq) {
                 const uint32_t kp[kWatch] = {raw.x & 0xffffu, raw.x >> 16, raw.y & 0xffffu, raw.y >> 16, raw.z & 0xffffu, raw.z >> 16};
 #pragma unroll
                 for (int j = 0; j < kWatch; ++j)
                     if ((uint32_t)j < wn) walk |= ((cur[kp[j]] < q) != (((wb >> j) & 1u) != 0u));
             }
-            if (walk) s_wlist[atomicAdd(&s_nwalk, 1)] = q;          // order irrelevant: an evaluation reads `cur` and writes its own records only
+            // queue up (order irrelevant: an evaluation reads `cur` and writes its own records only); one shared-memory atomic per warp
+            const uint32_t wm = __ballot_sync(0xffffffffu, walk);
+            int wbase = 0;
+            if (lane32 == 0 && wm) wbase = atomicAdd(&s_nwalk, __popc(wm));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (walk) s_wlist[wbase + __popc(wm & ((1u << lane32) - 1))] = q;
         }
         for (int i = tid; i < n; i += nthr) nxt[i] = nxt[i] < 0 ? -1 : INF;
         __syncthreads();
