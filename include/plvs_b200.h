@@ -59,6 +59,7 @@ int plvs_set_profiling(int mask);
 #define PLVS_MATCH_K_FUSE 4
 #define PLVS_MATCH_K_BOW 5
 #define PLVS_MATCH_K_INIT 6
+#define PLVS_MATCH_K_LINES 7
 #define PLVS_TSDF_K_TILES 0
 #define PLVS_TSDF_K_CLASSIFY 1
 #define PLVS_TSDF_K_INTEGRATE 2
@@ -408,6 +409,17 @@ int plvs_match_fuse_sim3(plvs_match* h, const plvs_frame_view* kf, const plvs_fu
  * them from mObservations), offsets[n_points+1] = start of each point's run.  best[i] = index INSIDE the run of the descriptor
  * with the least median distance to the others (median = sorted[0.5*(N-1)], first minimum wins), -1 for an empty run. */
 int plvs_distinctive_descriptors(plvs_match* h, const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best);
+
+/* SURVEY.md §8f rank 4, line features, the matcher's data-parallel part: LineMatcher::ComputeDescriptorMatches (src/LineMatcher.cc:2567-2615) =
+ * cv::line_descriptor_c::BinaryDescriptorMatcher::knnMatch(query, train, lmatches, 2, queryMask, true)
+ * (Thirdparty/line_descriptor/src/binary_descriptor_matcher_custom.cpp:258-337) + the ratio test `d0 < nn_ratio * d1`.
+ * query / train: nq / nt 256-bit LBD descriptors (32 bytes each, host); mask: nq bytes or NULL (0 = the query is skipped; compact result: it gets no
+ * row).  Per row r (the queries with a non-zero mask entry, in order): query_idx[r], train_idx[2r], train_idx[2r+1] (nearest, second nearest -- among
+ * equal Hamming distances in the order the library's multi-index hashing returns them), dist[2r], dist[2r+1] (Hamming distances as float, like
+ * DMatch::distance), valid[r] = vValidMatch.  Output arrays hold nq rows.  Needs nt >= 2 (with fewer train descriptors than k the reference returns
+ * uninitialised indices). */
+int plvs_line_knn2(plvs_match* h, const uint8_t* query, int nq, const uint8_t* train, int nt, const uint8_t* mask, float nn_ratio,
+                   int32_t* query_idx, int32_t* train_idx, float* dist, uint8_t* valid, int* n_rows, int* n_valid);
 
 /* Device view of one frame's pyramid (all levels) of an extractor handle: what Frame::ComputeStereoMatches
  * reads through mpORBextractorLeft/Right->mvImagePyramid (src/Frame.cc:1886,1914). */

@@ -1,0 +1,2 @@
+// stand-in: see opencv2/opencv.hpp
+#include "opencv.hpp"

@@ -120,7 +120,36 @@ public:
     template <typename T> const T* ptr(int i = 0) const { return (const T*)(data + (size_t)i * step); }
     template <typename T> T& at(int y, int x) { return *(T*)(data + (size_t)y * step + (size_t)x * sizeof(T)); }
     template <typename T> const T& at(int y, int x) const { return *(const T*)(data + (size_t)y * step + (size_t)x * sizeof(T)); }
+    // single index: element i of a row or column vector (the query masks of the line matcher are n x 1)
+    template <typename T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+    template <typename T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+    // append the rows of m (8-bit, same width): BinaryDescriptorMatcher::add, not on any path the harnesses call
+    void push_back(const Mat& m)
+    {
+        if (m.empty()) return;
+        Mat out(rows + m.rows, m.cols, CV_8UC1);
+        for (int y = 0; y < rows; ++y) std::memcpy(out.data + (size_t)y * out.step, data + (size_t)y * step, (size_t)cols);
+        for (int y = 0; y < m.rows; ++y) std::memcpy(out.data + (size_t)(rows + y) * out.step, m.data + (size_t)y * m.step, (size_t)m.cols);
+        *this = out;
+    }
 };
+
+// bookkeeping types Thirdparty/line_descriptor's matcher needs besides Mat (oracle/ref_build.py::build_linematch)
+class Algorithm { public: virtual ~Algorithm() {} };
+struct DMatch {
+    int queryIdx, trainIdx, imgIdx; float distance;
+    DMatch() : queryIdx(-1), trainIdx(-1), imgIdx(-1), distance(3.4028235e38f) {}
+    DMatch(int q, int t, float d) : queryIdx(q), trainIdx(t), imgIdx(-1), distance(d) {}
+};
+template <class T> class Ptr : public std::shared_ptr<T> {
+public:
+    Ptr() {}
+    explicit Ptr(T* p) : std::shared_ptr<T>(p) {}
+    Ptr(const std::shared_ptr<T>& p) : std::shared_ptr<T>(p) {}
+    void release() { this->reset(); }
+    bool empty() const { return !*this; }
+};
+template <class T, class... A> inline Ptr<T> makePtr(A&&... a) { return Ptr<T>(new T(std::forward<A>(a)...)); }
 
 // cv::InputArray / cv::OutputArray are `const _InputArray&` / `const _OutputArray&` in OpenCV too
 class _InputArray {

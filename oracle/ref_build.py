@@ -226,3 +226,51 @@ def build_bow(force=False):
     flags = ["-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w", "-I", str(HERE / "cv_standin"), "-I", str(ref / "DBoW2"), "-I", str(ref)]
     subprocess.check_call(["g++"] + flags + ["-shared", "-o", str(BOW_OUT)] + [str(x) for x in srcs] + ["-lm"])
     return str(BOW_OUT)
+
+
+LINEMATCH_OUT = OUTDIR / "liblinematch_ref.so"
+
+
+def _slice_class(text, head):
+    """the class declaration that starts with `head` up to the `};` that closes it"""
+    a = text.index(head)
+    i = text.index("{", a)
+    depth = 0
+    for j in range(i, len(text)):
+        if text[j] == "{":
+            depth += 1
+        elif text[j] == "}":
+            depth -= 1
+            if depth == 0:
+                return text[a:text.index(";", j) + 1]
+    raise ValueError(head)
+
+
+def build_linematch(force=False):
+    """Thirdparty/line_descriptor/src/binary_descriptor_matcher_custom.cpp (multi-index hashing k-NN over 256-bit LBD descriptors, what
+    LineMatcher::ComputeDescriptorMatches calls, src/LineMatcher.cc:2572) + oracle/ref_linematch_harness.cpp -> oracle/_ref/liblinematch_ref.so.
+    The .cpp is compiled unmodified where it lies.  Its header (descriptor_custom.hpp) also declares the LSD / LBD extractor classes, which need
+    half of OpenCV: the build writes a `line_descriptor_custom.hpp` holding only the text of `class BinaryDescriptorMatcher` (sliced out at build
+    time into the git-ignored oracle/_ref/gen/, deleted afterwards) and puts it first on the include path."""
+    ref = pathlib.Path("/root/reference/Thirdparty/line_descriptor")
+    src = ref / "src" / "binary_descriptor_matcher_custom.cpp"
+    if not src.exists():
+        return str(LINEMATCH_OUT) if LINEMATCH_OUT.exists() else None
+    hdr = ref / "include" / "line_descriptor" / "descriptor_custom.hpp"
+    deps = [src, hdr, HERE / "ref_linematch_harness.cpp", HERE / "cv_standin" / "opencv2" / "opencv.hpp"]
+    if LINEMATCH_OUT.exists() and not force and all(LINEMATCH_OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return str(LINEMATCH_OUT)
+    gen = OUTDIR / "gen_linematch"
+    gen.mkdir(parents=True, exist_ok=True)
+    decl = _slice_class(hdr.read_text(), "class CV_EXPORTS BinaryDescriptorMatcher")
+    (gen / "line_descriptor_custom.hpp").write_text(
+        "// generated at build time from /root/reference/Thirdparty/line_descriptor/include/line_descriptor/descriptor_custom.hpp -- do not commit\n"
+        "#pragma once\n#include <map>\n#include <vector>\n#include <cmath>\n#include <cstring>\n#include <opencv2/opencv.hpp>\n"
+        "#include \"types_custom.hpp\"\n#ifndef CV_EXPORTS\n#define CV_EXPORTS\n#endif\n"
+        "namespace cv { namespace line_descriptor_c {\n" + decl + "\n} }\n")
+    flags = ["-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w", "-I", str(gen), "-I", str(HERE / "cv_standin"), "-I", str(ref / "src")]
+    try:
+        subprocess.check_call(["g++"] + flags + ["-shared", "-o", str(LINEMATCH_OUT), str(src), str(HERE / "ref_linematch_harness.cpp"), "-lm"])
+    finally:
+        shutil.rmtree(gen, ignore_errors=True)
+    return str(LINEMATCH_OUT)

@@ -122,6 +122,8 @@ def declare(lib):
     lib.plvs_orb_device_result.argtypes = [C.c_void_p, C.c_int, C.POINTER(OrbDeviceView)]
     lib.plvs_orb_set_frame_grid.argtypes = [C.c_void_p, C.c_void_p]
     lib.plvs_match_last_phase_cycles.argtypes = [C.c_void_p, C.c_void_p]
+    lib.plvs_line_knn2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.plvs_orb_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.plvs_orb_last_stats.argtypes = [C.c_void_p, C.POINTER(OrbStats)]
     lib.plvs_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]

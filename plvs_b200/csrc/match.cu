@@ -20,6 +20,7 @@ using namespace plvs;
 namespace {
 
 #include "match_common.cuh"
+#include "match_lines.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Phase A (both projection searches): one warp per query walks the window column by column
@@ -1074,6 +1075,9 @@ struct plvs_match {
     bool state_zeroed = false;
     int last_phase[4] = {0, 0, 0, 0};                    // SM cycles of the last one-CTA resolve: claim table, watch-set compare, re-evaluations, rounds + wrap-up
     bool use_pdl = true;                                 // k_resolve_cta as a programmatic dependent launch behind k_candidates (PLVS_MATCH_PDL=0: plain)
+    DevBuf<unsigned long long> d_line_best;              // plvs_line_knn2: the two smallest keys per query
+    DevBuf<int> d_line_rank; bool line_rank_ready = false;
+    DevBuf<uint8_t> d_line_u8; DevBuf<float> d_line_f32;
     int resolve_threads = 1024;                          // CTA size of k_resolve_cta (PLVS_MATCH_RESOLVE_THREADS: 256 / 512 / 1024)
     DevBuf<Round0> d_round0;                              // per query: what round 0 of the claim resolution leaves (written by k_candidates)
     int last_walks = 0;                                   // list re-evaluations of the last search after round 0 (statistics)
@@ -1696,6 +1700,77 @@ int plvs_distinctive_descriptors(plvs_match* h, const uint8_t* desc, const int32
     PLVS_CUDA(cudaStreamSynchronize(st));
     std::memcpy(best, h->p_assign.h, (size_t)n_points * 4);
     h->last_launches = 1;
+    return PLVS_OK;
+}
+
+// position of every 8-bit string in Mihasher::query's enumeration of the strings with the same number of ones
+// (Thirdparty/line_descriptor/src/binary_descriptor_matcher_custom.cpp:683-760: its `power` / `bit` walk), replayed once on the host
+static void line_enumeration_rank(int rank[256])
+{
+    const int curb = 8;
+    for (int s = 0; s <= 8; ++s) {
+        int power[16] = {0}; unsigned bitstr = 0;
+        for (int i = 0; i < s; ++i) power[i] = i;
+        power[s] = curb + 1;
+        int bit = s - 1, r = 0;
+        for (;;) {
+            if (bit != -1) {
+                bitstr ^= (power[bit] == bit) ? (1u << power[bit]) : (3u << (power[bit] - 1));
+                power[bit]++; bit--;
+            } else {
+                rank[bitstr & 0xffu] = r++;
+                while (++bit < s && power[bit] == power[bit + 1] - 1) { bitstr ^= 1u << (power[bit] - 1); power[bit] = bit; }
+                if (bit == s) break;
+            }
+        }
+    }
+}
+
+int plvs_line_knn2(plvs_match* h, const uint8_t* query, int nq, const uint8_t* train, int nt, const uint8_t* mask, float nn_ratio,
+                   int32_t* query_idx, int32_t* train_idx, float* dist, uint8_t* valid, int* n_rows, int* n_valid)
+{
+    if (!h || !n_rows || nq < 0 || nt < 0 || (nq && (!query || !query_idx || !train_idx || !dist || !valid)) || (nt && !train)) { set_error("null argument"); return PLVS_EINVAL; }
+    *n_rows = 0; if (n_valid) *n_valid = 0;
+    if (nq == 0 || nt == 0) { set_error("descriptors matrices cannot be void"); return PLVS_EINVAL; }          // the reference prints this and returns no matches (:262-266)
+    if (nt < 2) { set_error("fewer train descriptors than k = 2: the reference returns uninitialised indices"); return PLVS_EINVAL; }
+    if (nt >= (1 << 20)) { set_error("more than 2^20 train descriptors are not supported"); return PLVS_ECAP; }
+    std::lock_guard<std::mutex> lock(h->mu);
+    PLVS_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    int rc;
+    if ((rc = h->d_line_rank.alloc(256)) || (rc = h->d_line_best.alloc((size_t)2 * nq)) || (rc = h->d_line_u8.alloc((size_t)32 * (nq + nt) + 2 * (size_t)nq)) ||
+        (rc = h->d_line_f32.alloc((size_t)2 * nq)) || (rc = h->d_assign.alloc((size_t)3 * nq + 2)) || (rc = h->p_result.alloc(8))) return rc;
+    if (!h->line_rank_ready) {
+        int rank[256];
+        line_enumeration_rank(rank);
+        PLVS_CUDA(cudaMemcpyAsync(h->d_line_rank.p, rank, sizeof(rank), cudaMemcpyHostToDevice, st));
+        PLVS_CUDA(cudaStreamSynchronize(st));       // `rank` is a local
+        h->line_rank_ready = true;
+    }
+    uint8_t* d_q = h->d_line_u8.p; uint8_t* d_t = d_q + (size_t)32 * nq; uint8_t* d_mask = d_t + (size_t)32 * nt; uint8_t* d_valid = d_mask + nq;
+    PLVS_CUDA(cudaMemcpyAsync(d_q, query, (size_t)32 * nq, cudaMemcpyHostToDevice, st));
+    PLVS_CUDA(cudaMemcpyAsync(d_t, train, (size_t)32 * nt, cudaMemcpyHostToDevice, st));
+    if (mask) PLVS_CUDA(cudaMemcpyAsync(d_mask, mask, (size_t)nq, cudaMemcpyHostToDevice, st));
+    int32_t* d_qidx = h->d_assign.p; int32_t* d_tidx = d_qidx + nq; int* d_res = d_tidx + 2 * (size_t)nq;
+    h->timer.begin(PLVS_MATCH_K_LINES, st);
+    k_line_knn2<<<div_up(nq, 8), 256, 0, st>>>(d_q, nq, d_t, nt, h->d_line_rank.p, h->d_line_best.p);
+    k_line_rows<<<1, 1024, 0, st>>>(h->d_line_best.p, nq, mask ? d_mask : nullptr, nn_ratio, d_qidx, d_tidx, h->d_line_f32.p, d_valid, d_res);
+    h->timer.end(st);
+    PLVS_CUDA(cudaGetLastError());
+    PLVS_CUDA(cudaMemcpyAsync(h->p_result.h, d_res, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PLVS_CUDA(cudaStreamSynchronize(st));
+    const int rows = h->p_result.h[0];
+    if (rows > 0) {
+        PLVS_CUDA(cudaMemcpyAsync(query_idx, d_qidx, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
+        PLVS_CUDA(cudaMemcpyAsync(train_idx, d_tidx, (size_t)rows * 8, cudaMemcpyDeviceToHost, st));
+        PLVS_CUDA(cudaMemcpyAsync(dist, h->d_line_f32.p, (size_t)rows * 8, cudaMemcpyDeviceToHost, st));
+        PLVS_CUDA(cudaMemcpyAsync(valid, d_valid, (size_t)rows, cudaMemcpyDeviceToHost, st));
+        PLVS_CUDA(cudaStreamSynchronize(st));
+    }
+    h->timer.collect();
+    *n_rows = rows; if (n_valid) *n_valid = h->p_result.h[1];
+    h->grid_key = 0; h->grid_n = -1;
+    h->last_launches = 2;
     return PLVS_OK;
 }
 

@@ -288,6 +288,28 @@ class ORBmatcher:
         return nm.value, m12[:KF1.n]
 
 
+class LineMatcher:
+    """The data-parallel part of PLVS2::LineMatcher (include/LineMatcher.h): ComputeDescriptorMatches = 2-NN over 256-bit LBD descriptors with the
+    tie order of the vendored multi-index hashing + the ratio test (src/LineMatcher.cc:2567-2615)."""
+
+    def __init__(self, nnratio=0.78, device=0):
+        self._m = ORBmatcher(nnratio, False, device=device)
+        self.mfNNratio = float(nnratio)
+
+    def ComputeDescriptorMatches(self, ldesc_q, ldesc_t, queryMask=None):
+        """-> (numValidMatches, query_idx[M], train_idx[M, 2], distance[M, 2], vValidMatch[M]): lmatches[i] = (DMatch(query_idx[i], train_idx[i, 0], distance[i, 0]),
+        DMatch(query_idx[i], train_idx[i, 1], distance[i, 1]))"""
+        q = np.ascontiguousarray(ldesc_q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(ldesc_t, np.uint8).reshape(-1, 32)
+        nq = len(q)
+        mk = None if queryMask is None else np.ascontiguousarray(queryMask, np.uint8).reshape(-1)
+        qi = np.zeros(max(nq, 1), np.int32); ti = np.zeros((max(nq, 1), 2), np.int32); di = np.zeros((max(nq, 1), 2), np.float32); vi = np.zeros(max(nq, 1), np.uint8)
+        rows, nv = C.c_int(), C.c_int()
+        _lib.check(self._m._lib.plvs_line_knn2(self._m._h, q.ctypes.data, nq, t.ctypes.data, len(t), None if mk is None else mk.ctypes.data, self.mfNNratio,
+                                               qi.ctypes.data, ti.ctypes.data, di.ctypes.data, vi.ctypes.data, C.byref(rows), C.byref(nv)), "plvs_line_knn2")
+        m = rows.value
+        return nv.value, qi[:m].copy(), ti[:m].copy(), di[:m].copy(), vi[:m].copy()
+
+
 def ComputeStereoMatches(matcher, left, right, pyr_left, pyr_right, inv_scale, mb, mbf):
     """Frame::ComputeStereoMatches (src/Frame.cc:1780): left/right are Frame views whose keys are mvKeys / mvKeysRight,
     pyr_* the extractors' device pyramid views.  Returns (mvuRight, mvDepth, number of stereo points kept)."""

@@ -721,6 +721,45 @@ private:
     std::vector<uint8_t> desc_; std::vector<uint32_t> bowIds_, fvNodes_; std::vector<double> bowVals_; std::vector<int32_t> fvOff_, fvFeat_;
 };
 
+// ------------------------------------------------------------------------------------------------------
+// LineMatcher::ComputeDescriptorMatches (include/LineMatcher.h, src/LineMatcher.cc:2567-2615): the k = 2 nearest LBD descriptors per query line
+// with the neighbour order of the vendored multi-index hashing (Thirdparty/line_descriptor), then the ratio test.  The rest of LineMatcher (the
+// geometric gates of SearchByKnn / SearchForTriangulation) stays in the reference's file and calls this instead of mBdm->knnMatch + the loop.
+// DMatchT = cv::DMatch (queryIdx, trainIdx, imgIdx, distance).
+class LineDescriptorMatcher {
+public:
+    explicit LineDescriptorMatcher(float nnratio = 0.78f, int device = 0) : mfNNratio(nnratio) { plvs_shim::check(plvs_match_create(device, &h_), "plvs_match_create"); }
+    ~LineDescriptorMatcher() { if (h_) plvs_match_destroy(h_); }
+    LineDescriptorMatcher(const LineDescriptorMatcher&) = delete;
+    template <class DMatchT>
+    int ComputeDescriptorMatches(const cv::Mat& ldesc_q, const cv::Mat& ldesc_t, const cv::Mat& queryMask, std::vector<std::vector<DMatchT> >& lmatches, std::vector<bool>& vValidMatch)
+    {
+        lmatches.clear(); vValidMatch.clear();
+        const int nq = ldesc_q.rows, nt = ldesc_t.rows;
+        if (nq == 0 || nt < 2) return 0;            // the reference prints an error for empty matrices; with one train descriptor its result is undefined
+        q_.resize((size_t)nq * 32); t_.resize((size_t)nt * 32); m_.assign((size_t)nq, 1);
+        for (int i = 0; i < nq; ++i) std::memcpy(&q_[(size_t)i * 32], ldesc_q.data + (size_t)i * ldesc_q.step, 32);
+        for (int i = 0; i < nt; ++i) std::memcpy(&t_[(size_t)i * 32], ldesc_t.data + (size_t)i * ldesc_t.step, 32);
+        const bool masked = !queryMask.empty();
+        if (masked) for (int i = 0; i < nq; ++i) m_[i] = queryMask.data[(size_t)i * queryMask.step];
+        qi_.resize(nq); ti_.resize((size_t)2 * nq); d_.resize((size_t)2 * nq); v_.resize(nq);
+        int rows = 0, nvalid = 0;
+        plvs_shim::check(plvs_line_knn2(h_, q_.data(), nq, t_.data(), nt, masked ? m_.data() : nullptr, mfNNratio, qi_.data(), ti_.data(), d_.data(), v_.data(), &rows, &nvalid),
+                         "plvs_line_knn2");
+        lmatches.resize(rows); vValidMatch.resize(rows);
+        for (int r = 0; r < rows; ++r) {
+            lmatches[r].resize(2);
+            for (int k = 0; k < 2; ++k) { DMatchT& dm = lmatches[r][k]; dm.queryIdx = qi_[r]; dm.trainIdx = ti_[2 * r + k]; dm.imgIdx = 0; dm.distance = d_[2 * r + k]; }
+            vValidMatch[r] = v_[r] != 0;
+        }
+        return nvalid;
+    }
+    float mfNNratio;
+private:
+    plvs_match* h_ = nullptr;
+    std::vector<uint8_t> q_, t_, m_, v_; std::vector<int32_t> qi_, ti_; std::vector<float> d_;
+};
+
 }  // namespace PLVS2
 
 // ------------------------------------------------------------------------------------------------------

@@ -95,6 +95,11 @@ extern "C" int shim_instantiate(int run)
     PLVS2::ORBVocabulary voc; voc.loadFromTextFile("ORBvoc.txt");
     std::map<unsigned, double> bowVec; std::map<unsigned, std::vector<unsigned>> featVec; std::vector<cv::Mat> vDesc(1, cv::Mat(1, 32, CV_8U));
     voc.transform(vDesc, bowVec, featVec, 4); c += (int)voc.size();
+    struct DMatchS { int queryIdx, trainIdx, imgIdx; float distance; };
+    PLVS2::LineDescriptorMatcher lmx(0.78f);
+    cv::Mat lq(5, 32, CV_8U), lt(7, 32, CV_8U), lmask(5, 1, CV_8U);
+    std::vector<std::vector<DMatchS> > lmatches; std::vector<bool> lvalid;
+    c += lmx.ComputeDescriptorMatches(lq, lt, lmask, lmatches, lvalid);
     chisel_server::ChiselServerParams p; chisel_server::ChiselServer cs(p);
     cs.SetDepthCameraInfo(500, 500, 320, 240, 640, 480);
     Eigen::Affine3f T; cs.SetDepthPose(T);

@@ -353,7 +353,7 @@ def test_gpu_tests_replayed_on_the_cpu_model(product_bound_to_emulated_units, mo
 
 @pytest.mark.parametrize("name", ["_impl_tsdf_from_raw_u16_depth", "_impl_mesh_read_out", "_impl_search_for_initialization", "_impl_search_local_points_resident",
                                   "_impl_bow_transform", "_impl_undistort_keypoints_on_device", "_impl_reference_goldens", "_impl_keyframe_ids", "_impl_deform",
-                                  "_impl_world_cloud"])
+                                  "_impl_world_cloud", "_impl_line_knn2"])
 def test_unverified_gpu_tests_replayed_on_the_cpu_model(product_bound_to_emulated_units, tmp_path, name):
     """the bodies of tests/test_gpu_widened.py (the rows that have not met a GPU), unchanged, against the emulated translation units: entry points,
     host sequencing and kernels of the 16-bit depth path, the mesh read-out, SearchForInitialization, the resident SearchLocalPoints, the BoW

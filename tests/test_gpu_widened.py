@@ -414,3 +414,45 @@ def _impl_world_cloud():
 
 def test_world_cloud(gpu):
     _isolated("_impl_world_cloud")
+
+
+def _impl_line_knn2():
+    """§8f rank 4, line features: LineMatcher::ComputeDescriptorMatches -- the 2-NN of the vendored multi-index hashing (tie order included) and the
+    ratio test -- against the restatement, against the golden recorded from the compiled reference, and against that library itself where it travelled"""
+    import pathlib
+    from plvs_b200.matcher import LineMatcher
+    from oracle import linematch as L
+    from tests.linematch_cases import cases
+    lm = LineMatcher(0.78)
+    ties = 0
+    for q, t, mask in cases(40, seed=1, nq_max=300, nt_max=400):
+        nv, qi, ti, di, vi = lm.ComputeDescriptorMatches(q, t, mask)
+        a = L.knn2(q, t, mask, 0.78)
+        assert np.array_equal(qi, a[0]) and np.array_equal(ti, a[1]) and np.array_equal(di, a[2]) and np.array_equal(vi, a[3]) and nv == a[4]
+        ties += int(np.sum(di[:, 0] == di[:, 1]))
+    assert ties > 100
+    g = np.load(pathlib.Path(__file__).parent / "golden" / "linematch_ref.npz")
+    for i, (q, t, mask) in enumerate(cases(int(g["n_cases"]), seed=int(g["seed"]))):
+        nv, qi, ti, di, vi = lm.ComputeDescriptorMatches(q, t, mask)
+        assert np.array_equal(qi, g[f"qi{i}"]) and np.array_equal(ti, g[f"ti{i}"]) and np.array_equal(di, g[f"di{i}"]) and np.array_equal(vi, g[f"vi{i}"])
+    try:
+        R = L.RefLineMatcher()
+    except Exception:
+        R = None
+    if R is not None:                 # oracle/_ref travels to the GPU box
+        for q, t, mask in cases(8, seed=9, nq_max=500, nt_max=600):
+            nv, qi, ti, di, vi = lm.ComputeDescriptorMatches(q, t, mask)
+            b = R.knn2(q, t, mask, 0.78)
+            assert np.array_equal(qi, b[0]) and np.array_equal(ti, b[1]) and np.array_equal(di, b[2]) and np.array_equal(vi, b[3]) and nv == b[4]
+    # error behaviour: empty inputs and fewer train descriptors than k are refused, nothing is written
+    import ctypes as C
+    from plvs_b200 import _lib
+    rows, nvv = C.c_int(7), C.c_int(7)
+    z = np.zeros((4, 32), np.uint8); o = np.zeros(16, np.int32); f = np.zeros(16, np.float32); u = np.zeros(8, np.uint8)
+    for nq_, nt_ in ((0, 4), (4, 0), (4, 1)):
+        rc = lm._m._lib.plvs_line_knn2(lm._m._h, z.ctypes.data, nq_, z.ctypes.data, nt_, None, 0.78, o.ctypes.data, o.ctypes.data, f.ctypes.data, u.ctypes.data, C.byref(rows), C.byref(nvv))
+        assert rc == -1 and rows.value == 0          # PLVS_EINVAL
+
+
+def test_line_knn2(gpu):
+    _impl_line_knn2()
