@@ -118,7 +118,11 @@ __device__ inline void quadrant_counts(const uint32_t* __restrict__ cand, int n,
     __syncthreads();
     const int* __restrict__ nof = D.node_of[0];
     const DNode* __restrict__ nodes = D.nodes;
-    for (int p0 = tid; p0 < n; p0 += 4 * T) {            // four candidates per thread and step: their dependent loads are in flight together
+    // With few parents thousands of candidates hit a handful of counters: the lanes of a warp that hit the same one are found with MATCH.ANY and
+    // their leader adds the group's size (same-address shared-memory atomics serialise)
+    const bool aggregate = nparents <= 64;
+    for (int pb = 0; pb < n; pb += 4 * T) {              // four candidates per thread and step: their dependent loads are in flight together
+        const int p0 = pb + tid;
         int k[4]; uint32_t c[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) { const int p = p0 + u * T; k[u] = p < n ? nof[p] : -1; c[u] = p < n ? cand[p] : 0u; }
@@ -129,8 +133,13 @@ __device__ inline void quadrant_counts(const uint32_t* __restrict__ cand, int n,
             if (k[u] >= 0) { const uint32_t* nw32 = reinterpret_cast<const uint32_t*>(&nodes[k[u]]); bd[u] = make_uint2(nw32[0], nw32[1]); tg[u] = nodes[k[u]].tag; sl[u] = nodes[k[u]].slot; }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (tg[u] == tag) atomicAdd(&cnt[4 * sl[u] + quadrant_of_packed(bd[u], unpack_x(c[u]) - kRoiMargin, unpack_y(c[u]) - kRoiMargin)], 1);
+        for (int u = 0; u < 4; ++u) {
+            const int key = tg[u] == tag ? 4 * sl[u] + quadrant_of_packed(bd[u], unpack_x(c[u]) - kRoiMargin, unpack_y(c[u]) - kRoiMargin) : -1;
+            if (aggregate) {
+                const uint32_t grp = __match_any_sync(0xffffffffu, key);
+                if (key >= 0 && (__ffs(grp) - 1) == (tid & 31)) atomicAdd(&cnt[key], __popc(grp));
+            } else if (key >= 0) atomicAdd(&cnt[key], 1);
+        }
     }
     __syncthreads();
     if (in_smem) { for (int i = tid; i < 4 * nparents; i += T) qc[i] = s_q[i]; __syncthreads(); }
@@ -273,11 +282,16 @@ restart:
     }
     for (int i = tid; i < nIni; i += T) s_q[i] = 0;
     __syncthreads();
-    for (int p = tid; p < n; p += T) {
-        const int r = (int)((float)(unpack_x(cand[p]) - kRoiMargin) / hX);
-        const bool in = r >= 0 && r < nIni;
-        D.node_of[0][p] = in ? r : -1;
-        if (in) atomicAdd(&s_q[r], 1);
+    for (int pb = 0; pb < n; pb += T) {
+        const int p = pb + tid;
+        int r = -1;
+        if (p < n) {
+            r = (int)((float)(unpack_x(cand[p]) - kRoiMargin) / hX);
+            if (!(r >= 0 && r < nIni)) r = -1;
+            D.node_of[0][p] = r;
+        }
+        const uint32_t grp = __match_any_sync(0xffffffffu, r);          // one to three roots: one atomic per warp and root
+        if (r >= 0 && (__ffs(grp) - 1) == (tid & 31)) atomicAdd(&s_q[r], __popc(grp));
     }
     __syncthreads();
     for (int r = tid; r < nIni; r += T) { D.nodes[r].count = s_q[r]; D.nodes[r].leaf = s_q[r] == 1; }
@@ -377,7 +391,8 @@ restart:
     // are in candidate-index order, so "first maximum" is the largest (response, lowest index) -- one atomicMax per candidate
     {
         const int* ord = D.order[ocur];
-        unsigned long long* best = D.expand[0];                 // free by now; indexed by node id
+        unsigned long long* best = A.scratch[frame * A.nlevels + level].expand[0];     // free by now; indexed by node id.  Always the GLOBAL array: a 64-bit
+                                                                                       // atomicMax is one fire-and-forget RED in L2, but a CAS loop in shared memory
         const int m = min(live, D.ncap);
         const int nc = s_nc;
         for (int i = tid; i < nc; i += T) best[i] = 0ull;

@@ -427,12 +427,23 @@ k_compact(const uint32_t* __restrict__ slots, long long slots_per_frame,
     uint32_t* oh = cand_host + (long long)frame * slots_per_frame + g.slot_begin;
     // flat copy: thread <-> output position; its cell is the last one whose offset is <= the position (empty cells share an offset with the next
     // non-empty one, which is the last of the run).  Every load is independent: one trip to L2 per thread instead of one per cell and warp.
-    for (int j = tid; j < running; j += T) {
-        int lo = 0, hi = ncell;                      // s_off[lo] <= j < s_off[hi]
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= j) lo = mid; else hi = mid; }
-        const uint32_t v = in[s_slot[lo] + (j - s_off[lo])];
-        od[j] = v;
-        if (cand_host) oh[j] = v;
+    for (int jb = 0; jb < running; jb += 4 * T) {       // four positions per thread and step: their loads are in flight together
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = jb + u * T + tid;
+            v[u] = 0u;
+            if (j < running) {
+                int lo = 0, hi = ncell;                  // s_off[lo] <= j < s_off[hi]
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= j) lo = mid; else hi = mid; }
+                v[u] = in[s_slot[lo] + (j - s_off[lo])];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = jb + u * T + tid;
+            if (j < running) { od[j] = v[u]; if (cand_host) oh[j] = v[u]; }
+        }
     }
 }
 

@@ -334,6 +334,12 @@ template <class T> inline T __reduce_add_sync(uint32_t mask, T v)
     for (int o = 16; o; o >>= 1) r += emu::shfl(mask, r, emu::lane_id() ^ o);
     return r;
 }
+template <class T> inline uint32_t __match_any_sync(uint32_t mask, T v)
+{
+    uint32_t r = 0;
+    for (int j = 0; j < 32; ++j) { const T o = emu::shfl(mask, v, j); if (((mask >> j) & 1u) && o == v) r |= 1u << j; }
+    return r & emu::my_warp().alive;
+}
 inline int __any_sync(uint32_t mask, int pred) { return __ballot_sync(mask, pred != 0) != 0; }
 inline int __all_sync(uint32_t mask, int pred) { emu::Warp& w = emu::my_warp(); const uint32_t b = __ballot_sync(mask, pred != 0); return b == (mask & w.alive); }
 template <class T> inline T __reduce_or_sync(uint32_t mask, T v)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, call 13: warp-aggregated walk queue; stream-order A/B (TSDF first); reference arm; smoke
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_match.py tests/test_gpu_bench_config.py tests/test_match_golden.py -m gpu -q -p no:cacheprovider > gpurun_out/r2c13_pytest.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/r2c13_pytest.log
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/r2c13_pytest.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/r2c13_pytest.log
 timeout 300 python tools/resolve_phases.py 3 > gpurun_out/r2c13_resolve_phases.log 2>&1; tail -7 gpurun_out/r2c13_resolve_phases.log
 run() { tag=$1; shift; env "$@" timeout 500 python bench.py --no-cpu-baseline --repeats 5 --no-latency > gpurun_out/r2c13_${tag}.json 2> gpurun_out/r2c13_${tag}.err; echo "bench $tag exit $?"; }
 run default
