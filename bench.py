@@ -226,14 +226,19 @@ class ClockSampler:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, period_ms=50, enabled=True):
+        """index: one GPU index or a list of them (one process samples them all: under torchrun rank 0 watches every GPU of the job, the other
+        ranks start nothing -- eight 20 Hz nvidia-smi loops on one host were part of what bent round 1's scaling curve)"""
+        self.index, self.proc, self.lines, self.period_ms, self.enabled = index, None, [], period_ms, enabled
 
     def start(self):
         """one nvidia-smi process for the whole bench, started BEFORE any timed region: its start-up (NVML initialisation,
         a few hundred ms during which driver calls of this process can stall) must not fall into a timed window"""
+        if not self.enabled:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
+            idx = ",".join(str(i) for i in self.index) if isinstance(self.index, (list, tuple)) else str(self.index)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms), "-i", idx],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
             t0 = time.perf_counter()
@@ -372,7 +377,8 @@ def run_b200_arm(a):
     hp = HotPath(data, a.nfeatures, a.voxel, a.far, max_blocks=a.max_blocks, device=local, batch=B)
     hp.prepare()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    sampler = ClockSampler(local); sampler.start()
+    # N = 1: this GPU at 20 Hz; N > 1: rank 0 samples all GPUs of the job at 10 Hz (LOCAL_RANK i drives GPU i), the other ranks none
+    sampler = ClockSampler(local if world == 1 else list(range(world)), 50 if world == 1 else 100, enabled=(rank == 0)); sampler.start()
 
     def barrier():
         if world > 1:
