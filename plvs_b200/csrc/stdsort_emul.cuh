@@ -165,18 +165,74 @@ PLVS_SORT_HD void leaf_insertion(elem_t* base, int a, int b)
     }
 }
 
+// __unguarded_partition as a statement about ranks: the scans never revisit an element that was swapped (it is behind the pointers), so the i-th
+// swap exchanges the i-th position from the left whose ORIGINAL key is not less than the pivot's with the i-th position from the right whose
+// original key is not greater, for as long as the left one lies below the right one; the cut is where the last left scan stops: the next such left
+// position or the right partner of the last swap, whichever comes first.  The two
+// position lists come from two independent scans and the swaps touch disjoint positions: a warp does them with ballots (warp_partition below).
+// This serial form is what the host test checks against std::sort.  lpos / rpos: scratch, indexed first .. last-1.
+PLVS_SORT_HD int partition_by_ranks(elem_t* base, int first /*pivot*/, int last, int* lpos, int* rpos)
+{
+    const elem_t pv = base[first];
+    int nl = 0, nr = 0;
+    for (int p = first + 1; p < last; ++p) if (!less_key(base[p], pv)) lpos[first + nl++] = p;
+    for (int p = last - 1; p >= first; --p) if (!less_key(pv, base[p])) rpos[first + nr++] = p;
+    int ns = 0;
+    while (ns < nl && ns < nr && lpos[first + ns] < rpos[first + ns]) { swap_e(&base[lpos[first + ns]], &base[rpos[first + ns]]); ++ns; }
+    // the last left scan stops at the next original stopper OR at the right partner of the last swap (which now holds a key >= the pivot's), whichever comes first
+    const int next_l = ns < nl ? lpos[first + ns] : last;
+    return ns > 0 && rpos[first + ns - 1] < next_l ? rpos[first + ns - 1] : next_l;
+}
+
 PLVS_SORT_HD int depth_limit(int n) { int lg = 0; for (int t = n; t > 1; t >>= 1) ++lg; return 2 * lg; }
 
 #if defined(__CUDACC__) || defined(PLVS_CUDA_EMU)
 // std::sort on base[0..n) by a whole CTA (every thread calls it).  scratch: 2 * n ints for the leaves, 6 * (n / 16 + 2) ints for the two range
 // lists, 4 counters -- see sort_cta_scratch_ints().
-__host__ __device__ inline int sort_cta_scratch_ints(int n) { return 2 * (n + 1) + 6 * (n / 16 + 2) + 4; }
+__host__ __device__ inline int sort_cta_scratch_ints(int n) { return 4 * (n + 1) + 6 * (n / 16 + 2) + 4; }
+
+// partition_by_ranks by one warp (all 32 lanes call it; pivot already at base[first])
+__device__ inline int warp_partition(elem_t* base, int first, int last, int lane, int* lpos, int* rpos)
+{
+    const uint32_t pk = (uint32_t)(base[first] >> 32);
+    const uint32_t below = (1u << lane) - 1u;
+    int nl = 0, nr = 0;
+    for (int p0 = first + 1; p0 < last; p0 += 32) {
+        const int p = p0 + lane;
+        const bool f = p < last && !((uint32_t)(base[p] >> 32) < pk);
+        const uint32_t m = __ballot_sync(0xffffffffu, f);
+        if (f) lpos[first + nl + __popc(m & below)] = p;
+        nl += __popc(m);
+    }
+    for (int p0 = last - 1; p0 >= first; p0 -= 32) {
+        const int p = p0 - lane;
+        const bool f = p >= first && !(pk < (uint32_t)(base[p] >> 32));
+        const uint32_t m = __ballot_sync(0xffffffffu, f);
+        if (f) rpos[first + nr + __popc(m & below)] = p;
+        nr += __popc(m);
+    }
+    __syncwarp();
+    const int nm = nl < nr ? nl : nr;
+    int ns = 0;
+    for (int i0 = 0; i0 < nm; i0 += 32) {
+        const int i = i0 + lane;
+        const bool f = i < nm && lpos[first + i] < rpos[first + i];
+        const uint32_t m = __ballot_sync(0xffffffffu, f);
+        if (f) { const int a = lpos[first + i], b = rpos[first + i]; const elem_t t = base[a]; base[a] = base[b]; base[b] = t; }
+        ns += __popc(m);
+        if (m != 0xffffffffu) break;                  // the predicate holds for a prefix (left positions ascend, right positions descend)
+    }
+    __syncwarp();
+    const int next_l = ns < nl ? lpos[first + ns] : last;
+    return ns > 0 && rpos[first + ns - 1] < next_l ? rpos[first + ns - 1] : next_l;
+}
 __device__ inline void sort_cta(elem_t* base, int n, int* scratch)
 {
     if (n <= 1) return;
     const int tid = threadIdx.x, R = n / 16 + 2;
     int* leaf_a = scratch; int* leaf_b = leaf_a + (n + 1);
-    int* rng[2] = {leaf_b + (n + 1), leaf_b + (n + 1) + 3 * R};
+    int* lpos = leaf_b + (n + 1); int* rpos = lpos + (n + 1);
+    int* rng[2] = {rpos + (n + 1), rpos + (n + 1) + 3 * R};
     int* cnt = rng[1] + 3 * R;                       // [0] ranges of the current level, [1] of the next, [2] leaves
     if (tid == 0) {
         cnt[0] = cnt[1] = cnt[2] = 0;
@@ -189,9 +245,17 @@ __device__ inline void sort_cta(elem_t* base, int n, int* scratch)
         const int ncur = cnt[0];
         if (ncur == 0) break;
         __syncthreads();                              // everyone has read cnt[0]
-        for (int r = tid; r < ncur; r += blockDim.x) {
+        for (int r = tid >> 5; r < ncur; r += (int)(blockDim.x >> 5)) {        // one warp per range of this level
+            const int lane = tid & 31;
             const int first = rng[cur][3 * r], last = rng[cur][3 * r + 1], depth = rng[cur][3 * r + 2];
-            const int cut = introsort_step(base, first, last, depth);
+            int cut = -1;
+            if (depth == 0) { if (lane == 0) heap_sort(base + first, last - first); __syncwarp(); }          // sorted: no children
+            else {
+                if (lane == 0) move_median_to_first(&base[first], &base[first + 1], &base[first + (last - first) / 2], &base[last - 1]);
+                __syncwarp();
+                cut = warp_partition(base, first, last, lane, lpos, rpos);
+            }
+            if (lane != 0) continue;
             if (cut < 0) { const int l = atomicAdd(&cnt[2], 1); leaf_a[l] = first; leaf_b[l] = last; continue; }
             const int lo[2] = {first, cut}, hi[2] = {cut, last};
 #pragma unroll

@@ -44,12 +44,18 @@ int chk_stdsort_ranges(int n, const uint32_t* keys)
     std::sort(ref.begin(), ref.end(), [](const std::pair<uint32_t, int>& a, const std::pair<uint32_t, int>& b) { return a.first < b.first; });
     struct R { int first, last, depth; };
     std::vector<R> cur, next; std::vector<std::pair<int, int>> leaves;
+    std::vector<int> lpos(n + 1), rpos(n + 1);
     if (n > 16) cur.push_back(R{0, n, depth_limit(n)}); else if (n > 1) leaves.push_back(std::make_pair(0, n));
     while (!cur.empty()) {
         next.clear();
         for (size_t r = cur.size(); r-- > 0;) {                 // any order inside a level: here back to front
             const R g = cur[r];
-            const int cut = introsort_step(em.data(), g.first, g.last, g.depth);
+            int cut;
+            if (g.depth == 0) { heap_sort(em.data() + g.first, g.last - g.first); cut = -1; }
+            else {      // the step as the device's warps do it: median to the front, then the partition as a statement about ranks
+                move_median_to_first(&em[g.first], &em[g.first + 1], &em[g.first + (g.last - g.first) / 2], &em[g.last - 1]);
+                cut = partition_by_ranks(em.data(), g.first, g.last, lpos.data(), rpos.data());
+            }
             if (cut < 0) { leaves.push_back(std::make_pair(g.first, g.last)); continue; }
             const int lo[2] = {g.first, cut}, hi[2] = {cut, g.last};
             for (int c = 0; c < 2; ++c) {
