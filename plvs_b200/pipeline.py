@@ -54,7 +54,8 @@ class StreamData:
         # rendering a frame is pure numpy (about 0.2 s at VGA, 1.7 s at 1080p): long or large streams are rendered by worker processes
         grays = None
         if workers is None:
-            workers = min(32, os.cpu_count() or 1) if n * w * h >= 64 * 640 * 480 else 0
+            ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))       # ranks of a torchrun job share the host's cores
+            workers = min(32, max(1, (os.cpu_count() or 1) // ranks)) if n * w * h >= 64 * 640 * 480 else 0
         if workers > 1:
             grays = synth.render_gray_parallel(n, w, h, stream, min(workers, n))       # None if the worker processes could not be used
         for f in range(n):
