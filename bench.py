@@ -354,6 +354,29 @@ def latency_block(hp, data, f_first, n):
     return out
 
 
+def bind_to_gpu_socket(torch, local):
+    """Host side of a rank, as a deployment would run it: the process (and with it the stage threads, the pinned staging buffers and the mapped result
+    buffers it allocates afterwards) is bound to the CPUs that are local to its GPU's PCIe root (sysfs local_cpulist).  With eight ranks on a two-socket
+    box, un-pinned ranks put half of their staging traffic on the inter-socket link.  PLVS_BENCH_NUMA=0 turns it off.  Returns a note for the JSON line."""
+    if os.environ.get("PLVS_BENCH_NUMA", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return "off"
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        txt = pathlib.Path(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read_text().strip()
+        cpus = set()
+        for part in txt.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) < 8:
+            return f"not applied ({len(cpus)} local cpus)"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to the {len(cpus)} cpus local to GPU {local} ({txt})"
+    except Exception as e:
+        return f"not applied ({type(e).__name__})"
+
+
 def run_b200_arm(a):
     import torch
     sys.setswitchinterval(1e-4)          # python driver: 4 stage threads hand the GIL over quickly when a library call returns
@@ -363,6 +386,7 @@ def run_b200_arm(a):
     from plvs_b200.pipeline import StreamData, HotPath
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_socket(torch, local)          # before the first pinned allocation: first touch puts the staging memory on the GPU's socket
     if world > 1:
         # NCCL writes its version banner (NCCL_DEBUG=VERSION/INFO) to stdout by default; stdout carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -492,12 +516,13 @@ def run_b200_arm(a):
             "config": workload_config(a, {"l2": "256 MiB device buffer rewritten at the start of every step (inside the timed region); every step reads new frames",
                                           "timing": f"torch.cuda.Event pair around K steps, barrier+synchronize both sides, max over ranks; median of {R} timed passes "
                                                     "(each: map reset, seed scan, W warm-up steps, K timed steps); library calls synchronise their own streams before returning",
-                                          "threads": "4 host threads = the reference's thread roles, each with its own library handle/CUDA stream: frame construction (ORB extraction, "
+                                          "threads": "host threads = the reference's thread roles, each with its own library handle/CUDA stream: frame construction (two threads on alternate batches with the native driver; ORB extraction, "
                                                      f"batches of {B} frames: a throughput construct -- the reference's operator() takes one frame, see `latency`), Tracking (2x "
                                                      "SearchByProjection per frame), LocalMapping (SearchForTriangulation per frame), PointCloudMapping (TSDF per frame); consecutive "
                                                      "steps overlap as a software pipeline, the timed region ends when all stages have drained; the searches' queries are prepared "
                                                      "before the timed region (caller-side work, SURVEY.md §8d), which a live tracker would do between the calls",
-                                          "driver": "plvs_pipeline_run (C++ stage threads over the C ABI)" if a.driver == "native" else "Python stage threads over the ctypes mirror"}),
+                                          "driver": "plvs_pipeline_run (C++ stage threads over the C ABI)" if a.driver == "native" else "Python stage threads over the ctypes mirror",
+                                          "host_affinity": numa}),
             "value_passes": [round(v, 1) for v in vals],
             "roofline": roof,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(emed["h2d"] / K), "d2h_bytes_per_step": int(emed["d2h"] / K),
