@@ -43,6 +43,7 @@ def parse():
         ap.add_argument("--" + k.replace("_", "-"), type=t, default=None)
     ap.add_argument("--repeats", type=int, default=5, help="timed passes per arm; the median is reported")
     ap.add_argument("--driver", default="native", choices=["native", "python"], help="stage threads in C++ (plvs_pipeline_run) or in Python")
+    ap.add_argument("--rank-streams", default="same", choices=["same", "distinct"], help="N > 1: every rank the same synthetic stream (identical work per GPU) or one stream per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=2)
@@ -62,7 +63,9 @@ def workload_config(a, extra=None):
                      f"SearchByProjection(Cur,Last) th=15 + SearchByProjection(F,map) th=3 + SearchForTriangulation + "
                      f"Chisel TSDF {a.voxel * 100:g} cm voxels (colour depth-scan, carving on, planes 0.1-{a.far:g} m), every frame integrated",
          "baseline_config": {"c2": "BASELINE.json configs[1]", "c3": "BASELINE.json configs[2] (ORB part)"}[a.config],
-         "frames_per_step": a.batch, "streams_per_gpu": 1, "parallelism": f"1 camera stream per GPU x{a.gpus}"}
+         "frames_per_step": a.batch, "streams_per_gpu": 1, "parallelism": f"1 camera stream per GPU x{a.gpus}",
+         "rank_streams": ("every rank processes the same synthetic stream: identical work per GPU (weak scaling)" if getattr(a, "rank_streams", "same") == "same"
+                          else "one synthetic stream per rank (different content, different work per GPU)")}
     if extra:
         c.update(extra)
     return c
@@ -397,7 +400,8 @@ def run_b200_arm(a):
     B, K, W, R = a.batch, a.steps, a.warmup, max(1, a.repeats)
     n_lat = 0 if a.no_latency else 16
     nframes = 1 + (W + K) * B + n_lat            # frame 0 only seeds the map / the "last frame"
-    data = StreamData(nframes, a.width, a.height, stream=rank, pinned=True)
+    # weak scaling: identical work per GPU -- every rank processes the same synthetic stream unless --rank-streams distinct gives each its own
+    data = StreamData(nframes, a.width, a.height, stream=(rank if a.rank_streams == "distinct" else 0), pinned=True)
     hp = HotPath(data, a.nfeatures, a.voxel, a.far, max_blocks=a.max_blocks, device=local, batch=B)
     hp.prepare()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -434,10 +438,14 @@ def run_b200_arm(a):
         lib.plvs_io_bytes(C.byref(h2d), C.byref(d2h), 0)
         clocks = sampler.window(mark)
         t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        per_rank = [float(t_ms.item())]
         if world > 1:
+            each = [torch.zeros_like(t_ms) for _ in range(world)]
+            dist.all_gather(each, t_ms)                         # every rank's own device time: shows imbalance between the ranks
+            per_rank = [float(x.item()) for x in each]
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         lib.plvs_set_profiling(0)
-        return dict(ms=float(t_ms.item()), wall=wall, clocks=clocks, agg=agg, h2d=h2d.value, d2h=d2h.value)
+        return dict(ms=float(t_ms.item()), wall=wall, clocks=clocks, agg=agg, h2d=h2d.value, d2h=d2h.value, per_rank_ms=per_rank)
 
     def reset_timers():
         lib.plvs_tsdf_kernel_times(hp.tsdf._h, None, None, 1)
@@ -534,7 +542,8 @@ def run_b200_arm(a):
                          "tsdf_blocks_visited_per_scan": vis_per_launch, "tsdf_blocks_updated_per_scan": upd_per_launch,
                          "match_rounds_last_call": hp.match_rounds()},
             "stage_busy_ms_per_step": {k[5:-2]: round(v / K * 1e3, 3) for k, v in agg.items() if k.startswith("busy_")},
-            "wall_s": [round(med["wall"], 4), round(emed["wall"], 4)]}
+            "wall_s": [round(med["wall"], 4), round(emed["wall"], 4)],
+            "per_rank_ms_per_step": {"value": [round(x / K, 4) for x in med["per_rank_ms"]], "e2e": [round(x / K, 4) for x in emed["per_rank_ms"]]}}
     if latency:
         line["latency"] = latency
     if not a.no_cpu_baseline and world == 1:
