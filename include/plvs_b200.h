@@ -555,6 +555,18 @@ int plvs_tsdf_integrate_world_cloud(plvs_tsdf* h, const float* xyz, const float*
  * or NULL for a map without colour) that plvs_tsdf_get_meshes returned, as the reference's ASCII PLY.  Host I/O only. */
 int plvs_mesh_save_ply(const char* path, const float* verts, const float* colors, long long n_verts);
 
+/* The volumetric map on disk ("PLY save / load"): PointCloudMap<PointT>::WritePLY (src/PointCloudMap.cc:325-437) as
+ * PointCloudMapChisel::SaveMap -> SaveTriangleMeshMap calls it (binary by default, one face per three consecutive vertices), byte for byte: vertex
+ * properties x y z | red green blue | normal_x normal_y normal_z | label | kfid.  bgra: PCL's memory order (b, g, r, a), 4 bytes per point -- the binary form
+ * stores its first three bytes under the names red, green, blue, exactly as the reference does.  Host I/O only. */
+int plvs_map_save_ply(const char* path, const float* xyz, const uint8_t* bgra, const float* normals, const uint32_t* label, const uint32_t* kfid, long long n,
+                      int is_mesh, int binary);
+/* The reading half of PointCloudMap<PointT>::LoadMap (src/PointCloudMap.cc:466-503): vertex properties by name (ASCII or binary_little_endian; other
+ * properties and the faces are skipped); rgb[3i..] = red, green, blue as named in the file.  *fields: 1 xyz, 2 rgb, 4 normals, 8 label, 16 kfid present.
+ * PLVS_ECAP with *n_out set when the file holds more than cap points.  LoadMap's next steps -- InvertColors (swap red and blue) and
+ * IntegrateWorldPointCloud -- are plvs_tsdf_integrate_world_cloud's caller's.  Host I/O only. */
+int plvs_map_load_ply(const char* path, float* xyz, uint8_t* rgb, float* normals, uint32_t* label, uint32_t* kfid, long long cap, long long* n_out, int* fields);
+
 /* read-out for tests/merge: chunk ids (x,y,z), per-voxel sdf / weight (4096 each, voxel index
  * (z*16+y)*16+x as Chunk.h:90-93) and rgba (r,g,b,colour-weight).  Any output may be NULL. */
 int plvs_tsdf_download_blocks(plvs_tsdf* h, int32_t* keys, float* sdf, float* weight, uint8_t* rgba,

@@ -274,3 +274,31 @@ def build_linematch(force=False):
     finally:
         shutil.rmtree(gen, ignore_errors=True)
     return str(LINEMATCH_OUT)
+
+
+MAPPLY_OUT = OUTDIR / "libmapply_ref.so"
+
+
+def build_mapply(force=False):
+    """PointCloudMap<PointT>::WritePLY + writeCustomData (src/PointCloudMap.cc:304-437: the volumetric map file PointCloudMapChisel::SaveMap writes and
+    LoadMap reads back), sliced out at build time into the git-ignored oracle/_ref/gen_mapply/ and compiled inside oracle/ref_mapply_harness.cpp
+    -> oracle/_ref/libmapply_ref.so."""
+    src = pathlib.Path("/root/reference/src/PointCloudMap.cc")
+    if not src.exists():
+        return str(MAPPLY_OUT) if MAPPLY_OUT.exists() else None
+    deps = [src, HERE / "ref_mapply_harness.cpp"]
+    if MAPPLY_OUT.exists() and not force and all(MAPPLY_OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return str(MAPPLY_OUT)
+    text = src.read_text()
+    gen = OUTDIR / "gen_mapply"
+    gen.mkdir(parents=True, exist_ok=True)
+    parts = [_slice_function(text, "template <class PointT, typename std::enable_if<!pcl::traits::has_field<PointT, pcl::fields::kfid>::value>::type* = nullptr>"),
+             _slice_function(text, "template <class PointT, typename std::enable_if<pcl::traits::has_field<PointT, pcl::fields::kfid>::value>::type* = nullptr>"),
+             "template<typename PointT>\n" + _slice_function(text, "bool PointCloudMap<PointT>::WritePLY(")]
+    (gen / "mapply_slices.inc").write_text("// generated at build time from /root/reference/src/PointCloudMap.cc -- do not commit\n" + "\n\n".join(parts) + "\n")
+    try:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w", "-I", str(gen), "-shared", "-o", str(MAPPLY_OUT),
+                               str(HERE / "ref_mapply_harness.cpp")])
+    finally:
+        shutil.rmtree(gen, ignore_errors=True)
+    return str(MAPPLY_OUT)

@@ -172,6 +172,8 @@ def declare(lib):
     lib.plvs_tsdf_download_kfid.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.plvs_tsdf_get_mesh_kfids.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]
     lib.plvs_mesh_save_ply.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_longlong]
+    lib.plvs_map_save_ply.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int]
+    lib.plvs_map_load_ply.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
     lib.plvs_tsdf_update_meshes.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
     lib.plvs_tsdf_get_meshes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]
     lib.plvs_tsdf_download_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]

@@ -1,6 +1,11 @@
 // Library-wide helpers: error string, version, device count, pinned host memory.
 #include <cstdarg>
+#include <cstdlib>
+#include <cstring>
 #include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
 #include "common.cuh"
 
 namespace plvs {

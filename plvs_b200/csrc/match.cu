@@ -517,6 +517,7 @@ __device__ __forceinline__ bool reevaluate(int q, int m, uint32_t e_first, const
         }
     }
     bool changed = false;
+    __syncwarp();              // every lane has read this query's record (its length, when the batch was fetched) before lane 0 rewrites the word
     if (lane32 == 0) {
         reinterpret_cast<uint32_t*>(&s_watch[q])[3] = (cnt > kWatch ? 255u : (uint32_t)cnt) | (bits << 8) | ((uint32_t)m << 16);
         if (t != s_target[q]) { s_target[q] = t; changed = true; }

@@ -203,3 +203,28 @@ def save_ply(filename, verts, colors=None):
     rc = _lib.load().plvs_mesh_save_ply(str(filename).encode(), V.ctypes.data_as(C.c_void_p), Cc.ctypes.data_as(C.c_void_p) if Cc is not None else None, len(V))
     _lib.check(rc, "plvs_mesh_save_ply")
     return True
+
+
+def save_map_ply(filename, xyz, bgra, normals, label, kfid, is_mesh=True, binary=True):
+    """PointCloudMap<PointT>::WritePLY (src/PointCloudMap.cc:325-437): the map file PointCloudMapChisel::SaveMap writes.  bgra: n x 4 bytes in PCL's order."""
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3); n = len(xyz)
+    bgra = np.ascontiguousarray(bgra, np.uint8).reshape(n, 4); normals = np.ascontiguousarray(normals, np.float32).reshape(n, 3)
+    label = np.ascontiguousarray(label, np.uint32).reshape(n); kfid = np.ascontiguousarray(kfid, np.uint32).reshape(n)
+    _lib.check(_lib.load().plvs_map_save_ply(str(filename).encode(), xyz.ctypes.data, bgra.ctypes.data, normals.ctypes.data, label.ctypes.data, kfid.ctypes.data, n,
+                                             int(is_mesh), int(binary)), "plvs_map_save_ply")
+
+
+def load_map_ply(filename):
+    """the reading half of PointCloudMap<PointT>::LoadMap: -> dict(xyz, rgb (as named in the file), normals, label, kfid, fields)"""
+    lib = _lib.load()
+    n, fields = C.c_longlong(), C.c_int()
+    rc = lib.plvs_map_load_ply(str(filename).encode(), None, None, None, None, None, 0, C.byref(n), C.byref(fields))
+    if rc not in (0, -4):
+        _lib.check(rc, "plvs_map_load_ply")
+    m = max(int(n.value), 1)
+    out = dict(xyz=np.zeros((m, 3), np.float32), rgb=np.zeros((m, 3), np.uint8), normals=np.zeros((m, 3), np.float32), label=np.zeros(m, np.uint32), kfid=np.zeros(m, np.uint32))
+    _lib.check(lib.plvs_map_load_ply(str(filename).encode(), out["xyz"].ctypes.data, out["rgb"].ctypes.data, out["normals"].ctypes.data, out["label"].ctypes.data,
+                                     out["kfid"].ctypes.data, m, C.byref(n), C.byref(fields)), "plvs_map_load_ply")
+    out = {k: v[:n.value] for k, v in out.items()}
+    out["fields"] = fields.value
+    return out

@@ -955,6 +955,28 @@ public:
         plvs_shim::check(plvs_tsdf_integrate_world_cloud(h_, xyz.data(), rgb.empty() ? nullptr : rgb.data(), nrm.data(), hasKfid ? kf.data() : nullptr, 0u, (int)n, T),
                          "plvs_tsdf_integrate_world_cloud");
     }
+    // PointCloudMapChisel<PointT>::LoadMap (src/PointCloudMapChisel.cc:527-549) without PCL: PointCloudMap::LoadMap's file reading (src/PointCloudMap.cc:466-503,
+    // plvs_map_load_ply), InvertColors (:505-514: swap red and blue), then IntegrateWorldPointCloud with the identity.  A file without normals makes the
+    // reference estimate them with pcl::NormalEstimation, which is not replaced: such a file is refused (false), like a missing one.
+    bool LoadMapPLY(const std::string& filename)
+    {
+        long long n = 0; int fields = 0;
+        int rc = plvs_map_load_ply(filename.c_str(), nullptr, nullptr, nullptr, nullptr, nullptr, 0, &n, &fields);
+        if ((rc != PLVS_OK && rc != PLVS_ECAP) || !(fields & 1) || !(fields & 4)) return false;
+        std::vector<float> xyz(3 * (size_t)n + 3), nrm(3 * (size_t)n + 3), rgbf; std::vector<uint8_t> rgb(3 * (size_t)n + 3); std::vector<uint32_t> lab((size_t)n + 1), kf((size_t)n + 1);
+        if (plvs_map_load_ply(filename.c_str(), xyz.data(), rgb.data(), nrm.data(), lab.data(), kf.data(), n, &n, &fields) != PLVS_OK) return false;
+        if (useColor && (fields & 2)) {
+            rgbf.resize(3 * (size_t)n);
+            const float byteToFloat = 1.0f / 255.0f;
+            for (long long i = 0; i < n; ++i) {       // after InvertColors: r = the file's blue, b = the file's red
+                rgbf[3 * i] = rgb[3 * i + 2] * byteToFloat; rgbf[3 * i + 1] = rgb[3 * i + 1] * byteToFloat; rgbf[3 * i + 2] = rgb[3 * i] * byteToFloat;
+            }
+        }
+        const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        plvs_shim::check(plvs_tsdf_integrate_world_cloud(h_, xyz.data(), rgbf.empty() ? nullptr : rgbf.data(), nrm.data(), (fields & 16) ? kf.data() : nullptr, 0u, (int)n, I),
+                         "plvs_tsdf_integrate_world_cloud");
+        return true;
+    }
     plvs_tsdf* handle() { return h_; }
 
 protected:

@@ -132,5 +132,6 @@ extern "C" int shim_instantiate(int run)
     struct PointN { float x, y, z, normal_x, normal_y, normal_z; unsigned char b, g, r, a; unsigned kfid; };
     struct CloudN { std::vector<PointN> points; } cn; cn.points.push_back({0.1f, 0.2f, 1.f, 0.f, 0.f, -1.f, 1, 2, 3, 255, 7u});
     cs.IntegrateWorldPointCloud(cn, T);
+    c += cs.LoadMapPLY("volumetric_map_out_0.ply") ? 1 : 0;
     return mono + a + b + c;
 }

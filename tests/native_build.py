@@ -1,6 +1,16 @@
-import pathlib, subprocess
+import fcntl, os, pathlib, subprocess
 
 HERE = pathlib.Path(__file__).resolve().parent
+
+
+def _build_once(out, deps, cmd):
+    """run `cmd` (which must write out + '.tmp') unless `out` is newer than `deps`; pytest-xdist workers serialise on a lock file and the result appears atomically"""
+    with open(str(out) + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not out.exists() or any(out.stat().st_mtime < d.stat().st_mtime for d in deps):
+            subprocess.check_call(cmd)
+            os.replace(str(out) + ".tmp", str(out))
+    return str(out)
 
 
 def build_host_checks():
@@ -8,9 +18,7 @@ def build_host_checks():
     out = HERE / "native" / "libhost_checks.so"
     deps = [src, HERE.parent / "plvs_b200" / "csrc" / "orb_distribute.hpp", HERE.parent / "plvs_b200" / "csrc" / "libm_sincosf.cuh",
             HERE.parent / "plvs_b200" / "csrc" / "stdsort_emul.cuh"]
-    if not out.exists() or any(out.stat().st_mtime < d.stat().st_mtime for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", str(src), "-o", str(out), "-lm"])
-    return str(out)
+    return _build_once(out, deps, ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", str(src), "-o", str(out) + ".tmp", "-lm"])
 
 
 def build_emulated_kernels():
@@ -20,9 +28,7 @@ def build_emulated_kernels():
     csrc = HERE.parent / "plvs_b200" / "csrc"
     deps = [src, HERE / "native" / "cuda_emu.hpp", HERE.parent / "include" / "plvs_b200.h"] + \
         [csrc / n for n in ("match_common.cuh", "match_frustum.cuh", "match_init.cuh", "orb_undistort.cuh", "tsdf_hash.cuh", "mesh_kernels.cuh", "mc_tables.inc", "bow_kernels.cuh")]
-    if not out.exists() or any(out.stat().st_mtime < d.stat().st_mtime for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", str(src), "-o", str(out), "-lm"])
-    return str(out)
+    return _build_once(out, deps, ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", str(src), "-o", str(out) + ".tmp", "-lm"])
 
 
 CLUSTER_KERNELS = {"k_resolve": 8}          # __cluster_dims__ of the kernels that need their CTAs resident together

@@ -353,14 +353,14 @@ def test_gpu_tests_replayed_on_the_cpu_model(product_bound_to_emulated_units, mo
 
 @pytest.mark.parametrize("name", ["_impl_tsdf_from_raw_u16_depth", "_impl_mesh_read_out", "_impl_search_for_initialization", "_impl_search_local_points_resident",
                                   "_impl_bow_transform", "_impl_undistort_keypoints_on_device", "_impl_reference_goldens", "_impl_keyframe_ids", "_impl_deform",
-                                  "_impl_world_cloud", "_impl_line_knn2"])
+                                  "_impl_world_cloud", "_impl_line_knn2", "_impl_map_file_round_trip"])
 def test_unverified_gpu_tests_replayed_on_the_cpu_model(product_bound_to_emulated_units, tmp_path, name):
     """the bodies of tests/test_gpu_widened.py (the rows that have not met a GPU), unchanged, against the emulated translation units: entry points,
     host sequencing and kernels of the 16-bit depth path, the mesh read-out, SearchForInitialization, the resident SearchLocalPoints, the BoW
     transform and UndistortKeyPoints (on keypoints left "on the device" by the emulated extractor) all give the oracle's results"""
     import tests.test_gpu_widened as Z
     fn = getattr(Z, name)
-    fn(tmp_path) if name in ("_impl_bow_transform", "_impl_reference_goldens") else fn()
+    fn(tmp_path) if name in ("_impl_bow_transform", "_impl_reference_goldens", "_impl_map_file_round_trip") else fn()
 
 
 def test_smoke_replayed_on_the_cpu_model(product_bound_to_emulated_units):

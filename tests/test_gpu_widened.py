@@ -456,3 +456,42 @@ def _impl_line_knn2():
 
 def test_line_knn2(gpu):
     _impl_line_knn2()
+
+
+def _impl_map_file_round_trip(tmp_path):
+    """§8f rank 3, "PLY save / load": a map point cloud written like PointCloudMapChisel::SaveMap writes it (plvs_map_save_ply == the reference's WritePLY byte for
+    byte, tests/test_map_ply.py), read back like PointCloudMap::LoadMap reads it, InvertColors, IntegrateWorldPointCloud with the identity == the oracle fed the
+    original points"""
+    from plvs_b200 import scenario, tsdf as T
+    from oracle import tsdf as OT
+    w, h = 160, 120
+    K = synth.intrinsics(w, h)
+    rng = np.random.default_rng(4)
+    d = synth.depth_frame(2, w, h)
+    xyz, rgb = scenario.cloud_from_depth(d, synth.bgr_frame(2, w, h), K, step=2)            # rgb: floats in [0, 1], r g b
+    Pw = (xyz @ synth.pose(2)[:, :3].T + synth.pose(2)[:, 3]).astype(np.float32)
+    nrm = (rng.normal(size=Pw.shape).astype(np.float32) * np.float32(0.2) + np.array([0, 0, -1], np.float32)).astype(np.float32)
+    kf = rng.integers(1, 9, len(Pw)).astype(np.uint32)
+    rgb8 = np.clip(np.round(rgb * 255.0), 0, 255).astype(np.uint8)
+    bgra = np.concatenate([rgb8[:, ::-1], np.full((len(Pw), 1), 255, np.uint8)], 1)          # PCL's memory order
+    n3 = len(Pw) // 3 * 3
+    f = tmp_path / "volumetric_map_out_0.ply"
+    T.save_map_ply(f, Pw[:n3], bgra[:n3], nrm[:n3], np.zeros(n3, np.uint32), kf[:n3], is_mesh=True, binary=True)
+    m = T.load_map_ply(f)
+    assert m["fields"] == 31 and len(m["xyz"]) == n3
+    # the binary file stores (b, g, r) under the names red, green, blue; InvertColors swaps red and blue back: r g b again
+    rgb_loaded = m["rgb"][:, ::-1].astype(np.float32) * np.float32(1.0 / 255.0)
+    assert np.array_equal(m["rgb"][:, ::-1], rgb8[:n3])
+    p = T.default_params(voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=8192, use_color=1)
+    g = T.ChiselServer(p); o = OT.Map(p, threads=8)
+    I = np.eye(4, dtype=np.float32)[:3]
+    g.IntegrateWorldPointCloud(m["xyz"], rgb_loaded, m["normals"], I, kfids=m["kfid"])
+    o.integrate_world_cloud(Pw[:n3], rgb8[:n3].astype(np.float32) * np.float32(1.0 / 255.0), nrm[:n3], I, kfids=kf[:n3])
+    gk, gs, gw, gc = g.download(); ok, os_, ow, oc = o.download()
+    assert np.array_equal(gk, ok) and len(gk) > 30
+    assert np.array_equal(gw.view(np.uint32), ow.view(np.uint32)) and np.array_equal(gs.view(np.uint32), os_.view(np.uint32)) and np.array_equal(gc, oc)
+    assert np.array_equal(g.download_kfid(), o.download_kfid())
+
+
+def test_map_file_round_trip(gpu, tmp_path):
+    _impl_map_file_round_trip(tmp_path)
