@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Randomised comparison of the CPU oracle with the compiled reference (oracle/_ref/*.so) -- a development tool, not part of the test
-suite (needs /root/reference or a prebuilt oracle/_ref).  python tools/fuzz_oracle_vs_reference.py [match|tsdf|orb] [seconds]
-Round 1, 150 s each on 8 cores: match 5534 iterations x 5 searches, tsdf 246 maps (~800 integrations), orb 1159 images: 0 mismatches."""
+suite (needs /root/reference or a prebuilt oracle/_ref).  python tools/fuzz_oracle_vs_reference.py [match|tsdf|orb|linematch] [seconds]
+Round 1, 150 s each on 8 cores: match 5534 iterations x 5 searches, tsdf 246 maps (~800 integrations), orb 1159 images: 0 mismatches.
+Round 2: linematch 960 query / train sets (39 399 rows whose two neighbours are equidistant) in 9 s: 0 mismatches."""
 import sys
 which = sys.argv[1] if len(sys.argv) > 1 else "match"
 SECONDS = float(sys.argv[2]) if len(sys.argv) > 2 else 150.0
@@ -123,3 +124,17 @@ if which == "orb":
         if not ok: bad+=1; print("MISMATCH",w,h,nf,f,mode,lap)
         it+=1
     print("images",it,"mismatches",bad)
+
+if which == "linematch":
+    import time, numpy as np
+    from oracle import linematch as L
+    from tests.linematch_cases import cases
+    R = L.RefLineMatcher()
+    t0 = time.time(); bad = 0; n = 0; ties = 0; seed = 1000
+    while time.time() - t0 < SECONDS:
+        for q, t, mask in cases(24, seed=seed, nq_max=200, nt_max=300):
+            a = L.knn2(q, t, mask, 0.78); b = R.knn2(q, t, mask, 0.78)
+            bad += not (all(np.array_equal(x, y) for x, y in zip(a[:4], b[:4])) and a[4] == b[4]); n += 1
+            ties += int(np.sum(a[2][:, 0] == a[2][:, 1]))
+        seed += 1
+    print(f"linematch: {n} query / train sets, {ties} rows with equidistant neighbours, {bad} mismatches")
