@@ -385,7 +385,7 @@ def run_b200_arm(a):
     sys.setswitchinterval(1e-4)          # python driver: 4 stage threads hand the GIL over quickly when a library call returns
     import torch.distributed as dist
     import ctypes as C
-    from plvs_b200 import _lib
+    from plvs_b200 import _lib, parallel
     from plvs_b200.pipeline import StreamData, HotPath
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -401,7 +401,7 @@ def run_b200_arm(a):
     n_lat = 0 if a.no_latency else 16
     nframes = 1 + (W + K) * B + n_lat            # frame 0 only seeds the map / the "last frame"
     # weak scaling: identical work per GPU -- every rank processes the same synthetic stream unless --rank-streams distinct gives each its own
-    data = StreamData(nframes, a.width, a.height, stream=(rank if a.rank_streams == "distinct" else 0), pinned=True)
+    data = StreamData(nframes, a.width, a.height, stream=parallel.stream_of_rank(rank, a.rank_streams), pinned=True)
     hp = HotPath(data, a.nfeatures, a.voxel, a.far, max_blocks=a.max_blocks, device=local, batch=B)
     hp.prepare()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -437,15 +437,10 @@ def run_b200_arm(a):
         h2d, d2h = C.c_longlong(), C.c_longlong()
         lib.plvs_io_bytes(C.byref(h2d), C.byref(d2h), 0)
         clocks = sampler.window(mark)
-        t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        per_rank = [float(t_ms.item())]
-        if world > 1:
-            each = [torch.zeros_like(t_ms) for _ in range(world)]
-            dist.all_gather(each, t_ms)                         # every rank's own device time: shows imbalance between the ranks
-            per_rank = [float(x.item()) for x in each]
-            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        # job time = MAX over ranks of each rank's own device time; the line also lists every rank's own time (imbalance between the ranks)
+        job_ms, per_rank = parallel.job_time(torch.tensor([e0.elapsed_time(e1)], device=dev))
         lib.plvs_set_profiling(0)
-        return dict(ms=float(t_ms.item()), wall=wall, clocks=clocks, agg=agg, h2d=h2d.value, d2h=d2h.value, per_rank_ms=per_rank)
+        return dict(ms=job_ms, wall=wall, clocks=clocks, agg=agg, h2d=h2d.value, d2h=d2h.value, per_rank_ms=per_rank)
 
     def reset_timers():
         lib.plvs_tsdf_kernel_times(hp.tsdf._h, None, None, 1)

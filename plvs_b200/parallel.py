@@ -87,3 +87,21 @@ def merge_maps(server, group=None, device=None, report=None):
                                              C.c_void_p(planes[2].data_ptr()), len(rk))
         assert rc == 0, lib.plvs_last_error()
     return n, len(rk)
+
+
+def job_time(t_ms, group=None):
+    """The multi-rank timing rule of bench.py: t_ms = this rank's own device time of the timed region (a one-element tensor on the rank's device: CUDA
+    under NCCL, CPU under gloo).  Returns (job time = MAX over ranks, [every rank's own time]) -- the same on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return float(t_ms.item()), [float(t_ms.item())]
+    each = [torch.zeros_like(t_ms) for _ in range(world)]
+    dist.all_gather(each, t_ms, group=group)
+    mx = t_ms.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    return float(mx.item()), [float(x.item()) for x in each]
+
+
+def stream_of_rank(rank, rank_streams="same"):
+    """which synthetic stream a rank processes: weak scaling gives every GPU identical work (stream 0); `distinct` gives rank r stream r"""
+    return rank if rank_streams == "distinct" else 0

@@ -130,3 +130,30 @@ def test_merge_maps_world2_with_the_library_on_the_cpu_model():
         assert ret[r]["shared"] > 10
         total += ret[r]["n"]
     assert sum(ret[r]["sent"] for r in range(world)) == sum(ret[r]["received"] for r in range(world)) >= total
+
+
+def _time_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from plvs_b200 import parallel
+    mine = 10.0 + 2.5 * rank                                  # rank 1 is the slow one
+    job, per_rank = parallel.job_time(torch.tensor([mine], dtype=torch.float32))
+    ret[rank] = dict(job=job, per_rank=per_rank, stream_same=parallel.stream_of_rank(rank), stream_distinct=parallel.stream_of_rank(rank, "distinct"))
+    dist.destroy_process_group()
+
+
+def test_bench_timing_rule_world2():
+    """bench.py's N > 1 rule on two gloo ranks: the job's time is the MAX over the ranks' own times, every rank reports the same list; by default every
+    rank processes the same synthetic stream (identical work per GPU), `distinct` gives rank r stream r"""
+    world, port = 2, _free_port()
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    mp.spawn(_time_worker, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r]["job"] == 12.5 and ret[r]["per_rank"] == [10.0, 12.5], ret[r]
+        assert ret[r]["stream_same"] == 0 and ret[r]["stream_distinct"] == r
+
+
+def test_bench_timing_rule_single_process():
+    from plvs_b200 import parallel
+    assert parallel.job_time(torch.tensor([3.25])) == (3.25, [3.25])
