@@ -43,6 +43,8 @@ def parse():
         ap.add_argument("--" + k.replace("_", "-"), type=t, default=None)
     ap.add_argument("--repeats", type=int, default=5, help="timed passes per arm; the median is reported")
     ap.add_argument("--driver", default="native", choices=["native", "python"], help="stage threads in C++ (plvs_pipeline_run) or in Python")
+    ap.add_argument("--dataset", default=None, help="directory of a TUM RGB-D sequence (rgb.txt, depth.txt, groundtruth.txt or an associations file): BASELINE.json configs[0] on real data; "
+                                                    "without it the stream is synthetic")
     ap.add_argument("--rank-streams", default="same", choices=["same", "distinct"], help="N > 1: every rank the same synthetic stream (identical work per GPU) or one stream per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
@@ -59,7 +61,7 @@ def metric_name(a):
 
 
 def workload_config(a, extra=None):
-    c = {"workload": f"synthetic {a.width}x{a.height} RGB-D stream, ORB nFeatures={a.nfeatures} (8 levels, 1.2, FAST 20/7) + "
+    c = {"workload": f"{'TUM RGB-D sequence (--dataset)' if getattr(a, 'dataset', None) else 'synthetic'} {a.width}x{a.height} RGB-D stream, ORB nFeatures={a.nfeatures} (8 levels, 1.2, FAST 20/7) + "
                      f"SearchByProjection(Cur,Last) th=15 + SearchByProjection(F,map) th=3 + SearchForTriangulation + "
                      f"Chisel TSDF {a.voxel * 100:g} cm voxels (colour depth-scan, carving on, planes 0.1-{a.far:g} m), every frame integrated",
          "baseline_config": {"c2": "BASELINE.json configs[1]", "c3": "BASELINE.json configs[2] (ORB part)"}[a.config],
@@ -98,6 +100,11 @@ class CpuPath:
         from plvs_b200 import synth
         self.a, self.O, self.OM, self.OT, self.synth = a, O, OM, OT, synth
         self.K = synth.intrinsics(a.width, a.height)
+        self.seq = None
+        if getattr(a, "dataset", None):          # the same frames the b200 arm reads (loaded on first use, enough of them for both arms' longest run)
+            from plvs_b200.pipeline import StreamData
+            self.seq = StreamData.from_tum(a.dataset, 1 + (min(a.warmup, 1) + a.steps) * a.batch, pinned=False)
+            self.K = self.seq.K
         self.tab = O.Tables(a.nfeatures)
         self.have_ref = O.ref_available() and OM.ref_available() and OT.ref_available()
         self.ex = O.RefExtractor(a.nfeatures) if self.have_ref else None
@@ -115,7 +122,12 @@ class CpuPath:
         from plvs_b200 import scenario
         from plvs_b200.matcher import featvec
         a, O, OM, synth = self.a, self.O, self.OM, self.synth
-        img = synth.gray_frame(f, a.width, a.height); depth = synth.depth_frame(f, a.width, a.height); bgr = synth.bgr_frame(f, a.width, a.height)
+        if self.seq is not None:
+            img, depth, bgr = self.seq.gray[f], self.seq.depth[f], self.seq.bgr[f]
+            pose = lambda i: self.seq.poses[i]
+        else:
+            img = synth.gray_frame(f, a.width, a.height); depth = synth.depth_frame(f, a.width, a.height); bgr = synth.bgr_frame(f, a.width, a.height)
+            pose = synth.pose
         t0 = time.perf_counter()
         if self.ex is not None:
             kp, desc, mono = self.ex(img)
@@ -126,10 +138,10 @@ class CpuPath:
         t_match = 0.0
         if self.prev is not None:
             prev = self.prev
-            ql, _ = scenario.last_queries(prev, cur, self.K, synth.pose(f - 1), synth.pose(f))
-            qm, _ = scenario.map_queries(prev, cur, self.K, synth.pose(f - 1), synth.pose(f), seed=f)
+            ql, _ = scenario.last_queries(prev, cur, self.K, pose(f - 1), pose(f))
+            qm, _ = scenario.map_queries(prev, cur, self.K, pose(f - 1), pose(f), seed=f)
             fv1, fv2 = featvec(scenario.node_ids(cur.desc)), featvec(scenario.node_ids(prev.desc))
-            F12, ep = scenario.fundamental(self.K, synth.pose(f), synth.pose(f - 1))
+            F12, ep = scenario.fundamental(self.K, pose(f), pose(f - 1))
             z0, z1 = np.zeros(cur.n, np.uint8), np.zeros(prev.n, np.uint8)
             if self.have_ref:
                 qc, z = OM.canonical_last_queries(ql)
@@ -147,12 +159,12 @@ class CpuPath:
         t3 = time.perf_counter()
         t_ref = t_port = None
         if tsdf in ("port", "both"):
-            self.port_map.integrate(depth, synth.pose(f), bgr)
+            self.port_map.integrate(depth, pose(f), bgr)
             t_port = time.perf_counter() - t3
         if tsdf in ("ref", "both") and self.ref_map is not None:
             t4 = time.perf_counter()
             with _quiet_stdout():
-                self.ref_map.integrate(depth, synth.pose(f), bgr)
+                self.ref_map.integrate(depth, pose(f), bgr)
             t_ref = time.perf_counter() - t4
         if timed:
             self.t["extract_s"] += t1 - t0; self.t["match_s"] += t_match; self.n["frames"] += 1
@@ -212,7 +224,7 @@ def run_reference_arm(a):
     all_ref_step = B * (front_end + pf.get("tsdf_ref_s", pf.get("tsdf_port_s", 0.0)))
     line = {"impl": "reference", "metric": metric_name(a), "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1000.0 * mean_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32+f32",
-            "data": "synthetic", "config": workload_config(a, {"note": note}),
+            "data": (f"TUM RGB-D sequence {cp.seq.stream}" if cp.seq is not None else "synthetic"), "config": workload_config(a, {"note": note}),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                              "sample": f"{a.steps} steps x {B} frames of the same stream; seconds/frame {json.dumps({k: round(v, 4) for k, v in pf.items()})}; "
                                        f"reference TSDF on 1 of {B} frames per step, restated TSDF ({threads} threads) on the rest",
@@ -401,7 +413,12 @@ def run_b200_arm(a):
     n_lat = 0 if a.no_latency else 16
     nframes = 1 + (W + K) * B + n_lat            # frame 0 only seeds the map / the "last frame"
     # weak scaling: identical work per GPU -- every rank processes the same synthetic stream unless --rank-streams distinct gives each its own
-    data = StreamData(nframes, a.width, a.height, stream=parallel.stream_of_rank(rank, a.rank_streams), pinned=True)
+    if a.dataset:
+        data = StreamData.from_tum(a.dataset, nframes, pinned=True)
+        if (data.w, data.h) != (a.width, a.height):
+            raise SystemExit(f"--dataset: the sequence is {data.w}x{data.h}, the configuration {a.width}x{a.height}; pass --width / --height")
+    else:
+        data = StreamData(nframes, a.width, a.height, stream=parallel.stream_of_rank(rank, a.rank_streams), pinned=True)
     hp = HotPath(data, a.nfeatures, a.voxel, a.far, max_blocks=a.max_blocks, device=local, batch=B)
     hp.prepare()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -515,7 +532,8 @@ def run_b200_arm(a):
         return
     agg = med["agg"]
     line = {"metric": metric_name(a), "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32+f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32+f32",
+            "data": (f"TUM RGB-D sequence {data.stream}: first {nframes} associated frames, ground-truth poses" if a.dataset else "synthetic"),
             "config": workload_config(a, {"l2": "256 MiB device buffer rewritten at the start of every step (inside the timed region); every step reads new frames",
                                           "timing": f"torch.cuda.Event pair around K steps, barrier+synchronize both sides, max over ranks; median of {R} timed passes "
                                                     "(each: map reset, seed scan, W warm-up steps, K timed steps); library calls synchronise their own streams before returning",

@@ -67,6 +67,73 @@ class StreamData:
     def input_bytes_per_frame(self):
         return self.w * self.h * (1 + 4 + 3)
 
+    @classmethod
+    def from_tum(cls, root, n, pinned=True, rgb_flag=True, depth_factor=5000.0, K=None, max_dt=0.02):
+        """The first `n` frames of a TUM RGB-D benchmark sequence directory -- BASELINE.json configs[0], what Examples_old/RGB-D/rgbd_tum.cc reads
+        (LoadImages :199-230: an associations file `t_rgb rgb/x.png t_depth depth/x.png`; without one, rgb.txt and depth.txt are paired by nearest timestamp,
+        as the benchmark's associate.py does).  Gray as Tracking::GrabImageRGBD makes it (src/Tracking.cc:1797-1810: cvtColor of the BGR data cv::imread returns
+        with COLOR_RGB2GRAY when Camera.RGB is 1, as in TUM1.yaml), depth = raw 16-bit x 1 / DepthMapFactor (:1812-1813), colour = the image as read,
+        poses = groundtruth.txt (camera-to-world, nearest timestamp) -- the TSDF stage needs a pose and there is no tracker here to supply one."""
+        import pathlib
+        import cv2
+        root = pathlib.Path(root)
+
+        def table(name):
+            rows = []
+            for ln in (root / name).read_text().splitlines():
+                ln = ln.strip()
+                if ln and not ln.startswith("#"):
+                    rows.append(ln.replace(",", " ").split())
+            return rows
+
+        pairs = []
+        for cand in ("associations.txt", "associate.txt", "association.txt"):
+            if (root / cand).exists():
+                pairs = [(float(r[0]), r[1], r[3]) for r in table(cand) if len(r) >= 4]
+                break
+        if not pairs:
+            rgb = [(float(r[0]), r[1]) for r in table("rgb.txt")]; dep = [(float(r[0]), r[1]) for r in table("depth.txt")]
+            td = np.array([t for t, _ in dep]); used = set()
+            for t, f in rgb:
+                j = int(np.argmin(np.abs(td - t)))
+                if abs(td[j] - t) <= max_dt and j not in used:
+                    used.add(j); pairs.append((t, f, dep[j][1]))
+        if len(pairs) < n:
+            raise ValueError(f"{root}: {len(pairs)} associated RGB-D pairs, {n} needed")
+        gt = np.array([[float(x) for x in r[:8]] for r in table("groundtruth.txt")]) if (root / "groundtruth.txt").exists() else None
+        first = cv2.imread(str(root / pairs[0][1]), cv2.IMREAD_COLOR)
+        if first is None:
+            raise ValueError(f"cannot read {root / pairs[0][1]}")
+        h, w = first.shape[:2]
+        self = cls.__new__(cls)
+        self.n, self.w, self.h, self.stream = n, w, h, str(root.name)
+        self.K = dict(K) if K else synth.intrinsics(w, h)              # TUM1.yaml's pinhole parameters scaled to the image size
+        self._pins = []
+
+        def alloc(shape, dtype):
+            if pinned:
+                p = PinnedArray(shape, dtype); self._pins.append(p); return p.array
+            return np.empty(shape, dtype)
+        self.gray = alloc((n, h, w), np.uint8); self.depth = alloc((n, h, w), np.float32); self.bgr = alloc((n, h, w, 3), np.uint8)
+        self.poses = np.zeros((n, 3, 4), np.float32)
+        for i, (t, frgb, fdep) in enumerate(pairs[:n]):
+            img = cv2.imread(str(root / frgb), cv2.IMREAD_COLOR); d16 = cv2.imread(str(root / fdep), cv2.IMREAD_UNCHANGED)
+            if img is None or d16 is None or img.shape[:2] != (h, w) or d16.shape[:2] != (h, w):
+                raise ValueError(f"{root}: frame {i} ({frgb}, {fdep}) unreadable or of a different size")
+            self.bgr[i] = img
+            self.gray[i] = cv2.cvtColor(img, cv2.COLOR_RGB2GRAY if rgb_flag else cv2.COLOR_BGR2GRAY)
+            self.depth[i] = d16.astype(np.float32) * np.float32(1.0 / depth_factor)
+            T = np.eye(4, dtype=np.float64)
+            if gt is not None and len(gt):
+                g = gt[int(np.argmin(np.abs(gt[:, 0] - t)))]
+                qx, qy, qz, qw = g[4:8] / np.linalg.norm(g[4:8])
+                T[:3, :3] = [[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)],
+                             [2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw)],
+                             [2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)]]
+                T[:3, 3] = g[1:4]
+            self.poses[i] = T[:3].astype(np.float32)
+        return self
+
 
 class HotPath:
     """extract + match + TSDF for one stream on one GPU."""
