@@ -441,6 +441,36 @@ def test_bench_step_dataflow_on_the_cpu_model(product_bound_to_emulated_units, m
     assert nblk > 20 and nm > 100
 
 
+def test_dataset_stream_through_the_hot_path_on_the_cpu_model(product_bound_to_emulated_units, monkeypatch, tmp_path):
+    """`bench.py --dataset DIR` (BASELINE configs[0]): a sequence in the TUM RGB-D benchmark's on-disk format goes through StreamData.from_tum, HotPath.prepare and
+    the native stream driver exactly like the synthetic stream; same totals as the step-by-step form, map equal to the oracle fed the loaded frames"""
+    pytest.importorskip("cv2")
+    from plvs_b200 import tsdf as T
+    from plvs_b200.pipeline import StreamData, HotPath
+    from oracle import tsdf as OT
+    from tests.test_tum_loader import _write_sequence
+    monkeypatch.setenv("PLVS_PIPELINE_SERIAL", "1")
+    _write_sequence(tmp_path, 5, 320, 240, True)
+    d = StreamData.from_tum(tmp_path, 5, pinned=False)
+    hp = HotPath(d, nfeatures=500, voxel=0.04, far=4.0, max_blocks=4096, batch=2)
+    hp.prepare()
+    hp.tsdf.Reset(); hp.tsdf.integrate(d.depth[0], d.poses[0], d.bgr[0])
+    got = {}
+    for s_ in range(2):
+        for k, v in hp.step(1 + 2 * s_, 2, resident=False, concurrent=False).items():
+            got[k] = got.get(k, 0) + v
+    assert got["keypoints"] > 400 and got["matches"] > 20
+    p = T.default_params(voxel_resolution=0.04, use_carving=1, near_plane=0.1, far_plane=4.0, max_blocks=4096, use_color=1)
+    o = OT.Map(p, threads=4); o.set_camera(d.K["fx"], d.K["fy"], d.K["cx"], d.K["cy"], d.w, d.h)
+    for f in range(5):
+        o.integrate(d.depth[f], d.poses[f], d.bgr[f])
+    gk, gs, gw, gc = hp.tsdf.download(); ok, os_, ow, oc = o.download()
+    assert np.array_equal(gk, ok) and len(gk) > 20 and np.allclose(gs, os_, atol=1e-4) and np.array_equal(gw.view(np.uint32), ow.view(np.uint32)) and np.array_equal(gc, oc)
+    hp.tsdf.Reset(); hp.tsdf.integrate(d.depth[0], d.poses[0], d.bgr[0])
+    agg = hp.run_stream_native(1, 2, False)
+    assert agg["keypoints"] == got["keypoints"] and agg["matches"] == got["matches"]
+
+
 def test_bench_geometry_scan_sequence_on_the_cpu_model(product_bound_to_emulated_units):
     """the body of tests/test_gpu_bench_config.py::test_c2_bench_geometry_ten_scans at 160x120 / 4 cm: consecutive colour scans with carving on one
     map, planes 0.1-5 m, compared after every scan"""
